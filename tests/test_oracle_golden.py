@@ -1,0 +1,202 @@
+"""Pins the CPU oracle (oracle/) against golden vectors produced by the reference itself.
+
+tests/golden/*.npz were written by oracle/gen_golden.py, which imports /root/reference/model/*.py and
+runs the reference's own functions / nn.Modules on seeded synthetic clouds.  Index results must be
+bit-exact (torch.equal in spirit); floating-point block / network outputs must agree to fp32 noise.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from pointnet12_b200 import synthetic as syn
+
+FP32_TOL = 2e-5      # oracle vs reference: same fp32 maths, different accumulation order (MKL/oneDNN vs C loops)
+
+
+def _xyz_feat(pts):
+    pm = pts.transpose(0, 2, 1)          # strided view, like pointnet_util.py:184
+    return pm[:, :, :3], pm[:, :, 3:]
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def test_inputs_reproducible(golden):
+    g = golden("primitives_c2")
+    assert syn.checksum(syn.kitti_batch(2, 24000, config=2)) == str(g["input_sum"])
+    assert syn.checksum(syn.kitti_batch(2, 24000, config=2)) == str(golden("pointnet2_semseg_ckpt")["n24000_input_sum"])
+
+
+def test_duplicates_present():
+    """The loader resamples with replacement, so ties are real."""
+    p = syn.kitti_cloud(24000, 2000)
+    uniq = np.unique(p.T, axis=0).shape[0]
+    assert 0.5 < uniq / 24000 < 0.75
+
+
+def test_fps_and_ball_chain_c2(golden):
+    """farthest_point_sample / query_ball_point at the four PointNet2SemSeg levels, N0 = 24000."""
+    g = golden("primitives_c2")
+    xyz, _ = _xyz_feat(syn.kitti_batch(2, 24000, config=2))
+    cur = xyz
+    for lvl, (npoint, radius) in enumerate([(1024, 0.1), (256, 0.2), (64, 0.4), (16, 0.8)], 1):
+        fps = orc.farthest_point_sample(cur, npoint, g[f"l{lvl}_start"])
+        assert np.array_equal(fps, g[f"l{lvl}_fps"].astype(np.int64)), f"FPS level {lvl}"
+        new_xyz = orc.index_points(cur, fps)
+        assert np.array_equal(new_xyz, g[f"l{lvl}_new_xyz"])
+        ball = orc.query_ball_point(radius, 32, cur, new_xyz)
+        assert np.array_equal(ball, g[f"l{lvl}_ball"].astype(np.int64)), f"ball query level {lvl}"
+        cur = new_xyz
+
+
+def test_square_distance_bit_exact(golden):
+    g = golden("primitives_c2")
+    xyz, _ = _xyz_feat(syn.kitti_batch(2, 24000, config=2))
+    a, b = np.ascontiguousarray(xyz[:, :64, :]), xyz[:, 5000:5512, :]
+    assert np.array_equal(orc.square_distance(a, b), g["sqd_ab"])
+    assert np.array_equal(orc.square_distance(b, a), g["sqd_ba"])
+
+
+def test_sample_and_group(golden):
+    g = golden("primitives_c2")
+    xyz, feat = _xyz_feat(syn.kitti_batch(2, 24000, config=2))
+    _, grouped, _, _ = orc.sample_and_group(1024, 0.1, 32, xyz, feat, g["l1_start"])
+    assert np.array_equal(grouped[0, :64], g["sg_new_points_b0"])
+
+
+@pytest.mark.parametrize("n", [4096, 16384])
+def test_fps_ball_other_sizes(golden, n):
+    import torch
+
+    g = golden("primitives_misc")
+    xyz, _ = _xyz_feat(syn.kitti_batch(1, n, config=3))
+    for npoint, radius in ((256, 0.2), (64, 0.4)):
+        torch.manual_seed(n + npoint)
+        start = torch.randint(0, n, (1,), dtype=torch.long).numpy()
+        fps = orc.farthest_point_sample(xyz, npoint, start)
+        assert np.array_equal(fps, g[f"n{n}_p{npoint}_fps"].astype(np.int64))
+        ball = orc.query_ball_point(radius, 32, xyz, orc.index_points(xyz, fps))
+        assert np.array_equal(ball, g[f"n{n}_p{npoint}_ball"].astype(np.int64))
+
+
+def test_modelnet_msg_primitives(golden):
+    import torch
+
+    g = golden("primitives_misc")
+    xyz = syn.modelnet_batch(2, 1024).transpose(0, 2, 1)
+    torch.manual_seed(7)
+    start = torch.randint(0, 1024, (2,), dtype=torch.long).numpy()
+    fps = orc.farthest_point_sample(xyz, 512, start)
+    assert np.array_equal(fps, g["mn_fps"].astype(np.int64))
+    new_xyz = orc.index_points(xyz, fps)
+    for r, k in ((0.1, 16), (0.2, 32), (0.4, 128)):
+        assert np.array_equal(orc.query_ball_point(r, k, xyz, new_xyz), g[f"mn_ball_r{r}_k{k}"].astype(np.int64))
+
+
+def _starts(ns, B, seed=0):
+    """The FPS start-index draws of one forward, in call order (pointnet_util.py:75)."""
+    import torch
+
+    torch.manual_seed(seed)
+    return [torch.randint(0, n, (B,), dtype=torch.long).numpy() for n in ns]
+
+
+def test_blocks_with_checkpoint(golden, ckpt_state):
+    g = golden("blocks_ckpt")
+    pts = syn.kitti_batch(2, 4096, config=2)
+    assert syn.checksum(pts) == str(g["input_sum"])
+    xyz, feat = _xyz_feat(pts)
+    st = _starts([4096, 1024], 2)
+    x1, f1 = orc.set_abstraction(ckpt_state, "sa1", 1024, 0.1, 32, False, xyz, feat, st[0])
+    x2, f2 = orc.set_abstraction(ckpt_state, "sa2", 256, 0.2, 32, False, x1, f1, st[1])
+    assert np.array_equal(x1.transpose(0, 2, 1), g["sa1_xyz"])
+    assert np.array_equal(x2.transpose(0, 2, 1), g["sa2_xyz"])
+    assert rel_err(f1.transpose(0, 2, 1), g["sa1_feat"]) < FP32_TOL
+    assert rel_err(f2.transpose(0, 2, 1), g["sa2_feat"]) < FP32_TOL
+    p2 = np.random.default_rng(5).normal(0, 1, (2, 256, 256)).astype(np.float32).transpose(0, 2, 1)
+    trace = {}
+    o2 = orc.feature_propagation(ckpt_state, "fp2", x1, x2, f1, p2, trace)
+    assert not trace["fp2.nn_tie"].any()
+    assert rel_err(o2.transpose(0, 2, 1), g["fp2_out"]) < FP32_TOL
+    o1 = orc.feature_propagation(ckpt_state, "fp1", xyz, x1, None, o2, trace)
+    ok = ~trace["fp1.nn_tie"]                      # rows with d3 == d4: the reference's sort order is undefined
+    assert ok.mean() > 0.999
+    got, ref = o1.transpose(0, 2, 1)[:, :, ::8], g["fp1_out_sub8"]
+    okc = ok[:, ::8][:, None, :]
+    assert float((np.abs(got - ref) * okc).max() / max(1.0, np.abs(ref).max())) < FP32_TOL
+
+
+def test_pointnet2_semseg_n4096(golden, ckpt_state):
+    g = golden("pointnet2_semseg_ckpt")
+    pts = syn.kitti_batch(2, 4096, config=2)
+    logp = orc.pointnet2_semseg(ckpt_state, pts, _starts([4096, 1024, 256, 64], 2))
+    assert logp.shape == (2, 4096, 19)
+    assert rel_err(logp, g["n4096_logp"]) < 1e-4
+    assert (logp.argmax(-1) == g["n4096_logp"].argmax(-1)).mean() > 0.9995
+
+
+def test_pointnet2_semseg_n24000(golden, ckpt_state):
+    """Config C2 shape (two clouds of the eight): log-probs on every 16th point, labels on all."""
+    g = golden("pointnet2_semseg_ckpt")
+    pts = syn.kitti_batch(2, 24000, config=2)
+    trace = {}
+    logp = orc.pointnet2_semseg(ckpt_state, pts, _starts([24000, 1024, 256, 64], 2), trace)
+    # 3-NN rows whose 3rd and 4th neighbour are equidistant are resolved by an UNSTABLE sort in the
+    # reference (pointnet_util.py:296): excluded per SURVEY 8c.  At the coarse levels a tie would touch
+    # many points, so there must be none.
+    assert not (trace["fp4.nn_tie"].any() or trace["fp3.nn_tie"].any() or trace["fp2.nn_tie"].any())
+    ok = ~trace["fp1.nn_tie"]
+    assert (~ok).sum() <= 8
+    d = np.abs(logp[:, ::16, :] - g["n24000_logp_sub"]).max(-1) * ok[:, ::16]
+    assert float(d.max() / max(1.0, np.abs(g["n24000_logp_sub"]).max())) < 1e-4
+    label = logp.argmax(-1)
+    flips = (label != g["n24000_label"]) & ok
+    # flips are only tolerated where the reference's own top-2 margin is within fp32 noise
+    assert (g["n24000_margin"].astype(np.float32)[flips] < 2e-3).all()
+    assert flips.mean() < 5e-4
+    assert len(np.unique(g["n24000_label"])) >= 4          # the check is not vacuous: several classes predicted
+
+
+def _seeded_sd(shapes_from, seed):
+    return syn.random_state_dict(shapes_from, seed)
+
+
+def _shapes(module_ctor):
+    return {k: tuple(v.shape) for k, v in module_ctor().state_dict().items()}
+
+
+def test_pointnet_seg_seeded(golden):
+    from pointnet12_b200.model.pointnet import PointNetSeg
+
+    g = golden("pointnet_seg_seed1234")
+    pts = syn.kitti_batch(2, 2048, config=1)
+    assert syn.checksum(pts) == str(g["input_sum"])
+    sd = _seeded_sd(_shapes(lambda: PointNetSeg(19, input_dims=4, feature_transform=True)), 1234)
+    logp, tf = orc.pointnet_seg(sd, pts, feature_transform=True)
+    assert rel_err(tf, g["trans_feat"]) < 1e-4
+    assert rel_err(logp, g["logp"]) < 1e-4
+
+
+def test_pointnet2_cls_msg_seeded(golden):
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsMsg
+
+    g = golden("pointnet2_cls_msg_seed1234")
+    sd = _seeded_sd(_shapes(PointNet2ClsMsg), 1234)
+    logp, l3 = orc.pointnet2_cls_msg(sd, syn.modelnet_batch(4, 1024), _starts([1024, 512], 4))
+    assert rel_err(l3, g["l3_points"]) < 1e-4
+    assert rel_err(logp, g["logp"]) < 1e-4
+
+
+def test_other_heads_seeded(golden):
+    from pointnet12_b200.model.pointnet import PointNetCls
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsSsg
+
+    g = golden("other_heads_seeded")
+    x = syn.modelnet_batch(2, 1024)
+    sd = _seeded_sd(_shapes(PointNet2ClsSsg), 77)
+    assert rel_err(orc.pointnet2_cls_ssg(sd, x, _starts([1024, 512], 2)), g["cls_ssg_logp"]) < 1e-4
+    sd = _seeded_sd(_shapes(lambda: PointNetCls(k=40, feature_transform=True)), 79)
+    logp, tf = orc.pointnet_cls(sd, x, feature_transform=True)
+    assert rel_err(tf, g["pointnet_cls_tf"]) < 1e-4
+    assert rel_err(logp, g["pointnet_cls_logp"]) < 1e-4
