@@ -1,0 +1,129 @@
+/*
+ * pn12_b200.h -- C ABI of libpn12_b200.so: hand-written sm_100a CUDA kernels for the PointNet /
+ * PointNet++ forward hot path of Jiang-Muyun/PointNet12.
+ *
+ * The reference has no FFI layer (it is pure Python/PyTorch); this header IS the native boundary the
+ * new build creates underneath the reference's Python API.  Every entry point
+ * names the reference function it replaces (file:line into the reference repo).  The Python binding a
+ * maintainer adds on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All pointers are DEVICE pointers unless noted.
+ *   - The caller owns every buffer; the library never allocates, frees or synchronises.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and capturable in a
+ *     CUDA graph.  Entry points are stateless and re-entrant.
+ *   - Point clouds are addressed point-major through ELEMENT strides (sB, sN, sC): element (b, n, c)
+ *     lives at base[b*sB + n*sN + c*sC].  This covers the permuted [B,3,N] views the reference passes
+ *     around (model/pointnet_util.py:184) as well as contiguous [B,N,3].
+ *   - Feature matrices are row-major [rows, C] with a leading dimension (ld*, in elements).
+ *   - Indices are int64 at the boundary, as in the reference.
+ *   - Return value: 0 on success; negative pn_status on bad arguments; positive = cudaError_t of
+ *     the launch.  pn_last_error_string() describes the last failure on the calling thread.
+ *     Nothing is printed and nothing throws.
+ */
+#ifndef PN12_B200_H
+#define PN12_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pn_stream_t; /* cudaStream_t */
+
+enum pn_status {
+    PN_OK = 0,
+    PN_ERR_BAD_ARG = -1,     /* null pointer, non-positive size, inconsistent shape */
+    PN_ERR_UNSUPPORTED = -2, /* size outside what the kernels were built for */
+    PN_ERR_ALIGNMENT = -3,   /* pointer / leading dimension not aligned as documented */
+    PN_ERR_DEVICE = -4       /* not an sm_100 device */
+};
+
+/* Library identification: version = major*10000 + minor*100 + patch. */
+int pn_version(void);
+const char* pn_last_error_string(void);
+/* Queries the current device; fails with PN_ERR_DEVICE unless compute capability is 10.x. */
+int pn_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* farthest_point_sample (model/pointnet_util.py:63-84).
+ * xyz [B,N,3] via strides; start_idx [B] = the torch.randint draw of :75 (made by the caller on the
+ * CPU generator, then copied to the device); out_idx [B,npoint].
+ * Distances are ((dx*dx + dy*dy) + dz*dz) in fp32 without fused multiply-add, running minimum,
+ * arg-max with the lowest index winning ties -- bit-exact with the reference.
+ * One thread-block cluster per cloud; coordinates and running distances stay in registers. */
+int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+               const int64_t* start_idx, int64_t* out_idx, pn_stream_t stream);
+
+/* Tuning hook for pn_fps_f32: force the cluster size (1,2,4,8,16) and threads per CTA (128..1024);
+ * 0 = automatic.  Process-wide; meant for benchmarks and tests. */
+int pn_fps_set_config(int cluster_size, int threads);
+
+/* square_distance (model/pointnet_util.py:19-40): out[b,i,j] = ((-2*dot) + |src_i|^2) + |dst_j|^2
+ * with dot = fma(z,z', fma(y,y', x*x')), i.e. the fp32 rounding sequence of the reference's CPU path.
+ * out is contiguous [B,N,M].  Provided for API completeness; the hot path never materialises it. */
+int pn_square_distance_f32(const float* src, int64_t aB, int64_t aN, int64_t aC, const float* dst, int64_t bB,
+                           int64_t bN, int64_t bC, int B, int N, int M, float* out, pn_stream_t stream);
+
+/* query_ball_point (model/pointnet_util.py:87-107).
+ * out_idx [B,S,nsample]: the first nsample indices j (ascending) with NOT(sqdist(new_xyz_s, xyz_j) >
+ * radius2), padded with the first hit; rows without any hit are filled with N (as the reference
+ * would).  radius2 = (float)(radius**2).  Membership uses the square_distance formula above. */
+int pn_ball_query_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const float* new_xyz, int64_t qB,
+                      int64_t qN, int64_t qC, int B, int N, int S, float radius2, int nsample,
+                      int64_t* out_idx, pn_stream_t stream);
+
+/* index_points (model/pointnet_util.py:43-60): out[b,m,:] = points[b, idx[b,m], :].
+ * points [B,N,C] via strides, idx [B,M], out contiguous [B,M,C]. */
+int pn_index_points_f32(const float* points, int64_t pB, int64_t pN, int64_t pC, int B, int N, int C,
+                        const int64_t* idx, int64_t M, float* out, pn_stream_t stream);
+
+/* Gather + recentre + concat of sample_and_group (model/pointnet_util.py:127-131, order
+ * [xyz_rel, feat]) or of PointNetSetAbstractionMsg.forward (:243-247, msg_order=1: [feat, xyz_rel]).
+ * feat may be NULL (D = 0).  out rows are (b,s,k) with 3+D channels and leading dimension ldo. */
+int pn_group_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const float* feat, int64_t fB,
+                 int64_t fN, int64_t fC, int D, const float* new_xyz, int64_t qB, int64_t qN, int64_t qC,
+                 const int64_t* idx, int B, int N, int S, int K, int msg_order, float* out, int64_t ldo,
+                 pn_stream_t stream);
+
+/* One layer of a shared MLP: 1x1 Conv2d/Conv1d/Linear with BatchNorm already folded into (w, bias),
+ * optional ReLU (model/pointnet_util.py:195-197, :253-255, :310-312; pointnet2.py:172-173;
+ * pointnet.py passim).  y[b][r][co] = act(sum_ci x[b][r][ci] * w[b][co][ci] + bias[co]).
+ * x rows have leading dimension ldx, batch stride x_bstride (elements); w is [cout,cin] row-major
+ * with batch stride w_bstride (0 = shared; non-zero for the per-cloud transforms applied with
+ * torch.bmm in pointnet.py:105-107); bias may be NULL, bias_bstride != 0 gives every batch item its
+ * own bias (the global-feature half of PointNetSeg's 1088->512 conv folded per cloud,
+ * pointnet.py:128-131, 247).  fp32 FMA accumulation. */
+int pn_linear_f32(const float* x, int64_t ldx, int64_t x_bstride, const float* w, int64_t w_bstride,
+                  const float* bias, int64_t bias_bstride, int relu, int B, int64_t rows, int cin, int cout,
+                  float* y, int64_t ldy, int64_t y_bstride, pn_stream_t stream);
+
+/* torch.max(new_points, 2)[0] (model/pointnet_util.py:199, :256) and the global max over points of
+ * pointnet.py:35,74,122: y[g,:] = max over the K consecutive rows g*K .. g*K+K-1 of x. */
+int pn_group_max_f32(const float* x, int64_t ldx, int64_t groups, int K, int C, float* y, int64_t ldy,
+                     pn_stream_t stream);
+
+/* 3-NN search + inverse-distance weights of PointNetFeaturePropagation.forward
+ * (model/pointnet_util.py:295-300): idx [B,N,3] = the three sources with the smallest
+ * sqdist(xyz1_n, xyz2_s) (ties: lowest index), weight [B,N,3] = (1/max(d,1e-10)) normalised. */
+int pn_three_nn_f32(const float* xyz1, int64_t aB, int64_t aN, int64_t aC, const float* xyz2, int64_t bB,
+                    int64_t bN, int64_t bC, int B, int N, int S, int64_t* idx, float* weight,
+                    pn_stream_t stream);
+
+/* Weighted gather of model/pointnet_util.py:301 fused with the concat of :303-307:
+ * out[b,n,0:D1] = points1[b,n,:] (skipped when points1 == NULL), out[b,n,D1:D1+D2] =
+ * sum_k points2[b, idx[b,n,k], :] * weight[b,n,k].  out rows have leading dimension ldo. */
+int pn_three_interpolate_f32(const float* points1, int64_t p1B, int64_t p1N, int64_t p1C, int D1,
+                             const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2, int S,
+                             const int64_t* idx, const float* weight, int B, int N, float* out, int64_t ldo,
+                             int64_t o_bstride, pn_stream_t stream);
+
+/* F.log_softmax over the channels of each row (pointnet2.py:174; pointnet.py:251). */
+int pn_log_softmax_f32(const float* x, int64_t ldx, int64_t rows, int C, float* y, int64_t ldy,
+                       pn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN12_B200_H */

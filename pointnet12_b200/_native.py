@@ -1,0 +1,76 @@
+"""ctypes binding of libpn12_b200.so (the C ABI declared in include/pn12_b200.h).
+
+There is no CPU fallback and no alternative backend: if the library is missing or a call fails,
+a RuntimeError is raised.  Pointers come from `tensor.data_ptr()`, the stream from
+`torch.cuda.current_stream()`, so every call is asynchronous and CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libpn12_b200.so")
+HEADER = os.path.join(os.path.dirname(PKG), "include", "pn12_b200.h")
+
+_lib = None
+
+vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+
+# name -> argtypes, mirroring include/pn12_b200.h
+_SIGNATURES = {
+    "pn_version": [],
+    "pn_device_check": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+    "pn_fps_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp],
+    "pn_fps_set_config": [i32, i32],
+    "pn_square_distance_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp],
+    "pn_ball_query_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, vp],
+    "pn_index_points_f32": [vp, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp],
+    "pn_group_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32, i32, i32, vp,
+                     i64, vp],
+    "pn_linear_f32": [vp, i64, i64, vp, i64, vp, i64, i32, i32, i64, i32, i32, vp, i64, i64, vp],
+    "pn_group_max_f32": [vp, i64, i64, i32, i32, vp, i64, vp],
+    "pn_three_nn_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp, vp],
+    "pn_three_interpolate_f32": [vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, i32, vp, i64, i64,
+                                 vp],
+    "pn_log_softmax_f32": [vp, i64, i64, i32, vp, i64, vp],
+}
+
+
+def declared_symbols() -> list:
+    """Every function name include/pn12_b200.h declares (used by the export test)."""
+    with open(HEADER) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pn_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    """Load the library once; fail loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m pointnet12_b200.build` "
+                "(nvcc, sm_100a). pointnet12_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        handle.pn_last_error_string.restype = C.c_char_p
+        handle.pn_last_error_string.argtypes = []
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = i32
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().pn_last_error_string().decode("utf-8", "replace")
+        kind = "CUDA error" if status > 0 else "argument error"
+        raise RuntimeError(f"{what} failed ({kind} {status}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,280 @@
+"""B200-native drop-in for the reference's model/pointnet.py (PointNet networks).
+
+Same class names, constructor arguments, submodule names (state_dict keys) and return values as the
+reference.  Everything is computed on point-major rows [B*N, C] by the C-ABI kernels:
+
+  * per-point conv chains          -> pn_linear_f32 (BatchNorm folded)
+  * max over points                -> pn_group_max_f32
+  * STN fully connected tail       -> pn_linear_f32 on [B, 1024] rows; the "+ identity" of
+                                      pointnet.py:40-43 / 77-83 is folded into fc3's bias
+  * torch.bmm(x, trans)            -> pn_linear_f32 with one weight matrix per cloud (w_bstride)
+  * seg head on cat([global, pointfeat]) (pointnet.py:128-131, 247): the 1024 global channels are the
+    same for every point of a cloud, so that half of conv1 becomes a per-cloud bias
+    (bias_bstride) and the per-point work drops from 1088 to 64 input channels.
+
+Inference only (train() mode raises); no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .pointnet_util import FoldedLayers, _eval_only
+
+
+def _point_rows(x_cm: torch.Tensor) -> torch.Tensor:
+    """User input [B, C, N] channel-major -> point-major [B, N, C] (layout change of the raw input)."""
+    return x_cm.permute(0, 2, 1).contiguous()
+
+
+class _STN(nn.Module):
+    """Shared implementation of the spatial transformers (pointnet.py:10-84)."""
+
+    def __init__(self, k: int):
+        super().__init__()
+        self.conv1 = nn.Conv1d(k, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.conv3 = nn.Conv1d(128, 1024, 1)
+        self.fc1 = nn.Linear(1024, 512)
+        self.fc2 = nn.Linear(512, 256)
+        self.fc3 = nn.Linear(256, k * k)
+        self.relu = nn.ReLU()
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(1024)
+        self.bn4 = nn.BatchNorm1d(512)
+        self.bn5 = nn.BatchNorm1d(256)
+        self.k = k
+        self._folded = FoldedLayers()
+
+    def transform_rows(self, x_pm: torch.Tensor) -> torch.Tensor:
+        """x_pm [B,N,k] point-major -> [B,k,k]."""
+        B, N, k = x_pm.shape
+        layers = self._folded.get([self.conv1, self.conv2, self.conv3, self.fc1, self.fc2, self.fc3],
+                                  [self.bn1, self.bn2, self.bn3, self.bn4, self.bn5, None])
+        h = x_pm.reshape(B * N, k)
+        for w, b in layers[:3]:
+            h = ops.linear(h, w, b, relu=True)
+        g = ops.group_max(h, N)                                                   # [B,1024]
+        g = ops.linear(g, *layers[3], relu=True)
+        g = ops.linear(g, *layers[4], relu=True)
+        w3, b3 = layers[5]
+        b3 = b3 + torch.eye(self.k, device=b3.device, dtype=b3.dtype).flatten()   # "+ iden" as a bias
+        return ops.linear(g, w3, b3, relu=False).view(B, self.k, self.k)
+
+    def forward(self, x):
+        _eval_only(self)
+        return self.transform_rows(_point_rows(x))
+
+
+class STN3d(_STN):
+    """Reference pointnet.py:10-45: [B,3,N] -> [B,3,3]."""
+
+    def __init__(self):
+        super().__init__(3)
+
+
+class STNkd(_STN):
+    """Reference pointnet.py:47-84: [B,k,N] -> [B,k,k]."""
+
+    def __init__(self, k=64):
+        super().__init__(k)
+
+
+class PointNetEncoder(nn.Module):
+    """Reference pointnet.py:86-131."""
+
+    def __init__(self, global_feat=True, input_dims=4, feature_transform=False):
+        super().__init__()
+        self.stn = STNkd(k=input_dims)
+        self.conv1 = nn.Conv1d(input_dims, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.conv3 = nn.Conv1d(128, 1024, 1)
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(1024)
+        self.global_feat = global_feat
+        self.feature_transform = feature_transform
+        if self.feature_transform:
+            self.fstn = STNkd(k=64)
+        self._folded = FoldedLayers()
+
+    def encode_rows(self, x_pm: torch.Tensor):
+        """x_pm [B,N,k] -> (global [B,1024], pointfeat [B,N,64], trans, trans_feat)."""
+        B, N, _ = x_pm.shape
+        (w1, b1), (w2, b2), (w3, b3) = self._folded.get([self.conv1, self.conv2, self.conv3],
+                                                        [self.bn1, self.bn2, self.bn3])
+        trans = self.stn.transform_rows(x_pm)
+        x = ops.bmm_points(x_pm, trans)                                           # pointnet.py:105-107
+        x = ops.linear(x.view(B * N, -1), w1, b1, relu=True).view(B, N, 64)
+        trans_feat = None
+        if self.feature_transform:
+            trans_feat = self.fstn.transform_rows(x)
+            x = ops.bmm_points(x, trans_feat)                                     # pointnet.py:111-114
+        pointfeat = x
+        h = ops.linear(x.view(B * N, 64), w2, b2, relu=True)
+        h = ops.linear(h, w3, b3, relu=False)                                     # bn3(conv3), no ReLU (:120)
+        return ops.group_max(h, N), pointfeat, trans, trans_feat
+
+    def forward(self, x):
+        _eval_only(self)
+        B, _, N = x.shape
+        g, pointfeat, trans, trans_feat = self.encode_rows(_point_rows(x))
+        if self.global_feat:
+            return g, trans, trans_feat
+        cat = torch.cat([g.view(B, 1024, 1).expand(B, 1024, N), pointfeat.permute(0, 2, 1)], 1)   # API parity only
+        return cat, trans, trans_feat
+
+
+class PointNetCls(nn.Module):
+    """Reference pointnet.py:133-151: [B,3,N] -> (log_probs [B,k], trans_feat)."""
+
+    def __init__(self, k=2, feature_transform=False):
+        super().__init__()
+        self.feature_transform = feature_transform
+        self.feat = PointNetEncoder(global_feat=True, feature_transform=feature_transform, input_dims=3)
+        self.fc1 = nn.Linear(1024, 512)
+        self.fc2 = nn.Linear(512, 256)
+        self.fc3 = nn.Linear(256, k)
+        self.dropout = nn.Dropout(p=0.3)
+        self.bn1 = nn.BatchNorm1d(512)
+        self.bn2 = nn.BatchNorm1d(256)
+        self.relu = nn.ReLU()
+        self._folded = FoldedLayers()
+
+    def forward(self, x):
+        _eval_only(self)
+        g, _, _, trans_feat = self.feat.encode_rows(_point_rows(x))
+        (w1, b1), (w2, b2), (w3, b3) = self._folded.get([self.fc1, self.fc2, self.fc3], [self.bn1, self.bn2, None])
+        h = ops.linear(g, w1, b1, relu=True)
+        h = ops.linear(h, w2, b2, relu=True)                                      # dropout = identity in eval
+        return ops.log_softmax(ops.linear(h, w3, b3, relu=False)), trans_feat
+
+
+class PointNetSeg(nn.Module):
+    """Reference pointnet.py:230-254: [B,input_dims,N] -> (log_probs [B,N,num_class], trans_feat [B,64,64])."""
+
+    def __init__(self, num_class, input_dims=4, feature_transform=False):
+        super().__init__()
+        self.k = num_class
+        self.feat = PointNetEncoder(global_feat=False, input_dims=input_dims, feature_transform=feature_transform)
+        self.conv1 = nn.Conv1d(1088, 512, 1)
+        self.conv2 = nn.Conv1d(512, 256, 1)
+        self.conv3 = nn.Conv1d(256, 128, 1)
+        self.conv4 = nn.Conv1d(128, self.k, 1)
+        self.bn1 = nn.BatchNorm1d(512)
+        self.bn2 = nn.BatchNorm1d(256)
+        self.bn3 = nn.BatchNorm1d(128)
+        self._folded = FoldedLayers()
+
+    def forward(self, x):
+        _eval_only(self)
+        B, _, N = x.shape
+        g, pointfeat, _, trans_feat = self.feat.encode_rows(_point_rows(x))
+        (w1, b1), (w2, b2), (w3, b3), (w4, b4) = self._folded.get(
+            [self.conv1, self.conv2, self.conv3, self.conv4], [self.bn1, self.bn2, self.bn3, None])
+        # conv1 on cat([global(1024) repeated, pointfeat(64)]): the global half is a per-cloud bias
+        cloud_bias = ops.linear(g, w1[:, :1024].contiguous(), b1, relu=False)     # [B,512]
+        h = ops.linear_cloud_bias(pointfeat, w1[:, 1024:].contiguous(), cloud_bias, relu=True).view(B * N, 512)
+        h = ops.linear(h, w2, b2, relu=True)
+        h = ops.linear(h, w3, b3, relu=True)
+        logp = ops.log_softmax(ops.linear(h, w4, b4, relu=False))
+        return logp.view(B, N, self.k), trans_feat
+
+
+class PointNetDenseCls(nn.Module):
+    """Reference pointnet.py:153-228 (ShapeNet part segmentation net):
+    forward(point_cloud [B,3,N], label [B,16]) -> (cls logits [B,cat_num], seg log_probs [B,N,part_num], trans_feat)."""
+
+    def __init__(self, cat_num=16, part_num=50):
+        super().__init__()
+        self.cat_num = cat_num
+        self.part_num = part_num
+        self.stn = STN3d()
+        self.conv1 = nn.Conv1d(3, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.conv3 = nn.Conv1d(128, 128, 1)
+        self.conv4 = nn.Conv1d(128, 512, 1)
+        self.conv5 = nn.Conv1d(512, 2048, 1)
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(128)
+        self.bn4 = nn.BatchNorm1d(512)
+        self.bn5 = nn.BatchNorm1d(2048)
+        self.fstn = STNkd(k=128)
+        self.fc1 = nn.Linear(2048, 256)
+        self.fc2 = nn.Linear(256, 256)
+        self.fc3 = nn.Linear(256, cat_num)
+        self.dropout = nn.Dropout(p=0.3)
+        self.bnc1 = nn.BatchNorm1d(256)
+        self.bnc2 = nn.BatchNorm1d(256)
+        self.convs1 = nn.Conv1d(4944, 256, 1)
+        self.convs2 = nn.Conv1d(256, 256, 1)
+        self.convs3 = nn.Conv1d(256, 128, 1)
+        self.convs4 = nn.Conv1d(128, part_num, 1)
+        self.bns1 = nn.BatchNorm1d(256)
+        self.bns2 = nn.BatchNorm1d(256)
+        self.bns3 = nn.BatchNorm1d(128)
+        self._folded = FoldedLayers()
+
+    def forward(self, point_cloud, label):
+        _eval_only(self)
+        B, _, N = point_cloud.shape
+        L = self._folded.get(
+            [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.fc1, self.fc2, self.fc3,
+             self.convs1, self.convs2, self.convs3, self.convs4],
+            [self.bn1, self.bn2, self.bn3, self.bn4, self.bn5, self.bnc1, self.bnc2, None,
+             self.bns1, self.bns2, self.bns3, None])
+        x = _point_rows(point_cloud)
+        x = ops.bmm_points(x, self.stn.transform_rows(x))
+        # per-point features out1..out5 are written side by side: they are the per-point half of `concat`
+        widths = [64, 128, 128, 512, 2048]
+        cat = torch.empty((B * N, sum(widths)), dtype=torch.float32, device=x.device)
+        cols = [0, 64, 192, 320, 832, 2880]
+        out1 = ops.linear(x.view(B * N, 3), *L[0], relu=True, out=cat[:, cols[0]:cols[1]])
+        out2 = ops.linear(out1, *L[1], relu=True, out=cat[:, cols[1]:cols[2]])
+        out3 = ops.linear(out2, *L[2], relu=True, out=cat[:, cols[2]:cols[3]])
+        trans_feat = self.fstn.transform_rows(out3.view(B, N, 128))
+        net_t = ops.bmm_points(out3.view(B, N, 128), trans_feat).view(B * N, 128)
+        out4 = ops.linear(net_t, *L[3], relu=True, out=cat[:, cols[3]:cols[4]])
+        out5 = ops.linear(out4, *L[4], relu=False, out=cat[:, cols[4]:cols[5]])
+        out_max = ops.group_max(out5, N)                                          # [B,2048]
+        net = ops.linear(out_max, *L[5], relu=True)
+        net = ops.linear(net, *L[6], relu=True)
+        net = ops.linear(net, *L[7], relu=False)                                  # [B,cat_num] (no log_softmax in the reference)
+        # segmentation: convs1 over cat([out_max, label] expanded, out1..out5): global half -> per-cloud bias
+        ws1, bs1 = L[8]
+        glob = torch.cat([out_max, label.to(out_max.dtype)], 1)                   # [B,2064]
+        cloud_bias = ops.linear(glob, ws1[:, :2064].contiguous(), bs1, relu=False)
+        h = ops.linear_cloud_bias(cat.view(B, N, -1), ws1[:, 2064:].contiguous(), cloud_bias, relu=True).view(B * N, 256)
+        h = ops.linear(h, *L[9], relu=True)
+        h = ops.linear(h, *L[10], relu=True)
+        seg = ops.log_softmax(ops.linear(h, *L[11], relu=False)).view(B, N, self.part_num)
+        return net, seg, trans_feat
+
+
+def feature_transform_reguliarzer(trans: torch.Tensor) -> torch.Tensor:
+    """Reference pointnet.py:257-263 (training-side regulariser; tiny, plain torch):
+    mean Frobenius norm of trans @ (trans^T - I)."""
+    d = trans.shape[1]
+    eye = torch.eye(d, device=trans.device, dtype=trans.dtype)[None]
+    return torch.mean(torch.norm(torch.bmm(trans, trans.transpose(2, 1) - eye), dim=(1, 2)))
+
+
+class PointNetLoss(nn.Module):
+    """Reference pointnet.py:266-278."""
+
+    def __init__(self, weight=1, mat_diff_loss_scale=0.001):
+        super().__init__()
+        self.mat_diff_loss_scale = mat_diff_loss_scale
+        self.weight = weight
+
+    def forward(self, labels_pred, label, seg_pred, seg, trans_feat):
+        seg_loss = nn.functional.nll_loss(seg_pred, seg)
+        label_loss = nn.functional.nll_loss(labels_pred, label)
+        reg = feature_transform_reguliarzer(trans_feat)
+        total = self.weight * seg_loss + (1 - self.weight) * label_loss + reg * self.mat_diff_loss_scale
+        return total, seg_loss, label_loss

@@ -1,0 +1,176 @@
+"""B200-native drop-in for the reference's model/pointnet2.py (PointNet++ networks).
+
+Class names, constructor arguments, submodule names (hence state_dict keys) and return values follow
+the reference; `checkpoints/pointnet2-inview-0.55884-0001.pth` loads with strict=True.  The five
+networks differ only in their level tables, so they are built from specs; the heads
+(conv/linear + BatchNorm + ReLU, log_softmax) run through the same C-ABI kernels as the blocks, on
+point-major rows, so a segmentation output [B, N, k] is produced directly in its final layout
+(the reference permutes at the end, pointnet2.py:175).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .pointnet_util import (FoldedLayers, PointNetFeaturePropagation, PointNetSetAbstraction,
+                            PointNetSetAbstractionMsg, _eval_only)
+
+
+def _ssg(npoint, radius, nsample, in_channel, mlp):
+    return PointNetSetAbstraction(npoint, radius, nsample, in_channel, mlp, False)
+
+
+def _msg(npoint, radii, nsamples, in_channel, mlps):
+    return PointNetSetAbstractionMsg(npoint, radii, nsamples, in_channel, mlps)
+
+
+def _all(in_channel, mlp):
+    return PointNetSetAbstraction(None, None, None, in_channel, mlp, True)
+
+
+def _fp(in_channel, mlp):
+    return PointNetFeaturePropagation(in_channel, mlp)
+
+
+class _Net(nn.Module):
+    """Registers named levels in order and owns the folded head weights."""
+
+    def _levels(self, **named):
+        for name, module in named.items():
+            setattr(self, name, module)
+        self._head = FoldedLayers()
+
+    def _cls_fc(self, dropout: float, classes: int):
+        """fc1-bn1-drop1-fc2-bn2-drop2-fc3 of the classification nets (pointnet2.py:28-35)."""
+        self.fc1, self.bn1, self.drop1 = nn.Linear(1024, 512), nn.BatchNorm1d(512), nn.Dropout(dropout)
+        self.fc2, self.bn2, self.drop2 = nn.Linear(512, 256), nn.BatchNorm1d(256), nn.Dropout(dropout)
+        self.fc3 = nn.Linear(256, classes)
+
+    def _seg_convs(self, classes: int):
+        """conv1-bn1-drop1-conv2 of the segmentation nets (pointnet2.py:154-157)."""
+        self.conv1, self.bn1, self.drop1 = nn.Conv1d(128, 128, 1), nn.BatchNorm1d(128), nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(128, classes, 1)
+
+    # -- heads (eval: dropout is the identity) ---------------------------------------------------
+    def _cls_head(self, global_feat: torch.Tensor) -> torch.Tensor:
+        (w1, b1), (w2, b2), (w3, b3) = self._head.get([self.fc1, self.fc2, self.fc3], [self.bn1, self.bn2, None])
+        x = ops.linear(global_feat, w1, b1, relu=True)
+        x = ops.linear(x, w2, b2, relu=True)
+        return ops.log_softmax(ops.linear(x, w3, b3, relu=False))
+
+    def _seg_head(self, l0_points: torch.Tensor):
+        """[B,128,N] -> (log_probs [B,N,k], feat [B,128,N])."""
+        B, C, N = l0_points.shape
+        (w1, b1), (w2, b2) = self._head.get([self.conv1, self.conv2], [self.bn1, None])
+        rows = l0_points.permute(0, 2, 1).reshape(B * N, C)        # a view when it comes from our own blocks
+        feat = ops.linear(rows, w1, b1, relu=True)
+        logp = ops.log_softmax(ops.linear(feat, w2, b2, relu=False))
+        return logp.view(B, N, -1), feat.view(B, N, -1).permute(0, 2, 1)
+
+    def _encode(self, names, xyz, points):
+        """Run set-abstraction levels in order; returns the per-level (xyz, features) lists."""
+        xs, fs = [xyz], [points]
+        for name in names:
+            x, f = getattr(self, name)(xs[-1], fs[-1])
+            xs.append(x)
+            fs.append(f)
+        return xs, fs
+
+
+class PointNet2ClsMsg(_Net):
+    """Reference pointnet2.py:7-47.  forward(xyz [B,3,N]) -> (log_probs [B,40], l3_points [B,1024,1])."""
+
+    def __init__(self):
+        super().__init__()
+        self._levels(
+            sa1=_msg(512, [0.1, 0.2, 0.4], [16, 32, 128], 0, [[32, 32, 64], [64, 64, 128], [64, 96, 128]]),
+            sa2=_msg(128, [0.2, 0.4, 0.8], [32, 64, 128], 320, [[64, 64, 128], [128, 128, 256], [128, 128, 256]]),
+            sa3=_all(640 + 3, [256, 512, 1024]))
+        self._cls_fc(0.4, 40)
+
+    def forward(self, xyz):
+        _eval_only(self)
+        _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+        return self._cls_head(fs[3].reshape(xyz.shape[0], 1024)), fs[3]
+
+
+class PointNet2ClsSsg(_Net):
+    """Reference pointnet2.py:49-73.  forward(xyz [B,3,N]) -> log_probs [B,40]."""
+
+    def __init__(self):
+        super().__init__()
+        self._levels(sa1=_ssg(512, 0.2, 32, 3, [64, 64, 128]),
+                     sa2=_ssg(128, 0.4, 64, 128 + 3, [128, 128, 256]),
+                     sa3=_all(256 + 3, [256, 512, 1024]))
+        self._cls_fc(0.4, 40)
+
+    def forward(self, xyz):
+        _eval_only(self)
+        _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+        return self._cls_head(fs[3].reshape(xyz.shape[0], 1024))
+
+
+class PointNet2PartSegSsg(_Net):
+    """Reference pointnet2.py:75-104.  forward(xyz [B,3,N]) -> (log_probs [B,N,k], feat [B,128,N])."""
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self._levels(sa1=_ssg(512, 0.2, 64, 3, [64, 64, 128]),
+                     sa2=_ssg(128, 0.4, 64, 128 + 3, [128, 128, 256]),
+                     sa3=_all(256 + 3, [256, 512, 1024]),
+                     fp3=_fp(1280, [256, 256]), fp2=_fp(384, [256, 128]), fp1=_fp(128, [128, 128, 128]))
+        self._seg_convs(num_classes)
+
+    def forward(self, xyz):
+        _eval_only(self)
+        xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+        f2 = self.fp3(xs[2], xs[3], fs[2], fs[3])
+        f1 = self.fp2(xs[1], xs[2], fs[1], f2)
+        return self._seg_head(self.fp1(xyz, xs[1], None, f1))
+
+
+class PointNet2PartSegMsg_one_hot(_Net):
+    """Reference pointnet2.py:106-139.  forward(xyz, norm_plt, cls_label [B,16]) -> log_probs [B,N,k]."""
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self._levels(
+            sa1=_msg(512, [0.1, 0.2, 0.4], [32, 64, 128], 0 + 3, [[32, 32, 64], [64, 64, 128], [64, 96, 128]]),
+            sa2=_msg(128, [0.4, 0.8], [64, 128], 128 + 128 + 64, [[128, 128, 256], [128, 196, 256]]),
+            sa3=_all(512 + 3, [256, 512, 1024]),
+            fp3=_fp(1536, [256, 256]), fp2=_fp(576, [256, 128]), fp1=_fp(150, [128, 128]))
+        self._seg_convs(num_classes)
+
+    def forward(self, xyz, norm_plt, cls_label):
+        _eval_only(self)
+        B, _, N = xyz.shape
+        xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, norm_plt)
+        f2 = self.fp3(xs[2], xs[3], fs[2], fs[3])
+        f1 = self.fp2(xs[1], xs[2], fs[1], f2)
+        skip = torch.cat([cls_label.view(B, 16, 1).expand(B, 16, N), xyz, norm_plt], 1)   # host-side glue [B,22,N]
+        return self._seg_head(self.fp1(xyz, xs[1], skip, f1))[0]
+
+
+class PointNet2SemSeg(_Net):
+    """Reference pointnet2.py:141-176.  forward(points [B, 3+feature_dims, N]) -> log_probs [B, N, num_classes]."""
+
+    def __init__(self, num_classes, feature_dims=3):
+        super().__init__()
+        self.feature_dims = feature_dims
+        self._levels(sa1=_ssg(1024, 0.1, 32, feature_dims + 3, [32, 32, 64]),
+                     sa2=_ssg(256, 0.2, 32, 64 + 3, [64, 64, 128]),
+                     sa3=_ssg(64, 0.4, 32, 128 + 3, [128, 128, 256]),
+                     sa4=_ssg(16, 0.8, 32, 256 + 3, [256, 256, 512]),
+                     fp4=_fp(768, [256, 256]), fp3=_fp(384, [256, 256]),
+                     fp2=_fp(320, [256, 128]), fp1=_fp(128, [128, 128, 128]))
+        self._seg_convs(num_classes)
+
+    def forward(self, points):
+        _eval_only(self)
+        xyz, feature = points[:, :3, :], points[:, 3:, :]
+        xs, fs = self._encode(("sa1", "sa2", "sa3", "sa4"), xyz, feature)
+        f3 = self.fp4(xs[3], xs[4], fs[3], fs[4])
+        f2 = self.fp3(xs[2], xs[3], fs[2], f3)
+        f1 = self.fp2(xs[1], xs[2], fs[1], f2)
+        return self._seg_head(self.fp1(xyz, xs[1], None, f1))[0]

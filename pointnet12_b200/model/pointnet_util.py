@@ -1,0 +1,240 @@
+"""B200-native drop-in for the reference's model/pointnet_util.py.
+
+Same names, argument order, layouts and state_dict as the reference (so its checkpoints load
+unchanged), but every step is a hand-written sm_100a kernel reached through the C ABI of
+libpn12_b200.so:
+
+    reference (model/pointnet_util.py)              here
+    ------------------------------------------      ---------------------------------------------
+    square_distance            :19-40               pn_square_distance_f32 (never used on the hot path)
+    index_points               :43-60               pn_index_points_f32
+    farthest_point_sample      :63-84               pn_fps_f32 (cluster per cloud, register resident)
+    query_ball_point           :87-107              pn_ball_query_f32 (ordered scan, no distance cube, no sort)
+    sample_and_group(_all)     :110-157             the three above + pn_group_f32
+    PointNetSetAbstraction     :160-201             + pn_linear_f32 (BN folded) + pn_group_max_f32
+    PointNetSetAbstractionMsg  :204-261             same, one ball query per radius, MSG channel order
+    PointNetFeaturePropagation :264-313             pn_three_nn_f32 + pn_three_interpolate_f32 + pn_linear_f32
+
+Functions take point-major [B, N, C] float32 CUDA tensors (strided views welcome) and return int64
+indices; modules take and return channel-major [B, C, N] like the reference.  Internally features stay
+point-major (a row per point, channels contiguous); the channel-major tensors the modules return are
+views of that storage, so chaining modules costs no transposes.
+
+Inference only for now: BatchNorm is folded into the conv weights from the running statistics, and
+calling a module in train() mode raises.  CPU tensors raise: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+# ------------------------------------------------------------------------------------------------
+# L1 primitives
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """[B,N,3] x [B,M,3] -> [B,N,M] with the reference's |a|^2 + |b|^2 - 2ab rounding sequence."""
+    return ops.square_distance(src, dst)
+
+
+def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,C] / [B,S,K,C]."""
+    return ops.index_points(points, idx)
+
+
+def farthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """xyz [B,N,3] -> centroids [B,npoint] int64.
+
+    The first centroid is drawn exactly like the reference draws it -- torch.randint on the CPU default
+    generator (pointnet_util.py:75) -- so torch.manual_seed(s) reproduces the reference's indices.
+    `start_idx` ([B], any device) overrides the draw.
+    """
+    B, N, _ = xyz.shape
+    if start_idx is None:
+        start_idx = torch.randint(0, N, (B,), dtype=torch.long)
+    elif not start_idx.is_cuda and (int(start_idx.min()) < 0 or int(start_idx.max()) >= N):
+        raise IndexError(f"start_idx out of range for N={N}")
+    return ops.fps(xyz, npoint, start_idx.to(xyz.device, non_blocking=True))
+
+
+def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """xyz [B,N,3], new_xyz [B,S,3] -> group_idx [B,S,nsample] int64: first nsample in-ball points in index order."""
+    return ops.ball_query(radius, nsample, xyz, new_xyz)
+
+
+def sample_and_group(npoint: int, radius: float, nsample: int, xyz: torch.Tensor, points: Optional[torch.Tensor],
+                     returnfps: bool = False):
+    """-> new_xyz [B,npoint,3], new_points [B,npoint,nsample,3+D] (xyz relative to the centroid first)."""
+    fps_idx = farthest_point_sample(xyz, npoint)
+    new_xyz = ops.index_points(xyz, fps_idx)
+    idx = ops.ball_query(radius, nsample, xyz, new_xyz)
+    new_points = ops.group(xyz, points, new_xyz, idx, msg_order=False)
+    if returnfps:
+        return new_xyz, new_points, ops.index_points(xyz, idx), fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz: torch.Tensor, points: Optional[torch.Tensor]):
+    """-> new_xyz zeros [B,1,3], new_points [B,1,N,3+D]: one group holding every point, not recentred."""
+    B, N, _ = xyz.shape
+    new_xyz = torch.zeros((B, 1, 3), dtype=torch.float32, device=xyz.device)
+    everyone = torch.arange(N, dtype=torch.int64, device=xyz.device).expand(B, 1, N).contiguous()
+    return new_xyz, ops.group(xyz, points, new_xyz, everyone, msg_order=False)   # x - 0 == x exactly
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm folding shared by the blocks and the networks
+def fold_conv_bn(conv: nn.Module, bn: Optional[nn.Module]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(W', b') with eval-mode BatchNorm folded in: W' = W*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta."""
+    w = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale[:, None]
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w.contiguous(), b.contiguous()
+
+
+class FoldedLayers:
+    """Lazily folded (W', b') list for a conv/bn chain; refolded when any parameter or buffer changes."""
+
+    def __init__(self):
+        self._key = None
+        self._layers: List[Tuple[torch.Tensor, torch.Tensor]] = []
+
+    @staticmethod
+    def _tensors(convs, bns):
+        for conv, bn in zip(convs, bns):
+            yield conv.weight
+            if conv.bias is not None:
+                yield conv.bias
+            if bn is not None:
+                yield from (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+
+    def get(self, convs: Sequence[nn.Module], bns: Sequence[Optional[nn.Module]]):
+        key = tuple((t.data_ptr(), t._version) for t in self._tensors(convs, bns))
+        if key != self._key:
+            self._layers = [fold_conv_bn(c, b) for c, b in zip(convs, bns)]
+            self._key = key
+        return self._layers
+
+
+def _eval_only(module: nn.Module) -> None:
+    if module.training:
+        raise NotImplementedError(
+            f"{type(module).__name__}: only the inference forward is implemented in this round "
+            "(BatchNorm is folded from running statistics); call .eval() first")
+
+
+def _mlp_rows(rows: torch.Tensor, layers) -> torch.Tensor:
+    for w, b in layers:
+        rows = ops.linear(rows, w, b, relu=True)
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+# L2 blocks
+class PointNetSetAbstraction(nn.Module):
+    """Sample (FPS) -> group (ball query) -> shared MLP -> max over the group.  Reference :160-201."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        c = in_channel
+        for width in mlp:
+            self.mlp_convs.append(nn.Conv2d(c, width, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(width))
+            c = width
+        self._folded = FoldedLayers()
+
+    def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor]):
+        """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,C',S]."""
+        _eval_only(self)
+        xyz_pm = xyz.permute(0, 2, 1)
+        pts_pm = points.permute(0, 2, 1) if points is not None else None
+        if self.group_all:
+            new_xyz, grouped = sample_and_group_all(xyz_pm, pts_pm)
+        else:
+            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_pm, pts_pm)
+        B, S, K, C = grouped.shape
+        rows = _mlp_rows(grouped.view(B * S * K, C), self._folded.get(self.mlp_convs, self.mlp_bns))
+        pooled = ops.group_max(rows, K).view(B, S, -1)
+        return new_xyz.permute(0, 2, 1), pooled.permute(0, 2, 1)
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """Multi-scale grouping: one FPS, then per radius ball query -> MLP -> max, scales concatenated.
+    Reference :204-261 (channel order inside a group is [features, xyz_rel], :247)."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for widths in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            c = in_channel + 3
+            for width in widths:
+                convs.append(nn.Conv2d(c, width, 1))
+                bns.append(nn.BatchNorm2d(width))
+                c = width
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self._folded = [FoldedLayers() for _ in mlp_list]
+
+    def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor]):
+        _eval_only(self)
+        xyz_pm = xyz.permute(0, 2, 1)
+        pts_pm = points.permute(0, 2, 1) if points is not None else None
+        B = xyz_pm.shape[0]
+        S = self.npoint
+        new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, S))
+        widths = [blk[-1].out_channels for blk in self.conv_blocks]
+        out = torch.empty((B, S, sum(widths)), dtype=torch.float32, device=xyz.device)
+        col = 0
+        for i, radius in enumerate(self.radius_list):
+            K = self.nsample_list[i]
+            idx = ops.ball_query(radius, K, xyz_pm, new_xyz)
+            grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=True)
+            rows = _mlp_rows(grouped.view(B * S * K, -1), self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]))
+            ops.group_max(rows, K, out=out.view(B * S, -1)[:, col:col + widths[i]])   # written in place: no concat
+            col += widths[i]
+        return new_xyz.permute(0, 2, 1), out.permute(0, 2, 1)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """3-NN inverse-distance interpolation of coarse features onto the fine points, skip concat, MLP.
+    Reference :264-313."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        c = in_channel
+        for width in mlp:
+            self.mlp_convs.append(nn.Conv1d(c, width, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(width))
+            c = width
+        self._folded = FoldedLayers()
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        _eval_only(self)
+        x1, x2 = xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1)
+        p2 = points2.permute(0, 2, 1)
+        p1 = points1.permute(0, 2, 1) if points1 is not None else None
+        B, N, _ = x1.shape
+        S = x2.shape[1]
+        if S == 1:   # a single coarse point: broadcast it (reference :292-293)
+            idx = torch.zeros((B, N, 3), dtype=torch.int64, device=x1.device)
+            w = torch.tensor([1.0, 0.0, 0.0], device=x1.device).expand(B, N, 3).contiguous()
+        else:
+            idx, w = ops.three_nn(x1, x2)
+        rows = ops.three_interpolate(p1, p2, idx, w).view(B * N, -1)
+        rows = _mlp_rows(rows, self._folded.get(self.mlp_convs, self.mlp_bns))
+        return rows.view(B, N, -1).permute(0, 2, 1)

@@ -1,0 +1,269 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers and strides.
+
+PyTorch is used here for device memory and streams only.  CUDA float32 tensors in, CUDA tensors out;
+CPU tensors raise (there is no CPU fallback).  Strided (permuted) point clouds are passed through
+unchanged -- the kernels take element strides, like the reference's functions take views.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as nv
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is a {t.device} tensor: pointnet12_b200 runs on CUDA (sm_100a) only and has no CPU fallback")
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    _need_cuda(t, name)
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def _i64(t: torch.Tensor, name: str) -> torch.Tensor:
+    _need_cuda(t, name)
+    t = t if t.dtype == torch.int64 else t.long()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cloud(t: torch.Tensor, name: str, channels: Optional[int] = None) -> torch.Tensor:
+    t = _f32(t, name)
+    if t.dim() != 3:
+        raise ValueError(f"{name} must be [B, N, C], got shape {tuple(t.shape)}")
+    if channels is not None and t.shape[2] != channels:
+        raise ValueError(f"{name} must have {channels} channels in its last dimension, got {t.shape[2]}")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _on_device:
+    """Make the tensor's device current for the duration of a launch (no-op in the common case)."""
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index
+        self.ctx = None
+
+    def __enter__(self):
+        if self.idx != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(self.idx)
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
+def device_check() -> Tuple[int, int, int]:
+    import ctypes as C
+
+    sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+    nv.call("pn_device_check", C.byref(sm), C.byref(ma), C.byref(mi))
+    return sm.value, ma.value, mi.value
+
+
+def fps_set_config(cluster_size: int = 0, threads: int = 0) -> None:
+    nv.call("pn_fps_set_config", cluster_size, threads)
+
+
+# ------------------------------------------------------------------------------------------------
+def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor) -> torch.Tensor:
+    """farthest_point_sample (pointnet_util.py:63-84); start_idx [B] int64 on the device."""
+    xyz = _cloud(xyz, "xyz", 3)
+    B, N, _ = xyz.shape
+    start_idx = _i64(start_idx, "start_idx")
+    if start_idx.shape != (B,):
+        raise ValueError(f"start_idx must have shape ({B},), got {tuple(start_idx.shape)}")
+    out = torch.empty((B, int(npoint)), dtype=torch.int64, device=xyz.device)
+    with _on_device(xyz):
+        nv.call("pn_fps_f32", xyz.data_ptr(), *xyz.stride(), B, N, int(npoint), start_idx.data_ptr(), out.data_ptr(),
+                _stream())
+    return out
+
+
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """pointnet_util.py:19-40 -> [B, N, M]."""
+    src, dst = _cloud(src, "src", 3), _cloud(dst, "dst", 3)
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float32, device=src.device)
+    with _on_device(src):
+        nv.call("pn_square_distance_f32", src.data_ptr(), *src.stride(), dst.data_ptr(), *dst.stride(), B, N, M,
+                out.data_ptr(), _stream())
+    return out
+
+
+def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """query_ball_point (pointnet_util.py:87-107) -> int64 [B, S, nsample]."""
+    xyz, new_xyz = _cloud(xyz, "xyz", 3), _cloud(new_xyz, "new_xyz", 3)
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty((B, S, int(nsample)), dtype=torch.int64, device=xyz.device)
+    r2 = float(radius ** 2)  # the reference compares against the python scalar radius ** 2 (cast to fp32 by torch)
+    with _on_device(xyz):
+        nv.call("pn_ball_query_f32", xyz.data_ptr(), *xyz.stride(), new_xyz.data_ptr(), *new_xyz.stride(), B, N, S, r2,
+                int(nsample), out.data_ptr(), _stream())
+    return out
+
+
+def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """pointnet_util.py:43-60: points [B,N,C], idx [B, ...] -> [B, ..., C]."""
+    points = _cloud(points, "points")
+    idx = _i64(idx, "idx")
+    B, N, Cc = points.shape
+    if idx.shape[0] != B:
+        raise ValueError("idx and points disagree on the batch size")
+    M = idx[0].numel()
+    out = torch.empty(tuple(idx.shape) + (Cc,), dtype=torch.float32, device=points.device)
+    if M:
+        with _on_device(points):
+            nv.call("pn_index_points_f32", points.data_ptr(), *points.stride(), B, N, Cc, idx.data_ptr(), M,
+                    out.data_ptr(), _stream())
+    return out
+
+
+def group(xyz: torch.Tensor, feat: Optional[torch.Tensor], new_xyz: torch.Tensor, idx: torch.Tensor,
+          msg_order: bool) -> torch.Tensor:
+    """Gather + recentre + concat (pointnet_util.py:127-131 / :243-247) -> [B, S, K, 3+D]."""
+    xyz, new_xyz = _cloud(xyz, "xyz", 3), _cloud(new_xyz, "new_xyz", 3)
+    idx = _i64(idx, "idx")
+    B, N, _ = xyz.shape
+    _, S, K = idx.shape
+    if feat is not None:
+        feat = _cloud(feat, "points")
+        D, fs = feat.shape[2], feat.stride()
+    else:
+        D, fs = 0, (0, 0, 0)
+    out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=xyz.device)
+    with _on_device(xyz):
+        nv.call("pn_group_f32", xyz.data_ptr(), *xyz.stride(), _p(feat), *fs, D, new_xyz.data_ptr(), *new_xyz.stride(),
+                idx.data_ptr(), B, N, S, K, int(msg_order), out.data_ptr(), 3 + D, _stream())
+    return out
+
+
+def _rows(x: torch.Tensor, name: str) -> Tuple[torch.Tensor, int, int, int]:
+    """2-D row-major view (rows, C) with unit channel stride -> (tensor, rows, C, ld)."""
+    x = _f32(x, name)
+    if x.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [rows, channels], got {tuple(x.shape)}")
+    if x.stride(1) != 1 and x.shape[1] != 1:
+        x = x.contiguous()
+    ld = x.stride(0) if x.shape[0] > 1 else max(x.stride(0), x.shape[1])
+    return x, x.shape[0], x.shape[1], ld
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(x @ w.T + bias) for x [rows, cin], w [cout, cin] (BatchNorm already folded)."""
+    x, rows, cin, ldx = _rows(x, "x")
+    w = _f32(w, "w").contiguous()
+    cout = w.shape[0]
+    if w.shape != (cout, cin):
+        raise ValueError(f"weight shape {tuple(w.shape)} does not match input channels {cin}")
+    if bias is not None:
+        bias = _f32(bias, "bias").contiguous()
+    if out is None:
+        out = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
+    ldy = out.stride(0) if rows > 1 else max(out.stride(0), cout)
+    with _on_device(x):
+        nv.call("pn_linear_f32", x.data_ptr(), ldx, 0, w.data_ptr(), 0, _p(bias), 0, int(relu), 1, rows, cin, cout,
+                out.data_ptr(), ldy, 0, _stream())
+    return out
+
+
+def bmm_points(x: torch.Tensor, trans: torch.Tensor) -> torch.Tensor:
+    """torch.bmm(x [B,N,k], trans [B,k,k2]) of pointnet.py:105-107 as a batched linear layer."""
+    x = _f32(x, "x").contiguous()
+    wt = _f32(trans, "trans").transpose(1, 2).contiguous()        # [B, k2, k]: rows = output channels
+    B, N, k = x.shape
+    k2 = wt.shape[1]
+    out = torch.empty((B, N, k2), dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        nv.call("pn_linear_f32", x.data_ptr(), k, N * k, wt.data_ptr(), k2 * k, None, 0, 0, B, N, k, k2, out.data_ptr(),
+                k2, N * k2, _stream())
+    return out
+
+
+def linear_cloud_bias(x: torch.Tensor, w: torch.Tensor, cloud_bias: torch.Tensor, relu: bool) -> torch.Tensor:
+    """y[b,n,:] = act(x[b,n,:] @ w.T + cloud_bias[b,:]) for x [B,N,cin]: shared weights, one bias row per cloud."""
+    x = _f32(x, "x").contiguous()
+    w = _f32(w, "w").contiguous()
+    cloud_bias = _f32(cloud_bias, "cloud_bias").contiguous()
+    B, N, cin = x.shape
+    cout = w.shape[0]
+    if w.shape != (cout, cin) or cloud_bias.shape != (B, cout):
+        raise ValueError("linear_cloud_bias: shape mismatch")
+    out = torch.empty((B, N, cout), dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        nv.call("pn_linear_f32", x.data_ptr(), cin, N * cin, w.data_ptr(), 0, cloud_bias.data_ptr(), cout, int(relu), B, N,
+                cin, cout, out.data_ptr(), cout, N * cout, _stream())
+    return out
+
+
+def group_max(x: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """max over each run of K consecutive rows: [G*K, C] -> [G, C] (optionally into a strided `out` view)."""
+    x, rows, Cc, ldx = _rows(x, "x")
+    if rows % K:
+        raise ValueError(f"{rows} rows are not a multiple of K={K}")
+    G = rows // K
+    if out is None:
+        out = torch.empty((G, Cc), dtype=torch.float32, device=x.device)
+    elif out.shape != (G, Cc) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("out must be a float32 [groups, C] view with unit channel stride")
+    ldy = out.stride(0) if G > 1 else max(out.stride(0), Cc)
+    with _on_device(x):
+        nv.call("pn_group_max_f32", x.data_ptr(), ldx, G, int(K), Cc, out.data_ptr(), ldy, _stream())
+    return out
+
+
+def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """3 nearest sources and normalised inverse-distance weights (pointnet_util.py:295-300)."""
+    xyz1, xyz2 = _cloud(xyz1, "xyz1", 3), _cloud(xyz2, "xyz2", 3)
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    idx = torch.empty((B, N, 3), dtype=torch.int64, device=xyz1.device)
+    w = torch.empty((B, N, 3), dtype=torch.float32, device=xyz1.device)
+    with _on_device(xyz1):
+        nv.call("pn_three_nn_f32", xyz1.data_ptr(), *xyz1.stride(), xyz2.data_ptr(), *xyz2.stride(), B, N, S,
+                idx.data_ptr(), w.data_ptr(), _stream())
+    return idx, w
+
+
+def three_interpolate(points1: Optional[torch.Tensor], points2: torch.Tensor, idx: torch.Tensor,
+                      weight: torch.Tensor) -> torch.Tensor:
+    """cat([points1, sum_k points2[idx_k] * weight_k]) (pointnet_util.py:301-307) -> [B, N, D1+D2]."""
+    points2 = _cloud(points2, "points2")
+    idx = _i64(idx, "idx")
+    weight = _f32(weight, "weight").contiguous()
+    B, S, D2 = points2.shape
+    N = idx.shape[1]
+    if points1 is not None:
+        points1 = _cloud(points1, "points1")
+        D1, s1 = points1.shape[2], points1.stride()
+    else:
+        D1, s1 = 0, (0, 0, 0)
+    out = torch.empty((B, N, D1 + D2), dtype=torch.float32, device=points2.device)
+    with _on_device(points2):
+        nv.call("pn_three_interpolate_f32", _p(points1), *s1, D1, points2.data_ptr(), *points2.stride(), D2, S,
+                idx.data_ptr(), weight.data_ptr(), B, N, out.data_ptr(), D1 + D2, N * (D1 + D2), _stream())
+    return out
+
+
+def log_softmax(x: torch.Tensor) -> torch.Tensor:
+    x, rows, Cc, ldx = _rows(x, "x")
+    out = torch.empty((rows, Cc), dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        nv.call("pn_log_softmax_f32", x.data_ptr(), ldx, rows, Cc, out.data_ptr(), Cc, _stream())
+    return out

@@ -36,6 +36,11 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def ckpt_path():
+    return CKPT
+
+
+@pytest.fixture(scope="session")
 def ckpt_state():
     """The reference's shipped PointNet2SemSeg checkpoint as {name: ndarray} without the module. prefix."""
     import torch

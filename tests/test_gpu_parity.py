@@ -1,0 +1,482 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden vectors.
+
+Bar (SURVEY.md section 8c / north_star):
+  * FPS, ball-query, gather and 3-NN indices: bit-exact (3-NN rows whose 3rd/4th neighbours tie are excluded:
+    the reference resolves them with an unstable sort);
+  * floating point: max|delta| / max(1, max|ref|) <= 1e-3 on log-probs (fp32 mode), and labels equal except
+    where the reference's own top-2 margin is below 2e-3.
+Sizes the oracle finishes in seconds are compared directly; config-C2 full size (B=8, N=24000) is checked
+through the golden fixtures (two clouds) and size-independent properties.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from pointnet12_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+LOGP_TOL = 1e-3     # north_star: logits within 1e-3 relative in fp32
+FEAT_TOL = 1e-4     # intermediate features, same metric
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (run with -m 'not gpu' on CPU boxes)")
+    from pointnet12_b200 import ops
+
+    sm, major, minor = ops.device_check()
+    assert major == 10, "kernels are built for sm_100a"
+    return torch.device("cuda", 0)
+
+
+def rel_err(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def cuda(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def views(pts_dev):
+    """[B,4,N] -> strided point-major views (xyz [B,N,3], feat [B,N,1]) exactly as the reference makes them."""
+    pm = pts_dev.permute(0, 2, 1)
+    return pm[:, :, :3], pm[:, :, 3:]
+
+
+def starts(ns, B, seed=0):
+    torch.manual_seed(seed)
+    return [torch.randint(0, n, (B,), dtype=torch.long) for n in ns]
+
+
+# ------------------------------------------------------------------------------------------------ primitives
+@pytest.mark.parametrize("N,npoint,B", [(24000, 1024, 2), (1024, 256, 8), (256, 64, 8), (64, 16, 8), (4096, 256, 3),
+                                        (8192, 64, 2), (16384, 256, 1), (33, 7, 2), (5000, 100, 5)])
+def test_fps_vs_oracle(dev, N, npoint, B):
+    from pointnet12_b200.model import pointnet_util as U
+
+    pts = syn.kitti_batch(B, N, config=3)
+    st = starts([N], B, seed=N)[0]
+    want = orc.farthest_point_sample(pts.transpose(0, 2, 1)[:, :, :3], npoint, st.numpy())
+    got = U.farthest_point_sample(views(cuda(pts, dev))[0], npoint, start_idx=st)
+    assert got.dtype == torch.int64 and got.shape == (B, npoint)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("cluster,threads", [(1, 1024), (2, 512), (4, 256), (8, 128), (8, 512), (16, 128), (16, 256)])
+def test_fps_every_cluster_shape(dev, cluster, threads):
+    """Every cluster size / CTA width gives the same (bit-exact) answer."""
+    from pointnet12_b200 import ops
+
+    N, npoint, B = 8000, 128, 3
+    pts = syn.kitti_batch(B, N, config=5)
+    st = starts([N], B, seed=11)[0]
+    want = orc.farthest_point_sample(pts.transpose(0, 2, 1)[:, :, :3], npoint, st.numpy())
+    try:
+        ops.fps_set_config(cluster, threads)
+        got = ops.fps(views(cuda(pts, dev))[0], npoint, st.to(dev))
+        torch.cuda.synchronize()
+    finally:
+        ops.fps_set_config(0, 0)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_contiguous_layout_and_seed(dev):
+    """Contiguous [B,N,3] input and the implicit torch.randint draw (pointnet_util.py:75)."""
+    from pointnet12_b200.model import pointnet_util as U
+
+    pts = syn.kitti_batch(2, 4096, config=3)
+    xyz = np.ascontiguousarray(pts.transpose(0, 2, 1)[:, :, :3])
+    st = starts([4096], 2, seed=5)[0]
+    want = orc.farthest_point_sample(xyz, 64, st.numpy())
+    torch.manual_seed(5)
+    got = U.farthest_point_sample(cuda(xyz, dev), 64)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_ball_golden_chain(dev, golden):
+    """The four PointNet2SemSeg levels at N0 = 24000 against the reference's own indices."""
+    from pointnet12_b200.model import pointnet_util as U
+
+    g = golden("primitives_c2")
+    cur = views(cuda(syn.kitti_batch(2, 24000, config=2), dev))[0]
+    for lvl, (npoint, radius) in enumerate([(1024, 0.1), (256, 0.2), (64, 0.4), (16, 0.8)], 1):
+        fps = U.farthest_point_sample(cur, npoint, start_idx=torch.from_numpy(g[f"l{lvl}_start"]))
+        assert np.array_equal(fps.cpu().numpy(), g[f"l{lvl}_fps"].astype(np.int64)), f"FPS level {lvl}"
+        new_xyz = U.index_points(cur, fps)
+        assert np.array_equal(new_xyz.cpu().numpy(), g[f"l{lvl}_new_xyz"])
+        ball = U.query_ball_point(radius, 32, cur, new_xyz)
+        assert np.array_equal(ball.cpu().numpy(), g[f"l{lvl}_ball"].astype(np.int64)), f"ball query level {lvl}"
+        cur = new_xyz
+
+
+@pytest.mark.parametrize("N,S,radius,K,B", [(24000, 1024, 0.1, 32, 2), (1024, 256, 0.2, 32, 8), (64, 16, 0.8, 32, 8),
+                                            (4096, 100, 0.4, 64, 2), (3000, 37, 0.05, 16, 3), (2049, 9, 2.0, 128, 1)])
+def test_ball_query_vs_oracle(dev, N, S, radius, K, B):
+    from pointnet12_b200.model import pointnet_util as U
+
+    pts = syn.kitti_batch(B, N, config=3)
+    xyz = pts.transpose(0, 2, 1)[:, :, :3]
+    rng = np.random.default_rng(N + S)
+    q = np.ascontiguousarray(np.stack([xyz[b][rng.choice(N, S, replace=False)] for b in range(B)]))
+    want = orc.query_ball_point(radius, K, xyz, q)
+    got = U.query_ball_point(radius, K, views(cuda(pts, dev))[0], cuda(q, dev))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_ball_query_empty_ball(dev):
+    """A query far from every point: the reference leaves the row filled with N."""
+    from pointnet12_b200.model import pointnet_util as U
+
+    pts = syn.kitti_batch(1, 512, config=3)
+    xyz = pts.transpose(0, 2, 1)[:, :, :3]
+    q = np.full((1, 4, 3), 50.0, dtype=np.float32)
+    q[0, 0] = xyz[0, 17]
+    got = U.query_ball_point(0.1, 8, cuda(np.ascontiguousarray(xyz), dev), cuda(q, dev)).cpu().numpy()
+    want = orc.query_ball_point(0.1, 8, xyz, q)
+    assert np.array_equal(got, want)
+    assert (got[0, 1:] == 512).all()
+
+
+def test_modelnet_msg_primitives_golden(dev, golden):
+    from pointnet12_b200.model import pointnet_util as U
+
+    g = golden("primitives_misc")
+    xyz = cuda(syn.modelnet_batch(2, 1024), dev).permute(0, 2, 1)
+    torch.manual_seed(7)
+    fps = U.farthest_point_sample(xyz, 512)
+    assert np.array_equal(fps.cpu().numpy(), g["mn_fps"].astype(np.int64))
+    new_xyz = U.index_points(xyz, fps)
+    for r, k in ((0.1, 16), (0.2, 32), (0.4, 128)):
+        got = U.query_ball_point(r, k, xyz, new_xyz).cpu().numpy()
+        assert np.array_equal(got, g[f"mn_ball_r{r}_k{k}"].astype(np.int64))
+
+
+def test_square_distance_bit_exact(dev, golden):
+    from pointnet12_b200.model import pointnet_util as U
+
+    g = golden("primitives_c2")
+    xyz = views(cuda(syn.kitti_batch(2, 24000, config=2), dev))[0]
+    a, b = xyz[:, :64, :].contiguous(), xyz[:, 5000:5512, :]
+    assert np.array_equal(U.square_distance(a, b).cpu().numpy(), g["sqd_ab"])
+    assert np.array_equal(U.square_distance(b, a).cpu().numpy(), g["sqd_ba"])
+
+
+def test_sample_and_group_golden(dev, golden):
+    from pointnet12_b200.model import pointnet_util as U
+
+    g = golden("primitives_c2")
+    xyz, feat = views(cuda(syn.kitti_batch(2, 24000, config=2), dev))
+    torch.manual_seed(0)
+    new_xyz, new_points = U.sample_and_group(1024, 0.1, 32, xyz, feat)
+    assert new_points.shape == (2, 1024, 32, 4)
+    assert np.array_equal(new_points[0, :64].cpu().numpy(), g["sg_new_points_b0"])
+    torch.manual_seed(0)
+    _, _, grouped_xyz, fps_idx = U.sample_and_group(1024, 0.1, 32, xyz, feat, returnfps=True)
+    assert grouped_xyz.shape == (2, 1024, 32, 3) and fps_idx.shape == (2, 1024)
+
+
+def test_group_msg_order_and_group_all(dev):
+    from pointnet12_b200 import ops
+    from pointnet12_b200.model import pointnet_util as U
+
+    rng = np.random.default_rng(0)
+    xyz = rng.normal(size=(2, 300, 3)).astype(np.float32)
+    feat = rng.normal(size=(2, 300, 5)).astype(np.float32)
+    q = xyz[:, :10].copy()
+    idx = rng.integers(0, 300, size=(2, 10, 6))
+    want = orc.group(xyz, feat, q, idx, msg_order=True)
+    got = ops.group(cuda(xyz, dev), cuda(feat, dev), cuda(q, dev), cuda(idx, dev), msg_order=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    want0 = orc.group(xyz, None, q, idx, msg_order=False)
+    got0 = ops.group(cuda(xyz, dev), None, cuda(q, dev), cuda(idx, dev), msg_order=False)
+    assert np.array_equal(got0.cpu().numpy(), want0)
+    nx, allp = U.sample_and_group_all(cuda(xyz, dev), cuda(feat, dev))
+    wx, wp = orc.sample_and_group_all(xyz, feat)
+    assert np.array_equal(nx.cpu().numpy(), wx) and np.array_equal(allp.cpu().numpy(), wp)
+
+
+@pytest.mark.parametrize("rows,cin,cout,relu", [(4096, 4, 32, True), (1000, 67, 64, True), (777, 131, 128, True),
+                                                (512, 259, 256, True), (2048, 128, 19, False), (8, 1024, 512, True),
+                                                (300, 3, 64, True), (129, 320, 256, False)])
+def test_linear_vs_oracle(dev, rows, cin, cout, relu):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(rows + cin)
+    x = rng.normal(size=(rows, cin)).astype(np.float32)
+    w = (rng.normal(size=(cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.normal(size=(cout,)).astype(np.float32)
+    want = orc.linear(x, w, b, None, relu)
+    got = ops.linear(cuda(x, dev), cuda(w, dev), cuda(b, dev), relu)
+    assert rel_err(got, want) < 1e-5
+
+
+def test_linear_batched_and_cloud_bias(dev):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(3, 500, 64)).astype(np.float32)
+    t = rng.normal(size=(3, 64, 64)).astype(np.float32)
+    want = np.einsum("bnk,bkj->bnj", x.astype(np.float64), t.astype(np.float64))
+    got = ops.bmm_points(cuda(x, dev), cuda(t, dev))
+    assert rel_err(got, want.astype(np.float32)) < 1e-5
+    w = rng.normal(size=(40, 64)).astype(np.float32)
+    cb = rng.normal(size=(3, 40)).astype(np.float32)
+    want = np.maximum(np.einsum("bnk,ok->bno", x.astype(np.float64), w.astype(np.float64)) + cb[:, None, :], 0)
+    got = ops.linear_cloud_bias(cuda(x, dev), cuda(w, dev), cuda(cb, dev), relu=True)
+    assert rel_err(got, want.astype(np.float32)) < 1e-5
+
+
+def test_group_max_and_log_softmax(dev):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(64 * 32, 70)).astype(np.float32)
+    assert np.array_equal(ops.group_max(cuda(x, dev), 32).cpu().numpy(), orc.group_max(x, 32))
+    tall = rng.normal(size=(3 * 1000, 130)).astype(np.float32)
+    assert np.array_equal(ops.group_max(cuda(tall, dev), 1000).cpu().numpy(), orc.group_max(tall, 1000))
+    z = (rng.normal(size=(999, 19)) * 5).astype(np.float32)
+    assert rel_err(ops.log_softmax(cuda(z, dev)), orc.log_softmax(z)) < 1e-6
+    z = (rng.normal(size=(50, 50)) * 5).astype(np.float32)
+    assert rel_err(ops.log_softmax(cuda(z, dev)), orc.log_softmax(z)) < 1e-6
+
+
+@pytest.mark.parametrize("N,S,B", [(24000, 1024, 2), (1024, 256, 4), (64, 16, 8), (5000, 1500, 1)])
+def test_three_nn_interpolate_vs_oracle(dev, N, S, B):
+    from pointnet12_b200 import ops
+
+    pts = syn.kitti_batch(B, N, config=3)
+    xyz1 = pts.transpose(0, 2, 1)[:, :, :3]
+    rng = np.random.default_rng(S)
+    xyz2 = np.ascontiguousarray(np.stack([xyz1[b][np.sort(rng.choice(N, S, replace=False))] for b in range(B)]))
+    p1 = rng.normal(size=(B, N, 7)).astype(np.float32)
+    p2 = rng.normal(size=(B, S, 33)).astype(np.float32)
+    widx, ww, _, tie = orc.three_nn(xyz1, xyz2)
+    idx, w = ops.three_nn(views(cuda(pts, dev))[0], cuda(xyz2, dev))
+    assert np.array_equal(idx.cpu().numpy(), widx)          # same (distance, index) order, ties included
+    assert np.allclose(w.cpu().numpy(), ww, rtol=1e-6, atol=1e-7)
+    got = ops.three_interpolate(cuda(p1, dev), cuda(p2, dev), idx, w)
+    want = np.concatenate([p1, orc.three_interpolate(p2, widx, ww)], axis=-1)
+    assert rel_err(got, want) < 1e-6
+    got = ops.three_interpolate(None, cuda(p2, dev), idx, w)
+    assert rel_err(got, want[:, :, 7:]) < 1e-6
+
+
+def test_cpu_tensor_raises(dev):
+    from pointnet12_b200.model import pointnet_util as U
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        U.farthest_point_sample(torch.zeros(1, 64, 3), 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        U.query_ball_point(0.1, 4, torch.zeros(1, 64, 3), torch.zeros(1, 4, 3))
+
+
+def test_bad_arguments_report_errors(dev):
+    from pointnet12_b200 import _native as nv
+
+    rc = nv.lib().pn_fps_f32(None, 0, 0, 0, 1, 16, 4, None, None, None)
+    assert rc == -1 and b"null pointer" in nv.lib().pn_last_error_string()
+    x = torch.zeros(1, 200000, 3, device=dev)
+    with pytest.raises(RuntimeError, match="pn_fps_f32"):
+        from pointnet12_b200 import ops
+        ops.fps(x, 4, torch.zeros(1, dtype=torch.long, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------ blocks / networks
+def test_checkpoint_loads_strict(dev, ckpt_path):
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+    from pointnet12_b200.model.utils import load_pointnet
+
+    sd = torch.load(ckpt_path, map_location="cpu")
+    assert len(sd) == 156 and all(k.startswith("module.") for k in sd)
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    assert isinstance(net.module, PointNet2SemSeg) and not net.training
+    assert set(net.state_dict().keys()) == set(sd.keys())
+
+
+def test_blocks_golden(dev, golden, ckpt_path):
+    from pointnet12_b200.model.utils import load_pointnet
+
+    g = golden("blocks_ckpt")
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev).module
+    p = cuda(syn.kitti_batch(2, 4096, config=2), dev)
+    torch.manual_seed(0)
+    l1_xyz, l1_f = net.sa1(p[:, :3, :], p[:, 3:, :])
+    l2_xyz, l2_f = net.sa2(l1_xyz, l1_f)
+    assert l1_xyz.shape == (2, 3, 1024) and l1_f.shape == (2, 64, 1024) and l2_f.shape == (2, 128, 256)
+    assert np.array_equal(l1_xyz.cpu().numpy(), g["sa1_xyz"]) and np.array_equal(l2_xyz.cpu().numpy(), g["sa2_xyz"])
+    assert rel_err(l1_f, g["sa1_feat"]) < FEAT_TOL
+    assert rel_err(l2_f, g["sa2_feat"]) < FEAT_TOL
+    p2 = cuda(np.random.default_rng(5).normal(0, 1, (2, 256, 256)).astype(np.float32), dev)
+    o2 = net.fp2(l1_xyz, l2_xyz, l1_f, p2)
+    assert o2.shape == (2, 128, 1024)
+    assert rel_err(o2, g["fp2_out"]) < FEAT_TOL
+    o1 = net.fp1(p[:, :3, :], l1_xyz, None, o2)
+    _, _, _, tie = orc.three_nn(p[:, :3, :].permute(0, 2, 1).cpu().numpy(), l1_xyz.permute(0, 2, 1).cpu().numpy())
+    ok = (~tie)[:, ::8][:, None, :]
+    d = np.abs(o1[:, :, ::8].cpu().numpy() - g["fp1_out_sub8"]) * ok
+    assert float(d.max() / max(1.0, np.abs(g["fp1_out_sub8"]).max())) < FEAT_TOL
+
+
+def test_pointnet2_semseg_golden_n4096(dev, golden, ckpt_path):
+    from pointnet12_b200.model.utils import load_pointnet
+
+    g = golden("pointnet2_semseg_ckpt")
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    p = cuda(syn.kitti_batch(2, 4096, config=2), dev)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        logp = net(p)
+    assert logp.shape == (2, 4096, 19)
+    assert rel_err(logp, g["n4096_logp"]) < LOGP_TOL
+    assert (logp.argmax(-1).cpu().numpy() == g["n4096_logp"].argmax(-1)).mean() > 0.999
+
+
+def test_pointnet2_semseg_golden_n24000(dev, golden, ckpt_path):
+    """Config C2 clouds 0 and 1 against the reference: log-probs (every 16th point) and labels (all points)."""
+    from pointnet12_b200.model.utils import load_pointnet
+
+    g = golden("pointnet2_semseg_ckpt")
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    pts = syn.kitti_batch(2, 24000, config=2)
+    p = cuda(pts, dev)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        logp = net(p).cpu().numpy()
+    # fp1 3-NN tie rows are undefined in the reference (unstable sort): exclude them
+    g1 = golden("primitives_c2")
+    _, _, _, tie = orc.three_nn(pts.transpose(0, 2, 1)[:, :, :3], g1["l1_new_xyz"])
+    ok = ~tie
+    d = np.abs(logp[:, ::16, :] - g["n24000_logp_sub"]).max(-1) * ok[:, ::16]
+    assert float(d.max() / max(1.0, np.abs(g["n24000_logp_sub"]).max())) < LOGP_TOL
+    flips = (logp.argmax(-1) != g["n24000_label"]) & ok
+    assert (g["n24000_margin"].astype(np.float32)[flips] < 2e-3).all()
+    assert flips.mean() < 5e-4
+
+
+def test_pointnet2_semseg_vs_oracle_batch8(dev, ckpt_state, ckpt_path):
+    """B = 8 (the C2 batch) at a size the oracle finishes quickly; different seed than the fixtures."""
+    from pointnet12_b200.model.utils import load_pointnet
+
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    pts = syn.kitti_batch(8, 2048, config=6)
+    st = [s.numpy() for s in starts([2048, 1024, 256, 64], 8, seed=3)]
+    trace = {}
+    want = orc.pointnet2_semseg(ckpt_state, pts, st, trace)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        got = net(cuda(pts, dev)).cpu().numpy()
+    assert not (trace["fp4.nn_tie"].any() or trace["fp3.nn_tie"].any() or trace["fp2.nn_tie"].any())
+    assert rel_err(got, want) < LOGP_TOL            # ties included: the CUDA path breaks them like the oracle does
+    assert (got.argmax(-1) == want.argmax(-1)).mean() > 0.999
+
+
+def _seeded(net, seed, dev):
+    sd = syn.random_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return net.to(dev).eval()
+
+
+def test_pointnet_seg_golden(dev, golden):
+    from pointnet12_b200.model.pointnet import PointNetSeg
+
+    g = golden("pointnet_seg_seed1234")
+    net = _seeded(PointNetSeg(19, input_dims=4, feature_transform=True), 1234, dev)
+    with torch.no_grad():
+        logp, tf = net(cuda(syn.kitti_batch(2, 2048, config=1), dev))
+    assert logp.shape == (2, 2048, 19) and tf.shape == (2, 64, 64)
+    assert rel_err(tf, g["trans_feat"]) < LOGP_TOL
+    assert rel_err(logp, g["logp"]) < LOGP_TOL
+    assert (logp.argmax(-1).cpu().numpy() == g["logp"].argmax(-1)).mean() > 0.999
+
+
+def test_pointnet2_cls_msg_golden(dev, golden):
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsMsg
+
+    g = golden("pointnet2_cls_msg_seed1234")
+    net = _seeded(PointNet2ClsMsg(), 1234, dev)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        logp, l3 = net(cuda(syn.modelnet_batch(4, 1024), dev))
+    assert logp.shape == (4, 40) and l3.shape == (4, 1024, 1)
+    assert rel_err(l3, g["l3_points"]) < LOGP_TOL
+    assert rel_err(logp, g["logp"]) < LOGP_TOL
+    assert np.array_equal(logp.argmax(-1).cpu().numpy(), g["logp"].argmax(-1))
+
+
+def test_other_heads_golden(dev, golden):
+    from pointnet12_b200.model.pointnet import PointNetCls
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsSsg, PointNet2PartSegSsg
+
+    g = golden("other_heads_seeded")
+    x = cuda(syn.modelnet_batch(2, 1024), dev)
+    # build the nets first: constructing a module consumes the RNG that the FPS start draw uses
+    cls_ssg, partseg, cls = (_seeded(PointNet2ClsSsg(), 77, dev), _seeded(PointNet2PartSegSsg(50), 78, dev),
+                             _seeded(PointNetCls(k=40, feature_transform=True), 79, dev))
+    with torch.no_grad():
+        torch.manual_seed(0)
+        assert rel_err(cls_ssg(x), g["cls_ssg_logp"]) < LOGP_TOL
+        torch.manual_seed(0)
+        logp, feat = partseg(x)
+        assert rel_err(logp, g["partseg_ssg_logp"]) < LOGP_TOL and rel_err(feat, g["partseg_ssg_feat"]) < LOGP_TOL
+        logp, tf = cls(x)
+        assert rel_err(logp, g["pointnet_cls_logp"]) < LOGP_TOL and rel_err(tf, g["pointnet_cls_tf"]) < LOGP_TOL
+
+
+def test_partseg_msg_smoke_shape(dev):
+    """The reference's only runnable smoke test (pointnet2.py:179-187): (8,3,2048) -> [8,2048,50]."""
+    from pointnet12_b200.model.pointnet2 import PointNet2PartSegMsg_one_hot
+
+    net = _seeded(PointNet2PartSegMsg_one_hot(50), 5, dev)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((8, 3, 2048), generator=g).to(dev)
+    label = torch.randn((8, 16), generator=g).to(dev)
+    with torch.no_grad():
+        out = net(x, x, label)
+    assert out.shape == (8, 2048, 50)
+    assert torch.allclose(out.exp().sum(-1), torch.ones(8, 2048, device=dev), atol=1e-4)
+
+
+def test_train_mode_raises(dev):
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+
+    net = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 4, 2048, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties (C2)
+def test_c2_full_size_properties(dev):
+    """B=8, N=24000: properties that need no oracle run.
+    FPS: first index is the start, indices are distinct points in range, and the sequence of
+    selected-point distances to the already-selected set is non-increasing (the defining FPS property).
+    Ball query: rows are ascending until the padding starts, padding repeats the first hit, the centroid
+    itself is in its ball, and every listed point passes the membership test."""
+    from pointnet12_b200.model import pointnet_util as U
+
+    B, N, S, K, r = 8, 24000, 1024, 32, 0.1
+    pts = cuda(syn.kitti_batch(B, N, config=2), dev)
+    xyz, _ = views(pts)
+    st = starts([N], B, seed=0)[0]
+    fps = U.farthest_point_sample(xyz, S, start_idx=st)
+    assert torch.equal(fps[:, 0].cpu(), st)
+    assert int(fps.min()) >= 0 and int(fps.max()) < N
+    new_xyz = U.index_points(xyz, fps)                                  # [B,S,3]
+    sel = new_xyz.double()
+    d = torch.cdist(sel, sel)                                           # plain torch as a checker only
+    tri = torch.tril(torch.ones(S, S, device=dev, dtype=torch.bool), diagonal=-1)
+    mind = torch.where(tri, d, torch.full_like(d, float("inf"))).min(dim=2)[0][:, 1:]   # dist to earlier picks
+    assert bool((mind[:, 1:] <= mind[:, :-1] + 1e-6).all())
+    ball = U.query_ball_point(r, K, xyz, new_xyz)
+    assert int(ball.min()) >= 0 and int(ball.max()) < N
+    first = ball[:, :, :1]
+    asc = (ball[:, :, 1:] > ball[:, :, :-1]) | (ball[:, :, 1:] == first)
+    assert bool(asc.all())
+    g = U.index_points(xyz, ball) - new_xyz[:, :, None, :]
+    assert float((g.double() ** 2).sum(-1).max()) <= r * r * (1 + 1e-4)
+    # idempotence / determinism
+    assert torch.equal(ball, U.query_ball_point(r, K, xyz, new_xyz))
+    assert torch.equal(fps, U.farthest_point_sample(xyz, S, start_idx=st))
