@@ -72,5 +72,30 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what} failed ({kind} {status}): {msg}")
 
 
-def call(name: str, *args) -> None:
+# ---- launch accounting (used by bench.py): how many of our kernels were launched, and optional CUDA-event
+# timing of selected entry points on the launching stream.
+launch_count = 0
+_timed = {}          # name -> list of (start_event, stop_event, tag)
+
+
+def time_entry_points(names=None):
+    """Enable (names = iterable of entry points) or disable (None) CUDA-event timing; returns the old records."""
+    global _timed
+    old, _timed = _timed, ({n: [] for n in names} if names else {})
+    return old
+
+
+def call(name: str, *args, tag=None) -> None:
+    global launch_count
+    launch_count += 1
+    rec = _timed.get(name)
+    if rec is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    import torch
+
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     check(getattr(lib(), name)(*args), name)
+    b.record()
+    rec.append((a, b, tag))

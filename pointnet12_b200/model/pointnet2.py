@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from .. import ops
 from .pointnet_util import (FoldedLayers, PointNetFeaturePropagation, PointNetSetAbstraction,
-                            PointNetSetAbstractionMsg, _eval_only)
+                            PointNetSetAbstractionMsg, _eval_only, draw_fps_starts)
 
 
 def _ssg(npoint, radius, nsample, in_channel, mlp):
@@ -69,10 +69,22 @@ class _Net(nn.Module):
         return logp.view(B, N, -1), feat.view(B, N, -1).permute(0, 2, 1)
 
     def _encode(self, names, xyz, points):
-        """Run set-abstraction levels in order; returns the per-level (xyz, features) lists."""
+        """Run set-abstraction levels in order; returns the per-level (xyz, features) lists.
+        The FPS start indices of all sampling levels are drawn up front (same generator, same order as the
+        reference's per-level draws) so that they reach the device in one asynchronous copy."""
+        levels = [getattr(self, name) for name in names]
+        sizes, n = [], xyz.shape[2]
+        for lvl in levels:
+            if not getattr(lvl, "group_all", False):
+                sizes.append(n)
+                n = lvl.npoint
+        starts = iter(draw_fps_starts(xyz.shape[0], sizes, xyz.device))
         xs, fs = [xyz], [points]
-        for name in names:
-            x, f = getattr(self, name)(xs[-1], fs[-1])
+        for lvl in levels:
+            if getattr(lvl, "group_all", False):
+                x, f = lvl(xs[-1], fs[-1])
+            else:
+                x, f = lvl(xs[-1], fs[-1], start_idx=next(starts))
             xs.append(x)
             fs.append(f)
         return xs, fs

@@ -57,7 +57,9 @@ def farthest_point_sample(xyz: torch.Tensor, npoint: int, start_idx: Optional[to
         start_idx = torch.randint(0, N, (B,), dtype=torch.long)
     elif not start_idx.is_cuda and (int(start_idx.min()) < 0 or int(start_idx.max()) >= N):
         raise IndexError(f"start_idx out of range for N={N}")
-    return ops.fps(xyz, npoint, start_idx.to(xyz.device, non_blocking=True))
+    if not start_idx.is_cuda:
+        start_idx = start_idx.to(xyz.device, non_blocking=True)
+    return ops.fps(xyz, npoint, start_idx)
 
 
 def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
@@ -65,10 +67,18 @@ def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: to
     return ops.ball_query(radius, nsample, xyz, new_xyz)
 
 
+def draw_fps_starts(batch: int, level_sizes: Sequence[int], device) -> List[torch.Tensor]:
+    """All FPS start-index draws of one forward, made up front in call order on the CPU generator (the very
+    torch.randint calls of pointnet_util.py:75, so torch.manual_seed reproduces the reference), staged in one
+    pinned buffer and sent with a single asynchronous copy: the host never waits for the device mid-forward."""
+    draws = torch.stack([torch.randint(0, n, (batch,), dtype=torch.long) for n in level_sizes]).pin_memory()
+    return list(draws.to(device, non_blocking=True).unbind(0))
+
+
 def sample_and_group(npoint: int, radius: float, nsample: int, xyz: torch.Tensor, points: Optional[torch.Tensor],
-                     returnfps: bool = False):
+                     returnfps: bool = False, start_idx: Optional[torch.Tensor] = None):
     """-> new_xyz [B,npoint,3], new_points [B,npoint,nsample,3+D] (xyz relative to the centroid first)."""
-    fps_idx = farthest_point_sample(xyz, npoint)
+    fps_idx = farthest_point_sample(xyz, npoint, start_idx)
     new_xyz = ops.index_points(xyz, fps_idx)
     idx = ops.ball_query(radius, nsample, xyz, new_xyz)
     new_points = ops.group(xyz, points, new_xyz, idx, msg_order=False)
@@ -152,15 +162,17 @@ class PointNetSetAbstraction(nn.Module):
             c = width
         self._folded = FoldedLayers()
 
-    def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor]):
-        """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,C',S]."""
+    def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx: Optional[torch.Tensor] = None):
+        """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,C',S].
+        `start_idx` (extension): the FPS start indices, when the caller has already drawn them."""
         _eval_only(self)
         xyz_pm = xyz.permute(0, 2, 1)
         pts_pm = points.permute(0, 2, 1) if points is not None else None
         if self.group_all:
             new_xyz, grouped = sample_and_group_all(xyz_pm, pts_pm)
         else:
-            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_pm, pts_pm)
+            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_pm, pts_pm,
+                                                start_idx=start_idx)
         B, S, K, C = grouped.shape
         rows = _mlp_rows(grouped.view(B * S * K, C), self._folded.get(self.mlp_convs, self.mlp_bns))
         pooled = ops.group_max(rows, K).view(B, S, -1)
@@ -187,13 +199,13 @@ class PointNetSetAbstractionMsg(nn.Module):
             self.bn_blocks.append(bns)
         self._folded = [FoldedLayers() for _ in mlp_list]
 
-    def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor]):
+    def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx: Optional[torch.Tensor] = None):
         _eval_only(self)
         xyz_pm = xyz.permute(0, 2, 1)
         pts_pm = points.permute(0, 2, 1) if points is not None else None
         B = xyz_pm.shape[0]
         S = self.npoint
-        new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, S))
+        new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, S, start_idx))
         widths = [blk[-1].out_channels for blk in self.conv_blocks]
         out = torch.empty((B, S, sum(widths)), dtype=torch.float32, device=xyz.device)
         col = 0

@@ -89,7 +89,7 @@ def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor) -> torch.Tensor
     out = torch.empty((B, int(npoint)), dtype=torch.int64, device=xyz.device)
     with _on_device(xyz):
         nv.call("pn_fps_f32", xyz.data_ptr(), *xyz.stride(), B, N, int(npoint), start_idx.data_ptr(), out.data_ptr(),
-                _stream())
+                _stream(), tag=(B, N, int(npoint)))
     return out
 
 
