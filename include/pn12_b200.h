@@ -52,13 +52,16 @@ int pn_device_check(int* sm_count, int* cc_major, int* cc_minor);
  * CPU generator, then copied to the device); out_idx [B,npoint].
  * Distances are ((dx*dx + dy*dy) + dz*dz) in fp32 without fused multiply-add, running minimum,
  * arg-max with the lowest index winning ties -- bit-exact with the reference.
- * One thread-block cluster per cloud; coordinates and running distances stay in registers. */
+ * One thread-block cluster per cloud; coordinates and running distances stay in registers; the
+ * per-iteration arg-max is exchanged between the CTAs with st.async + mbarrier (no barrier in the loop).
+ * Limits: N <= 131072. */
 int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
                const int64_t* start_idx, int64_t* out_idx, pn_stream_t stream);
 
-/* Tuning hook for pn_fps_f32: force the cluster size (1,2,4,8,16) and threads per CTA (128..1024);
- * 0 = automatic.  Process-wide; meant for benchmarks and tests. */
-int pn_fps_set_config(int cluster_size, int threads);
+/* Tuning hook for pn_fps_f32: force the cluster size (1,2,4,8,16), threads per CTA (64..1024) and the
+ * intra-cluster exchange (1 = DSMEM store + barrier.cluster, 2 = st.async + mbarrier); 0 = automatic.
+ * Process-wide; meant for benchmarks and tests. */
+int pn_fps_set_config(int cluster_size, int threads, int exchange);
 
 /* square_distance (model/pointnet_util.py:19-40): out[b,i,j] = ((-2*dot) + |src_i|^2) + |dst_j|^2
  * with dot = fma(z,z', fma(y,y', x*x')), i.e. the fp32 rounding sequence of the reference's CPU path.

@@ -23,7 +23,7 @@ _SIGNATURES = {
     "pn_version": [],
     "pn_device_check": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
     "pn_fps_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp],
-    "pn_fps_set_config": [i32, i32],
+    "pn_fps_set_config": [i32, i32, i32],
     "pn_square_distance_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp],
     "pn_ball_query_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, vp],
     "pn_index_points_f32": [vp, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp],

@@ -12,6 +12,12 @@
 //      shared memory through DSMEM, one barrier.cluster, then all threads pick the cluster winner.
 // Slots are double-buffered by iteration parity so that one barrier per level and iteration is enough.
 //
+// fps_async_kernel (the default for clusters) removes both barriers from the loop: every WARP pushes its
+// own winner (distance bits, index, x, y, z = 20 bytes) straight into a slot of every CTA of the cluster with
+// st.async, whose completion is counted in bytes on the RECEIVER's mbarrier (complete_tx); each warp then
+// waits on its CTA's local mbarrier, reads the CL*NW slots (one or two per lane) and reduces them with the
+// same two-REDUX arg-max.  One-way DSMEM latency instead of store + barrier round trip, no __syncthreads.
+//
 // Bit-exactness: distance = ((dx*dx + dy*dy) + dz*dz) with explicit _rn intrinsics (no FMA
 // contraction), running min, ties resolved to the lowest point index -- as torch.max does on CPU.
 #include <cooperative_groups.h>
@@ -144,59 +150,201 @@ fps_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// st.async + mbarrier exchange
+struct __align__(32) FpsSlot {
+    unsigned val, idx;  // distance bits, point index
+    float x, y, z;
+    float pad[3];
+};
+constexpr int kMaxSlots = 64;
+constexpr int kSlotBytes = 20;  // bytes actually transmitted per slot (v4.b32 + b32)
+constexpr int kAsyncSmemHeader = 64 + 2 * kMaxSlots * (int)sizeof(FpsSlot);
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned map_to_cta(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+template <int NW, int PTS>
+__global__ void __launch_bounds__(NW * 32, 1)
+fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, int N, int npoint,
+                 const int64_t* __restrict__ start, int64_t* __restrict__ out, int chunk) {
+    constexpr int THREADS = NW * 32;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw);          // [2]
+    FpsSlot* slots = reinterpret_cast<FpsSlot*>(smem_raw + 64);                            // [2][kMaxSlots]
+    float* sx = reinterpret_cast<float*>(smem_raw + kAsyncSmemHeader);
+    float* sy = sx + chunk;
+    float* sz = sy + chunk;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CL = cluster.num_blocks();
+    const unsigned rank = cluster.block_rank();
+    const int nslot = (int)CL * NW;
+    const int b = blockIdx.x / CL;
+    const float* __restrict__ p = xyz + (int64_t)b * sB;
+    const int base = rank * chunk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    float x[PTS], y[PTS], z[PTS], d[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) {
+        const int li = tid + k * THREADS;
+        const int j = base + li;
+        const bool ok = li < chunk && j < N;
+        x[k] = ok ? p[(int64_t)j * sN] : 0.0f;
+        y[k] = ok ? p[(int64_t)j * sN + sC] : 0.0f;
+        z[k] = ok ? p[(int64_t)j * sN + 2 * sC] : 0.0f;
+        d[k] = ok ? 1e10f : -2.0f;
+        if (li < chunk) {
+            sx[li] = x[k];
+            sy[li] = y[k];
+            sz[li] = z[k];
+        }
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int far = (int)start[b];
+    far = min(max(far, 0), N - 1);
+    float cx = p[(int64_t)far * sN], cy = p[(int64_t)far * sN + sC], cz = p[(int64_t)far * sN + 2 * sC];
+    __syncthreads();
+    cluster.sync();  // barriers initialised and peers resident before any st.async
+
+    // remote addresses this lane sends to (lane < CL: CTA `lane`); parity 1 lives at a fixed offset
+    const unsigned my_slot = rank * NW + warp;
+    const unsigned dst_cta = lane < (int)CL ? lane : 0;
+    const unsigned r_slot0 = map_to_cta(smem_u32(&slots[my_slot]), dst_cta);
+    const unsigned r_bar0 = map_to_cta(smem_u32(&mbar[0]), dst_cta);
+    const unsigned l_bar0 = smem_u32(&mbar[0]);
+    constexpr unsigned kParSlotOff = kMaxSlots * sizeof(FpsSlot), kParBarOff = sizeof(unsigned long long);
+
+    int64_t* __restrict__ o = out + (int64_t)b * npoint;
+    for (int i = 0; i < npoint; ++i) {
+        const int par = i & 1;
+        if (rank == 0 && tid == 0) o[i] = far;
+        if (i == npoint - 1) break;  // the last arg-max would never be used
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_bar0 + par * kParBarOff),
+                         "r"((unsigned)(nslot * kSlotBytes))
+                         : "memory");
+        float bv = -1.0f;
+        int bk = 0;
+#pragma unroll
+        for (int k = 0; k < PTS; ++k) {
+            const float dd = sqdist_diff(x[k], y[k], z[k], cx, cy, cz);
+            d[k] = fminf(d[k], dd);
+            if (d[k] > bv) {
+                bv = d[k];
+                bk = k;
+            }
+        }
+        const unsigned vb = __float_as_uint(fmaxf(bv, 0.0f));
+        const unsigned gi = bv < 0.0f ? kNoIndex : (unsigned)(base + tid + bk * THREADS);
+        const unsigned wm = __reduce_max_sync(0xffffffffu, vb);
+        const unsigned wi = __reduce_min_sync(0xffffffffu, vb == wm ? gi : kNoIndex);
+        if (lane < (int)CL) {
+            const int li = wi == kNoIndex ? 0 : (int)wi - base;
+            const float mx = sx[li], my = sy[li], mz = sz[li];
+            const unsigned r_slot = r_slot0 + par * kParSlotOff, r_bar = r_bar0 + par * kParBarOff;
+            asm volatile(
+                "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                    r_slot),
+                "r"(wm), "r"(wi), "r"(__float_as_uint(mx)), "r"(__float_as_uint(my)), "r"(r_bar)
+                : "memory");
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
+                             r_slot + 16),
+                         "r"(__float_as_uint(mz)), "r"(r_bar)
+                         : "memory");
+        }
+        mbar_wait(l_bar0 + par * kParBarOff, (unsigned)((i >> 1) & 1));
+        // reduce the CL*NW slots: one or two per lane
+        unsigned sv = 0u, si = kNoIndex;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (lane < nslot) {
+            const FpsSlot& s0 = slots[par * kMaxSlots + lane];
+            sv = s0.val; si = s0.idx; px = s0.x; py = s0.y; pz = s0.z;
+        }
+        if (lane + 32 < nslot) {
+            const FpsSlot& s1 = slots[par * kMaxSlots + lane + 32];
+            if (s1.val > sv || (s1.val == sv && s1.idx < si)) {
+                sv = s1.val; si = s1.idx; px = s1.x; py = s1.y; pz = s1.z;
+            }
+        }
+        const unsigned bm = __reduce_max_sync(0xffffffffu, sv);
+        const unsigned bi = __reduce_min_sync(0xffffffffu, sv == bm ? si : kNoIndex);
+        const unsigned who = __ballot_sync(0xffffffffu, sv == bm && si == bi);
+        const int src = __ffs(who) - 1;
+        far = (int)bi;
+        cx = __shfl_sync(0xffffffffu, px, src);
+        cy = __shfl_sync(0xffffffffu, py, src);
+        cz = __shfl_sync(0xffffffffu, pz, src);
+    }
+    cluster.sync();  // nobody leaves while a peer may still be storing into its shared memory
+}
+
 static int g_force_cluster = 0;
 static int g_force_threads = 0;
+static int g_force_exchange = 0;  // 0 auto (st.async where possible), 1 barrier.cluster, 2 st.async
 
-template <int THREADS, int PTS>
-static int launch_fps(bool use_cluster, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N,
-                      int npoint, const int64_t* start, int64_t* out, int chunk, cudaStream_t stream) {
-    const size_t smem = (size_t)kFpsSmemHeader + (size_t)chunk * 3 * sizeof(float);
+template <typename Kern>
+static int launch_cluster_kernel(Kern kern, const char* what, int CL, int threads, size_t smem, const float* xyz, int64_t sB,
+                                 int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start, int64_t* out,
+                                 int chunk, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("pn_fps_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CL));
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    cudaError_t e;
-    if (use_cluster) {
-        auto kern = fps_kernel<THREADS, PTS, true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) {
-            set_error("pn_fps_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
+    if (CL > 1) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)CL;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, xyz, sB, sN, sC, N, npoint, start, out, chunk);
-    } else {
-        auto kern = fps_kernel<THREADS, PTS, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("pn_fps_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        e = cudaLaunchKernelEx(&cfg, kern, xyz, sB, sN, sC, N, npoint, start, out, chunk);
     }
+    e = cudaLaunchKernelEx(&cfg, kern, xyz, sB, sN, sC, N, npoint, start, out, chunk);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        set_error("pn_fps_f32: launch failed (cluster=%d threads=%d pts=%d smem=%zu): %s", CL, THREADS, PTS, smem,
+        set_error("pn_fps_f32: launch of %s failed (cluster=%d threads=%d smem=%zu): %s", what, CL, threads, smem,
                   cudaGetErrorString(e));
         return (int)e;
     }
     return PN_OK;
 }
 
+#define PN_FPS_ARGS xyz, sB, sN, sC, B, N, npoint, start, out, chunk, stream
+
 template <int THREADS>
-static int dispatch_pts(int pts, bool use_cluster, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B,
-                        int N, int npoint, const int64_t* start, int64_t* out, int chunk, cudaStream_t stream) {
-#define PN_FPS_CASE(P)                                                                                           \
-    if (pts <= P)                                                                                                \
-    return launch_fps<THREADS, P>(use_cluster, CL, xyz, sB, sN, sC, B, N, npoint, start, out, chunk, stream)
+static int dispatch_barrier(int pts, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+                            const int64_t* start, int64_t* out, int chunk, cudaStream_t stream) {
+    const size_t smem = (size_t)kFpsSmemHeader + (size_t)chunk * 3 * sizeof(float);
+#define PN_FPS_CASE(P)                                                                                              \
+    if (pts <= P)                                                                                                   \
+        return CL > 1 ? launch_cluster_kernel(fps_kernel<THREADS, P, true>, "fps_kernel", CL, THREADS, smem, PN_FPS_ARGS) \
+                      : launch_cluster_kernel(fps_kernel<THREADS, P, false>, "fps_kernel", CL, THREADS, smem, PN_FPS_ARGS)
     PN_FPS_CASE(1);
     PN_FPS_CASE(2);
     PN_FPS_CASE(4);
@@ -209,25 +357,45 @@ static int dispatch_pts(int pts, bool use_cluster, int CL, const float* xyz, int
     return PN_ERR_UNSUPPORTED;
 }
 
+template <int NW>
+static int dispatch_async(int pts, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+                          const int64_t* start, int64_t* out, int chunk, cudaStream_t stream) {
+    const size_t smem = (size_t)kAsyncSmemHeader + (size_t)chunk * 3 * sizeof(float);
+#define PN_FPS_CASE(P) \
+    if (pts <= P) return launch_cluster_kernel(fps_async_kernel<NW, P>, "fps_async_kernel", CL, NW * 32, smem, PN_FPS_ARGS)
+    PN_FPS_CASE(4);
+    PN_FPS_CASE(8);
+    PN_FPS_CASE(12);
+    PN_FPS_CASE(16);
+    PN_FPS_CASE(24);
+    PN_FPS_CASE(32);
+#undef PN_FPS_CASE
+    set_error("pn_fps_f32: %d points per thread at %d warps exceeds the register-resident limit", pts, NW);
+    return PN_ERR_UNSUPPORTED;
+}
+
 }  // namespace pn
 
-PN_EXPORT int pn_fps_set_config(int cluster_size, int threads) {
+PN_EXPORT int pn_fps_set_config(int cluster_size, int threads, int exchange) {
     const bool cl_ok = cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 ||
                        cluster_size == 8 || cluster_size == 16;
     const bool th_ok = threads == 0 || threads == 64 || threads == 128 || threads == 256 || threads == 512 ||
                        threads == 1024;
-    PN_REQUIRE(cl_ok && th_ok, PN_ERR_BAD_ARG, "pn_fps_set_config: cluster_size in {0,1,2,4,8,16}, threads in {0,64..1024}");
+    PN_REQUIRE(cl_ok && th_ok && exchange >= 0 && exchange <= 2, PN_ERR_BAD_ARG,
+               "pn_fps_set_config: cluster_size in {0,1,2,4,8,16}, threads in {0,64..1024}, exchange in {0,1,2}");
     pn::g_force_cluster = cluster_size;
     pn::g_force_threads = threads;
+    pn::g_force_exchange = exchange;
     return PN_OK;
 }
 
 PN_EXPORT int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
-                         const int64_t* start_idx, int64_t* out_idx, pn_stream_t stream) {
+                         const int64_t* start, int64_t* out, pn_stream_t stream_) {
     using namespace pn;
-    PN_REQUIRE(xyz && start_idx && out_idx, PN_ERR_BAD_ARG, "pn_fps_f32: null pointer");
+    PN_REQUIRE(xyz && start && out, PN_ERR_BAD_ARG, "pn_fps_f32: null pointer");
     PN_REQUIRE(B > 0 && N > 0 && npoint > 0, PN_ERR_BAD_ARG, "pn_fps_f32: B, N, npoint must be positive (got %d, %d, %d)", B,
                N, npoint);
+    cudaStream_t stream = (cudaStream_t)stream_;
     int CL = g_force_cluster;
     if (CL == 0) {
         if (N <= 3072) CL = 1;
@@ -236,19 +404,40 @@ PN_EXPORT int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, i
         else if (N <= 24576) CL = 8;
         else CL = 16;
     }
-    int threads = g_force_threads;
-    if (threads == 0) threads = N <= 128 ? 64 : N <= 512 ? 128 : N <= 2048 ? 256 : 512;
     const int chunk = (int)ceil_div(N, CL);
+    // st.async exchange: clusters only, at most 64 slots (cluster size x warps) and 32 points per thread
+    bool use_async = CL > 1 && g_force_exchange != 1;
+    int threads = g_force_threads;
+    if (use_async) {
+        if (threads == 0) threads = (chunk <= 4096 && CL * 4 <= kMaxSlots) ? 128 : 256;
+        const int nw = threads / 32;
+        if (threads > 256 || CL * nw > kMaxSlots || ceil_div(chunk, threads) > 32) {
+            PN_REQUIRE(g_force_exchange != 2, PN_ERR_UNSUPPORTED,
+                       "pn_fps_f32: st.async exchange needs cluster*warps <= 64, threads <= 256 and <= 32 points per thread "
+                       "(N=%d cluster=%d threads=%d)", N, CL, threads);
+            use_async = false;
+            threads = g_force_threads;
+        }
+    }
+    if (use_async) {
+        const int pts = (int)ceil_div(chunk, threads);
+        PN_REQUIRE((size_t)kAsyncSmemHeader + (size_t)chunk * 12 <= 227 * 1024, PN_ERR_UNSUPPORTED,
+                   "pn_fps_f32: N=%d needs %d points per CTA at cluster size %d; shared memory holds 19000", N, chunk, CL);
+        switch (threads) {
+            case 64: return dispatch_async<2>(pts, CL, PN_FPS_ARGS);
+            case 128: return dispatch_async<4>(pts, CL, PN_FPS_ARGS);
+            default: return dispatch_async<8>(pts, CL, PN_FPS_ARGS);
+        }
+    }
+    if (threads == 0) threads = N <= 128 ? 64 : N <= 512 ? 128 : N <= 2048 ? 256 : 512;
     const int pts = (int)ceil_div(chunk, threads);
     PN_REQUIRE((size_t)kFpsSmemHeader + (size_t)chunk * 12 <= 227 * 1024, PN_ERR_UNSUPPORTED,
                "pn_fps_f32: N=%d needs %d points per CTA at cluster size %d; shared memory holds 19200", N, chunk, CL);
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool uc = CL > 1;
     switch (threads) {
-        case 64: return dispatch_pts<64>(pts, uc, CL, xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, chunk, st);
-        case 128: return dispatch_pts<128>(pts, uc, CL, xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, chunk, st);
-        case 256: return dispatch_pts<256>(pts, uc, CL, xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, chunk, st);
-        case 512: return dispatch_pts<512>(pts, uc, CL, xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, chunk, st);
-        default: return dispatch_pts<1024>(pts, uc, CL, xyz, sB, sN, sC, B, N, npoint, start_idx, out_idx, chunk, st);
+        case 64: return dispatch_barrier<64>(pts, CL, PN_FPS_ARGS);
+        case 128: return dispatch_barrier<128>(pts, CL, PN_FPS_ARGS);
+        case 256: return dispatch_barrier<256>(pts, CL, PN_FPS_ARGS);
+        case 512: return dispatch_barrier<512>(pts, CL, PN_FPS_ARGS);
+        default: return dispatch_barrier<1024>(pts, CL, PN_FPS_ARGS);
     }
 }

@@ -66,9 +66,13 @@ def test_fps_vs_oracle(dev, N, npoint, B):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("cluster,threads", [(1, 1024), (2, 512), (4, 256), (8, 128), (8, 512), (16, 128), (16, 256)])
-def test_fps_every_cluster_shape(dev, cluster, threads):
-    """Every cluster size / CTA width gives the same (bit-exact) answer."""
+@pytest.mark.parametrize("cluster,threads,exchange", [(1, 1024, 0), (2, 512, 1), (4, 256, 1), (8, 128, 1), (8, 512, 1),
+                                                      (16, 128, 1), (16, 256, 1), (2, 128, 2), (2, 256, 2), (4, 64, 2),
+                                                      (4, 128, 2), (8, 64, 2), (8, 128, 2), (8, 256, 2), (16, 64, 2),
+                                                      (16, 128, 2)])
+def test_fps_every_cluster_shape(dev, cluster, threads, exchange):
+    """Every cluster size / CTA width / exchange mechanism (barrier.cluster or st.async + mbarrier) gives the
+    same (bit-exact) answer."""
     from pointnet12_b200 import ops
 
     N, npoint, B = 8000, 128, 3
@@ -76,11 +80,11 @@ def test_fps_every_cluster_shape(dev, cluster, threads):
     st = starts([N], B, seed=11)[0]
     want = orc.farthest_point_sample(pts.transpose(0, 2, 1)[:, :, :3], npoint, st.numpy())
     try:
-        ops.fps_set_config(cluster, threads)
+        ops.fps_set_config(cluster, threads, exchange)
         got = ops.fps(views(cuda(pts, dev))[0], npoint, st.to(dev))
         torch.cuda.synchronize()
     finally:
-        ops.fps_set_config(0, 0)
+        ops.fps_set_config(0, 0, 0)
     assert np.array_equal(got.cpu().numpy(), want)
 
 

@@ -63,18 +63,19 @@ def main():
         pts = torch.from_numpy(syn.kitti_batch(B, N, config=2)).to(dev)
         xyz = pts.permute(0, 2, 1)[:, :, :3]
         start = torch.zeros(B, dtype=torch.long, device=dev)
-        for cl in (2, 4, 8, 16):
-            for th in (128, 256, 512, 1024):
+        for ex, cl, th in [(1, 8, 256), (1, 8, 512), (2, 4, 128), (2, 4, 256), (2, 8, 64), (2, 8, 128), (2, 8, 256),
+                           (2, 16, 64), (2, 16, 128)]:
+            if True:
                 try:
-                    ops.fps_set_config(cl, th)
+                    ops.fps_set_config(cl, th, ex)
                     t = time_ms(lambda: ops.fps(xyz, npoint, start))
-                    print(json.dumps(dict(sweep="fps", cluster=cl, threads=th, ms=round(t, 4),
+                    print(json.dumps(dict(sweep="fps", exchange=ex, cluster=cl, threads=th, ms=round(t, 4),
                                           us_per_iter=round(t * 1000 / npoint, 3),
                                           gbs=round(B * npoint * N * 16 / t / 1e6, 1))), flush=True)
                 except RuntimeError as e:
                     print(json.dumps(dict(sweep="fps", cluster=cl, threads=th, error=str(e)[:100])), flush=True)
                 finally:
-                    ops.fps_set_config(0, 0)
+                    ops.fps_set_config(0, 0, 0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w") as f:
         json.dump(out, f, indent=1)
