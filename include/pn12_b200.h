@@ -126,6 +126,55 @@ int pn_three_interpolate_f32(const float* points1, int64_t p1B, int64_t p1N, int
 int pn_log_softmax_f32(const float* x, int64_t ldx, int64_t rows, int C, float* y, int64_t ldy,
                        pn_stream_t stream);
 
+/* ---- fused shared-MLP chains on the tensor cores (tcgen05 + TMEM), fp32 parity by 3-pass split bf16 ----
+ * A chain is up to PN_MLP_MAX_LAYERS layers  y = act(x * w^T + bias)  with BatchNorm already folded into
+ * (w, bias); relu[l] selects the activation.  Hidden layers are limited to 256 channels, the last layer to 1024.
+ * The weights are pre-packed once (pn_mlp_pack_bf16x3) into a device blob of pn_mlp_blob_bytes() bytes:
+ * per layer the bf16 hi and lo images in the UMMA shared-memory layout, then the fp32 bias table.
+ * Products are computed as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation (relative error ~1e-5). */
+#define PN_MLP_MAX_LAYERS 6
+typedef struct pn_mlp_desc {
+    int nlayers;
+    int cin[PN_MLP_MAX_LAYERS];
+    int cout[PN_MLP_MAX_LAYERS];
+    int relu[PN_MLP_MAX_LAYERS];
+} pn_mlp_desc;
+
+/* Size of the packed blob; 0 (and an error string) if the chain is not supported. */
+size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc);
+/* w[l]: device pointer to [cout[l], cin[l]] row-major fp32; bias[l]: device pointer or NULL.  The arrays w and
+ * bias themselves live in HOST memory.  blob: 128-byte aligned device buffer. */
+int pn_mlp_pack_bf16x3(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, void* blob,
+                       pn_stream_t stream);
+
+/* Output modes of the fused chains. */
+enum pn_mlp_out { PN_MLP_OUT_ROWS = 0, PN_MLP_OUT_MAX32 = 1, PN_MLP_OUT_LOG_SOFTMAX = 2 };
+
+/* Plain rows: y = chain(x) for x [rows, cin[0]] (leading dimension ldx).  out_mode ROWS: y [rows, cout];
+ * MAX32: y [rows/32, cout] = max over each run of 32 rows; LOG_SOFTMAX: y [rows, cout] log-probabilities.
+ * (The per-point conv chains of model/pointnet.py.) */
+int pn_mlp_rows_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* x, int64_t ldx, int64_t rows,
+                       int out_mode, float* y, int64_t ldy, pn_stream_t stream);
+
+/* One whole set-abstraction level after sampling (model/pointnet_util.py:127-131 + :194-199, or the MSG
+ * branch :243-256 with msg_order = 1): gather + recentre + concat straight into the tensor-core operand,
+ * the conv+BN+ReLU chain, and the max over the nsample (= 32) rows of each group.
+ * out [B*S, cout_last] rows with leading dimension ldo.  Arguments as pn_group_f32. */
+int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
+                         int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
+                         const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
+                         int S, int K, int msg_order, float* out, int64_t ldo, pn_stream_t stream);
+
+/* One feature-propagation level after the 3-NN search (model/pointnet_util.py:301-312): weighted gather of
+ * the three coarse rows + skip concat straight into the tensor-core operand, then the conv+BN+ReLU chain.
+ * With out_mode LOG_SOFTMAX and the segmentation head appended to the chain (pointnet2.py:172-175) the
+ * log-probabilities [B, N, classes] are written directly.  out rows (b, n) have leading dimension ldo and
+ * must be contiguous over the batch.  Arguments as pn_three_interpolate_f32. */
+int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
+                     int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2, int S,
+                     const int64_t* idx, const float* weight, int B, int N, int out_mode, float* out, int64_t ldo,
+                     pn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,17 @@ _lib = None
 
 vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
 
+MLP_MAX_LAYERS = 6
+
+
+class MlpDesc(C.Structure):
+    """pn_mlp_desc of include/pn12_b200.h."""
+    _fields_ = [("nlayers", C.c_int), ("cin", C.c_int * MLP_MAX_LAYERS), ("cout", C.c_int * MLP_MAX_LAYERS),
+                ("relu", C.c_int * MLP_MAX_LAYERS)]
+
+
+_descp = C.POINTER(MlpDesc)
+
 # name -> argtypes, mirroring include/pn12_b200.h
 _SIGNATURES = {
     "pn_version": [],
@@ -35,6 +46,12 @@ _SIGNATURES = {
     "pn_three_interpolate_f32": [vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, i32, vp, i64, i64,
                                  vp],
     "pn_log_softmax_f32": [vp, i64, i64, i32, vp, i64, vp],
+    "pn_mlp_pack_bf16x3": [_descp, C.POINTER(vp), C.POINTER(vp), vp, vp],
+    "pn_mlp_rows_bf16x3": [_descp, vp, vp, i64, i64, i32, vp, i64, vp],
+    "pn_sa_mlp_max_bf16x3": [_descp, vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32,
+                             i32, i32, vp, i64, vp],
+    "pn_fp_mlp_bf16x3": [_descp, vp, vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, i32, i32, vp, i64,
+                         vp],
 }
 
 
@@ -61,6 +78,8 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = i32
+        handle.pn_mlp_blob_bytes.argtypes = [_descp]
+        handle.pn_mlp_blob_bytes.restype = C.c_size_t
         _lib = handle
     return _lib
 

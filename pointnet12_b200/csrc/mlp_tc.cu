@@ -1,0 +1,700 @@
+// mlp_tc.cu -- fused shared-MLP chains on the 5th-generation tensor cores (tcgen05 + TMEM), fp32 parity
+// through a 3-pass split-bf16 product ("bf16x3": a = a_hi + a_lo, w = w_hi + w_lo, a*w ~ a_hi*w_hi + a_hi*w_lo +
+// a_lo*w_hi with fp32 accumulation in TMEM; the dropped a_lo*w_lo term is ~2^-18 relative).
+//
+// One kernel runs a whole chain  rows -> [linear + bias (+ReLU)] x L -> {rows | max over groups | log_softmax}
+// for a tile of 128 rows (points) per CTA:
+//   reference                                                   here
+//   gather + recentre + concat   pointnet_util.py:127-131,:243-247   producer: each thread builds ITS row
+//   3-NN interpolate + concat    pointnet_util.py:301-307            producer: weighted gather of 3 coarse rows
+//   conv1x1 + BN + ReLU chain    pointnet_util.py:195-197,:310-312   tcgen05.mma, BN folded into W and bias
+//   max over nsample             pointnet_util.py:199                warp REDUX over the 32 rows of a group
+//   conv2 + log_softmax          pointnet2.py:172-175                in-thread over the row's classes
+//
+// Orientation: D[128 rows x N channels] = A[128 rows x K] * W[N x K]^T.  TMEM lanes are rows (thread t owns row t
+// of the tile), TMEM columns are channels.  The activations NEVER touch shared memory: a layer's accumulator is
+// read back with tcgen05.ld by the thread that owns the row, gets bias + ReLU, is split into bf16 hi/lo, packed two
+// per 32-bit cell and written with tcgen05.st into the TMEM region the next layer's MMAs read their A operand
+// from (tcgen05.mma with A in TMEM).  Shared memory only holds weight tiles: pre-packed on the device into the
+// exact UMMA K-major core-matrix image (8 rows x 16 bytes, no swizzle), streamed per 64-wide K slice with one
+// cp.async.bulk (TMA engine) each into a 2-stage ring, completion on mbarriers (complete_tx), stage release by
+// tcgen05.commit.  Conventions (descriptor fields, A packing, TMEM addressing) were pinned on hardware with
+// tools/probes/tc_probe.cu.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace pn {
+
+constexpr int kTcThreads = 128;
+constexpr int kTcMaxLayers = PN_MLP_MAX_LAYERS;
+constexpr int kTcKSub = 64;     // K values per streamed weight slice
+constexpr int kTcAChunk = 256;  // K values resident in TMEM as the A operand (128 columns hi + 128 columns lo)
+constexpr int kTcNPass = 256;   // output channels per accumulation pass (TMEM D columns)
+
+struct TcLayer {
+    int k_real, k_pad, n_real, n_pad, relu;
+    unsigned w_off;  // byte offset of the layer's weight images in the blob
+    unsigned b_off;  // float offset of the layer's bias in the bias table
+};
+struct TcChain {
+    int nlayers, stage_bytes, tmem_cols, x_cols, a_lo_off, bias_floats;
+    unsigned bias_off;  // byte offset of the bias table in the blob
+    unsigned blob_bytes;
+    TcLayer L[kTcMaxLayers];
+};
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Plans the chain: padded sizes, blob layout, TMEM columns, ring stage size.  Returns false if unsupported.
+static bool plan_chain(const pn_mlp_desc* d, TcChain* c, const char** why) {
+    *why = "";
+    if (!d || d->nlayers < 1 || d->nlayers > kTcMaxLayers) { *why = "nlayers must be in [1, 6]"; return false; }
+    c->nlayers = d->nlayers;
+    unsigned off = 0;
+    int bias_floats = 0, stage = 0, x_cols = 0, a_k = 0;
+    for (int l = 0; l < d->nlayers; ++l) {
+        TcLayer& L = c->L[l];
+        if (d->cin[l] < 1 || d->cout[l] < 1) { *why = "channel counts must be positive"; return false; }
+        if (l > 0 && d->cin[l] != d->cout[l - 1]) { *why = "cin[l] must equal cout[l-1]"; return false; }
+        L.k_real = d->cin[l];
+        L.n_real = d->cout[l];
+        L.relu = d->relu[l];
+        L.n_pad = round_up(L.n_real, 32);
+        L.k_pad = l == 0 ? round_up(L.k_real, 32) : c->L[l - 1].n_pad;
+        if (l + 1 < d->nlayers && L.n_pad > kTcNPass) { *why = "hidden layers are limited to 256 channels"; return false; }
+        if (L.n_pad > 1024 || L.k_pad > 4096) { *why = "layer too wide"; return false; }
+        L.w_off = off;
+        off += (unsigned)L.n_pad * (unsigned)L.k_pad * 4u;  // hi + lo bf16 images
+        L.b_off = (unsigned)bias_floats;
+        bias_floats += L.n_pad;
+        const int rows_p = L.n_pad < kTcNPass ? L.n_pad : kTcNPass;
+        const int kw = L.k_pad < kTcKSub ? L.k_pad : kTcKSub;
+        stage = stage > rows_p * kw * 4 ? stage : rows_p * kw * 4;
+        x_cols = x_cols > rows_p ? x_cols : rows_p;
+        const int ak = L.k_pad < kTcAChunk ? L.k_pad : kTcAChunk;
+        a_k = a_k > ak ? a_k : ak;
+    }
+    c->bias_off = off;
+    c->bias_floats = bias_floats;
+    c->blob_bytes = off + (unsigned)bias_floats * 4u;
+    c->stage_bytes = stage;
+    c->x_cols = x_cols;
+    c->a_lo_off = a_k / 2;
+    int cols = x_cols + a_k, p2 = 32;
+    while (p2 < cols) p2 <<= 1;
+    if (p2 > 512) { *why = "chain needs more than 512 TMEM columns"; return false; }
+    c->tmem_cols = p2;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+// Weight image of one (pass, K slice): element (n, k) at (n/8)*SBO + (k/8)*128 + (n%8)*16 + (k%8)*2 bytes,
+// SBO = (kw/8)*128; hi image first, lo image right after it.
+__global__ void tc_pack_layer_kernel(const float* __restrict__ w, const float* __restrict__ bias, int k_real, int k_pad,
+                                     int n_real, int n_pad, unsigned char* __restrict__ img, float* __restrict__ bias_out) {
+    const int total = n_pad * k_pad;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int n = e / k_pad, k = e % k_pad;
+        const float v = (n < n_real && k < k_real) ? w[(size_t)n * k_real + k] : 0.0f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int p = n / kTcNPass, np = n % kTcNPass;
+        const int rows_p = min(kTcNPass, n_pad - p * kTcNPass);
+        const int s = k / kTcKSub, ks = k % kTcKSub;
+        const int kw = min(kTcKSub, k_pad - s * kTcKSub);
+        // offset of (pass p, slice s): passes are [rows_p x k_pad] blocks, slices inside a pass are consecutive
+        size_t off = (size_t)p * kTcNPass * k_pad * 4 + (size_t)rows_p * (s * kTcKSub) * 4;
+        const size_t in_img = (size_t)(np / 8) * (kw / 8) * 128 + (size_t)(ks / 8) * 128 + (np % 8) * 16 + (ks % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(img + off + in_img) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(img + off + (size_t)rows_p * kw * 2 + in_img) = lo;
+    }
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_pad; n += gridDim.x * blockDim.x)
+        bias_out[n] = (bias && n < n_real) ? bias[n] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ unsigned tc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_st16(unsigned taddr, const unsigned (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                 "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+// 32 fp32 values -> 16 packed bf16x2 "hi" words + 16 "lo" words (even k in the low half), stored at column c of both regions
+__device__ __forceinline__ void tc_store_split32(unsigned t_hi, unsigned t_lo, const float (&v)[32]) {
+    unsigned hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+        hi[j] = (unsigned)__bfloat16_as_ushort(h0) | ((unsigned)__bfloat16_as_ushort(h1) << 16);
+        lo[j] = (unsigned)__bfloat16_as_ushort(l0) | ((unsigned)__bfloat16_as_ushort(l1) << 16);
+    }
+    tc_st16(t_hi, hi);
+    tc_st16(t_lo, lo);
+}
+// order-preserving float <-> uint key (for REDUX max over possibly negative values)
+__device__ __forceinline__ unsigned tc_key(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float tc_unkey(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// ------------------------------------------------------------------------------------------------ row producers
+enum { TC_IN_ROWS = 0, TC_IN_SA = 1, TC_IN_FP = 2 };
+enum { TC_OUT_ROWS = 0, TC_OUT_MAX = 1, TC_OUT_LOGSOFTMAX = 2 };
+
+struct TcIo {
+    // rows are organised in `nseg` segments of `seg_rows` rows; a tile never straddles two segments
+    int64_t nseg, seg_rows;
+    // TC_IN_ROWS
+    const float* x; int64_t ldx;
+    // TC_IN_SA: row = (b, s, k)
+    const float* xyz; int64_t xB, xN, xC;
+    const float* feat; int64_t fB, fN, fC; int D;
+    const float* qxyz; int64_t qB, qN, qC;
+    const int64_t* idx; int N, S, K, msg_order;
+    // TC_IN_FP: row = (b, n)
+    const float* p1; int64_t p1B, p1N, p1C; int D1;
+    const float* p2; int64_t p2B, p2N, p2C; int D2; int S2;
+    const int64_t* idx3; const float* w3;
+    // output
+    int out_mode; float* y; int64_t ldy; int group;
+};
+
+template <int IN>
+struct RowCtx {
+    bool valid;
+    int64_t row;      // global row index
+    // SA
+    const float* xyz_j; const float* feat_j; float cx, cy, cz;
+    // FP
+    const float* p1row; const float* r0; const float* r1; const float* r2; float w0, w1, w2;
+    // ROWS
+    const float* xrow;
+};
+
+template <int IN>
+__device__ __forceinline__ void row_setup(const TcIo& io, RowCtx<IN>& c) {
+    if (!c.valid) return;
+    if constexpr (IN == TC_IN_ROWS) {
+        c.xrow = io.x + c.row * io.ldx;
+    } else if constexpr (IN == TC_IN_SA) {
+        const int64_t bs = c.row / io.K;
+        const int64_t b = bs / io.S, s = bs % io.S;
+        int64_t j = io.idx[c.row];
+        j = j < 0 ? 0 : (j >= io.N ? io.N - 1 : j);
+        c.xyz_j = io.xyz + b * io.xB + j * io.xN;
+        c.feat_j = io.feat ? io.feat + b * io.fB + j * io.fN : nullptr;
+        const float* q = io.qxyz + b * io.qB + s * io.qN;
+        c.cx = q[0];
+        c.cy = q[io.qC];
+        c.cz = q[2 * io.qC];
+    } else {
+        const int64_t b = c.row / io.seg_rows, n = c.row % io.seg_rows;
+        c.p1row = io.p1 ? io.p1 + b * io.p1B + n * io.p1N : nullptr;
+        int64_t j0 = io.idx3[c.row * 3], j1 = io.idx3[c.row * 3 + 1], j2 = io.idx3[c.row * 3 + 2];
+        const int64_t hi = io.S2 - 1;
+        j0 = j0 < 0 ? 0 : (j0 > hi ? hi : j0);
+        j1 = j1 < 0 ? 0 : (j1 > hi ? hi : j1);
+        j2 = j2 < 0 ? 0 : (j2 > hi ? hi : j2);
+        c.r0 = io.p2 + b * io.p2B + j0 * io.p2N;
+        c.r1 = io.p2 + b * io.p2B + j1 * io.p2N;
+        c.r2 = io.p2 + b * io.p2B + j2 * io.p2N;
+        c.w0 = io.w3[c.row * 3];
+        c.w1 = io.w3[c.row * 3 + 1];
+        c.w2 = io.w3[c.row * 3 + 2];
+    }
+}
+
+// value of input channel k of this thread's row (0 beyond the real channels / rows)
+template <int IN>
+__device__ __forceinline__ float row_value(const TcIo& io, const RowCtx<IN>& c, int k, int k_real) {
+    if (!c.valid || k >= k_real) return 0.0f;
+    if constexpr (IN == TC_IN_ROWS) {
+        return c.xrow[k];
+    } else if constexpr (IN == TC_IN_SA) {
+        const int kx = io.msg_order ? k - io.D : k;   // channel inside the recentred-xyz block if 0 <= kx < 3
+        if (kx >= 0 && kx < 3) {
+            const float p = c.xyz_j[kx * io.xC];
+            return __fsub_rn(p, kx == 0 ? c.cx : (kx == 1 ? c.cy : c.cz));
+        }
+        return c.feat_j[(io.msg_order ? k : k - 3) * io.fC];
+    } else {
+        if (k < io.D1) return c.p1row[k * io.p1C];
+        const int d = k - io.D1;
+        return __fadd_rn(__fadd_rn(__fmul_rn(c.r0[d * io.p2C], c.w0), __fmul_rn(c.r1[d * io.p2C], c.w1)),
+                         __fmul_rn(c.r2[d * io.p2C], c.w2));
+    }
+}
+
+// 32 consecutive input channels starting at k0 (vectorised fast paths for contiguous rows)
+template <int IN>
+__device__ __forceinline__ void row_load32(const TcIo& io, const RowCtx<IN>& c, int k0, int k_real, float (&v)[32]) {
+    if constexpr (IN == TC_IN_ROWS) {
+        if (c.valid && k0 + 32 <= k_real && ((reinterpret_cast<uintptr_t>(c.xrow + k0) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(c.xrow + k0 + 4 * j);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            return;
+        }
+    }
+    if constexpr (IN == TC_IN_FP) {
+        const int d0 = k0 - io.D1;
+        if (c.valid && d0 >= 0 && k0 + 32 <= k_real && io.p2C == 1 &&
+            (((reinterpret_cast<uintptr_t>(c.r0 + d0) | reinterpret_cast<uintptr_t>(c.r1 + d0) |
+               reinterpret_cast<uintptr_t>(c.r2 + d0)) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 a = *reinterpret_cast<const float4*>(c.r0 + d0 + 4 * j);
+                const float4 b = *reinterpret_cast<const float4*>(c.r1 + d0 + 4 * j);
+                const float4 e = *reinterpret_cast<const float4*>(c.r2 + d0 + 4 * j);
+                v[4 * j] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, c.w0), __fmul_rn(b.x, c.w1)), __fmul_rn(e.x, c.w2));
+                v[4 * j + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, c.w0), __fmul_rn(b.y, c.w1)), __fmul_rn(e.y, c.w2));
+                v[4 * j + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, c.w0), __fmul_rn(b.z, c.w1)), __fmul_rn(e.z, c.w2));
+                v[4 * j + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a.w, c.w0), __fmul_rn(b.w, c.w1)), __fmul_rn(e.w, c.w2));
+            }
+            return;
+        }
+        if (c.valid && k0 + 32 <= io.D1 && io.p1C == 1 && ((reinterpret_cast<uintptr_t>(c.p1row + k0) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(c.p1row + k0 + 4 * j);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            return;
+        }
+    }
+    if constexpr (IN == TC_IN_SA) {
+        const int f0 = io.msg_order ? k0 : k0 - 3;   // first feature channel covered if the block is all features
+        const bool all_feat = io.msg_order ? (k0 + 32 <= io.D) : (k0 >= 3 && k0 + 32 <= k_real);
+        if (c.valid && all_feat && io.fC == 1 && ((reinterpret_cast<uintptr_t>(c.feat_j + f0) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(c.feat_j + f0 + 4 * j);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = row_value<IN>(io, c, k0 + j, k_real);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int IN>
+__global__ void __launch_bounds__(kTcThreads)
+mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restrict__ blob, const __grid_constant__ TcIo io) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // layout: [stage 0][stage 1][bias table][barriers: full0 full1 empty0 empty1 done][tmem ptr]
+    float* sbias = reinterpret_cast<float*>(smem + 2 * ch.stage_bytes);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 2 * ch.stage_bytes + ((ch.bias_floats * 4 + 15) & ~15));
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 5);
+    const unsigned bar_full0 = tc_smem_u32(&bars[0]), bar_empty0 = tc_smem_u32(&bars[2]);   // stage 1: + 8 bytes
+    const unsigned bar_done = tc_smem_u32(&bars[4]);
+    const unsigned stage0 = tc_smem_u32(smem);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(ch.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        tc_mbar_init(bar_full0, 1);
+        tc_mbar_init(bar_full0 + 8, 1);
+        tc_mbar_init(bar_empty0, 1);
+        tc_mbar_init(bar_empty0 + 8, 1);
+        tc_mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const float* gb = reinterpret_cast<const float*>(blob + ch.bias_off);
+        for (int i = tid; i < ch.bias_floats; i += kTcThreads) sbias[i] = gb[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tbase = *tmem_slot;
+    const unsigned tlane = tbase + ((unsigned)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const unsigned t_x = tlane;                                      // accumulator columns
+    const unsigned t_ahi = tlane + ch.x_cols, t_alo = t_ahi + ch.a_lo_off;
+    const unsigned a_hi_col = tbase + ch.x_cols, a_lo_col = a_hi_col + ch.a_lo_off;   // lane 0 addresses for the MMA
+
+    unsigned fill = 0, use = 0, done_phase = 0;   // ring / barrier bookkeeping (fill, use: thread 0 only)
+
+    const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
+    const int64_t ntiles = io.nseg * tiles_per_seg;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t seg = tile / tiles_per_seg;
+        const int64_t r_in_seg = (tile % tiles_per_seg) * 128 + tid;
+        RowCtx<IN> rc;
+        rc.valid = r_in_seg < io.seg_rows;
+        rc.row = seg * io.seg_rows + r_in_seg;
+        row_setup<IN>(io, rc);
+
+        for (int l = 0; l < ch.nlayers; ++l) {
+            const TcLayer& L = ch.L[l];
+            const bool last = l + 1 == ch.nlayers;
+            const int npass = (L.n_pad + kTcNPass - 1) / kTcNPass;
+            const int nchunk = (L.k_pad + kTcAChunk - 1) / kTcAChunk;   // > 1 only for a wide first layer
+            for (int p = 0; p < npass; ++p) {
+                const int rows_p = min(kTcNPass, L.n_pad - p * kTcNPass);
+                for (int a = 0; a < nchunk; ++a) {
+                    const int kbase = a * kTcAChunk;
+                    const int kchunk = min(kTcAChunk, L.k_pad - kbase);
+                    if (l == 0) {
+                        // ---- producer: this thread's row, channels [kbase, kbase + kchunk) -> TMEM A region
+                        for (int k0 = 0; k0 < kchunk; k0 += 32) {
+                            float v[32];
+                            row_load32<IN>(io, rc, kbase + k0, L.k_real, v);
+                            tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
+                        }
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncthreads();
+                    }
+                    if (warp == 0) {
+                      if (lane == 0) {
+                        tc_fence_after();
+                        // ---- weight slices of this chunk: 2-stage ring, MMAs issued as slices land
+                        const int s0 = kbase / kTcKSub, ns = (kchunk + kTcKSub - 1) / kTcKSub;
+                        const unsigned char* wpass = blob + L.w_off + (size_t)p * kTcNPass * L.k_pad * 4;
+                        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(rows_p >> 3) << 17) | (8u << 24);
+                        auto issue_copy = [&](int s) {
+                            const int kw = min(kTcKSub, L.k_pad - s * kTcKSub);
+                            const unsigned bytes = (unsigned)rows_p * kw * 4;
+                            const unsigned st = fill & 1;
+                            tc_mbar_wait(bar_empty0 + 8 * st, ((fill >> 1) & 1) ^ 1);
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full0 + 8 * st), "r"(bytes) : "memory");
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                    stage0 + st * (unsigned)ch.stage_bytes),
+                                "l"(wpass + (size_t)rows_p * (s * kTcKSub) * 4), "r"(bytes), "r"(bar_full0 + 8 * st)
+                                : "memory");
+                            ++fill;
+                        };
+                        const int pre = ns < 2 ? ns : 2;
+                        for (int s = 0; s < pre; ++s) issue_copy(s0 + s);
+                        for (int s = 0; s < ns; ++s) {
+                            const int kw = min(kTcKSub, L.k_pad - (s0 + s) * kTcKSub);
+                            const unsigned st = use & 1;
+                            tc_mbar_wait(bar_full0 + 8 * st, (use >> 1) & 1);
+                            tc_fence_after();
+                            const unsigned b_hi = stage0 + st * (unsigned)ch.stage_bytes, b_lo = b_hi + (unsigned)rows_p * kw * 2;
+                            const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
+                                                             ((unsigned long long)((((unsigned)kw / 8) * 128u >> 4) & 0x3FFF) << 32) |
+                                                             (1ull << 46);
+                            for (int t = 0; t < kw / 16; ++t) {
+                                const unsigned kcol = (unsigned)(s * kTcKSub + t * 16) / 2;   // A columns of this K step
+                                const unsigned long long dh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
+                                const unsigned long long dl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
+                                const unsigned acc0 = (a > 0 || s > 0 || t > 0) ? 1u : 0u;
+                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                 tbase),
+                                             "r"(a_hi_col + kcol), "l"(dh), "r"(idesc), "r"(acc0)
+                                             : "memory");
+                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                 tbase),
+                                             "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
+                                             : "memory");
+                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                 tbase),
+                                             "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
+                                             : "memory");
+                            }
+                            tc_commit(bar_empty0 + 8 * st);
+                            ++use;
+                            if (s + 2 < ns) issue_copy(s0 + s + 2);
+                        }
+                        tc_commit(bar_done);
+                      }
+                      __syncwarp();   // lanes 1-31 park here (no spinning) while lane 0 feeds the tensor core
+                    }
+                    // ---- everyone waits for this chunk's MMAs (the A region / accumulator are then free to touch)
+                    tc_mbar_wait(bar_done, done_phase);
+                    done_phase ^= 1;
+                    tc_fence_after();
+                }
+                // ---- epilogue of pass p: accumulator columns [0, rows_p)
+                const float* bias = sbias + L.b_off + p * kTcNPass;
+                if (!last) {
+                    for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                        unsigned r[32];
+                        tc_ld32(t_x + c0, r);
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float f = __uint_as_float(r[j]) + bias[c0 + j];
+                            v[j] = L.relu ? fmaxf(f, 0.0f) : f;
+                        }
+                        tc_store_split32(t_ahi + c0 / 2, t_alo + c0 / 2, v);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncthreads();
+                } else if (io.out_mode == TC_OUT_ROWS) {
+                    for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                        unsigned r[32];
+                        tc_ld32(t_x + c0, r);
+                        if (rc.valid) {
+                            float* dst = io.y + rc.row * io.ldy + p * kTcNPass + c0;
+                            const int nleft = L.n_real - (p * kTcNPass + c0);
+                            const bool vec = nleft >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 o;
+                                o.x = __uint_as_float(r[j]) + bias[c0 + j];
+                                o.y = __uint_as_float(r[j + 1]) + bias[c0 + j + 1];
+                                o.z = __uint_as_float(r[j + 2]) + bias[c0 + j + 2];
+                                o.w = __uint_as_float(r[j + 3]) + bias[c0 + j + 3];
+                                if (L.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                                if (vec) {
+                                    *reinterpret_cast<float4*>(dst + j) = o;
+                                } else {
+                                    if (j < nleft) dst[j] = o.x;
+                                    if (j + 1 < nleft) dst[j + 1] = o.y;
+                                    if (j + 2 < nleft) dst[j + 2] = o.z;
+                                    if (j + 3 < nleft) dst[j + 3] = o.w;
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncthreads();
+                } else if (io.out_mode == TC_OUT_MAX) {
+                    // group = 32 consecutive rows = this warp: REDUX max per channel, lane j keeps channel c0 + j
+                    const int64_t grp = rc.row / 32;   // warp-uniform when the warp has any valid row
+                    const bool any_valid = __any_sync(0xffffffffu, rc.valid);
+                    const int64_t g = __shfl_sync(0xffffffffu, grp, 0);
+                    for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                        unsigned r[32];
+                        tc_ld32(t_x + c0, r);
+                        unsigned mine = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float f = __uint_as_float(r[j]) + bias[c0 + j];
+                            if (L.relu) f = fmaxf(f, 0.0f);
+                            const unsigned k = rc.valid ? tc_key(f) : 0u;
+                            const unsigned m = __reduce_max_sync(0xffffffffu, k);
+                            if (lane == j) mine = m;
+                        }
+                        const int n = p * kTcNPass + c0 + lane;
+                        if (any_valid && n < L.n_real) io.y[g * io.ldy + n] = tc_unkey(mine);
+                    }
+                    tc_fence_before();
+                    __syncthreads();
+                } else {   // TC_OUT_LOGSOFTMAX over the n_real (<= 64) classes of the row
+                    float v[64];
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        if (c0 < rows_p) {
+                            unsigned r[32];
+                            tc_ld32(t_x + c0, r);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + bias[c0 + j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[c0 + j] = 0.0f;
+                        }
+                    }
+                    float m = -CUDART_INF_F;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j)
+                        if (j < L.n_real) m = fmaxf(m, v[j]);
+                    float s = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j)
+                        if (j < L.n_real) s += expf(v[j] - m);
+                    const float ls = logf(s);
+                    if (rc.valid) {
+                        float* dst = io.y + rc.row * io.ldy;
+#pragma unroll
+                        for (int j = 0; j < 64; ++j)
+                            if (j < L.n_real) dst[j] = (v[j] - m) - ls;
+                    }
+                    tc_fence_before();
+                    __syncthreads();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(ch.tmem_cols));
+}
+
+static size_t tc_smem_bytes(const TcChain& c) { return (size_t)2 * c.stage_bytes + ((c.bias_floats * 4 + 15) & ~15) + 5 * 8 + 16; }
+
+template <int IN>
+static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaStream_t stream, const char* what) {
+    const size_t smem = tc_smem_bytes(ch);
+    PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "%s: chain needs %zu bytes of shared memory", what, smem);
+    auto kern = mlp_tc_kernel<IN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    const int64_t ntiles = io.nseg * ((io.seg_rows + 127) / 128);
+    // co-resident CTAs per SM: limited by TMEM columns (512) and shared memory
+    int per_sm = 512 / ch.tmem_cols;
+    const int by_smem = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < by_smem ? per_sm : by_smem;
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    const int64_t cap = 148LL * per_sm;
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    kern<<<grid, kTcThreads, smem, stream>>>(ch, static_cast<const unsigned char*>(blob), io);
+    return finish_launch(what);
+}
+
+}  // namespace pn
+
+// ------------------------------------------------------------------------------------------------ C ABI
+PN_EXPORT size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc) {
+    pn::TcChain ch;
+    const char* why;
+    if (!pn::plan_chain(desc, &ch, &why)) {
+        pn::set_error("pn_mlp_blob_bytes: %s", why);
+        return 0;
+    }
+    return ch.blob_bytes;
+}
+
+PN_EXPORT int pn_mlp_pack_bf16x3(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, void* blob,
+                                 pn_stream_t stream) {
+    using namespace pn;
+    TcChain ch;
+    const char* why;
+    PN_REQUIRE(plan_chain(desc, &ch, &why), PN_ERR_UNSUPPORTED, "pn_mlp_pack_bf16x3: %s", why);
+    PN_REQUIRE(w && blob, PN_ERR_BAD_ARG, "pn_mlp_pack_bf16x3: null pointer");
+    PN_REQUIRE(((uintptr_t)blob & 127) == 0, PN_ERR_ALIGNMENT, "pn_mlp_pack_bf16x3: blob must be 128-byte aligned");
+    for (int l = 0; l < ch.nlayers; ++l) {
+        const TcLayer& L = ch.L[l];
+        PN_REQUIRE(w[l], PN_ERR_BAD_ARG, "pn_mlp_pack_bf16x3: weight pointer %d is null", l);
+        unsigned char* img = static_cast<unsigned char*>(blob) + L.w_off;
+        float* bo = reinterpret_cast<float*>(static_cast<unsigned char*>(blob) + ch.bias_off) + L.b_off;
+        const int total = L.n_pad * L.k_pad;
+        tc_pack_layer_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w[l], bias ? bias[l] : nullptr, L.k_real,
+                                                                                    L.k_pad, L.n_real, L.n_pad, img, bo);
+    }
+    return finish_launch("pn_mlp_pack_bf16x3");
+}
+
+static int tc_common_checks(const pn_mlp_desc* desc, const void* blob, pn::TcChain* ch, int out_mode, const char* what) {
+    using namespace pn;
+    const char* why;
+    PN_REQUIRE(plan_chain(desc, ch, &why), PN_ERR_UNSUPPORTED, "%s: %s", what, why);
+    PN_REQUIRE(blob && ((uintptr_t)blob & 127) == 0, PN_ERR_ALIGNMENT, "%s: blob must be a 128-byte aligned device pointer", what);
+    PN_REQUIRE(out_mode >= 0 && out_mode <= 2, PN_ERR_BAD_ARG, "%s: out_mode must be 0 (rows), 1 (max) or 2 (log_softmax)", what);
+    const TcLayer& last = ch->L[ch->nlayers - 1];
+    PN_REQUIRE(out_mode != TC_OUT_LOGSOFTMAX || last.n_real <= 64, PN_ERR_UNSUPPORTED, "%s: log_softmax head is limited to 64 classes", what);
+    return PN_OK;
+}
+
+PN_EXPORT int pn_mlp_rows_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* x, int64_t ldx, int64_t rows,
+                                 int out_mode, float* y, int64_t ldy, pn_stream_t stream) {
+    using namespace pn;
+    TcChain ch;
+    int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_mlp_rows_bf16x3");
+    if (rc) return rc;
+    PN_REQUIRE(x && y && rows > 0 && ldx >= desc->cin[0], PN_ERR_BAD_ARG, "pn_mlp_rows_bf16x3: bad arguments");
+    PN_REQUIRE(out_mode != TC_OUT_MAX || rows % 32 == 0, PN_ERR_UNSUPPORTED, "pn_mlp_rows_bf16x3: max-pool needs rows %% 32 == 0");
+    TcIo io = {};
+    io.nseg = 1;
+    io.seg_rows = rows;
+    io.x = x;
+    io.ldx = ldx;
+    io.out_mode = out_mode;
+    io.y = y;
+    io.ldy = ldy;
+    io.group = 32;
+    return tc_launch<TC_IN_ROWS>(ch, blob, io, (cudaStream_t)stream, "pn_mlp_rows_bf16x3");
+}
+
+PN_EXPORT int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
+                                   int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
+                                   const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
+                                   int S, int K, int msg_order, float* out, int64_t ldo, pn_stream_t stream) {
+    using namespace pn;
+    TcChain ch;
+    int rc = tc_common_checks(desc, blob, &ch, TC_OUT_MAX, "pn_sa_mlp_max_bf16x3");
+    if (rc) return rc;
+    PN_REQUIRE(xyz && new_xyz && idx && out, PN_ERR_BAD_ARG, "pn_sa_mlp_max_bf16x3: null pointer");
+    PN_REQUIRE((feat != nullptr) == (D > 0) && desc->cin[0] == 3 + D, PN_ERR_BAD_ARG,
+               "pn_sa_mlp_max_bf16x3: first layer expects %d channels, grouping provides 3 + %d", desc->cin[0], D);
+    PN_REQUIRE(K == 32, PN_ERR_UNSUPPORTED, "pn_sa_mlp_max_bf16x3: nsample must be 32 (got %d)", K);
+    PN_REQUIRE(B > 0 && N > 0 && S > 0 && ldo >= desc->cout[desc->nlayers - 1], PN_ERR_BAD_ARG, "pn_sa_mlp_max_bf16x3: bad sizes");
+    TcIo io = {};
+    io.nseg = 1;
+    io.seg_rows = (int64_t)B * S * K;
+    io.xyz = xyz; io.xB = xB; io.xN = xN; io.xC = xC;
+    io.feat = feat; io.fB = fB; io.fN = fN; io.fC = fC; io.D = D;
+    io.qxyz = new_xyz; io.qB = qB; io.qN = qN; io.qC = qC;
+    io.idx = idx; io.N = N; io.S = S; io.K = K; io.msg_order = msg_order;
+    io.out_mode = TC_OUT_MAX;
+    io.y = out;
+    io.ldy = ldo;
+    io.group = K;
+    return tc_launch<TC_IN_SA>(ch, blob, io, (cudaStream_t)stream, "pn_sa_mlp_max_bf16x3");
+}
+
+PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
+                               int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2,
+                               int S, const int64_t* idx, const float* weight, int B, int N, int out_mode, float* out,
+                               int64_t ldo, pn_stream_t stream) {
+    using namespace pn;
+    TcChain ch;
+    int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_fp_mlp_bf16x3");
+    if (rc) return rc;
+    PN_REQUIRE(points2 && idx && weight && out, PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: null pointer");
+    PN_REQUIRE((points1 != nullptr) == (D1 > 0) && desc->cin[0] == D1 + D2, PN_ERR_BAD_ARG,
+               "pn_fp_mlp_bf16x3: first layer expects %d channels, inputs provide %d + %d", desc->cin[0], D1, D2);
+    PN_REQUIRE(out_mode != TC_OUT_MAX, PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: out_mode must be 0 (rows) or 2 (log_softmax)");
+    PN_REQUIRE(B > 0 && N > 0 && S > 0 && ldo >= desc->cout[desc->nlayers - 1], PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: bad sizes");
+    TcIo io = {};
+    io.nseg = B;
+    io.seg_rows = N;
+    io.p1 = points1; io.p1B = p1B; io.p1N = p1N; io.p1C = p1C; io.D1 = D1;
+    io.p2 = points2; io.p2B = p2B; io.p2N = p2N; io.p2C = p2C; io.D2 = D2; io.S2 = S;
+    io.idx3 = idx; io.w3 = weight;
+    io.out_mode = out_mode;
+    io.y = out;
+    io.ldy = ldo;
+    io.group = 32;
+    return tc_launch<TC_IN_FP>(ch, blob, io, (cudaStream_t)stream, "pn_fp_mlp_bf16x3");
+}

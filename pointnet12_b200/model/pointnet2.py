@@ -185,4 +185,6 @@ class PointNet2SemSeg(_Net):
         f3 = self.fp4(xs[3], xs[4], fs[3], fs[4])
         f2 = self.fp3(xs[2], xs[3], fs[2], f3)
         f1 = self.fp2(xs[1], xs[2], fs[1], f2)
-        return self._seg_head(self.fp1(xyz, xs[1], None, f1))[0]
+        # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs
+        head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
+        return self.fp1(xyz, xs[1], None, f1, head=head)

@@ -129,7 +129,24 @@ class FoldedLayers:
         if key != self._key:
             self._layers = [fold_conv_bn(c, b) for c, b in zip(convs, bns)]
             self._key = key
+            self._chain = None
         return self._layers
+
+    def chain(self, convs: Sequence[nn.Module], bns: Sequence[Optional[nn.Module]],
+              relus: Optional[Sequence[bool]] = None) -> Optional[ops.PackedChain]:
+        """The same layers packed for the tensor-core kernels, or None when the mode is 'fp32' or the chain
+        does not fit them (then the caller uses the layer-by-layer CUDA-core path)."""
+        if ops.mlp_mode() != "bf16x3":
+            return None
+        layers = self.get(convs, bns)
+        if getattr(self, "_chain", None) is None:
+            dims = [(w.shape[1], w.shape[0]) for w, _ in layers]
+            if not ops.PackedChain.supported(dims):
+                self._chain = False
+            else:
+                relus = [True] * len(layers) if relus is None else list(relus)
+                self._chain = ops.PackedChain([(w, b, r) for (w, b), r in zip(layers, relus)])
+        return self._chain or None
 
 
 def _eval_only(module: nn.Module) -> None:
@@ -168,6 +185,13 @@ class PointNetSetAbstraction(nn.Module):
         _eval_only(self)
         xyz_pm = xyz.permute(0, 2, 1)
         pts_pm = points.permute(0, 2, 1) if points is not None else None
+        chain = None if self.group_all or self.nsample != 32 else self._folded.chain(self.mlp_convs, self.mlp_bns)
+        if chain is not None:
+            # one kernel: gather + recentre + concat -> tensor-core MLP chain -> max over the group
+            new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, self.npoint, start_idx))
+            idx = ops.ball_query(self.radius, self.nsample, xyz_pm, new_xyz)
+            pooled = ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=False)
+            return new_xyz.permute(0, 2, 1), pooled.permute(0, 2, 1)
         if self.group_all:
             new_xyz, grouped = sample_and_group_all(xyz_pm, pts_pm)
         else:
@@ -212,6 +236,12 @@ class PointNetSetAbstractionMsg(nn.Module):
         for i, radius in enumerate(self.radius_list):
             K = self.nsample_list[i]
             idx = ops.ball_query(radius, K, xyz_pm, new_xyz)
+            chain = self._folded[i].chain(self.conv_blocks[i], self.bn_blocks[i]) if K == 32 else None
+            if chain is not None:
+                ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=True,
+                                  out=out.view(B * S, -1)[:, col:col + widths[i]])
+                col += widths[i]
+                continue
             grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=True)
             rows = _mlp_rows(grouped.view(B * S * K, -1), self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]))
             ops.group_max(rows, K, out=out.view(B * S, -1)[:, col:col + widths[i]])   # written in place: no concat
@@ -234,8 +264,10 @@ class PointNetFeaturePropagation(nn.Module):
             c = width
         self._folded = FoldedLayers()
 
-    def forward(self, xyz1, xyz2, points1, points2):
-        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+    def forward(self, xyz1, xyz2, points1, points2, head=None):
+        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N].
+        `head` (extension used by the networks): extra layers run in the same kernel; the result is then the
+        point-major [B,N,classes] tensor."""
         _eval_only(self)
         x1, x2 = xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1)
         p2 = points2.permute(0, 2, 1)
@@ -247,6 +279,20 @@ class PointNetFeaturePropagation(nn.Module):
             w = torch.tensor([1.0, 0.0, 0.0], device=x1.device).expand(B, N, 3).contiguous()
         else:
             idx, w = ops.three_nn(x1, x2)
+        convs, bns, relus = list(self.mlp_convs), list(self.mlp_bns), [True] * len(self.mlp_convs)
+        folded, out_mode = self._folded, ops.OUT_ROWS
+        if head is not None:   # (FoldedLayers, convs, bns, relus, out_mode) appended by the network: fused seg head
+            folded, hconvs, hbns, hrelus, out_mode = head
+            convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
+        chain = folded.chain(convs, bns, relus)
+        if chain is not None:
+            # one kernel: weighted 3-row gather + skip concat -> tensor-core MLP chain (-> head -> log_softmax)
+            out = ops.fp_mlp_tc(chain, p1, p2, idx, w, out_mode)
+            return out if head is not None else out.permute(0, 2, 1)
         rows = ops.three_interpolate(p1, p2, idx, w).view(B * N, -1)
-        rows = _mlp_rows(rows, self._folded.get(self.mlp_convs, self.mlp_bns))
+        layers = folded.get(convs, bns)
+        for (wt, b), r in zip(layers, relus):
+            rows = ops.linear(rows, wt, b, relu=r)
+        if head is not None:
+            return (ops.log_softmax(rows) if out_mode == ops.OUT_LOG_SOFTMAX else rows).view(B, N, -1)
         return rows.view(B, N, -1).permute(0, 2, 1)

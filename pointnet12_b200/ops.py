@@ -6,7 +6,9 @@ unchanged -- the kernels take element strides, like the reference's functions ta
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -267,4 +269,122 @@ def log_softmax(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((rows, Cc), dtype=torch.float32, device=x.device)
     with _on_device(x):
         nv.call("pn_log_softmax_f32", x.data_ptr(), ldx, rows, Cc, out.data_ptr(), Cc, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused shared-MLP chains on the tensor cores (tcgen05 + TMEM): pn_*_bf16x3 entry points.
+# "bf16x3" computes every product as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation: fp32 parity
+# (relative error ~1e-5) at tensor-core speed.  "fp32" keeps the exact-fp32 CUDA-core path (pn_linear_f32).
+_MLP_MODE = os.environ.get("PN12_MLP", "bf16x3")
+OUT_ROWS, OUT_MAX32, OUT_LOG_SOFTMAX = 0, 1, 2
+
+
+def set_mlp_mode(mode: str) -> str:
+    """'bf16x3' (tensor cores, default) or 'fp32' (CUDA cores, exact fp32 accumulation).  Returns the old mode."""
+    global _MLP_MODE
+    if mode not in ("bf16x3", "fp32"):
+        raise ValueError("mode must be 'bf16x3' or 'fp32'")
+    old, _MLP_MODE = _MLP_MODE, mode
+    return old
+
+
+def mlp_mode() -> str:
+    return _MLP_MODE
+
+
+class PackedChain:
+    """A conv+BN(+ReLU) chain folded and packed for the tensor-core kernels (device blob + descriptor)."""
+
+    def __init__(self, layers: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], bool]]):
+        self.desc = nv.MlpDesc()
+        self.desc.nlayers = len(layers)
+        for i, (w, _, relu) in enumerate(layers):
+            self.desc.cout[i], self.desc.cin[i] = int(w.shape[0]), int(w.shape[1])
+            self.desc.relu[i] = int(bool(relu))
+        self.cin, self.cout = int(layers[0][0].shape[1]), int(layers[-1][0].shape[0])
+        nbytes = nv.lib().pn_mlp_blob_bytes(C.byref(self.desc))
+        if nbytes == 0:
+            raise RuntimeError("chain not supported by the tensor-core path: "
+                               + nv.lib().pn_last_error_string().decode("utf-8", "replace"))
+        dev = layers[0][0].device
+        self.blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        ws = [_f32(w, "w").contiguous() for w, _, _ in layers]
+        bs = [None if b is None else _f32(b, "bias").contiguous() for _, b, _ in layers]
+        n = len(layers)
+        wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
+        bp = (C.c_void_p * n)(*[None if b is None else b.data_ptr() for b in bs])
+        with _on_device(self.blob):
+            nv.call("pn_mlp_pack_bf16x3", C.byref(self.desc), wp, bp, self.blob.data_ptr(), _stream())
+        self._keep = (ws, bs)     # the pack kernels read them asynchronously
+
+    @staticmethod
+    def supported(dims: Sequence[Tuple[int, int]]) -> bool:
+        """dims = [(cin, cout), ...]"""
+        if not 1 <= len(dims) <= nv.MLP_MAX_LAYERS:
+            return False
+        d = nv.MlpDesc()
+        d.nlayers = len(dims)
+        for i, (ci, co) in enumerate(dims):
+            d.cin[i], d.cout[i], d.relu[i] = int(ci), int(co), 1
+        return nv.lib().pn_mlp_blob_bytes(C.byref(d)) > 0
+
+
+def mlp_rows_tc(chain: PackedChain, x: torch.Tensor, out_mode: int = OUT_ROWS) -> torch.Tensor:
+    """chain(x) for x [rows, cin]; OUT_MAX32 pools every 32 consecutive rows, OUT_LOG_SOFTMAX ends in log_softmax."""
+    x, rows, cin, ldx = _rows(x, "x")
+    if cin != chain.cin:
+        raise ValueError(f"chain expects {chain.cin} input channels, got {cin}")
+    out_rows = rows // 32 if out_mode == OUT_MAX32 else rows
+    out = torch.empty((out_rows, chain.cout), dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        nv.call("pn_mlp_rows_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), x.data_ptr(), ldx, rows, out_mode,
+                out.data_ptr(), chain.cout, _stream())
+    return out
+
+
+def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Tensor], new_xyz: torch.Tensor,
+                  idx: torch.Tensor, msg_order: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Grouping + shared MLP + max over nsample in one kernel -> [B, S, cout] (or into the strided view `out`)."""
+    xyz, new_xyz = _cloud(xyz, "xyz", 3), _cloud(new_xyz, "new_xyz", 3)
+    idx = _i64(idx, "idx")
+    B, N, _ = xyz.shape
+    _, S, K = idx.shape
+    if feat is not None:
+        feat = _cloud(feat, "points")
+        D, fs = feat.shape[2], feat.stride()
+    else:
+        D, fs = 0, (0, 0, 0)
+    if out is None:
+        out = torch.empty((B, S, chain.cout), dtype=torch.float32, device=xyz.device)
+        ldo = chain.cout
+    else:
+        if out.shape != (B * S, chain.cout) or out.stride(1) != 1:
+            raise ValueError("out must be a [B*S, cout] view with unit channel stride")
+        ldo = out.stride(0)
+    with _on_device(xyz):
+        nv.call("pn_sa_mlp_max_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), xyz.data_ptr(), *xyz.stride(), _p(feat),
+                *fs, D, new_xyz.data_ptr(), *new_xyz.stride(), idx.data_ptr(), B, N, S, K, int(msg_order), out.data_ptr(),
+                ldo, _stream())
+    return out
+
+
+def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torch.Tensor, idx: torch.Tensor,
+              weight: torch.Tensor, out_mode: int = OUT_ROWS) -> torch.Tensor:
+    """3-NN interpolation + skip concat + shared MLP (+ head + log_softmax) in one kernel -> [B, N, cout]."""
+    points2 = _cloud(points2, "points2")
+    idx = _i64(idx, "idx")
+    weight = _f32(weight, "weight").contiguous()
+    B, S, D2 = points2.shape
+    N = idx.shape[1]
+    if points1 is not None:
+        points1 = _cloud(points1, "points1")
+        D1, s1 = points1.shape[2], points1.stride()
+    else:
+        D1, s1 = 0, (0, 0, 0)
+    out = torch.empty((B, N, chain.cout), dtype=torch.float32, device=points2.device)
+    with _on_device(points2):
+        nv.call("pn_fp_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), _p(points1), *s1, D1, points2.data_ptr(),
+                *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), B, N, out_mode, out.data_ptr(), chain.cout,
+                _stream())
     return out
