@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from .. import ops
 from .pointnet_util import (FoldedLayers, PointNetFeaturePropagation, PointNetSetAbstraction,
-                            PointNetSetAbstractionMsg, _eval_only, draw_fps_starts)
+                            PointNetSetAbstractionMsg, _eval_only, draw_fps_starts, farthest_point_sample)
 
 
 def _ssg(npoint, radius, nsample, in_channel, mlp):
@@ -178,13 +178,64 @@ class PointNet2SemSeg(_Net):
                      fp2=_fp(320, [256, 128]), fp1=_fp(128, [128, 128, 128]))
         self._seg_convs(num_classes)
 
-    def forward(self, points):
+    def forward(self, points, fps_starts=None):
+        """points [B, 3+feature_dims, N] -> log-probabilities [B, N, num_classes].
+        `fps_starts` (extension): the four FPS start-index tensors ([B] int64 on the device) when the caller has
+        drawn them already (CUDA-graph replay); by default they are drawn like the reference draws them.
+
+        Everything that depends on xyz only -- FPS, ball query and 3-NN search of every level -- is issued on
+        side streams right after the level-1 sampling, so it overlaps the feature path (SA MLPs) instead of
+        sitting on its critical path.  fp1 and the segmentation head run as one tensor-core chain."""
         _eval_only(self)
-        xyz, feature = points[:, :3, :], points[:, 3:, :]
-        xs, fs = self._encode(("sa1", "sa2", "sa3", "sa4"), xyz, feature)
-        f3 = self.fp4(xs[3], xs[4], fs[3], fs[4])
-        f2 = self.fp3(xs[2], xs[3], fs[2], f3)
-        f1 = self.fp2(xs[1], xs[2], fs[1], f2)
+        B, _, N = points.shape
+        pm = points.permute(0, 2, 1)
+        x0, f0 = pm[:, :, :3], (pm[:, :, 3:] if points.shape[1] > 3 else None)
+        sa = [self.sa1, self.sa2, self.sa3, self.sa4]
+        fp = [self.fp1, self.fp2, self.fp3, self.fp4]              # fp[i] upsamples level i+1 -> level i
+        if fps_starts is None:
+            fps_starts = draw_fps_starts(B, [N] + [m.npoint for m in sa[:-1]], points.device)
+        main = torch.cuda.current_stream(points.device)
+        side_a, side_b = self._side_streams(points.device)
+
+        # level-1 sampling (the long serial kernel) on the main stream
+        x1 = ops.index_points(x0, farthest_point_sample(x0, sa[0].npoint, fps_starts[0]))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        xs, balls, nns, ready = [x0, x1], [None] * 4, [None] * 4, [None] * 4
+        with torch.cuda.stream(side_b):                            # fp1's 3-NN: 24000 x 1024 per cloud
+            side_b.wait_event(fork)
+            nns[0] = fp[0].geometry(x0, x1)
+            done_b = torch.cuda.Event()
+            done_b.record(side_b)
+        with torch.cuda.stream(side_a):                            # sampling / grouping / 3-NN of levels 2..4
+            side_a.wait_event(fork)
+            for i in (1, 2, 3):
+                nx, balls[i] = sa[i].geometry(xs[i], fps_starts[i])
+                xs.append(nx)
+                ready[i] = torch.cuda.Event()
+                ready[i].record(side_a)
+                nns[i] = fp[i].geometry(xs[i], nx)
+            done_a = torch.cuda.Event()
+            done_a.record(side_a)
+
+        # feature path on the main stream
+        balls[0] = ops.ball_query(sa[0].radius, sa[0].nsample, x0, x1)
+        fs = [f0, sa[0].features(x0, f0, x1, balls[0])]
+        for i in (1, 2, 3):
+            main.wait_event(ready[i])
+            fs.append(sa[i].features(xs[i], fs[i], xs[i + 1], balls[i]))
+        main.wait_event(done_a)
+        up = fs[4]
+        for i in (3, 2, 1):
+            up = fp[i].features(fs[i], up, *nns[i])
+        main.wait_event(done_b)
         # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs
         head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
-        return self.fp1(xyz, xs[1], None, f1, head=head)
+        return fp[0].features(None, up, *nns[0], head=head)
+
+    def _side_streams(self, device):
+        key = torch.device(device).index
+        streams = self.__dict__.setdefault("_streams", {})
+        if key not in streams:
+            streams[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        return streams[key]

@@ -179,27 +179,38 @@ class PointNetSetAbstraction(nn.Module):
             c = width
         self._folded = FoldedLayers()
 
+    # The level splits into a geometry half (depends on xyz only: FPS + ball query) and a feature half
+    # (grouping + MLP + max).  The networks run the geometry of all levels on side streams.
+    def geometry(self, xyz_pm: torch.Tensor, start_idx: Optional[torch.Tensor] = None):
+        """xyz_pm [B,N,3] -> (new_xyz [B,S,3], group_idx [B,S,K])."""
+        new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, self.npoint, start_idx))
+        return new_xyz, ops.ball_query(self.radius, self.nsample, xyz_pm, new_xyz)
+
+    def features(self, xyz_pm, pts_pm, new_xyz, idx) -> torch.Tensor:
+        """-> pooled [B,S,C'] point-major."""
+        B, S, K = idx.shape
+        chain = self._folded.chain(self.mlp_convs, self.mlp_bns) if K == 32 else None
+        if chain is not None:
+            # one kernel: gather + recentre + concat -> tensor-core MLP chain -> max over the group
+            return ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=False)
+        grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=False)
+        rows = _mlp_rows(grouped.view(B * S * K, -1), self._folded.get(self.mlp_convs, self.mlp_bns))
+        return ops.group_max(rows, K).view(B, S, -1)
+
     def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx: Optional[torch.Tensor] = None):
         """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,C',S].
         `start_idx` (extension): the FPS start indices, when the caller has already drawn them."""
         _eval_only(self)
         xyz_pm = xyz.permute(0, 2, 1)
         pts_pm = points.permute(0, 2, 1) if points is not None else None
-        chain = None if self.group_all or self.nsample != 32 else self._folded.chain(self.mlp_convs, self.mlp_bns)
-        if chain is not None:
-            # one kernel: gather + recentre + concat -> tensor-core MLP chain -> max over the group
-            new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, self.npoint, start_idx))
-            idx = ops.ball_query(self.radius, self.nsample, xyz_pm, new_xyz)
-            pooled = ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=False)
-            return new_xyz.permute(0, 2, 1), pooled.permute(0, 2, 1)
         if self.group_all:
             new_xyz, grouped = sample_and_group_all(xyz_pm, pts_pm)
+            B, S, K, C = grouped.shape
+            rows = _mlp_rows(grouped.view(B * S * K, C), self._folded.get(self.mlp_convs, self.mlp_bns))
+            pooled = ops.group_max(rows, K).view(B, S, -1)
         else:
-            new_xyz, grouped = sample_and_group(self.npoint, self.radius, self.nsample, xyz_pm, pts_pm,
-                                                start_idx=start_idx)
-        B, S, K, C = grouped.shape
-        rows = _mlp_rows(grouped.view(B * S * K, C), self._folded.get(self.mlp_convs, self.mlp_bns))
-        pooled = ops.group_max(rows, K).view(B, S, -1)
+            new_xyz, idx = self.geometry(xyz_pm, start_idx)
+            pooled = self.features(xyz_pm, pts_pm, new_xyz, idx)
         return new_xyz.permute(0, 2, 1), pooled.permute(0, 2, 1)
 
 
@@ -264,35 +275,38 @@ class PointNetFeaturePropagation(nn.Module):
             c = width
         self._folded = FoldedLayers()
 
-    def forward(self, xyz1, xyz2, points1, points2, head=None):
-        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N].
-        `head` (extension used by the networks): extra layers run in the same kernel; the result is then the
-        point-major [B,N,classes] tensor."""
-        _eval_only(self)
-        x1, x2 = xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1)
-        p2 = points2.permute(0, 2, 1)
-        p1 = points1.permute(0, 2, 1) if points1 is not None else None
+    def geometry(self, x1: torch.Tensor, x2: torch.Tensor):
+        """x1 [B,N,3] fine points, x2 [B,S,3] coarse points -> (idx [B,N,3], weight [B,N,3])."""
         B, N, _ = x1.shape
-        S = x2.shape[1]
-        if S == 1:   # a single coarse point: broadcast it (reference :292-293)
+        if x2.shape[1] == 1:   # a single coarse point: broadcast it (reference :292-293)
             idx = torch.zeros((B, N, 3), dtype=torch.int64, device=x1.device)
-            w = torch.tensor([1.0, 0.0, 0.0], device=x1.device).expand(B, N, 3).contiguous()
-        else:
-            idx, w = ops.three_nn(x1, x2)
+            return idx, torch.tensor([1.0, 0.0, 0.0], device=x1.device).expand(B, N, 3).contiguous()
+        return ops.three_nn(x1, x2)
+
+    def features(self, p1, p2, idx, w, head=None) -> torch.Tensor:
+        """p1 [B,N,D1] or None, p2 [B,S,D2] point-major -> [B,N,D'] point-major.
+        `head`: (FoldedLayers, convs, bns, relus, out_mode) appended by a network: the segmentation head runs
+        in the same kernel and the result is the [B,N,classes] log-probabilities."""
+        B, N, _ = idx.shape
         convs, bns, relus = list(self.mlp_convs), list(self.mlp_bns), [True] * len(self.mlp_convs)
         folded, out_mode = self._folded, ops.OUT_ROWS
-        if head is not None:   # (FoldedLayers, convs, bns, relus, out_mode) appended by the network: fused seg head
+        if head is not None:
             folded, hconvs, hbns, hrelus, out_mode = head
             convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
         chain = folded.chain(convs, bns, relus)
         if chain is not None:
             # one kernel: weighted 3-row gather + skip concat -> tensor-core MLP chain (-> head -> log_softmax)
-            out = ops.fp_mlp_tc(chain, p1, p2, idx, w, out_mode)
-            return out if head is not None else out.permute(0, 2, 1)
+            return ops.fp_mlp_tc(chain, p1, p2, idx, w, out_mode)
         rows = ops.three_interpolate(p1, p2, idx, w).view(B * N, -1)
-        layers = folded.get(convs, bns)
-        for (wt, b), r in zip(layers, relus):
+        for (wt, b), r in zip(folded.get(convs, bns), relus):
             rows = ops.linear(rows, wt, b, relu=r)
-        if head is not None:
-            return (ops.log_softmax(rows) if out_mode == ops.OUT_LOG_SOFTMAX else rows).view(B, N, -1)
-        return rows.view(B, N, -1).permute(0, 2, 1)
+        if out_mode == ops.OUT_LOG_SOFTMAX:
+            rows = ops.log_softmax(rows)
+        return rows.view(B, N, -1)
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        _eval_only(self)
+        idx, w = self.geometry(xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1))
+        p1 = points1.permute(0, 2, 1) if points1 is not None else None
+        return self.features(p1, points2.permute(0, 2, 1), idx, w).permute(0, 2, 1)

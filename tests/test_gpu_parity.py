@@ -488,6 +488,31 @@ def test_pointnet2_semseg_vs_oracle_batch8(dev, ckpt_state, ckpt_path, mlp_mode)
     assert (got.argmax(-1) == want.argmax(-1)).mean() > 0.999
 
 
+def test_graph_replay_matches_eager(dev, ckpt_path):
+    """GraphedSemSeg (CUDA-graph replay, 3 streams) gives bit-identical log-probs to the eager forward."""
+    from pointnet12_b200.model.utils import load_pointnet
+    from pointnet12_b200.runtime import GraphedSemSeg
+
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    runner = GraphedSemSeg(net)
+    for i, n in enumerate((4096, 4096, 2048)):
+        p = cuda(syn.kitti_batch(2, n, config=7 + i), dev)
+        torch.manual_seed(i)
+        with torch.no_grad():
+            want = net(p).clone()
+        torch.manual_seed(i)
+        got = runner(p)
+        assert torch.equal(got, want)
+    host = torch.from_numpy(syn.kitti_batch(2, 2048, config=9)).pin_memory()
+    out = torch.empty((2, 2048, 19)).pin_memory()
+    torch.manual_seed(5)
+    runner(host, out=out)
+    torch.cuda.synchronize()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        assert torch.equal(out, net(host.to(dev)).cpu())
+
+
 def _seeded(net, seed, dev):
     sd = syn.random_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
