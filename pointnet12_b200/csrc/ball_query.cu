@@ -13,14 +13,15 @@ namespace pn {
 
 constexpr int kBqThreads = 256;
 constexpr int kBqWarps = kBqThreads / 32;
-constexpr int kBqTile = 2048;  // points per shared-memory tile (32 KB)
 
-template <int QPW>  // queries per warp
+// QPW queries per warp share every shared-memory read; two 32-point chunks are tested per loop trip so that each
+// warp has 2*QPW independent load -> distance -> ballot chains in flight (the loop is latency-, not issue-bound).
+template <int QPW, int TILE>
 __global__ void __launch_bounds__(kBqThreads)
 ball_query_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC,
                   const float* __restrict__ qxyz, int64_t qB, int64_t qN, int64_t qC, int N, int S,
                   float radius2, int K, int64_t* __restrict__ out) {
-    __shared__ float4 tile[kBqTile];
+    extern __shared__ __align__(16) float4 tile[];
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = (blockIdx.x * kBqWarps + warp) * QPW;
@@ -43,45 +44,56 @@ ball_query_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t
     }
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    for (int t0 = 0; t0 < N; t0 += kBqTile) {
-        const int tn = min(kBqTile, N - t0);
+    for (int t0 = 0; t0 < N; t0 += TILE) {
+        const int tn = min(TILE, N - t0);
         for (int i = threadIdx.x; i < tn; i += kBqThreads) {
             const float* r = p + (int64_t)(t0 + i) * xN;
             const float x = r[0], y = r[xC], z = r[2 * xC];
             tile[i] = make_float4(x, y, z, sqnorm3(x, y, z));
         }
         __syncthreads();
-        bool warp_active = false;
+        bool open = false;
 #pragma unroll
-        for (int q = 0; q < QPW; ++q) {
-            if (cnt[q] >= K) continue;  // warp-uniform
-            int64_t* __restrict__ o = out + ((int64_t)b * S + (q0 + q)) * K;
-            for (int c = 0; c < tn && cnt[q] < K; c += 32) {
-                const int i = c + lane;
-                bool hit = false;
-                if (i < tn) {
-                    const float4 v = tile[i];
-                    const float d = sqdist_expand(ax[q], ay[q], az[q], sa[q], v.x, v.y, v.z, v.w);
-                    hit = !(d > radius2);
+        for (int q = 0; q < QPW; ++q) open |= cnt[q] < K;
+        if (open) {  // warp-uniform
+            for (int c = 0; c < tn; c += 64) {
+                const int i0 = c + lane, i1 = c + 32 + lane;
+                // out-of-tile lanes read a far-away dummy point (never a hit: d = +inf > radius2)
+                const float4 v0 = i0 < tn ? tile[i0] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+                const float4 v1 = i1 < tn ? tile[i1] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+                bool any_open = false;
+#pragma unroll
+                for (int q = 0; q < QPW; ++q) {
+                    const float d0 = sqdist_expand(ax[q], ay[q], az[q], sa[q], v0.x, v0.y, v0.z, v0.w);
+                    const float d1 = sqdist_expand(ax[q], ay[q], az[q], sa[q], v1.x, v1.y, v1.z, v1.w);
+                    const bool h0 = !(d0 > radius2), h1 = !(d1 > radius2);
+                    const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                    if ((m0 | m1) && cnt[q] < K) {
+                        int64_t* __restrict__ o = out + ((int64_t)b * S + (q0 + q)) * K;
+                        if (cnt[q] == 0) first[q] = t0 + c + (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1);
+                        const int p0 = cnt[q] + __popc(m0 & lt_mask);
+                        if (h0 && p0 < K) o[p0] = t0 + i0;
+                        const int n0 = cnt[q] + __popc(m0);
+                        const int p1 = n0 + __popc(m1 & lt_mask);
+                        if (h1 && p1 < K) o[p1] = t0 + i1;
+                        cnt[q] = n0 + __popc(m1);
+                    }
+                    any_open |= cnt[q] < K;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    if (cnt[q] == 0) first[q] = t0 + c + (__ffs(m) - 1);
-                    const int pos = cnt[q] + __popc(m & lt_mask);
-                    if (hit && pos < K) o[pos] = t0 + i;
-                    cnt[q] += __popc(m);
-                }
+                if (!any_open) break;
             }
-            warp_active |= cnt[q] < K;
         }
+        open = false;
+#pragma unroll
+        for (int q = 0; q < QPW; ++q) open |= cnt[q] < K;
         // leave early when every query of the CTA is complete
-        if (!__syncthreads_or(warp_active)) break;
+        if (!__syncthreads_or(open)) break;
     }
 #pragma unroll
     for (int q = 0; q < QPW; ++q) {
         if (q0 + q >= S) continue;
         int64_t* __restrict__ o = out + ((int64_t)b * S + (q0 + q)) * K;
-        for (int k = cnt[q] + lane; k < K; k += 32) o[k] = first[q];  // pad with the first hit (or N)
+        for (int k = min(cnt[q], K) + lane; k < K; k += 32) o[k] = first[q];  // pad with the first hit (or N)
     }
 }
 
@@ -112,16 +124,19 @@ PN_EXPORT int pn_ball_query_f32(const float* xyz, int64_t xB, int64_t xN, int64_
                "pn_ball_query_f32: B, N, S, nsample must be positive (got %d, %d, %d, %d)", B, N, S, nsample);
     PN_REQUIRE(B <= 65535, PN_ERR_UNSUPPORTED, "pn_ball_query_f32: B=%d exceeds 65535", B);
     cudaStream_t st = (cudaStream_t)stream;
-    // Few queries: one per warp so that the grid still covers the SMs; many: two per warp share a tile pass.
+    // Few queries: one per warp so that the grid still covers the SMs; many: two per warp share every tile read.
     const int64_t total_q = (int64_t)B * S;
-    if (total_q >= 148 * 8 * 8) {
+    if (total_q >= 4096) {
+        constexpr int TILE = 4096;
+        auto kern = ball_query_kernel<2, TILE>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16);
         dim3 grid((unsigned)ceil_div(S, kBqWarps * 2), (unsigned)B);
-        ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
-                                                          out_idx);
+        kern<<<grid, kBqThreads, TILE * 16, st>>>(xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample, out_idx);
     } else {
+        constexpr int TILE = 2048;
+        auto kern = ball_query_kernel<1, TILE>;
         dim3 grid((unsigned)ceil_div(S, kBqWarps), (unsigned)B);
-        ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
-                                                          out_idx);
+        kern<<<grid, kBqThreads, TILE * 16, st>>>(xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample, out_idx);
     }
     return finish_launch("pn_ball_query_f32");
 }

@@ -27,7 +27,7 @@
 
 namespace pn {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;  // 8 warps: warp w owns TMEM lanes 32*(w%4).., column half w/4 of every 64 columns
 constexpr int kTcMaxLayers = PN_MLP_MAX_LAYERS;
 constexpr int kTcKSub = 64;     // K values per streamed weight slice
 constexpr int kTcAChunk = 256;  // K values resident in TMEM as the A operand (128 columns hi + 128 columns lo)
@@ -154,11 +154,14 @@ __device__ __forceinline__ void tc_store_split32(unsigned t_hi, unsigned t_lo, c
     unsigned hi[16], lo[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-        hi[j] = (unsigned)__bfloat16_as_ushort(h0) | ((unsigned)__bfloat16_as_ushort(h1) << 16);
-        lo[j] = (unsigned)__bfloat16_as_ushort(l0) | ((unsigned)__bfloat16_as_ushort(l1) << 16);
+        // cvt.rn.bf16x2.f32: two conversions per instruction; .x (low half) = even k
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        const unsigned hb = *reinterpret_cast<const unsigned*>(&h);
+        const float r0 = v[2 * j] - __uint_as_float(hb << 16);
+        const float r1 = v[2 * j + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+        hi[j] = hb;
+        lo[j] = *reinterpret_cast<const unsigned*>(&l);
     }
     tc_st16(t_hi, hi);
     tc_st16(t_lo, lo);
@@ -317,7 +320,7 @@ __device__ __forceinline__ void row_load32(const TcIo& io, const RowCtx<IN>& c, 
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int IN>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
 mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restrict__ blob, const __grid_constant__ TcIo io) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [stage 0][stage 1][bias table][barriers: full0 full1 empty0 empty1 done][tmem ptr]
@@ -349,7 +352,8 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     __syncthreads();
     tc_fence_after();
     const unsigned tbase = *tmem_slot;
-    const unsigned tlane = tbase + ((unsigned)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const int wl = warp & 3, half = warp >> 2;                      // lane quarter / column half of this warp
+    const unsigned tlane = tbase + ((unsigned)(wl * 32) << 16);      // this warp's 32 TMEM lanes
     const unsigned t_x = tlane;                                      // accumulator columns
     const unsigned t_ahi = tlane + ch.x_cols, t_alo = t_ahi + ch.a_lo_off;
     const unsigned a_hi_col = tbase + ch.x_cols, a_lo_col = a_hi_col + ch.a_lo_off;   // lane 0 addresses for the MMA
@@ -360,7 +364,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     const int64_t ntiles = io.nseg * tiles_per_seg;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t seg = tile / tiles_per_seg;
-        const int64_t r_in_seg = (tile % tiles_per_seg) * 128 + tid;
+        const int64_t r_in_seg = (tile % tiles_per_seg) * 128 + wl * 32 + lane;
         RowCtx<IN> rc;
         rc.valid = r_in_seg < io.seg_rows;
         rc.row = seg * io.seg_rows + r_in_seg;
@@ -378,7 +382,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     const int kchunk = min(kTcAChunk, L.k_pad - kbase);
                     if (l == 0) {
                         // ---- producer: this thread's row, channels [kbase, kbase + kchunk) -> TMEM A region
-                        for (int k0 = 0; k0 < kchunk; k0 += 32) {
+                        for (int k0 = half * 32; k0 < kchunk; k0 += 64) {
                             float v[32];
                             row_load32<IN>(io, rc, kbase + k0, L.k_real, v);
                             tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
@@ -452,7 +456,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                 // ---- epilogue of pass p: accumulator columns [0, rows_p)
                 const float* bias = sbias + L.b_off + p * kTcNPass;
                 if (!last) {
-                    for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                    for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         float v[32];
@@ -467,7 +471,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     tc_fence_before();
                     __syncthreads();
                 } else if (io.out_mode == TC_OUT_ROWS) {
-                    for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                    for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         if (rc.valid) {
@@ -500,7 +504,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     const int64_t grp = rc.row / 32;   // warp-uniform when the warp has any valid row
                     const bool any_valid = __any_sync(0xffffffffu, rc.valid);
                     const int64_t g = __shfl_sync(0xffffffffu, grp, 0);
-                    for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                    for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         unsigned mine = 0;
@@ -517,34 +521,34 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     }
                     tc_fence_before();
                     __syncthreads();
-                } else {   // TC_OUT_LOGSOFTMAX over the n_real (<= 64) classes of the row
-                    float v[64];
-#pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        if (c0 < rows_p) {
+                } else {   // TC_OUT_LOGSOFTMAX over the n_real (<= 64) classes of the row: column-half 0 warps only
+                    if (half == 0) {
+                        float m = -CUDART_INF_F, ssum = 0.0f;
+                        for (int c0 = 0; c0 < rows_p; c0 += 32) {
                             unsigned r[32];
                             tc_ld32(t_x + c0, r);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]) + bias[c0 + j];
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[c0 + j] = 0.0f;
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < L.n_real) m = fmaxf(m, __uint_as_float(r[j]) + bias[c0 + j]);
                         }
-                    }
-                    float m = -CUDART_INF_F;
+                        for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                            unsigned r[32];
+                            tc_ld32(t_x + c0, r);
 #pragma unroll
-                    for (int j = 0; j < 64; ++j)
-                        if (j < L.n_real) m = fmaxf(m, v[j]);
-                    float s = 0.0f;
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < L.n_real) ssum += __expf((__uint_as_float(r[j]) + bias[c0 + j]) - m);
+                        }
+                        const float ls = __logf(ssum);
+                        for (int c0 = 0; c0 < rows_p; c0 += 32) {
+                            unsigned r[32];
+                            tc_ld32(t_x + c0, r);
+                            if (rc.valid) {
+                                float* dst = io.y + rc.row * io.ldy + c0;
 #pragma unroll
-                    for (int j = 0; j < 64; ++j)
-                        if (j < L.n_real) s += expf(v[j] - m);
-                    const float ls = logf(s);
-                    if (rc.valid) {
-                        float* dst = io.y + rc.row * io.ldy;
-#pragma unroll
-                        for (int j = 0; j < 64; ++j)
-                            if (j < L.n_real) dst[j] = (v[j] - m) - ls;
+                                for (int j = 0; j < 32; ++j)
+                                    if (c0 + j < L.n_real) dst[j] = ((__uint_as_float(r[j]) + bias[c0 + j]) - m) - ls;
+                            }
+                        }
                     }
                     tc_fence_before();
                     __syncthreads();
@@ -575,7 +579,7 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     int per_sm = 512 / ch.tmem_cols;
     const int by_smem = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < by_smem ? per_sm : by_smem;
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);   // __launch_bounds__(256, 2): registers allow two CTAs per SM
     const int64_t cap = 148LL * per_sm;
     const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
     kern<<<grid, kTcThreads, smem, stream>>>(ch, static_cast<const unsigned char*>(blob), io);

@@ -27,6 +27,7 @@ from .pointnet_util import FoldedLayers, _eval_only
 
 def _point_rows(x_cm: torch.Tensor) -> torch.Tensor:
     """User input [B, C, N] channel-major -> point-major [B, N, C] (layout change of the raw input)."""
+    ops._need_cuda(x_cm, "input")
     return x_cm.permute(0, 2, 1).contiguous()
 
 

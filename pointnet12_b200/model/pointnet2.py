@@ -72,6 +72,7 @@ class _Net(nn.Module):
         """Run set-abstraction levels in order; returns the per-level (xyz, features) lists.
         The FPS start indices of all sampling levels are drawn up front (same generator, same order as the
         reference's per-level draws) so that they reach the device in one asynchronous copy."""
+        ops._need_cuda(xyz, "xyz")
         levels = [getattr(self, name) for name in names]
         sizes, n = [], xyz.shape[2]
         for lvl in levels:
@@ -187,6 +188,7 @@ class PointNet2SemSeg(_Net):
         side streams right after the level-1 sampling, so it overlaps the feature path (SA MLPs) instead of
         sitting on its critical path.  fp1 and the segmentation head run as one tensor-core chain."""
         _eval_only(self)
+        ops._need_cuda(points, "points")
         B, _, N = points.shape
         pm = points.permute(0, 2, 1)
         x0, f0 = pm[:, :, :3], (pm[:, :, 3:] if points.shape[1] > 3 else None)

@@ -1,0 +1,161 @@
+"""CPU-only checks of the host side: the C ABI loads and exports every declared symbol, argument validation
+works without a GPU, CPU tensors are refused, state_dict / checkpoint compatibility, and the data-parallel
+sharding helpers under a world_size-2 gloo group."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from pointnet12_b200 import _native as nv
+from pointnet12_b200 import dist as pdist
+
+
+def test_library_exports_every_declared_symbol():
+    lib = nv.lib()
+    declared = nv.declared_symbols()
+    assert len(declared) >= 19 and "pn_fps_f32" in declared and "pn_fp_mlp_bf16x3" in declared
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"libpn12_b200.so does not export {missing}"
+    assert lib.pn_version() >= 100
+    # every bound signature is a declared symbol (no stale bindings)
+    assert set(nv._SIGNATURES) <= set(declared)
+
+
+def test_argument_validation_needs_no_gpu():
+    lib = nv.lib()
+    assert lib.pn_fps_f32(None, 0, 0, 0, 1, 16, 4, None, None, None) == -1
+    assert b"null pointer" in lib.pn_last_error_string()
+    assert lib.pn_fps_set_config(3, 0, 0) == -1
+    assert lib.pn_fps_set_config(0, 0, 0) == 0
+    d = nv.MlpDesc()
+    d.nlayers = 2
+    d.cin[0], d.cout[0], d.relu[0] = 128, 128, 1
+    d.cin[1], d.cout[1], d.relu[1] = 128, 19, 0
+    assert lib.pn_mlp_blob_bytes(C.byref(d)) == 128 * 128 * 4 + 32 * 128 * 4 + (128 + 32) * 4
+    d.cin[1] = 64                                  # does not chain
+    assert lib.pn_mlp_blob_bytes(C.byref(d)) == 0 and b"cin[l]" in lib.pn_last_error_string()
+    d.cin[1], d.cout[0], d.cin[1] = 512, 512, 512   # hidden layer wider than 256
+    assert lib.pn_mlp_blob_bytes(C.byref(d)) == 0
+
+
+def test_cpu_tensors_are_refused():
+    from pointnet12_b200.model import pointnet_util as U
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        U.square_distance(torch.zeros(1, 16, 3), torch.zeros(1, 16, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        U.index_points(torch.zeros(1, 16, 3), torch.zeros(1, 4, dtype=torch.long))
+    net = PointNet2SemSeg(19, feature_dims=1).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 4, 2048))
+
+
+def test_checkpoint_state_dict_contract(ckpt_path):
+    """The reference's checkpoint loads strict=True into the drop-in modules (names, shapes, dtypes)."""
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+    from pointnet12_b200.model.utils import ModuleWrapper
+
+    sd = torch.load(ckpt_path, map_location="cpu")
+    net = ModuleWrapper(PointNet2SemSeg(19, feature_dims=1))
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    own = net.state_dict()
+    assert list(own.keys()) == list(sd.keys())
+    assert all(own[k].shape == sd[k].shape and own[k].dtype == sd[k].dtype for k in sd)
+    assert sum(p.numel() for p in net.parameters()) == 968787
+
+
+def test_bn_folding_matches_unfolded():
+    from pointnet12_b200.model.pointnet_util import FoldedLayers, fold_conv_bn
+
+    torch.manual_seed(0)
+    conv, bn = torch.nn.Conv1d(7, 5, 1), torch.nn.BatchNorm1d(5).eval()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2)
+    bn.weight.data.normal_()
+    bn.bias.data.normal_()
+    x = torch.randn(3, 7, 11)
+    w, b = fold_conv_bn(conv, bn)
+    got = torch.einsum("oc,bcn->bon", w, x) + b[None, :, None]
+    assert torch.allclose(got, bn(conv(x)), atol=1e-5)
+    f = FoldedLayers()
+    first = f.get([conv], [bn])
+    assert f.get([conv], [bn]) is first                 # cached
+    bn.running_mean.add_(1.0)                           # any change refolds
+    assert f.get([conv], [bn]) is not first
+
+
+def test_shard_range_partitions():
+    for n, world in [(8, 1), (8, 2), (8, 4), (8, 8), (7, 4), (3, 8), (64, 8)]:
+        spans = [pdist.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        pdist.shard_range(8, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert pdist.env_world() == (rank, world, rank)
+        from pointnet12_b200 import synthetic as syn
+
+        glob = torch.from_numpy(syn.kitti_batch(5, 256, config=8))          # uneven: 3 + 2 clouds
+        mine = pdist.shard_batch(glob, rank, world)
+        lo, hi = pdist.shard_range(5, rank, world)
+        assert mine.shape[0] == hi - lo and torch.equal(mine, glob[lo:hi])
+        labels = (mine[:, 0, :] * 1000).long()                              # stand-in for per-rank predictions
+        allv = pdist.gather_labels(labels, 5)
+        assert torch.equal(allv, (glob[:, 0, :] * 1000).long())
+        ms = pdist.max_over_ranks([1.0 + rank, 5.0 - rank])
+        assert ms == [float(world), 5.0]
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_world_size_2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: "ok", 1: "ok"}, results
+
+
+def test_reference_import_path_aliases():
+    """`from model.pointnet2 import PointNet2SemSeg` (the reference's spelling) resolves to the drop-in."""
+    import model.pointnet2 as m2
+    import model.pointnet_util as mu
+    from pointnet12_b200.model import pointnet2, pointnet_util
+
+    assert m2.PointNet2SemSeg is pointnet2.PointNet2SemSeg
+    assert mu.farthest_point_sample is pointnet_util.farthest_point_sample
+    for name in ("square_distance", "index_points", "farthest_point_sample", "query_ball_point", "sample_and_group",
+                 "sample_and_group_all", "PointNetSetAbstraction", "PointNetSetAbstractionMsg",
+                 "PointNetFeaturePropagation"):
+        assert hasattr(mu, name)
