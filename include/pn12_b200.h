@@ -77,6 +77,25 @@ int pn_ball_query_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, cons
                       int64_t qN, int64_t qC, int B, int N, int S, float radius2, int nsample,
                       int64_t* out_idx, pn_stream_t stream);
 
+/* query_ball_point through a uniform-grid bucket pass (same result as pn_ball_query_f32, bit for bit).
+ * pn_ball_grid_build_f32 depends on xyz and the radius only (not on the centroids), so a caller can run it
+ * beside farthest-point sampling: per cloud it computes the bounding box, picks a cell size >= radius (plus
+ * slack for the fp32 rounding of the membership formula) and counting-sorts the points by cell into
+ * (x, y, z, original index) records.  grid: caller-owned, 16-byte aligned device buffer of
+ * pn_ball_grid_bytes(B, N) bytes.
+ * pn_ball_query_grid_f32: one warp per centroid; when the 27 neighbouring cells hold at most `threshold`
+ * points they are all tested and the hits are ordered through a shared-memory bitmap over original indices,
+ * otherwise the ball is dense and the ordered scan over the raw cloud stops after a short prefix.
+ * threshold: 0 = automatic (~sqrt(213 N)), negative = always scan, INT_MAX = always use the cells.
+ * Limits: N <= 1048576. */
+size_t pn_ball_grid_bytes(int B, int N);
+int pn_ball_grid_build_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, int B, int N, float radius2,
+                           void* grid, size_t grid_bytes, pn_stream_t stream);
+int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const float* new_xyz, int64_t qB,
+                           int64_t qN, int64_t qC, int B, int N, int S, float radius2, int nsample,
+                           const void* grid, size_t grid_bytes, int threshold, int64_t* out_idx,
+                           pn_stream_t stream);
+
 /* index_points (model/pointnet_util.py:43-60): out[b,m,:] = points[b, idx[b,m], :].
  * points [B,N,C] via strides, idx [B,M], out contiguous [B,M,C]. */
 int pn_index_points_f32(const float* points, int64_t pB, int64_t pN, int64_t pC, int B, int N, int C,

@@ -37,6 +37,9 @@ _SIGNATURES = {
     "pn_fps_set_config": [i32, i32, i32],
     "pn_square_distance_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp],
     "pn_ball_query_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, vp],
+    "pn_ball_grid_build_f32": [vp, i64, i64, i64, i32, i32, f32, vp, C.c_size_t, vp],
+    "pn_ball_query_grid_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, vp,
+                               vp],
     "pn_index_points_f32": [vp, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp],
     "pn_group_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32, i32, i32, vp,
                      i64, vp],
@@ -80,6 +83,8 @@ def lib():
             fn.restype = i32
         handle.pn_mlp_blob_bytes.argtypes = [_descp]
         handle.pn_mlp_blob_bytes.restype = C.c_size_t
+        handle.pn_ball_grid_bytes.argtypes = [i32, i32]
+        handle.pn_ball_grid_bytes.restype = C.c_size_t
         _lib = handle
     return _lib
 

@@ -108,16 +108,55 @@ def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
-    """query_ball_point (pointnet_util.py:87-107) -> int64 [B, S, nsample]."""
+GRID_MIN_POINTS = 4096     # below this the ordered scan of pn_ball_query_f32 is already short
+
+
+class BallGrid:
+    """Uniform-grid buckets of a batch of clouds for one radius (pn_ball_grid_build_f32).  Depends on xyz and the
+    radius only, so it can be built on a side stream while farthest-point sampling runs."""
+
+    def __init__(self, xyz: torch.Tensor, radius: float):
+        xyz = _cloud(xyz, "xyz", 3)
+        B, N, _ = xyz.shape
+        self.B, self.N, self.r2 = B, N, float(radius ** 2)
+        self.nbytes = int(nv.lib().pn_ball_grid_bytes(B, N))
+        self.buf = torch.empty((self.nbytes,), dtype=torch.uint8, device=xyz.device)
+        with _on_device(xyz):
+            nv.call("pn_ball_grid_build_f32", xyz.data_ptr(), *xyz.stride(), B, N, self.r2, self.buf.data_ptr(),
+                    self.nbytes, _stream())
+
+
+def ball_grid(xyz: torch.Tensor, radius: float) -> BallGrid:
+    return BallGrid(xyz, radius)
+
+
+def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
+               grid: Optional[BallGrid] = None, method: str = "auto") -> torch.Tensor:
+    """query_ball_point (pointnet_util.py:87-107) -> int64 [B, S, nsample].
+    method: "auto" (grid buckets for N >= GRID_MIN_POINTS, ordered scan below), "scan" (pn_ball_query_f32),
+    "grid" / "grid-cells" / "grid-scan" (pn_ball_query_grid_f32 with the automatic threshold / every query through
+    the cells / every query through the per-warp scan).  All return identical indices."""
     xyz, new_xyz = _cloud(xyz, "xyz", 3), _cloud(new_xyz, "new_xyz", 3)
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     out = torch.empty((B, S, int(nsample)), dtype=torch.int64, device=xyz.device)
     r2 = float(radius ** 2)  # the reference compares against the python scalar radius ** 2 (cast to fp32 by torch)
+    if method == "auto":
+        method = "grid" if (grid is not None or N >= GRID_MIN_POINTS) else "scan"
     with _on_device(xyz):
-        nv.call("pn_ball_query_f32", xyz.data_ptr(), *xyz.stride(), new_xyz.data_ptr(), *new_xyz.stride(), B, N, S, r2,
-                int(nsample), out.data_ptr(), _stream())
+        if method == "scan":
+            nv.call("pn_ball_query_f32", xyz.data_ptr(), *xyz.stride(), new_xyz.data_ptr(), *new_xyz.stride(), B, N, S,
+                    r2, int(nsample), out.data_ptr(), _stream())
+            return out
+        if method not in ("grid", "grid-cells", "grid-scan"):
+            raise ValueError(f"unknown ball query method {method!r}")
+        if grid is None:
+            grid = BallGrid(xyz, radius)
+        elif (grid.B, grid.N) != (B, N) or grid.r2 != r2:
+            raise ValueError("grid was built for another cloud shape or radius")
+        threshold = {"grid": 0, "grid-cells": 2 ** 31 - 1, "grid-scan": -1}[method]
+        nv.call("pn_ball_query_grid_f32", xyz.data_ptr(), *xyz.stride(), new_xyz.data_ptr(), *new_xyz.stride(), B, N, S,
+                r2, int(nsample), grid.buf.data_ptr(), grid.nbytes, threshold, out.data_ptr(), _stream())
     return out
 
 

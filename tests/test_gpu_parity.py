@@ -142,6 +142,59 @@ def test_ball_query_vs_oracle(dev, N, S, radius, K, B):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("method", ["scan", "grid", "grid-cells", "grid-scan"])
+@pytest.mark.parametrize("N,S,radius,K,B,fps_queries", [(24000, 1024, 0.1, 32, 2, True), (4096, 256, 0.2, 32, 3, True),
+                                                        (8191, 100, 0.4, 64, 2, False), (3000, 37, 0.05, 16, 3, False),
+                                                        (2049, 9, 2.0, 128, 1, False), (40000, 64, 0.02, 32, 1, True),
+                                                        (120000, 256, 0.1, 32, 1, False)])
+def test_ball_query_every_method(dev, method, N, S, radius, K, B, fps_queries):
+    """The ordered scan, the grid buckets (bitmap-ordered hits), the per-warp scan and their automatic mix return
+    the same indices, bit for bit, as the oracle -- on farthest-point centroids (sparse regions) and on random ones."""
+    from pointnet12_b200 import ops
+
+    pts = syn.kitti_batch(B, N, config=4)
+    xyz = pts.transpose(0, 2, 1)[:, :, :3]
+    if fps_queries:
+        sel = orc.farthest_point_sample(xyz, S, np.zeros(B, dtype=np.int64))
+    else:
+        rng = np.random.default_rng(N + S)
+        sel = np.stack([rng.choice(N, S, replace=False) for _ in range(B)])
+    q = np.ascontiguousarray(np.stack([xyz[b][sel[b]] for b in range(B)]))
+    want = orc.query_ball_point(radius, K, xyz, q)
+    got = ops.ball_query(radius, K, views(cuda(pts, dev))[0], cuda(q, dev), method=method)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("method", ["grid", "grid-cells", "grid-scan"])
+def test_ball_query_grid_edge_cases(dev, method):
+    """Queries outside the cloud's bounding box (no hit -> row of N, or hits only across the box face), a cloud
+    collapsed to one point, a contiguous [B,N,3] layout, unnormalised metre-scale coordinates and a prebuilt grid."""
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(3)
+    # (a) arbitrary queries, many outside the box; contiguous layout
+    xyz = rng.uniform(-1, 1, (2, 5000, 3)).astype(np.float32)
+    q = rng.uniform(-1.6, 1.6, (2, 300, 3)).astype(np.float32)
+    want = orc.query_ball_point(0.3, 32, xyz, q)
+    grid = ops.ball_grid(cuda(xyz, dev), 0.3)
+    got = ops.ball_query(0.3, 32, cuda(xyz, dev), cuda(q, dev), grid=grid, method=method).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert (want == 5000).any() and (want != 5000).any()
+    # (b) every point identical (one cell), and a far query
+    one = np.tile(np.float32([[0.25, -0.5, 0.125]]), (1, 4100, 1))
+    q1 = np.float32([[[0.25, -0.5, 0.125], [0.3, -0.5, 0.125], [9.0, 9.0, 9.0]]])
+    assert np.array_equal(ops.ball_query(0.1, 32, cuda(one, dev), cuda(q1, dev), method=method).cpu().numpy(),
+                          orc.query_ball_point(0.1, 32, one, q1))
+    # (c) metre-scale coordinates (|p| ~ 80): the cell slack must cover the larger rounding of the formula
+    big = (rng.uniform(-1, 1, (1, 6000, 3)) * np.float32([80, 80, 3])).astype(np.float32)
+    qb = big[:, rng.choice(6000, 200, replace=False)]
+    assert np.array_equal(ops.ball_query(2.5, 32, cuda(big, dev), cuda(qb, dev), method=method).cpu().numpy(),
+                          orc.query_ball_point(2.5, 32, big, qb))
+    # (d) a grid built for another radius is refused
+    with pytest.raises(ValueError):
+        ops.ball_query(0.2, 32, cuda(xyz, dev), cuda(q, dev), grid=grid, method=method)
+
+
 def test_ball_query_empty_ball(dev):
     """A query far from every point: the reference leaves the row filled with N."""
     from pointnet12_b200.model import pointnet_util as U

@@ -38,7 +38,7 @@ def main():
     dev = torch.device("cuda", 0)
     out = []
     Ns = [4096, 24000] if quick else [4096, 8192, 16384, 24000, 32768, 65536, 120000]
-    for B in ([8] if quick else [1, 8]):
+    for B in ([] if '--only-sweeps' in sys.argv else [8] if quick else [1, 8]):
         for N in Ns:
             pts = torch.from_numpy(syn.kitti_batch(B, N, config=3)).to(dev)
             xyz = pts.permute(0, 2, 1)[:, :, :3]
@@ -76,6 +76,20 @@ def main():
                     print(json.dumps(dict(sweep="fps", cluster=cl, threads=th, error=str(e)[:100])), flush=True)
                 finally:
                     ops.fps_set_config(0, 0, 0)
+    if "--ball-sweep" in sys.argv:
+        for B, N, npoint, radius in [(8, 24000, 1024, 0.1), (1, 120000, 1024, 0.1), (8, 8192, 1024, 0.1)]:
+            pts = torch.from_numpy(syn.kitti_batch(B, N, config=2)).to(dev)
+            xyz = pts.permute(0, 2, 1)[:, :, :3]
+            start = torch.zeros(B, dtype=torch.long, device=dev)
+            new_xyz = ops.index_points(xyz, ops.fps(xyz, npoint, start))
+            t_build = time_ms(lambda: ops.ball_grid(xyz, radius))
+            grid = ops.ball_grid(xyz, radius)
+            for method in ("scan", "grid", "grid-cells", "grid-scan"):
+                t = time_ms(lambda: ops.ball_query(radius, 32, xyz, new_xyz, grid=None if method == "scan" else grid,
+                                                   method=method))
+                print(json.dumps(dict(sweep="ball", B=B, N=N, S=npoint, method=method, ms=round(t, 4),
+                                      build_ms=round(t_build, 4),
+                                      gbs=round((B * npoint * N * 12 + B * npoint * 256) / t / 1e6, 1))), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w") as f:
         json.dump(out, f, indent=1)
