@@ -179,131 +179,156 @@ ball_grid_build_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, in
 }
 
 // ------------------------------------------------------------------------------------------------ query
+constexpr int kGqTile = 2048;   // points per staged tile in the dense phase (32 KB as float4)
+
+// One CTA = WARPS centroids of one cloud.
+//   phase 1 (per warp): count the candidates of the 27 neighbouring cells; at most `threshold` -> test them all,
+//                       128 per trip with the four 16-byte loads of a lane in flight together, hits -> bitmap ->
+//                       first K set bits.  More -> the centroid is left pending.
+//   phase 2 (per CTA) : the pending (dense) centroids scan the raw cloud in index order through tiles staged in
+//                       shared memory by the whole CTA (the bitmap space is reused); early exit per warp and per CTA.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC,
-                       const float* __restrict__ qxyz, int64_t qB, int64_t qN, int64_t qC, int N, int S, int64_t total_q,
+                       const float* __restrict__ qxyz, int64_t qB, int64_t qN, int64_t qC, int N, int S,
                        float radius2, int K, const unsigned char* __restrict__ ws_all, size_t ws_stride, int threshold,
                        int bm_words, int64_t* __restrict__ out) {
-    extern __shared__ unsigned bitmaps[];   // WARPS x bm_words, zero between queries
+    extern __shared__ __align__(16) unsigned char gq_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned* __restrict__ bm = bitmaps + (size_t)warp * bm_words;
-    for (int w = lane; w < bm_words; w += 32) bm[w] = 0u;
-    __syncwarp();
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * WARPS + warp;
+    const bool valid = s < S;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned char* ws = ws_all + (size_t)b * ws_stride;
+    const float* a = qxyz + (int64_t)b * qB + (int64_t)(valid ? s : 0) * qN;
+    const float ax = a[0], ay = a[qC], az = a[2 * qC];
+    const float sa = sqnorm3(ax, ay, az);
+    int64_t* __restrict__ o = out + ((int64_t)b * S + (valid ? s : 0)) * K;
+    int cnt = valid ? 0 : K;          // out-of-range warps are born finished
+    int64_t first = N;
+    bool pending = false;
 
-    for (int64_t q = (int64_t)blockIdx.x * WARPS + warp; q < total_q; q += (int64_t)gridDim.x * WARPS) {
-        const int b = (int)(q / S);
-        const unsigned char* ws = ws_all + (size_t)b * ws_stride;
+    if (valid) {
         const GridHdr* h = grid_hdr(ws);
         const int* __restrict__ cell_start = grid_cells(ws);
-        const float4* __restrict__ sorted = grid_sorted(ws);
-        const float* a = qxyz + (int64_t)b * qB + (q % S) * qN;
-        const float ax = a[0], ay = a[qC], az = a[2 * qC];
-        const float sa = sqnorm3(ax, ay, az);
         const int gx = h->g[0], gy = h->g[1], gz = h->g[2];
         const int cx = grid_coord(ax, h->lo[0], h->inv[0]);
         const int cy = grid_coord(ay, h->lo[1], h->inv[1]);
         const int cz = grid_coord(az, h->lo[2], h->inv[2]);
         // the 27 neighbouring cells = 9 runs along x; lane r < 9 owns run (dy, dz) = (r % 3 - 1, r / 3 - 1)
-        int r_beg = 0, r_end = 0;
+        int r_beg = 0, r_len = 0;
         if (lane < 9) {
             const int y = cy + lane % 3 - 1, z = cz + lane / 3 - 1;
             const int x0 = max(cx - 1, 0), x1 = min(cx + 1, gx - 1);
             if (y >= 0 && y < gy && z >= 0 && z < gz && x0 <= x1) {
                 const int row = (z * gy + y) * gx;
                 r_beg = cell_start[row + x0];
-                r_end = cell_start[row + x1 + 1];
+                r_len = cell_start[row + x1 + 1] - r_beg;
             }
         }
-        int cand = r_end - r_beg;
+        int beg[9], len[9], cand = 0;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-
-        int64_t* __restrict__ o = out + q * K;
-        int cnt = 0;
-        int64_t first = N;
+        for (int r = 0; r < 9; ++r) {
+            beg[r] = __shfl_sync(0xffffffffu, r_beg, r);
+            len[r] = __shfl_sync(0xffffffffu, r_len, r);
+            cand += len[r];
+        }
         if (cand <= threshold) {
-            // ---- sparse neighbourhood: test every candidate, mark hits by original index
+            // ---- sparse neighbourhood: every candidate is tested; hits are ordered through the bitmap
+            unsigned* __restrict__ bm = reinterpret_cast<unsigned*>(gq_smem) + (size_t)warp * bm_words;
+            for (int w = lane; w < bm_words; w += 32) bm[w] = 0u;
+            __syncwarp();
+            const float4* __restrict__ sorted = grid_sorted(ws);
             int hits = 0;
-            for (int r = 0; r < 9; ++r) {
-                const int beg = __shfl_sync(0xffffffffu, r_beg, r), end = __shfl_sync(0xffffffffu, r_end, r);
-                for (int i0 = beg; i0 < end; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool hit = false;
-                    int j = 0;
-                    if (i < end) {
-                        const float4 v = sorted[i];
-                        const float d = sqdist_expand(ax, ay, az, sa, v.x, v.y, v.z, sqnorm3(v.x, v.y, v.z));
-                        hit = !(d > radius2);
-                        j = __float_as_int(v.w);
+            for (int t0 = 0; t0 < cand; t0 += 128) {
+                float4 v[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int off = t0 + u * 32 + lane, i = -1;
+#pragma unroll
+                    for (int r = 0; r < 9; ++r) {
+                        if (i < 0 && off < len[r]) i = beg[r] + off;
+                        off -= len[r];
                     }
+                    ok[u] = i >= 0;
+                    v[u] = ok[u] ? sorted[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float d = sqdist_expand(ax, ay, az, sa, v[u].x, v[u].y, v[u].z, sqnorm3(v[u].x, v[u].y, v[u].z));
+                    const bool hit = ok[u] && !(d > radius2);
+                    const int j = __float_as_int(v[u].w);
                     if (hit) atomicOr(&bm[j >> 5], 1u << (j & 31));
                     hits += __popc(__ballot_sync(0xffffffffu, hit));
                 }
             }
             __syncwarp();
-            if (hits > 0) {
-                for (int w0 = 0; w0 < bm_words; w0 += 32) {
-                    unsigned word = bm[w0 + lane];     // bm_words is a multiple of 32
-                    bm[w0 + lane] = 0u;
-                    const int pc = __popc(word);
-                    int incl = pc;
+            for (int w0 = 0; w0 < bm_words && hits > 0 && cnt < K; w0 += 32) {
+                unsigned word = bm[w0 + lane];     // bm_words is a multiple of 32
+                const int pc = __popc(word);
+                int incl = pc;
 #pragma unroll
-                    for (int s = 1; s < 32; s <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, s);
-                        if (lane >= s) incl += t;
-                    }
-                    const unsigned has = __ballot_sync(0xffffffffu, pc > 0);
-                    if (cnt == 0 && has) {
-                        const int src = __ffs(has) - 1;
-                        const int lowest = (w0 + lane) * 32 + __ffs(word) - 1;
-                        first = __shfl_sync(0xffffffffu, lowest, src);
-                    }
-                    int pos = cnt + incl - pc;
-                    while (word && pos < K) {
-                        o[pos++] = (int64_t)(w0 + lane) * 32 + (__ffs(word) - 1);
-                        word &= word - 1;
-                    }
-                    cnt += __shfl_sync(0xffffffffu, incl, 31);
-                    hits -= __shfl_sync(0xffffffffu, incl, 31);
-                    if (cnt >= K || hits <= 0) {
-                        // words not yet visited may still hold bits (cnt >= K): clear them
-                        if (hits > 0)
-                            for (int w = w0 + 32 + lane; w < bm_words; w += 32) bm[w] = 0u;
-                        break;
-                    }
+                for (int sh = 1; sh < 32; sh <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, sh);
+                    if (lane >= sh) incl += t;
                 }
-                __syncwarp();
+                const unsigned has = __ballot_sync(0xffffffffu, pc > 0);
+                if (cnt == 0 && has) {
+                    const int lowest = (w0 + lane) * 32 + __ffs(word) - 1;
+                    first = __shfl_sync(0xffffffffu, lowest, __ffs(has) - 1);
+                }
+                int pos = cnt + incl - pc;
+                while (word && pos < K) {
+                    o[pos++] = (int64_t)(w0 + lane) * 32 + (__ffs(word) - 1);
+                    word &= word - 1;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                cnt += total;
+                hits -= total;
             }
         } else {
-            // ---- dense neighbourhood: ordered scan over the raw cloud, ends after a short prefix
-            const float* __restrict__ p = xyz + (int64_t)b * xB;
-            for (int c = 0; c < N && cnt < K; c += 64) {
-                const int i0 = c + lane, i1 = c + 32 + lane;
-                bool h0 = false, h1 = false;
-                if (i0 < N) {
-                    const float x = p[(int64_t)i0 * xN], y = p[(int64_t)i0 * xN + xC], z = p[(int64_t)i0 * xN + 2 * xC];
-                    h0 = !(sqdist_expand(ax, ay, az, sa, x, y, z, sqnorm3(x, y, z)) > radius2);
-                }
-                if (i1 < N) {
-                    const float x = p[(int64_t)i1 * xN], y = p[(int64_t)i1 * xN + xC], z = p[(int64_t)i1 * xN + 2 * xC];
-                    h1 = !(sqdist_expand(ax, ay, az, sa, x, y, z, sqnorm3(x, y, z)) > radius2);
-                }
-                const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-                if (m0 | m1) {
-                    if (cnt == 0) first = c + (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1);
-                    const int p0 = cnt + __popc(m0 & lt_mask);
-                    if (h0 && p0 < K) o[p0] = i0;
-                    const int n0 = cnt + __popc(m0);
-                    const int p1 = n0 + __popc(m1 & lt_mask);
-                    if (h1 && p1 < K) o[p1] = i1;
-                    cnt = n0 + __popc(m1);
-                }
-            }
+            pending = true;
         }
-        for (int k = min(cnt, K) + lane; k < K; k += 32) o[k] = first;   // pad with the first hit (or N)
     }
+
+    // ---- dense neighbourhoods: ordered scan over staged tiles, ends after a short prefix
+    if (__syncthreads_or(pending)) {
+        float4* __restrict__ tile = reinterpret_cast<float4*>(gq_smem);
+        const float* __restrict__ p = xyz + (int64_t)b * xB;
+        for (int t0 = 0; t0 < N; t0 += kGqTile) {
+            const int tn = min(kGqTile, N - t0);
+            for (int i = threadIdx.x; i < tn; i += WARPS * 32) {
+                const float* r = p + (int64_t)(t0 + i) * xN;
+                const float x = r[0], y = r[xC], z = r[2 * xC];
+                tile[i] = make_float4(x, y, z, sqnorm3(x, y, z));
+            }
+            __syncthreads();
+            if (pending) {   // warp-uniform
+                for (int c = 0; c < tn && cnt < K; c += 64) {
+                    const int i0 = c + lane, i1 = c + 32 + lane;
+                    const float4 v0 = i0 < tn ? tile[i0] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+                    const float4 v1 = i1 < tn ? tile[i1] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+                    const bool h0 = !(sqdist_expand(ax, ay, az, sa, v0.x, v0.y, v0.z, v0.w) > radius2);
+                    const bool h1 = !(sqdist_expand(ax, ay, az, sa, v1.x, v1.y, v1.z, v1.w) > radius2);
+                    const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                    if (m0 | m1) {
+                        if (cnt == 0) first = t0 + c + (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1);
+                        const int p0 = cnt + __popc(m0 & lt_mask);
+                        if (h0 && p0 < K) o[p0] = t0 + i0;
+                        const int n0 = cnt + __popc(m0);
+                        const int p1 = n0 + __popc(m1 & lt_mask);
+                        if (h1 && p1 < K) o[p1] = t0 + i1;
+                        cnt = n0 + __popc(m1);
+                    }
+                }
+                pending = cnt < K;
+            }
+            if (!__syncthreads_or(pending)) break;
+        }
+    }
+    if (valid)
+        for (int k = min(cnt, K) + lane; k < K; k += 32) o[k] = first;   // pad with the first hit (or N)
 }
 
 }  // namespace pn
@@ -336,40 +361,41 @@ PN_EXPORT int pn_ball_grid_build_f32(const float* xyz, int64_t xB, int64_t xN, i
 
 PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const float* new_xyz, int64_t qB,
                                      int64_t qN, int64_t qC, int B, int N, int S, float radius2, int nsample,
-                                     const void* grid, size_t grid_bytes, int threshold, int64_t* out_idx,
+                                     const void* grid_ws, size_t grid_bytes, int threshold, int64_t* out_idx,
                                      pn_stream_t stream) {
     using namespace pn;
-    PN_REQUIRE(xyz && new_xyz && out_idx && grid, PN_ERR_BAD_ARG, "pn_ball_query_grid_f32: null pointer");
+    PN_REQUIRE(xyz && new_xyz && out_idx && grid_ws, PN_ERR_BAD_ARG, "pn_ball_query_grid_f32: null pointer");
     PN_REQUIRE(B > 0 && N > 0 && S > 0 && nsample > 0, PN_ERR_BAD_ARG,
                "pn_ball_query_grid_f32: B, N, S, nsample must be positive (got %d, %d, %d, %d)", B, N, S, nsample);
     PN_REQUIRE(grid_bytes >= pn_ball_grid_bytes(B, N), PN_ERR_BAD_ARG,
                "pn_ball_query_grid_f32: grid buffer holds %zu bytes, %zu needed", grid_bytes, pn_ball_grid_bytes(B, N));
     PN_REQUIRE(N <= 1048576, PN_ERR_UNSUPPORTED, "pn_ball_query_grid_f32: N=%d exceeds 1048576", N);
+    PN_REQUIRE(B <= 65535, PN_ERR_UNSUPPORTED, "pn_ball_query_grid_f32: B=%d exceeds 65535", B);
     if (threshold == 0) {
-        // break-even between testing C candidates and scanning ~ 33 N / (hits + 1) points, hits ~ 0.155 C
+        // break-even between testing C candidates (~7 cycles each, latency-bound) and scanning ~ 33 N / (hits + 1)
+        // staged points (~1.5 cycles each), hits ~ 0.155 C
         int t = 64;
-        while ((int64_t)t * t < (int64_t)213 * N) t += 64;
+        while ((int64_t)t * t < (int64_t)64 * N) t += 64;
         threshold = t;
     }
     const int bm_words = (int)ceil_div(ceil_div(N, 32), 32) * 32;
-    const int64_t total_q = (int64_t)B * S;
     cudaStream_t st = (cudaStream_t)stream;
     auto launch = [&](auto kern, int warps) -> int {
-        const size_t smem = (size_t)warps * bm_words * 4;
+        size_t smem = (size_t)warps * bm_words * 4;
+        if (smem < (size_t)kGqTile * 16) smem = (size_t)kGqTile * 16;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             cudaGetLastError();
             set_error("pn_ball_query_grid_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        const int64_t ctas = ceil_div(total_q, warps);
-        const int64_t cap = 148LL * 16;
-        kern<<<(unsigned)(ctas < cap ? ctas : cap), warps * 32, smem, st>>>(
-            xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, total_q, radius2, nsample, static_cast<const unsigned char*>(grid),
-            grid_cloud_bytes(N), threshold, bm_words, out_idx);
+        dim3 grid((unsigned)ceil_div(S, warps), (unsigned)B);
+        kern<<<grid, warps * 32, smem, st>>>(xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
+                                             static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N), threshold,
+                                             bm_words, out_idx);
         return finish_launch("pn_ball_query_grid_f32");
     };
-    if (N <= 32768) return launch(ball_query_grid_kernel<8>, 8);
-    if (N <= 262144) return launch(ball_query_grid_kernel<4>, 4);
-    return launch(ball_query_grid_kernel<1>, 1);
+    if (N <= 32768) return launch(ball_query_grid_kernel<8>, 8);      // bitmaps: <= 4 KB per warp
+    if (N <= 262144) return launch(ball_query_grid_kernel<4>, 4);     // <= 32 KB per warp
+    return launch(ball_query_grid_kernel<1>, 1);                      // <= 128 KB
 }

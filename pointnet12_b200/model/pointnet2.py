@@ -199,6 +199,17 @@ class PointNet2SemSeg(_Net):
         main = torch.cuda.current_stream(points.device)
         side_a, side_b = self._side_streams(points.device)
 
+        # the level-1 ball-query buckets depend on xyz only: built on a side stream beside the level-1 sampling
+        begin = torch.cuda.Event()
+        begin.record(main)
+        grid1 = None
+        if N >= ops.GRID_MIN_POINTS:
+            with torch.cuda.stream(side_a):
+                side_a.wait_event(begin)
+                grid1 = ops.ball_grid(x0, sa[0].radius)
+                grid_ready = torch.cuda.Event()
+                grid_ready.record(side_a)
+
         # level-1 sampling (the long serial kernel) on the main stream
         x1 = ops.index_points(x0, farthest_point_sample(x0, sa[0].npoint, fps_starts[0]))
         fork = torch.cuda.Event()
@@ -221,7 +232,9 @@ class PointNet2SemSeg(_Net):
             done_a.record(side_a)
 
         # feature path on the main stream
-        balls[0] = ops.ball_query(sa[0].radius, sa[0].nsample, x0, x1)
+        if grid1 is not None:
+            main.wait_event(grid_ready)
+        balls[0] = ops.ball_query(sa[0].radius, sa[0].nsample, x0, x1, grid=grid1)
         fs = [f0, sa[0].features(x0, f0, x1, balls[0])]
         for i in (1, 2, 3):
             main.wait_event(ready[i])

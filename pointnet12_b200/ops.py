@@ -131,7 +131,7 @@ def ball_grid(xyz: torch.Tensor, radius: float) -> BallGrid:
 
 
 def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
-               grid: Optional[BallGrid] = None, method: str = "auto") -> torch.Tensor:
+               grid: Optional[BallGrid] = None, method: str = "auto", threshold: Optional[int] = None) -> torch.Tensor:
     """query_ball_point (pointnet_util.py:87-107) -> int64 [B, S, nsample].
     method: "auto" (grid buckets for N >= GRID_MIN_POINTS, ordered scan below), "scan" (pn_ball_query_f32),
     "grid" / "grid-cells" / "grid-scan" (pn_ball_query_grid_f32 with the automatic threshold / every query through
@@ -154,7 +154,8 @@ def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Te
             grid = BallGrid(xyz, radius)
         elif (grid.B, grid.N) != (B, N) or grid.r2 != r2:
             raise ValueError("grid was built for another cloud shape or radius")
-        threshold = {"grid": 0, "grid-cells": 2 ** 31 - 1, "grid-scan": -1}[method]
+        if threshold is None:
+            threshold = {"grid": 0, "grid-cells": 2 ** 31 - 1, "grid-scan": -1}[method]
         nv.call("pn_ball_query_grid_f32", xyz.data_ptr(), *xyz.stride(), new_xyz.data_ptr(), *new_xyz.stride(), B, N, S,
                 r2, int(nsample), grid.buf.data_ptr(), grid.nbytes, threshold, out.data_ptr(), _stream())
     return out

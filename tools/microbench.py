@@ -84,6 +84,9 @@ def main():
             new_xyz = ops.index_points(xyz, ops.fps(xyz, npoint, start))
             t_build = time_ms(lambda: ops.ball_grid(xyz, radius))
             grid = ops.ball_grid(xyz, radius)
+            for thr in (512, 1024, 2048, 4096, 8192):
+                t = time_ms(lambda: ops.ball_query(radius, 32, xyz, new_xyz, grid=grid, method="grid", threshold=thr))
+                print(json.dumps(dict(sweep="ball-threshold", B=B, N=N, S=npoint, threshold=thr, ms=round(t, 4))), flush=True)
             for method in ("scan", "grid", "grid-cells", "grid-scan"):
                 t = time_ms(lambda: ops.ball_query(radius, 32, xyz, new_xyz, grid=None if method == "scan" else grid,
                                                    method=method))
