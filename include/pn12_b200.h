@@ -188,11 +188,21 @@ int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float*
  * the three coarse rows + skip concat straight into the tensor-core operand, then the conv+BN+ReLU chain.
  * With out_mode LOG_SOFTMAX and the segmentation head appended to the chain (pointnet2.py:172-175) the
  * log-probabilities [B, N, classes] are written directly.  out rows (b, n) have leading dimension ldo and
- * must be contiguous over the batch.  Arguments as pn_three_interpolate_f32. */
+ * must be contiguous over the batch.  Arguments as pn_three_interpolate_f32.
+ * relu_in = 1 (needs points1 == NULL): ReLU is applied to the interpolated channels before the chain.  This is how
+ * a caller folds the level's FIRST layer into the coarse level -- interpolation is linear and its weights sum
+ * to one, so conv(interp(p2)) + b == interp(conv(p2) + b): the caller runs that layer once over the S coarse
+ * points (pn_mlp_rows_bf16x3, no ReLU), passes the result as points2 and drops the layer from the chain. */
 int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
                      int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2, int S,
-                     const int64_t* idx, const float* weight, int B, int N, int out_mode, float* out, int64_t ldo,
-                     pn_stream_t stream);
+                     const int64_t* idx, const float* weight, int relu_in, int B, int N, int out_mode, float* out,
+                     int64_t ldo, pn_stream_t stream);
+
+/* Tuning hook for the fused chains: 0 = automatic (chains whose packed weights fit in shared memory run on the
+ * resident-weight kernel: weights loaded once per CTA, 2 or 4 warp groups per CTA each with its own row tile
+ * and TMEM slice; larger chains stream their weights through a ring), 1 = always stream, 2 = resident or fail.
+ * Process-wide; meant for benchmarks and tests. */
+int pn_mlp_set_engine(int engine);
 
 #ifdef __cplusplus
 }

@@ -193,6 +193,7 @@ struct TcIo {
     const float* p1; int64_t p1B, p1N, p1C; int D1;
     const float* p2; int64_t p2B, p2N, p2C; int D2; int S2;
     const int64_t* idx3; const float* w3;
+    int relu_in;   // TC_IN_FP: ReLU applied to the interpolated channels (layer 1 was folded into the coarse level)
     // output
     int out_mode; float* y; int64_t ldy; int group;
 };
@@ -258,8 +259,9 @@ __device__ __forceinline__ float row_value(const TcIo& io, const RowCtx<IN>& c, 
     } else {
         if (k < io.D1) return c.p1row[k * io.p1C];
         const int d = k - io.D1;
-        return __fadd_rn(__fadd_rn(__fmul_rn(c.r0[d * io.p2C], c.w0), __fmul_rn(c.r1[d * io.p2C], c.w1)),
-                         __fmul_rn(c.r2[d * io.p2C], c.w2));
+        const float v = __fadd_rn(__fadd_rn(__fmul_rn(c.r0[d * io.p2C], c.w0), __fmul_rn(c.r1[d * io.p2C], c.w1)),
+                                  __fmul_rn(c.r2[d * io.p2C], c.w2));
+        return io.relu_in ? fmaxf(v, 0.0f) : v;
     }
 }
 
@@ -290,6 +292,10 @@ __device__ __forceinline__ void row_load32(const TcIo& io, const RowCtx<IN>& c, 
                 v[4 * j + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, c.w0), __fmul_rn(b.y, c.w1)), __fmul_rn(e.y, c.w2));
                 v[4 * j + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, c.w0), __fmul_rn(b.z, c.w1)), __fmul_rn(e.z, c.w2));
                 v[4 * j + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a.w, c.w0), __fmul_rn(b.w, c.w1)), __fmul_rn(e.w, c.w2));
+            }
+            if (io.relu_in) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
             return;
         }
@@ -561,10 +567,273 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(ch.tmem_cols));
 }
 
+// ------------------------------------------------------------------------------------------------ resident kernel
+// Chains whose packed weights fit in shared memory (<= ~225 KB: sa1, sa2, fp1 + segmentation head, the PointNet
+// per-point chains) do not stream anything: the whole blob (weight images + bias table) is brought in ONCE per CTA
+// with cp.async.bulk and stays resident; the CTA is persistent over row tiles.  512 threads form GROUPS independent
+// warp groups, each owning its own 128-row tile and its own slice of TMEM (512 / GROUPS columns: accumulator + A
+// operand); while one group waits for its MMAs the others run producers / epilogues, so the tensor pipe and the
+// issue slots overlap without any hand-written software pipeline.  Groups synchronise on named barriers.
+//   WPG = 8: 2 groups, warp gw owns TMEM lanes 32*(gw%4).. and column half gw/4     (x_cols + a_k <= 256)
+//   WPG = 4: 4 groups, a thread handles every column of its row                      (x_cols + a_k <= 128)
+constexpr int kResThreads = 512;
+
+__device__ __forceinline__ void tc_group_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int IN, int WPG>
+__global__ void __launch_bounds__(kResThreads, 1)
+mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restrict__ blob, const __grid_constant__ TcIo io) {
+    constexpr int GROUPS = 16 / WPG, GTHREADS = WPG * 32, HALVES = WPG / 4, GCOLS = 512 / GROUPS, CSTEP = 32 * HALVES;
+    extern __shared__ __align__(128) unsigned char smem[];
+    // layout: [blob: weight images | bias table][barriers: weights, done[GROUPS]][tmem ptr]
+    const float* sbias = reinterpret_cast<const float*>(smem + ch.bias_off);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + ((ch.blob_bytes + 15u) & ~15u));
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 1 + GROUPS);
+    const unsigned bar_w = tc_smem_u32(&bars[0]);
+    const unsigned smem_w = tc_smem_u32(smem);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = warp / WPG, gw = warp % WPG;
+    const unsigned bar_done = tc_smem_u32(&bars[1 + g]);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        tc_mbar_init(bar_w, 1);
+        for (int i = 0; i < GROUPS; ++i) tc_mbar_init(tc_smem_u32(&bars[1 + i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the whole blob, in pieces of at most 32 KB, all completing on one barrier
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(ch.blob_bytes) : "memory");
+        for (unsigned off = 0; off < ch.blob_bytes; off += 32768u) {
+            const unsigned n = ch.blob_bytes - off < 32768u ? ch.blob_bytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_w + off),
+                         "l"(blob + off), "r"(n), "r"(bar_w)
+                         : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tbase = *tmem_slot + (unsigned)(g * GCOLS);
+    const int wl = gw & 3, half = gw >> 2;                           // lane quarter (== warp % 4) / column half
+    const unsigned tlane = tbase + ((unsigned)(wl * 32) << 16);      // this warp's 32 TMEM lanes
+    const unsigned t_x = tlane;                                      // accumulator columns
+    const unsigned t_ahi = tlane + ch.x_cols, t_alo = t_ahi + ch.a_lo_off;
+    const unsigned a_hi_col = tbase + ch.x_cols, a_lo_col = a_hi_col + ch.a_lo_off;   // lane 0 addresses for the MMA
+    unsigned done_phase = 0;
+    bool w_ready = false;
+
+    const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
+    const int64_t ntiles = io.nseg * tiles_per_seg;
+    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + g; tile < ntiles; tile += (int64_t)gridDim.x * GROUPS) {
+        const int64_t seg = tile / tiles_per_seg;
+        const int64_t r_in_seg = (tile % tiles_per_seg) * 128 + wl * 32 + lane;
+        RowCtx<IN> rc;
+        rc.valid = r_in_seg < io.seg_rows;
+        rc.row = seg * io.seg_rows + r_in_seg;
+        row_setup<IN>(io, rc);
+
+        for (int l = 0; l < ch.nlayers; ++l) {
+            const TcLayer& L = ch.L[l];
+            const bool last = l + 1 == ch.nlayers;
+            if (l == 0) {
+                // ---- producer: this thread's row -> TMEM A region
+                for (int k0 = half * 32; k0 < L.k_pad; k0 += CSTEP) {
+                    float v[32];
+                    row_load32<IN>(io, rc, k0, L.k_real, v);
+                    tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                tc_group_bar(1 + g, GTHREADS);
+            }
+            if (gw == 0) {
+                if (lane == 0) {
+                    if (!w_ready) tc_mbar_wait(bar_w, 0);
+                    tc_fence_after();
+                    const unsigned wl_base = smem_w + L.w_off;
+                    const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(L.n_pad >> 3) << 17) | (8u << 24);
+                    const int ns = (L.k_pad + kTcKSub - 1) / kTcKSub;
+                    for (int s = 0; s < ns; ++s) {
+                        const int kw = min(kTcKSub, L.k_pad - s * kTcKSub);
+                        const unsigned b_hi = wl_base + (unsigned)L.n_pad * (s * kTcKSub) * 4, b_lo = b_hi + (unsigned)L.n_pad * kw * 2;
+                        const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
+                                                         ((unsigned long long)((((unsigned)kw / 8) * 128u >> 4) & 0x3FFF) << 32) |
+                                                         (1ull << 46);
+                        for (int t = 0; t < kw / 16; ++t) {
+                            const unsigned kcol = (unsigned)(s * kTcKSub + t * 16) / 2;   // A columns of this K step
+                            const unsigned long long dh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
+                            const unsigned long long dl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
+                            const unsigned acc0 = (s > 0 || t > 0) ? 1u : 0u;
+                            asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                             tbase),
+                                         "r"(a_hi_col + kcol), "l"(dh), "r"(idesc), "r"(acc0)
+                                         : "memory");
+                            asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                             tbase),
+                                         "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
+                                         : "memory");
+                            asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                             tbase),
+                                         "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
+                                         : "memory");
+                        }
+                    }
+                    tc_commit(bar_done);
+                }
+                __syncwarp();   // lanes 1-31 park here while lane 0 feeds the tensor core
+            }
+            tc_mbar_wait(bar_done, done_phase);
+            done_phase ^= 1;
+            if (!w_ready) {     // the bias table arrived with the weights: every reader observes the barrier once
+                tc_mbar_wait(bar_w, 0);
+                w_ready = true;
+            }
+            tc_fence_after();
+
+            // ---- epilogue: accumulator columns [0, n_pad)
+            const float* bias = sbias + L.b_off;
+            if (!last) {
+                for (int c0 = half * 32; c0 < L.n_pad; c0 += CSTEP) {
+                    unsigned r[32];
+                    tc_ld32(t_x + c0, r);
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float f = __uint_as_float(r[j]) + bias[c0 + j];
+                        v[j] = L.relu ? fmaxf(f, 0.0f) : f;
+                    }
+                    tc_store_split32(t_ahi + c0 / 2, t_alo + c0 / 2, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            } else if (io.out_mode == TC_OUT_ROWS) {
+                for (int c0 = half * 32; c0 < L.n_pad; c0 += CSTEP) {
+                    unsigned r[32];
+                    tc_ld32(t_x + c0, r);
+                    if (rc.valid) {
+                        float* dst = io.y + rc.row * io.ldy + c0;
+                        const int nleft = L.n_real - c0;
+                        const bool vec = nleft >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o;
+                            o.x = __uint_as_float(r[j]) + bias[c0 + j];
+                            o.y = __uint_as_float(r[j + 1]) + bias[c0 + j + 1];
+                            o.z = __uint_as_float(r[j + 2]) + bias[c0 + j + 2];
+                            o.w = __uint_as_float(r[j + 3]) + bias[c0 + j + 3];
+                            if (L.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            if (vec) {
+                                *reinterpret_cast<float4*>(dst + j) = o;
+                            } else {
+                                if (j < nleft) dst[j] = o.x;
+                                if (j + 1 < nleft) dst[j + 1] = o.y;
+                                if (j + 2 < nleft) dst[j + 2] = o.z;
+                                if (j + 3 < nleft) dst[j + 3] = o.w;
+                            }
+                        }
+                    }
+                }
+            } else if (io.out_mode == TC_OUT_MAX) {
+                // group = 32 consecutive rows = this warp: REDUX max per channel, lane j keeps channel c0 + j
+                const int64_t grp = rc.row / 32;
+                const bool any_valid = __any_sync(0xffffffffu, rc.valid);
+                const int64_t gi = __shfl_sync(0xffffffffu, grp, 0);
+                for (int c0 = half * 32; c0 < L.n_pad; c0 += CSTEP) {
+                    unsigned r[32];
+                    tc_ld32(t_x + c0, r);
+                    unsigned mine = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float f = __uint_as_float(r[j]) + bias[c0 + j];
+                        if (L.relu) f = fmaxf(f, 0.0f);
+                        const unsigned k = rc.valid ? tc_key(f) : 0u;
+                        const unsigned m = __reduce_max_sync(0xffffffffu, k);
+                        if (lane == j) mine = m;
+                    }
+                    const int n = c0 + lane;
+                    if (any_valid && n < L.n_real) io.y[gi * io.ldy + n] = tc_unkey(mine);
+                }
+            } else {   // TC_OUT_LOGSOFTMAX over the n_real (<= 64) classes of the row: column-half 0 warps only
+                if (half == 0) {
+                    float m = -CUDART_INF_F, ssum = 0.0f;
+                    for (int c0 = 0; c0 < L.n_pad; c0 += 32) {
+                        unsigned r[32];
+                        tc_ld32(t_x + c0, r);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < L.n_real) m = fmaxf(m, __uint_as_float(r[j]) + bias[c0 + j]);
+                    }
+                    for (int c0 = 0; c0 < L.n_pad; c0 += 32) {
+                        unsigned r[32];
+                        tc_ld32(t_x + c0, r);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < L.n_real) ssum += __expf((__uint_as_float(r[j]) + bias[c0 + j]) - m);
+                    }
+                    const float ls = __logf(ssum);
+                    for (int c0 = 0; c0 < L.n_pad; c0 += 32) {
+                        unsigned r[32];
+                        tc_ld32(t_x + c0, r);
+                        if (rc.valid) {
+                            float* dst = io.y + rc.row * io.ldy + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c0 + j < L.n_real) dst[j] = ((__uint_as_float(r[j]) + bias[c0 + j]) - m) - ls;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            tc_group_bar(1 + g, GTHREADS);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512));
+}
+
+static size_t tc_res_smem_bytes(const TcChain& c) { return (size_t)((c.blob_bytes + 15u) & ~15u) + 8 * 8 + 16; }
+
+// 0 = automatic (resident when the chain fits), 1 = always stream (mlp_tc_kernel), 2 = resident or fail
+static int g_tc_engine = 0;
+
+// Resident kernel usable?  Returns warps per group (8 or 4), or 0.
+static int tc_resident_wpg(const TcChain& c) {
+    if (tc_res_smem_bytes(c) > 227 * 1024) return 0;
+    int a_k = 2 * c.a_lo_off;
+    for (int l = 0; l < c.nlayers; ++l)
+        if (c.L[l].k_pad > kTcAChunk || c.L[l].n_pad > kTcNPass) return 0;
+    if (c.x_cols + a_k <= 128) return 4;
+    if (c.x_cols + a_k <= 256) return 8;
+    return 0;
+}
+
 static size_t tc_smem_bytes(const TcChain& c) { return (size_t)2 * c.stage_bytes + ((c.bias_floats * 4 + 15) & ~15) + 5 * 8 + 16; }
 
 template <int IN>
 static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaStream_t stream, const char* what) {
+    const int64_t ntiles_all = io.nseg * ((io.seg_rows + 127) / 128);
+    const int wpg = g_tc_engine == 1 ? 0 : tc_resident_wpg(ch);
+    PN_REQUIRE(g_tc_engine != 2 || wpg != 0, PN_ERR_UNSUPPORTED, "%s: chain does not fit the resident kernel", what);
+    if (wpg != 0) {
+        const size_t rsmem = tc_res_smem_bytes(ch);
+        auto launch_res = [&](auto rkern, int groups) -> int {
+            cudaError_t e = cudaFuncSetAttribute(rkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
+                return (int)e;
+            }
+            const int64_t want = (ntiles_all + groups - 1) / groups;
+            const unsigned grid = (unsigned)(want < 148 ? want : 148);
+            rkern<<<grid, kResThreads, rsmem, stream>>>(ch, static_cast<const unsigned char*>(blob), io);
+            return finish_launch(what);
+        };
+        return wpg == 8 ? launch_res(mlp_tc_res_kernel<IN, 8>, 2) : launch_res(mlp_tc_res_kernel<IN, 4>, 4);
+    }
     const size_t smem = tc_smem_bytes(ch);
     PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "%s: chain needs %zu bytes of shared memory", what, smem);
     auto kern = mlp_tc_kernel<IN>;
@@ -589,6 +858,12 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
 }  // namespace pn
 
 // ------------------------------------------------------------------------------------------------ C ABI
+PN_EXPORT int pn_mlp_set_engine(int engine) {
+    PN_REQUIRE(engine >= 0 && engine <= 2, PN_ERR_BAD_ARG, "pn_mlp_set_engine: 0 = automatic, 1 = streaming, 2 = resident");
+    pn::g_tc_engine = engine;
+    return PN_OK;
+}
+
 PN_EXPORT size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc) {
     pn::TcChain ch;
     const char* why;
@@ -679,8 +954,8 @@ PN_EXPORT int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, co
 
 PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
                                int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2,
-                               int S, const int64_t* idx, const float* weight, int B, int N, int out_mode, float* out,
-                               int64_t ldo, pn_stream_t stream) {
+                               int S, const int64_t* idx, const float* weight, int relu_in, int B, int N, int out_mode,
+                               float* out, int64_t ldo, pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
     int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_fp_mlp_bf16x3");
@@ -689,6 +964,7 @@ PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
     PN_REQUIRE((points1 != nullptr) == (D1 > 0) && desc->cin[0] == D1 + D2, PN_ERR_BAD_ARG,
                "pn_fp_mlp_bf16x3: first layer expects %d channels, inputs provide %d + %d", desc->cin[0], D1, D2);
     PN_REQUIRE(out_mode != TC_OUT_MAX, PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: out_mode must be 0 (rows) or 2 (log_softmax)");
+    PN_REQUIRE(!relu_in || D1 == 0, PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: relu_in needs points1 == NULL");
     PN_REQUIRE(B > 0 && N > 0 && S > 0 && ldo >= desc->cout[desc->nlayers - 1], PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: bad sizes");
     TcIo io = {};
     io.nseg = B;
@@ -696,6 +972,7 @@ PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
     io.p1 = points1; io.p1B = p1B; io.p1N = p1N; io.p1C = p1C; io.D1 = D1;
     io.p2 = points2; io.p2B = p2B; io.p2N = p2N; io.p2C = p2C; io.D2 = D2; io.S2 = S;
     io.idx3 = idx; io.w3 = weight;
+    io.relu_in = relu_in;
     io.out_mode = out_mode;
     io.y = out;
     io.ldy = ldo;

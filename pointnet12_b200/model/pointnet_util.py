@@ -148,6 +148,25 @@ class FoldedLayers:
                 self._chain = ops.PackedChain([(w, b, r) for (w, b), r in zip(layers, relus)])
         return self._chain or None
 
+    def chain_folded_first(self, convs, bns, relus):
+        """(first, rest): the first layer as a one-layer chain WITHOUT activation and the remaining layers, for a
+        feature-propagation level without skip input: conv(interp(p2)) + b == interp(conv(p2) + b) because the
+        interpolation is linear and its weights sum to one, so the first layer runs once over the coarse points and
+        the fine level starts from relu(interp(.)).  None when the mode is 'fp32' or a part does not fit."""
+        if ops.mlp_mode() != "bf16x3" or len(convs) < 2:
+            return None
+        layers = self.get(convs, bns)
+        if getattr(self, "_split", None) is None or self._split_key is not self._layers:
+            dims = [(w.shape[1], w.shape[0]) for w, _ in layers]
+            if not (relus[0] and ops.PackedChain.supported(dims[:1]) and ops.PackedChain.supported(dims[1:])):
+                self._split = False
+            else:
+                (w0, b0), rest = layers[0], layers[1:]
+                self._split = (ops.PackedChain([(w0, b0, False)]),
+                               ops.PackedChain([(w, b, r) for (w, b), r in zip(rest, relus[1:])]))
+            self._split_key = self._layers
+        return self._split or None
+
 
 def _eval_only(module: nn.Module) -> None:
     if module.training:
@@ -293,6 +312,15 @@ class PointNetFeaturePropagation(nn.Module):
         if head is not None:
             folded, hconvs, hbns, hrelus, out_mode = head
             convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
+        if p1 is None and ops.FOLD_FIRST_FP_LAYER and N > p2.shape[1]:
+            split = folded.chain_folded_first(convs, bns, relus)
+            if split is not None:
+                # first layer at the coarse level (S rows instead of N), then one kernel: relu(weighted 3-row gather)
+                # -> the remaining layers (-> head -> log_softmax)
+                first, rest = split
+                S, D2 = p2.shape[1], p2.shape[2]
+                z = ops.mlp_rows_tc(first, p2.reshape(B * S, D2)).view(B, S, -1)
+                return ops.fp_mlp_tc(rest, None, z, idx, w, out_mode, relu_in=True)
         chain = folded.chain(convs, bns, relus)
         if chain is not None:
             # one kernel: weighted 3-row gather + skip concat -> tensor-core MLP chain (-> head -> log_softmax)

@@ -333,6 +333,15 @@ def mlp_mode() -> str:
     return _MLP_MODE
 
 
+def set_mlp_engine(engine: str = "auto") -> None:
+    """Tuning hook (pn_mlp_set_engine): 'auto' (resident-weight kernel when the packed chain fits in shared memory,
+    streaming ring otherwise), 'stream' or 'resident'."""
+    nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2}[engine])
+
+
+FOLD_FIRST_FP_LAYER = os.environ.get("PN12_FP_FOLD", "1") != "0"
+
+
 class PackedChain:
     """A conv+BN(+ReLU) chain folded and packed for the tensor-core kernels (device blob + descriptor)."""
 
@@ -410,8 +419,9 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
 
 
 def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torch.Tensor, idx: torch.Tensor,
-              weight: torch.Tensor, out_mode: int = OUT_ROWS) -> torch.Tensor:
-    """3-NN interpolation + skip concat + shared MLP (+ head + log_softmax) in one kernel -> [B, N, cout]."""
+              weight: torch.Tensor, out_mode: int = OUT_ROWS, relu_in: bool = False) -> torch.Tensor:
+    """3-NN interpolation + skip concat + shared MLP (+ head + log_softmax) in one kernel -> [B, N, cout].
+    relu_in: ReLU on the interpolated channels first (the level's first layer was folded into the coarse level)."""
     points2 = _cloud(points2, "points2")
     idx = _i64(idx, "idx")
     weight = _f32(weight, "weight").contiguous()
@@ -425,6 +435,6 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
     out = torch.empty((B, N, chain.cout), dtype=torch.float32, device=points2.device)
     with _on_device(points2):
         nv.call("pn_fp_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), _p(points1), *s1, D1, points2.data_ptr(),
-                *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), B, N, out_mode, out.data_ptr(), chain.cout,
-                _stream())
+                *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), B, N, out_mode,
+                out.data_ptr(), chain.cout, _stream())
     return out

@@ -32,6 +32,17 @@ def mlp_mode(request):
     ops.set_mlp_mode(old)
 
 
+@pytest.fixture(params=["auto", "stream"])
+def mlp_engine(request):
+    """Run a chain test on both tensor-core kernels: resident weights + warp groups (where the chain fits) and the
+    streaming ring."""
+    from pointnet12_b200 import ops
+
+    ops.set_mlp_engine(request.param)
+    yield request.param
+    ops.set_mlp_engine("auto")
+
+
 @pytest.fixture(scope="module")
 def dev():
     if not torch.cuda.is_available():
@@ -376,7 +387,7 @@ def _rand_layers(dims, seed, last_relu=True):
                                        ([(259, 256), (256, 256), (256, 512)], 700), ([(768, 256), (256, 256)], 129),
                                        ([(320, 256), (256, 128)], 1024),
                                        ([(128, 128), (128, 128), (128, 128), (128, 128), (128, 19)], 5000)])
-def test_mlp_rows_tc_vs_oracle(dev, dims, rows):
+def test_mlp_rows_tc_vs_oracle(dev, mlp_engine, dims, rows):
     """pn_mlp_rows_bf16x3: every chain shape of PointNet2SemSeg (incl. multi-slice K, two-chunk K, two-pass N)."""
     from pointnet12_b200 import ops
 
@@ -389,7 +400,7 @@ def test_mlp_rows_tc_vs_oracle(dev, dims, rows):
     assert rel_err(got, want) < TC_TOL
 
 
-def test_mlp_rows_tc_max_and_log_softmax(dev):
+def test_mlp_rows_tc_max_and_log_softmax(dev, mlp_engine):
     from pointnet12_b200 import ops
 
     layers = _rand_layers([(67, 64), (64, 128)], seed=5, last_relu=True)
@@ -414,7 +425,7 @@ def test_mlp_rows_tc_max_and_log_softmax(dev):
 
 
 @pytest.mark.parametrize("D,msg", [(1, False), (64, False), (128, True), (0, False)])
-def test_sa_mlp_max_tc_vs_oracle(dev, D, msg):
+def test_sa_mlp_max_tc_vs_oracle(dev, mlp_engine, D, msg):
     """Fused grouping + MLP + max against the oracle's group -> linear x3 -> max."""
     from pointnet12_b200 import ops
 
@@ -433,7 +444,7 @@ def test_sa_mlp_max_tc_vs_oracle(dev, D, msg):
 
 
 @pytest.mark.parametrize("D1,D2,S", [(0, 128, 100), (64, 256, 50), (7, 33, 20), (256, 512, 16)])
-def test_fp_mlp_tc_vs_oracle(dev, D1, D2, S):
+def test_fp_mlp_tc_vs_oracle(dev, mlp_engine, D1, D2, S):
     from pointnet12_b200 import ops
 
     rng = np.random.default_rng(D1 + D2)
@@ -450,6 +461,66 @@ def test_fp_mlp_tc_vs_oracle(dev, D1, D2, S):
     chain = ops.PackedChain([(cuda(wt, dev), cuda(b, dev), r) for wt, b, r in layers])
     got = ops.fp_mlp_tc(chain, cuda(p1, dev) if D1 else None, cuda(p2, dev), cuda(idx, dev), cuda(w, dev), ops.OUT_ROWS)
     assert rel_err(got, want) < TC_TOL
+
+
+@pytest.mark.parametrize("dims,rows,mode", [([(4, 32), (32, 32), (32, 64)], 128 * 1300 + 32, "max"),
+                                            ([(128, 128), (128, 128), (128, 128), (128, 19)], 128 * 700 + 5, "logsoftmax"),
+                                            ([(67, 64), (64, 64), (64, 128)], 128 * 650 + 64, "rows")])
+def test_mlp_resident_many_tiles(dev, dims, rows, mode):
+    """The resident-weight kernel is persistent: every warp group walks many row tiles (ragged tail included)."""
+    from pointnet12_b200 import ops
+
+    layers = _rand_layers(dims, seed=rows % 1000, last_relu=(mode == "max"))
+    x = np.random.default_rng(rows).normal(size=(rows, dims[0][0])).astype(np.float32)
+    ref = _chain_ref(x, layers)
+    chain = ops.PackedChain([(cuda(w, dev), cuda(b, dev), r) for w, b, r in layers])
+    try:
+        ops.set_mlp_engine("resident")
+        if mode == "max":
+            got, want = ops.mlp_rows_tc(chain, cuda(x, dev), ops.OUT_MAX32), orc.group_max(ref, 32)
+        elif mode == "logsoftmax":
+            got, want = ops.mlp_rows_tc(chain, cuda(x, dev), ops.OUT_LOG_SOFTMAX), orc.log_softmax(ref)
+        else:
+            got, want = ops.mlp_rows_tc(chain, cuda(x, dev), ops.OUT_ROWS), ref
+    finally:
+        ops.set_mlp_engine("auto")
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TC_TOL
+
+
+def test_fp_first_layer_folded_into_coarse_level(dev):
+    """PointNetFeaturePropagation without skip input: conv1(interp(p2)) == interp(conv1(p2)) -- the block runs its
+    first layer over the coarse points and the fused kernel starts from relu(interp(.)); same result as the oracle's
+    interpolate -> conv chain within the tensor-core tolerance."""
+    from pointnet12_b200 import ops
+    from pointnet12_b200.model import pointnet_util as U
+
+    rng = np.random.default_rng(77)
+    B, N, S = 2, 3000, 200
+    x1 = rng.uniform(-1, 1, size=(B, N, 3)).astype(np.float32)
+    x2 = np.ascontiguousarray(x1[:, :S])
+    p2 = rng.normal(size=(B, S, 128)).astype(np.float32)
+    fp = U.PointNetFeaturePropagation(128, [128, 128, 128]).to(dev).eval()
+    with torch.no_grad():
+        for bn in fp.mlp_bns:
+            bn.running_mean.normal_(0, 0.1)
+            bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_(0, 0.1)
+    layers = [(w.cpu().numpy(), b.cpu().numpy(), True) for w, b in
+              (U.fold_conv_bn(c, b) for c, b in zip(fp.mlp_convs, fp.mlp_bns))]
+    idx, wgt, _, _ = orc.three_nn(x1, x2)
+    want = _chain_ref(orc.three_interpolate(p2, idx, wgt).reshape(B * N, -1), layers).reshape(B, N, -1)
+    args = (cuda(x1, dev).permute(0, 2, 1), cuda(x2, dev).permute(0, 2, 1), None, cuda(p2, dev).permute(0, 2, 1))
+    with torch.no_grad():
+        got = fp(*args).permute(0, 2, 1)
+        assert rel_err(got, want) < FEAT_TOL
+        old, ops.FOLD_FIRST_FP_LAYER = ops.FOLD_FIRST_FP_LAYER, False
+        try:
+            got_unfolded = fp(*args).permute(0, 2, 1)
+        finally:
+            ops.FOLD_FIRST_FP_LAYER = old
+    assert rel_err(got_unfolded, want) < FEAT_TOL
 
 
 # ------------------------------------------------------------------------------------------------ blocks / networks
