@@ -89,6 +89,9 @@ int pn_ball_query_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, cons
  * threshold: 0 = automatic (~sqrt(213 N)), negative = always scan, INT_MAX = always use the cells.
  * Limits: N <= 1048576. */
 size_t pn_ball_grid_bytes(int B, int N);
+/* The bucket-sorted point order stored in a grid built by pn_ball_grid_build_f32, as (pointer, element stride, batch
+ * stride) in int32 elements: order[b*bstride + r*estride] = original index of the r-th point of cloud b in cell order. */
+int pn_ball_grid_order(const void* grid, int N, const int32_t** order, int64_t* estride, int64_t* bstride);
 int pn_ball_grid_build_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, int B, int N, float radius2,
                            void* grid, size_t grid_bytes, pn_stream_t stream);
 int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const float* new_xyz, int64_t qB,
@@ -192,17 +195,25 @@ int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float*
  * relu_in = 1 (needs points1 == NULL): ReLU is applied to the interpolated channels before the chain.  This is how
  * a caller folds the level's FIRST layer into the coarse level -- interpolation is linear and its weights sum
  * to one, so conv(interp(p2)) + b == interp(conv(p2) + b): the caller runs that layer once over the S coarse
- * points (pn_mlp_rows_bf16x3, no ReLU), passes the result as points2 and drops the layer from the chain. */
+ * points (pn_mlp_rows_bf16x3, no ReLU), passes the result as points2 and drops the layer from the chain.
+ * order (may be NULL): a permutation of the N points of every cloud -- tile row r of cloud b handles point
+ * order[b*order_bs + r*order_es] (strides in int32 elements).  The result is the same; with a spatially sorted order
+ * (pn_ball_grid_order) the rows of a warp share their three coarse neighbours and the gather hits in L1. */
 int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
                      int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2, int S,
-                     const int64_t* idx, const float* weight, int relu_in, int B, int N, int out_mode, float* out,
-                     int64_t ldo, pn_stream_t stream);
+                     const int64_t* idx, const float* weight, int relu_in, const int32_t* order, int64_t order_es,
+                     int64_t order_bs, int B, int N, int out_mode, float* out, int64_t ldo, pn_stream_t stream);
 
 /* Tuning hook for the fused chains: 0 = automatic (chains whose packed weights fit in shared memory run on the
  * resident-weight kernel: weights loaded once per CTA, 2 or 4 warp groups per CTA each with its own row tile
- * and TMEM slice; larger chains stream their weights through a ring), 1 = always stream, 2 = resident or fail.
+ * and TMEM slice; larger chains stream their weights through a ring), 1 = always stream, 2 = resident or fail;
+ * +4 = keep the row-per-thread producers (disables the coalesced quad producer of the FP levels).
  * Process-wide; meant for benchmarks and tests. */
 int pn_mlp_set_engine(int engine);
+/* Profiling hook: a device buffer of 4 * 64 * 32 int64 (or NULL to disable).  While set, CTA 0 of every resident-
+ * weight chain launch records clock64() per phase: [group][tile round % 64][tile start, producer done, then per
+ * layer: MMA issue start, MMAs issued, accumulator ready, epilogue done; last: tile done]. */
+int pn_mlp_set_debug(void* timeline);
 
 #ifdef __cplusplus
 }

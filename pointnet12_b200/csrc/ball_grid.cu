@@ -338,6 +338,15 @@ PN_EXPORT size_t pn_ball_grid_bytes(int B, int N) {
     return (size_t)B * pn::grid_cloud_bytes(N);
 }
 
+PN_EXPORT int pn_ball_grid_order(const void* grid, int N, const int32_t** order, int64_t* estride, int64_t* bstride) {
+    PN_REQUIRE(grid && order && estride && bstride && N > 0, PN_ERR_BAD_ARG, "pn_ball_grid_order: bad arguments");
+    const size_t sorted_off = (size_t)pn::kGridHdrWords * 4 + (((size_t)pn::kGridMaxCells + 1 + 3) / 4) * 16;
+    *order = reinterpret_cast<const int32_t*>(static_cast<const unsigned char*>(grid) + sorted_off) + 3;   // float4.w
+    *estride = 4;
+    *bstride = (int64_t)(pn::grid_cloud_bytes(N) / 4);
+    return PN_OK;
+}
+
 PN_EXPORT int pn_ball_grid_build_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, int B, int N, float radius2,
                                      void* grid, size_t grid_bytes, pn_stream_t stream) {
     using namespace pn;

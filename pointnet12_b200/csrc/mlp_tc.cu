@@ -193,9 +193,12 @@ struct TcIo {
     const float* p1; int64_t p1B, p1N, p1C; int D1;
     const float* p2; int64_t p2B, p2N, p2C; int D2; int S2;
     const int64_t* idx3; const float* w3;
+    const int* order; int64_t order_es, order_bs;   // TC_IN_FP: optional processing order (row r of cloud b handles point order[b*bs + r*es])
     int relu_in;   // TC_IN_FP: ReLU applied to the interpolated channels (layer 1 was folded into the coarse level)
     // output
     int out_mode; float* y; int64_t ldy; int group;
+    int quad_fp;      // TC_IN_FP: all channel runs are float4-addressable -> coalesced quad producer (fp_quad_producer)
+    long long* dbg;   // optional timeline (pn_mlp_set_debug): CTA 0 records clock64() per phase
 };
 
 template <int IN>
@@ -211,7 +214,7 @@ struct RowCtx {
 };
 
 template <int IN>
-__device__ __forceinline__ void row_setup(const TcIo& io, RowCtx<IN>& c) {
+__device__ __forceinline__ void row_setup(const TcIo& io, RowCtx<IN>& c) {   // may remap c.row (TC_IN_FP with an order)
     if (!c.valid) return;
     if constexpr (IN == TC_IN_ROWS) {
         c.xrow = io.x + c.row * io.ldx;
@@ -227,7 +230,13 @@ __device__ __forceinline__ void row_setup(const TcIo& io, RowCtx<IN>& c) {
         c.cy = q[io.qC];
         c.cz = q[2 * io.qC];
     } else {
-        const int64_t b = c.row / io.seg_rows, n = c.row % io.seg_rows;
+        const int64_t b = c.row / io.seg_rows;
+        int64_t n = c.row % io.seg_rows;
+        if (io.order) {   // spatially sorted processing order: the rows of a warp share their coarse neighbours
+            n = io.order[b * io.order_bs + n * io.order_es];
+            n = n < 0 ? 0 : (n >= io.seg_rows ? io.seg_rows - 1 : n);
+            c.row = b * io.seg_rows + n;
+        }
         c.p1row = io.p1 ? io.p1 + b * io.p1B + n * io.p1N : nullptr;
         int64_t j0 = io.idx3[c.row * 3], j1 = io.idx3[c.row * 3 + 1], j2 = io.idx3[c.row * 3 + 2];
         const int64_t hi = io.S2 - 1;
@@ -322,6 +331,99 @@ __device__ __forceinline__ void row_load32(const TcIo& io, const RowCtx<IN>& c, 
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = row_value<IN>(io, c, k0 + j, k_real);
+}
+
+// ------------------------------------------------------------------------------------------------ quad producer
+// tcgen05.st.16x256b.x1: the warp stores a 16-lane x 8-column block; thread t provides {row t/4: columns 2(t%4),
+// 2(t%4)+1; row t/4 + 8: the same columns} (pinned on hardware with tools/probes/st_shape_probe.cu).  With packed
+// bf16 pairs two columns are four consecutive channels = one float4, so the four threads of a quad read 64
+// CONTIGUOUS bytes of a source row and a warp-wide load touches 8 rows instead of 32: the row-per-thread producer
+// is bound by L1 tag lookups (32 distinct lines per load instruction), this one needs a quarter of them.
+__device__ __forceinline__ void tc_st_16x256(unsigned taddr, unsigned a0, unsigned a1, unsigned b0, unsigned b1) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a0), "r"(a1), "r"(b0), "r"(b1) : "memory");
+}
+__device__ __forceinline__ void tc_split4(const float4 v, unsigned& h0, unsigned& h1, unsigned& l0, unsigned& l1) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    h0 = *reinterpret_cast<const unsigned*>(&a);
+    h1 = *reinterpret_cast<const unsigned*>(&b);
+    const __nv_bfloat162 c = __floats2bfloat162_rn(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xFFFF0000u));
+    const __nv_bfloat162 d = __floats2bfloat162_rn(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xFFFF0000u));
+    l0 = *reinterpret_cast<const unsigned*>(&c);
+    l1 = *reinterpret_cast<const unsigned*>(&d);
+}
+
+struct FpQuadRow {   // one of the four rows a thread serves
+    const float* p1row; const float* r0; const float* r1; const float* r2;
+    float w0, w1, w2;
+    bool valid;
+};
+
+__device__ __forceinline__ void fp_quad_row_setup(const TcIo& io, int64_t seg, int64_t r_in_seg, FpQuadRow& q) {
+    q.valid = r_in_seg < io.seg_rows;
+    q.p1row = nullptr;
+    q.r0 = q.r1 = q.r2 = io.p2;
+    q.w0 = q.w1 = q.w2 = 0.0f;
+    if (!q.valid) return;
+    int64_t n = r_in_seg;
+    if (io.order) {
+        n = io.order[seg * io.order_bs + n * io.order_es];
+        n = n < 0 ? 0 : (n >= io.seg_rows ? io.seg_rows - 1 : n);
+    }
+    const int64_t row = seg * io.seg_rows + n;
+    if (io.p1) q.p1row = io.p1 + seg * io.p1B + n * io.p1N;
+    int64_t j0 = io.idx3[row * 3], j1 = io.idx3[row * 3 + 1], j2 = io.idx3[row * 3 + 2];
+    const int64_t hi = io.S2 - 1;
+    j0 = j0 < 0 ? 0 : (j0 > hi ? hi : j0);
+    j1 = j1 < 0 ? 0 : (j1 > hi ? hi : j1);
+    j2 = j2 < 0 ? 0 : (j2 > hi ? hi : j2);
+    q.r0 = io.p2 + seg * io.p2B + j0 * io.p2N;
+    q.r1 = io.p2 + seg * io.p2B + j1 * io.p2N;
+    q.r2 = io.p2 + seg * io.p2B + j2 * io.p2N;
+    q.w0 = io.w3[row * 3];
+    q.w1 = io.w3[row * 3 + 1];
+    q.w2 = io.w3[row * 3 + 2];
+}
+
+// channels [k, k+4) of the row: skip features, interpolated features (same fp32 operation order as row_value) or zero padding
+__device__ __forceinline__ float4 fp_quad_value(const TcIo& io, const FpQuadRow& q, int k, int k_real) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!q.valid || k >= k_real) return v;
+    if (k < io.D1) return *reinterpret_cast<const float4*>(q.p1row + k);
+    const int d = k - io.D1;
+    const float4 a = *reinterpret_cast<const float4*>(q.r0 + d);
+    const float4 b = *reinterpret_cast<const float4*>(q.r1 + d);
+    const float4 e = *reinterpret_cast<const float4*>(q.r2 + d);
+    v.x = __fadd_rn(__fadd_rn(__fmul_rn(a.x, q.w0), __fmul_rn(b.x, q.w1)), __fmul_rn(e.x, q.w2));
+    v.y = __fadd_rn(__fadd_rn(__fmul_rn(a.y, q.w0), __fmul_rn(b.y, q.w1)), __fmul_rn(e.y, q.w2));
+    v.z = __fadd_rn(__fadd_rn(__fmul_rn(a.z, q.w0), __fmul_rn(b.z, q.w1)), __fmul_rn(e.z, q.w2));
+    v.w = __fadd_rn(__fadd_rn(__fmul_rn(a.w, q.w0), __fmul_rn(b.w, q.w1)), __fmul_rn(e.w, q.w2));
+    if (io.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+}
+
+// The warp fills its 32 TMEM lanes (tile rows row0 .. row0+31 of segment `seg`) of the A region for the channel
+// groups cg = cg0, cg0 + cgstep, ... of 16 channels each.  t_ahi / t_alo: the warp's lane-0 addresses of the regions.
+__device__ __forceinline__ void fp_quad_producer(const TcIo& io, int64_t seg, int64_t row0, int lane, int k_pad, int k_real,
+                                                 int cg0, int cgstep, unsigned t_ahi, unsigned t_alo) {
+    const int qd = lane & 3, rq = lane >> 2;
+    FpQuadRow R[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fp_quad_row_setup(io, seg, row0 + rq + 8 * i, R[i]);
+    for (int cg = cg0; cg * 16 < k_pad; cg += cgstep) {
+        const int k = cg * 16 + qd * 4;
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = fp_quad_value(io, R[i], k, k_real);
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            unsigned ha0, ha1, la0, la1, hb0, hb1, lb0, lb1;
+            tc_split4(v[2 * blk], ha0, ha1, la0, la1);
+            tc_split4(v[2 * blk + 1], hb0, hb1, lb0, lb1);
+            const unsigned off = ((unsigned)(blk * 16) << 16) + (unsigned)cg * 8;
+            tc_st_16x256(t_ahi + off, ha0, ha1, hb0, hb1);
+            tc_st_16x256(t_alo + off, la0, la1, lb0, lb1);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -634,22 +736,35 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
         RowCtx<IN> rc;
         rc.valid = r_in_seg < io.seg_rows;
         rc.row = seg * io.seg_rows + r_in_seg;
+        const bool rec = io.dbg != nullptr && blockIdx.x == 0 && gw == 0 && lane == 0;
+        long long* drow = io.dbg + (g * 64 + (tile / ((int64_t)gridDim.x * GROUPS)) % 64) * 32;
+        int dcol = 0;
+        if (rec) drow[dcol++] = clock64();
         row_setup<IN>(io, rc);
 
         for (int l = 0; l < ch.nlayers; ++l) {
             const TcLayer& L = ch.L[l];
             const bool last = l + 1 == ch.nlayers;
             if (l == 0) {
-                // ---- producer: this thread's row -> TMEM A region
-                for (int k0 = half * 32; k0 < L.k_pad; k0 += CSTEP) {
-                    float v[32];
-                    row_load32<IN>(io, rc, k0, L.k_real, v);
-                    tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
+                // ---- producer: rows -> TMEM A region
+                bool quad = false;
+                if constexpr (IN == TC_IN_FP) quad = io.quad_fp != 0;
+                if (quad) {
+                    fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, L.k_pad, L.k_real, half, HALVES,
+                                     t_ahi, t_alo);
+                } else {
+                    for (int k0 = half * 32; k0 < L.k_pad; k0 += CSTEP) {   // this thread's row
+                        float v[32];
+                        row_load32<IN>(io, rc, k0, L.k_real, v);
+                        tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
+                    }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (rec) drow[dcol++] = clock64();
                 tc_fence_before();
                 tc_group_bar(1 + g, GTHREADS);
             }
+            if (rec) drow[dcol++] = clock64();
             if (gw == 0) {
                 if (lane == 0) {
                     if (!w_ready) tc_mbar_wait(bar_w, 0);
@@ -683,11 +798,13 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                         }
                     }
                     tc_commit(bar_done);
+                    if (rec) drow[dcol++] = clock64();
                 }
                 __syncwarp();   // lanes 1-31 park here while lane 0 feeds the tensor core
             }
             tc_mbar_wait(bar_done, done_phase);
             done_phase ^= 1;
+            if (rec) drow[dcol++] = clock64();
             if (!w_ready) {     // the bias table arrived with the weights: every reader observes the barrier once
                 tc_mbar_wait(bar_w, 0);
                 w_ready = true;
@@ -786,9 +903,11 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                     }
                 }
             }
+            if (rec) drow[dcol++] = clock64();
             tc_fence_before();
             tc_group_bar(1 + g, GTHREADS);
         }
+        if (rec) drow[dcol++] = clock64();
     }
     tc_fence_before();
     __syncthreads();
@@ -799,6 +918,8 @@ static size_t tc_res_smem_bytes(const TcChain& c) { return (size_t)((c.blob_byte
 
 // 0 = automatic (resident when the chain fits), 1 = always stream (mlp_tc_kernel), 2 = resident or fail
 static int g_tc_engine = 0;
+static long long* g_tc_dbg = nullptr;   // pn_mlp_set_debug
+static int g_tc_quad = 1;               // pn_mlp_set_engine(engine | 4) disables the coalesced quad producer
 
 // Resident kernel usable?  Returns warps per group (8 or 4), or 0.
 static int tc_resident_wpg(const TcChain& c) {
@@ -829,7 +950,9 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
             }
             const int64_t want = (ntiles_all + groups - 1) / groups;
             const unsigned grid = (unsigned)(want < 148 ? want : 148);
-            rkern<<<grid, kResThreads, rsmem, stream>>>(ch, static_cast<const unsigned char*>(blob), io);
+            TcIo io2 = io;
+            io2.dbg = g_tc_dbg;
+            rkern<<<grid, kResThreads, rsmem, stream>>>(ch, static_cast<const unsigned char*>(blob), io2);
             return finish_launch(what);
         };
         return wpg == 8 ? launch_res(mlp_tc_res_kernel<IN, 8>, 2) : launch_res(mlp_tc_res_kernel<IN, 4>, 4);
@@ -858,9 +981,16 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
 }  // namespace pn
 
 // ------------------------------------------------------------------------------------------------ C ABI
+PN_EXPORT int pn_mlp_set_debug(void* timeline) {
+    pn::g_tc_dbg = static_cast<long long*>(timeline);
+    return PN_OK;
+}
+
 PN_EXPORT int pn_mlp_set_engine(int engine) {
-    PN_REQUIRE(engine >= 0 && engine <= 2, PN_ERR_BAD_ARG, "pn_mlp_set_engine: 0 = automatic, 1 = streaming, 2 = resident");
-    pn::g_tc_engine = engine;
+    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 8, PN_ERR_BAD_ARG,
+               "pn_mlp_set_engine: 0 = automatic, 1 = streaming, 2 = resident; +4 = row-per-thread producers only");
+    pn::g_tc_engine = engine & 3;
+    pn::g_tc_quad = (engine & 4) ? 0 : 1;
     return PN_OK;
 }
 
@@ -954,8 +1084,9 @@ PN_EXPORT int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, co
 
 PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
                                int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2,
-                               int S, const int64_t* idx, const float* weight, int relu_in, int B, int N, int out_mode,
-                               float* out, int64_t ldo, pn_stream_t stream) {
+                               int S, const int64_t* idx, const float* weight, int relu_in, const int32_t* order,
+                               int64_t order_es, int64_t order_bs, int B, int N, int out_mode, float* out, int64_t ldo,
+                               pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
     int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_fp_mlp_bf16x3");
@@ -973,6 +1104,13 @@ PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
     io.p2 = points2; io.p2B = p2B; io.p2N = p2N; io.p2C = p2C; io.D2 = D2; io.S2 = S;
     io.idx3 = idx; io.w3 = weight;
     io.relu_in = relu_in;
+    io.order = order; io.order_es = order_es; io.order_bs = order_bs;
+    {
+        auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+        bool ok = p2C == 1 && (p2N % 4) == 0 && (p2B % 4) == 0 && (D2 % 4) == 0 && al16(points2);
+        if (D1 > 0) ok = ok && p1C == 1 && (p1N % 4) == 0 && (p1B % 4) == 0 && (D1 % 4) == 0 && al16(points1);
+        io.quad_fp = (ok && g_tc_quad) ? 1 : 0;
+    }
     io.out_mode = out_mode;
     io.y = out;
     io.ldy = ldo;

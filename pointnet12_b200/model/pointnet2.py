@@ -246,7 +246,7 @@ class PointNet2SemSeg(_Net):
         main.wait_event(done_b)
         # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs
         head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
-        return fp[0].features(None, up, *nns[0], head=head)
+        return fp[0].features(None, up, *nns[0], head=head, order=grid1)
 
     def _side_streams(self, device):
         key = torch.device(device).index

@@ -126,6 +126,14 @@ class BallGrid:
                     self.nbytes, _stream())
 
 
+    def order(self) -> Tuple[int, int, int]:
+        """(device pointer, element stride, batch stride) of the bucket-sorted point order, in int32 elements."""
+        ptr, es, bs = C.c_void_p(), C.c_int64(), C.c_int64()
+        nv.check(nv.lib().pn_ball_grid_order(self.buf.data_ptr(), self.N, C.byref(ptr), C.byref(es), C.byref(bs)),
+                 "pn_ball_grid_order")
+        return ptr.value, es.value, bs.value
+
+
 def ball_grid(xyz: torch.Tensor, radius: float) -> BallGrid:
     return BallGrid(xyz, radius)
 
@@ -335,8 +343,9 @@ def mlp_mode() -> str:
 
 def set_mlp_engine(engine: str = "auto") -> None:
     """Tuning hook (pn_mlp_set_engine): 'auto' (resident-weight kernel when the packed chain fits in shared memory,
-    streaming ring otherwise), 'stream' or 'resident'."""
-    nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2}[engine])
+    streaming ring otherwise), 'stream' or 'resident'; '*-rowwise' keeps the row-per-thread producers (no coalesced
+    quad producer) for A/B comparisons."""
+    nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2, "auto-rowwise": 4, "resident-rowwise": 6}[engine])
 
 
 FOLD_FIRST_FP_LAYER = os.environ.get("PN12_FP_FOLD", "1") != "0"
@@ -419,9 +428,11 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
 
 
 def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torch.Tensor, idx: torch.Tensor,
-              weight: torch.Tensor, out_mode: int = OUT_ROWS, relu_in: bool = False) -> torch.Tensor:
+              weight: torch.Tensor, out_mode: int = OUT_ROWS, relu_in: bool = False,
+              order: Optional[BallGrid] = None) -> torch.Tensor:
     """3-NN interpolation + skip concat + shared MLP (+ head + log_softmax) in one kernel -> [B, N, cout].
-    relu_in: ReLU on the interpolated channels first (the level's first layer was folded into the coarse level)."""
+    relu_in: ReLU on the interpolated channels first (the level's first layer was folded into the coarse level).
+    order: a BallGrid of the fine cloud -- tiles then walk the points in bucket order (same result, L1-friendly)."""
     points2 = _cloud(points2, "points2")
     idx = _i64(idx, "idx")
     weight = _f32(weight, "weight").contiguous()
@@ -433,8 +444,13 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
     else:
         D1, s1 = 0, (0, 0, 0)
     out = torch.empty((B, N, chain.cout), dtype=torch.float32, device=points2.device)
+    optr, oes, obs = (None, 0, 0)
+    if order is not None:
+        if (order.B, order.N) != (B, N):
+            raise ValueError("order grid was built for another cloud shape")
+        optr, oes, obs = order.order()
     with _on_device(points2):
         nv.call("pn_fp_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), _p(points1), *s1, D1, points2.data_ptr(),
-                *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), B, N, out_mode,
-                out.data_ptr(), chain.cout, _stream())
+                *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), optr, oes, obs, B, N,
+                out_mode, out.data_ptr(), chain.cout, _stream())
     return out

@@ -523,6 +523,64 @@ def test_fp_first_layer_folded_into_coarse_level(dev):
     assert rel_err(got_unfolded, want) < FEAT_TOL
 
 
+@pytest.mark.parametrize("engine", ["auto", "auto-rowwise", "stream"])
+@pytest.mark.parametrize("D1,D2,widths,N", [(32, 64, [128, 64], 333), (0, 32, [32, 64], 1000), (0, 128, [128, 128, 19], 4111),
+                                            (64, 64, [96], 129), (30, 64, [64, 64], 500)])
+def test_fp_mlp_tc_small_chains(dev, engine, D1, D2, widths, N):
+    """FP chains that fit the resident-weight kernel (2 and 4 warp groups), through the coalesced quad producer
+    (float4-addressable channel runs), the row-per-thread producer and the streaming kernel."""
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(D1 * 7 + D2 + N)
+    B, S = 2, 60
+    p1 = rng.normal(size=(B, N, D1)).astype(np.float32) if D1 else None
+    p2 = rng.normal(size=(B, S, D2)).astype(np.float32)
+    idx = rng.integers(0, S, size=(B, N, 3))
+    w = rng.uniform(0.1, 1, size=(B, N, 3)).astype(np.float32)
+    w /= w.sum(-1, keepdims=True)
+    dims = list(zip([D1 + D2] + widths[:-1], widths))
+    layers = _rand_layers(dims, seed=N, last_relu=True)
+    interp = orc.three_interpolate(p2, idx, w)
+    rows = interp if p1 is None else np.concatenate([p1, interp], -1)
+    want = _chain_ref(rows.reshape(B * N, -1), layers).reshape(B, N, -1)
+    chain = ops.PackedChain([(cuda(wt, dev), cuda(b, dev), r) for wt, b, r in layers])
+    try:
+        ops.set_mlp_engine(engine)
+        got = ops.fp_mlp_tc(chain, cuda(p1, dev) if D1 else None, cuda(p2, dev), cuda(idx, dev), cuda(w, dev), ops.OUT_ROWS)
+    finally:
+        ops.set_mlp_engine("auto")
+    assert rel_err(got, want) < TC_TOL
+
+
+@pytest.mark.parametrize("engine", ["auto", "stream"])
+def test_fp_mlp_tc_processing_order(dev, engine):
+    """Walking the fine points in bucket (spatial) order changes which rows share a tile, not the result."""
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(21)
+    B, N, S, D2 = 2, 5000, 300, 128
+    x1 = cuda(rng.uniform(-1, 1, size=(B, N, 3)).astype(np.float32), dev)
+    p2 = cuda(rng.normal(size=(B, S, D2)).astype(np.float32), dev)
+    idx = cuda(rng.integers(0, S, size=(B, N, 3)), dev)
+    w = rng.uniform(0.1, 1, size=(B, N, 3)).astype(np.float32)
+    w = cuda(w / w.sum(-1, keepdims=True), dev)
+    layers = _rand_layers([(D2, 128), (128, 128), (128, 19)], seed=4, last_relu=False)
+    chain = ops.PackedChain([(cuda(wt, dev), cuda(b, dev), r) for wt, b, r in layers])
+    grid = ops.ball_grid(x1, 0.1)
+    order = grid.buf.view(torch.int32)
+    try:
+        ops.set_mlp_engine(engine)
+        plain = ops.fp_mlp_tc(chain, None, p2, idx, w, ops.OUT_LOG_SOFTMAX)
+        sorted_ = ops.fp_mlp_tc(chain, None, p2, idx, w, ops.OUT_LOG_SOFTMAX, order=grid)
+    finally:
+        ops.set_mlp_engine("auto")
+    assert torch.equal(plain, sorted_)
+    ptr, es, bs = grid.order()
+    perm = order[(ptr - grid.buf.data_ptr()) // 4:][: bs * (B - 1) + es * N].cpu().numpy()
+    for b in range(B):   # the order is a permutation of every cloud
+        assert np.array_equal(np.sort(perm[b * bs: b * bs + es * N: es]), np.arange(N))
+
+
 # ------------------------------------------------------------------------------------------------ blocks / networks
 def test_checkpoint_loads_strict(dev, ckpt_path):
     from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
