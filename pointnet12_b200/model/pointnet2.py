@@ -179,8 +179,12 @@ class PointNet2SemSeg(_Net):
                      fp2=_fp(320, [256, 128]), fp1=_fp(128, [128, 128, 128]))
         self._seg_convs(num_classes)
 
-    def forward(self, points, fps_starts=None):
+    def forward(self, points, fps_starts=None, host_out=None):
         """points [B, 3+feature_dims, N] -> log-probabilities [B, N, num_classes].
+        `host_out` (extension): a pinned host tensor [B, N, num_classes]; the last level then runs in two batch
+        halves and each half starts its device-to-host copy on a copy stream as soon as it is computed, so the
+        transfer of the first clouds overlaps the computation of the last ones.  The copies are ordered before
+        anything issued later on the current stream.
         `fps_starts` (extension): the four FPS start-index tensors ([B] int64 on the device) when the caller has
         drawn them already (CUDA-graph replay); by default they are drawn like the reference draws them.
 
@@ -246,7 +250,32 @@ class PointNet2SemSeg(_Net):
         main.wait_event(done_b)
         # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs
         head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
-        return fp[0].features(None, up, *nns[0], head=head, order=grid1)
+        if host_out is None or ops.mlp_mode() != "bf16x3":
+            logp = fp[0].features(None, up, *nns[0], head=head, order=grid1)
+            if host_out is not None:
+                host_out.copy_(logp, non_blocking=True)
+            return logp
+        logp = torch.empty((B, N, self.conv2.out_channels), dtype=torch.float32, device=points.device)
+        copier = self._copy_stream(points.device)
+        half = (B + 1) // 2
+        for b0, b1 in ((0, half), (half, B)):
+            if b0 == b1:
+                continue
+            fp[0].features(None, up, *nns[0], head=head, order=grid1, out=logp, clouds=(b0, b1))
+            part = torch.cuda.Event()
+            part.record(main)
+            with torch.cuda.stream(copier):
+                copier.wait_event(part)
+                host_out[b0:b1].copy_(logp[b0:b1], non_blocking=True)
+        main.wait_stream(copier)
+        return logp
+
+    def _copy_stream(self, device):
+        key = ("copy", torch.device(device).index)
+        streams = self.__dict__.setdefault("_streams", {})
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device)
+        return streams[key]
 
     def _side_streams(self, device):
         key = torch.device(device).index

@@ -302,11 +302,13 @@ class PointNetFeaturePropagation(nn.Module):
             return idx, torch.tensor([1.0, 0.0, 0.0], device=x1.device).expand(B, N, 3).contiguous()
         return ops.three_nn(x1, x2)
 
-    def features(self, p1, p2, idx, w, head=None, order=None) -> torch.Tensor:
+    def features(self, p1, p2, idx, w, head=None, order=None, out=None, clouds=None) -> torch.Tensor:
         """p1 [B,N,D1] or None, p2 [B,S,D2] point-major -> [B,N,D'] point-major.
         `head`: (FoldedLayers, convs, bns, relus, out_mode) appended by a network: the segmentation head runs
         in the same kernel and the result is the [B,N,classes] log-probabilities.
-        `order`: an ops.BallGrid of the fine cloud; the fused kernel then walks the points in bucket order."""
+        `order`: an ops.BallGrid of the fine cloud; the fused kernel then walks the points in bucket order.
+        `out`, `clouds`: write into a caller-provided [B,N,D'] buffer / compute only the batch slice (b0, b1)
+        (tensor-core path only)."""
         B, N, _ = idx.shape
         convs, bns, relus = list(self.mlp_convs), list(self.mlp_bns), [True] * len(self.mlp_convs)
         folded, out_mode = self._folded, ops.OUT_ROWS
@@ -320,12 +322,15 @@ class PointNetFeaturePropagation(nn.Module):
                 # -> the remaining layers (-> head -> log_softmax)
                 first, rest = split
                 S, D2 = p2.shape[1], p2.shape[2]
-                z = ops.mlp_rows_tc(first, p2.reshape(B * S, D2)).view(B, S, -1)
-                return ops.fp_mlp_tc(rest, None, z, idx, w, out_mode, relu_in=True, order=order)
+                z = getattr(self, "_z_cache", None)
+                if clouds is None or z is None or z[0] is not p2:
+                    z = (p2, ops.mlp_rows_tc(first, p2.reshape(B * S, D2)).view(B, S, -1))
+                    self._z_cache = z if clouds is not None else None   # reused by the next batch slice of this call
+                return ops.fp_mlp_tc(rest, None, z[1], idx, w, out_mode, relu_in=True, order=order, out=out, clouds=clouds)
         chain = folded.chain(convs, bns, relus)
         if chain is not None:
             # one kernel: weighted 3-row gather + skip concat -> tensor-core MLP chain (-> head -> log_softmax)
-            return ops.fp_mlp_tc(chain, p1, p2, idx, w, out_mode, order=order)
+            return ops.fp_mlp_tc(chain, p1, p2, idx, w, out_mode, order=order, out=out, clouds=clouds)
         rows = ops.three_interpolate(p1, p2, idx, w).view(B * N, -1)
         for (wt, b), r in zip(folded.get(convs, bns), relus):
             rows = ops.linear(rows, wt, b, relu=r)

@@ -429,10 +429,13 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
 
 def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torch.Tensor, idx: torch.Tensor,
               weight: torch.Tensor, out_mode: int = OUT_ROWS, relu_in: bool = False,
-              order: Optional[BallGrid] = None) -> torch.Tensor:
+              order: Optional[BallGrid] = None, out: Optional[torch.Tensor] = None,
+              clouds: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """3-NN interpolation + skip concat + shared MLP (+ head + log_softmax) in one kernel -> [B, N, cout].
     relu_in: ReLU on the interpolated channels first (the level's first layer was folded into the coarse level).
-    order: a BallGrid of the fine cloud -- tiles then walk the points in bucket order (same result, L1-friendly)."""
+    order: a BallGrid of the fine cloud -- tiles then walk the points in bucket order (same result, L1-friendly).
+    out: a contiguous [B, N, cout] float32 buffer to write into; clouds = (b0, b1): only that slice of the batch is
+    computed (into out[b0:b1]) -- a caller can then start moving the first clouds while the rest are computed."""
     points2 = _cloud(points2, "points2")
     idx = _i64(idx, "idx")
     weight = _f32(weight, "weight").contiguous()
@@ -443,14 +446,27 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
         D1, s1 = points1.shape[2], points1.stride()
     else:
         D1, s1 = 0, (0, 0, 0)
-    out = torch.empty((B, N, chain.cout), dtype=torch.float32, device=points2.device)
+    if out is None:
+        out = torch.empty((B, N, chain.cout), dtype=torch.float32, device=points2.device)
+    elif out.shape != (B, N, chain.cout) or not out.is_contiguous() or out.dtype != torch.float32 or not out.is_cuda:
+        raise ValueError("out must be a contiguous float32 CUDA tensor of shape [B, N, cout]")
     optr, oes, obs = (None, 0, 0)
     if order is not None:
         if (order.B, order.N) != (B, N):
             raise ValueError("order grid was built for another cloud shape")
         optr, oes, obs = order.order()
+    full_out = out
+    if clouds is not None:
+        b0, b1 = clouds
+        if not 0 <= b0 < b1 <= B:
+            raise ValueError(f"clouds={clouds} is not a slice of the batch of {B}")
+        points1 = points1[b0:b1] if points1 is not None else None
+        points2, idx, weight, out = points2[b0:b1], idx[b0:b1], weight[b0:b1], out[b0:b1]
+        if optr is not None:
+            optr += 4 * obs * b0
+        B = b1 - b0
     with _on_device(points2):
         nv.call("pn_fp_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), _p(points1), *s1, D1, points2.data_ptr(),
                 *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), optr, oes, obs, B, N,
                 out_mode, out.data_ptr(), chain.cout, _stream())
-    return out
+    return full_out

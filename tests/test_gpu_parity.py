@@ -693,6 +693,22 @@ def test_graph_replay_matches_eager(dev, ckpt_path):
     torch.manual_seed(5)
     with torch.no_grad():
         assert torch.equal(out, net(host.to(dev)).cpu())
+    # device-to-host copies as graph nodes (two batch halves, the first travels while the second is computed)
+    for B in (3, 1):
+        host = torch.from_numpy(syn.kitti_batch(B, 4096, config=11)).pin_memory()
+        torch.manual_seed(6)
+        got = runner(host, to_host=True)
+        torch.cuda.synchronize()
+        assert not got.is_cuda and got.is_pinned()
+        torch.manual_seed(6)
+        with torch.no_grad():
+            want = net(host.to(dev))
+            assert torch.equal(got, want.cpu())
+            eager_host = torch.empty((B, 4096, 19)).pin_memory()
+            torch.manual_seed(6)
+            net(host.to(dev), host_out=eager_host)
+            torch.cuda.synchronize()
+            assert torch.equal(eager_host, want.cpu())
 
 
 def _seeded(net, seed, dev):
