@@ -175,6 +175,27 @@ __device__ __forceinline__ float tc_unkey(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
+// Column-wise max over the 32 rows (= lanes) of a warp for 32 columns held one row per lane: a butterfly in which
+// every step halves the columns a lane is responsible for (16 + 8 + 4 + 2 + 1 = 31 shuffles and max per lane instead
+// of 32 REDUX instructions, which the hardware serialises).  Afterwards lane j holds the max of column j.
+template <int W>
+__device__ __forceinline__ void tc_colmax_step(float (&v)[32], int lane) {
+    if constexpr (W >= 1) {
+        const bool up = (lane & W) != 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const float send = up ? v[i] : v[i + W];
+            const float keep = up ? v[i + W] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, W));
+        }
+        tc_colmax_step<W / 2>(v, lane);
+    }
+}
+__device__ __forceinline__ float tc_colmax32(float (&v)[32], int lane) {
+    tc_colmax_step<16>(v, lane);
+    return v[0];
+}
+
 // ------------------------------------------------------------------------------------------------ row producers
 enum { TC_IN_ROWS = 0, TC_IN_SA = 1, TC_IN_FP = 2 };
 enum { TC_OUT_ROWS = 0, TC_OUT_MAX = 1, TC_OUT_LOGSOFTMAX = 2 };
@@ -352,6 +373,71 @@ __device__ __forceinline__ void tc_split4(const float4 v, unsigned& h0, unsigned
     l1 = *reinterpret_cast<const unsigned*>(&d);
 }
 
+// tcgen05.ld.16x256b.x4: 16 lanes x 32 columns; r[4m + 2rb + c] = row t/4 + 8rb, column 8m + 2(t%4) + c.
+__device__ __forceinline__ void tc_ld_16x256_x4(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// log_softmax over the first n_real (<= 32) accumulator columns of the 16 TMEM lanes at `taddr`, quad layout: the four
+// threads of a quad share a row (8 classes each), so the row max / sum are two xor-shuffles, one TMEM read instead
+// of three, and a warp-wide store touches 8 output rows instead of 32.  rowA / rowB: output rows (or -1) of the two
+// rows this thread serves (lanes t/4 and t/4 + 8 of the block).
+__device__ __forceinline__ void tc_logsoftmax_quad(unsigned taddr, const float* bias, int n_real, int lane, int64_t rowA,
+                                                   int64_t rowB, float* y, int64_t ldy) {
+    unsigned r[16];
+    tc_ld_16x256_x4(taddr, r);
+    const int qd = lane & 3;
+    float v[2][8];
+    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int col = 8 * m + 2 * qd + c;
+            const float b = bias[col];
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb) {
+                const float f = col < n_real ? __uint_as_float(r[4 * m + 2 * rb + c]) + b : -CUDART_INF_F;
+                v[rb][2 * m + c] = f;
+                mx[rb] = fmaxf(mx[rb], f);
+            }
+        }
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        mx[rb] = fmaxf(mx[rb], __shfl_xor_sync(0xffffffffu, mx[rb], 1));
+        mx[rb] = fmaxf(mx[rb], __shfl_xor_sync(0xffffffffu, mx[rb], 2));
+    }
+    float sm[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm[rb] += __expf(v[rb][i] - mx[rb]);     // exp(-inf) = 0 for the padding classes
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        sm[rb] += __shfl_xor_sync(0xffffffffu, sm[rb], 1);
+        sm[rb] += __shfl_xor_sync(0xffffffffu, sm[rb], 2);
+    }
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        const int64_t row = rb ? rowB : rowA;
+        if (row < 0) continue;
+        const float ls = __logf(sm[rb]);
+        float* dst = y + row * ldy;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col = 8 * m + 2 * qd + c;
+                if (col < n_real) dst[col] = (v[rb][2 * m + c] - mx[rb]) - ls;
+            }
+    }
+}
+
 struct FpQuadRow {   // one of the four rows a thread serves
     const float* p1row; const float* r0; const float* r1; const float* r2;
     float w0, w1, w2;
@@ -439,7 +525,8 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     const unsigned bar_done = tc_smem_u32(&bars[4]);
     const unsigned stage0 = tc_smem_u32(smem);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: MMA operands stay in uniform registers
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(ch.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -459,7 +546,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const unsigned tbase = *tmem_slot;
+    const unsigned tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int wl = warp & 3, half = warp >> 2;                      // lane quarter / column half of this warp
     const unsigned tlane = tbase + ((unsigned)(wl * 32) << 16);      // this warp's 32 TMEM lanes
     const unsigned t_x = tlane;                                      // accumulator columns
@@ -615,17 +702,16 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
-                        unsigned mine = 0;
+                        float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float f = __uint_as_float(r[j]) + bias[c0 + j];
                             if (L.relu) f = fmaxf(f, 0.0f);
-                            const unsigned k = rc.valid ? tc_key(f) : 0u;
-                            const unsigned m = __reduce_max_sync(0xffffffffu, k);
-                            if (lane == j) mine = m;
+                            v[j] = rc.valid ? f : -CUDART_INF_F;
                         }
+                        const float mine = tc_colmax32(v, lane);
                         const int n = p * kTcNPass + c0 + lane;
-                        if (any_valid && n < L.n_real) io.y[g * io.ldy + n] = tc_unkey(mine);
+                        if (any_valid && n < L.n_real) io.y[g * io.ldy + n] = mine;
                     }
                     tc_fence_before();
                     __syncthreads();
@@ -696,7 +782,8 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
     const unsigned bar_w = tc_smem_u32(&bars[0]);
     const unsigned smem_w = tc_smem_u32(smem);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: MMA operands stay in uniform registers
     const int g = warp / WPG, gw = warp % WPG;
     const unsigned bar_done = tc_smem_u32(&bars[1 + g]);
     if (warp == 0) {
@@ -719,7 +806,7 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const unsigned tbase = *tmem_slot + (unsigned)(g * GCOLS);
+    const unsigned tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0) + (unsigned)(g * GCOLS);
     const int wl = gw & 3, half = gw >> 2;                           // lane quarter (== warp % 4) / column half
     const unsigned tlane = tbase + ((unsigned)(wl * 32) << 16);      // this warp's 32 TMEM lanes
     const unsigned t_x = tlane;                                      // accumulator columns
@@ -861,17 +948,26 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 for (int c0 = half * 32; c0 < L.n_pad; c0 += CSTEP) {
                     unsigned r[32];
                     tc_ld32(t_x + c0, r);
-                    unsigned mine = 0;
+                    float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float f = __uint_as_float(r[j]) + bias[c0 + j];
                         if (L.relu) f = fmaxf(f, 0.0f);
-                        const unsigned k = rc.valid ? tc_key(f) : 0u;
-                        const unsigned m = __reduce_max_sync(0xffffffffu, k);
-                        if (lane == j) mine = m;
+                        v[j] = rc.valid ? f : -CUDART_INF_F;
                     }
+                    const float mine = tc_colmax32(v, lane);
                     const int n = c0 + lane;
-                    if (any_valid && n < L.n_real) io.y[gi * io.ldy + n] = tc_unkey(mine);
+                    if (any_valid && n < L.n_real) io.y[gi * io.ldy + n] = mine;
+                }
+            } else if (L.n_pad == 32) {   // TC_OUT_LOGSOFTMAX, up to 32 classes: quad layout, every warp takes part
+                const int64_t orow = rc.valid ? rc.row : -1;
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    // (shuffles are executed by the whole warp; with two column-half warps each takes one 16-lane block)
+                    const int64_t rowA = __shfl_sync(0xffffffffu, orow, blk * 16 + (lane >> 2));
+                    const int64_t rowB = __shfl_sync(0xffffffffu, orow, blk * 16 + (lane >> 2) + 8);
+                    if (HALVES == 1 || half == blk)
+                        tc_logsoftmax_quad(t_x + ((unsigned)(blk * 16) << 16), bias, L.n_real, lane, rowA, rowB, io.y, io.ldy);
                 }
             } else {   // TC_OUT_LOGSOFTMAX over the n_real (<= 64) classes of the row: column-half 0 warps only
                 if (half == 0) {
