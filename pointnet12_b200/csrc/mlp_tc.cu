@@ -29,7 +29,8 @@ namespace pn {
 
 constexpr int kTcThreads = 256;  // 8 warps: warp w owns TMEM lanes 32*(w%4).., column half w/4 of every 64 columns
 constexpr int kTcMaxLayers = PN_MLP_MAX_LAYERS;
-constexpr int kTcKSub = 64;     // K values per streamed weight slice
+constexpr int kTcKSub = 32;     // K values per streamed weight slice
+constexpr int kTcMaxStages = 8; // ring depth limit of the streaming kernel
 constexpr int kTcAChunk = 256;  // K values resident in TMEM as the A operand (128 columns hi + 128 columns lo)
 constexpr int kTcNPass = 256;   // output channels per accumulation pass (TMEM D columns)
 
@@ -40,6 +41,7 @@ struct TcLayer {
 };
 struct TcChain {
     int nlayers, stage_bytes, tmem_cols, x_cols, a_lo_off, bias_floats;
+    int nstages;        // ring depth of the streaming kernel (set at launch)
     unsigned bias_off;  // byte offset of the bias table in the blob
     unsigned blob_bytes;
     TcLayer L[kTcMaxLayers];
@@ -488,15 +490,16 @@ __device__ __forceinline__ float4 fp_quad_value(const TcIo& io, const FpQuadRow&
 }
 
 // The warp fills its 32 TMEM lanes (tile rows row0 .. row0+31 of segment `seg`) of the A region for the channel
-// groups cg = cg0, cg0 + cgstep, ... of 16 channels each.  t_ahi / t_alo: the warp's lane-0 addresses of the regions.
-__device__ __forceinline__ void fp_quad_producer(const TcIo& io, int64_t seg, int64_t row0, int lane, int k_pad, int k_real,
-                                                 int cg0, int cgstep, unsigned t_ahi, unsigned t_alo) {
+// groups cg = cg0, cg0 + cgstep, ... of 16 channels each of the chunk [kbase, kbase + kchunk).  t_ahi / t_alo: the warp's
+// lane-0 addresses of the regions.
+__device__ __forceinline__ void fp_quad_producer(const TcIo& io, int64_t seg, int64_t row0, int lane, int kbase, int kchunk,
+                                                 int k_real, int cg0, int cgstep, unsigned t_ahi, unsigned t_alo) {
     const int qd = lane & 3, rq = lane >> 2;
     FpQuadRow R[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) fp_quad_row_setup(io, seg, row0 + rq + 8 * i, R[i]);
-    for (int cg = cg0; cg * 16 < k_pad; cg += cgstep) {
-        const int k = cg * 16 + qd * 4;
+    for (int cg = cg0; cg * 16 < kchunk; cg += cgstep) {   // channels [kbase, kbase + kchunk) -> A columns [0, kchunk / 2)
+        const int k = kbase + cg * 16 + qd * 4;
         float4 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = fp_quad_value(io, R[i], k, k_real);
@@ -517,12 +520,13 @@ template <int IN>
 __global__ void __launch_bounds__(kTcThreads, 2)
 mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restrict__ blob, const __grid_constant__ TcIo io) {
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [stage 0][stage 1][bias table][barriers: full0 full1 empty0 empty1 done][tmem ptr]
-    float* sbias = reinterpret_cast<float*>(smem + 2 * ch.stage_bytes);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 2 * ch.stage_bytes + ((ch.bias_floats * 4 + 15) & ~15));
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 5);
-    const unsigned bar_full0 = tc_smem_u32(&bars[0]), bar_empty0 = tc_smem_u32(&bars[2]);   // stage 1: + 8 bytes
-    const unsigned bar_done = tc_smem_u32(&bars[4]);
+    // layout: [stage 0 .. nstages-1][bias table][barriers: full[8] empty[8] done][tmem ptr]
+    const int NS = ch.nstages;
+    float* sbias = reinterpret_cast<float*>(smem + NS * ch.stage_bytes);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + NS * ch.stage_bytes + ((ch.bias_floats * 4 + 15) & ~15));
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * kTcMaxStages + 1);
+    const unsigned bar_full0 = tc_smem_u32(&bars[0]), bar_empty0 = tc_smem_u32(&bars[kTcMaxStages]);   // stage st: + 8 st bytes
+    const unsigned bar_done = tc_smem_u32(&bars[2 * kTcMaxStages]);
     const unsigned stage0 = tc_smem_u32(smem);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -532,10 +536,10 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
-        tc_mbar_init(bar_full0, 1);
-        tc_mbar_init(bar_full0 + 8, 1);
-        tc_mbar_init(bar_empty0, 1);
-        tc_mbar_init(bar_empty0 + 8, 1);
+        for (int st = 0; st < NS; ++st) {
+            tc_mbar_init(bar_full0 + 8 * st, 1);
+            tc_mbar_init(bar_empty0 + 8 * st, 1);
+        }
         tc_mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -553,7 +557,17 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     const unsigned t_ahi = tlane + ch.x_cols, t_alo = t_ahi + ch.a_lo_off;
     const unsigned a_hi_col = tbase + ch.x_cols, a_lo_col = a_hi_col + ch.a_lo_off;   // lane 0 addresses for the MMA
 
-    unsigned fill = 0, use = 0, done_phase = 0;   // ring / barrier bookkeeping (fill, use: thread 0 only)
+    // ring bookkeeping: `fill` lives in the copy thread (warp 4, lane 0), `use` in the MMA thread (warp 0, lane 0); both walk
+    // the same static schedule of (tile, layer, pass, chunk, slice), so slice number i always sits in stage i % NS
+    unsigned fill = 0, use = 0, fill_st = 0, use_st = 0, done_phase = 0;
+    int nlog = 0;
+    auto stamp = [&](int tag) {   // pn_mlp_set_debug: flat (tag, clock) log of CTA 0, thread 0
+        if (io.dbg != nullptr && blockIdx.x == 0 && tid == 0 && nlog < 500) {
+            io.dbg[1 + 2 * nlog] = tag;
+            io.dbg[2 + 2 * nlog] = clock64();
+            io.dbg[0] = ++nlog;
+        }
+    };
 
     const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
     const int64_t ntiles = io.nseg * tiles_per_seg;
@@ -563,6 +577,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
         RowCtx<IN> rc;
         rc.valid = r_in_seg < io.seg_rows;
         rc.row = seg * io.seg_rows + r_in_seg;
+        stamp(1);
         row_setup<IN>(io, rc);
 
         for (int l = 0; l < ch.nlayers; ++l) {
@@ -576,44 +591,56 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     const int kbase = a * kTcAChunk;
                     const int kchunk = min(kTcAChunk, L.k_pad - kbase);
                     if (l == 0) {
-                        // ---- producer: this thread's row, channels [kbase, kbase + kchunk) -> TMEM A region
-                        for (int k0 = half * 32; k0 < kchunk; k0 += 64) {
-                            float v[32];
-                            row_load32<IN>(io, rc, kbase + k0, L.k_real, v);
-                            tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
+                        // ---- producer: channels [kbase, kbase + kchunk) of the tile's rows -> TMEM A region
+                        bool quad = false;
+                        if constexpr (IN == TC_IN_FP) quad = io.quad_fp != 0;
+                        if (quad) {
+                            fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, kbase, kchunk, L.k_real, half, 2,
+                                             t_ahi, t_alo);
+                        } else {
+                            for (int k0 = half * 32; k0 < kchunk; k0 += 64) {   // this thread's row
+                                float v[32];
+                                row_load32<IN>(io, rc, kbase + k0, L.k_real, v);
+                                tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
+                            }
                         }
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
                         __syncthreads();
+                        stamp(2);
+                    }
+                    const int s0 = kbase / kTcKSub, ns = (kchunk + kTcKSub - 1) / kTcKSub;
+                    if (warp == 4) {
+                      if (lane == 0) {
+                        // ---- copy thread: the weight slices of this chunk, one cp.async.bulk (TMA engine) each, running up to
+                        // NS slices ahead of the tensor core; a stage is reused once the MMAs that read it have completed
+                        const unsigned char* wpass = blob + L.w_off + (size_t)p * kTcNPass * L.k_pad * 4;
+                        for (int s = 0; s < ns; ++s) {
+                            const int kw = min(kTcKSub, L.k_pad - (s0 + s) * kTcKSub);
+                            const unsigned bytes = (unsigned)rows_p * kw * 4;
+                            tc_mbar_wait(bar_empty0 + 8 * fill_st, ((fill / NS) & 1) ^ 1);
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full0 + 8 * fill_st), "r"(bytes) : "memory");
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                    stage0 + fill_st * (unsigned)ch.stage_bytes),
+                                "l"(wpass + (size_t)rows_p * ((s0 + s) * kTcKSub) * 4), "r"(bytes), "r"(bar_full0 + 8 * fill_st)
+                                : "memory");
+                            ++fill;
+                            fill_st = fill_st + 1 == (unsigned)NS ? 0u : fill_st + 1;
+                        }
+                      }
+                      __syncwarp();
                     }
                     if (warp == 0) {
                       if (lane == 0) {
                         tc_fence_after();
-                        // ---- weight slices of this chunk: 2-stage ring, MMAs issued as slices land
-                        const int s0 = kbase / kTcKSub, ns = (kchunk + kTcKSub - 1) / kTcKSub;
-                        const unsigned char* wpass = blob + L.w_off + (size_t)p * kTcNPass * L.k_pad * 4;
+                        // ---- MMA thread: issues the MMAs of a slice as soon as it has landed
                         const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(rows_p >> 3) << 17) | (8u << 24);
-                        auto issue_copy = [&](int s) {
-                            const int kw = min(kTcKSub, L.k_pad - s * kTcKSub);
-                            const unsigned bytes = (unsigned)rows_p * kw * 4;
-                            const unsigned st = fill & 1;
-                            tc_mbar_wait(bar_empty0 + 8 * st, ((fill >> 1) & 1) ^ 1);
-                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full0 + 8 * st), "r"(bytes) : "memory");
-                            asm volatile(
-                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                    stage0 + st * (unsigned)ch.stage_bytes),
-                                "l"(wpass + (size_t)rows_p * (s * kTcKSub) * 4), "r"(bytes), "r"(bar_full0 + 8 * st)
-                                : "memory");
-                            ++fill;
-                        };
-                        const int pre = ns < 2 ? ns : 2;
-                        for (int s = 0; s < pre; ++s) issue_copy(s0 + s);
                         for (int s = 0; s < ns; ++s) {
                             const int kw = min(kTcKSub, L.k_pad - (s0 + s) * kTcKSub);
-                            const unsigned st = use & 1;
-                            tc_mbar_wait(bar_full0 + 8 * st, (use >> 1) & 1);
+                            tc_mbar_wait(bar_full0 + 8 * use_st, (use / NS) & 1);
                             tc_fence_after();
-                            const unsigned b_hi = stage0 + st * (unsigned)ch.stage_bytes, b_lo = b_hi + (unsigned)rows_p * kw * 2;
+                            const unsigned b_hi = stage0 + use_st * (unsigned)ch.stage_bytes, b_lo = b_hi + (unsigned)rows_p * kw * 2;
                             const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
                                                              ((unsigned long long)((((unsigned)kw / 8) * 128u >> 4) & 0x3FFF) << 32) |
                                                              (1ull << 46);
@@ -635,11 +662,12 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                                              "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
                                              : "memory");
                             }
-                            tc_commit(bar_empty0 + 8 * st);
+                            tc_commit(bar_empty0 + 8 * use_st);
                             ++use;
-                            if (s + 2 < ns) issue_copy(s0 + s + 2);
+                            use_st = use_st + 1 == (unsigned)NS ? 0u : use_st + 1;
                         }
                         tc_commit(bar_done);
+                        stamp(3);
                       }
                       __syncwarp();   // lanes 1-31 park here (no spinning) while lane 0 feeds the tensor core
                     }
@@ -647,6 +675,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     tc_mbar_wait(bar_done, done_phase);
                     done_phase ^= 1;
                     tc_fence_after();
+                    stamp(4);
                 }
                 // ---- epilogue of pass p: accumulator columns [0, rows_p)
                 const float* bias = sbias + L.b_off + p * kTcNPass;
@@ -747,6 +776,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     tc_fence_before();
                     __syncthreads();
                 }
+                stamp(5);
             }
         }
     }
@@ -837,7 +867,7 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 bool quad = false;
                 if constexpr (IN == TC_IN_FP) quad = io.quad_fp != 0;
                 if (quad) {
-                    fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, L.k_pad, L.k_real, half, HALVES,
+                    fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, 0, L.k_pad, L.k_real, half, HALVES,
                                      t_ahi, t_alo);
                 } else {
                     for (int k0 = half * 32; k0 < L.k_pad; k0 += CSTEP) {   // this thread's row
@@ -1028,7 +1058,9 @@ static int tc_resident_wpg(const TcChain& c) {
     return 0;
 }
 
-static size_t tc_smem_bytes(const TcChain& c) { return (size_t)2 * c.stage_bytes + ((c.bias_floats * 4 + 15) & ~15) + 5 * 8 + 16; }
+static size_t tc_smem_bytes(const TcChain& c, int nstages) {
+    return (size_t)nstages * c.stage_bytes + ((c.bias_floats * 4 + 15) & ~15) + (2 * kTcMaxStages + 1) * 8 + 16;
+}
 
 template <int IN>
 static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaStream_t stream, const char* what) {
@@ -1053,7 +1085,18 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
         };
         return wpg == 8 ? launch_res(mlp_tc_res_kernel<IN, 8>, 2) : launch_res(mlp_tc_res_kernel<IN, 4>, 4);
     }
-    const size_t smem = tc_smem_bytes(ch);
+    // ring depth: as deep as shared memory allows (a CTA alone on its SM when the grid is small: up to ~200 KB;
+    // otherwise ~110 KB so that two CTAs share an SM), at least 2, at most kTcMaxStages
+    TcChain chs = ch;
+    {
+        const int by_tmem = 512 / ch.tmem_cols;
+        const size_t budget = (ntiles_all <= 148 || by_tmem < 2) ? 200 * 1024 : 110 * 1024;
+        const size_t fixed = tc_smem_bytes(ch, 0);
+        int ns = (int)((budget - fixed) / (size_t)ch.stage_bytes);
+        ns = ns < 2 ? 2 : (ns > kTcMaxStages ? kTcMaxStages : ns);
+        chs.nstages = ns;
+    }
+    const size_t smem = tc_smem_bytes(chs, chs.nstages);
     PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "%s: chain needs %zu bytes of shared memory", what, smem);
     auto kern = mlp_tc_kernel<IN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1070,7 +1113,9 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);   // __launch_bounds__(256, 2): registers allow two CTAs per SM
     const int64_t cap = 148LL * per_sm;
     const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
-    kern<<<grid, kTcThreads, smem, stream>>>(ch, static_cast<const unsigned char*>(blob), io);
+    TcIo io2 = io;
+    io2.dbg = g_tc_dbg;
+    kern<<<grid, kTcThreads, smem, stream>>>(chs, static_cast<const unsigned char*>(blob), io2);
     return finish_launch(what);
 }
 

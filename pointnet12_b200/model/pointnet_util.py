@@ -133,9 +133,12 @@ class FoldedLayers:
         return self._layers
 
     def chain(self, convs: Sequence[nn.Module], bns: Sequence[Optional[nn.Module]],
-              relus: Optional[Sequence[bool]] = None) -> Optional[ops.PackedChain]:
+              relus: Optional[Sequence[bool]] = None, xyz_last: bool = False) -> Optional[ops.PackedChain]:
         """The same layers packed for the tensor-core kernels, or None when the mode is 'fp32' or the chain
-        does not fit them (then the caller uses the layer-by-layer CUDA-core path)."""
+        does not fit them (then the caller uses the layer-by-layer CUDA-core path).
+        xyz_last: the first layer's input columns are rotated from [xyz_rel(3), features] (sample_and_group order,
+        pointnet_util.py:131) to [features, xyz_rel]: the same dot products, but the gathered feature rows then start
+        at channel 0 and can be read with aligned 16-byte loads (the kernel is called with msg_order=1)."""
         if ops.mlp_mode() != "bf16x3":
             return None
         layers = self.get(convs, bns)
@@ -145,7 +148,11 @@ class FoldedLayers:
                 self._chain = False
             else:
                 relus = [True] * len(layers) if relus is None else list(relus)
-                self._chain = ops.PackedChain([(w, b, r) for (w, b), r in zip(layers, relus)])
+                packed = [(w, b, r) for (w, b), r in zip(layers, relus)]
+                if xyz_last:
+                    w0, b0, r0 = packed[0]
+                    packed[0] = (torch.cat([w0[:, 3:], w0[:, :3]], 1).contiguous(), b0, r0)
+                self._chain = ops.PackedChain(packed)
         return self._chain or None
 
     def chain_folded_first(self, convs, bns, relus):
@@ -208,10 +215,11 @@ class PointNetSetAbstraction(nn.Module):
     def features(self, xyz_pm, pts_pm, new_xyz, idx) -> torch.Tensor:
         """-> pooled [B,S,C'] point-major."""
         B, S, K = idx.shape
-        chain = self._folded.chain(self.mlp_convs, self.mlp_bns) if K == 32 else None
+        chain = self._folded.chain(self.mlp_convs, self.mlp_bns, xyz_last=True) if K == 32 else None
         if chain is not None:
             # one kernel: gather + recentre + concat -> tensor-core MLP chain -> max over the group
-            return ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=False)
+            # (weights packed with the xyz columns last, hence msg_order=True: aligned feature gathers)
+            return ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=True)
         grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=False)
         rows = _mlp_rows(grouped.view(B * S * K, -1), self._folded.get(self.mlp_convs, self.mlp_bns))
         return ops.group_max(rows, K).view(B, S, -1)
