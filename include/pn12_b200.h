@@ -59,7 +59,8 @@ int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int 
                const int64_t* start_idx, int64_t* out_idx, pn_stream_t stream);
 
 /* Tuning hook for pn_fps_f32: force the cluster size (1,2,4,8,16), threads per CTA (64..1024) and the
- * intra-cluster exchange (1 = DSMEM store + barrier.cluster, 2 = st.async + mbarrier); 0 = automatic.
+ * intra-cluster exchange (1 = DSMEM store + barrier.cluster, 2 = st.async + mbarrier, 3 = the same without the
+ * per-CTA z table, i.e. two st.async per winner instead of one); 0 = automatic.
  * Process-wide; meant for benchmarks and tests. */
 int pn_fps_set_config(int cluster_size, int threads, int exchange);
 
@@ -186,6 +187,13 @@ int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float*
                          int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
                          const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
                          int S, int K, int msg_order, float* out, int64_t ldo, pn_stream_t stream);
+/* The same with the output mode chosen by the caller: PN_MLP_OUT_MAX32 as above, or PN_MLP_OUT_ROWS to keep the
+ * [B*S*K, cout_last] rows (used when a level with few row tiles runs layer by layer: single-layer chains are
+ * N-sliced over gridDim.y so that they fill the GPU). */
+int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
+                     int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
+                     const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
+                     int S, int K, int msg_order, int out_mode, float* out, int64_t ldo, pn_stream_t stream);
 
 /* One feature-propagation level after the 3-NN search (model/pointnet_util.py:301-312): weighted gather of
  * the three coarse rows + skip concat straight into the tensor-core operand, then the conv+BN+ReLU chain.
@@ -207,7 +215,8 @@ int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* poi
 /* Tuning hook for the fused chains: 0 = automatic (chains whose packed weights fit in shared memory run on the
  * resident-weight kernel: weights loaded once per CTA, 2 or 4 warp groups per CTA each with its own row tile
  * and TMEM slice; larger chains stream their weights through a ring), 1 = always stream, 2 = resident or fail;
- * +4 = keep the row-per-thread producers (disables the coalesced quad producer of the FP levels).
+ * +4 = keep the row-per-thread producers (disables the coalesced quad producer of the FP levels);
+ * +8 = no N-slicing of single-layer chains.
  * Process-wide; meant for benchmarks and tests. */
 int pn_mlp_set_engine(int engine);
 /* Profiling hook: a device buffer of 4 * 64 * 32 int64 (or NULL to disable).  While set, CTA 0 of every resident-

@@ -176,7 +176,43 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     }
 }
 
-template <int NW, int PTS>
+// Packed fp32 pairs (FADD2 / FMUL2: two IEEE-rounded fp32 operations per instruction, bit-identical to the scalar
+// sequence): the distance update of two points costs 8 arithmetic instructions instead of 16.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// ((dx*dx + dy*dy) + dz*dz) for two points at once; n* = the negated centroid broadcast to both halves (p + (-c) == p - c)
+__device__ __forceinline__ void sqdist_diff2(unsigned long long px, unsigned long long py, unsigned long long pz,
+                                             unsigned long long ncx, unsigned long long ncy, unsigned long long ncz, float& d0,
+                                             float& d1) {
+    const unsigned long long dx = add2(px, ncx), dy = add2(py, ncy), dz = add2(pz, ncz);
+    // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it does not for the scalar .rn forms), which would
+    // change the rounding; the sums are therefore taken on the unpacked halves with the scalar _rn intrinsics.
+    const unsigned long long xx = mul2(dx, dx), yy = mul2(dy, dy), zz = mul2(dz, dz);
+    float x0, x1, y0, y1, z0, z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(y0), "=f"(y1) : "l"(yy));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(zz));
+    d0 = __fadd_rn(__fadd_rn(x0, y0), z0);
+    d1 = __fadd_rn(__fadd_rn(x1, y1), z1);
+}
+
+// ZT: every CTA also keeps the z coordinate of the WHOLE cloud in shared memory (4 N bytes), so a winner travels as
+// one 16-byte st.async (distance, index, x, y) instead of two (z is looked up locally by index): half the remote
+// writes per iteration on the receiving barriers.
+template <int NW, int PTS, bool ZT>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, int N, int npoint,
                  const int64_t* __restrict__ start, int64_t* __restrict__ out, int chunk) {
@@ -187,6 +223,7 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
     float* sx = reinterpret_cast<float*>(smem_raw + kAsyncSmemHeader);
     float* sy = sx + chunk;
     float* sz = sy + chunk;
+    float* zt = sz + chunk;   // [N] when ZT
 
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned CL = cluster.num_blocks();
@@ -197,21 +234,33 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
     const int base = rank * chunk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    float x[PTS], y[PTS], z[PTS], d[PTS];
+    static_assert(PTS % 2 == 0, "points are processed in packed pairs");
+    unsigned long long xp[PTS / 2], yp[PTS / 2], zp[PTS / 2];
+    float d[PTS];
 #pragma unroll
-    for (int k = 0; k < PTS; ++k) {
-        const int li = tid + k * THREADS;
-        const int j = base + li;
-        const bool ok = li < chunk && j < N;
-        x[k] = ok ? p[(int64_t)j * sN] : 0.0f;
-        y[k] = ok ? p[(int64_t)j * sN + sC] : 0.0f;
-        z[k] = ok ? p[(int64_t)j * sN + 2 * sC] : 0.0f;
-        d[k] = ok ? 1e10f : -2.0f;
-        if (li < chunk) {
-            sx[li] = x[k];
-            sy[li] = y[k];
-            sz[li] = z[k];
+    for (int k = 0; k < PTS; k += 2) {
+        float x[2], y[2], z[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int li = tid + (k + u) * THREADS;
+            const int j = base + li;
+            const bool ok = li < chunk && j < N;
+            x[u] = ok ? p[(int64_t)j * sN] : 0.0f;
+            y[u] = ok ? p[(int64_t)j * sN + sC] : 0.0f;
+            z[u] = ok ? p[(int64_t)j * sN + 2 * sC] : 0.0f;
+            d[k + u] = ok ? 1e10f : -2.0f;
+            if (li < chunk) {
+                sx[li] = x[u];
+                sy[li] = y[u];
+                sz[li] = z[u];
+            }
         }
+        xp[k / 2] = pack2(x[0], x[1]);
+        yp[k / 2] = pack2(y[0], y[1]);
+        zp[k / 2] = pack2(z[0], z[1]);
+    }
+    if constexpr (ZT) {
+        for (int i = tid; i < N; i += THREADS) zt[i] = p[(int64_t)i * sN + 2 * sC];
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[0])), "r"(1));
@@ -239,17 +288,24 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
         if (i == npoint - 1) break;  // the last arg-max would never be used
         if (tid == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_bar0 + par * kParBarOff),
-                         "r"((unsigned)(nslot * kSlotBytes))
+                         "r"((unsigned)(nslot * (ZT ? 16 : kSlotBytes)))
                          : "memory");
         float bv = -1.0f;
         int bk = 0;
+        const unsigned long long ncx = pack2(-cx, -cx), ncy = pack2(-cy, -cy), ncz = pack2(-cz, -cz);
 #pragma unroll
-        for (int k = 0; k < PTS; ++k) {
-            const float dd = sqdist_diff(x[k], y[k], z[k], cx, cy, cz);
-            d[k] = fminf(d[k], dd);
+        for (int k = 0; k < PTS; k += 2) {
+            float d0, d1;
+            sqdist_diff2(xp[k / 2], yp[k / 2], zp[k / 2], ncx, ncy, ncz, d0, d1);
+            d[k] = fminf(d[k], d0);
             if (d[k] > bv) {
                 bv = d[k];
                 bk = k;
+            }
+            d[k + 1] = fminf(d[k + 1], d1);
+            if (d[k + 1] > bv) {
+                bv = d[k + 1];
+                bk = k + 1;
             }
         }
         const unsigned vb = __float_as_uint(fmaxf(bv, 0.0f));
@@ -258,17 +314,20 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
         const unsigned wi = __reduce_min_sync(0xffffffffu, vb == wm ? gi : kNoIndex);
         if (lane < (int)CL) {
             const int li = wi == kNoIndex ? 0 : (int)wi - base;
-            const float mx = sx[li], my = sy[li], mz = sz[li];
+            const float mx = sx[li], my = sy[li];
             const unsigned r_slot = r_slot0 + par * kParSlotOff, r_bar = r_bar0 + par * kParBarOff;
             asm volatile(
                 "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
                     r_slot),
                 "r"(wm), "r"(wi), "r"(__float_as_uint(mx)), "r"(__float_as_uint(my)), "r"(r_bar)
                 : "memory");
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
-                             r_slot + 16),
-                         "r"(__float_as_uint(mz)), "r"(r_bar)
-                         : "memory");
+            if constexpr (!ZT) {
+                const float mz = sz[li];
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
+                                 r_slot + 16),
+                             "r"(__float_as_uint(mz)), "r"(r_bar)
+                             : "memory");
+            }
         }
         mbar_wait(l_bar0 + par * kParBarOff, (unsigned)((i >> 1) & 1));
         // reduce the CL*NW slots: one or two per lane
@@ -276,12 +335,14 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
         float px = 0.f, py = 0.f, pz = 0.f;
         if (lane < nslot) {
             const FpsSlot& s0 = slots[par * kMaxSlots + lane];
-            sv = s0.val; si = s0.idx; px = s0.x; py = s0.y; pz = s0.z;
+            sv = s0.val; si = s0.idx; px = s0.x; py = s0.y;
+            if constexpr (!ZT) pz = s0.z;
         }
         if (lane + 32 < nslot) {
             const FpsSlot& s1 = slots[par * kMaxSlots + lane + 32];
             if (s1.val > sv || (s1.val == sv && s1.idx < si)) {
-                sv = s1.val; si = s1.idx; px = s1.x; py = s1.y; pz = s1.z;
+                sv = s1.val; si = s1.idx; px = s1.x; py = s1.y;
+                if constexpr (!ZT) pz = s1.z;
             }
         }
         const unsigned bm = __reduce_max_sync(0xffffffffu, sv);
@@ -291,7 +352,8 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
         far = (int)bi;
         cx = __shfl_sync(0xffffffffu, px, src);
         cy = __shfl_sync(0xffffffffu, py, src);
-        cz = __shfl_sync(0xffffffffu, pz, src);
+        if constexpr (ZT) cz = zt[min(bi, (unsigned)(N - 1))];
+        else cz = __shfl_sync(0xffffffffu, pz, src);
     }
     cluster.sync();  // nobody leaves while a peer may still be storing into its shared memory
 }
@@ -357,12 +419,18 @@ static int dispatch_barrier(int pts, int CL, const float* xyz, int64_t sB, int64
     return PN_ERR_UNSUPPORTED;
 }
 
+static int g_force_ztable = 0;   // 0 auto (z table when it fits), 1 never
+
 template <int NW>
 static int dispatch_async(int pts, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
                           const int64_t* start, int64_t* out, int chunk, cudaStream_t stream) {
-    const size_t smem = (size_t)kAsyncSmemHeader + (size_t)chunk * 3 * sizeof(float);
-#define PN_FPS_CASE(P) \
-    if (pts <= P) return launch_cluster_kernel(fps_async_kernel<NW, P>, "fps_async_kernel", CL, NW * 32, smem, PN_FPS_ARGS)
+    const size_t smem0 = (size_t)kAsyncSmemHeader + (size_t)chunk * 3 * sizeof(float);
+    const bool zt = g_force_ztable == 0 && smem0 + (size_t)N * sizeof(float) <= 200 * 1024;
+    const size_t smem = smem0 + (zt ? (size_t)N * sizeof(float) : 0);
+#define PN_FPS_CASE(P)                                                                                                       \
+    if (pts <= P)                                                                                                            \
+        return zt ? launch_cluster_kernel(fps_async_kernel<NW, P, true>, "fps_async_kernel", CL, NW * 32, smem, PN_FPS_ARGS) \
+                  : launch_cluster_kernel(fps_async_kernel<NW, P, false>, "fps_async_kernel", CL, NW * 32, smem, PN_FPS_ARGS)
     PN_FPS_CASE(4);
     PN_FPS_CASE(8);
     PN_FPS_CASE(12);
@@ -381,11 +449,12 @@ PN_EXPORT int pn_fps_set_config(int cluster_size, int threads, int exchange) {
                        cluster_size == 8 || cluster_size == 16;
     const bool th_ok = threads == 0 || threads == 64 || threads == 128 || threads == 256 || threads == 512 ||
                        threads == 1024;
-    PN_REQUIRE(cl_ok && th_ok && exchange >= 0 && exchange <= 2, PN_ERR_BAD_ARG,
-               "pn_fps_set_config: cluster_size in {0,1,2,4,8,16}, threads in {0,64..1024}, exchange in {0,1,2}");
+    PN_REQUIRE(cl_ok && th_ok && exchange >= 0 && exchange <= 3, PN_ERR_BAD_ARG,
+               "pn_fps_set_config: cluster_size in {0,1,2,4,8,16}, threads in {0,64..1024}, exchange in {0,1,2,3}");
     pn::g_force_cluster = cluster_size;
     pn::g_force_threads = threads;
-    pn::g_force_exchange = exchange;
+    pn::g_force_exchange = exchange == 3 ? 2 : exchange;
+    pn::g_force_ztable = exchange == 3 ? 1 : 0;
     return PN_OK;
 }
 

@@ -42,6 +42,7 @@ struct TcLayer {
 struct TcChain {
     int nlayers, stage_bytes, tmem_cols, x_cols, a_lo_off, bias_floats;
     int nstages;        // ring depth of the streaming kernel (set at launch)
+    int pass_w;         // output channels per accumulation pass of the streaming kernel: kTcNPass, or the N-slice width
     unsigned bias_off;  // byte offset of the bias table in the blob
     unsigned blob_bytes;
     TcLayer L[kTcMaxLayers];
@@ -128,6 +129,13 @@ __device__ __forceinline__ void tc_mbar_wait(unsigned bar, unsigned parity) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
+}
+// one lane of a converged warp (the instruction sequence around it stays warp-uniform, so descriptors and barrier
+// addresses are computed in uniform registers instead of being moved there lane by lane)
+__device__ __forceinline__ bool tc_elect() {
+    unsigned p;
+    asm volatile("{ .reg .pred q; elect.sync _|q, 0xffffffff; selp.u32 %0, 1, 0, q; }" : "=r"(p));
+    return p != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -583,10 +591,14 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
         for (int l = 0; l < ch.nlayers; ++l) {
             const TcLayer& L = ch.L[l];
             const bool last = l + 1 == ch.nlayers;
-            const int npass = (L.n_pad + kTcNPass - 1) / kTcNPass;
+            // output channels are produced in passes of PW columns; with gridDim.y > 1 (single-layer chains on few row
+            // tiles) the passes of a tile are spread over the CTAs (tile, y): N-slicing fills the GPU when rows are scarce
+            const int PW = ch.pass_w;
+            const int npass = (L.n_pad + PW - 1) / PW;
             const int nchunk = (L.k_pad + kTcAChunk - 1) / kTcAChunk;   // > 1 only for a wide first layer
-            for (int p = 0; p < npass; ++p) {
-                const int rows_p = min(kTcNPass, L.n_pad - p * kTcNPass);
+            for (int p = blockIdx.y; p < npass; p += gridDim.y) {
+                const int n0 = p * PW;                                   // first output channel of the pass
+                const int rows_p = min(PW, L.n_pad - n0);
                 for (int a = 0; a < nchunk; ++a) {
                     const int kbase = a * kTcAChunk;
                     const int kchunk = min(kTcAChunk, L.k_pad - kbase);
@@ -611,65 +623,86 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     }
                     const int s0 = kbase / kTcKSub, ns = (kchunk + kTcKSub - 1) / kTcKSub;
                     if (warp == 4) {
-                      if (lane == 0) {
-                        // ---- copy thread: the weight slices of this chunk, one cp.async.bulk (TMA engine) each, running up to
-                        // NS slices ahead of the tensor core; a stage is reused once the MMAs that read it have completed
-                        const unsigned char* wpass = blob + L.w_off + (size_t)p * kTcNPass * L.k_pad * 4;
+                        // ---- copy warp (all lanes walk the loop, one elected lane issues): the weight slices of this chunk, one
+                        // or two cp.async.bulk (TMA engine) each, running up to NS slices ahead of the tensor core; a stage is
+                        // reused once the MMAs that read it have completed.
+                        // The blob stores 256-row blocks: [block P][slice][hi image | lo image]; rows [r0, r0 + rows_p) of a
+                        // slice image are contiguous (8-row groups are the outer dimension of the core-matrix layout).
+                        const int P = n0 / kTcNPass, r0 = n0 % kTcNPass;
+                        const int rows_P = min(kTcNPass, L.n_pad - P * kTcNPass);
+                        const unsigned char* wpass = blob + L.w_off + (size_t)P * kTcNPass * L.k_pad * 4;
                         for (int s = 0; s < ns; ++s) {
                             const int kw = min(kTcKSub, L.k_pad - (s0 + s) * kTcKSub);
                             const unsigned bytes = (unsigned)rows_p * kw * 4;
+                            const unsigned char* src = wpass + (size_t)rows_P * ((s0 + s) * kTcKSub) * 4 + (size_t)r0 * kw * 2;
+                            const unsigned dst = stage0 + fill_st * (unsigned)ch.stage_bytes;
+                            const unsigned full = bar_full0 + 8 * fill_st;
                             tc_mbar_wait(bar_empty0 + 8 * fill_st, ((fill / NS) & 1) ^ 1);
-                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full0 + 8 * fill_st), "r"(bytes) : "memory");
-                            asm volatile(
-                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                    stage0 + fill_st * (unsigned)ch.stage_bytes),
-                                "l"(wpass + (size_t)rows_p * ((s0 + s) * kTcKSub) * 4), "r"(bytes), "r"(bar_full0 + 8 * fill_st)
-                                : "memory");
+                            if (tc_elect()) {
+                                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+                                if (rows_p == rows_P) {   // hi and lo images are adjacent: one copy
+                                    asm volatile(
+                                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                                        "l"(src), "r"(bytes), "r"(full)
+                                        : "memory");
+                                } else {
+                                    asm volatile(
+                                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                                        "l"(src), "r"(bytes / 2), "r"(full)
+                                        : "memory");
+                                    asm volatile(
+                                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                            dst + bytes / 2),
+                                        "l"(src + (size_t)rows_P * kw * 2), "r"(bytes / 2), "r"(full)
+                                        : "memory");
+                                }
+                            }
+                            __syncwarp();
                             ++fill;
                             fill_st = fill_st + 1 == (unsigned)NS ? 0u : fill_st + 1;
                         }
-                      }
-                      __syncwarp();
                     }
                     if (warp == 0) {
-                      if (lane == 0) {
+                        // ---- MMA warp (same scheme): the MMAs of a slice are issued as soon as it has landed
                         tc_fence_after();
-                        // ---- MMA thread: issues the MMAs of a slice as soon as it has landed
                         const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(rows_p >> 3) << 17) | (8u << 24);
                         for (int s = 0; s < ns; ++s) {
                             const int kw = min(kTcKSub, L.k_pad - (s0 + s) * kTcKSub);
                             tc_mbar_wait(bar_full0 + 8 * use_st, (use / NS) & 1);
                             tc_fence_after();
+                            stamp(6);
                             const unsigned b_hi = stage0 + use_st * (unsigned)ch.stage_bytes, b_lo = b_hi + (unsigned)rows_p * kw * 2;
                             const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
                                                              ((unsigned long long)((((unsigned)kw / 8) * 128u >> 4) & 0x3FFF) << 32) |
                                                              (1ull << 46);
-                            for (int t = 0; t < kw / 16; ++t) {
-                                const unsigned kcol = (unsigned)(s * kTcKSub + t * 16) / 2;   // A columns of this K step
-                                const unsigned long long dh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
-                                const unsigned long long dl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
-                                const unsigned acc0 = (a > 0 || s > 0 || t > 0) ? 1u : 0u;
-                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                                 tbase),
-                                             "r"(a_hi_col + kcol), "l"(dh), "r"(idesc), "r"(acc0)
-                                             : "memory");
-                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                                 tbase),
-                                             "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
-                                             : "memory");
-                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                                 tbase),
-                                             "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
-                                             : "memory");
+                            if (tc_elect()) {
+                                for (int t = 0; t < kw / 16; ++t) {
+                                    const unsigned kcol = (unsigned)(s * kTcKSub + t * 16) / 2;   // A columns of this K step
+                                    const unsigned long long dh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
+                                    const unsigned long long dl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
+                                    const unsigned acc0 = (a > 0 || s > 0 || t > 0) ? 1u : 0u;
+                                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                     tbase),
+                                                 "r"(a_hi_col + kcol), "l"(dh), "r"(idesc), "r"(acc0)
+                                                 : "memory");
+                                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                     tbase),
+                                                 "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
+                                                 : "memory");
+                                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                     tbase),
+                                                 "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
+                                                 : "memory");
+                                }
+                                tc_commit(bar_empty0 + 8 * use_st);
+                                if (s + 1 == ns) tc_commit(bar_done);
                             }
-                            tc_commit(bar_empty0 + 8 * use_st);
+                            __syncwarp();
+                            stamp(7);
                             ++use;
                             use_st = use_st + 1 == (unsigned)NS ? 0u : use_st + 1;
                         }
-                        tc_commit(bar_done);
                         stamp(3);
-                      }
-                      __syncwarp();   // lanes 1-31 park here (no spinning) while lane 0 feeds the tensor core
                     }
                     // ---- everyone waits for this chunk's MMAs (the A region / accumulator are then free to touch)
                     tc_mbar_wait(bar_done, done_phase);
@@ -678,7 +711,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     stamp(4);
                 }
                 // ---- epilogue of pass p: accumulator columns [0, rows_p)
-                const float* bias = sbias + L.b_off + p * kTcNPass;
+                const float* bias = sbias + L.b_off + n0;
                 if (!last) {
                     for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
                         unsigned r[32];
@@ -699,8 +732,8 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         if (rc.valid) {
-                            float* dst = io.y + rc.row * io.ldy + p * kTcNPass + c0;
-                            const int nleft = L.n_real - (p * kTcNPass + c0);
+                            float* dst = io.y + rc.row * io.ldy + n0 + c0;
+                            const int nleft = L.n_real - (n0 + c0);
                             const bool vec = nleft >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -739,7 +772,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                             v[j] = rc.valid ? f : -CUDART_INF_F;
                         }
                         const float mine = tc_colmax32(v, lane);
-                        const int n = p * kTcNPass + c0 + lane;
+                        const int n = n0 + c0 + lane;
                         if (any_valid && n < L.n_real) io.y[g * io.ldy + n] = mine;
                     }
                     tc_fence_before();
@@ -1046,6 +1079,7 @@ static size_t tc_res_smem_bytes(const TcChain& c) { return (size_t)((c.blob_byte
 static int g_tc_engine = 0;
 static long long* g_tc_dbg = nullptr;   // pn_mlp_set_debug
 static int g_tc_quad = 1;               // pn_mlp_set_engine(engine | 4) disables the coalesced quad producer
+static int g_tc_nslice = 1;             // pn_mlp_set_engine(engine | 8) disables N-slicing of single-layer chains
 
 // Resident kernel usable?  Returns warps per group (8 or 4), or 0.
 static int tc_resident_wpg(const TcChain& c) {
@@ -1065,7 +1099,13 @@ static size_t tc_smem_bytes(const TcChain& c, int nstages) {
 template <int IN>
 static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaStream_t stream, const char* what) {
     const int64_t ntiles_all = io.nseg * ((io.seg_rows + 127) / 128);
-    const int wpg = g_tc_engine == 1 ? 0 : tc_resident_wpg(ch);
+    // single-layer chains on few row tiles: slice the output channels over gridDim.y so that the launch fills the GPU
+    int pass_w = kTcNPass;
+    if (ch.nlayers == 1 && g_tc_nslice && io.out_mode != TC_OUT_LOGSOFTMAX && ntiles_all * ((ch.L[0].n_pad + kTcNPass - 1) / kTcNPass) < 148) {
+        pass_w = 128;
+        while (pass_w > 32 && ntiles_all * ((ch.L[0].n_pad + pass_w - 1) / pass_w) < 148) pass_w /= 2;
+    }
+    const int wpg = (g_tc_engine == 1 || (pass_w != kTcNPass && g_tc_engine != 2)) ? 0 : tc_resident_wpg(ch);
     PN_REQUIRE(g_tc_engine != 2 || wpg != 0, PN_ERR_UNSUPPORTED, "%s: chain does not fit the resident kernel", what);
     if (wpg != 0) {
         const size_t rsmem = tc_res_smem_bytes(ch);
@@ -1088,11 +1128,22 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     // ring depth: as deep as shared memory allows (a CTA alone on its SM when the grid is small: up to ~200 KB;
     // otherwise ~110 KB so that two CTAs share an SM), at least 2, at most kTcMaxStages
     TcChain chs = ch;
+    chs.pass_w = pass_w;
+    if (pass_w != kTcNPass) {   // re-plan the per-CTA resources for the narrower pass
+        const TcLayer& L0 = ch.L[0];
+        const int xw = L0.n_pad < pass_w ? L0.n_pad : pass_w;
+        const int a_k = 2 * ch.a_lo_off;
+        chs.x_cols = xw;
+        chs.stage_bytes = xw * (L0.k_pad < kTcKSub ? L0.k_pad : kTcKSub) * 4;
+        int p2 = 32;
+        while (p2 < xw + a_k) p2 <<= 1;
+        chs.tmem_cols = p2;
+    }
     {
-        const int by_tmem = 512 / ch.tmem_cols;
+        const int by_tmem = 512 / chs.tmem_cols;
         const size_t budget = (ntiles_all <= 148 || by_tmem < 2) ? 200 * 1024 : 110 * 1024;
-        const size_t fixed = tc_smem_bytes(ch, 0);
-        int ns = (int)((budget - fixed) / (size_t)ch.stage_bytes);
+        const size_t fixed = tc_smem_bytes(chs, 0);
+        int ns = (int)((budget - fixed) / (size_t)chs.stage_bytes);
         ns = ns < 2 ? 2 : (ns > kTcMaxStages ? kTcMaxStages : ns);
         chs.nstages = ns;
     }
@@ -1107,12 +1158,13 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     }
     const int64_t ntiles = io.nseg * ((io.seg_rows + 127) / 128);
     // co-resident CTAs per SM: limited by TMEM columns (512) and shared memory
-    int per_sm = 512 / ch.tmem_cols;
+    int per_sm = 512 / chs.tmem_cols;
     const int by_smem = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < by_smem ? per_sm : by_smem;
     per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);   // __launch_bounds__(256, 2): registers allow two CTAs per SM
     const int64_t cap = 148LL * per_sm;
-    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    const unsigned ny = (unsigned)((ch.L[ch.nlayers - 1].n_pad + pass_w - 1) / pass_w);
+    const dim3 grid((unsigned)(ntiles < cap ? ntiles : cap), pass_w != kTcNPass ? ny : 1u);
     TcIo io2 = io;
     io2.dbg = g_tc_dbg;
     kern<<<grid, kTcThreads, smem, stream>>>(chs, static_cast<const unsigned char*>(blob), io2);
@@ -1128,10 +1180,12 @@ PN_EXPORT int pn_mlp_set_debug(void* timeline) {
 }
 
 PN_EXPORT int pn_mlp_set_engine(int engine) {
-    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 8, PN_ERR_BAD_ARG,
-               "pn_mlp_set_engine: 0 = automatic, 1 = streaming, 2 = resident; +4 = row-per-thread producers only");
+    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 16, PN_ERR_BAD_ARG,
+               "pn_mlp_set_engine: 0 = automatic, 1 = streaming, 2 = resident; +4 = row-per-thread producers only; "
+               "+8 = no N-slicing");
     pn::g_tc_engine = engine & 3;
     pn::g_tc_quad = (engine & 4) ? 0 : 1;
+    pn::g_tc_nslice = (engine & 8) ? 0 : 1;
     return PN_OK;
 }
 
@@ -1200,10 +1254,20 @@ PN_EXPORT int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, co
                                    int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
                                    const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
                                    int S, int K, int msg_order, float* out, int64_t ldo, pn_stream_t stream) {
+    return pn_sa_mlp_bf16x3(desc, blob, xyz, xB, xN, xC, feat, fB, fN, fC, D, new_xyz, qB, qN, qC, idx, B, N, S, K, msg_order,
+                            PN_MLP_OUT_MAX32, out, ldo, stream);
+}
+
+PN_EXPORT int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
+                               int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
+                               const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
+                               int S, int K, int msg_order, int out_mode, float* out, int64_t ldo, pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
-    int rc = tc_common_checks(desc, blob, &ch, TC_OUT_MAX, "pn_sa_mlp_max_bf16x3");
+    int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_sa_mlp_max_bf16x3");
     if (rc) return rc;
+    PN_REQUIRE(out_mode == TC_OUT_MAX || out_mode == TC_OUT_ROWS, PN_ERR_BAD_ARG,
+               "pn_sa_mlp_bf16x3: out_mode must be 0 (rows) or 1 (max over nsample)");
     PN_REQUIRE(xyz && new_xyz && idx && out, PN_ERR_BAD_ARG, "pn_sa_mlp_max_bf16x3: null pointer");
     PN_REQUIRE((feat != nullptr) == (D > 0) && desc->cin[0] == 3 + D, PN_ERR_BAD_ARG,
                "pn_sa_mlp_max_bf16x3: first layer expects %d channels, grouping provides 3 + %d", desc->cin[0], D);
@@ -1216,7 +1280,7 @@ PN_EXPORT int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, co
     io.feat = feat; io.fB = fB; io.fN = fN; io.fC = fC; io.D = D;
     io.qxyz = new_xyz; io.qB = qB; io.qN = qN; io.qC = qC;
     io.idx = idx; io.N = N; io.S = S; io.K = K; io.msg_order = msg_order;
-    io.out_mode = TC_OUT_MAX;
+    io.out_mode = out_mode;
     io.y = out;
     io.ldy = ldo;
     io.group = K;

@@ -155,6 +155,26 @@ class FoldedLayers:
                 self._chain = ops.PackedChain(packed)
         return self._chain or None
 
+    def layer_chains(self, convs, bns, relus=None, xyz_last: bool = False):
+        """Every layer as its own packed single-layer chain (for levels with so few row tiles that a fused chain
+        would leave most SMs idle: a single-layer launch is N-sliced over the grid instead), or None."""
+        if ops.mlp_mode() != "bf16x3":
+            return None
+        layers = self.get(convs, bns)
+        if getattr(self, "_per_layer", None) is None or self._per_layer_key is not self._layers:
+            dims = [(w.shape[1], w.shape[0]) for w, _ in layers]
+            if not all(ops.PackedChain.supported([d]) for d in dims):
+                self._per_layer = False
+            else:
+                relus = [True] * len(layers) if relus is None else list(relus)
+                packed = [(w, b, r) for (w, b), r in zip(layers, relus)]
+                if xyz_last:
+                    w0, b0, r0 = packed[0]
+                    packed[0] = (torch.cat([w0[:, 3:], w0[:, :3]], 1).contiguous(), b0, r0)
+                self._per_layer = [ops.PackedChain([t]) for t in packed]
+            self._per_layer_key = self._layers
+        return self._per_layer or None
+
     def chain_folded_first(self, convs, bns, relus):
         """(first, rest): the first layer as a one-layer chain WITHOUT activation and the remaining layers, for a
         feature-propagation level without skip input: conv(interp(p2)) + b == interp(conv(p2) + b) because the
@@ -215,6 +235,14 @@ class PointNetSetAbstraction(nn.Module):
     def features(self, xyz_pm, pts_pm, new_xyz, idx) -> torch.Tensor:
         """-> pooled [B,S,C'] point-major."""
         B, S, K = idx.shape
+        if K == 32 and len(self.mlp_convs) > 1 and B * S * K // 128 < ops.LAYERWISE_MAX_TILES:
+            per_layer = self._folded.layer_chains(self.mlp_convs, self.mlp_bns, xyz_last=True)
+            if per_layer is not None:
+                # few row tiles: layer by layer, every launch N-sliced over the whole GPU
+                rows = ops.sa_mlp_max_tc(per_layer[0], xyz_pm, pts_pm, new_xyz, idx, msg_order=True, out_mode=ops.OUT_ROWS)
+                for c in per_layer[1:-1]:
+                    rows = ops.mlp_rows_tc(c, rows)
+                return ops.mlp_rows_tc(per_layer[-1], rows, ops.OUT_MAX32).view(B, S, -1)
         chain = self._folded.chain(self.mlp_convs, self.mlp_bns, xyz_last=True) if K == 32 else None
         if chain is not None:
             # one kernel: gather + recentre + concat -> tensor-core MLP chain -> max over the group
@@ -335,6 +363,15 @@ class PointNetFeaturePropagation(nn.Module):
                     z = (p2, ops.mlp_rows_tc(first, p2.reshape(B * S, D2)).view(B, S, -1))
                     self._z_cache = z if clouds is not None else None   # reused by the next batch slice of this call
                 return ops.fp_mlp_tc(rest, None, z[1], idx, w, out_mode, relu_in=True, order=order, out=out, clouds=clouds)
+        if (head is None and out is None and clouds is None and len(convs) > 1
+                and B * ((N + 127) // 128) < ops.LAYERWISE_MAX_TILES):
+            per_layer = folded.layer_chains(convs, bns, relus)
+            if per_layer is not None:
+                # few row tiles: layer by layer, every launch N-sliced over the whole GPU
+                rows = ops.fp_mlp_tc(per_layer[0], p1, p2, idx, w, ops.OUT_ROWS, order=order).view(B * N, -1)
+                for c in per_layer[1:]:
+                    rows = ops.mlp_rows_tc(c, rows)
+                return rows.view(B, N, -1)
         chain = folded.chain(convs, bns, relus)
         if chain is not None:
             # one kernel: weighted 3-row gather + skip concat -> tensor-core MLP chain (-> head -> log_softmax)

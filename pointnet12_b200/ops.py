@@ -345,10 +345,16 @@ def set_mlp_engine(engine: str = "auto") -> None:
     """Tuning hook (pn_mlp_set_engine): 'auto' (resident-weight kernel when the packed chain fits in shared memory,
     streaming ring otherwise), 'stream' or 'resident'; '*-rowwise' keeps the row-per-thread producers (no coalesced
     quad producer) for A/B comparisons."""
-    nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2, "auto-rowwise": 4, "resident-rowwise": 6}[engine])
+    nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2, "auto-rowwise": 4, "resident-rowwise": 6,
+                                  "auto-noslice": 8, "stream-noslice": 9}[engine])
 
 
 FOLD_FIRST_FP_LAYER = os.environ.get("PN12_FP_FOLD", "1") != "0"
+# Levels with fewer 128-row tiles than this run layer by layer: a single-layer chain is N-sliced over gridDim.y, so
+# every launch fills the GPU, whereas the fused chain occupies only `tiles` SMs for the whole level.  Measured on
+# B200 at C2 size the fused chains still win (every sliced launch repeats the row producer, which is the latency-
+# bound part: sa4 73 vs 40 us, fp2 84 vs 41 us), so the default is 0 = never; kept for larger per-level row counts.
+LAYERWISE_MAX_TILES = int(os.environ.get("PN12_LAYERWISE_TILES", "0"))
 
 
 class PackedChain:
@@ -388,22 +394,30 @@ class PackedChain:
         return nv.lib().pn_mlp_blob_bytes(C.byref(d)) > 0
 
 
-def mlp_rows_tc(chain: PackedChain, x: torch.Tensor, out_mode: int = OUT_ROWS) -> torch.Tensor:
-    """chain(x) for x [rows, cin]; OUT_MAX32 pools every 32 consecutive rows, OUT_LOG_SOFTMAX ends in log_softmax."""
+def mlp_rows_tc(chain: PackedChain, x: torch.Tensor, out_mode: int = OUT_ROWS,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """chain(x) for x [rows, cin]; OUT_MAX32 pools every 32 consecutive rows, OUT_LOG_SOFTMAX ends in log_softmax.
+    out: optional [out_rows, cout] view with unit channel stride to write into."""
     x, rows, cin, ldx = _rows(x, "x")
     if cin != chain.cin:
         raise ValueError(f"chain expects {chain.cin} input channels, got {cin}")
     out_rows = rows // 32 if out_mode == OUT_MAX32 else rows
-    out = torch.empty((out_rows, chain.cout), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((out_rows, chain.cout), dtype=torch.float32, device=x.device)
+    elif out.shape != (out_rows, chain.cout) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("out must be a float32 [out_rows, cout] view with unit channel stride")
+    ldy = out.stride(0) if out_rows > 1 else max(out.stride(0), chain.cout)
     with _on_device(x):
         nv.call("pn_mlp_rows_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), x.data_ptr(), ldx, rows, out_mode,
-                out.data_ptr(), chain.cout, _stream())
+                out.data_ptr(), ldy, _stream())
     return out
 
 
 def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Tensor], new_xyz: torch.Tensor,
-                  idx: torch.Tensor, msg_order: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Grouping + shared MLP + max over nsample in one kernel -> [B, S, cout] (or into the strided view `out`)."""
+                  idx: torch.Tensor, msg_order: bool, out: Optional[torch.Tensor] = None,
+                  out_mode: int = 1) -> torch.Tensor:
+    """Grouping + shared MLP + max over nsample in one kernel -> [B, S, cout] (or into the strided view `out`).
+    out_mode=OUT_ROWS keeps the grouped rows instead: [B*S*K, cout] (layer-by-layer execution of small levels)."""
     xyz, new_xyz = _cloud(xyz, "xyz", 3), _cloud(new_xyz, "new_xyz", 3)
     idx = _i64(idx, "idx")
     B, N, _ = xyz.shape
@@ -413,7 +427,12 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
         D, fs = feat.shape[2], feat.stride()
     else:
         D, fs = 0, (0, 0, 0)
-    if out is None:
+    if out_mode == OUT_ROWS:
+        if out is not None:
+            raise ValueError("out= is only supported with the max-pooled output")
+        out = torch.empty((B * S * K, chain.cout), dtype=torch.float32, device=xyz.device)
+        ldo = chain.cout
+    elif out is None:
         out = torch.empty((B, S, chain.cout), dtype=torch.float32, device=xyz.device)
         ldo = chain.cout
     else:
@@ -421,9 +440,9 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
             raise ValueError("out must be a [B*S, cout] view with unit channel stride")
         ldo = out.stride(0)
     with _on_device(xyz):
-        nv.call("pn_sa_mlp_max_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), xyz.data_ptr(), *xyz.stride(), _p(feat),
-                *fs, D, new_xyz.data_ptr(), *new_xyz.stride(), idx.data_ptr(), B, N, S, K, int(msg_order), out.data_ptr(),
-                ldo, _stream())
+        nv.call("pn_sa_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), xyz.data_ptr(), *xyz.stride(), _p(feat),
+                *fs, D, new_xyz.data_ptr(), *new_xyz.stride(), idx.data_ptr(), B, N, S, K, int(msg_order), int(out_mode),
+                out.data_ptr(), ldo, _stream())
     return out
 
 

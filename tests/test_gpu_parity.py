@@ -91,10 +91,10 @@ def test_fps_vs_oracle(dev, N, npoint, B):
 @pytest.mark.parametrize("cluster,threads,exchange", [(1, 1024, 0), (2, 512, 1), (4, 256, 1), (8, 128, 1), (8, 512, 1),
                                                       (16, 128, 1), (16, 256, 1), (2, 128, 2), (2, 256, 2), (4, 64, 2),
                                                       (4, 128, 2), (8, 64, 2), (8, 128, 2), (8, 256, 2), (16, 64, 2),
-                                                      (16, 128, 2)])
+                                                      (16, 128, 2), (8, 128, 3), (4, 128, 3), (16, 64, 3)])
 def test_fps_every_cluster_shape(dev, cluster, threads, exchange):
-    """Every cluster size / CTA width / exchange mechanism (barrier.cluster or st.async + mbarrier) gives the
-    same (bit-exact) answer."""
+    """Every cluster size / CTA width / exchange mechanism (barrier.cluster, st.async + mbarrier with the per-CTA z
+    table = one 16-byte message per winner, or without it = two messages) gives the same (bit-exact) answer."""
     from pointnet12_b200 import ops
 
     N, npoint, B = 8000, 128, 3
@@ -461,6 +461,50 @@ def test_fp_mlp_tc_vs_oracle(dev, mlp_engine, D1, D2, S):
     chain = ops.PackedChain([(cuda(wt, dev), cuda(b, dev), r) for wt, b, r in layers])
     got = ops.fp_mlp_tc(chain, cuda(p1, dev) if D1 else None, cuda(p2, dev), cuda(idx, dev), cuda(w, dev), ops.OUT_ROWS)
     assert rel_err(got, want) < TC_TOL
+
+
+@pytest.mark.parametrize("engine", ["auto", "auto-noslice"])
+@pytest.mark.parametrize("cin,cout,rows,mode", [(768, 256, 512, "rows"), (256, 512, 4096, "max"), (259, 256, 4096, "rows"),
+                                                (320, 256, 2048, "rows"), (128, 1024, 256, "max"), (131, 96, 640, "rows"),
+                                                (64, 300, 100, "rows")])
+def test_mlp_single_layer_n_sliced(dev, engine, cin, cout, rows, mode):
+    """Single-layer chains on few row tiles are N-sliced over gridDim.y (32/64/128-column passes, weight sub-blocks
+    fetched as two bulk copies); same result as the unsliced launch and the oracle."""
+    from pointnet12_b200 import ops
+
+    layers = _rand_layers([(cin, cout)], seed=cin + cout, last_relu=True)
+    x = np.random.default_rng(rows).normal(size=(rows, cin)).astype(np.float32)
+    ref = _chain_ref(x, layers)
+    chain = ops.PackedChain([(cuda(w, dev), cuda(b, dev), r) for w, b, r in layers])
+    try:
+        ops.set_mlp_engine(engine)
+        if mode == "max":
+            got, want = ops.mlp_rows_tc(chain, cuda(x, dev), ops.OUT_MAX32), orc.group_max(ref, 32)
+        else:
+            got, want = ops.mlp_rows_tc(chain, cuda(x, dev), ops.OUT_ROWS), ref
+    finally:
+        ops.set_mlp_engine("auto")
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TC_TOL
+
+
+def test_small_levels_layerwise_equals_fused(dev, ckpt_path):
+    """A level with few row tiles runs layer by layer (N-sliced launches); the fused chain gives the same features."""
+    from pointnet12_b200 import ops
+    from pointnet12_b200.model.utils import load_pointnet
+
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev).module
+    pts = cuda(syn.kitti_batch(2, 4096, config=12), dev)
+    outs = []
+    for limit in (100000, 0):
+        old, ops.LAYERWISE_MAX_TILES = ops.LAYERWISE_MAX_TILES, limit
+        try:
+            torch.manual_seed(3)
+            with torch.no_grad():
+                outs.append(net(pts).clone())
+        finally:
+            ops.LAYERWISE_MAX_TILES = old
+    assert rel_err(outs[0], outs[1].cpu().numpy()) < 1e-5
 
 
 @pytest.mark.parametrize("dims,rows,mode", [([(4, 32), (32, 32), (32, 64)], 128 * 1300 + 32, "max"),

@@ -22,7 +22,8 @@ def mk(dims, last_relu=True):
     return ops.PackedChain(out)
 
 
-cfg = {"fp4": (64, 16, 512, 256, [(768, 256), (256, 256)]), "fp3": (256, 64, 256, 128, [(384, 256), (256, 256)]),
+cfg = {"fp4l1": (64, 16, 512, 256, [(768, 256)]), "fp2l1": (1024, 256, 64, 256, [(320, 256)]),
+       "fp4": (64, 16, 512, 256, [(768, 256), (256, 256)]), "fp3": (256, 64, 256, 128, [(384, 256), (256, 256)]),
        "fp2": (1024, 256, 64, 256, [(320, 256), (256, 128)])}
 if which in cfg:
     N, S, D1, D2, dims = cfg[which]
@@ -51,7 +52,7 @@ torch.cuda.synchronize()
 nv.call("pn_mlp_set_debug", None)
 t = dbg.cpu().numpy()
 n = int(t[0])
-names = {1: "tile", 2: "prod", 3: "issued", 4: "ready", 5: "epi"}
+names = {1: "tile", 2: "prod", 3: "issued", 4: "ready", 5: "epi", 6: "w", 7: "m"}
 prev = t[2]
 out = []
 for i in range(n):
