@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (our arm only)")
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch of the critical-path kernels")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: one CUDA-graph replay per step (default); eager: ~40 launches per step")
     return ap.parse_args()
@@ -170,6 +171,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.pdl:
+        ops.set_pdl(True)
     net = load_pointnet("pointnet2", CLASSES, CKPT, device=dev)
     # four different batches per rank, rotated, so consecutive steps never see the same clouds
     host_batches = [torch.from_numpy(syn.kitti_batch(BATCH, NPOINTS, config=2, first=(rank * 4 + i) * BATCH)).pin_memory()

@@ -44,6 +44,9 @@ enum pn_status {
 /* Library identification: version = major*10000 + minor*100 + patch. */
 int pn_version(void);
 const char* pn_last_error_string(void);
+/* Programmatic dependent launch of the critical-path kernels (chains, grid ball query, index_points): 1 = on,
+ * 0 = plain stream-ordered launches (default: inside the CUDA graph the dependent launch brought no gain).  Process-wide. */
+int pn_set_pdl(int enabled);
 /* Queries the current device; fails with PN_ERR_DEVICE unless compute capability is 10.x. */
 int pn_device_check(int* sm_count, int* cc_major, int* cc_minor);
 

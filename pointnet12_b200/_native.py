@@ -32,6 +32,7 @@ _descp = C.POINTER(MlpDesc)
 # name -> argtypes, mirroring include/pn12_b200.h
 _SIGNATURES = {
     "pn_version": [],
+    "pn_set_pdl": [i32],
     "pn_device_check": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
     "pn_fps_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp],
     "pn_fps_set_config": [i32, i32, i32],

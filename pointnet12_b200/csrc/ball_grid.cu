@@ -194,6 +194,8 @@ ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, in
                        float radius2, int K, const unsigned char* __restrict__ ws_all, size_t ws_stride, int threshold,
                        int bm_words, int64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char gq_smem[];
+    pdl_trigger();
+    pdl_wait();   // the centroids come from the kernel before
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int s = blockIdx.x * WARPS + warp;
@@ -399,10 +401,14 @@ PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, i
             return (int)e;
         }
         dim3 grid((unsigned)ceil_div(S, warps), (unsigned)B);
-        kern<<<grid, warps * 32, smem, st>>>(xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
-                                             static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N), threshold,
-                                             bm_words, out_idx);
-        return finish_launch("pn_ball_query_grid_f32");
+        e = launch_pdl(kern, grid, dim3(warps * 32), smem, st, xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
+                       static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N), threshold, bm_words, out_idx);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pn_ball_query_grid_f32: launch failed: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        return PN_OK;
     };
     if (N <= 32768) return launch(ball_query_grid_kernel<8>, 8);      // bitmaps: <= 4 KB per warp
     if (N <= 262144) return launch(ball_query_grid_kernel<4>, 4);     // <= 32 KB per warp

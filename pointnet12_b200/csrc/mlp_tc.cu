@@ -577,6 +577,9 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
         }
     };
 
+    pdl_trigger();
+    pdl_wait();   // everything above touched only this kernel's own resources and the weight blob
+
     const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
     const int64_t ntiles = io.nseg * tiles_per_seg;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -878,6 +881,9 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
     unsigned done_phase = 0;
     bool w_ready = false;
 
+    pdl_trigger();
+    pdl_wait();   // everything above (TMEM, barriers, the weight blob on its way) is independent of the kernel before
+
     const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
     const int64_t ntiles = io.nseg * tiles_per_seg;
     for (int64_t tile = (int64_t)blockIdx.x * GROUPS + g; tile < ntiles; tile += (int64_t)gridDim.x * GROUPS) {
@@ -1120,8 +1126,13 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
             const unsigned grid = (unsigned)(want < 148 ? want : 148);
             TcIo io2 = io;
             io2.dbg = g_tc_dbg;
-            rkern<<<grid, kResThreads, rsmem, stream>>>(ch, static_cast<const unsigned char*>(blob), io2);
-            return finish_launch(what);
+            e = launch_pdl(rkern, dim3(grid), dim3(kResThreads), rsmem, stream, ch, static_cast<const unsigned char*>(blob), io2);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+                return (int)e;
+            }
+            return PN_OK;
         };
         return wpg == 8 ? launch_res(mlp_tc_res_kernel<IN, 8>, 2) : launch_res(mlp_tc_res_kernel<IN, 4>, 4);
     }
@@ -1167,8 +1178,13 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     const dim3 grid((unsigned)(ntiles < cap ? ntiles : cap), pass_w != kTcNPass ? ny : 1u);
     TcIo io2 = io;
     io2.dbg = g_tc_dbg;
-    kern<<<grid, kTcThreads, smem, stream>>>(chs, static_cast<const unsigned char*>(blob), io2);
-    return finish_launch(what);
+    e = launch_pdl(kern, grid, dim3(kTcThreads), smem, stream, chs, static_cast<const unsigned char*>(blob), io2);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return PN_OK;
 }
 
 }  // namespace pn

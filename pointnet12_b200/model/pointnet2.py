@@ -200,74 +200,94 @@ class PointNet2SemSeg(_Net):
         fp = [self.fp1, self.fp2, self.fp3, self.fp4]              # fp[i] upsamples level i+1 -> level i
         if fps_starts is None:
             fps_starts = draw_fps_starts(B, [N] + [m.npoint for m in sa[:-1]], points.device)
-        main = torch.cuda.current_stream(points.device)
-        side_a, side_b = self._side_streams(points.device)
-
-        # the level-1 ball-query buckets depend on xyz only: built on a side stream beside the level-1 sampling
+        # Streams: the caller's stream only brackets the forward.  `main` (high priority) carries the critical path
+        # FPS1 -> ball query 1 -> SA chains -> FP chains; `geo` (high priority) the sampling / grouping of levels 2-4, which
+        # the SA chains wait for; the 3-NN searches are only needed by the FP chains at the end, so they run at default
+        # (= lower) priority on two more streams and fill whatever the critical path leaves idle instead of competing
+        # with it: the big one (24000 x 1024 per cloud, for fp1) on its own stream, released after sa2.
+        user = torch.cuda.current_stream(points.device)
+        main, geo, nn_small, nn_big = self._side_streams(points.device)
         begin = torch.cuda.Event()
-        begin.record(main)
+        begin.record(user)
+        main.wait_event(begin)
+
+        # the level-1 ball-query buckets depend on xyz only: built beside the level-1 sampling
         grid1 = None
         if N >= ops.GRID_MIN_POINTS:
-            with torch.cuda.stream(side_a):
-                side_a.wait_event(begin)
+            with torch.cuda.stream(geo):
+                geo.wait_event(begin)
                 grid1 = ops.ball_grid(x0, sa[0].radius)
                 grid_ready = torch.cuda.Event()
-                grid_ready.record(side_a)
+                grid_ready.record(geo)
 
-        # level-1 sampling (the long serial kernel) on the main stream
-        x1 = ops.index_points(x0, farthest_point_sample(x0, sa[0].npoint, fps_starts[0]))
-        fork = torch.cuda.Event()
-        fork.record(main)
-        xs, balls, nns, ready = [x0, x1], [None] * 4, [None] * 4, [None] * 4
-        with torch.cuda.stream(side_b):                            # fp1's 3-NN: 24000 x 1024 per cloud
-            side_b.wait_event(fork)
-            nns[0] = fp[0].geometry(x0, x1)
-            done_b = torch.cuda.Event()
-            done_b.record(side_b)
-        with torch.cuda.stream(side_a):                            # sampling / grouping / 3-NN of levels 2..4
-            side_a.wait_event(fork)
+        with torch.cuda.stream(main):
+            # level-1 sampling (the long serial kernel)
+            x1 = ops.index_points(x0, farthest_point_sample(x0, sa[0].npoint, fps_starts[0]))
+            fork = torch.cuda.Event()
+            fork.record(main)
+        xs, balls, nns, ready, have_x = [x0, x1], [None] * 4, [None] * 4, [None] * 4, [None] * 4
+        with torch.cuda.stream(geo):                               # sampling / grouping of levels 2..4, back to back
+            geo.wait_event(fork)
             for i in (1, 2, 3):
                 nx, balls[i] = sa[i].geometry(xs[i], fps_starts[i])
                 xs.append(nx)
                 ready[i] = torch.cuda.Event()
-                ready[i].record(side_a)
-                nns[i] = fp[i].geometry(xs[i], nx)
-            done_a = torch.cuda.Event()
-            done_a.record(side_a)
+                ready[i].record(geo)
+        with torch.cuda.stream(nn_small):                          # 3-NN of levels 2..4 (inputs: the level centroids)
+            for i in (3, 2, 1):                                    # fp4 is the first to need its neighbours
+                nn_small.wait_event(ready[i])
+                nns[i] = fp[i].geometry(xs[i], xs[i + 1])
+            done_small = torch.cuda.Event()
+            done_small.record(nn_small)
 
-        # feature path on the main stream
-        if grid1 is not None:
-            main.wait_event(grid_ready)
-        balls[0] = ops.ball_query(sa[0].radius, sa[0].nsample, x0, x1, grid=grid1)
-        fs = [f0, sa[0].features(x0, f0, x1, balls[0])]
-        for i in (1, 2, 3):
-            main.wait_event(ready[i])
-            fs.append(sa[i].features(xs[i], fs[i], xs[i + 1], balls[i]))
-        main.wait_event(done_a)
-        up = fs[4]
-        for i in (3, 2, 1):
-            up = fp[i].features(fs[i], up, *nns[i])
-        main.wait_event(done_b)
-        # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs
-        head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
-        if host_out is None or ops.mlp_mode() != "bf16x3":
-            logp = fp[0].features(None, up, *nns[0], head=head, order=grid1)
-            if host_out is not None:
-                host_out.copy_(logp, non_blocking=True)
-            return logp
-        logp = torch.empty((B, N, self.conv2.out_channels), dtype=torch.float32, device=points.device)
-        copier = self._copy_stream(points.device)
-        half = (B + 1) // 2
-        for b0, b1 in ((0, half), (half, B)):
-            if b0 == b1:
-                continue
-            fp[0].features(None, up, *nns[0], head=head, order=grid1, out=logp, clouds=(b0, b1))
-            part = torch.cuda.Event()
-            part.record(main)
-            with torch.cuda.stream(copier):
-                copier.wait_event(part)
-                host_out[b0:b1].copy_(logp[b0:b1], non_blocking=True)
-        main.wait_stream(copier)
+        with torch.cuda.stream(main):
+            # feature path
+            if grid1 is not None:
+                main.wait_event(grid_ready)
+            balls[0] = ops.ball_query(sa[0].radius, sa[0].nsample, x0, x1, grid=grid1)
+            fs = [f0, sa[0].features(x0, f0, x1, balls[0])]
+            for i in (1, 2, 3):
+                main.wait_event(ready[i])
+                fs.append(sa[i].features(xs[i], fs[i], xs[i + 1], balls[i]))
+                if i == 1:
+                    # fp1's 3-NN search (24000 x 1024 per cloud) fills the GPU with long-lived CTAs, which stream
+                    # priorities cannot displace: it is released only now, when the wide kernels of the critical path
+                    # (ball query 1, sa1, sa2) are through and the small levels leave most SMs idle
+                    wide_done = torch.cuda.Event()
+                    wide_done.record(main)
+                    with torch.cuda.stream(nn_big):
+                        nn_big.wait_event(wide_done)
+                        nns[0] = fp[0].geometry(x0, x1)
+                        done_big = torch.cuda.Event()
+                        done_big.record(nn_big)
+            main.wait_event(done_small)
+            up = fs[4]
+            for i in (3, 2, 1):
+                up = fp[i].features(fs[i], up, *nns[i])
+            main.wait_event(done_big)
+            # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs
+            head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
+            if host_out is None or ops.mlp_mode() != "bf16x3":
+                logp = fp[0].features(None, up, *nns[0], head=head, order=grid1)
+                if host_out is not None:
+                    host_out.copy_(logp, non_blocking=True)
+            else:
+                logp = torch.empty((B, N, self.conv2.out_channels), dtype=torch.float32, device=points.device)
+                copier = self._copy_stream(points.device)
+                half = (B + 1) // 2
+                for b0, b1 in ((0, half), (half, B)):
+                    if b0 == b1:
+                        continue
+                    fp[0].features(None, up, *nns[0], head=head, order=grid1, out=logp, clouds=(b0, b1))
+                    part = torch.cuda.Event()
+                    part.record(main)
+                    with torch.cuda.stream(copier):
+                        copier.wait_event(part)
+                        host_out[b0:b1].copy_(logp[b0:b1], non_blocking=True)
+                main.wait_stream(copier)
+        user.wait_stream(main)
+        if not torch.cuda.is_current_stream_capturing():
+            logp.record_stream(user)       # allocated on `main`, handed to the caller's stream
         return logp
 
     def _copy_stream(self, device):
@@ -281,5 +301,8 @@ class PointNet2SemSeg(_Net):
         key = torch.device(device).index
         streams = self.__dict__.setdefault("_streams", {})
         if key not in streams:
-            streams[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+            rng = torch.cuda.Stream.priority_range()             # lower number = higher priority; 0 = default = lowest
+            lo, hi = max(rng), min(rng)
+            streams[key] = (torch.cuda.Stream(device, priority=hi), torch.cuda.Stream(device, priority=hi),
+                            torch.cuda.Stream(device, priority=lo), torch.cuda.Stream(device, priority=lo))
         return streams[key]

@@ -76,6 +76,11 @@ def device_check() -> Tuple[int, int, int]:
     return sm.value, ma.value, mi.value
 
 
+def set_pdl(enabled: bool = True) -> None:
+    """Programmatic dependent launch of the critical-path kernels (pn_set_pdl)."""
+    nv.call("pn_set_pdl", int(bool(enabled)))
+
+
 def fps_set_config(cluster_size: int = 0, threads: int = 0, exchange: int = 0) -> None:
     """Tuning hook: cluster size, threads per CTA, exchange (1 = barrier.cluster, 2 = st.async); 0 = automatic."""
     nv.call("pn_fps_set_config", cluster_size, threads, exchange)
