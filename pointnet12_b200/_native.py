@@ -47,6 +47,8 @@ _SIGNATURES = {
     "pn_linear_f32": [vp, i64, i64, vp, i64, vp, i64, i32, i32, i64, i32, i32, vp, i64, i64, vp],
     "pn_group_max_f32": [vp, i64, i64, i32, i32, vp, i64, vp],
     "pn_three_nn_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp, vp],
+    "pn_three_nn_blocks_build_f32": [vp, i64, i64, i64, i32, i32, vp, C.c_size_t, vp],
+    "pn_three_nn_blocks_f32": [vp, i64, i64, i64, vp, i64, i64, vp, C.c_size_t, i32, i32, i32, vp, vp, vp],
     "pn_three_interpolate_f32": [vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, i32, vp, i64, i64,
                                  vp],
     "pn_log_softmax_f32": [vp, i64, i64, i32, vp, i64, vp],
@@ -91,6 +93,8 @@ def lib():
         handle.pn_mlp_blob_bytes.restype = C.c_size_t
         handle.pn_ball_grid_bytes.argtypes = [i32, i32]
         handle.pn_ball_grid_bytes.restype = C.c_size_t
+        handle.pn_three_nn_blocks_bytes.argtypes = [i32, i32]
+        handle.pn_three_nn_blocks_bytes.restype = C.c_size_t
         _lib = handle
     return _lib
 

@@ -257,7 +257,9 @@ class PointNet2SemSeg(_Net):
                     wide_done.record(main)
                     with torch.cuda.stream(nn_big):
                         nn_big.wait_event(wide_done)
-                        nns[0] = fp[0].geometry(x0, x1)
+                        if grid1 is not None:
+                            nn_big.wait_event(grid_ready)
+                        nns[0] = fp[0].geometry(x0, x1, order=grid1)
                         done_big = torch.cuda.Event()
                         done_big.record(nn_big)
             main.wait_event(done_small)

@@ -284,13 +284,36 @@ def group_max(x: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> to
     return out
 
 
-def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """3 nearest sources and normalised inverse-distance weights (pointnet_util.py:295-300)."""
+NN_BLOCKS_MIN_EVALS = 1 << 22   # N * S per cloud from which the block search pays for its build
+NN_BLOCKS_MAX_S = 8192
+
+
+def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor, order: Optional[BallGrid] = None,
+             method: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
+    """3 nearest sources and normalised inverse-distance weights (pointnet_util.py:295-300).
+    method: "scan" (pn_three_nn_f32, all N x S distances), "blocks" (pn_three_nn_blocks_f32: exact branch-and-bound
+    over Morton blocks of the coarse cloud) or "auto" (blocks for large N x S when `order`, the bucket order of the
+    fine cloud, is available).  Both return identical results."""
     xyz1, xyz2 = _cloud(xyz1, "xyz1", 3), _cloud(xyz2, "xyz2", 3)
     B, N, _ = xyz1.shape
     S = xyz2.shape[1]
     idx = torch.empty((B, N, 3), dtype=torch.int64, device=xyz1.device)
     w = torch.empty((B, N, 3), dtype=torch.float32, device=xyz1.device)
+    if method == "auto":
+        method = "blocks" if (order is not None and 32 <= S <= NN_BLOCKS_MAX_S and N * S >= NN_BLOCKS_MIN_EVALS) else "scan"
+    if method == "blocks":
+        if order is not None and (order.B, order.N) != (B, N):
+            raise ValueError("order grid was built for another cloud shape")
+        optr, oes, obs = order.order() if order is not None else (None, 0, 0)
+        nbytes = int(nv.lib().pn_three_nn_blocks_bytes(B, S))
+        blocks = torch.empty((nbytes,), dtype=torch.uint8, device=xyz1.device)
+        with _on_device(xyz1):
+            nv.call("pn_three_nn_blocks_build_f32", xyz2.data_ptr(), *xyz2.stride(), B, S, blocks.data_ptr(), nbytes, _stream())
+            nv.call("pn_three_nn_blocks_f32", xyz1.data_ptr(), *xyz1.stride(), optr, oes, obs, blocks.data_ptr(), nbytes, B, N,
+                    S, idx.data_ptr(), w.data_ptr(), _stream())
+        return idx, w
+    if method != "scan":
+        raise ValueError(f"unknown 3-NN method {method!r}")
     with _on_device(xyz1):
         nv.call("pn_three_nn_f32", xyz1.data_ptr(), *xyz1.stride(), xyz2.data_ptr(), *xyz2.stride(), B, N, S,
                 idx.data_ptr(), w.data_ptr(), _stream())

@@ -344,6 +344,29 @@ def test_three_nn_interpolate_vs_oracle(dev, N, S, B):
     assert rel_err(got, want[:, :, 7:]) < 1e-6
 
 
+@pytest.mark.parametrize("N,S,B,ordered", [(24000, 1024, 2, True), (24000, 1024, 1, False), (5000, 1500, 2, True),
+                                           (4096, 37, 3, True), (9000, 8192, 1, True), (777, 64, 2, False)])
+def test_three_nn_blocks_vs_oracle(dev, N, S, B, ordered):
+    """The pruned block search returns what the all-pairs scan returns (and the oracle, outside its flagged ties):
+    with the fine points walked in bucket order (tight warps, strong pruning) and in raw order (loose warps)."""
+    from pointnet12_b200 import ops
+
+    pts = syn.kitti_batch(B, N, config=6)
+    x1 = pts.transpose(0, 2, 1)[:, :, :3]
+    sel = orc.farthest_point_sample(x1, S, np.zeros(B, dtype=np.int64))
+    x2 = np.ascontiguousarray(np.stack([x1[b][sel[b]] for b in range(B)]))
+    widx, ww, _, tie = orc.three_nn(x1, x2)
+    fine = views(cuda(pts, dev))[0]
+    coarse = cuda(x2, dev)
+    grid = ops.ball_grid(fine, 0.1) if ordered else None
+    gi, gw = ops.three_nn(fine, coarse, order=grid, method="blocks")
+    si, sw = ops.three_nn(fine, coarse, method="scan")
+    assert torch.equal(gi, si) and torch.equal(gw, sw)
+    keep = ~tie
+    assert np.array_equal(gi.cpu().numpy()[keep], widx[keep])
+    assert np.abs(gw.cpu().numpy()[keep] - ww[keep]).max() < 1e-6
+
+
 def test_cpu_tensor_raises(dev):
     from pointnet12_b200.model import pointnet_util as U
 
