@@ -146,13 +146,15 @@ int pn_three_nn_f32(const float* xyz1, int64_t aB, int64_t aN, int64_t aC, const
  * pn_three_nn_blocks_f32 one warp serves 32 fine points, visits the blocks nearest-first and stops when the nearest
  * unvisited block is farther than the warp's worst third-neighbour distance.  order (may be NULL): processing order
  * of the fine points as in pn_fp_mlp_bf16x3 -- pass the bucket order of the fine cloud (pn_ball_grid_order) so that
- * the 32 points of a warp are spatial neighbours and the pruning bites. */
+ * the 32 points of a warp are spatial neighbours and the pruning bites.  background = 1 caps the grid at ~3 small
+ * CTAs per SM (persistent over the fine points) so that the search can run beside the kernels of another stream
+ * without taking their registers / shared memory. */
 size_t pn_three_nn_blocks_bytes(int B, int S);
 int pn_three_nn_blocks_build_f32(const float* xyz2, int64_t bB, int64_t bN, int64_t bC, int B, int S, void* blocks,
                                  size_t blocks_bytes, pn_stream_t stream);
 int pn_three_nn_blocks_f32(const float* xyz1, int64_t aB, int64_t aN, int64_t aC, const int32_t* order,
                            int64_t order_es, int64_t order_bs, const void* blocks, size_t blocks_bytes, int B, int N,
-                           int S, int64_t* idx, float* weight, pn_stream_t stream);
+                           int S, int background, int64_t* idx, float* weight, pn_stream_t stream);
 
 /* Weighted gather of model/pointnet_util.py:301 fused with the concat of :303-307:
  * out[b,n,0:D1] = points1[b,n,:] (skipped when points1 == NULL), out[b,n,D1:D1+D2] =

@@ -48,7 +48,7 @@ _SIGNATURES = {
     "pn_group_max_f32": [vp, i64, i64, i32, i32, vp, i64, vp],
     "pn_three_nn_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp, vp],
     "pn_three_nn_blocks_build_f32": [vp, i64, i64, i64, i32, i32, vp, C.c_size_t, vp],
-    "pn_three_nn_blocks_f32": [vp, i64, i64, i64, vp, i64, i64, vp, C.c_size_t, i32, i32, i32, vp, vp, vp],
+    "pn_three_nn_blocks_f32": [vp, i64, i64, i64, vp, i64, i64, vp, C.c_size_t, i32, i32, i32, i32, vp, vp, vp],
     "pn_three_interpolate_f32": [vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, i32, vp, i64, i64,
                                  vp],
     "pn_log_softmax_f32": [vp, i64, i64, i32, vp, i64, vp],

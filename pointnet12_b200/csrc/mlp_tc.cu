@@ -1136,8 +1136,7 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
         };
         return wpg == 8 ? launch_res(mlp_tc_res_kernel<IN, 8>, 2) : launch_res(mlp_tc_res_kernel<IN, 4>, 4);
     }
-    // ring depth: as deep as shared memory allows (a CTA alone on its SM when the grid is small: up to ~200 KB;
-    // otherwise ~110 KB so that two CTAs share an SM), at least 2, at most kTcMaxStages
+    // ring depth: what fits in ~110 KB (two CTAs can share an SM), at least 2, at most kTcMaxStages
     TcChain chs = ch;
     chs.pass_w = pass_w;
     if (pass_w != kTcNPass) {   // re-plan the per-CTA resources for the narrower pass
@@ -1152,7 +1151,9 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     }
     {
         const int by_tmem = 512 / chs.tmem_cols;
-        const size_t budget = (ntiles_all <= 148 || by_tmem < 2) ? 200 * 1024 : 110 * 1024;
+        (void)by_tmem;
+        const size_t budget = 110 * 1024;   // deeper rings bought nothing (the MMAs, not the copies, pace a chunk); a modest
+                                            // footprint lets background kernels of other streams share the SM
         const size_t fixed = tc_smem_bytes(chs, 0);
         int ns = (int)((budget - fixed) / (size_t)chs.stage_bytes);
         ns = ns < 2 ? 2 : (ns > kTcMaxStages ? kTcMaxStages : ns);

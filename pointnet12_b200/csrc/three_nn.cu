@@ -193,8 +193,9 @@ three_nn_blocks_kernel(const float* __restrict__ xyz1, int64_t aB, int64_t aN, i
     const float m2c = reinterpret_cast<const float*>(ws)[0];
     __syncthreads();
 
-    {
-    const int r = (blockIdx.x * kNbWarps + warp) * 32 + lane;   // position in the processing order
+    // (a capped grid -- background mode -- walks several groups of kNbWarps * 32 fine points per CTA)
+    for (int r0 = blockIdx.x * kNbWarps * 32; r0 < N; r0 += gridDim.x * kNbWarps * 32) {
+    const int r = r0 + warp * 32 + lane;   // position in the processing order
     const bool ok = r < N;
     int n = ok ? r : 0;
     if (ok && order) {
@@ -292,7 +293,7 @@ three_nn_blocks_kernel(const float* __restrict__ xyz1, int64_t aB, int64_t aN, i
             }
         }
     }
-    if (!ok) return;
+    if (!ok) continue;
     // dists[dists < 1e-10] = 1e-10 ; weight = 1/d ; weight /= sum(weight)   (pointnet_util.py:298-300)
     const float c0 = d0 < 1e-10f ? 1e-10f : d0, c1 = d1 < 1e-10f ? 1e-10f : d1, c2 = d2 < 1e-10f ? 1e-10f : d2;
     const float w0 = __fdiv_rn(1.0f, c0), w1 = __fdiv_rn(1.0f, c1), w2 = __fdiv_rn(1.0f, c2);
@@ -340,7 +341,7 @@ PN_EXPORT int pn_three_nn_blocks_build_f32(const float* xyz2, int64_t bB, int64_
 
 PN_EXPORT int pn_three_nn_blocks_f32(const float* xyz1, int64_t aB, int64_t aN, int64_t aC, const int32_t* order,
                                      int64_t order_es, int64_t order_bs, const void* blocks, size_t blocks_bytes, int B, int N,
-                                     int S, int64_t* idx, float* weight, pn_stream_t stream) {
+                                     int S, int background, int64_t* idx, float* weight, pn_stream_t stream) {
     using namespace pn;
     PN_REQUIRE(xyz1 && blocks && idx && weight, PN_ERR_BAD_ARG, "pn_three_nn_blocks_f32: null pointer");
     PN_REQUIRE(B > 0 && N > 0 && S >= 3, PN_ERR_BAD_ARG, "pn_three_nn_blocks_f32: need B, N > 0 and S >= 3 (got %d, %d, %d)", B, N, S);
@@ -356,7 +357,14 @@ PN_EXPORT int pn_three_nn_blocks_f32(const float* xyz1, int64_t aB, int64_t aN, 
         set_error("pn_three_nn_blocks_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    dim3 grid((unsigned)ceil_div(N, kNbWarps * 32), (unsigned)B);
+    // background: at most ~3 CTAs (12 warps, 65 KB of shared memory) per SM, so that kernels of a concurrent stream
+    // still find room on every SM; the search then takes longer but stays out of their way
+    int64_t gx = ceil_div(N, kNbWarps * 32);
+    if (background) {
+        const int64_t cap = ceil_div(148 * 3, B);
+        gx = gx < cap ? gx : cap;
+    }
+    dim3 grid((unsigned)gx, (unsigned)B);
     kern<<<grid, kNbWarps * 32, smem, (cudaStream_t)stream>>>(xyz1, aB, aN, aC, order, order_es, order_bs,
                                                              static_cast<const unsigned char*>(blocks), nb_cloud_bytes(S), N, S,
                                                              idx, weight);

@@ -259,7 +259,7 @@ class PointNet2SemSeg(_Net):
                         nn_big.wait_event(wide_done)
                         if grid1 is not None:
                             nn_big.wait_event(grid_ready)
-                        nns[0] = fp[0].geometry(x0, x1, order=grid1)
+                        nns[0] = fp[0].geometry(x0, x1, order=grid1, background=True)
                         done_big = torch.cuda.Event()
                         done_big.record(nn_big)
             main.wait_event(done_small)

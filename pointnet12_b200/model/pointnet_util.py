@@ -330,14 +330,14 @@ class PointNetFeaturePropagation(nn.Module):
             c = width
         self._folded = FoldedLayers()
 
-    def geometry(self, x1: torch.Tensor, x2: torch.Tensor, order=None):
+    def geometry(self, x1: torch.Tensor, x2: torch.Tensor, order=None, background: bool = False):
         """x1 [B,N,3] fine points, x2 [B,S,3] coarse points -> (idx [B,N,3], weight [B,N,3]).
         `order`: an ops.BallGrid of the fine cloud (bucket order) -> the pruned block search for large N x S."""
         B, N, _ = x1.shape
         if x2.shape[1] == 1:   # a single coarse point: broadcast it (reference :292-293)
             idx = torch.zeros((B, N, 3), dtype=torch.int64, device=x1.device)
             return idx, torch.tensor([1.0, 0.0, 0.0], device=x1.device).expand(B, N, 3).contiguous()
-        return ops.three_nn(x1, x2, order=order)
+        return ops.three_nn(x1, x2, order=order, background=background)
 
     def features(self, p1, p2, idx, w, head=None, order=None, out=None, clouds=None) -> torch.Tensor:
         """p1 [B,N,D1] or None, p2 [B,S,D2] point-major -> [B,N,D'] point-major.

@@ -289,11 +289,12 @@ NN_BLOCKS_MAX_S = 8192
 
 
 def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor, order: Optional[BallGrid] = None,
-             method: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
+             method: str = "auto", background: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """3 nearest sources and normalised inverse-distance weights (pointnet_util.py:295-300).
     method: "scan" (pn_three_nn_f32, all N x S distances), "blocks" (pn_three_nn_blocks_f32: exact branch-and-bound
     over Morton blocks of the coarse cloud) or "auto" (blocks for large N x S when `order`, the bucket order of the
-    fine cloud, is available).  Both return identical results."""
+    fine cloud, is available).  Both return identical results.  background: the block search runs on a capped grid
+    (~3 small CTAs per SM) so that it can share the GPU with the kernels of another stream."""
     xyz1, xyz2 = _cloud(xyz1, "xyz1", 3), _cloud(xyz2, "xyz2", 3)
     B, N, _ = xyz1.shape
     S = xyz2.shape[1]
@@ -310,7 +311,7 @@ def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor, order: Optional[BallGrid] =
         with _on_device(xyz1):
             nv.call("pn_three_nn_blocks_build_f32", xyz2.data_ptr(), *xyz2.stride(), B, S, blocks.data_ptr(), nbytes, _stream())
             nv.call("pn_three_nn_blocks_f32", xyz1.data_ptr(), *xyz1.stride(), optr, oes, obs, blocks.data_ptr(), nbytes, B, N,
-                    S, idx.data_ptr(), w.data_ptr(), _stream())
+                    S, int(bool(background)), idx.data_ptr(), w.data_ptr(), _stream())
         return idx, w
     if method != "scan":
         raise ValueError(f"unknown 3-NN method {method!r}")

@@ -362,6 +362,8 @@ def test_three_nn_blocks_vs_oracle(dev, N, S, B, ordered):
     gi, gw = ops.three_nn(fine, coarse, order=grid, method="blocks")
     si, sw = ops.three_nn(fine, coarse, method="scan")
     assert torch.equal(gi, si) and torch.equal(gw, sw)
+    bi, bw = ops.three_nn(fine, coarse, order=grid, method="blocks", background=True)   # capped, persistent grid
+    assert torch.equal(bi, si) and torch.equal(bw, sw)
     keep = ~tie
     assert np.array_equal(gi.cpu().numpy()[keep], widx[keep])
     assert np.abs(gw.cpu().numpy()[keep] - ww[keep]).max() < 1e-6
