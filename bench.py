@@ -112,6 +112,8 @@ def oracle_forward_timer(batch):
     from oracle import oracle as orc
     from pointnet12_b200 import synthetic as syn
 
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses all host cores explicitly
+    orc.set_num_threads(os.cpu_count() or 1)
     sd = orc.numpy_state_dict(torch.load(CKPT, map_location="cpu"))
     pts = syn.kitti_batch(batch, NPOINTS, config=2)
     torch.manual_seed(0)
