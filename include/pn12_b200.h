@@ -235,7 +235,7 @@ int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* poi
  * resident-weight kernel: weights loaded once per CTA, 2 or 4 warp groups per CTA each with its own row tile
  * and TMEM slice; larger chains stream their weights through a ring), 1 = always stream, 2 = resident or fail;
  * +4 = keep the row-per-thread producers (disables the coalesced quad producer of the FP levels);
- * +8 = no N-slicing of single-layer chains.
+ * +8 = no N-slicing of single-layer chains; +16 = 8-warp streaming CTAs only (no 16-warp CTAs on small grids).
  * Process-wide; meant for benchmarks and tests. */
 int pn_mlp_set_engine(int engine);
 /* Profiling hook: a device buffer of 4 * 64 * 32 int64 (or NULL to disable).  While set, CTA 0 of every resident-

@@ -470,8 +470,8 @@ PN_EXPORT int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, i
         if (N <= 3072) CL = 1;
         else if (N <= 6144) CL = 2;
         else if (N <= 12288) CL = 4;
-        else if (N <= 24576) CL = 8;
-        else CL = 16;
+        else if (N <= 65536) CL = 8;   // 8 x 256 threads x 32 points; clusters of 16 are placed one per GPC at best and were
+        else CL = 16;                  // measured slower wherever 8 CTAs can hold the cloud (N = 32768: 1.07 vs 0.56 ms)
     }
     const int chunk = (int)ceil_div(N, CL);
     // st.async exchange: clusters only, at most 64 slots (cluster size x warps) and 32 points per thread

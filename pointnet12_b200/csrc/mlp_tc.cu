@@ -524,8 +524,10 @@ __device__ __forceinline__ void fp_quad_producer(const TcIo& io, int64_t seg, in
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int IN>
-__global__ void __launch_bounds__(kTcThreads, 2)
+// THREADS = 256 (8 warps, two CTAs per SM) or 512 (16 warps, one CTA per SM: used when the grid has at most one CTA per
+// SM anyway -- twice the warps halve the latency-bound producer and epilogue phases of the small levels).
+template <int IN, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restrict__ blob, const __grid_constant__ TcIo io) {
     extern __shared__ __align__(128) unsigned char smem[];
     // layout: [stage 0 .. nstages-1][bias table][barriers: full[8] empty[8] done][tmem ptr]
@@ -553,13 +555,14 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     }
     {
         const float* gb = reinterpret_cast<const float*>(blob + ch.bias_off);
-        for (int i = tid; i < ch.bias_floats; i += kTcThreads) sbias[i] = gb[i];
+        for (int i = tid; i < ch.bias_floats; i += THREADS) sbias[i] = gb[i];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const unsigned tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-    const int wl = warp & 3, half = warp >> 2;                      // lane quarter / column half of this warp
+    constexpr int HALVES = THREADS / 128, CSTEP = 32 * HALVES;
+    const int wl = warp & 3, half = warp >> 2;                      // lane quarter / column slice (of HALVES) of this warp
     const unsigned tlane = tbase + ((unsigned)(wl * 32) << 16);      // this warp's 32 TMEM lanes
     const unsigned t_x = tlane;                                      // accumulator columns
     const unsigned t_ahi = tlane + ch.x_cols, t_alo = t_ahi + ch.a_lo_off;
@@ -610,10 +613,10 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                         bool quad = false;
                         if constexpr (IN == TC_IN_FP) quad = io.quad_fp != 0;
                         if (quad) {
-                            fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, kbase, kchunk, L.k_real, half, 2,
+                            fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, kbase, kchunk, L.k_real, half, HALVES,
                                              t_ahi, t_alo);
                         } else {
-                            for (int k0 = half * 32; k0 < kchunk; k0 += 64) {   // this thread's row
+                            for (int k0 = half * 32; k0 < kchunk; k0 += CSTEP) {   // this thread's row
                                 float v[32];
                                 row_load32<IN>(io, rc, kbase + k0, L.k_real, v);
                                 tc_store_split32(t_ahi + k0 / 2, t_alo + k0 / 2, v);
@@ -716,7 +719,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                 // ---- epilogue of pass p: accumulator columns [0, rows_p)
                 const float* bias = sbias + L.b_off + n0;
                 if (!last) {
-                    for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
+                    for (int c0 = half * 32; c0 < rows_p; c0 += CSTEP) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         float v[32];
@@ -731,7 +734,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     tc_fence_before();
                     __syncthreads();
                 } else if (io.out_mode == TC_OUT_ROWS) {
-                    for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
+                    for (int c0 = half * 32; c0 < rows_p; c0 += CSTEP) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         if (rc.valid) {
@@ -764,7 +767,7 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     const int64_t grp = rc.row / 32;   // warp-uniform when the warp has any valid row
                     const bool any_valid = __any_sync(0xffffffffu, rc.valid);
                     const int64_t g = __shfl_sync(0xffffffffu, grp, 0);
-                    for (int c0 = half * 32; c0 < rows_p; c0 += 64) {
+                    for (int c0 = half * 32; c0 < rows_p; c0 += CSTEP) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         float v[32];
@@ -1086,6 +1089,7 @@ static int g_tc_engine = 0;
 static long long* g_tc_dbg = nullptr;   // pn_mlp_set_debug
 static int g_tc_quad = 1;               // pn_mlp_set_engine(engine | 4) disables the coalesced quad producer
 static int g_tc_nslice = 1;             // pn_mlp_set_engine(engine | 8) disables N-slicing of single-layer chains
+static int g_tc_wide = 1;               // pn_mlp_set_engine(engine | 16) disables the 16-warp streaming CTAs
 
 // Resident kernel usable?  Returns warps per group (8 or 4), or 0.
 static int tc_resident_wpg(const TcChain& c) {
@@ -1161,7 +1165,8 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     }
     const size_t smem = tc_smem_bytes(chs, chs.nstages);
     PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "%s: chain needs %zu bytes of shared memory", what, smem);
-    auto kern = mlp_tc_kernel<IN>;
+    const bool wide = g_tc_wide && (int64_t)ntiles_all * (pass_w != kTcNPass ? (ch.L[0].n_pad + pass_w - 1) / pass_w : 1) <= 148;
+    auto kern = wide ? mlp_tc_kernel<IN, 512> : mlp_tc_kernel<IN, 256>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1179,7 +1184,7 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     const dim3 grid((unsigned)(ntiles < cap ? ntiles : cap), pass_w != kTcNPass ? ny : 1u);
     TcIo io2 = io;
     io2.dbg = g_tc_dbg;
-    e = launch_pdl(kern, grid, dim3(kTcThreads), smem, stream, chs, static_cast<const unsigned char*>(blob), io2);
+    e = launch_pdl(kern, grid, dim3(wide ? 512 : 256), smem, stream, chs, static_cast<const unsigned char*>(blob), io2);
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -1197,12 +1202,13 @@ PN_EXPORT int pn_mlp_set_debug(void* timeline) {
 }
 
 PN_EXPORT int pn_mlp_set_engine(int engine) {
-    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 16, PN_ERR_BAD_ARG,
+    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 32, PN_ERR_BAD_ARG,
                "pn_mlp_set_engine: 0 = automatic, 1 = streaming, 2 = resident; +4 = row-per-thread producers only; "
-               "+8 = no N-slicing");
+               "+8 = no N-slicing; +16 = 8-warp streaming CTAs only");
     pn::g_tc_engine = engine & 3;
     pn::g_tc_quad = (engine & 4) ? 0 : 1;
     pn::g_tc_nslice = (engine & 8) ? 0 : 1;
+    pn::g_tc_wide = (engine & 16) ? 0 : 1;
     return PN_OK;
 }
 

@@ -266,9 +266,12 @@ class PointNet2SemSeg(_Net):
             up = fs[4]
             for i in (3, 2, 1):
                 up = fp[i].features(fs[i], up, *nns[i])
-            main.wait_event(done_big)
-            # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs
+            # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs;
+            # its first layer runs on the 1024 coarse points and needs no neighbours: issued before the 3-NN wait
             head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
+            if ops.FOLD_FIRST_FP_LAYER:
+                fp[0].fold_first_layer(up, head)
+            main.wait_event(done_big)
             if host_out is None or ops.mlp_mode() != "bf16x3":
                 logp = fp[0].features(None, up, *nns[0], head=head, order=grid1)
                 if host_out is not None:

@@ -339,6 +339,27 @@ class PointNetFeaturePropagation(nn.Module):
             return idx, torch.tensor([1.0, 0.0, 0.0], device=x1.device).expand(B, N, 3).contiguous()
         return ops.three_nn(x1, x2, order=order, background=background)
 
+    def fold_first_layer(self, p2, head=None):
+        """(remaining chain, z): the level's first layer applied to the coarse features p2 [B,S,D2] (no activation).
+        Needs no neighbour search, so a network can issue it before it waits for the 3-NN result; the value is cached
+        until `features` has consumed it.  None when the tensor-core path is off or a part does not fit."""
+        cached = getattr(self, "_z_cache", None)
+        if cached is not None and cached[0] is p2:
+            return cached[1], cached[2]
+        convs, bns, relus = list(self.mlp_convs), list(self.mlp_bns), [True] * len(self.mlp_convs)
+        folded = self._folded
+        if head is not None:
+            folded, hconvs, hbns, hrelus, _ = head
+            convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
+        split = folded.chain_folded_first(convs, bns, relus)
+        if split is None:
+            return None
+        first, rest = split
+        B, S, D2 = p2.shape
+        z = ops.mlp_rows_tc(first, p2.reshape(B * S, D2)).view(B, S, -1)
+        self._z_cache = (p2, rest, z)
+        return rest, z
+
     def features(self, p1, p2, idx, w, head=None, order=None, out=None, clouds=None) -> torch.Tensor:
         """p1 [B,N,D1] or None, p2 [B,S,D2] point-major -> [B,N,D'] point-major.
         `head`: (FoldedLayers, convs, bns, relus, out_mode) appended by a network: the segmentation head runs
@@ -353,17 +374,14 @@ class PointNetFeaturePropagation(nn.Module):
             folded, hconvs, hbns, hrelus, out_mode = head
             convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
         if p1 is None and ops.FOLD_FIRST_FP_LAYER and N > p2.shape[1]:
-            split = folded.chain_folded_first(convs, bns, relus)
-            if split is not None:
+            folded_first = self.fold_first_layer(p2, head)
+            if folded_first is not None:
                 # first layer at the coarse level (S rows instead of N), then one kernel: relu(weighted 3-row gather)
                 # -> the remaining layers (-> head -> log_softmax)
-                first, rest = split
-                S, D2 = p2.shape[1], p2.shape[2]
-                z = getattr(self, "_z_cache", None)
-                if clouds is None or z is None or z[0] is not p2:
-                    z = (p2, ops.mlp_rows_tc(first, p2.reshape(B * S, D2)).view(B, S, -1))
-                    self._z_cache = z if clouds is not None else None   # reused by the next batch slice of this call
-                return ops.fp_mlp_tc(rest, None, z[1], idx, w, out_mode, relu_in=True, order=order, out=out, clouds=clouds)
+                rest, z = folded_first
+                if clouds is None or clouds[1] == B:
+                    self._z_cache = None                               # last use in this forward
+                return ops.fp_mlp_tc(rest, None, z, idx, w, out_mode, relu_in=True, order=order, out=out, clouds=clouds)
         if (head is None and out is None and clouds is None and len(convs) > 1
                 and B * ((N + 127) // 128) < ops.LAYERWISE_MAX_TILES):
             per_layer = folded.layer_chains(convs, bns, relus)

@@ -375,7 +375,7 @@ def set_mlp_engine(engine: str = "auto") -> None:
     streaming ring otherwise), 'stream' or 'resident'; '*-rowwise' keeps the row-per-thread producers (no coalesced
     quad producer) for A/B comparisons."""
     nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2, "auto-rowwise": 4, "resident-rowwise": 6,
-                                  "auto-noslice": 8, "stream-noslice": 9}[engine])
+                                  "auto-noslice": 8, "stream-noslice": 9, "auto-narrow": 16, "stream-narrow": 17}[engine])
 
 
 FOLD_FIRST_FP_LAYER = os.environ.get("PN12_FP_FOLD", "1") != "0"

@@ -32,10 +32,10 @@ def mlp_mode(request):
     ops.set_mlp_mode(old)
 
 
-@pytest.fixture(params=["auto", "stream"])
+@pytest.fixture(params=["auto", "stream", "stream-narrow"])
 def mlp_engine(request):
-    """Run a chain test on both tensor-core kernels: resident weights + warp groups (where the chain fits) and the
-    streaming ring."""
+    """Run a chain test on the tensor-core kernels: resident weights + warp groups (where the chain fits), the
+    streaming ring with 16-warp CTAs (small grids) and with 8-warp CTAs."""
     from pointnet12_b200 import ops
 
     ops.set_mlp_engine(request.param)
