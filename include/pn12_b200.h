@@ -90,7 +90,8 @@ int pn_ball_query_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, cons
  * pn_ball_query_grid_f32: one warp per centroid; when the 27 neighbouring cells hold at most `threshold`
  * points they are all tested and the hits are ordered through a shared-memory bitmap over original indices,
  * otherwise the ball is dense and the ordered scan over the raw cloud stops after a short prefix.
- * threshold: 0 = automatic (~sqrt(213 N)), negative = always scan, INT_MAX = always use the cells.
+ * threshold: 0 = automatic (~sqrt(64 N)), negative = always scan, INT_MAX = always use the cells.
+ * done (may be NULL): [B, S] flags of rows that are already complete (see pn_ball_query_stream_f32) and are skipped.
  * Limits: N <= 1048576. */
 size_t pn_ball_grid_bytes(int B, int N);
 /* The bucket-sorted point order stored in a grid built by pn_ball_grid_build_f32, as (pointer, element stride, batch
@@ -100,8 +101,25 @@ int pn_ball_grid_build_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC,
                            void* grid, size_t grid_bytes, pn_stream_t stream);
 int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const float* new_xyz, int64_t qB,
                            int64_t qN, int64_t qC, int B, int N, int S, float radius2, int nsample,
-                           const void* grid, size_t grid_bytes, int threshold, int64_t* out_idx,
+                           const void* grid, size_t grid_bytes, int threshold, const int32_t* done, int64_t* out_idx,
                            pn_stream_t stream);
+
+/* query_ball_point fed by a RUNNING farthest-point-sampling kernel.  pn_fps_progress_f32 is pn_fps_f32 that also
+ * publishes every centroid the moment it is chosen (progress [B, npoint], zeroed by the caller before the launch:
+ * one 8-byte word per centroid, index << 32 | 1).  pn_ball_query_stream_f32, launched on ANOTHER stream once the grid
+ * is built, runs `ctas` persistent CTAs (a multiple of B; the caller sizes it to the SMs sampling leaves idle, see
+ * pn_fps_launch_info, and passes min_smem_bytes so large that a CTA cannot share an SM with a sampling CTA), polls
+ * the feed and writes out_idx rows plus done[b, s] = 1 as centroids appear.  A CTA whose wait exceeds 3 ms gives up.
+ * The caller then runs pn_ball_query_grid_f32 with the same `done` array after sampling: it computes whatever is
+ * not done -- normally nothing -- so the result never depends on the two kernels having run side by side.
+ * Limits: N <= 32768. */
+int pn_fps_progress_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+                        const int64_t* start_idx, int64_t* out_idx, uint64_t* progress, pn_stream_t stream);
+/* Launch shape pn_fps_f32 would use for (B, N, npoint): CTAs in the grid and dynamic shared memory per CTA. */
+int pn_fps_launch_info(int B, int N, int npoint, int* ctas, size_t* smem_bytes);
+int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const uint64_t* progress, int B, int N,
+                             int S, float radius2, int nsample, const void* grid, size_t grid_bytes, int ctas,
+                             size_t min_smem_bytes, int32_t* done, int64_t* out_idx, pn_stream_t stream);
 
 /* index_points (model/pointnet_util.py:43-60): out[b,m,:] = points[b, idx[b,m], :].
  * points [B,N,C] via strides, idx [B,M], out contiguous [B,M,C]. */
@@ -238,6 +256,9 @@ int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* poi
  * +8 = no N-slicing of single-layer chains; +16 = 8-warp streaming CTAs only (no 16-warp CTAs on small grids).
  * Process-wide; meant for benchmarks and tests. */
 int pn_mlp_set_engine(int engine);
+/* SMs the resident-weight launches (one persistent CTA per SM) leave to kernels running on other streams at the same
+ * time (e.g. the next level's sampling, one CTA per cloud).  Read at launch; 0 by default.  Process-wide. */
+int pn_mlp_set_reserved_sms(int sms);
 /* Profiling hook: a device buffer of 4 * 64 * 32 int64 (or NULL to disable).  While set, CTA 0 of every resident-
  * weight chain launch records clock64() per phase: [group][tile round % 64][tile start, producer done, then per
  * layer: MMA issue start, MMAs issued, accumulator ready, epilogue done; last: tile done]. */

@@ -39,8 +39,11 @@ _SIGNATURES = {
     "pn_square_distance_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp],
     "pn_ball_query_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, vp],
     "pn_ball_grid_build_f32": [vp, i64, i64, i64, i32, i32, f32, vp, C.c_size_t, vp],
-    "pn_ball_query_grid_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, vp,
+    "pn_ball_query_grid_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, vp, vp,
                                vp],
+    "pn_fps_progress_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp, vp],
+    "pn_fps_launch_info": [i32, i32, i32, C.POINTER(i32), C.POINTER(C.c_size_t)],
+    "pn_ball_query_stream_f32": [vp, i64, i64, i64, vp, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, C.c_size_t, vp, vp, vp],
     "pn_index_points_f32": [vp, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp],
     "pn_group_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32, i32, i32, vp,
                      i64, vp],
@@ -63,6 +66,7 @@ _SIGNATURES = {
     "pn_ball_grid_order": [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)],
     "pn_mlp_set_engine": [i32],
     "pn_mlp_set_debug": [vp],
+    "pn_mlp_set_reserved_sms": [i32],
 }
 
 

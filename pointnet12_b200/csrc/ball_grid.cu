@@ -187,25 +187,15 @@ constexpr int kGqTile = 2048;   // points per staged tile in the dense phase (32
 //                       first K set bits.  More -> the centroid is left pending.
 //   phase 2 (per CTA) : the pending (dense) centroids scan the raw cloud in index order through tiles staged in
 //                       shared memory by the whole CTA (the bitmap space is reused); early exit per warp and per CTA.
+// The work of one CTA on WARPS centroids of cloud b (warp w: centroid (ax, ay, az), result row o; !valid warps only help).
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC,
-                       const float* __restrict__ qxyz, int64_t qB, int64_t qN, int64_t qC, int N, int S,
-                       float radius2, int K, const unsigned char* __restrict__ ws_all, size_t ws_stride, int threshold,
-                       int bm_words, int64_t* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char gq_smem[];
-    pdl_trigger();
-    pdl_wait();   // the centroids come from the kernel before
+__device__ __forceinline__ void gq_block(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC, int N, float radius2,
+                                         int K, const unsigned char* __restrict__ ws, int threshold, int bm_words,
+                                         unsigned char* gq_smem, int b, bool valid, float ax, float ay, float az,
+                                         int64_t* __restrict__ o) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y;
-    const int s = blockIdx.x * WARPS + warp;
-    const bool valid = s < S;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned char* ws = ws_all + (size_t)b * ws_stride;
-    const float* a = qxyz + (int64_t)b * qB + (int64_t)(valid ? s : 0) * qN;
-    const float ax = a[0], ay = a[qC], az = a[2 * qC];
     const float sa = sqnorm3(ax, ay, az);
-    int64_t* __restrict__ o = out + ((int64_t)b * S + (valid ? s : 0)) * K;
     int cnt = valid ? 0 : K;          // out-of-range warps are born finished
     int64_t first = N;
     bool pending = false;
@@ -333,6 +323,88 @@ ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, in
         for (int k = min(cnt, K) + lane; k < K; k += 32) o[k] = first;   // pad with the first hit (or N)
 }
 
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC,
+                       const float* __restrict__ qxyz, int64_t qB, int64_t qN, int64_t qC, int N, int S,
+                       float radius2, int K, const unsigned char* __restrict__ ws_all, size_t ws_stride, int threshold,
+                       int bm_words, const int* __restrict__ done, int64_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char gq_smem[];
+    pdl_trigger();
+    pdl_wait();   // the centroids come from the kernel before
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * WARPS + warp;
+    // `done` (may be NULL): rows already produced by ball_query_stream_kernel; a CTA whose rows are all done leaves
+    bool valid = s < S;
+    if (done) {
+        if (valid && done[(int64_t)b * S + s]) valid = false;
+        if (!__syncthreads_or(valid)) return;
+    }
+    const float* a = qxyz + (int64_t)b * qB + (int64_t)(s < S ? s : 0) * qN;
+    gq_block<WARPS>(xyz, xB, xN, xC, N, radius2, K, ws_all + (size_t)b * ws_stride, threshold, bm_words, gq_smem, b, valid, a[0],
+                    a[qC], a[2 * qC], out + ((int64_t)b * S + (s < S ? s : 0)) * K);
+}
+
+// The same search fed by a RUNNING farthest-point-sampling kernel: a persistent grid on the SMs that sampling leaves idle
+// polls the progress feed of pn_fps_progress_f32 (one 8-byte word per centroid: index << 32 | 1) and answers the ball
+// query of every centroid as soon as it exists, so that the level's grouping is (almost) complete when sampling ends.
+// CTA c serves cloud c % B: rounds of WARPS consecutive centroids.  A warp that waits too long gives up and the CTA
+// leaves; rows it did not finish keep done == 0 and are computed by ball_query_grid_kernel afterwards (correctness never
+// depends on the two kernels actually running side by side).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+ball_query_stream_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC,
+                         const unsigned long long* __restrict__ seq, int B, int N, int S, float radius2, int K,
+                         const unsigned char* __restrict__ ws_all, size_t ws_stride, int threshold, int bm_words,
+                         long long timeout_ns, int* __restrict__ done, int64_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char gq_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x % B;
+    const int per_cloud = gridDim.x / B;           // CTAs serving this cloud (the host launches a multiple of B)
+    if ((int)blockIdx.x >= per_cloud * B) return;
+    const float* __restrict__ p = xyz + (int64_t)b * xB;
+    for (int s0 = (blockIdx.x / B) * WARPS; s0 < S; s0 += per_cloud * WARPS) {
+        const int s = s0 + warp;
+        const bool valid = s < S;
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        bool gave_up = false;
+        if (valid) {
+            unsigned long long w = 0ull;
+            if (lane == 0) {
+                const volatile unsigned long long* slot = seq + (int64_t)b * S + s;
+                long long t0 = 0;
+                while (((w = *slot) & 1ull) == 0ull) {
+                    __nanosleep(200);
+                    long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > timeout_ns) break;
+                }
+            }
+            w = __shfl_sync(0xffffffffu, w, 0);
+            gave_up = (w & 1ull) == 0ull;
+            if (!gave_up) {
+                int j = (int)(w >> 32);
+                j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+                ax = p[(int64_t)j * xN];
+                ay = p[(int64_t)j * xN + xC];
+                az = p[(int64_t)j * xN + 2 * xC];
+            }
+        }
+        if (__syncthreads_or(gave_up)) return;     // sampling is not running beside us: leave everything to the fallback
+        gq_block<WARPS>(xyz, xB, xN, xC, N, radius2, K, ws_all + (size_t)b * ws_stride, threshold, bm_words, gq_smem, b, valid, ax,
+                        ay, az, out + ((int64_t)b * S + (valid ? s : 0)) * K);
+        __syncwarp();
+        if (valid && lane == 0) {
+            __threadfence();                       // the row before its flag
+            done[(int64_t)b * S + s] = 1;
+        }
+        __syncthreads();                           // shared memory is reused by the next round
+    }
+}
+
+
 }  // namespace pn
 
 PN_EXPORT size_t pn_ball_grid_bytes(int B, int N) {
@@ -372,8 +444,8 @@ PN_EXPORT int pn_ball_grid_build_f32(const float* xyz, int64_t xB, int64_t xN, i
 
 PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const float* new_xyz, int64_t qB,
                                      int64_t qN, int64_t qC, int B, int N, int S, float radius2, int nsample,
-                                     const void* grid_ws, size_t grid_bytes, int threshold, int64_t* out_idx,
-                                     pn_stream_t stream) {
+                                     const void* grid_ws, size_t grid_bytes, int threshold, const int32_t* done,
+                                     int64_t* out_idx, pn_stream_t stream) {
     using namespace pn;
     PN_REQUIRE(xyz && new_xyz && out_idx && grid_ws, PN_ERR_BAD_ARG, "pn_ball_query_grid_f32: null pointer");
     PN_REQUIRE(B > 0 && N > 0 && S > 0 && nsample > 0, PN_ERR_BAD_ARG,
@@ -402,7 +474,7 @@ PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, i
         }
         dim3 grid((unsigned)ceil_div(S, warps), (unsigned)B);
         e = launch_pdl(kern, grid, dim3(warps * 32), smem, st, xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
-                       static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N), threshold, bm_words, out_idx);
+                       static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N), threshold, bm_words, done, out_idx);
         if (e != cudaSuccess) {
             cudaGetLastError();
             set_error("pn_ball_query_grid_f32: launch failed: %s", cudaGetErrorString(e));
@@ -413,4 +485,38 @@ PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, i
     if (N <= 32768) return launch(ball_query_grid_kernel<8>, 8);      // bitmaps: <= 4 KB per warp
     if (N <= 262144) return launch(ball_query_grid_kernel<4>, 4);     // <= 32 KB per warp
     return launch(ball_query_grid_kernel<1>, 1);                      // <= 128 KB
+}
+
+static int gq_auto_threshold(int N) {
+    int t = 64;
+    while ((int64_t)t * t < (int64_t)64 * N) t += 64;
+    return t;
+}
+
+PN_EXPORT int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const uint64_t* progress, int B, int N,
+                                       int S, float radius2, int nsample, const void* grid_ws, size_t grid_bytes, int ctas,
+                                       size_t min_smem_bytes, int32_t* done, int64_t* out_idx, pn_stream_t stream) {
+    using namespace pn;
+    PN_REQUIRE(xyz && progress && grid_ws && done && out_idx, PN_ERR_BAD_ARG, "pn_ball_query_stream_f32: null pointer");
+    PN_REQUIRE(B > 0 && N > 0 && S > 0 && nsample > 0, PN_ERR_BAD_ARG, "pn_ball_query_stream_f32: sizes must be positive");
+    PN_REQUIRE(grid_bytes >= pn_ball_grid_bytes(B, N), PN_ERR_BAD_ARG, "pn_ball_query_stream_f32: grid buffer too small");
+    PN_REQUIRE(N <= 32768, PN_ERR_UNSUPPORTED, "pn_ball_query_stream_f32: N=%d exceeds 32768", N);
+    PN_REQUIRE(ctas >= B && ctas % B == 0, PN_ERR_BAD_ARG, "pn_ball_query_stream_f32: ctas=%d must be a positive multiple of B=%d",
+               ctas, B);
+    const int bm_words = (int)ceil_div(ceil_div(N, 32), 32) * 32;
+    size_t smem = (size_t)8 * bm_words * 4;
+    if (smem < (size_t)kGqTile * 16) smem = (size_t)kGqTile * 16;
+    if (smem < min_smem_bytes) smem = min_smem_bytes;   // large enough that a CTA cannot share an SM with the sampling kernel
+    PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "pn_ball_query_stream_f32: %zu bytes of shared memory requested", smem);
+    auto kern = ball_query_stream_kernel<8>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("pn_ball_query_stream_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    kern<<<ctas, 256, smem, (cudaStream_t)stream>>>(xyz, xB, xN, xC, reinterpret_cast<const unsigned long long*>(progress), B, N, S,
+                                                    radius2, nsample, static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N),
+                                                    gq_auto_threshold(N), bm_words, 3000000LL, done, out_idx);
+    return finish_launch("pn_ball_query_stream_f32");
 }

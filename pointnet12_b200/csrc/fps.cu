@@ -42,7 +42,7 @@ constexpr int kFpsSmemHeader = 2 * kMaxCluster * (int)sizeof(FpsMsg) + 2 * 32 * 
 template <int THREADS, int PTS, bool CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, int N, int npoint,
-           const int64_t* __restrict__ start, int64_t* __restrict__ out, int chunk) {
+           const int64_t* __restrict__ start, int64_t* __restrict__ out, unsigned long long* seq, int chunk) {
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     FpsMsg* cl_slots = reinterpret_cast<FpsMsg*>(smem_raw);                                   // [2][16]
@@ -85,7 +85,12 @@ fps_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, in
 
     int64_t* __restrict__ o = out + (int64_t)b * npoint;
     for (int i = 0; i < npoint; ++i) {
-        if (rank == 0 && tid == 0) o[i] = far;
+        if (rank == 0 && tid == 0) {
+            o[i] = far;
+            // progress feed for consumers running beside this kernel: index and "valid" flag in ONE 8-byte store, so a
+            // reader that sees the flag has the index (no fence in this latency-critical loop)
+            if (seq) *reinterpret_cast<volatile unsigned long long*>(seq + (int64_t)b * npoint + i) = ((unsigned long long)(unsigned)far << 32) | 1ull;
+        }
         float bv = -1.0f;
         int bk = 0;
 #pragma unroll
@@ -215,7 +220,7 @@ __device__ __forceinline__ void sqdist_diff2(unsigned long long px, unsigned lon
 template <int NW, int PTS, bool ZT>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, int N, int npoint,
-                 const int64_t* __restrict__ start, int64_t* __restrict__ out, int chunk) {
+                 const int64_t* __restrict__ start, int64_t* __restrict__ out, unsigned long long* seq, int chunk) {
     constexpr int THREADS = NW * 32;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw);          // [2]
@@ -284,7 +289,12 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
     int64_t* __restrict__ o = out + (int64_t)b * npoint;
     for (int i = 0; i < npoint; ++i) {
         const int par = i & 1;
-        if (rank == 0 && tid == 0) o[i] = far;
+        if (rank == 0 && tid == 0) {
+            o[i] = far;
+            // progress feed for consumers running beside this kernel: index and "valid" flag in ONE 8-byte store, so a
+            // reader that sees the flag has the index (no fence in this latency-critical loop)
+            if (seq) *reinterpret_cast<volatile unsigned long long*>(seq + (int64_t)b * npoint + i) = ((unsigned long long)(unsigned)far << 32) | 1ull;
+        }
         if (i == npoint - 1) break;  // the last arg-max would never be used
         if (tid == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_bar0 + par * kParBarOff),
@@ -358,6 +368,9 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
     cluster.sync();  // nobody leaves while a peer may still be storing into its shared memory
 }
 
+static thread_local int g_last_ctas = 0;        // launch shape of the last dispatch on this thread (pn_fps_launch_info)
+static thread_local size_t g_last_smem = 0;
+static thread_local bool g_query_only = false;
 static int g_force_cluster = 0;
 static int g_force_threads = 0;
 static int g_force_exchange = 0;  // 0 auto (st.async where possible), 1 barrier.cluster, 2 st.async
@@ -365,7 +378,10 @@ static int g_force_exchange = 0;  // 0 auto (st.async where possible), 1 barrier
 template <typename Kern>
 static int launch_cluster_kernel(Kern kern, const char* what, int CL, int threads, size_t smem, const float* xyz, int64_t sB,
                                  int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start, int64_t* out,
-                                 int chunk, cudaStream_t stream) {
+                                 unsigned long long* seq, int chunk, cudaStream_t stream) {
+    g_last_ctas = B * CL;
+    g_last_smem = smem;
+    if (g_query_only) return PN_OK;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) {
@@ -387,7 +403,7 @@ static int launch_cluster_kernel(Kern kern, const char* what, int CL, int thread
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    e = cudaLaunchKernelEx(&cfg, kern, xyz, sB, sN, sC, N, npoint, start, out, chunk);
+    e = cudaLaunchKernelEx(&cfg, kern, xyz, sB, sN, sC, N, npoint, start, out, seq, chunk);
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("pn_fps_f32: launch of %s failed (cluster=%d threads=%d smem=%zu): %s", what, CL, threads, smem,
@@ -397,11 +413,11 @@ static int launch_cluster_kernel(Kern kern, const char* what, int CL, int thread
     return PN_OK;
 }
 
-#define PN_FPS_ARGS xyz, sB, sN, sC, B, N, npoint, start, out, chunk, stream
+#define PN_FPS_ARGS xyz, sB, sN, sC, B, N, npoint, start, out, seq, chunk, stream
 
 template <int THREADS>
 static int dispatch_barrier(int pts, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
-                            const int64_t* start, int64_t* out, int chunk, cudaStream_t stream) {
+                            const int64_t* start, int64_t* out, unsigned long long* seq, int chunk, cudaStream_t stream) {
     const size_t smem = (size_t)kFpsSmemHeader + (size_t)chunk * 3 * sizeof(float);
 #define PN_FPS_CASE(P)                                                                                              \
     if (pts <= P)                                                                                                   \
@@ -423,7 +439,7 @@ static int g_force_ztable = 0;   // 0 auto (z table when it fits), 1 never
 
 template <int NW>
 static int dispatch_async(int pts, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
-                          const int64_t* start, int64_t* out, int chunk, cudaStream_t stream) {
+                          const int64_t* start, int64_t* out, unsigned long long* seq, int chunk, cudaStream_t stream) {
     const size_t smem0 = (size_t)kAsyncSmemHeader + (size_t)chunk * 3 * sizeof(float);
     const bool zt = g_force_ztable == 0 && smem0 + (size_t)N * sizeof(float) <= 200 * 1024;
     const size_t smem = smem0 + (zt ? (size_t)N * sizeof(float) : 0);
@@ -458,10 +474,35 @@ PN_EXPORT int pn_fps_set_config(int cluster_size, int threads, int exchange) {
     return PN_OK;
 }
 
+static int fps_dispatch(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start,
+                        int64_t* out, unsigned long long* seq, pn_stream_t stream_);
+
 PN_EXPORT int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
                          const int64_t* start, int64_t* out, pn_stream_t stream_) {
-    using namespace pn;
     PN_REQUIRE(xyz && start && out, PN_ERR_BAD_ARG, "pn_fps_f32: null pointer");
+    return fps_dispatch(xyz, sB, sN, sC, B, N, npoint, start, out, nullptr, stream_);
+}
+
+PN_EXPORT int pn_fps_progress_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+                                  const int64_t* start, int64_t* out, uint64_t* progress, pn_stream_t stream_) {
+    PN_REQUIRE(xyz && start && out && progress, PN_ERR_BAD_ARG, "pn_fps_progress_f32: null pointer");
+    return fps_dispatch(xyz, sB, sN, sC, B, N, npoint, start, out, reinterpret_cast<unsigned long long*>(progress), stream_);
+}
+
+PN_EXPORT int pn_fps_launch_info(int B, int N, int npoint, int* ctas, size_t* smem_bytes) {
+    PN_REQUIRE(ctas && smem_bytes, PN_ERR_BAD_ARG, "pn_fps_launch_info: null pointer");
+    pn::g_query_only = true;
+    const int rc = fps_dispatch(reinterpret_cast<const float*>(16), 3 * (int64_t)N, 1, N, B, N, npoint,
+                                reinterpret_cast<const int64_t*>(16), reinterpret_cast<int64_t*>(16), nullptr, nullptr);
+    pn::g_query_only = false;
+    *ctas = pn::g_last_ctas;
+    *smem_bytes = pn::g_last_smem;
+    return rc;
+}
+
+static int fps_dispatch(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start,
+                        int64_t* out, unsigned long long* seq, pn_stream_t stream_) {
+    using namespace pn;
     PN_REQUIRE(B > 0 && N > 0 && npoint > 0, PN_ERR_BAD_ARG, "pn_fps_f32: B, N, npoint must be positive (got %d, %d, %d)", B,
                N, npoint);
     cudaStream_t stream = (cudaStream_t)stream_;

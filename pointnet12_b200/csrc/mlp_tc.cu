@@ -1090,6 +1090,7 @@ static long long* g_tc_dbg = nullptr;   // pn_mlp_set_debug
 static int g_tc_quad = 1;               // pn_mlp_set_engine(engine | 4) disables the coalesced quad producer
 static int g_tc_nslice = 1;             // pn_mlp_set_engine(engine | 8) disables N-slicing of single-layer chains
 static int g_tc_wide = 1;               // pn_mlp_set_engine(engine | 16) disables the 16-warp streaming CTAs
+static int g_tc_reserved = 0;           // pn_mlp_set_reserved_sms
 
 // Resident kernel usable?  Returns warps per group (8 or 4), or 0.
 static int tc_resident_wpg(const TcChain& c) {
@@ -1126,8 +1127,11 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
                 set_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e));
                 return (int)e;
             }
+            // one persistent CTA per SM; SMs held by kernels of other streams are left out (a CTA that had to wait for
+            // its SM would start its full static share of tiles late and stretch the whole launch)
             const int64_t want = (ntiles_all + groups - 1) / groups;
-            const unsigned grid = (unsigned)(want < 148 ? want : 148);
+            const int64_t sms = 148 - g_tc_reserved > 1 ? 148 - g_tc_reserved : 1;
+            const unsigned grid = (unsigned)(want < sms ? want : sms);
             TcIo io2 = io;
             io2.dbg = g_tc_dbg;
             e = launch_pdl(rkern, dim3(grid), dim3(kResThreads), rsmem, stream, ch, static_cast<const unsigned char*>(blob), io2);
@@ -1165,7 +1169,9 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     }
     const size_t smem = tc_smem_bytes(chs, chs.nstages);
     PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "%s: chain needs %zu bytes of shared memory", what, smem);
-    const bool wide = g_tc_wide && (int64_t)ntiles_all * (pass_w != kTcNPass ? (ch.L[0].n_pad + pass_w - 1) / pass_w : 1) <= 148;
+    // (only the FP producer / epilogues gained from 16 warps; the SA levels did not, and their 8-warp CTAs fit beside the
+    // background 3-NN search that runs at the same time)
+    const bool wide = g_tc_wide && IN == TC_IN_FP && (int64_t)ntiles_all * (pass_w != kTcNPass ? (ch.L[0].n_pad + pass_w - 1) / pass_w : 1) <= 148;
     auto kern = wide ? mlp_tc_kernel<IN, 512> : mlp_tc_kernel<IN, 256>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -1196,6 +1202,12 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
 }  // namespace pn
 
 // ------------------------------------------------------------------------------------------------ C ABI
+PN_EXPORT int pn_mlp_set_reserved_sms(int sms) {
+    PN_REQUIRE(sms >= 0 && sms < 148, PN_ERR_BAD_ARG, "pn_mlp_set_reserved_sms: 0 <= sms < 148");
+    pn::g_tc_reserved = sms;
+    return PN_OK;
+}
+
 PN_EXPORT int pn_mlp_set_debug(void* timeline) {
     pn::g_tc_dbg = static_cast<long long*>(timeline);
     return PN_OK;

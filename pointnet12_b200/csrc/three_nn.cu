@@ -357,11 +357,12 @@ PN_EXPORT int pn_three_nn_blocks_f32(const float* xyz1, int64_t aB, int64_t aN, 
         set_error("pn_three_nn_blocks_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    // background: at most ~4 CTAs (16 warps, 86 KB of shared memory) per SM, so that kernels of a concurrent stream
-    // still find room on every SM; the search then takes longer but stays out of their way
+    // background: at most ~3 CTAs (12 warps, 15 K registers, 65 KB of shared memory) per SM, so that kernels of a concurrent
+    // stream still find room on every SM (an 8-warp streaming CTA of the chains: 25 K registers, 110 KB); the search then
+    // takes longer but stays out of their way
     int64_t gx = ceil_div(N, kNbWarps * 32);
     if (background) {
-        const int64_t cap = ceil_div(148 * 4, B);
+        const int64_t cap = ceil_div(148 * 3, B);
         gx = gx < cap ? gx : cap;
     }
     dim3 grid((unsigned)gx, (unsigned)B);

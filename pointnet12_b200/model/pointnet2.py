@@ -206,23 +206,47 @@ class PointNet2SemSeg(_Net):
         # (= lower) priority on two more streams and fill whatever the critical path leaves idle instead of competing
         # with it: the big one (24000 x 1024 per cloud, for fp1) on its own stream, released after sa2.
         user = torch.cuda.current_stream(points.device)
-        main, geo, nn_small, nn_big = self._side_streams(points.device)
+        main, geo, nn_small, nn_big, feed = self._side_streams(points.device)
         begin = torch.cuda.Event()
         begin.record(user)
         main.wait_event(begin)
 
-        # the level-1 ball-query buckets depend on xyz only: built beside the level-1 sampling
-        grid1 = None
+        # the level-1 ball-query buckets depend on xyz only: built beside the level-1 sampling.  If sampling leaves
+        # enough SMs idle, the level-1 ball query itself runs there WHILE sampling runs, fed centroid by centroid
+        # (ops.ball_query_stream); the regular query afterwards only fills in what the streamed one did not finish.
+        grid1, streamed = None, None
+        S1, K1 = sa[0].npoint, sa[0].nsample
+        if N >= ops.GRID_MIN_POINTS:
+            if ops.STREAM_BALL_QUERY and N <= 32768:
+                fps_ctas, fps_smem = ops.fps_launch_info(B, N, S1)
+                sms = torch.cuda.get_device_properties(points.device).multi_processor_count
+                ctas = (sms - fps_ctas) // B * B
+                if ctas >= max(B, ops.STREAM_BALL_MIN_FREE_SMS):
+                    streamed = {"progress": torch.zeros((B, S1), dtype=torch.int64, device=points.device),
+                                "done": torch.zeros((B, S1), dtype=torch.int32, device=points.device),
+                                "out": torch.empty((B, S1, K1), dtype=torch.int64, device=points.device)}
+                    begin.record(user)                       # (again: the zero fills come first)
+                    main.wait_event(begin)
+        with torch.cuda.stream(main):
+            # level-1 sampling (the long serial kernel), issued FIRST: its clusters need whole groups of free SMs, so the
+            # kernels that run beside it must find it already in place
+            fps1 = ops.fps(x0, S1, ops._i64(fps_starts[0], "start_idx"), progress=streamed["progress"] if streamed else None)
         if N >= ops.GRID_MIN_POINTS:
             with torch.cuda.stream(geo):
                 geo.wait_event(begin)
                 grid1 = ops.ball_grid(x0, sa[0].radius)
                 grid_ready = torch.cuda.Event()
                 grid_ready.record(geo)
+            if streamed is not None:
+                with torch.cuda.stream(feed):                # its own stream: `geo` must be free for level 2 when sampling ends
+                    feed.wait_event(grid_ready)
+                    ops.ball_query_stream(sa[0].radius, K1, x0, grid1, streamed["progress"], streamed["done"], streamed["out"],
+                                          ctas, 227 * 1024 - fps_smem + 1024)
+                    streamed["finished"] = torch.cuda.Event()
+                    streamed["finished"].record(feed)
 
         with torch.cuda.stream(main):
-            # level-1 sampling (the long serial kernel)
-            x1 = ops.index_points(x0, farthest_point_sample(x0, sa[0].npoint, fps_starts[0]))
+            x1 = ops.index_points(x0, fps1)
             fork = torch.cuda.Event()
             fork.record(main)
         xs, balls, nns, ready, have_x = [x0, x1], [None] * 4, [None] * 4, [None] * 4, [None] * 4
@@ -244,11 +268,23 @@ class PointNet2SemSeg(_Net):
             # feature path
             if grid1 is not None:
                 main.wait_event(grid_ready)
-            balls[0] = ops.ball_query(sa[0].radius, sa[0].nsample, x0, x1, grid=grid1)
-            fs = [f0, sa[0].features(x0, f0, x1, balls[0])]
+            if streamed is not None:
+                main.wait_event(streamed["finished"])
+                balls[0] = ops.ball_query(sa[0].radius, K1, x0, x1, grid=grid1, done=streamed["done"], out=streamed["out"])
+            else:
+                balls[0] = ops.ball_query(sa[0].radius, K1, x0, x1, grid=grid1)
+            # sa1 / sa2 run one persistent CTA per SM while level 2-4 sampling holds a few SMs: leave those out
+            ops.set_reserved_sms(ops.fps_launch_info(B, S1, sa[1].npoint)[0])
+            try:
+                fs = [f0, sa[0].features(x0, f0, x1, balls[0])]
+                main.wait_event(ready[1])
+                fs.append(sa[1].features(xs[1], fs[1], xs[2], balls[1]))
+            finally:
+                ops.set_reserved_sms(0)
             for i in (1, 2, 3):
-                main.wait_event(ready[i])
-                fs.append(sa[i].features(xs[i], fs[i], xs[i + 1], balls[i]))
+                if i > 1:
+                    main.wait_event(ready[i])
+                    fs.append(sa[i].features(xs[i], fs[i], xs[i + 1], balls[i]))
                 if i == 1:
                     # fp1's 3-NN search (24000 x 1024 per cloud) fills the GPU with long-lived CTAs, which stream
                     # priorities cannot displace: it is released only now, when the wide kernels of the critical path
@@ -309,5 +345,6 @@ class PointNet2SemSeg(_Net):
             rng = torch.cuda.Stream.priority_range()             # lower number = higher priority; 0 = default = lowest
             lo, hi = max(rng), min(rng)
             streams[key] = (torch.cuda.Stream(device, priority=hi), torch.cuda.Stream(device, priority=hi),
-                            torch.cuda.Stream(device, priority=lo), torch.cuda.Stream(device, priority=lo))
+                            torch.cuda.Stream(device, priority=lo), torch.cuda.Stream(device, priority=lo),
+                            torch.cuda.Stream(device, priority=hi))
         return streams[key]

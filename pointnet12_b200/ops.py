@@ -87,8 +87,10 @@ def fps_set_config(cluster_size: int = 0, threads: int = 0, exchange: int = 0) -
 
 
 # ------------------------------------------------------------------------------------------------
-def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor) -> torch.Tensor:
-    """farthest_point_sample (pointnet_util.py:63-84); start_idx [B] int64 on the device."""
+def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor, progress: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """farthest_point_sample (pointnet_util.py:63-84); start_idx [B] int64 on the device.
+    progress: a ZEROED int64 [B, npoint] tensor -> the kernel also publishes every centroid as it is chosen
+    (index << 32 | 1), for consumers running beside it (ball_query_stream)."""
     xyz = _cloud(xyz, "xyz", 3)
     B, N, _ = xyz.shape
     start_idx = _i64(start_idx, "start_idx")
@@ -96,9 +98,39 @@ def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor) -> torch.Tensor
         raise ValueError(f"start_idx must have shape ({B},), got {tuple(start_idx.shape)}")
     out = torch.empty((B, int(npoint)), dtype=torch.int64, device=xyz.device)
     with _on_device(xyz):
-        nv.call("pn_fps_f32", xyz.data_ptr(), *xyz.stride(), B, N, int(npoint), start_idx.data_ptr(), out.data_ptr(),
-                _stream(), tag=(B, N, int(npoint)))
+        if progress is None:
+            nv.call("pn_fps_f32", xyz.data_ptr(), *xyz.stride(), B, N, int(npoint), start_idx.data_ptr(), out.data_ptr(),
+                    _stream(), tag=(B, N, int(npoint)))
+        else:
+            if progress.shape != (B, int(npoint)) or progress.dtype != torch.int64 or not progress.is_contiguous():
+                raise ValueError("progress must be a contiguous int64 [B, npoint] tensor")
+            nv.call("pn_fps_progress_f32", xyz.data_ptr(), *xyz.stride(), B, N, int(npoint), start_idx.data_ptr(),
+                    out.data_ptr(), progress.data_ptr(), _stream(), tag=(B, N, int(npoint)))
     return out
+
+
+def fps_launch_info(B: int, N: int, npoint: int) -> Tuple[int, int]:
+    """(CTAs, dynamic shared memory per CTA) of the sampling launch for this shape."""
+    ctas, smem = C.c_int(), C.c_size_t()
+    nv.check(nv.lib().pn_fps_launch_info(int(B), int(N), int(npoint), C.byref(ctas), C.byref(smem)), "pn_fps_launch_info")
+    return ctas.value, smem.value
+
+
+STREAM_BALL_QUERY = os.environ.get("PN12_STREAM_BALL", "1") != "0"
+STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for the streamed ball query to be worth it
+
+
+def ball_query_stream(radius: float, nsample: int, xyz: torch.Tensor, grid: "BallGrid", progress: torch.Tensor,
+                      done: torch.Tensor, out: torch.Tensor, ctas: int, min_smem: int) -> None:
+    """Answers the ball queries of the centroids a RUNNING fps(..., progress=...) publishes (pn_ball_query_stream_f32);
+    call it on another stream than the sampling.  done int32 [B, S] (zeroed), out int64 [B, S, nsample]."""
+    xyz = _cloud(xyz, "xyz", 3)
+    B, N, _ = xyz.shape
+    S = progress.shape[1]
+    with _on_device(xyz):
+        nv.call("pn_ball_query_stream_f32", xyz.data_ptr(), *xyz.stride(), progress.data_ptr(), B, N, S, float(radius ** 2),
+                int(nsample), grid.buf.data_ptr(), grid.nbytes, int(ctas), int(min_smem), done.data_ptr(), out.data_ptr(),
+                _stream())
 
 
 def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
@@ -144,15 +176,22 @@ def ball_grid(xyz: torch.Tensor, radius: float) -> BallGrid:
 
 
 def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor,
-               grid: Optional[BallGrid] = None, method: str = "auto", threshold: Optional[int] = None) -> torch.Tensor:
+               grid: Optional[BallGrid] = None, method: str = "auto", threshold: Optional[int] = None,
+               done: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """query_ball_point (pointnet_util.py:87-107) -> int64 [B, S, nsample].
     method: "auto" (grid buckets for N >= GRID_MIN_POINTS, ordered scan below), "scan" (pn_ball_query_f32),
     "grid" / "grid-cells" / "grid-scan" (pn_ball_query_grid_f32 with the automatic threshold / every query through
-    the cells / every query through the per-warp scan).  All return identical indices."""
+    the cells / every query through the per-warp scan).  All return identical indices.
+    done / out: int32 [B, S] flags of rows ball_query_stream has already written into `out`; only the others are computed."""
     xyz, new_xyz = _cloud(xyz, "xyz", 3), _cloud(new_xyz, "new_xyz", 3)
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
-    out = torch.empty((B, S, int(nsample)), dtype=torch.int64, device=xyz.device)
+    if out is None:
+        out = torch.empty((B, S, int(nsample)), dtype=torch.int64, device=xyz.device)
+    elif out.shape != (B, S, int(nsample)) or out.dtype != torch.int64 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int64 [B, S, nsample] tensor")
+    if done is not None and (method not in ("auto", "grid") or grid is None):
+        raise ValueError("done= (rows finished by ball_query_stream) needs the grid method")
     r2 = float(radius ** 2)  # the reference compares against the python scalar radius ** 2 (cast to fp32 by torch)
     if method == "auto":
         method = "grid" if (grid is not None or N >= GRID_MIN_POINTS) else "scan"
@@ -170,7 +209,7 @@ def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Te
         if threshold is None:
             threshold = {"grid": 0, "grid-cells": 2 ** 31 - 1, "grid-scan": -1}[method]
         nv.call("pn_ball_query_grid_f32", xyz.data_ptr(), *xyz.stride(), new_xyz.data_ptr(), *new_xyz.stride(), B, N, S,
-                r2, int(nsample), grid.buf.data_ptr(), grid.nbytes, threshold, out.data_ptr(), _stream())
+                r2, int(nsample), grid.buf.data_ptr(), grid.nbytes, threshold, _p(done), out.data_ptr(), _stream())
     return out
 
 
@@ -376,6 +415,11 @@ def set_mlp_engine(engine: str = "auto") -> None:
     quad producer) for A/B comparisons."""
     nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2, "auto-rowwise": 4, "resident-rowwise": 6,
                                   "auto-noslice": 8, "stream-noslice": 9, "auto-narrow": 16, "stream-narrow": 17}[engine])
+
+
+def set_reserved_sms(sms: int = 0) -> None:
+    """SMs the resident-weight chain launches leave to kernels of other streams (pn_mlp_set_reserved_sms)."""
+    nv.call("pn_mlp_set_reserved_sms", int(sms))
 
 
 FOLD_FIRST_FP_LAYER = os.environ.get("PN12_FP_FOLD", "1") != "0"

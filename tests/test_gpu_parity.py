@@ -206,6 +206,46 @@ def test_ball_query_grid_edge_cases(dev, method):
         ops.ball_query(0.2, 32, cuda(xyz, dev), cuda(q, dev), grid=grid, method=method)
 
 
+def test_ball_query_streamed_beside_fps(dev):
+    """The level-1 ball query fed by the running sampling kernel: (a) both kernels side by side on two streams,
+    (b) the streamed kernel alone (nothing ever arrives: it gives up after its time-out) -- in both cases the
+    follow-up query over the `done` flags completes the result, bit-identical to the plain query and the oracle."""
+    from pointnet12_b200 import ops
+
+    B, N, S, K, r = 4, 24000, 512, 32, 0.1
+    pts = syn.kitti_batch(B, N, config=8)
+    xyz_h = pts.transpose(0, 2, 1)[:, :, :3]
+    xyz = views(cuda(pts, dev))[0]
+    start = torch.zeros(B, dtype=torch.long, device=dev)
+    want_fps = orc.farthest_point_sample(xyz_h, S, np.zeros(B, dtype=np.int64))
+    q = np.ascontiguousarray(np.stack([xyz_h[b][want_fps[b]] for b in range(B)]))
+    want = orc.query_ball_point(r, K, xyz_h, q)
+    grid = ops.ball_grid(xyz, r)
+    fps_ctas, fps_smem = ops.fps_launch_info(B, N, S)
+    assert fps_ctas == B * 8 and 0 < fps_smem < 227 * 1024
+    ctas = (148 - fps_ctas) // B * B
+    for side_by_side in (True, False):
+        progress = torch.zeros((B, S), dtype=torch.int64, device=dev)
+        done = torch.zeros((B, S), dtype=torch.int32, device=dev)
+        out = torch.full((B, S, K), -7, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(dev)
+        if side_by_side:                                 # sampling first: its clusters need whole groups of free SMs
+            fps_idx = ops.fps(xyz, S, start, progress=progress)
+        with torch.cuda.stream(side):
+            ops.ball_query_stream(r, K, xyz, grid, progress, done, out, ctas, 227 * 1024 - fps_smem + 1024)
+        torch.cuda.synchronize()
+        if not side_by_side:
+            assert int(done.sum()) == 0                      # timed out without touching anything
+            fps_idx = ops.fps(xyz, S, start)
+        assert np.array_equal(fps_idx.cpu().numpy(), want_fps)
+        streamed_rows = int(done.sum())
+        got = ops.ball_query(r, K, xyz, ops.index_points(xyz, fps_idx), grid=grid, done=done, out=out)
+        assert np.array_equal(got.cpu().numpy(), want)
+        if side_by_side:
+            assert streamed_rows > 0, "the streamed kernel never ran beside the sampling kernel"
+
+
 def test_ball_query_empty_ball(dev):
     """A query far from every point: the reference leaves the row filled with N."""
     from pointnet12_b200.model import pointnet_util as U
