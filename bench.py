@@ -220,7 +220,9 @@ def run_ours(args):
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)      # ms
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        timed.last = per_step
+        return sum(per_step)      # ms
 
     torch.manual_seed(1234 + rank)
     for i in range(max(args.warmup, 3)):
@@ -235,6 +237,7 @@ def run_ours(args):
     with ClockSampler(local) as clocks:
         ms = timed(step_resident, args.steps)
     barrier()
+    spread = sorted(timed.last)
     launches = nv.launch_count - launches0
     if runner is None:
         fps_records = sum(nv.time_entry_points(None).values(), [])
@@ -281,6 +284,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": BATCH * 4 * NPOINTS * 4 + 4 * BATCH * 8,
                     "d2h_bytes_per_step": BATCH * NPOINTS * CLASSES * 4},
             "gpu_launches": launches,
+            "step_ms": {"min": spread[0], "median": spread[len(spread) // 2], "max": spread[-1]},
             "roofline": {"kernel": "pn_fps_f32 (fps_kernel, level 1: N=24000 -> 1024 centroids)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": fps_bytes,
