@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (our arm only)")
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch of the critical-path kernels")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
+                    help="bf16x3 (default, fp32 parity), bf16 (single-pass, stated tolerance) or fp32 (CUDA cores)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: one CUDA-graph replay per step (default); eager: ~40 launches per step")
     return ap.parse_args()
@@ -176,6 +178,7 @@ def run_ours(args):
 
     if args.pdl:
         ops.set_pdl(True)
+    ops.set_mlp_mode(args.precision)
     net = load_pointnet("pointnet2", CLASSES, CKPT, device=dev)
     # four different batches per rank, rotated, so consecutive steps never see the same clouds
     host_batches = [torch.from_numpy(syn.kitti_batch(BATCH, NPOINTS, config=2, first=(rank * 4 + i) * BATCH)).pin_memory()
@@ -271,11 +274,16 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": points / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (MLP products as split bf16 hi/lo on tensor cores)" if ops.mlp_mode() == "bf16x3" else "f32",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16x3": "f32 (MLP products as split bf16 hi/lo on tensor cores)", "bf16": "bf16 (fp32 accumulation)",
+                      "fp32": "f32"}[ops.mlp_precision()],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "points_per_cloud": NPOINTS,
-                       "precision": ("bf16x3: tcgen05 tensor cores, 3-pass split bf16 with fp32 accumulation (fp32 parity, "
-                                     "~1e-5 relative)" if ops.mlp_mode() == "bf16x3" else "fp32 FMA on CUDA cores"),
+                       "precision": {"bf16x3": "bf16x3: tcgen05 tensor cores, 3-pass split bf16 with fp32 accumulation (fp32 "
+                                               "parity, ~1e-5 relative)",
+                                     "bf16": "bf16: tcgen05 tensor cores, single pass (max |delta log-prob| 0.38, 99.6 % equal "
+                                             "labels at this config)",
+                                     "fp32": "fp32 FMA on CUDA cores"}[ops.mlp_precision()],
                        "launch": ("one CUDA-graph replay per step (3 streams forked/joined inside the graph)"
                                   if runner is not None else "eager launches on 3 streams"),
                        "l2": "512 MiB written between timed steps",

@@ -256,6 +256,10 @@ int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* poi
  * +8 = no N-slicing of single-layer chains; +16 = 8-warp streaming CTAs only (no 16-warp CTAs on small grids).
  * Process-wide; meant for benchmarks and tests. */
 int pn_mlp_set_engine(int engine);
+/* Precision of the fused chains: 3 (default) = all three split-bf16 products, fp32 parity (~1e-5 relative); 1 = only
+ * a_hi * w_hi, i.e. plain bf16 inputs with fp32 accumulation -- a third of the tensor-core work, for callers that accept
+ * bf16 accuracy (config C4).  The packed blob is the same.  Process-wide. */
+int pn_mlp_set_precision(int passes);
 /* SMs the resident-weight launches (one persistent CTA per SM) leave to kernels running on other streams at the same
  * time (e.g. the next level's sampling, one CTA per cloud).  Read at launch; 0 by default.  Process-wide. */
 int pn_mlp_set_reserved_sms(int sms);

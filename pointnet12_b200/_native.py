@@ -67,6 +67,7 @@ _SIGNATURES = {
     "pn_mlp_set_engine": [i32],
     "pn_mlp_set_debug": [vp],
     "pn_mlp_set_reserved_sms": [i32],
+    "pn_mlp_set_precision": [i32],
 }
 
 

@@ -43,6 +43,7 @@ struct TcChain {
     int nlayers, stage_bytes, tmem_cols, x_cols, a_lo_off, bias_floats;
     int nstages;        // ring depth of the streaming kernel (set at launch)
     int pass_w;         // output channels per accumulation pass of the streaming kernel: kTcNPass, or the N-slice width
+    int split;          // 1 = all three products a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (fp32 parity); 0 = a_hi*w_hi only (plain bf16)
     unsigned bias_off;  // byte offset of the bias table in the blob
     unsigned blob_bytes;
     TcLayer L[kTcMaxLayers];
@@ -691,14 +692,16 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                                                      tbase),
                                                  "r"(a_hi_col + kcol), "l"(dh), "r"(idesc), "r"(acc0)
                                                  : "memory");
-                                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                                     tbase),
-                                                 "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
-                                                 : "memory");
-                                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                                     tbase),
-                                                 "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
-                                                 : "memory");
+                                    if (ch.split) {
+                                        asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                         tbase),
+                                                     "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
+                                                     : "memory");
+                                        asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                         tbase),
+                                                     "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
+                                                     : "memory");
+                                    }
                                 }
                                 tc_commit(bar_empty0 + 8 * use_st);
                                 if (s + 1 == ns) tc_commit(bar_done);
@@ -946,14 +949,16 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                                              tbase),
                                          "r"(a_hi_col + kcol), "l"(dh), "r"(idesc), "r"(acc0)
                                          : "memory");
-                            asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                             tbase),
-                                         "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
-                                         : "memory");
-                            asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                             tbase),
-                                         "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
-                                         : "memory");
+                            if (ch.split) {
+                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                 tbase),
+                                             "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
+                                             : "memory");
+                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
+                                                 tbase),
+                                             "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
+                                             : "memory");
+                            }
                         }
                     }
                     tc_commit(bar_done);
@@ -1091,6 +1096,7 @@ static int g_tc_quad = 1;               // pn_mlp_set_engine(engine | 4) disable
 static int g_tc_nslice = 1;             // pn_mlp_set_engine(engine | 8) disables N-slicing of single-layer chains
 static int g_tc_wide = 1;               // pn_mlp_set_engine(engine | 16) disables the 16-warp streaming CTAs
 static int g_tc_reserved = 0;           // pn_mlp_set_reserved_sms
+static int g_tc_split = 1;              // pn_mlp_set_precision: 1 = bf16x3 (fp32 parity), 0 = single-pass bf16
 
 // Resident kernel usable?  Returns warps per group (8 or 4), or 0.
 static int tc_resident_wpg(const TcChain& c) {
@@ -1134,7 +1140,9 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
             const unsigned grid = (unsigned)(want < sms ? want : sms);
             TcIo io2 = io;
             io2.dbg = g_tc_dbg;
-            e = launch_pdl(rkern, dim3(grid), dim3(kResThreads), rsmem, stream, ch, static_cast<const unsigned char*>(blob), io2);
+            TcChain chr = ch;
+            chr.split = g_tc_split;
+            e = launch_pdl(rkern, dim3(grid), dim3(kResThreads), rsmem, stream, chr, static_cast<const unsigned char*>(blob), io2);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -1147,6 +1155,7 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     // ring depth: what fits in ~110 KB (two CTAs can share an SM), at least 2, at most kTcMaxStages
     TcChain chs = ch;
     chs.pass_w = pass_w;
+    chs.split = g_tc_split;
     if (pass_w != kTcNPass) {   // re-plan the per-CTA resources for the narrower pass
         const TcLayer& L0 = ch.L[0];
         const int xw = L0.n_pad < pass_w ? L0.n_pad : pass_w;
@@ -1202,6 +1211,12 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
 }  // namespace pn
 
 // ------------------------------------------------------------------------------------------------ C ABI
+PN_EXPORT int pn_mlp_set_precision(int passes) {
+    PN_REQUIRE(passes == 1 || passes == 3, PN_ERR_BAD_ARG, "pn_mlp_set_precision: 3 = split bf16 (fp32 parity), 1 = plain bf16");
+    pn::g_tc_split = passes == 3 ? 1 : 0;
+    return PN_OK;
+}
+
 PN_EXPORT int pn_mlp_set_reserved_sms(int sms) {
     PN_REQUIRE(sms >= 0 && sms < 148, PN_ERR_BAD_ARG, "pn_mlp_set_reserved_sms: 0 <= sms < 148");
     pn::g_tc_reserved = sms;

@@ -393,20 +393,38 @@ def log_softmax(x: torch.Tensor) -> torch.Tensor:
 # "bf16x3" computes every product as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation: fp32 parity
 # (relative error ~1e-5) at tensor-core speed.  "fp32" keeps the exact-fp32 CUDA-core path (pn_linear_f32).
 _MLP_MODE = os.environ.get("PN12_MLP", "bf16x3")
+if _MLP_MODE == "bf16":       # PN12_MLP=bf16: resolved to the single-pass precision at the first set_mlp_mode / import below
+    _MLP_MODE = "bf16x3"
+    _ENV_BF16 = True
+else:
+    _ENV_BF16 = False
 OUT_ROWS, OUT_MAX32, OUT_LOG_SOFTMAX = 0, 1, 2
 
 
+_MLP_BF16 = False
+
+
 def set_mlp_mode(mode: str) -> str:
-    """'bf16x3' (tensor cores, default) or 'fp32' (CUDA cores, exact fp32 accumulation).  Returns the old mode."""
-    global _MLP_MODE
-    if mode not in ("bf16x3", "fp32"):
-        raise ValueError("mode must be 'bf16x3' or 'fp32'")
-    old, _MLP_MODE = _MLP_MODE, mode
+    """'bf16x3' (tensor cores, 3-pass split bf16 = fp32 parity, default), 'bf16' (the same kernels issuing only the
+    hi x hi product: plain bf16 inputs, fp32 accumulation, a third of the tensor-core work) or 'fp32' (CUDA cores, exact
+    fp32 accumulation).  Returns the old mode."""
+    global _MLP_MODE, _MLP_BF16
+    if mode not in ("bf16x3", "bf16", "fp32"):
+        raise ValueError("mode must be 'bf16x3', 'bf16' or 'fp32'")
+    old = "bf16" if (_MLP_BF16 and _MLP_MODE == "bf16x3") else _MLP_MODE
+    _MLP_MODE = "fp32" if mode == "fp32" else "bf16x3"       # which engine the modules pick
+    _MLP_BF16 = mode == "bf16"
+    nv.call("pn_mlp_set_precision", 1 if _MLP_BF16 else 3)
     return old
 
 
 def mlp_mode() -> str:
+    """The engine the modules use: 'bf16x3' (tensor-core chains, in either precision) or 'fp32'."""
     return _MLP_MODE
+
+
+def mlp_precision() -> str:
+    return "fp32" if _MLP_MODE == "fp32" else ("bf16" if _MLP_BF16 else "bf16x3")
 
 
 def set_mlp_engine(engine: str = "auto") -> None:
@@ -562,3 +580,7 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
                 *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), optr, oes, obs, B, N,
                 out_mode, out.data_ptr(), chain.cout, _stream())
     return full_out
+
+
+if _ENV_BF16:
+    set_mlp_mode("bf16")
