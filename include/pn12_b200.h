@@ -218,8 +218,9 @@ int pn_mlp_rows_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* x
 
 /* One whole set-abstraction level after sampling (model/pointnet_util.py:127-131 + :194-199, or the MSG
  * branch :243-256 with msg_order = 1): gather + recentre + concat straight into the tensor-core operand,
- * the conv+BN+ReLU chain, and the max over the nsample (= 32) rows of each group.
- * out [B*S, cout_last] rows with leading dimension ldo.  Arguments as pn_group_f32. */
+ * the conv+BN+ReLU chain, and the max over the nsample rows of each group.  nsample = 16 or 32: out [B*S, cout_last]
+ * rows with leading dimension ldo.  nsample = 32 m (64, 128, ...): the kernel pools runs of 32 rows, out has B*S*m rows
+ * and the caller reduces every m consecutive rows (pn_group_max_f32).  Arguments as pn_group_f32. */
 int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
                          int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
                          const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,

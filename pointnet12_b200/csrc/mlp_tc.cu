@@ -206,6 +206,31 @@ __device__ __forceinline__ float tc_colmax32(float (&v)[32], int lane) {
     tc_colmax_step<16>(v, lane);
     return v[0];
 }
+// The same over the 16 rows of each half-warp for the 16 columns in v[0..15]: lane j holds column j % 16 of its half.
+__device__ __forceinline__ float tc_colmax16(float (&v)[32], int lane) {
+    tc_colmax_step<8>(v, lane);
+    return v[0];
+}
+// Max-pool epilogue for groups of 16 rows (two groups per warp): 32 accumulator columns in r -> y[group, c0 .. c0+31]
+__device__ __forceinline__ void tc_store_max16(const unsigned (&r)[32], const float* bias, int relu, bool valid, int64_t row,
+                                               int lane, int c0, int n_real, float* y, int64_t ldy) {
+    const unsigned half_mask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+    const bool any_valid = (__ballot_sync(0xffffffffu, valid) & half_mask) != 0u;
+    const int64_t g = __shfl_sync(0xffffffffu, row / 16, lane & 16);   // the group of this half-warp (its first lane)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float f = __uint_as_float(r[h * 16 + j]) + bias[c0 + h * 16 + j];
+            if (relu) f = fmaxf(f, 0.0f);
+            v[j] = valid ? f : -CUDART_INF_F;
+        }
+        const float m = tc_colmax16(v, lane);
+        const int n = c0 + h * 16 + (lane & 15);
+        if (any_valid && n < n_real) y[g * ldy + n] = m;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ row producers
 enum { TC_IN_ROWS = 0, TC_IN_SA = 1, TC_IN_FP = 2 };
@@ -773,6 +798,10 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                     for (int c0 = half * 32; c0 < rows_p; c0 += CSTEP) {
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
+                        if (io.group == 16) {
+                            tc_store_max16(r, bias, L.relu, rc.valid, rc.row, lane, c0, L.n_real - n0, io.y + n0, io.ldy);
+                            continue;
+                        }
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -1025,6 +1054,10 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 for (int c0 = half * 32; c0 < L.n_pad; c0 += CSTEP) {
                     unsigned r[32];
                     tc_ld32(t_x + c0, r);
+                    if (io.group == 16) {
+                        tc_store_max16(r, bias, L.relu, rc.valid, rc.row, lane, c0, L.n_real, io.y, io.ldy);
+                        continue;
+                    }
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -1321,7 +1354,8 @@ PN_EXPORT int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
     PN_REQUIRE(xyz && new_xyz && idx && out, PN_ERR_BAD_ARG, "pn_sa_mlp_max_bf16x3: null pointer");
     PN_REQUIRE((feat != nullptr) == (D > 0) && desc->cin[0] == 3 + D, PN_ERR_BAD_ARG,
                "pn_sa_mlp_max_bf16x3: first layer expects %d channels, grouping provides 3 + %d", desc->cin[0], D);
-    PN_REQUIRE(K == 32, PN_ERR_UNSUPPORTED, "pn_sa_mlp_max_bf16x3: nsample must be 32 (got %d)", K);
+    PN_REQUIRE(K == 16 || K % 32 == 0 || out_mode == TC_OUT_ROWS, PN_ERR_UNSUPPORTED,
+               "pn_sa_mlp_bf16x3: nsample must be 16 or a multiple of 32 for the pooled output (got %d)", K);
     PN_REQUIRE(B > 0 && N > 0 && S > 0 && ldo >= desc->cout[desc->nlayers - 1], PN_ERR_BAD_ARG, "pn_sa_mlp_max_bf16x3: bad sizes");
     TcIo io = {};
     io.nseg = 1;
@@ -1333,7 +1367,7 @@ PN_EXPORT int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
     io.out_mode = out_mode;
     io.y = out;
     io.ldy = ldo;
-    io.group = K;
+    io.group = K == 16 ? 16 : 32;   // pooled output: one row per 16 / 32 grouped rows (K > 32: the caller reduces the K/32 partial rows)
     return tc_launch<TC_IN_SA>(ch, blob, io, (cudaStream_t)stream, "pn_sa_mlp_max_bf16x3");
 }
 

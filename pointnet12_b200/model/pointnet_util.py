@@ -235,6 +235,7 @@ class PointNetSetAbstraction(nn.Module):
     def features(self, xyz_pm, pts_pm, new_xyz, idx) -> torch.Tensor:
         """-> pooled [B,S,C'] point-major."""
         B, S, K = idx.shape
+        tc_ok = K == 16 or K % 32 == 0          # group sizes the fused kernel pools
         if K == 32 and len(self.mlp_convs) > 1 and B * S * K // 128 < ops.LAYERWISE_MAX_TILES:
             per_layer = self._folded.layer_chains(self.mlp_convs, self.mlp_bns, xyz_last=True)
             if per_layer is not None:
@@ -243,7 +244,7 @@ class PointNetSetAbstraction(nn.Module):
                 for c in per_layer[1:-1]:
                     rows = ops.mlp_rows_tc(c, rows)
                 return ops.mlp_rows_tc(per_layer[-1], rows, ops.OUT_MAX32).view(B, S, -1)
-        chain = self._folded.chain(self.mlp_convs, self.mlp_bns, xyz_last=True) if K == 32 else None
+        chain = self._folded.chain(self.mlp_convs, self.mlp_bns, xyz_last=True) if tc_ok else None
         if chain is not None:
             # one kernel: gather + recentre + concat -> tensor-core MLP chain -> max over the group
             # (weights packed with the xyz columns last, hence msg_order=True: aligned feature gathers)
@@ -302,7 +303,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         for i, radius in enumerate(self.radius_list):
             K = self.nsample_list[i]
             idx = ops.ball_query(radius, K, xyz_pm, new_xyz)
-            chain = self._folded[i].chain(self.conv_blocks[i], self.bn_blocks[i]) if K == 32 else None
+            chain = self._folded[i].chain(self.conv_blocks[i], self.bn_blocks[i]) if (K == 16 or K % 32 == 0) else None
             if chain is not None:
                 ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=True,
                                   out=out.view(B * S, -1)[:, col:col + widths[i]])

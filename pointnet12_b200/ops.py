@@ -518,6 +518,17 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
         D, fs = feat.shape[2], feat.stride()
     else:
         D, fs = 0, (0, 0, 0)
+    if out_mode != OUT_ROWS and K != 16 and K % 32:
+        raise ValueError(f"the fused set-abstraction kernel pools groups of 16 or 32 m samples, got nsample={K}")
+    if out_mode != OUT_ROWS and K > 32:
+        # the kernel pools runs of 32 rows; the K / 32 partial maxima of a group are reduced by pn_group_max_f32
+        part = torch.empty((B * S * (K // 32), chain.cout), dtype=torch.float32, device=xyz.device)
+        with _on_device(xyz):
+            nv.call("pn_sa_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), xyz.data_ptr(), *xyz.stride(), _p(feat),
+                    *fs, D, new_xyz.data_ptr(), *new_xyz.stride(), idx.data_ptr(), B, N, S, K, int(msg_order), int(out_mode),
+                    part.data_ptr(), chain.cout, _stream())
+        pooled = group_max(part, K // 32, out=out)
+        return pooled.view(B, S, chain.cout) if out is None else out
     if out_mode == OUT_ROWS:
         if out is not None:
             raise ValueError("out= is only supported with the max-pooled output")

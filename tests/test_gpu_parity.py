@@ -489,13 +489,15 @@ def test_mlp_rows_tc_max_and_log_softmax(dev, mlp_engine):
         assert rel_err(ops.mlp_rows_tc(chain, cuda(x, dev), ops.OUT_LOG_SOFTMAX), want) < TC_TOL
 
 
-@pytest.mark.parametrize("D,msg", [(1, False), (64, False), (128, True), (0, False)])
-def test_sa_mlp_max_tc_vs_oracle(dev, mlp_engine, D, msg):
-    """Fused grouping + MLP + max against the oracle's group -> linear x3 -> max."""
+@pytest.mark.parametrize("D,msg,K", [(1, False, 32), (64, False, 32), (128, True, 32), (0, False, 32), (0, True, 16),
+                                     (64, True, 64), (3, True, 128), (128, False, 16)])
+def test_sa_mlp_max_tc_vs_oracle(dev, mlp_engine, D, msg, K):
+    """Fused grouping + MLP + max against the oracle's group -> linear x3 -> max, for every group size of the
+    reference's networks (16 and 32 pooled in the kernel, 64 / 128 as partial maxima reduced afterwards)."""
     from pointnet12_b200 import ops
 
-    rng = np.random.default_rng(D + 7)
-    B, N, S, K = 3, 500, 40, 32
+    rng = np.random.default_rng(D + 7 + K)
+    B, N, S = 3, 500, 41
     xyz = rng.normal(size=(B, N, 3)).astype(np.float32)
     feat = rng.normal(size=(B, N, D)).astype(np.float32) if D else None
     q = np.ascontiguousarray(xyz[:, :S])
