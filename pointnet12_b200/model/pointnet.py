@@ -3,8 +3,9 @@
 Same class names, constructor arguments, submodule names (state_dict keys) and return values as the
 reference.  Everything is computed on point-major rows [B*N, C] by the C-ABI kernels:
 
-  * per-point conv chains          -> pn_linear_f32 (BatchNorm folded)
-  * max over points                -> pn_group_max_f32
+  * per-point conv chains + max    -> one tensor-core chain each (pn_mlp_rows_bf16x3, pooled in the kernel) +
+                                      pn_group_max_f32 over the partial rows; pn_linear_f32 (BatchNorm folded) in
+                                      fp32 mode, for layers wider than the chains take, and when N % 32 != 0
   * STN fully connected tail       -> pn_linear_f32 on [B, 1024] rows; the "+ identity" of
                                       pointnet.py:40-43 / 77-83 is folded into fc3's bias
   * torch.bmm(x, trans)            -> pn_linear_f32 with one weight matrix per cloud (w_bstride)
@@ -23,6 +24,19 @@ import torch.nn as nn
 
 from .. import ops
 from .pointnet_util import FoldedLayers, _eval_only
+
+
+def _chain_global_max(folded: FoldedLayers, convs, bns, relus, rows: torch.Tensor, B: int, N: int) -> Optional[torch.Tensor]:
+    """relu(bn(conv)) chain over the [B*N, C] rows followed by the max over the N points of each cloud, as ONE
+    tensor-core chain (pn_mlp_rows_bf16x3 pooling runs of 32 rows) + pn_group_max_f32 over the N/32 partial rows.
+    None when the tensor-core engine is off, the chain does not fit it, or N is not a multiple of 32."""
+    if N % 32:
+        return None
+    chain = folded.chain(convs, bns, relus)
+    if chain is None:
+        return None
+    part = ops.mlp_rows_tc(chain, rows, ops.OUT_MAX32)            # [B*N/32, C]
+    return ops.group_max(part, N // 32)                           # [B, C]
 
 
 def _point_rows(x_cm: torch.Tensor) -> torch.Tensor:
@@ -50,6 +64,7 @@ class _STN(nn.Module):
         self.bn5 = nn.BatchNorm1d(256)
         self.k = k
         self._folded = FoldedLayers()
+        self._folded_convs = FoldedLayers()
 
     def transform_rows(self, x_pm: torch.Tensor) -> torch.Tensor:
         """x_pm [B,N,k] point-major -> [B,k,k]."""
@@ -57,9 +72,13 @@ class _STN(nn.Module):
         layers = self._folded.get([self.conv1, self.conv2, self.conv3, self.fc1, self.fc2, self.fc3],
                                   [self.bn1, self.bn2, self.bn3, self.bn4, self.bn5, None])
         h = x_pm.reshape(B * N, k)
-        for w, b in layers[:3]:
-            h = ops.linear(h, w, b, relu=True)
-        g = ops.group_max(h, N)                                                   # [B,1024]
+        # conv1-3 + max over the points: one tensor-core chain (k -> 64 -> 128 -> 1024, pooled in the kernel)
+        g = _chain_global_max(self._folded_convs, [self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, self.bn3],
+                              [True, True, True], h, B, N)
+        if g is None:
+            for w, b in layers[:3]:
+                h = ops.linear(h, w, b, relu=True)
+            g = ops.group_max(h, N)                                               # [B,1024]
         g = ops.linear(g, *layers[3], relu=True)
         g = ops.linear(g, *layers[4], relu=True)
         w3, b3 = layers[5]
@@ -102,6 +121,7 @@ class PointNetEncoder(nn.Module):
         if self.feature_transform:
             self.fstn = STNkd(k=64)
         self._folded = FoldedLayers()
+        self._folded_tail = FoldedLayers()
 
     def encode_rows(self, x_pm: torch.Tensor):
         """x_pm [B,N,k] -> (global [B,1024], pointfeat [B,N,64], trans, trans_feat)."""
@@ -116,9 +136,14 @@ class PointNetEncoder(nn.Module):
             trans_feat = self.fstn.transform_rows(x)
             x = ops.bmm_points(x, trans_feat)                                     # pointnet.py:111-114
         pointfeat = x
-        h = ops.linear(x.view(B * N, 64), w2, b2, relu=True)
-        h = ops.linear(h, w3, b3, relu=False)                                     # bn3(conv3), no ReLU (:120)
-        return ops.group_max(h, N), pointfeat, trans, trans_feat
+        # relu(bn2(conv2)) -> bn3(conv3) (no ReLU, :120) -> max over the points: one tensor-core chain
+        g = _chain_global_max(self._folded_tail, [self.conv2, self.conv3], [self.bn2, self.bn3], [True, False],
+                              x.reshape(B * N, 64), B, N)
+        if g is None:
+            h = ops.linear(x.view(B * N, 64), w2, b2, relu=True)
+            h = ops.linear(h, w3, b3, relu=False)
+            g = ops.group_max(h, N)
+        return g, pointfeat, trans, trans_feat
 
     def forward(self, x):
         _eval_only(self)
@@ -170,6 +195,8 @@ class PointNetSeg(nn.Module):
         self.bn2 = nn.BatchNorm1d(256)
         self.bn3 = nn.BatchNorm1d(128)
         self._folded = FoldedLayers()
+        self._folded_c2 = FoldedLayers()
+        self._folded_tail = FoldedLayers()
 
     def forward(self, x):
         _eval_only(self)
@@ -180,9 +207,15 @@ class PointNetSeg(nn.Module):
         # conv1 on cat([global(1024) repeated, pointfeat(64)]): the global half is a per-cloud bias
         cloud_bias = ops.linear(g, w1[:, :1024].contiguous(), b1, relu=False)     # [B,512]
         h = ops.linear_cloud_bias(pointfeat, w1[:, 1024:].contiguous(), cloud_bias, relu=True).view(B * N, 512)
-        h = ops.linear(h, w2, b2, relu=True)
-        h = ops.linear(h, w3, b3, relu=True)
-        logp = ops.log_softmax(ops.linear(h, w4, b4, relu=False))
+        # conv2 (512 -> 256) as a single-layer tensor-core chain, conv3 -> conv4 -> log_softmax as one more
+        c2 = self._folded_c2.chain([self.conv2], [self.bn2], [True])
+        tail = self._folded_tail.chain([self.conv3, self.conv4], [self.bn3, None], [True, False])
+        if c2 is not None and tail is not None:
+            logp = ops.mlp_rows_tc(tail, ops.mlp_rows_tc(c2, h), ops.OUT_LOG_SOFTMAX)
+        else:
+            h = ops.linear(h, w2, b2, relu=True)
+            h = ops.linear(h, w3, b3, relu=True)
+            logp = ops.log_softmax(ops.linear(h, w4, b4, relu=False))
         return logp.view(B, N, self.k), trans_feat
 
 

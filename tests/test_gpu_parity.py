@@ -857,7 +857,9 @@ def _seeded(net, seed, dev):
     return net.to(dev).eval()
 
 
-def test_pointnet_seg_golden(dev, golden):
+def test_pointnet_seg_golden(dev, golden, mlp_mode):
+    """PointNetSeg (config C1) on both engines: tensor-core chains for the STN / encoder conv stacks (pooled in the
+    kernel) and the seg-head tail, and the exact-fp32 CUDA-core path."""
     from pointnet12_b200.model.pointnet import PointNetSeg
 
     g = golden("pointnet_seg_seed1234")
