@@ -810,6 +810,26 @@ def test_bf16_precision_stated_tolerance(dev, ckpt_path, ckpt_state):
     assert ((top2[..., 1] - top2[..., 0])[flipped] < 0.3).all()
 
 
+@pytest.mark.parametrize("B,N", [(3, 5000), (1, 4097), (2, 3000), (5, 9999)])
+def test_pointnet2_semseg_ragged_shapes(dev, ckpt_state, ckpt_path, B, N):
+    """Whole-network parity at awkward sizes: clouds that do not fill the last 128-row tile, odd batch sizes, N just
+    above / below the grid threshold (bucket order, streamed ball query, block 3-NN and the folded fp1 layer all see
+    ragged tails)."""
+    from pointnet12_b200.model.utils import load_pointnet
+
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    pts = syn.kitti_batch(B, N, config=14)
+    st = starts([N, 1024, 256, 64], B, seed=N)
+    want = orc.pointnet2_semseg(ckpt_state, pts, [s.numpy() for s in st])
+    with torch.no_grad():
+        got = net(cuda(pts, dev), fps_starts=[s.to(dev) for s in st]).cpu().numpy()
+    assert got.shape == (B, N, 19)
+    assert rel_err(got, want) < LOGP_TOL
+    top2 = np.sort(want, -1)[..., -2:]
+    sure = (top2[..., 1] - top2[..., 0]) > 2e-3
+    assert np.array_equal(got.argmax(-1)[sure], want.argmax(-1)[sure])
+
+
 def test_graph_replay_matches_eager(dev, ckpt_path):
     """GraphedSemSeg (CUDA-graph replay, 3 streams) gives bit-identical log-probs to the eager forward."""
     from pointnet12_b200.model.utils import load_pointnet
