@@ -109,7 +109,8 @@ int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC,
  * one 8-byte word per centroid, index << 32 | 1).  pn_ball_query_stream_f32, launched on ANOTHER stream once the grid
  * is built, runs `ctas` persistent CTAs (a multiple of B; the caller sizes it to the SMs sampling leaves idle, see
  * pn_fps_launch_info, and passes min_smem_bytes so large that a CTA cannot share an SM with a sampling CTA), polls
- * the feed and writes out_idx rows plus done[b, s] = 1 as centroids appear.  A CTA whose wait exceeds 3 ms gives up.
+ * the feed and writes out_idx rows plus done[b, s] = 1 as centroids appear, for the centroids s < s_end (the last few
+ * are better left to the follow-up kernel, which has the whole GPU).  A CTA whose wait exceeds 3 ms gives up.
  * The caller then runs pn_ball_query_grid_f32 with the same `done` array after sampling: it computes whatever is
  * not done -- normally nothing -- so the result never depends on the two kernels having run side by side.
  * Limits: N <= 32768. */
@@ -118,7 +119,7 @@ int pn_fps_progress_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, in
 /* Launch shape pn_fps_f32 would use for (B, N, npoint): CTAs in the grid and dynamic shared memory per CTA. */
 int pn_fps_launch_info(int B, int N, int npoint, int* ctas, size_t* smem_bytes);
 int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const uint64_t* progress, int B, int N,
-                             int S, float radius2, int nsample, const void* grid, size_t grid_bytes, int ctas,
+                             int S, int s_end, float radius2, int nsample, const void* grid, size_t grid_bytes, int ctas,
                              size_t min_smem_bytes, int32_t* done, int64_t* out_idx, pn_stream_t stream);
 
 /* index_points (model/pointnet_util.py:43-60): out[b,m,:] = points[b, idx[b,m], :].

@@ -355,7 +355,7 @@ ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, in
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 ball_query_stream_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC,
-                         const unsigned long long* __restrict__ seq, int B, int N, int S, float radius2, int K,
+                         const unsigned long long* __restrict__ seq, int B, int N, int S, int s_end, float radius2, int K,
                          const unsigned char* __restrict__ ws_all, size_t ws_stride, int threshold, int bm_words,
                          long long timeout_ns, int* __restrict__ done, int64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char gq_smem[];
@@ -364,9 +364,11 @@ ball_query_stream_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, 
     const int per_cloud = gridDim.x / B;           // CTAs serving this cloud (the host launches a multiple of B)
     if ((int)blockIdx.x >= per_cloud * B) return;
     const float* __restrict__ p = xyz + (int64_t)b * xB;
-    for (int s0 = (blockIdx.x / B) * WARPS; s0 < S; s0 += per_cloud * WARPS) {
+    // centroids [s_end, S) are left to the follow-up kernel: the last few appear when sampling ends, and the whole GPU
+    // answers them faster than the few CTAs of this grid
+    for (int s0 = (blockIdx.x / B) * WARPS; s0 < s_end; s0 += per_cloud * WARPS) {
         const int s = s0 + warp;
-        const bool valid = s < S;
+        const bool valid = s < s_end;
         float ax = 0.f, ay = 0.f, az = 0.f;
         bool gave_up = false;
         if (valid) {
@@ -494,8 +496,8 @@ static int gq_auto_threshold(int N) {
 }
 
 PN_EXPORT int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const uint64_t* progress, int B, int N,
-                                       int S, float radius2, int nsample, const void* grid_ws, size_t grid_bytes, int ctas,
-                                       size_t min_smem_bytes, int32_t* done, int64_t* out_idx, pn_stream_t stream) {
+                                       int S, int s_end, float radius2, int nsample, const void* grid_ws, size_t grid_bytes,
+                                       int ctas, size_t min_smem_bytes, int32_t* done, int64_t* out_idx, pn_stream_t stream) {
     using namespace pn;
     PN_REQUIRE(xyz && progress && grid_ws && done && out_idx, PN_ERR_BAD_ARG, "pn_ball_query_stream_f32: null pointer");
     PN_REQUIRE(B > 0 && N > 0 && S > 0 && nsample > 0, PN_ERR_BAD_ARG, "pn_ball_query_stream_f32: sizes must be positive");
@@ -515,8 +517,9 @@ PN_EXPORT int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN,
         set_error("pn_ball_query_stream_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return (int)e;
     }
+    PN_REQUIRE(s_end >= 0 && s_end <= S, PN_ERR_BAD_ARG, "pn_ball_query_stream_f32: s_end=%d outside [0, S=%d]", s_end, S);
     kern<<<ctas, 256, smem, (cudaStream_t)stream>>>(xyz, xB, xN, xC, reinterpret_cast<const unsigned long long*>(progress), B, N, S,
-                                                    radius2, nsample, static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N),
+                                                    s_end, radius2, nsample, static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N),
                                                     gq_auto_threshold(N), bm_words, 3000000LL, done, out_idx);
     return finish_launch("pn_ball_query_stream_f32");
 }

@@ -116,19 +116,24 @@ def fps_launch_info(B: int, N: int, npoint: int) -> Tuple[int, int]:
     return ctas.value, smem.value
 
 
+HOST_OUT_SLICES = int(os.environ.get("PN12_HOST_OUT_SLICES", "8"))   # batch slices of the last level when the output goes to the host
 STREAM_BALL_QUERY = os.environ.get("PN12_STREAM_BALL", "1") != "0"
 STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for the streamed ball query to be worth it
 
 
+STREAM_BALL_TAIL = int(os.environ.get("PN12_STREAM_BALL_TAIL", "0"))    # last centroids per cloud left to the follow-up query (measured at C2: 0 is best, 0.891 vs 0.905-0.918 ms with 16..128)
+
+
 def ball_query_stream(radius: float, nsample: int, xyz: torch.Tensor, grid: "BallGrid", progress: torch.Tensor,
-                      done: torch.Tensor, out: torch.Tensor, ctas: int, min_smem: int) -> None:
+                      done: torch.Tensor, out: torch.Tensor, ctas: int, min_smem: int, tail: Optional[int] = None) -> None:
     """Answers the ball queries of the centroids a RUNNING fps(..., progress=...) publishes (pn_ball_query_stream_f32);
     call it on another stream than the sampling.  done int32 [B, S] (zeroed), out int64 [B, S, nsample]."""
     xyz = _cloud(xyz, "xyz", 3)
     B, N, _ = xyz.shape
     S = progress.shape[1]
     with _on_device(xyz):
-        nv.call("pn_ball_query_stream_f32", xyz.data_ptr(), *xyz.stride(), progress.data_ptr(), B, N, S, float(radius ** 2),
+        s_end = max(0, S - (STREAM_BALL_TAIL if tail is None else int(tail)))
+        nv.call("pn_ball_query_stream_f32", xyz.data_ptr(), *xyz.stride(), progress.data_ptr(), B, N, S, s_end, float(radius ** 2),
                 int(nsample), grid.buf.data_ptr(), grid.nbytes, int(ctas), int(min_smem), done.data_ptr(), out.data_ptr(),
                 _stream())
 
