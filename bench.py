@@ -38,6 +38,7 @@ CKPT = os.path.join(ROOT, "tests", "golden", "pointnet2-inview-0.55884-0001.pth"
 BATCH, NPOINTS, CLASSES = 8, 24000, 19
 LEVEL_N = (24000, 1024, 256, 64)
 METRIC = "pointnet2_semseg_forward_points_per_sec"
+FPS_DRAM_BYTES_PER_LAUNCH = 2337024   # ncu: 2.34 MB read + 0 written per level-1 launch (the cloud lives in registers)
 FPS_ENTRY_POINTS = ["pn_fps_f32", "pn_fps_progress_f32"]   # the same kernel with / without the progress feed
 WORKLOAD = "C2: PointNet2SemSeg(19, feature_dims=1) eval forward, pointnet2-inview checkpoint, 8 synthetic KITTI-shaped clouds x 24000 points per GPU"
 
@@ -284,8 +285,8 @@ def run_ours(args):
                                      "bf16": "bf16: tcgen05 tensor cores, single pass (max |delta log-prob| 0.38, 99.6 % equal "
                                              "labels at this config)",
                                      "fp32": "fp32 FMA on CUDA cores"}[ops.mlp_precision()],
-                       "launch": ("one CUDA-graph replay per step (3 streams forked/joined inside the graph)"
-                                  if runner is not None else "eager launches on 3 streams"),
+                       "launch": ("one CUDA-graph replay per step (5 internal streams forked/joined inside the graph)"
+                                  if runner is not None else "eager launches on 5 internal streams"),
                        "l2": "512 MiB written between timed steps",
                        "fps_start": "torch.randint on the CPU generator per level, as the reference draws it"},
             "e2e": {"value": points / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
@@ -293,10 +294,14 @@ def run_ours(args):
                     "d2h_bytes_per_step": BATCH * NPOINTS * CLASSES * 4},
             "gpu_launches": launches,
             "step_ms": {"min": spread[0], "median": spread[len(spread) // 2], "max": spread[-1]},
-            "roofline": {"kernel": "pn_fps_f32 (fps_kernel, level 1: N=24000 -> 1024 centroids)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"kernel": "fps_async_kernel<4,24,true> (pn_fps_progress_f32, level 1: N=24000 -> 1024 centroids)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": FPS_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                           "(profiles/r01_v11_ncu_full_summary.csv)",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": fps_bytes,
-                         "launch_ms": fps_ms, "share_of_step": all_fps_ms / (ms / args.steps),
+                         "launch_ms": fps_ms, "share_of_step": fps_ms / (ms / args.steps),
+                         "all_fps_levels_ms_per_step": all_fps_ms,
                          "timing": ("CUDA events around the launch, eager pass over the same steps right after the timed "
                                     "graph replays" if runner is not None else "CUDA events around the launch inside the timed steps"),
                          "note": "coordinates and running distances are register-resident, so DRAM traffic is ~0; "

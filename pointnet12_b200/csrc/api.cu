@@ -22,7 +22,7 @@ PN_EXPORT int pn_set_pdl(int enabled) {
     return PN_OK;
 }
 
-PN_EXPORT int pn_version(void) { return 100; /* 0.1.0 */ }
+PN_EXPORT int pn_version(void) { return 200; /* 0.2.0 */ }
 
 PN_EXPORT const char* pn_last_error_string(void) { return pn::g_err; }
 
