@@ -309,7 +309,7 @@ class PointNet2SemSeg(_Net):
                 fp[0].fold_first_layer(up, head)
             main.wait_event(done_big)
             if host_out is None or ops.mlp_mode() != "bf16x3":
-                logp = fp[0].features(None, up, *nns[0], head=head, order=grid1)
+                logp = fp[0].features(None, up, *nns[0], head=head, order=grid1 if ops.FP1_BUCKET_ORDER else None)
                 if host_out is not None:
                     host_out.copy_(logp, non_blocking=True)
             else:
@@ -322,7 +322,7 @@ class PointNet2SemSeg(_Net):
                 for b0, b1 in zip(cuts[:-1], cuts[1:]):
                     if b0 == b1:
                         continue
-                    fp[0].features(None, up, *nns[0], head=head, order=grid1, out=logp, clouds=(b0, b1))
+                    fp[0].features(None, up, *nns[0], head=head, order=grid1 if ops.FP1_BUCKET_ORDER else None, out=logp, clouds=(b0, b1))
                     part = torch.cuda.Event()
                     part.record(main)
                     with torch.cuda.stream(copier):

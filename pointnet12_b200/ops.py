@@ -116,6 +116,7 @@ def fps_launch_info(B: int, N: int, npoint: int) -> Tuple[int, int]:
     return ctas.value, smem.value
 
 
+FP1_BUCKET_ORDER = os.environ.get("PN12_FP1_ORDER", "0") != "0"   # fp1 walks the fine points in bucket order (helped the row-per-thread gather: 195 -> 183 us; with the quad producer it costs 0.6 %: scattered index / output rows)
 HOST_OUT_SLICES = int(os.environ.get("PN12_HOST_OUT_SLICES", "8"))   # batch slices of the last level when the output goes to the host
 STREAM_BALL_QUERY = os.environ.get("PN12_STREAM_BALL", "1") != "0"
 STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for the streamed ball query to be worth it
