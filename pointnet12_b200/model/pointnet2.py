@@ -299,14 +299,20 @@ class PointNet2SemSeg(_Net):
                         done_big = torch.cuda.Event()
                         done_big.record(nn_big)
             main.wait_event(done_small)
-            up = fs[4]
-            for i in (3, 2, 1):
-                up = fp[i].features(fs[i], up, *nns[i])
-            # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs;
-            # its first layer runs on the 1024 coarse points and needs no neighbours: issued before the 3-NN wait
+            # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs.  Its
+            # first layer acts on the 1024 coarse points (interpolation commutes with it): it is appended to fp2's chain,
+            # whose output rows are exactly those points, so fp2 hands over z = W1 * l1_features + b1 directly.
             head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
-            if ops.FOLD_FIRST_FP_LAYER:
-                fp[0].fold_first_layer(up, head)
+            first = fp[0].first_layer_spec(head) if ops.mlp_mode() == "bf16x3" else None
+            up = fs[4]
+            for i in (3, 2):
+                up = fp[i].features(fs[i], up, *nns[i])
+            if first is not None:
+                fp2z = (self.__dict__.setdefault("_fp2z", FoldedLayers()), [first[0]], [first[1]], [False], ops.OUT_ROWS)
+                up = fp[1].features(fs[1], up, *nns[1], head=fp2z)       # = z
+                fp[0].adopt_folded(up, head)
+            else:
+                up = fp[1].features(fs[1], up, *nns[1])
             main.wait_event(done_big)
             if host_out is None or ops.mlp_mode() != "bf16x3":
                 logp = fp[0].features(None, up, *nns[0], head=head, order=grid1 if ops.FP1_BUCKET_ORDER else None)

@@ -361,6 +361,32 @@ class PointNetFeaturePropagation(nn.Module):
         self._z_cache = (p2, rest, z)
         return rest, z
 
+    def first_layer_spec(self, head=None):
+        """(conv, bn) of this level's first layer if `features` would fold it into the coarse level (no skip input,
+        tensor-core engine, chains supported), else None.  A network can then append that layer to the chain of the
+        level that PRODUCES the coarse features and hand the result over with `adopt_folded` -- one launch less."""
+        if not ops.FOLD_FIRST_FP_LAYER:
+            return None
+        convs, bns, relus = list(self.mlp_convs), list(self.mlp_bns), [True] * len(self.mlp_convs)
+        folded = self._folded
+        if head is not None:
+            folded, hconvs, hbns, hrelus, _ = head
+            convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
+        if folded.chain_folded_first(convs, bns, relus) is None:
+            return None
+        return self.mlp_convs[0], self.mlp_bns[0]
+
+    def adopt_folded(self, z: torch.Tensor, head=None) -> None:
+        """z [B,S,C1] = this level's first layer (BatchNorm folded, no activation) already applied to the coarse
+        features by the caller.  `features(None, z, ...)` then starts from relu(interp(z))."""
+        convs, bns, relus = list(self.mlp_convs), list(self.mlp_bns), [True] * len(self.mlp_convs)
+        folded = self._folded
+        if head is not None:
+            folded, hconvs, hbns, hrelus, _ = head
+            convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
+        _, rest = folded.chain_folded_first(convs, bns, relus)
+        self._z_cache = (z, rest, z)
+
     def features(self, p1, p2, idx, w, head=None, order=None, out=None, clouds=None) -> torch.Tensor:
         """p1 [B,N,D1] or None, p2 [B,S,D2] point-major -> [B,N,D'] point-major.
         `head`: (FoldedLayers, convs, bns, relus, out_mode) appended by a network: the segmentation head runs
