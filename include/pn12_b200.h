@@ -245,11 +245,16 @@ int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz
  * points (pn_mlp_rows_bf16x3, no ReLU), passes the result as points2 and drops the layer from the chain.
  * order (may be NULL): a permutation of the N points of every cloud -- tile row r of cloud b handles point
  * order[b*order_bs + r*order_es] (strides in int32 elements).  The result is the same; with a spatially sorted order
- * (pn_ball_grid_order) the rows of a warp share their three coarse neighbours and the gather hits in L1. */
+ * (pn_ball_grid_order) the rows of a warp share their three coarse neighbours and the gather hits in L1.
+ * residual (may be NULL; chains of >= 2 layers): rows [B*N, ldr] added to the FIRST layer's pre-activation.  This is how
+ * a caller takes the skip half of that layer off the critical path -- W [p1 ; interp] = W_a p1 + W_b interp: it computes
+ * W_a p1 early (pn_mlp_rows_bf16x3, no bias, no ReLU; ldr = cout[0] rounded up to 32, 16-byte aligned), passes points1 =
+ * NULL, D1 = 0 and a chain whose first layer holds only W_b. */
 int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
                      int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2, int S,
                      const int64_t* idx, const float* weight, int relu_in, const int32_t* order, int64_t order_es,
-                     int64_t order_bs, int B, int N, int out_mode, float* out, int64_t ldo, pn_stream_t stream);
+                     int64_t order_bs, const float* residual, int64_t ldr, int B, int N, int out_mode, float* out,
+                     int64_t ldo, pn_stream_t stream);
 
 /* Tuning hook for the fused chains: 0 = automatic (chains whose packed weights fit in shared memory run on the
  * resident-weight kernel: weights loaded once per CTA, 2 or 4 warp groups per CTA each with its own row tile

@@ -62,8 +62,8 @@ _SIGNATURES = {
                              i32, i32, vp, i64, vp],
     "pn_sa_mlp_bf16x3": [_descp, vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32,
                          i32, i32, i32, vp, i64, vp],
-    "pn_fp_mlp_bf16x3": [_descp, vp, vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, vp, i64, i64, i32,
-                         i32, i32, vp, i64, vp],
+    "pn_fp_mlp_bf16x3": [_descp, vp, vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, vp, i64, i64, vp,
+                         i64, i32, i32, i32, vp, i64, vp],
     "pn_ball_grid_order": [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)],
     "pn_mlp_set_engine": [i32],
     "pn_mlp_set_debug": [vp],

@@ -254,6 +254,7 @@ struct TcIo {
     int relu_in;   // TC_IN_FP: ReLU applied to the interpolated channels (layer 1 was folded into the coarse level)
     // output
     int out_mode; float* y; int64_t ldy; int group;
+    const float* res; int64_t ldr;   // optional per-row term added to layer 0's pre-activation: res[row * ldr + channel]
     int quad_fp;      // TC_IN_FP: all channel runs are float4-addressable -> coalesced quad producer (fp_quad_producer)
     long long* dbg;   // optional timeline (pn_mlp_set_debug): CTA 0 records clock64() per phase
 };
@@ -751,6 +752,17 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                         unsigned r[32];
                         tc_ld32(t_x + c0, r);
                         float v[32];
+                        if (l == 0 && io.res != nullptr) {   // the skip half of the layer, computed beforehand per row
+                            const float4* rr = reinterpret_cast<const float4*>(io.res + (rc.valid ? rc.row : 0) * io.ldr + n0 + c0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = rr[j];
+                                r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + t.x);
+                                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + t.y);
+                                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + t.z);
+                                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t.w);
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float f = __uint_as_float(r[j]) + bias[c0 + j];
@@ -1011,6 +1023,17 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                     unsigned r[32];
                     tc_ld32(t_x + c0, r);
                     float v[32];
+                    if (l == 0 && io.res != nullptr) {   // the skip half of the layer, computed beforehand per row
+                        const float4* rr = reinterpret_cast<const float4*>(io.res + (rc.valid ? rc.row : 0) * io.ldr + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = rr[j];
+                            r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + t.x);
+                            r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + t.y);
+                            r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + t.z);
+                            r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t.w);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float f = __uint_as_float(r[j]) + bias[c0 + j];
@@ -1374,8 +1397,8 @@ PN_EXPORT int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
 PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
                                int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2,
                                int S, const int64_t* idx, const float* weight, int relu_in, const int32_t* order,
-                               int64_t order_es, int64_t order_bs, int B, int N, int out_mode, float* out, int64_t ldo,
-                               pn_stream_t stream) {
+                               int64_t order_es, int64_t order_bs, const float* residual, int64_t ldr, int B, int N,
+                               int out_mode, float* out, int64_t ldo, pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
     int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_fp_mlp_bf16x3");
@@ -1385,6 +1408,10 @@ PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
                "pn_fp_mlp_bf16x3: first layer expects %d channels, inputs provide %d + %d", desc->cin[0], D1, D2);
     PN_REQUIRE(out_mode != TC_OUT_MAX, PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: out_mode must be 0 (rows) or 2 (log_softmax)");
     PN_REQUIRE(!relu_in || D1 == 0, PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: relu_in needs points1 == NULL");
+    PN_REQUIRE(residual == nullptr || (desc->nlayers >= 2 && !relu_in && ((uintptr_t)residual & 15) == 0 && (ldr % 4) == 0 &&
+                                       ldr >= ((desc->cout[0] + 31) / 32) * 32),
+               PN_ERR_BAD_ARG,
+               "pn_fp_mlp_bf16x3: residual needs a chain of >= 2 layers, 16-byte aligned rows and ldr >= cout[0] rounded up to 32");
     PN_REQUIRE(B > 0 && N > 0 && S > 0 && ldo >= desc->cout[desc->nlayers - 1], PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: bad sizes");
     TcIo io = {};
     io.nseg = B;
@@ -1394,6 +1421,7 @@ PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
     io.idx3 = idx; io.w3 = weight;
     io.relu_in = relu_in;
     io.order = order; io.order_es = order_es; io.order_bs = order_bs;
+    io.res = residual; io.ldr = ldr;
     {
         auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
         bool ok = p2C == 1 && (p2N % 4) == 0 && (p2B % 4) == 0 && (D2 % 4) == 0 && al16(points2);

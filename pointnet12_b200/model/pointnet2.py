@@ -206,7 +206,7 @@ class PointNet2SemSeg(_Net):
         # (= lower) priority on two more streams and fill whatever the critical path leaves idle instead of competing
         # with it: the big one (24000 x 1024 per cloud, for fp1) on its own stream, released after sa2.
         user = torch.cuda.current_stream(points.device)
-        main, geo, nn_small, nn_big, feed = self._side_streams(points.device)
+        main, geo, nn_small, nn_big, feed, ahead = self._side_streams(points.device)
         begin = torch.cuda.Event()
         begin.record(user)
         main.wait_event(begin)
@@ -273,6 +273,27 @@ class PointNet2SemSeg(_Net):
                 balls[0] = ops.ball_query(sa[0].radius, K1, x0, x1, grid=grid1, done=streamed["done"], out=streamed["out"])
             else:
                 balls[0] = ops.ball_query(sa[0].radius, K1, x0, x1, grid=grid1)
+            # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs.  Its
+            # first layer acts on the 1024 coarse points (interpolation commutes with it): it is appended to fp2's chain,
+            # whose output rows are exactly those points, so fp2 hands over z = W1 * l1_features + b1 directly.
+            head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
+            first = fp[0].first_layer_spec(head) if ops.mlp_mode() == "bf16x3" else None
+            fp2z = None
+            if first is not None:
+                fp2z = (self.__dict__.setdefault("_fp2z", FoldedLayers()), [first[0]], [first[1]], [False], ops.OUT_ROWS)
+            skipped = [None] * 4
+
+            def skip_ahead(i):
+                # the skip half of fp[i]'s first layer depends on the encoder feature fs[i] only: computed on a side
+                # stream as soon as that level exists, while the encoder goes on
+                made = torch.cuda.Event()
+                made.record(main)
+                with torch.cuda.stream(ahead):
+                    ahead.wait_event(made)
+                    if fp[i].skip_ahead(fs[i], fp2z if i == 1 else None):
+                        skipped[i] = torch.cuda.Event()
+                        skipped[i].record(ahead)
+
             # sa1 / sa2 run one persistent CTA per SM while level 2-4 sampling holds a few SMs: leave those out
             ops.set_reserved_sms(ops.fps_launch_info(B, S1, sa[1].npoint)[0])
             try:
@@ -281,10 +302,14 @@ class PointNet2SemSeg(_Net):
                 fs.append(sa[1].features(xs[1], fs[1], xs[2], balls[1]))
             finally:
                 ops.set_reserved_sms(0)
+            skip_ahead(1)
+            skip_ahead(2)
             for i in (1, 2, 3):
                 if i > 1:
                     main.wait_event(ready[i])
                     fs.append(sa[i].features(xs[i], fs[i], xs[i + 1], balls[i]))
+                    if i == 2:
+                        skip_ahead(3)
                 if i == 1:
                     # fp1's 3-NN search (24000 x 1024 per cloud) fills the GPU with long-lived CTAs, which stream
                     # priorities cannot displace: it is released only now, when the wide kernels of the critical path
@@ -299,16 +324,14 @@ class PointNet2SemSeg(_Net):
                         done_big = torch.cuda.Event()
                         done_big.record(nn_big)
             main.wait_event(done_small)
-            # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs.  Its
-            # first layer acts on the 1024 coarse points (interpolation commutes with it): it is appended to fp2's chain,
-            # whose output rows are exactly those points, so fp2 hands over z = W1 * l1_features + b1 directly.
-            head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
-            first = fp[0].first_layer_spec(head) if ops.mlp_mode() == "bf16x3" else None
             up = fs[4]
             for i in (3, 2):
+                if skipped[i] is not None:
+                    main.wait_event(skipped[i])
                 up = fp[i].features(fs[i], up, *nns[i])
-            if first is not None:
-                fp2z = (self.__dict__.setdefault("_fp2z", FoldedLayers()), [first[0]], [first[1]], [False], ops.OUT_ROWS)
+            if skipped[1] is not None:
+                main.wait_event(skipped[1])
+            if fp2z is not None:
                 up = fp[1].features(fs[1], up, *nns[1], head=fp2z)       # = z
                 fp[0].adopt_folded(up, head)
             else:
@@ -355,5 +378,5 @@ class PointNet2SemSeg(_Net):
             lo, hi = max(rng), min(rng)
             streams[key] = (torch.cuda.Stream(device, priority=hi), torch.cuda.Stream(device, priority=hi),
                             torch.cuda.Stream(device, priority=lo), torch.cuda.Stream(device, priority=lo),
-                            torch.cuda.Stream(device, priority=hi))
+                            torch.cuda.Stream(device, priority=hi), torch.cuda.Stream(device, priority=lo))
         return streams[key]

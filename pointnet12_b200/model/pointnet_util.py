@@ -175,6 +175,26 @@ class FoldedLayers:
             self._per_layer_key = self._layers
         return self._per_layer or None
 
+    def chain_skip_split(self, convs, bns, relus, d1: int):
+        """(skip, rest) for a feature-propagation level with skip input: the first layer's weight is cut at column d1 --
+        `skip` = W[:, :d1] alone (no bias, no activation: applied to the skip features ahead of time), `rest` = the chain
+        with W[:, d1:] as its first layer (the interpolated half; the kernel adds the skip term before the activation).
+        None when the mode is 'fp32', the chain is a single layer or a part does not fit."""
+        if ops.mlp_mode() != "bf16x3" or len(convs) < 2:
+            return None
+        layers = self.get(convs, bns)
+        if getattr(self, "_skip_split", None) is None or self._skip_split_key is not self._layers:
+            (w0, b0), rest = layers[0], layers[1:]
+            dims_b = [(w0.shape[1] - d1, w0.shape[0])] + [(w.shape[1], w.shape[0]) for w, _ in rest]
+            if not (0 < d1 < w0.shape[1] and ops.PackedChain.supported([(d1, w0.shape[0])]) and ops.PackedChain.supported(dims_b)):
+                self._skip_split = False
+            else:
+                self._skip_split = (ops.PackedChain([(w0[:, :d1].contiguous(), None, False)]),
+                                    ops.PackedChain([(w0[:, d1:].contiguous(), b0, relus[0])] +
+                                                    [(w, b, r) for (w, b), r in zip(rest, relus[1:])]))
+            self._skip_split_key = self._layers
+        return self._skip_split or None
+
     def chain_folded_first(self, convs, bns, relus):
         """(first, rest): the first layer as a one-layer chain WITHOUT activation and the remaining layers, for a
         feature-propagation level without skip input: conv(interp(p2)) + b == interp(conv(p2) + b) because the
@@ -387,6 +407,29 @@ class PointNetFeaturePropagation(nn.Module):
         _, rest = folded.chain_folded_first(convs, bns, relus)
         self._z_cache = (z, rest, z)
 
+    def skip_ahead(self, p1: torch.Tensor, head=None) -> bool:
+        """Computes the skip half of the first layer, W[:, :D1] p1, for the skip features p1 [B,N,D1] NOW (on the current
+        stream) and keeps it for the next `features(p1, ...)` call with the same tensor, which then only interpolates,
+        multiplies the other half and adds this term.  A network calls it on a side stream as soon as p1 exists, long
+        before the coarse features arrive.  Returns False when the level cannot be split (then features() is unchanged)."""
+        if not ops.FP_SKIP_AHEAD:
+            return False
+        convs, bns, relus = list(self.mlp_convs), list(self.mlp_bns), [True] * len(self.mlp_convs)
+        folded = self._folded
+        if head is not None:
+            folded, hconvs, hbns, hrelus, _ = head
+            convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
+        B, N, D1 = p1.shape
+        split = folded.chain_skip_split(convs, bns, relus, D1)
+        if split is None:
+            return False
+        skip, rest = split
+        width = (skip.cout + 31) // 32 * 32
+        term = torch.zeros((B, N, width), dtype=torch.float32, device=p1.device)
+        ops.mlp_rows_tc(skip, p1.reshape(B * N, D1), out=term.view(B * N, width)[:, :skip.cout])
+        self._skip_cache = (p1, rest, term)
+        return True
+
     def features(self, p1, p2, idx, w, head=None, order=None, out=None, clouds=None) -> torch.Tensor:
         """p1 [B,N,D1] or None, p2 [B,S,D2] point-major -> [B,N,D'] point-major.
         `head`: (FoldedLayers, convs, bns, relus, out_mode) appended by a network: the segmentation head runs
@@ -400,6 +443,12 @@ class PointNetFeaturePropagation(nn.Module):
         if head is not None:
             folded, hconvs, hbns, hrelus, out_mode = head
             convs, bns, relus = convs + hconvs, bns + hbns, relus + hrelus
+        ahead = getattr(self, "_skip_cache", None)
+        if ahead is not None:
+            self._skip_cache = None
+            if ahead[0] is p1 and out is None and clouds is None:
+                # the skip half of the first layer was computed ahead of time: interpolate, multiply the other half, add it
+                return ops.fp_mlp_tc(ahead[1], None, p2, idx, w, out_mode, order=order, residual=ahead[2])
         if p1 is None and ops.FOLD_FIRST_FP_LAYER and N > p2.shape[1]:
             folded_first = self.fold_first_layer(p2, head)
             if folded_first is not None:

@@ -116,6 +116,10 @@ def fps_launch_info(B: int, N: int, npoint: int) -> Tuple[int, int]:
     return ctas.value, smem.value
 
 
+# Skip half of an FP level's first layer computed early on a side stream (PointNetFeaturePropagation.skip_ahead).  Measured at
+# C2: fp4 40 -> 35, fp3 34 -> 31 us, but the three extra launches contend with sa3 / sa4 and the step got 15 us SLOWER
+# (0.890 vs 0.875 ms), so it is off by default.
+FP_SKIP_AHEAD = os.environ.get("PN12_FP_SKIP_AHEAD", "0") != "0"
 FP1_BUCKET_ORDER = os.environ.get("PN12_FP1_ORDER", "0") != "0"   # fp1 walks the fine points in bucket order (helped the row-per-thread gather: 195 -> 183 us; with the quad producer it costs 0.6 %: scattered index / output rows)
 HOST_OUT_SLICES = int(os.environ.get("PN12_HOST_OUT_SLICES", "8"))   # batch slices of the last level when the output goes to the host
 STREAM_BALL_QUERY = os.environ.get("PN12_STREAM_BALL", "1") != "0"
@@ -557,12 +561,14 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
 def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torch.Tensor, idx: torch.Tensor,
               weight: torch.Tensor, out_mode: int = OUT_ROWS, relu_in: bool = False,
               order: Optional[BallGrid] = None, out: Optional[torch.Tensor] = None,
-              clouds: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+              clouds: Optional[Tuple[int, int]] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """3-NN interpolation + skip concat + shared MLP (+ head + log_softmax) in one kernel -> [B, N, cout].
     relu_in: ReLU on the interpolated channels first (the level's first layer was folded into the coarse level).
     order: a BallGrid of the fine cloud -- tiles then walk the points in bucket order (same result, L1-friendly).
     out: a contiguous [B, N, cout] float32 buffer to write into; clouds = (b0, b1): only that slice of the batch is
-    computed (into out[b0:b1]) -- a caller can then start moving the first clouds while the rest are computed."""
+    computed (into out[b0:b1]) -- a caller can then start moving the first clouds while the rest are computed.
+    residual: [B, N, C] rows (C = first layer's width rounded up to 32) added to the first layer's pre-activation: the
+    skip half of that layer, computed by the caller beforehand (then points1 is None and the chain holds only W_b)."""
     points2 = _cloud(points2, "points2")
     idx = _i64(idx, "idx")
     weight = _f32(weight, "weight").contiguous()
@@ -582,6 +588,13 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
         if (order.B, order.N) != (B, N):
             raise ValueError("order grid was built for another cloud shape")
         optr, oes, obs = order.order()
+    rptr, ldr = None, 0
+    if residual is not None:
+        if clouds is not None or points1 is not None:
+            raise ValueError("residual= cannot be combined with points1 or clouds")
+        if residual.shape[:2] != (B, N) or not residual.is_contiguous() or residual.dtype != torch.float32:
+            raise ValueError("residual must be a contiguous float32 [B, N, C] tensor")
+        rptr, ldr = residual.data_ptr(), residual.shape[2]
     full_out = out
     if clouds is not None:
         b0, b1 = clouds
@@ -594,8 +607,8 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
         B = b1 - b0
     with _on_device(points2):
         nv.call("pn_fp_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), _p(points1), *s1, D1, points2.data_ptr(),
-                *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), optr, oes, obs, B, N,
-                out_mode, out.data_ptr(), chain.cout, _stream())
+                *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), optr, oes, obs, rptr, ldr,
+                B, N, out_mode, out.data_ptr(), chain.cout, _stream())
     return full_out
 
 

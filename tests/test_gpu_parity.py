@@ -663,6 +663,48 @@ def test_fp_mlp_tc_small_chains(dev, engine, D1, D2, widths, N):
     assert rel_err(got, want) < TC_TOL
 
 
+@pytest.mark.parametrize("D1,D2,widths,N", [(512, 256, [256, 256], 64), (128, 256, [256, 256], 256), (64, 256, [256, 128, 128], 1024),
+                                            (36, 100, [96, 64], 333)])
+def test_fp_skip_half_computed_ahead(dev, D1, D2, widths, N):
+    """PointNetFeaturePropagation with skip input: W [p1 ; interp(p2)] = W_a p1 + W_b interp(p2).  skip_ahead() computes
+    the first term early; features() then interpolates, multiplies W_b and adds it in the first layer's epilogue.  Same
+    result as the unsplit block and as the oracle's interpolate -> concat -> conv chain."""
+    from pointnet12_b200 import ops
+    from pointnet12_b200.model import pointnet_util as U
+
+    rng = np.random.default_rng(D1 + N)
+    B, S = 2, max(8, N // 4)
+    x1 = rng.uniform(-1, 1, size=(B, N, 3)).astype(np.float32)
+    x2 = np.ascontiguousarray(x1[:, :S])
+    p1 = rng.normal(size=(B, N, D1)).astype(np.float32)
+    p2 = rng.normal(size=(B, S, D2)).astype(np.float32)
+    fp = U.PointNetFeaturePropagation(D1 + D2, widths).to(dev).eval()
+    with torch.no_grad():
+        for bn in fp.mlp_bns:
+            bn.running_mean.normal_(0, 0.1)
+            bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_(0, 0.1)
+    layers = [(w.cpu().numpy(), b.cpu().numpy(), True) for w, b in
+              (U.fold_conv_bn(c, b) for c, b in zip(fp.mlp_convs, fp.mlp_bns))]
+    idx, wgt, _, _ = orc.three_nn(x1, x2)
+    rows = np.concatenate([p1, orc.three_interpolate(p2, idx, wgt)], -1)
+    want = _chain_ref(rows.reshape(B * N, -1), layers).reshape(B, N, -1)
+    d_p1, d_p2 = cuda(p1, dev), cuda(p2, dev)
+    gi, gw = ops.three_nn(cuda(x1, dev), cuda(x2, dev))
+    with torch.no_grad():
+        plain = fp.features(d_p1, d_p2, gi, gw)
+        old, ops.FP_SKIP_AHEAD = ops.FP_SKIP_AHEAD, True
+        try:
+            assert fp.skip_ahead(d_p1)
+            split = fp.features(d_p1, d_p2, gi, gw)
+        finally:
+            ops.FP_SKIP_AHEAD = old
+        assert getattr(fp, "_skip_cache", None) is None           # consumed
+    assert rel_err(plain, want) < FEAT_TOL and rel_err(split, want) < FEAT_TOL
+    assert rel_err(split, plain.cpu().numpy()) < 1e-5
+
+
 @pytest.mark.parametrize("engine", ["auto", "stream"])
 def test_fp_mlp_tc_processing_order(dev, engine):
     """Walking the fine points in bucket (spatial) order changes which rows share a tile, not the result."""
