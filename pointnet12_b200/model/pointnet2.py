@@ -188,9 +188,10 @@ class PointNet2SemSeg(_Net):
         `fps_starts` (extension): the four FPS start-index tensors ([B] int64 on the device) when the caller has
         drawn them already (CUDA-graph replay); by default they are drawn like the reference draws them.
 
-        Everything that depends on xyz only -- FPS, ball query and 3-NN search of every level -- is issued on
-        side streams right after the level-1 sampling, so it overlaps the feature path (SA MLPs) instead of
-        sitting on its critical path.  fp1 and the segmentation head run as one tensor-core chain."""
+        Schedule: everything that depends on xyz only -- bucket build, the level-1 ball query
+        (answered on the idle SMs WHILE level-1 sampling runs), sampling / grouping of levels 2-4, the 3-NN searches --
+        runs on internal side streams beside the critical path FPS1 -> sa1..sa4 -> fp4..fp1; fp1 and the
+        segmentation head run as one tensor-core chain whose first layer is folded into fp2's chain."""
         _eval_only(self)
         ops._need_cuda(points, "points")
         B, _, N = points.shape
@@ -249,7 +250,7 @@ class PointNet2SemSeg(_Net):
             x1 = ops.index_points(x0, fps1)
             fork = torch.cuda.Event()
             fork.record(main)
-        xs, balls, nns, ready, have_x = [x0, x1], [None] * 4, [None] * 4, [None] * 4, [None] * 4
+        xs, balls, nns, ready = [x0, x1], [None] * 4, [None] * 4, [None] * 4
         with torch.cuda.stream(geo):                               # sampling / grouping of levels 2..4, back to back
             geo.wait_event(fork)
             for i in (1, 2, 3):

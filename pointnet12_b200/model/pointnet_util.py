@@ -9,11 +9,15 @@ libpn12_b200.so:
     square_distance            :19-40               pn_square_distance_f32 (never used on the hot path)
     index_points               :43-60               pn_index_points_f32
     farthest_point_sample      :63-84               pn_fps_f32 (cluster per cloud, register resident)
-    query_ball_point           :87-107              pn_ball_query_f32 (ordered scan, no distance cube, no sort)
+    query_ball_point           :87-107              pn_ball_query_grid_f32 (uniform-grid buckets, N >= 4096) /
+                                                    pn_ball_query_f32 (ordered scan): no distance cube, no sort
     sample_and_group(_all)     :110-157             the three above + pn_group_f32
-    PointNetSetAbstraction     :160-201             + pn_linear_f32 (BN folded) + pn_group_max_f32
+    PointNetSetAbstraction     :160-201             pn_sa_mlp_bf16x3: gather + recentre + MLP chain + max in ONE
+                                                    tensor-core kernel (pn_linear_f32 + pn_group_max_f32 in fp32 mode)
     PointNetSetAbstractionMsg  :204-261             same, one ball query per radius, MSG channel order
-    PointNetFeaturePropagation :264-313             pn_three_nn_f32 + pn_three_interpolate_f32 + pn_linear_f32
+    PointNetFeaturePropagation :264-313             pn_three_nn_f32 / pn_three_nn_blocks_f32 + pn_fp_mlp_bf16x3:
+                                                    interpolation + concat + MLP chain in ONE tensor-core kernel
+                                                    (pn_three_interpolate_f32 + pn_linear_f32 in fp32 mode)
 
 Functions take point-major [B, N, C] float32 CUDA tensors (strided views welcome) and return int64
 indices; modules take and return channel-major [B, C, N] like the reference.  Internally features stay
