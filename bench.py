@@ -67,30 +67,78 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs.
+
+    The timed region is ~20 ms, shorter than one `nvidia-smi -lms` period (and than nvidia-smi's start-up on an 8-GPU
+    box), so the samples come from NVML directly -- the library nvidia-smi itself reads -- every 2 ms in a thread:
+    clocks.sm, clocks.max.sm and the clocks_event_reasons bits hw_slowdown / hw_thermal_slowdown / sw_thermal_slowdown /
+    sw_power_cap of the recipe's clocks line.  nvidia-smi is the fallback when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop = index, [], None, None, threading.Event()
+        self.source = None
 
     def __enter__(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.source = pynvml, "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
         return self
 
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown")
+                 else n.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap",
+                                         getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mask = reasons_fn(self.handle)
+                self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
-        if self.proc is not None:
+        if self.nvml is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
+        elif self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
@@ -101,7 +149,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def fps_starts(torch, batch):
