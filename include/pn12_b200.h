@@ -275,6 +275,85 @@ int pn_mlp_set_reserved_sms(int sms);
  * layer: MMA issue start, MMAs issued, accumulator ready, epilogue done; last: tile done]. */
 int pn_mlp_set_debug(void* timeline);
 
+/* ================================================================================================================
+ * Training step of PointNet2SemSeg (reference pcdseg.py:157-186) and evaluation
+ * metrics (row f-2; pcdseg.py:58-97).  In train mode BatchNorm uses the statistics of the current batch, so a
+ * layer is  pn_linear_f32 -> pn_bn_stats_f32 -> pn_bn_finalize_f32 -> pn_bn_act(_max)_f32  and every layer's
+ * pre-normalisation output y is kept for the backward pass.  All matrices are row-major [rows, C] fp32 with a
+ * leading dimension; the per-channel accumulators (sum, sumsq, s1, s2) are fp64 and must be ZEROED by the caller.
+ * ================================================================================================================ */
+
+/* Column sums of y and y*y in fp64 (nn.BatchNorm1d/2d in training mode, model/pointnet_util.py:196, :311,
+ * pointnet2.py:172: the batch mean / biased variance over every row of the layer).  Atomically ADDED to sum / sumsq. */
+int pn_bn_stats_f32(const float* y, int64_t ldy, int64_t rows, int C, double* sum, double* sumsq, pn_stream_t stream);
+/* mean = sum/n, var = sumsq/n - mean^2 (biased), invstd = 1/sqrt(var+eps), scale = gamma*invstd, shift = beta -
+ * mean*scale; running_mean/var (may be NULL) updated with `momentum` and the UNBIASED variance as torch does,
+ * num_batches_tracked (may be NULL) incremented. */
+int pn_bn_finalize_f32(const double* sum, const double* sumsq, int64_t n, int C, const float* gamma, const float* beta,
+                       float eps, float momentum, float* running_mean, float* running_var,
+                       int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
+                       pn_stream_t stream);
+/* z = act(y*scale + shift)  (F.relu(bn(conv(x))), model/pointnet_util.py:197, :312). */
+int pn_bn_act_f32(const float* y, int64_t ldy, int64_t rows, int C, const float* scale, const float* shift, int relu,
+                  float* z, int64_t ldz, pn_stream_t stream);
+/* The same followed by torch.max over the K rows of each group (model/pointnet_util.py:199): out [groups, C],
+ * argmax [groups, C] int32 = the first row of the group attaining the maximum (where the gradient is routed). */
+int pn_bn_act_max_f32(const float* y, int64_t ldy, int64_t groups, int K, int C, const float* scale,
+                      const float* shift, int relu, float* out, int64_t ldo, int32_t* argmax, pn_stream_t stream);
+/* Backward of act(bn(y)), first pass: g = dz * [y*scale+shift > 0], xhat = (y-mean)*invstd; s1 += sum g,
+ * s2 += sum g*xhat (fp64).  argmax != NULL: dz is the POOLED gradient [rows/K, C] and g[r] = dz[r/K] where
+ * argmax[r/K] == r%K, 0 elsewhere (backward of torch.max). */
+int pn_bn_bwd_stats_f32(const float* y, int64_t ldy, int64_t rows, int C, const float* dz, int64_t lddz,
+                        const int32_t* argmax, int K, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, int relu, double* s1, double* s2, pn_stream_t stream);
+/* Second pass: dy = gamma*invstd*(g - s1/rows - xhat*s2/rows); dgamma = s2, dbeta = s1 (may be NULL). */
+int pn_bn_bwd_apply_f32(const float* y, int64_t ldy, int64_t rows, int C, const float* dz, int64_t lddz,
+                        const int32_t* argmax, int K, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, int relu, const double* s1, const double* s2, float* dy, int64_t lddy,
+                        float* dgamma, float* dbeta, pn_stream_t stream);
+/* Weight gradient of a 1x1 conv: dw[co,ci] += sum_r dy[r,co]*x[r,ci], db[co] += sum_r dy[r,co] (db may be NULL).
+ * Split over the rows, accumulated with fp32 atomics: dw / db must be zeroed (or hold a gradient to add to). */
+int pn_grad_weight_f32(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin,
+                       float* dw, int64_t lddw, float* db, pn_stream_t stream);
+/* out [cols, rows] = in [rows, cols]^T (the weight of the input-gradient GEMM dx = dy W = pn_linear_f32(dy, W^T)). */
+int pn_transpose_f32(const float* in, int rows, int cols, float* out, pn_stream_t stream);
+/* Backward of the gather of sample_and_group (model/pointnet_util.py:128-131): dfeat[b, idx[b,s,k], :] +=
+ * dgrouped[(b,s,k), col0 : col0+D].  dfeat contiguous [B,N,D], zeroed by the caller.  (xyz carries no gradient.) */
+int pn_group_bwd_f32(const float* dgrouped, int64_t ldg, int col0, int D, const int64_t* idx, int B, int N, int S,
+                     int K, float* dfeat, pn_stream_t stream);
+/* Backward of pn_three_interpolate_f32 (model/pointnet_util.py:301-307): dpoints1 [B,N,D1] = dx[:, :D1];
+ * dpoints2[b, idx[b,n,k], :] += weight[b,n,k] * dx[(b,n), D1:].  dpoints2 contiguous [B,S,D2], zeroed by the caller. */
+int pn_three_interpolate_bwd_f32(const float* dx, int64_t ldx, int D1, int D2, const int64_t* idx, const float* weight,
+                                 int B, int N, int S, float* dpoints1, float* dpoints2, pn_stream_t stream);
+/* nn.Dropout(p) in training mode (pointnet2.py:172): y = x*keep/(1-p).  mask_in (bytes, dense [rows*C]) != NULL:
+ * keep = mask_in -- also the backward pass.  Otherwise keep ~ Bernoulli(1-p) from a Philox4x32-10 stream keyed by
+ * seed_offset[0] with counter offset seed_offset[1] (DEVICE memory, so a replayed CUDA graph sees fresh values) and
+ * is written to mask_out (may be NULL). */
+int pn_dropout_f32(const float* x, int64_t ldx, int64_t rows, int C, float p, const uint64_t* seed_offset,
+                   const uint8_t* mask_in, uint8_t* mask_out, float* y, int64_t ldy, pn_stream_t stream);
+/* nn.CrossEntropyLoss()(x^T, target) as pcdseg.py:177-178 applies it to the network's log-probabilities:
+ * loss = mean_r (logsumexp(x_r) - x_r[target_r]); dx (may be NULL) = (softmax(x_r) - onehot) * grad_scale / rows.
+ * loss_sum: one fp64 scratch word, loss: one fp32 word (both device). */
+int pn_cross_entropy_f32(const float* x, int64_t ldx, const int64_t* target, int64_t rows, int C, double* loss_sum,
+                         float* loss, float* dx, int64_t lddx, float grad_scale, pn_stream_t stream);
+/* Backward of F.log_softmax (pointnet2.py:174): dx = dy - exp(y)*sum_c dy, y = the log-probabilities. */
+int pn_log_softmax_bwd_f32(const float* dy, int64_t lddy, const float* y, int64_t ldy, int64_t rows, int C, float* dx,
+                           int64_t lddx, pn_stream_t stream);
+/* torch.optim.Adam(lr, betas, eps, weight_decay) of pcdseg.py:136-141 on one flat fp32 buffer: g = grad*grad_scale +
+ * weight_decay*p; m, v updated; p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).  step >= 1.
+ * grad_scale = 1/world_size after a summing all-reduce. */
+int pn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                float beta2, float eps, float weight_decay, int64_t step, float grad_scale, pn_stream_t stream);
+/* test_kitti_semseg's inner loop (pcdseg.py:72-83) without host round trips: pred (may be NULL) [rows] = argmax over
+ * the C <= 64 classes; counts int64 [3C+1] (overwritten) = per class intersection | predicted | target, then the
+ * number of correct points. */
+int pn_seg_metrics_f32(const float* logp, int64_t ldx, const int64_t* target, int64_t rows, int C, int64_t* pred,
+                       int64_t* counts, pn_stream_t stream);
+/* Folds one batch's counts into the running totals as the reference's Python does: ious[c] += (U == 0 ? 1 : I/U)
+ * (double division rounded to fp32, added in fp32), count[c] += 1, acc_sum += correct/points (fp64), batches += 1. */
+int pn_seg_metrics_accumulate(const int64_t* counts, int C, int64_t points, float* ious, uint32_t* count,
+                              double* acc_sum, int64_t* batches, pn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

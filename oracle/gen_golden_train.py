@@ -1,0 +1,142 @@
+"""Generate tests/golden/train_step_ckpt.npz by running the REFERENCE'S OWN training iteration (pcdseg.py:166-186)
+on the CPU in the build container (the reference is imported read-only from /root/reference):
+
+    python oracle/gen_golden_train.py
+
+model = PointNet2SemSeg(19, feature_dims=1) with the shipped checkpoint, model.train(), torch.manual_seed(0),
+logits = model(points); loss = nn.CrossEntropyLoss()(logits.transpose(2, 1), target); loss.backward().
+Stored: the loss, the log-probabilities, the dropout keep-mask the reference drew (captured with a forward hook on
+drop1; where the dropout input is 0 the mask is unobservable and irrelevant and is stored as 1), every parameter gradient
+(complete for tensors up to 20000 elements, every 9th element + sum + L2 norm for the larger ones), and the BatchNorm
+buffers after the forward.  Inputs are rebuilt from seeds (pointnet12_b200.synthetic, config 5), labels from
+numpy default_rng(5000).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from gen_golden import CKPT, OUT, REF, import_reference  # noqa: E402
+from pointnet12_b200 import synthetic as syn  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+B, N, CLASSES = 2, 2048, 19
+FULL_MAX, STRIDE = 20000, 9
+
+
+def seeded_block(ctor, seed: int):
+    """A block with seeded default init, then BatchNorm gamma ~ U(0.5, 1.5), beta ~ N(0, 0.1) from the same generator.
+    tests/ rebuild OUR block the same way; main() asserts that both constructions give identical parameters."""
+    torch.manual_seed(seed)
+    blk = ctor()
+    with torch.no_grad():
+        for bn in blk.mlp_bns:
+            bn.weight.copy_(torch.rand(bn.weight.shape) + 0.5)
+            bn.bias.copy_(torch.randn(bn.bias.shape) * 0.1)
+    return blk.train()
+
+
+def block_inputs():
+    """Seeded inputs of the two block fixtures: 1024 points of a synthetic cloud, 64-channel features, a coarse level
+    of 256 points (an FPS sample of the cloud) with 256-channel features, and the upstream gradients."""
+    rng = np.random.default_rng(6000)
+    xyz = np.ascontiguousarray(syn.kitti_batch(2, 1024, config=6)[:, :3, :])                 # [2,3,1024]
+    f1 = rng.standard_normal((2, 64, 1024)).astype(np.float32)
+    # coarse level: 256 DISTINCT points (an FPS sample, like the network's own levels; duplicates would tie in the 3-NN sort)
+    pm = np.ascontiguousarray(xyz.transpose(0, 2, 1))
+    xyz2 = np.ascontiguousarray(orc.index_points(pm, orc.farthest_point_sample(pm, 256, [0, 0])).transpose(0, 2, 1))
+    f2 = rng.standard_normal((2, 256, 256)).astype(np.float32)
+    g_sa = rng.standard_normal((2, 128, 256)).astype(np.float32)
+    g_fp = rng.standard_normal((2, 128, 1024)).astype(np.float32)
+    return xyz, f1, xyz2, f2, g_sa, g_fp
+
+
+def blocks(ref):
+    """PointNetSetAbstraction(256, 0.2, 32, 67, [64,64,128]) and PointNetFeaturePropagation(320, [256,128]) of the
+    reference in train mode: outputs, input gradients and parameter gradients for seeded inputs."""
+    from pointnet12_b200.model import pointnet_util as ours
+
+    pu = ref["pointnet_util"]
+    xyz, f1, xyz2, f2, g_sa, g_fp = block_inputs()
+    arrays = {}
+    sa = seeded_block(lambda: pu.PointNetSetAbstraction(256, 0.2, 32, 64 + 3, [64, 64, 128], False), 4321)
+    mine = seeded_block(lambda: ours.PointNetSetAbstraction(256, 0.2, 32, 64 + 3, [64, 64, 128], False), 4321)
+    assert all(torch.equal(a, b) for a, b in zip(sa.state_dict().values(), mine.state_dict().values()))
+    pts = torch.from_numpy(f1).requires_grad_(True)
+    torch.manual_seed(7)
+    start = torch.randint(0, 1024, (2,), dtype=torch.long).numpy()
+    torch.manual_seed(7)
+    new_xyz, new_points = sa(torch.from_numpy(xyz), pts)
+    new_points.backward(torch.from_numpy(g_sa))
+    arrays.update({"sa.start": start.astype(np.int32), "sa.out": new_points.detach().numpy(), "sa.dpoints": pts.grad.numpy()})
+    for n, p in sa.named_parameters():
+        arrays["sa.grad." + n] = p.grad.numpy()
+    for n, b in sa.named_buffers():
+        arrays["sa.buffer." + n] = b.numpy()
+    fp = seeded_block(lambda: pu.PointNetFeaturePropagation(320, [256, 128]), 4322)
+    mine = seeded_block(lambda: ours.PointNetFeaturePropagation(320, [256, 128]), 4322)
+    assert all(torch.equal(a, b) for a, b in zip(fp.state_dict().values(), mine.state_dict().values()))
+    p1 = torch.from_numpy(f1).requires_grad_(True)
+    p2 = torch.from_numpy(f2).requires_grad_(True)
+    out = fp(torch.from_numpy(xyz), torch.from_numpy(xyz2), p1, p2)
+    out.backward(torch.from_numpy(g_fp))
+    arrays.update({"fp.out": out.detach().numpy(), "fp.dpoints1": p1.grad.numpy(), "fp.dpoints2": p2.grad.numpy()})
+    for n, p in fp.named_parameters():
+        arrays["fp.grad." + n] = p.grad.numpy()
+    path = os.path.join(OUT, "train_blocks_seeded.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def main():
+    torch.set_num_threads(8)
+    ref = import_reference()
+    blocks(ref)
+    net = ref["pointnet2"].PointNet2SemSeg(CLASSES, feature_dims=1)
+    sd = torch.load(os.path.join(REF, "checkpoints", CKPT), map_location="cpu")
+    net.load_state_dict({k[len("module."):]: v for k, v in sd.items()})
+    net.train()
+    pts = syn.kitti_batch(B, N, config=5)
+    target = np.random.default_rng(5000).integers(0, CLASSES, size=(B, N)).astype(np.int64)
+    seen = {}
+    net.drop1.register_forward_hook(lambda m, i, o: seen.update(x=i[0].detach().clone(), y=o.detach().clone()))
+    torch.manual_seed(0)
+    starts = [torch.randint(0, n, (B,), dtype=torch.long).numpy() for n in (N, 1024, 256, 64)]
+    torch.manual_seed(0)
+    logits = net(torch.from_numpy(pts))
+    loss = torch.nn.CrossEntropyLoss()(logits.transpose(2, 1), torch.from_numpy(target))
+    net.zero_grad()
+    loss.backward()
+    x, y = seen["x"], seen["y"]                       # [B,128,N] channel-major
+    keep = torch.where(x != 0, (y != 0), torch.ones_like(x, dtype=torch.bool))
+    keep_rows = keep.permute(0, 2, 1).reshape(B * N, -1).numpy()
+    arrays = {
+        "input_checksum": np.array(syn.checksum(pts)),
+        "target": target.astype(np.int8),
+        "starts": np.stack(starts).astype(np.int32),
+        "keep_bits": np.packbits(keep_rows, axis=1),
+        "loss": np.float64(loss.item()),
+        "logp": logits.detach().numpy(),
+    }
+    for name, p in net.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1)
+        if g.size <= FULL_MAX:
+            arrays["grad." + name] = g.astype(np.float32)
+        else:
+            arrays["gradsub." + name] = g[::STRIDE].astype(np.float32)
+        arrays["gradstat." + name] = np.array([g.astype(np.float64).sum(), np.sqrt((g.astype(np.float64) ** 2).sum())])
+    for name, b in net.named_buffers():
+        arrays["buffer." + name] = b.detach().numpy()
+    path = os.path.join(OUT, "train_step_ckpt.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB, loss {loss.item():.6f}, "
+          f"kept fraction {keep_rows.mean():.4f}")
+
+
+if __name__ == "__main__":
+    main()

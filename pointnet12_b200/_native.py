@@ -69,6 +69,22 @@ _SIGNATURES = {
     "pn_mlp_set_debug": [vp],
     "pn_mlp_set_reserved_sms": [i32],
     "pn_mlp_set_precision": [i32],
+    "pn_bn_stats_f32": [vp, i64, i64, i32, vp, vp, vp],
+    "pn_bn_finalize_f32": [vp, vp, i64, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp],
+    "pn_bn_act_f32": [vp, i64, i64, i32, vp, vp, i32, vp, i64, vp],
+    "pn_bn_act_max_f32": [vp, i64, i64, i32, i32, vp, vp, i32, vp, i64, vp, vp],
+    "pn_bn_bwd_stats_f32": [vp, i64, i64, i32, vp, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp],
+    "pn_bn_bwd_apply_f32": [vp, i64, i64, i32, vp, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, vp],
+    "pn_grad_weight_f32": [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp, vp],
+    "pn_transpose_f32": [vp, i32, i32, vp, vp],
+    "pn_group_bwd_f32": [vp, i64, i32, i32, vp, i32, i32, i32, i32, vp, vp],
+    "pn_three_interpolate_bwd_f32": [vp, i64, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
+    "pn_dropout_f32": [vp, i64, i64, i32, f32, vp, vp, vp, vp, i64, vp],
+    "pn_cross_entropy_f32": [vp, i64, vp, i64, i32, vp, vp, vp, i64, f32, vp],
+    "pn_log_softmax_bwd_f32": [vp, i64, vp, i64, i64, i32, vp, i64, vp],
+    "pn_adam_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp],
+    "pn_seg_metrics_f32": [vp, i64, vp, i64, i32, vp, vp, vp],
+    "pn_seg_metrics_accumulate": [vp, i32, i64, vp, vp, vp, vp, vp],
 }
 
 

@@ -192,7 +192,9 @@ class PointNet2SemSeg(_Net):
         (answered on the idle SMs WHILE level-1 sampling runs), sampling / grouping of levels 2-4, the 3-NN searches --
         runs on internal side streams beside the critical path FPS1 -> sa1..sa4 -> fp4..fp1; fp1 and the
         segmentation head run as one tensor-core chain whose first layer is folded into fp2's chain."""
-        _eval_only(self)
+        if self.training:
+            from ..train import semseg_forward_train        # SURVEY 8 f-1: batch-stat BN, dropout, autograd
+            return semseg_forward_train(self, points, fps_starts)
         ops._need_cuda(points, "points")
         B, _, N = points.shape
         pm = points.permute(0, 2, 1)

@@ -24,8 +24,10 @@ indices; modules take and return channel-major [B, C, N] like the reference.  In
 point-major (a row per point, channels contiguous); the channel-major tensors the modules return are
 views of that storage, so chaining modules costs no transposes.
 
-Inference only for now: BatchNorm is folded into the conv weights from the running statistics, and
-calling a module in train() mode raises.  CPU tensors raise: there is no CPU fallback.
+eval(): BatchNorm is folded into the conv weights from the running statistics and the fused tensor-core chains run.
+train(): PointNetSetAbstraction and PointNetFeaturePropagation normalise with batch statistics and return tensors with a
+grad_fn (pointnet12_b200/train.py: forward and backward on our kernels); the MSG block still raises in train() mode.
+CPU tensors raise: there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -280,7 +282,9 @@ class PointNetSetAbstraction(nn.Module):
     def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx: Optional[torch.Tensor] = None):
         """xyz [B,3,N], points [B,D,N] or None -> new_xyz [B,3,S], new_points [B,C',S].
         `start_idx` (extension): the FPS start indices, when the caller has already drawn them."""
-        _eval_only(self)
+        if self.training:
+            from ..train import set_abstraction_train      # batch-statistics BatchNorm + autograd (SURVEY 8 f-1)
+            return set_abstraction_train(self, xyz, points, start_idx)
         xyz_pm = xyz.permute(0, 2, 1)
         pts_pm = points.permute(0, 2, 1) if points is not None else None
         if self.group_all:
@@ -484,7 +488,9 @@ class PointNetFeaturePropagation(nn.Module):
 
     def forward(self, xyz1, xyz2, points1, points2):
         """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
-        _eval_only(self)
+        if self.training:
+            from ..train import feature_propagation_train
+            return feature_propagation_train(self, xyz1, xyz2, points1, points2)
         idx, w = self.geometry(xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1))
         p1 = points1.permute(0, 2, 1) if points1 is not None else None
         return self.features(p1, points2.permute(0, 2, 1), idx, w).permute(0, 2, 1)

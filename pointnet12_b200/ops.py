@@ -240,8 +240,10 @@ def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 def group(xyz: torch.Tensor, feat: Optional[torch.Tensor], new_xyz: torch.Tensor, idx: torch.Tensor,
-          msg_order: bool) -> torch.Tensor:
-    """Gather + recentre + concat (pointnet_util.py:127-131 / :243-247) -> [B, S, K, 3+D]."""
+          msg_order: bool, pad4: bool = False) -> torch.Tensor:
+    """Gather + recentre + concat (pointnet_util.py:127-131 / :243-247) -> [B, S, K, 3+D].
+    pad4: rows are allocated with the channel count rounded up to a multiple of 4 (-> [B, S, K, ld], the data in
+    [..., :3+D]) so that the training GEMMs can read them with 16-byte loads."""
     xyz, new_xyz = _cloud(xyz, "xyz", 3), _cloud(new_xyz, "new_xyz", 3)
     idx = _i64(idx, "idx")
     B, N, _ = xyz.shape
@@ -251,10 +253,11 @@ def group(xyz: torch.Tensor, feat: Optional[torch.Tensor], new_xyz: torch.Tensor
         D, fs = feat.shape[2], feat.stride()
     else:
         D, fs = 0, (0, 0, 0)
-    out = torch.empty((B, S, K, 3 + D), dtype=torch.float32, device=xyz.device)
+    ld = (3 + D + 3) // 4 * 4 if pad4 else 3 + D
+    out = torch.empty((B, S, K, ld), dtype=torch.float32, device=xyz.device)
     with _on_device(xyz):
         nv.call("pn_group_f32", xyz.data_ptr(), *xyz.stride(), _p(feat), *fs, D, new_xyz.data_ptr(), *new_xyz.stride(),
-                idx.data_ptr(), B, N, S, K, int(msg_order), out.data_ptr(), 3 + D, _stream())
+                idx.data_ptr(), B, N, S, K, int(msg_order), out.data_ptr(), ld, _stream())
     return out
 
 
@@ -610,6 +613,211 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
                 *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), optr, oes, obs, rptr, ldr,
                 B, N, out_mode, out.data_ptr(), chain.cout, _stream())
     return full_out
+
+
+# ------------------------------------------------------------------------------------------------
+# Training-step and evaluation-metric kernels (csrc/train.cu).  Row matrices are 2-D float32 views with unit
+# channel stride (a leading dimension is taken from stride(0)); statistics accumulators are float64.
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _rowmat(t: torch.Tensor, name: str) -> torch.Tensor:
+    _need_cuda(t, name)
+    if t.dtype != torch.float32 or t.dim() != 2 or (t.stride(1) != 1 and t.shape[1] != 1):
+        raise ValueError(f"{name} must be a float32 [rows, C] matrix with unit channel stride")
+    return t
+
+
+class BatchStats:
+    """Batch statistics of one BatchNorm layer in training mode: scale/shift for the forward, mean/invstd for the backward."""
+
+    __slots__ = ("scale", "shift", "mean", "invstd", "rows")
+
+
+def bn_batch_stats(y: torch.Tensor, bn, momentum_update: bool = True) -> BatchStats:
+    """pn_bn_stats_f32 + pn_bn_finalize_f32 over the rows of y; updates bn.running_* / num_batches_tracked like
+    nn.BatchNorm in train mode (momentum = bn.momentum)."""
+    y = _rowmat(y, "y")
+    rows, Cc = y.shape
+    acc = torch.zeros((2, Cc), dtype=torch.float64, device=y.device)
+    st = BatchStats()
+    buf = torch.empty((4, Cc), dtype=torch.float32, device=y.device)
+    st.scale, st.shift, st.mean, st.invstd = buf[0], buf[1], buf[2], buf[3]
+    st.rows = rows
+    track = momentum_update and bn.track_running_stats and bn.running_mean is not None
+    with _on_device(y):
+        nv.call("pn_bn_stats_f32", y.data_ptr(), _ld(y), rows, Cc, acc[0].data_ptr(), acc[1].data_ptr(), _stream())
+        nv.call("pn_bn_finalize_f32", acc[0].data_ptr(), acc[1].data_ptr(), rows, Cc, _p(bn.weight), _p(bn.bias),
+                float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1),
+                bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                bn.num_batches_tracked.data_ptr() if track and bn.num_batches_tracked is not None else None,
+                st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), _stream())
+    if track:      # written through raw pointers: tell torch (the eval path refolds BatchNorm when a version changes)
+        torch.autograd.graph.increment_version([b for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked) if b is not None])
+    return st
+
+
+def bn_act(y: torch.Tensor, st: BatchStats, relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    y = _rowmat(y, "y")
+    rows, Cc = y.shape
+    if out is None:
+        out = torch.empty((rows, Cc), dtype=torch.float32, device=y.device)
+    with _on_device(y):
+        nv.call("pn_bn_act_f32", y.data_ptr(), _ld(y), rows, Cc, st.scale.data_ptr(), st.shift.data_ptr(), int(relu),
+                out.data_ptr(), _ld(out), _stream())
+    return out
+
+
+def bn_act_max(y: torch.Tensor, st: BatchStats, K: int, relu: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (pooled [rows/K, C], argmax int32 [rows/K, C])."""
+    y = _rowmat(y, "y")
+    rows, Cc = y.shape
+    G = rows // K
+    out = torch.empty((G, Cc), dtype=torch.float32, device=y.device)
+    am = torch.empty((G, Cc), dtype=torch.int32, device=y.device)
+    with _on_device(y):
+        nv.call("pn_bn_act_max_f32", y.data_ptr(), _ld(y), G, int(K), Cc, st.scale.data_ptr(), st.shift.data_ptr(),
+                int(relu), out.data_ptr(), Cc, am.data_ptr(), _stream())
+    return out, am
+
+
+def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: bool = True,
+                    argmax: Optional[torch.Tensor] = None, K: int = 1):
+    """Backward of act(bn(y)) with batch statistics -> (dy [rows, C], dgamma [C], dbeta [C]).
+    argmax/K: dz is the pooled gradient [rows/K, C] of bn_act_max."""
+    y, dz = _rowmat(y, "y"), _rowmat(dz, "dz")
+    rows, Cc = y.shape
+    acc = torch.zeros((2, Cc), dtype=torch.float64, device=y.device)
+    dy = torch.empty((rows, Cc), dtype=torch.float32, device=y.device)
+    dgb = torch.empty((2, Cc), dtype=torch.float32, device=y.device)
+    common = (y.data_ptr(), _ld(y), rows, Cc, dz.data_ptr(), _ld(dz), _p(argmax), int(K), st.scale.data_ptr(),
+              st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), int(relu), acc[0].data_ptr(), acc[1].data_ptr())
+    with _on_device(y):
+        nv.call("pn_bn_bwd_stats_f32", *common, _stream())
+        nv.call("pn_bn_bwd_apply_f32", *common, dy.data_ptr(), Cc, dgb[0].data_ptr(), dgb[1].data_ptr(), _stream())
+    return dy, dgb[0], dgb[1]
+
+
+def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    """dw [cout, cin] += dy^T x, db [cout] += column sums of dy (in place; the buffers hold zeros or a gradient)."""
+    dy, x = _rowmat(dy, "dy"), _rowmat(x, "x")
+    rows, cout = dy.shape
+    cin = x.shape[1]
+    if x.shape[0] != rows or dw.shape != (cout, cin) or not dw.is_contiguous() or dw.dtype != torch.float32:
+        raise ValueError("grad_weight: shape mismatch")
+    with _on_device(dy):
+        nv.call("pn_grad_weight_f32", dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), rows, cout, cin, dw.data_ptr(), cin,
+                _p(db), _stream())
+
+
+def transpose(w: torch.Tensor) -> torch.Tensor:
+    w = _f32(w, "w").contiguous()
+    r, c = w.shape
+    out = torch.empty((c, r), dtype=torch.float32, device=w.device)
+    with _on_device(w):
+        nv.call("pn_transpose_f32", w.data_ptr(), r, c, out.data_ptr(), _stream())
+    return out
+
+
+def group_backward(dgrouped: torch.Tensor, col0: int, D: int, idx: torch.Tensor, N: int) -> torch.Tensor:
+    """dgrouped [B*S*K, >= col0+D] -> dfeat [B, N, D] (scatter-add through the ball-query indices)."""
+    dgrouped = _rowmat(dgrouped, "dgrouped")
+    idx = _i64(idx, "idx")
+    B, S, K = idx.shape
+    dfeat = torch.zeros((B, N, D), dtype=torch.float32, device=dgrouped.device)
+    with _on_device(dgrouped):
+        nv.call("pn_group_bwd_f32", dgrouped.data_ptr(), _ld(dgrouped), int(col0), int(D), idx.data_ptr(), B, N, S, K,
+                dfeat.data_ptr(), _stream())
+    return dfeat
+
+
+def three_interpolate_backward(dx: torch.Tensor, D1: int, D2: int, idx: torch.Tensor, weight: torch.Tensor, S: int):
+    """dx [B*N, D1+D2] -> (dpoints1 [B,N,D1] or None, dpoints2 [B,S,D2])."""
+    dx = _rowmat(dx, "dx")
+    idx = _i64(idx, "idx")
+    weight = _f32(weight, "weight").contiguous()
+    B, N, _ = idx.shape
+    dp1 = torch.empty((B, N, D1), dtype=torch.float32, device=dx.device) if D1 else None
+    dp2 = torch.zeros((B, S, D2), dtype=torch.float32, device=dx.device)
+    with _on_device(dx):
+        nv.call("pn_three_interpolate_bwd_f32", dx.data_ptr(), _ld(dx), int(D1), int(D2), idx.data_ptr(), weight.data_ptr(),
+                B, N, int(S), _p(dp1), dp2.data_ptr(), _stream())
+    return dp1, dp2
+
+
+def dropout(x: torch.Tensor, p: float, seed_offset: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+            want_mask: bool = True):
+    """-> (y, mask uint8 [rows, C]).  mask given: applied as is (also the backward pass); else drawn from the Philox
+    stream named by seed_offset (uint64/int64 [2] on the device: seed, offset)."""
+    x = _rowmat(x, "x")
+    rows, Cc = x.shape
+    y = torch.empty((rows, Cc), dtype=torch.float32, device=x.device)
+    out_mask = None
+    if mask is None:
+        if seed_offset is None:
+            raise ValueError("dropout needs a mask or a seed")
+        out_mask = torch.empty((rows, Cc), dtype=torch.uint8, device=x.device) if want_mask else None
+    elif mask.dtype != torch.uint8 or mask.numel() != rows * Cc or not mask.is_contiguous():
+        raise ValueError("mask must be a contiguous uint8 [rows, C] tensor")
+    with _on_device(x):
+        nv.call("pn_dropout_f32", x.data_ptr(), _ld(x), rows, Cc, float(p), _p(seed_offset), _p(mask), _p(out_mask),
+                y.data_ptr(), Cc, _stream())
+    return y, (mask if mask is not None else out_mask)
+
+
+def cross_entropy(x: torch.Tensor, target: torch.Tensor, want_grad: bool = True, grad_scale: float = 1.0):
+    """nn.CrossEntropyLoss() over rows x [rows, C], target [rows] -> (loss 0-d tensor, dx or None)."""
+    x = _rowmat(x, "x")
+    target = _i64(target.reshape(-1), "target")
+    rows, Cc = x.shape
+    if target.numel() != rows:
+        raise ValueError("target must hold one label per row")
+    scratch = torch.empty((1,), dtype=torch.float64, device=x.device)
+    loss = torch.empty((), dtype=torch.float32, device=x.device)
+    dx = torch.empty((rows, Cc), dtype=torch.float32, device=x.device) if want_grad else None
+    with _on_device(x):
+        nv.call("pn_cross_entropy_f32", x.data_ptr(), _ld(x), target.data_ptr(), rows, Cc, scratch.data_ptr(),
+                loss.data_ptr(), _p(dx), Cc, float(grad_scale), _stream())
+    return loss, dx
+
+
+def log_softmax_backward(dy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    dy, y = _rowmat(dy, "dy"), _rowmat(y, "y")
+    rows, Cc = y.shape
+    dx = torch.empty((rows, Cc), dtype=torch.float32, device=y.device)
+    with _on_device(y):
+        nv.call("pn_log_softmax_bwd_f32", dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), rows, Cc, dx.data_ptr(), Cc, _stream())
+    return dx
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    """One torch.optim.Adam update of a flat float32 buffer, in place."""
+    for t, name in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _need_cuda(t, name)
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param.numel():
+            raise ValueError(f"{name} must be a contiguous float32 buffer of the parameter's size")
+    with _on_device(param):
+        nv.call("pn_adam_f32", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale),
+                _stream())
+
+
+def seg_metrics(logp: torch.Tensor, target: torch.Tensor, want_pred: bool = False):
+    """logp [..., C] log-probabilities, target [...] -> counts int64 [3C+1] (intersection | predicted | target per class,
+    then correct points) and optionally the arg-max labels."""
+    Cc = logp.shape[-1]
+    x = _rowmat(_f32(logp, "logp").reshape(-1, Cc), "logp")
+    target = _i64(target.reshape(-1), "target")
+    rows = x.shape[0]
+    if target.numel() != rows:
+        raise ValueError("target must hold one label per point")
+    counts = torch.empty((3 * Cc + 1,), dtype=torch.int64, device=x.device)
+    pred = torch.empty((rows,), dtype=torch.int64, device=x.device) if want_pred else None
+    with _on_device(x):
+        nv.call("pn_seg_metrics_f32", x.data_ptr(), _ld(x), target.data_ptr(), rows, Cc, _p(pred), counts.data_ptr(), _stream())
+    return (counts, pred.view(logp.shape[:-1])) if want_pred else counts
 
 
 if _ENV_BF16:

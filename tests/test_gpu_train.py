@@ -1,0 +1,352 @@
+"""GPU parity of the training step and the evaluation metrics (f-2), through the C ABI.
+
+Three layers of evidence: every kernel of csrc/train.cu against a numpy restatement; one set-abstraction and one
+feature-propagation block (forward, input gradients, parameter gradients, BatchNorm buffers) against the reference's own
+autograd (tests/golden/train_blocks_seeded.npz) and the float64 oracle, to fp32 round-off; and the whole PointNet2SemSeg
+training iteration on the shipped checkpoint against the reference's run (train_step_ckpt.npz) inside the band the
+reference's own float32-vs-float64 difference defines (tests/test_train_oracle.py explains the band).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import train_oracle as tor
+from test_train_oracle import block_inputs, check_step_against_golden, rl2, seeded_block, step_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda", 0)
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("rows,C,ld", [(4096, 32, 32), (1000, 67, 68), (70001, 128, 128), (33, 19, 19), (512, 512, 512)])
+def test_bn_forward_kernels(dev, rows, C, ld):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(rows + C)
+    y = (rng.standard_normal((rows, C)) * rng.uniform(0.1, 3, C) + rng.uniform(-20, 20, C)).astype(np.float32)
+    buf = torch.zeros((rows, ld), device=dev)
+    buf[:, :C] = T(y, dev)
+    yv = buf[:, :C]
+    bn = torch.nn.BatchNorm1d(C).to(dev)
+    with torch.no_grad():
+        bn.weight.copy_(T(rng.uniform(0.5, 1.5, C).astype(np.float32), dev))
+        bn.bias.copy_(T(rng.standard_normal(C).astype(np.float32), dev))
+        bn.running_mean.copy_(T(rng.standard_normal(C).astype(np.float32), dev))
+    rm0, rv0 = bn.running_mean.cpu().numpy().copy(), bn.running_var.cpu().numpy().copy()
+    st = ops.bn_batch_stats(yv, bn)
+    y64 = y.astype(np.float64)
+    mu, var = y64.mean(0), y64.var(0)
+    assert np.abs(st.mean.cpu().numpy() - mu).max() < 1e-5 * max(1, np.abs(mu).max())
+    assert np.abs(st.invstd.cpu().numpy() * np.sqrt(var + 1e-5) - 1).max() < 1e-5
+    assert np.abs(bn.running_mean.cpu().numpy() - (0.9 * rm0 + 0.1 * mu)).max() < 1e-5
+    assert np.abs(bn.running_var.cpu().numpy() - (0.9 * rv0 + 0.1 * var * rows / (rows - 1))).max() < 1e-5 * max(1, var.max())
+    assert int(bn.num_batches_tracked) == 1
+    g, b = bn.weight.detach().cpu().numpy().astype(np.float64), bn.bias.detach().cpu().numpy().astype(np.float64)
+    want = np.maximum((y64 - mu) / np.sqrt(var + 1e-5) * g + b, 0)
+    z = ops.bn_act(yv, st, relu=True).cpu().numpy()
+    assert np.abs(z - want).max() < 2e-5 * max(1, np.abs(want).max())
+    if rows % 32 == 0:
+        pooled, am = ops.bn_act_max(yv, st, 32, relu=True)
+        w3 = want.reshape(rows // 32, 32, C)
+        assert np.abs(pooled.cpu().numpy() - w3.max(1)).max() < 2e-5 * max(1, np.abs(want).max())
+        got_am = am.cpu().numpy().astype(np.int64)
+        z3 = z.reshape(rows // 32, 32, C)
+        assert np.array_equal(got_am, z3.argmax(1))                      # first maximum of what the kernel itself computes
+        # backward through the pooling: gradient routed to the arg-max row only
+        dpool = rng.standard_normal((rows // 32, C)).astype(np.float32)
+        dy, dg, db = ops.bn_act_backward(yv, st, T(dpool, dev), relu=True, argmax=am, K=32)
+        dz = np.zeros((rows // 32, 32, C))
+        np.put_along_axis(dz, got_am[:, None, :], dpool[:, None, :].astype(np.float64), axis=1)
+        _check_bn_backward(y64, mu, var, g, z > 0, dz.reshape(rows, C), dy, dg, db)
+    dzr = rng.standard_normal((rows, C)).astype(np.float32)
+    dy, dg, db = ops.bn_act_backward(yv, st, T(dzr, dev), relu=True)
+    _check_bn_backward(y64, mu, var, g, z > 0, dzr.astype(np.float64), dy, dg, db)
+
+
+def _check_bn_backward(y64, mu, var, g, mask, dz, dy, dg, db):
+    invstd = 1 / np.sqrt(var + 1e-5)
+    xhat = (y64 - mu) * invstd
+    gz = dz * mask
+    want = g * invstd * (gz - gz.mean(0) - xhat * (gz * xhat).mean(0))
+    assert rl2(dy.cpu().numpy(), want) < 2e-5
+    assert rl2(dg.cpu().numpy(), (gz * xhat).sum(0)) < 2e-5
+    assert rl2(db.cpu().numpy(), gz.sum(0)) < 2e-5
+
+
+@pytest.mark.parametrize("rows,cout,cin,ldx", [(8192, 64, 67, 68), (100003, 128, 128, 128), (777, 19, 128, 128), (4096, 32, 4, 4),
+                                               (2048, 256, 320, 320), (50, 512, 259, 260)])
+def test_grad_weight_and_input_gradient(dev, rows, cout, cin, ldx):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(rows)
+    dy = rng.standard_normal((rows, cout)).astype(np.float32)
+    x = rng.standard_normal((rows, cin)).astype(np.float32)
+    w = rng.standard_normal((cout, cin)).astype(np.float32)
+    xb = torch.zeros((rows, ldx), device=dev)
+    xb[:, :cin] = T(x, dev)
+    dw = torch.zeros((cout, cin), device=dev)
+    db = torch.zeros((cout,), device=dev)
+    ops.grad_weight(T(dy, dev), xb[:, :cin], dw, db)
+    assert rl2(dw.cpu().numpy(), dy.astype(np.float64).T @ x.astype(np.float64)) < 1e-5
+    assert rl2(db.cpu().numpy(), dy.astype(np.float64).sum(0)) < 1e-5
+    ops.grad_weight(T(dy, dev), xb[:, :cin], dw, db)                      # accumulates
+    assert rl2(dw.cpu().numpy(), 2 * (dy.astype(np.float64).T @ x.astype(np.float64))) < 1e-5
+    wt = ops.transpose(T(w, dev))
+    assert np.array_equal(wt.cpu().numpy(), w.T)
+    dx = ops.linear(T(dy, dev), wt, None, relu=False)
+    assert rl2(dx.cpu().numpy(), dy.astype(np.float64) @ w.astype(np.float64)) < 1e-5
+
+
+def test_group_and_interpolate_backward(dev):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(5)
+    B, N, S, K, D = 2, 500, 64, 32, 13
+    idx = rng.integers(0, N, (B, S, K))
+    dg = rng.standard_normal((B * S * K, 3 + D)).astype(np.float32)
+    got = ops.group_backward(T(dg, dev), 3, D, T(idx, dev), N).cpu().numpy()
+    want = np.zeros((B, N, D))
+    for b in range(B):
+        np.add.at(want[b], idx[b].reshape(-1), dg.reshape(B, S * K, -1)[b, :, 3:].astype(np.float64))
+    assert rl2(got, want) < 1e-5
+    D1, D2, Sc = 7, 24, 40
+    nn_idx = rng.integers(0, Sc, (B, N, 3))
+    wgt = rng.dirichlet(np.ones(3), (B, N)).astype(np.float32)
+    dx = rng.standard_normal((B * N, D1 + D2)).astype(np.float32)
+    dp1, dp2 = ops.three_interpolate_backward(T(dx, dev), D1, D2, T(nn_idx, dev), T(wgt, dev), Sc)
+    assert np.array_equal(dp1.cpu().numpy(), dx.reshape(B, N, -1)[:, :, :D1])
+    want2 = np.zeros((B, Sc, D2))
+    for b in range(B):
+        for k in range(3):
+            np.add.at(want2[b], nn_idx[b, :, k], dx.reshape(B, N, -1)[b, :, D1:].astype(np.float64) * wgt[b, :, k:k + 1])
+    assert rl2(dp2.cpu().numpy(), want2) < 1e-5
+    _, dp2_only = ops.three_interpolate_backward(T(dx[:, D1:].copy(), dev), 0, D2, T(nn_idx, dev), T(wgt, dev), Sc)
+    assert rl2(dp2_only.cpu().numpy(), want2) < 1e-5
+
+
+def test_dropout(dev):
+    from pointnet12_b200 import ops
+
+    rows, C = 5000, 128
+    x = torch.randn((rows, C), device=dev)
+    seed = torch.tensor([1234, 1], dtype=torch.int64, device=dev)
+    y, mask = ops.dropout(x, 0.5, seed_offset=seed)
+    y2, mask2 = ops.dropout(x, 0.5, seed_offset=seed)
+    assert torch.equal(mask, mask2) and torch.equal(y, y2)                 # a stream is a function of (seed, offset)
+    _, mask3 = ops.dropout(x, 0.5, seed_offset=torch.tensor([1234, 2], dtype=torch.int64, device=dev))
+    assert not torch.equal(mask, mask3)
+    keep = mask.float().mean().item()
+    assert abs(keep - 0.5) < 4 * 0.5 / np.sqrt(rows * C)
+    assert abs(mask.float().mean(0).cpu().numpy() - 0.5).max() < 0.05 and abs(mask.float().mean(1).cpu().numpy() - 0.5).max() < 0.25
+    assert torch.equal(y, torch.where(mask.bool(), x * 2.0, torch.zeros_like(x)))
+    _, m25 = ops.dropout(x, 0.25, seed_offset=seed)
+    assert abs(m25.float().mean().item() - 0.75) < 0.005
+    given = (torch.rand((rows, C), device=dev) < 0.3).to(torch.uint8)
+    y4, m4 = ops.dropout(x, 0.5, mask=given)
+    assert m4 is given and torch.equal(y4, torch.where(given.bool(), x * 2.0, torch.zeros_like(x)))
+
+
+def test_cross_entropy_and_log_softmax_backward(dev):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(9)
+    rows, C = 4099, 19
+    logits = rng.standard_normal((rows, C)) * 3
+    logp = (logits - np.log(np.exp(logits).sum(-1, keepdims=True))).astype(np.float32)
+    tgt = rng.integers(0, C, rows)
+    loss, dx = ops.cross_entropy(T(logp, dev), T(tgt, dev))
+    xt = torch.from_numpy(logp.astype(np.float64)).requires_grad_(True)
+    ref = torch.nn.CrossEntropyLoss()(xt, torch.from_numpy(tgt))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert rl2(dx.cpu().numpy(), xt.grad.numpy()) < 1e-5
+    dy = rng.standard_normal((rows, C)).astype(np.float32)
+    lt = torch.from_numpy(logits).requires_grad_(True)
+    torch.log_softmax(lt, -1).backward(torch.from_numpy(dy.astype(np.float64)))
+    got = ops.log_softmax_backward(T(dy, dev), T(logp, dev)).cpu().numpy()
+    assert rl2(got, lt.grad.numpy()) < 1e-5
+
+
+def test_adam_kernel_vs_torch(dev):
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(3)
+    n = 100003
+    p0 = rng.standard_normal(n).astype(np.float32)
+    ref = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    p, m, v = T(p0, dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for step in range(1, 5):
+        g = (rng.standard_normal(n) * 10.0 ** rng.integers(-6, 1, n)).astype(np.float32)
+        ref.grad = torch.from_numpy(g.copy())
+        opt.step()
+        ops.adam_step(p, T(g, dev), m, v, step, 1e-3, (0.9, 0.999), 1e-8, 1e-4)
+        assert np.abs(p.cpu().numpy() - ref.detach().numpy()).max() < 1e-6
+    ops.adam_step(p, T(g * 4, dev), m, v, 5, 1e-3, (0.9, 0.999), 1e-8, 1e-4, grad_scale=0.25)   # all-reduce sum / world
+    ref.grad = torch.from_numpy(g.copy())
+    opt.step()
+    assert np.abs(p.cpu().numpy() - ref.detach().numpy()).max() < 1e-6
+
+
+def test_seg_metrics_bit_exact(dev):
+    """pcdseg.py:58-97: per-class I/U per batch, fp32 accumulation of double ratios, accuracy list."""
+    from pointnet12_b200.train import SegMetrics
+
+    rng = np.random.default_rng(11)
+    k = 19
+    batches = []
+    m = SegMetrics(k, dev)
+    for i in range(3):
+        logp = np.log(rng.dirichlet(np.ones(k), size=(4, 6000))).astype(np.float32)
+        tgt = rng.integers(0, k if i else 7, size=(4, 6000))
+        if i == 0:
+            logp[..., 15:] = -50.0
+        batches.append((logp, tgt))
+        m.update(T(logp, dev), T(tgt, dev))
+    acc, miou, cat = tor.test_kitti_semseg(batches, k)
+    got_acc, got_miou, got_cat = m.result()
+    assert np.array_equal(got_cat, cat)
+    assert got_miou == miou
+    assert abs(got_acc - acc) < 1e-15
+    from pointnet12_b200 import ops
+
+    counts, pred = ops.seg_metrics(T(batches[1][0], dev), T(batches[1][1], dev), want_pred=True)
+    I, P, Tt, correct = tor.seg_counts(*batches[1])
+    c = counts.cpu().numpy()
+    assert np.array_equal(c[:k], I) and np.array_equal(c[k:2 * k], P) and np.array_equal(c[2 * k:3 * k], Tt) and c[3 * k] == correct
+    assert np.array_equal(pred.cpu().numpy(), batches[1][0].argmax(-1))
+
+
+# ------------------------------------------------------------------------------------------------ blocks
+def _grads(module):
+    return {n: p.grad.detach().cpu().numpy() for n, p in module.named_parameters()}
+
+
+def test_sa_block_train_vs_reference(dev, golden):
+    from pointnet12_b200.model import pointnet_util as ours
+
+    g = golden("train_blocks_seeded")
+    xyz, f1, _, _, g_sa, _ = block_inputs()
+    sa = seeded_block(lambda: ours.PointNetSetAbstraction(256, 0.2, 32, 64 + 3, [64, 64, 128], False), 4321).to(dev)
+    pts = T(f1, dev).requires_grad_(True)
+    new_xyz, out = sa(T(xyz, dev), pts, start_idx=T(g["sa.start"].astype(np.int64), dev))
+    assert out.shape == (2, 128, 256) and out.requires_grad
+    out.backward(T(g_sa, dev))
+    assert rl2(out.detach().cpu().numpy(), g["sa.out"]) < 2e-5
+    assert rl2(pts.grad.cpu().numpy(), g["sa.dpoints"]) < 1e-4
+    for n, gr in _grads(sa).items():
+        ref = g["sa.grad." + n]
+        if "convs" in n and n.endswith("bias"):
+            assert np.abs(gr).max() < 1e-3, n                             # true gradient 0 (BatchNorm follows)
+        else:
+            assert rl2(gr, ref) < 1e-4, (n, rl2(gr, ref))
+    for n, b in sa.named_buffers():
+        ref = g["sa.buffer." + n]
+        assert np.abs(b.cpu().numpy().astype(np.float64) - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), n
+
+
+def test_fp_block_train_vs_reference(dev, golden):
+    from pointnet12_b200.model import pointnet_util as ours
+
+    g = golden("train_blocks_seeded")
+    xyz, f1, xyz2, f2, _, g_fp = block_inputs()
+    fp = seeded_block(lambda: ours.PointNetFeaturePropagation(320, [256, 128]), 4322).to(dev)
+    p1, p2 = T(f1, dev).requires_grad_(True), T(f2, dev).requires_grad_(True)
+    out = fp(T(xyz, dev), T(xyz2, dev), p1, p2)
+    out.backward(T(g_fp, dev))
+    assert rl2(out.detach().cpu().numpy(), g["fp.out"]) < 2e-5
+    assert rl2(p1.grad.cpu().numpy(), g["fp.dpoints1"]) < 1e-4
+    assert rl2(p2.grad.cpu().numpy(), g["fp.dpoints2"]) < 1e-4
+    for n, gr in _grads(fp).items():
+        if "convs" in n and n.endswith("bias"):
+            assert np.abs(gr).max() < 1e-3, n
+        else:
+            assert rl2(gr, g["fp.grad." + n]) < 1e-4, (n, rl2(gr, g["fp.grad." + n]))
+
+
+# ------------------------------------------------------------------------------------------------ the step
+def _train_net(dev, ckpt_path):
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+
+    net = PointNet2SemSeg(19, feature_dims=1)
+    sd = torch.load(ckpt_path, map_location="cpu")
+    net.load_state_dict({k[len("module."):]: v for k, v in sd.items()}, strict=True)
+    return net.to(dev).train()
+
+
+def test_train_step_vs_reference_and_oracle(dev, golden, ckpt_path, ckpt_state):
+    """The reference's own iteration, written as in pcdseg.py:166-186, on our modules."""
+    from pointnet12_b200.train import cross_entropy, semseg_forward_train
+
+    g, pts, target, starts, keep = step_inputs(golden)
+    net = _train_net(dev, ckpt_path)
+    mask = T(keep.astype(np.uint8), dev)
+    logp = semseg_forward_train(net, T(pts, dev), fps_starts=[T(s, dev) for s in starts], dropout_mask=mask)
+    assert logp.shape == (2, 2048, 19) and logp.grad_fn is not None
+    loss = torch.nn.CrossEntropyLoss()(logp.transpose(2, 1), T(target, dev))       # torch's loss on our output: drop-in
+    net.zero_grad()
+    loss.backward()
+    grads = _grads(net)
+    buffers = {n: b.cpu().numpy() for n, b in net.named_buffers()}
+    # band 3: the CUDA path is a third float32 evaluation order of a computation whose float32 results already differ
+    # from each other by this much (see tests/test_train_oracle.py)
+    check_step_against_golden(g, loss.item(), logp.detach().cpu().numpy(), grads, buffers, band=3.0)
+    out = tor.semseg_train_step(ckpt_state, pts, target, starts, keep)
+    assert rl2(logp.detach().cpu().numpy(), out["logp"]) < 5e-4
+    assert rl2(grads["conv2.weight"], out["grads"]["conv2.weight"]) < 2e-4
+    assert rl2(grads["sa1.mlp_convs.0.weight"], out["grads"]["sa1.mlp_convs.0.weight"]) < 2e-2
+    # our fused loss kernel = torch's loss and gradient
+    net2 = _train_net(dev, ckpt_path)
+    logp2 = semseg_forward_train(net2, T(pts, dev), fps_starts=[T(s, dev) for s in starts], dropout_mask=mask)
+    loss2 = cross_entropy(logp2, T(target, dev))
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) < 1e-5
+    g2 = _grads(net2)
+    assert rl2(g2["conv2.weight"], grads["conv2.weight"]) < 1e-5 and rl2(g2["fp1.mlp_convs.0.weight"], grads["fp1.mlp_convs.0.weight"]) < 1e-3
+
+
+def test_reference_training_loop_runs_and_learns(dev):
+    """pcdseg.py:112-186 in miniature: model.train(), torch Adam with the reference's hyper-parameters, a few iterations on
+    one batch -- the loss must fall; then FlatAdam (one flat buffer, one kernel) must track torch.optim.Adam."""
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+    from pointnet12_b200.train import FlatAdam, cross_entropy
+
+    pts = T(syn.kitti_batch(4, 2048, config=5), dev)
+    target = (pts[:, 2, :] > pts[:, 2, :].median()).long() + 2 * (pts[:, 3, :] > 0).long()     # a learnable labelling
+    torch.manual_seed(1)
+    a = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    b = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    b.load_state_dict(a.state_dict())
+    a.drop1.p = b.drop1.p = 0.0                      # identical arithmetic in both replicas
+    opt_a = torch.optim.Adam(a.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    opt_b = FlatAdam(b.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    losses = []
+    for it in range(6):
+        starts = [torch.randint(0, n, (4,), dtype=torch.long).to(dev) for n in (2048, 1024, 256, 64)]
+        la = torch.nn.CrossEntropyLoss()(a(pts, fps_starts=starts).transpose(2, 1), target)
+        opt_a.zero_grad()
+        la.backward()
+        opt_a.step()
+        lb = cross_entropy(b(pts, fps_starts=starts), target)
+        opt_b.zero_grad()
+        lb.backward()
+        opt_b.step()
+        losses.append((la.item(), lb.item()))
+    assert losses[-1][0] < 0.7 * losses[0][0], losses
+    assert abs(losses[0][0] - losses[0][1]) < 1e-4, losses
+    assert abs(losses[-1][0] - losses[-1][1]) < 0.05 * losses[-1][0], losses     # atomics order + Adam's sign-like first steps
+    # eval after training uses the updated running statistics through the fused inference path
+    with torch.no_grad():
+        out = b.eval()(pts, fps_starts=starts)
+    assert torch.isfinite(out).all() and (out.argmax(-1) == target).float().mean().item() > 0.5

@@ -1,0 +1,112 @@
+"""Config C5 (BASELINE.json configs[4]): PointNet2SemSeg training step, batch 8 x 8000 points per GPU, data-parallel.
+
+    python tools/bench_train.py [--steps 20 --warmup 5 --batch 8 --points 8000]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_train.py
+
+A step = forward in train() mode (batch-statistics BatchNorm, dropout) + the reference's loss + backward + gradient
+all-reduce (NCCL, one flat 3.9 MB buffer; skipped at N=1) + Adam, all through the package's public training API
+(pointnet12_b200.train).  Inputs resident; CUDA events around every step; MAX over ranks.  Prints one JSON line
+(rank 0) with points/s, ms/step and the per-phase split of an extra instrumented step.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--points", type=int, default=8000)
+    args = ap.parse_args()
+    import torch.distributed as dist
+
+    from pointnet12_b200 import _native as nv, synthetic as syn
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+    from pointnet12_b200.train import FlatAdam, cross_entropy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)                                   # same initial weights on every rank (DataParallel replicas)
+    net = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    opt = FlatAdam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    B, N = args.batch, args.points
+    pts = torch.from_numpy(syn.kitti_batch(B, N, config=5, first=rank * B)).to(dev)
+    target = torch.from_numpy(np.random.default_rng(5000 + rank).integers(0, 19, size=(B, N))).to(dev)
+    torch.manual_seed(rank)
+
+    def step(marks=None):
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
+        logp = net(pts)
+        mark("forward")
+        loss = cross_entropy(logp, target)
+        mark("loss")
+        opt.zero_grad()
+        loss.backward()
+        mark("backward")
+        scale = opt.all_reduce()
+        mark("allreduce")
+        opt.step(scale)
+        mark("adam")
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n0 = nv.launch_count
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = step()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    launches = nv.launch_count - n0
+    times = np.array([a.elapsed_time(b) for a, b in evs])
+    total = torch.tensor([times.sum()], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    marks = []
+    step(marks)
+    torch.cuda.synchronize()
+    phases = {n1: round(e0.elapsed_time(e1), 4) for (n0_, e0), (n1, e1) in zip(marks[:-1], marks[1:])}
+    if rank == 0:
+        ms = float(total.item()) / args.steps
+        print(json.dumps({
+            "metric": "pointnet2_semseg_train_points_per_sec", "value": world * B * N / (ms * 1e-3), "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "dtype": "f32 (CUDA-core GEMMs)", "data": "synthetic",
+            "config": {"workload": f"C5: PointNet2SemSeg(19, feature_dims=1) training step (forward, CrossEntropyLoss, backward, "
+                                   f"gradient all-reduce, Adam), {B} clouds x {N} points per GPU, seeded random init",
+                       "l2": "256 MiB written between timed steps", "launch": "eager"},
+            "step_ms": {"min": float(times.min()), "median": float(np.median(times)), "max": float(times.max())},
+            "phases_ms": phases, "gpu_launches": int(launches), "final_loss": float(loss.item())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
