@@ -207,6 +207,11 @@ size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc);
  * bias themselves live in HOST memory.  blob: 128-byte aligned device buffer. */
 int pn_mlp_pack_bf16x3(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, void* blob,
                        pn_stream_t stream);
+/* The same with transposed[l] != 0 (host array, may be NULL) marking layers whose w[l] points to the TRANSPOSE of the
+ * layer's weight, i.e. a row-major [cin[l], cout[l]] matrix.  The training step packs W^T this way for the input-gradient
+ * GEMM dx = dy W (backward of a 1x1 conv) without materialising the transpose. */
+int pn_mlp_pack_t_bf16x3(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, const int* transposed,
+                         void* blob, pn_stream_t stream);
 
 /* Output modes of the fused chains. */
 enum pn_mlp_out { PN_MLP_OUT_ROWS = 0, PN_MLP_OUT_MAX32 = 1, PN_MLP_OUT_LOG_SOFTMAX = 2 };
@@ -306,7 +311,8 @@ int pn_bn_act_max_f32(const float* y, int64_t ldy, int64_t groups, int K, int C,
 int pn_bn_bwd_stats_f32(const float* y, int64_t ldy, int64_t rows, int C, const float* dz, int64_t lddz,
                         const int32_t* argmax, int K, const float* scale, const float* shift, const float* mean,
                         const float* invstd, int relu, double* s1, double* s2, pn_stream_t stream);
-/* Second pass: dy = gamma*invstd*(g - s1/rows - xhat*s2/rows); dgamma = s2, dbeta = s1 (may be NULL). */
+/* Second pass: dy = gamma*invstd*(g - s1/rows - xhat*s2/rows); dgamma += s2, dbeta += s1 (may be NULL; accumulated like
+ * dw / db, so the caller zeroes them or passes the parameter's gradient buffer). */
 int pn_bn_bwd_apply_f32(const float* y, int64_t ldy, int64_t rows, int C, const float* dz, int64_t lddz,
                         const int32_t* argmax, int K, const float* scale, const float* shift, const float* mean,
                         const float* invstd, int relu, const double* s1, const double* s2, float* dy, int64_t lddy,
@@ -344,6 +350,11 @@ int pn_log_softmax_bwd_f32(const float* dy, int64_t lddy, const float* y, int64_
  * grad_scale = 1/world_size after a summing all-reduce. */
 int pn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                 float beta2, float eps, float weight_decay, int64_t step, float grad_scale, pn_stream_t stream);
+/* The same update with the learning rate (*lr) and the step count (*step, incremented first: start it at 0) in DEVICE
+ * memory, so that a captured CUDA graph replays with the current values. */
+int pn_adam_dev_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr,
+                    int64_t* step, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                    pn_stream_t stream);
 /* test_kitti_semseg's inner loop (pcdseg.py:72-83) without host round trips: pred (may be NULL) [rows] = argmax over
  * the C <= 64 classes; counts int64 [3C+1] (overwritten) = per class intersection | predicted | target, then the
  * number of correct points. */

@@ -57,6 +57,7 @@ _SIGNATURES = {
                                  vp],
     "pn_log_softmax_f32": [vp, i64, i64, i32, vp, i64, vp],
     "pn_mlp_pack_bf16x3": [_descp, C.POINTER(vp), C.POINTER(vp), vp, vp],
+    "pn_mlp_pack_t_bf16x3": [_descp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp, vp],
     "pn_mlp_rows_bf16x3": [_descp, vp, vp, i64, i64, i32, vp, i64, vp],
     "pn_sa_mlp_max_bf16x3": [_descp, vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32,
                              i32, i32, vp, i64, vp],
@@ -83,6 +84,7 @@ _SIGNATURES = {
     "pn_cross_entropy_f32": [vp, i64, vp, i64, i32, vp, vp, vp, i64, f32, vp],
     "pn_log_softmax_bwd_f32": [vp, i64, vp, i64, i64, i32, vp, i64, vp],
     "pn_adam_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp],
+    "pn_adam_dev_f32": [vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, f32, vp],
     "pn_seg_metrics_f32": [vp, i64, vp, i64, i32, vp, vp, vp],
     "pn_seg_metrics_accumulate": [vp, i32, i64, vp, vp, vp, vp, vp],
 }

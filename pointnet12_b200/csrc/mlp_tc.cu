@@ -96,12 +96,15 @@ static bool plan_chain(const pn_mlp_desc* d, TcChain* c, const char** why) {
 // ------------------------------------------------------------------------------------------------ packing
 // Weight image of one (pass, K slice): element (n, k) at (n/8)*SBO + (k/8)*128 + (n%8)*16 + (k%8)*2 bytes,
 // SBO = (kw/8)*128; hi image first, lo image right after it.
+// Element (n, k) of the layer's weight is w[n*sn + k*sk]: (sn, sk) = (k_real, 1) for a row-major [n, k] matrix, (1, n_real)
+// for the TRANSPOSE of a row-major [k, n] matrix (the input-gradient GEMM dx = dy W of the training step reads W^T).
 __global__ void tc_pack_layer_kernel(const float* __restrict__ w, const float* __restrict__ bias, int k_real, int k_pad,
-                                     int n_real, int n_pad, unsigned char* __restrict__ img, float* __restrict__ bias_out) {
+                                     int n_real, int n_pad, int sn, int sk, unsigned char* __restrict__ img,
+                                     float* __restrict__ bias_out) {
     const int total = n_pad * k_pad;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int n = e / k_pad, k = e % k_pad;
-        const float v = (n < n_real && k < k_real) ? w[(size_t)n * k_real + k] : 0.0f;
+        const float v = (n < n_real && k < k_real) ? w[(size_t)n * sn + (size_t)k * sk] : 0.0f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         const int p = n / kTcNPass, np = n % kTcNPass;
@@ -1305,8 +1308,21 @@ PN_EXPORT size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc) {
     return ch.blob_bytes;
 }
 
+static int tc_pack(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, const int* transposed, void* blob,
+                   pn_stream_t stream);
+
 PN_EXPORT int pn_mlp_pack_bf16x3(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, void* blob,
                                  pn_stream_t stream) {
+    return tc_pack(desc, w, bias, nullptr, blob, stream);
+}
+
+PN_EXPORT int pn_mlp_pack_t_bf16x3(const pn_mlp_desc* desc, const float* const* w, const float* const* bias,
+                                   const int* transposed, void* blob, pn_stream_t stream) {
+    return tc_pack(desc, w, bias, transposed, blob, stream);
+}
+
+static int tc_pack(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, const int* transposed, void* blob,
+                   pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
     const char* why;
@@ -1319,8 +1335,10 @@ PN_EXPORT int pn_mlp_pack_bf16x3(const pn_mlp_desc* desc, const float* const* w,
         unsigned char* img = static_cast<unsigned char*>(blob) + L.w_off;
         float* bo = reinterpret_cast<float*>(static_cast<unsigned char*>(blob) + ch.bias_off) + L.b_off;
         const int total = L.n_pad * L.k_pad;
+        const bool tr = transposed && transposed[l];
         tc_pack_layer_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w[l], bias ? bias[l] : nullptr, L.k_real,
-                                                                                    L.k_pad, L.n_real, L.n_pad, img, bo);
+                                                                                    L.k_pad, L.n_real, L.n_pad, tr ? 1 : L.k_real,
+                                                                                    tr ? L.n_real : 1, img, bo);
     }
     return finish_launch("pn_mlp_pack_bf16x3");
 }

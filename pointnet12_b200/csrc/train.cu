@@ -164,7 +164,7 @@ __global__ void bn_act_max_kernel(const float* __restrict__ y, int64_t ldy, int6
     }
 }
 
-// dy = gamma*invstd * (g - s1/n - xhat*s2/n); block 0 also writes dgamma = s2, dbeta = s1.
+// dy = gamma*invstd * (g - s1/n - xhat*s2/n); block 0 also adds s2 to dgamma and s1 to dbeta.
 template <int MODE>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ y, int64_t ldy, int64_t rows, int C,
                                     const float* __restrict__ dz, int64_t lddz, const int32_t* __restrict__ argmax, int K,
@@ -177,8 +177,8 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ y, int64_t ldy, in
     const double inv_n = 1.0 / (double)rows;
     if (blockIdx.x == 0) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            if (dgamma) dgamma[c] = (float)s2[c];
-            if (dbeta) dbeta[c] = (float)s1[c];
+            if (dgamma) dgamma[c] += (float)s2[c];      // accumulated, like dW / db (a single writer: no atomics)
+            if (dbeta) dbeta[c] += (float)s1[c];
         }
     }
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -479,6 +479,30 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// The same update with the learning rate and the step count in DEVICE memory, so that a captured CUDA graph replays
+// with the current values: *step is incremented by a one-thread kernel first, then every thread derives the bias
+// corrections from it (double precision, like the host variant).
+__global__ void adam_step_increment_kernel(int64_t* step) { *step += 1; }
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr,
+                                const int64_t* __restrict__ step_ptr, float beta1, float beta2, float eps,
+                                float weight_decay, float grad_scale) {
+    const double step = (double)*step_ptr;
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    const float lr_over_bc1 = (float)((double)*lr_ptr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float pi = p[i];
+        const float gi = fmaf(weight_decay, pi, g[i] * grad_scale);
+        const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);
+        const float vi = fmaf(1.0f - beta2, gi * gi, v[i] * beta2);
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - lr_over_bc1 * (mi / denom);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Evaluation metrics of pcdseg.py:72-83: arg-max label per point, per-class intersection / prediction / target
 // counts and the number of correct points -- one pass over the log-probabilities, block-local histograms.
@@ -625,19 +649,25 @@ PN_EXPORT int pn_grad_weight_f32(const float* dy, int64_t lddy, const float* x, 
     PN_REQUIRE(dy && x && dw, PN_ERR_BAD_ARG, "pn_grad_weight_f32: null pointer");
     PN_REQUIRE(rows > 0 && cout > 0 && cin > 0 && lddy >= cout && ldx >= cin && lddw >= cin, PN_ERR_BAD_ARG,
                "pn_grad_weight_f32: bad shape");
-    constexpr int BM = 64, BN = 64, BK = 16;
     int vec_ok = 0;
     if (((uintptr_t)dy % 16 == 0) && (lddy % 4 == 0)) vec_ok |= 1;
     if (((uintptr_t)x % 16 == 0) && (ldx % 4 == 0)) vec_ok |= 2;
+    // 128 x 128 tiles with 8 x 8 register tiles for the wide layers (64 FMAs per 4 shared-memory loads), 64 x 64 otherwise
+    const bool wide = cout > 64 && cin > 64;
+    const int BM = wide ? 128 : 64, BN = BM, BK = wide ? 8 : 16;
     const int64_t tiles = ceil_div(cout, BM) * ceil_div(cin, BN);
-    int64_t splits = ceil_div((int64_t)sm_count() * 4, tiles);
+    int64_t splits = ceil_div((int64_t)sm_count() * (wide ? 2 : 4), tiles);
     int64_t rps = ceil_div(ceil_div(rows, splits), BK) * BK;
-    if (rps < 4 * BK) rps = 4 * BK;
+    if (rps < 64) rps = 64;
     splits = ceil_div(rows, rps);
     PN_REQUIRE(splits <= 65535, PN_ERR_UNSUPPORTED, "pn_grad_weight_f32: too many row splits");
     dim3 grid((unsigned)ceil_div(cout, BM), (unsigned)ceil_div(cin, BN), (unsigned)splits);
-    grad_weight_kernel<BM, BN, BK, 4, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, rows, rps, cout, cin, dw, lddw, db,
-                                                                                vec_ok);
+    if (wide)
+        grad_weight_kernel<128, 128, 8, 8, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, rows, rps, cout, cin, dw, lddw,
+                                                                                     db, vec_ok);
+    else
+        grad_weight_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, rows, rps, cout, cin, dw, lddw,
+                                                                                    db, vec_ok);
     return finish_launch("pn_grad_weight_f32");
 }
 
@@ -715,6 +745,18 @@ PN_EXPORT int pn_adam_f32(float* param, const float* grad, float* exp_avg, float
                                                                     beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)),
                                                                     grad_scale);
     return finish_launch("pn_adam_f32");
+}
+
+PN_EXPORT int pn_adam_dev_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              const float* lr, int64_t* step, float beta1, float beta2, float eps, float weight_decay,
+                              float grad_scale, pn_stream_t stream) {
+    PN_REQUIRE(param && grad && exp_avg && exp_avg_sq && lr && step, PN_ERR_BAD_ARG, "pn_adam_dev_f32: null pointer");
+    PN_REQUIRE(n > 0, PN_ERR_BAD_ARG, "pn_adam_dev_f32: n must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_step_increment_kernel<<<1, 1, 0, st>>>(step);
+    adam_dev_kernel<<<ew_blocks(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, step, beta1, beta2, eps, weight_decay,
+                                                      grad_scale);
+    return finish_launch("pn_adam_dev_f32");
 }
 
 PN_EXPORT int pn_seg_metrics_f32(const float* logp, int64_t ldx, const int64_t* target, int64_t rows, int C,

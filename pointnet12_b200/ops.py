@@ -464,26 +464,32 @@ LAYERWISE_MAX_TILES = int(os.environ.get("PN12_LAYERWISE_TILES", "0"))
 class PackedChain:
     """A conv+BN(+ReLU) chain folded and packed for the tensor-core kernels (device blob + descriptor)."""
 
-    def __init__(self, layers: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], bool]]):
+    def __init__(self, layers: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], bool]], transposed: bool = False):
+        """layers = [(w [cout, cin], bias or None, relu)].  transposed: every w is given as the TRANSPOSE of the layer's
+        weight, a row-major [cin, cout] matrix (the input-gradient GEMM of the training step packs W^T this way)."""
         self.desc = nv.MlpDesc()
         self.desc.nlayers = len(layers)
         for i, (w, _, relu) in enumerate(layers):
-            self.desc.cout[i], self.desc.cin[i] = int(w.shape[0]), int(w.shape[1])
+            co, ci = (int(w.shape[1]), int(w.shape[0])) if transposed else (int(w.shape[0]), int(w.shape[1]))
+            self.desc.cout[i], self.desc.cin[i] = co, ci
             self.desc.relu[i] = int(bool(relu))
-        self.cin, self.cout = int(layers[0][0].shape[1]), int(layers[-1][0].shape[0])
+        self.cin, self.cout = int(self.desc.cin[0]), int(self.desc.cout[len(layers) - 1])
         nbytes = nv.lib().pn_mlp_blob_bytes(C.byref(self.desc))
         if nbytes == 0:
             raise RuntimeError("chain not supported by the tensor-core path: "
                                + nv.lib().pn_last_error_string().decode("utf-8", "replace"))
         dev = layers[0][0].device
-        self.blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)      # the pack kernels write every byte (padding = 0)
         ws = [_f32(w, "w").contiguous() for w, _, _ in layers]
         bs = [None if b is None else _f32(b, "bias").contiguous() for _, b, _ in layers]
         n = len(layers)
         wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
         bp = (C.c_void_p * n)(*[None if b is None else b.data_ptr() for b in bs])
         with _on_device(self.blob):
-            nv.call("pn_mlp_pack_bf16x3", C.byref(self.desc), wp, bp, self.blob.data_ptr(), _stream())
+            if transposed:
+                nv.call("pn_mlp_pack_t_bf16x3", C.byref(self.desc), wp, bp, (C.c_int * n)(*([1] * n)), self.blob.data_ptr(), _stream())
+            else:
+                nv.call("pn_mlp_pack_bf16x3", C.byref(self.desc), wp, bp, self.blob.data_ptr(), _stream())
         self._keep = (ws, bs)     # the pack kernels read them asynchronously
 
     @staticmethod
@@ -683,20 +689,25 @@ def bn_act_max(y: torch.Tensor, st: BatchStats, K: int, relu: bool = True) -> Tu
 
 
 def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: bool = True,
-                    argmax: Optional[torch.Tensor] = None, K: int = 1):
-    """Backward of act(bn(y)) with batch statistics -> (dy [rows, C], dgamma [C], dbeta [C]).
+                    argmax: Optional[torch.Tensor] = None, K: int = 1, dgamma: Optional[torch.Tensor] = None,
+                    dbeta: Optional[torch.Tensor] = None):
+    """Backward of act(bn(y)) with batch statistics.  dgamma / dbeta given ([C] float32 buffers): the affine gradients
+    are ADDED to them and dy [rows, C] is returned; otherwise -> (dy, dgamma, dbeta) with fresh buffers.
     argmax/K: dz is the pooled gradient [rows/K, C] of bn_act_max."""
     y, dz = _rowmat(y, "y"), _rowmat(dz, "dz")
     rows, Cc = y.shape
     acc = torch.zeros((2, Cc), dtype=torch.float64, device=y.device)
     dy = torch.empty((rows, Cc), dtype=torch.float32, device=y.device)
-    dgb = torch.empty((2, Cc), dtype=torch.float32, device=y.device)
+    fresh = dgamma is None
+    if fresh:
+        dgb = torch.zeros((2, Cc), dtype=torch.float32, device=y.device)
+        dgamma, dbeta = dgb[0], dgb[1]
     common = (y.data_ptr(), _ld(y), rows, Cc, dz.data_ptr(), _ld(dz), _p(argmax), int(K), st.scale.data_ptr(),
               st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), int(relu), acc[0].data_ptr(), acc[1].data_ptr())
     with _on_device(y):
         nv.call("pn_bn_bwd_stats_f32", *common, _stream())
-        nv.call("pn_bn_bwd_apply_f32", *common, dy.data_ptr(), Cc, dgb[0].data_ptr(), dgb[1].data_ptr(), _stream())
-    return dy, dgb[0], dgb[1]
+        nv.call("pn_bn_bwd_apply_f32", *common, dy.data_ptr(), Cc, dgamma.data_ptr(), dbeta.data_ptr(), _stream())
+    return (dy, dgamma, dbeta) if fresh else dy
 
 
 def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
@@ -802,6 +813,17 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
         nv.call("pn_adam_f32", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
                 float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale),
                 _stream())
+
+
+def adam_step_dev(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                  lr: torch.Tensor, step: torch.Tensor, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                  grad_scale: float = 1.0) -> None:
+    """adam_step with the learning rate (float32 [1]) and the step counter (int64 [1], incremented by the call) on the
+    device: capturable in a CUDA graph."""
+    with _on_device(param):
+        nv.call("pn_adam_dev_f32", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                lr.data_ptr(), step.data_ptr(), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                float(grad_scale), _stream())
 
 
 def seg_metrics(logp: torch.Tensor, target: torch.Tensor, want_pred: bool = False):

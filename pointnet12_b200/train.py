@@ -16,8 +16,9 @@ On top of that, the pieces a B200-native training loop uses instead of the torch
                                    exchange is a single all-reduce of 3.9 MB and Adam is a single kernel launch
     SegMetrics(num_classes)        argmax + per-class I/U + accuracy accumulated on the device (no .item() per class)
 
-Layers are computed in exact fp32 on the CUDA cores here (pn_linear_f32 / pn_grad_weight_f32); moving the training
-GEMMs onto the tcgen05 chains is the next step for this row.
+The forward and input-gradient GEMMs run on the tensor cores (single-layer tcgen05 chains, 3-pass split bf16 = fp32 parity,
+weights re-packed every iteration); the weight-gradient GEMM (reduction over the rows) is a CUDA-core kernel with fp32
+atomics; `ops.set_mlp_mode("fp32")` puts every GEMM on the CUDA cores.
 """
 from __future__ import annotations
 
@@ -34,12 +35,31 @@ def _w2d(conv) -> torch.Tensor:
     return conv.weight.detach().reshape(conv.weight.shape[0], -1)
 
 
+def _gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], transposed: bool = False) -> torch.Tensor:
+    """x [rows, cin] @ W^T + bias with W = w [cout, cin] (or, transposed=True, W = w^T for w [cin, cout]: the input-
+    gradient GEMM dx = dy W of a conv with weight w).  Tensor cores (single-layer tcgen05 chain, 3-pass split bf16 = fp32
+    parity; the weight is re-packed on every call because it changes every iteration) unless the MLP mode is 'fp32'."""
+    cout, cin = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+    if ops.mlp_mode() == "bf16x3" and ops.PackedChain.supported([(cin, cout)]):
+        return ops.mlp_rows_tc(ops.PackedChain([(w, bias, False)], transposed=transposed), x)
+    return ops.linear(x, ops.transpose(w) if transposed else w, bias, relu=False)
+
+
+def _grad_sink(p: torch.Tensor, shape) -> Tuple[torch.Tensor, bool]:
+    """Where the gradient of parameter p is accumulated: straight into p.grad when an optimizer with a flat gradient
+    buffer owns it (FlatAdam marks its parameters; the kernels add atomically, so no per-parameter add launch is needed
+    and the Function returns None for it), else into a fresh zero tensor that autograd accumulates."""
+    if getattr(p, "_pn_direct_grad", False) and p.grad is not None:
+        return p.grad.view(shape), True
+    return torch.zeros(shape, dtype=torch.float32, device=p.device), False
+
+
 def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] = None):
     """x [rows, cin] -> (output, saved).  layers = [(conv, bn or None, relu)]; pool_K: the last layer's activation is
     max-pooled over runs of K rows (set abstraction)."""
     saved = []
     for li, (conv, bn, relu) in enumerate(layers):
-        y = ops.linear(x, _w2d(conv), conv.bias.detach() if conv.bias is not None else None, relu=False)
+        y = _gemm(x, _w2d(conv), conv.bias.detach() if conv.bias is not None else None)
         st, am = None, None
         if bn is not None:
             st = ops.bn_batch_stats(y, bn)
@@ -63,19 +83,19 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
         conv, bn, relu = layers[li]
         x, y, st, _, am = saved[li]
         dgamma = dbeta = None
+        g_direct = False
         if st is not None:
-            dy, dgamma, dbeta = ops.bn_act_backward(y, st, dz, relu, argmax=am, K=pool_K if am is not None else 1)
+            dgamma, g_direct = _grad_sink(bn.weight, bn.weight.shape)
+            dbeta, _ = _grad_sink(bn.bias, bn.bias.shape)
+            dy = ops.bn_act_backward(y, st, dz, relu, argmax=am, K=pool_K if am is not None else 1, dgamma=dgamma, dbeta=dbeta)
         else:
             dy = dz
         w = _w2d(conv)
-        dw = torch.zeros_like(w)
-        db = torch.zeros((w.shape[0],), dtype=torch.float32, device=w.device) if conv.bias is not None else None
-        ops.grad_weight(dy, x[:, :w.shape[1]] if x.shape[1] != w.shape[1] else x, dw, db)
-        grads[li] = (dw, db, dgamma, dbeta)
-        if li > 0 or need_dx:
-            dz = ops.linear(dy, ops.transpose(w), None, relu=False)
-        else:
-            dz = None
+        dw, w_direct = _grad_sink(conv.weight, w.shape)
+        db, b_direct = _grad_sink(conv.bias, (w.shape[0],)) if conv.bias is not None else (None, False)
+        ops.grad_weight(dy, x, dw, db)
+        grads[li] = (None if w_direct else dw, None if b_direct else db, None if g_direct else dgamma, None if g_direct else dbeta)
+        dz = _gemm(dy, w, None, transposed=True) if (li > 0 or need_dx) else None
     return dz, grads
 
 
@@ -93,7 +113,7 @@ def _layer_params(layers) -> List[torch.Tensor]:
 def _layer_grads(layers, grads) -> List[torch.Tensor]:
     out = []
     for (conv, bn, _), (dw, db, dgamma, dbeta) in zip(layers, grads):
-        out.append(dw.view_as(conv.weight))
+        out.append(dw.view_as(conv.weight) if dw is not None else None)
         if conv.bias is not None:
             out.append(db)
         if bn is not None:
@@ -173,7 +193,7 @@ class SegHeadFn(torch.autograd.Function):
             zd, mask = ops.dropout(z1, p, seed_offset=seed_offset, mask=mask)
         else:
             zd, mask = z1, None
-        logits = ops.linear(zd, _w2d(net.conv2), net.conv2.bias.detach(), relu=False)
+        logits = _gemm(zd, _w2d(net.conv2), net.conv2.bias.detach())
         logp = ops.log_softmax(logits)
         ctx.net, ctx.saved, ctx.tail = net, saved, (zd, mask, logp, p)
         return logp.view(B, N, -1)
@@ -185,15 +205,17 @@ class SegHeadFn(torch.autograd.Function):
         k = logp.shape[1]
         dlogits = ops.log_softmax_backward(_rows_of(dlogp, k), logp)
         w2 = _w2d(net.conv2)
-        dw2, db2 = torch.zeros_like(w2), torch.zeros((k,), dtype=torch.float32, device=w2.device)
+        dw2, w_direct = _grad_sink(net.conv2.weight, w2.shape)
+        db2, b_direct = _grad_sink(net.conv2.bias, (k,))
         ops.grad_weight(dlogits, zd, dw2, db2)
-        dzd = ops.linear(dlogits, ops.transpose(w2), None, relu=False)
+        dzd = _gemm(dlogits, w2, None, transposed=True)
         dz1 = ops.dropout(dzd, p, mask=mask)[0] if mask is not None else dzd
         layers = [(net.conv1, net.bn1, True)]
         dfeat, grads = mlp_backward(ctx.saved, layers, dz1, None, True)
         B, N = dlogp.shape[0], dlogp.shape[1]
         ctx.saved = ctx.tail = None
-        return (None, dfeat.view(B, N, -1), None, None, *_layer_grads(layers, grads), dw2.view_as(net.conv2.weight), db2)
+        return (None, dfeat.view(B, N, -1), None, None, *_layer_grads(layers, grads),
+                None if w_direct else dw2.view_as(net.conv2.weight), None if b_direct else db2)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -296,9 +318,17 @@ class FlatAdam:
             self.flat[o:o + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[o:o + k].view(p.shape)
             p.grad = self.grad[o:o + k].view(p.shape)
+            p._pn_direct_grad = True          # the backward kernels accumulate straight into the flat gradient
             o += k
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay, "params": self.params}]
-        self.steps = 0
+        # learning rate and step count live on the device (pn_adam_dev_f32): the update is capturable in a CUDA graph
+        self._lr_host = float(lr)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+
+    @property
+    def steps(self) -> int:
+        return int(self.step_dev.item())
 
     def zero_grad(self, set_to_none: bool = False):
         self.grad.zero_()
@@ -321,9 +351,11 @@ class FlatAdam:
 
     def step(self, grad_scale: float = 1.0):
         g = self.param_groups[0]
-        self.steps += 1
-        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.steps, g["lr"], g["betas"], g["eps"],
-                      g["weight_decay"], grad_scale)
+        if float(g["lr"]) != self._lr_host:          # the reference's per-epoch decay (pcdseg.py:160-164)
+            self._lr_host = float(g["lr"])
+            self.lr_dev.fill_(self._lr_host)
+        ops.adam_step_dev(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr_dev, self.step_dev, g["betas"], g["eps"],
+                          g["weight_decay"], grad_scale)
         self.mark_updated()
 
     def mark_updated(self):
@@ -368,3 +400,100 @@ class SegMetrics:
         categorical = ious / count
         acc = float(self.acc_sum.item() / max(1, int(self.batches.item())))
         return acc, float(np.mean(categorical[1:])), categorical
+
+
+# ------------------------------------------------------------------------------------------------
+class GraphedTrainStep:
+    """One training iteration of PointNet2SemSeg as ONE CUDA-graph replay + the gradient exchange + the Adam launch.
+
+    An eager iteration is ~240 kernel launches plus the autograd engine and is bound by the host (7.7 ms at config C5 for
+    ~3 ms of GPU work); captured once per input shape, forward + loss + backward replay as a single graph launch.
+
+        step = GraphedTrainStep(net, FlatAdam(net.parameters(), lr=1e-3, weight_decay=1e-4))
+        loss = step(points, target)         # points [B, 4, N], target [B, N]; returns the (device) loss of this iteration
+
+    Per call the FPS start indices are drawn on the CPU generator exactly like the reference draws them
+    (pointnet_util.py:75) and reach the graph, together with the dropout stream's {seed, offset}, through one small
+    pinned staging buffer; the gradient all-reduce (when torch.distributed is initialised) and Adam run right behind
+    the replay on the same stream.  Warm-up iterations needed for the capture are rolled back."""
+
+    RING = 8
+
+    def __init__(self, net, optimizer: "FlatAdam", group=None, warmup: int = 2):
+        self.net = net.module if hasattr(net, "module") else net
+        self.opt, self.group, self.warmup = optimizer, group, warmup
+        self._graphs = {}
+        self._calls = 0
+        self._bn_buffers = [b for m in self.net.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)
+                            for b in (m.running_mean, m.running_var, m.num_batches_tracked) if b is not None]
+
+    def _forward_backward(self, st):
+        logp = semseg_forward_train(self.net, st["x"], fps_starts=list(st["ctl"][:-2].view(4, -1).unbind(0)),
+                                    seed_offset=st["ctl"][-2:])
+        loss = cross_entropy(logp, st["target"])
+        self.opt.zero_grad()
+        loss.backward()
+        return loss
+
+    def _build(self, points, target):
+        dev = points.device
+        B, C, N = points.shape
+        net = self.net
+        sizes = [N] + [m.npoint for m in (net.sa1, net.sa2, net.sa3)]
+        st = {"x": points.clone(), "target": target.clone().long().view(B, N), "sizes": sizes,
+              "ctl": torch.zeros((4 * B + 2,), dtype=torch.int64, device=dev),
+              "pinned": [torch.zeros((4 * B + 2,), dtype=torch.int64).pin_memory() for _ in range(self.RING)],
+              "events": [None] * self.RING, "slot": 0}
+        keep = [t.clone() for t in (self.opt.flat, *self._bn_buffers)]           # warm-up must not train
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self._forward_backward(st)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for t, k in zip((self.opt.flat, *self._bn_buffers), keep):
+                t.copy_(k)
+        from . import _native as nv
+
+        graph = torch.cuda.CUDAGraph()
+        n0 = nv.launch_count
+        with torch.cuda.graph(graph):
+            st["loss"] = self._forward_backward(st)
+        st["launches"] = nv.launch_count - n0          # entry-point calls captured in the graph (bench accounting)
+        st["graph"] = graph
+        return st
+
+    def __call__(self, points: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        if not self.net.training:
+            raise RuntimeError("GraphedTrainStep: call net.train() first")
+        key = (tuple(points.shape), points.device)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = self._build(points, target)
+        B = points.shape[0]
+        slot = st["slot"] = (st["slot"] + 1) % self.RING
+        if st["events"][slot] is not None:
+            st["events"][slot].synchronize()
+        pinned = st["pinned"][slot]
+        for i, n in enumerate(st["sizes"]):                   # the reference's draws, same generator, same order
+            pinned[i * B:(i + 1) * B] = torch.randint(0, n, (B,), dtype=torch.long)
+        self._calls += 1
+        pinned[-2] = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        pinned[-1] = self._calls
+        st["ctl"].copy_(pinned, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st["events"][slot] = ev
+        if points.data_ptr() != st["x"].data_ptr():
+            st["x"].copy_(points, non_blocking=True)
+        if target.data_ptr() != st["target"].data_ptr():
+            st["target"].copy_(target.view(st["target"].shape), non_blocking=True)
+        st["graph"].replay()
+        from . import _native as nv
+
+        nv.launch_count += st["launches"]
+        torch.autograd.graph.increment_version(self._bn_buffers)
+        self.opt.step(self.opt.all_reduce(self.group))
+        return st["loss"]

@@ -26,12 +26,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--points", type=int, default=8000)
+    ap.add_argument("--eager", action="store_true", help="launch kernel by kernel through autograd instead of one CUDA-graph replay")
     args = ap.parse_args()
     import torch.distributed as dist
 
     from pointnet12_b200 import _native as nv, synthetic as syn
     from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
-    from pointnet12_b200.train import FlatAdam, cross_entropy
+    from pointnet12_b200.train import FlatAdam, GraphedTrainStep, cross_entropy
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -68,6 +69,12 @@ def main():
         mark("adam")
         return loss
 
+    graphed = None if args.eager else GraphedTrainStep(net, opt)
+    eager_step = step
+    if graphed is not None:
+        def step(marks=None):                                  # noqa: F811
+            return graphed(pts, target) if marks is None else eager_step(marks)
+
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -101,9 +108,9 @@ def main():
             "scaling": "weak", "dtype": "f32 (CUDA-core GEMMs)", "data": "synthetic",
             "config": {"workload": f"C5: PointNet2SemSeg(19, feature_dims=1) training step (forward, CrossEntropyLoss, backward, "
                                    f"gradient all-reduce, Adam), {B} clouds x {N} points per GPU, seeded random init",
-                       "l2": "256 MiB written between timed steps", "launch": "eager"},
+                       "l2": "256 MiB written between timed steps", "launch": "eager" if args.eager else "forward + loss + backward as one CUDA-graph replay, then all-reduce and Adam"},
             "step_ms": {"min": float(times.min()), "median": float(np.median(times)), "max": float(times.max())},
-            "phases_ms": phases, "gpu_launches": int(launches), "final_loss": float(loss.item())}))
+            "phases_ms_eager": phases, "gpu_launches": int(launches), "final_loss": float(loss.item())}))
     if world > 1:
         dist.destroy_process_group()
 
