@@ -321,6 +321,11 @@ int pn_bn_bwd_apply_f32(const float* y, int64_t ldy, int64_t rows, int C, const 
  * Split over the rows, accumulated with fp32 atomics: dw / db must be zeroed (or hold a gradient to add to). */
 int pn_grad_weight_f32(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin,
                        float* dw, int64_t lddw, float* db, pn_stream_t stream);
+/* The same on the tensor cores (tcgen05, both operands from shared memory, 3-pass split bf16 with fp32 accumulation =
+ * fp32 parity like the forward chains): a CTA owns a 128 x 128 tile of dw in TMEM and a slab of rows, converts dy / x to
+ * bf16 hi + lo on the fly straight into the UMMA K-major layout, and adds its tile to dw with fp32 atomics. */
+int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin,
+                          float* dw, int64_t lddw, float* db, pn_stream_t stream);
 /* out [cols, rows] = in [rows, cols]^T (the weight of the input-gradient GEMM dx = dy W = pn_linear_f32(dy, W^T)). */
 int pn_transpose_f32(const float* in, int rows, int cols, float* out, pn_stream_t stream);
 /* Backward of the gather of sample_and_group (model/pointnet_util.py:128-131): dfeat[b, idx[b,s,k], :] +=

@@ -652,8 +652,10 @@ PN_EXPORT int pn_grad_weight_f32(const float* dy, int64_t lddy, const float* x, 
     int vec_ok = 0;
     if (((uintptr_t)dy % 16 == 0) && (lddy % 4 == 0)) vec_ok |= 1;
     if (((uintptr_t)x % 16 == 0) && (ldx % 4 == 0)) vec_ok |= 2;
-    // 128 x 128 tiles with 8 x 8 register tiles for the wide layers (64 FMAs per 4 shared-memory loads), 64 x 64 otherwise
-    const bool wide = cout > 64 && cin > 64;
+    // (A 128 x 128 tile with 8 x 8 register tiles measured SLOWER on B200 -- 73 vs 49 us for 128 x 128 over 64 k rows: two
+    // resident CTAs cannot hide the global-load latency of a BK = 8 step -- so the 64 x 64 tile is used throughout; the
+    // fast path for wide layers is the tensor-core kernel pn_grad_weight_bf16x3.)
+    const bool wide = false;
     const int BM = wide ? 128 : 64, BN = BM, BK = wide ? 8 : 16;
     const int64_t tiles = ceil_div(cout, BM) * ceil_div(cin, BN);
     int64_t splits = ceil_div((int64_t)sm_count() * (wide ? 2 : 4), tiles);

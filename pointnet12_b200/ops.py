@@ -710,16 +710,24 @@ def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: boo
     return (dy, dgamma, dbeta) if fresh else dy
 
 
-def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor]) -> None:
-    """dw [cout, cin] += dy^T x, db [cout] += column sums of dy (in place; the buffers hold zeros or a gradient)."""
+GRAD_TC_MIN_TILE = 4096     # cout * cin from which the 128 x 128 tensor-core tile is worth its padding
+
+
+def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor],
+                engine: str = "auto") -> None:
+    """dw [cout, cin] += dy^T x, db [cout] += column sums of dy (in place; the buffers hold zeros or a gradient).
+    engine: "tc" (pn_grad_weight_bf16x3, tensor cores, 3-pass split bf16), "fp32" (pn_grad_weight_f32, CUDA cores) or
+    "auto" (tensor cores unless the MLP mode is 'fp32' or the layer is tiny)."""
     dy, x = _rowmat(dy, "dy"), _rowmat(x, "x")
     rows, cout = dy.shape
     cin = x.shape[1]
     if x.shape[0] != rows or dw.shape != (cout, cin) or not dw.is_contiguous() or dw.dtype != torch.float32:
         raise ValueError("grad_weight: shape mismatch")
+    if engine == "auto":
+        engine = "tc" if (_MLP_MODE == "bf16x3" and cout * cin >= GRAD_TC_MIN_TILE) else "fp32"
+    name = {"tc": "pn_grad_weight_bf16x3", "fp32": "pn_grad_weight_f32"}[engine]
     with _on_device(dy):
-        nv.call("pn_grad_weight_f32", dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), rows, cout, cin, dw.data_ptr(), cin,
-                _p(db), _stream())
+        nv.call(name, dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), rows, cout, cin, dw.data_ptr(), cin, _p(db), _stream())
 
 
 def transpose(w: torch.Tensor) -> torch.Tensor:

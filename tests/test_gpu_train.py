@@ -95,7 +95,8 @@ def _check_bn_backward(y64, mu, var, g, mask, dz, dy, dg, db):
 
 @pytest.mark.parametrize("rows,cout,cin,ldx", [(8192, 64, 67, 68), (100003, 128, 128, 128), (777, 19, 128, 128), (4096, 32, 4, 4),
                                                (2048, 256, 320, 320), (50, 512, 259, 260)])
-def test_grad_weight_and_input_gradient(dev, rows, cout, cin, ldx):
+@pytest.mark.parametrize("engine", ["fp32", "tc"])
+def test_grad_weight_and_input_gradient(dev, rows, cout, cin, ldx, engine):
     from pointnet12_b200 import ops
 
     rng = np.random.default_rng(rows)
@@ -106,15 +107,27 @@ def test_grad_weight_and_input_gradient(dev, rows, cout, cin, ldx):
     xb[:, :cin] = T(x, dev)
     dw = torch.zeros((cout, cin), device=dev)
     db = torch.zeros((cout,), device=dev)
-    ops.grad_weight(T(dy, dev), xb[:, :cin], dw, db)
-    assert rl2(dw.cpu().numpy(), dy.astype(np.float64).T @ x.astype(np.float64)) < 1e-5
+    ops.grad_weight(T(dy, dev), xb[:, :cin], dw, db, engine=engine)
+    assert rl2(dw.cpu().numpy(), dy.astype(np.float64).T @ x.astype(np.float64)) < 2e-5
     assert rl2(db.cpu().numpy(), dy.astype(np.float64).sum(0)) < 1e-5
-    ops.grad_weight(T(dy, dev), xb[:, :cin], dw, db)                      # accumulates
-    assert rl2(dw.cpu().numpy(), 2 * (dy.astype(np.float64).T @ x.astype(np.float64))) < 1e-5
+    ops.grad_weight(T(dy, dev), xb[:, :cin], dw, db, engine=engine)       # accumulates
+    assert rl2(dw.cpu().numpy(), 2 * (dy.astype(np.float64).T @ x.astype(np.float64))) < 2e-5
     wt = ops.transpose(T(w, dev))
     assert np.array_equal(wt.cpu().numpy(), w.T)
+    want_dx = dy.astype(np.float64) @ w.astype(np.float64)
     dx = ops.linear(T(dy, dev), wt, None, relu=False)
-    assert rl2(dx.cpu().numpy(), dy.astype(np.float64) @ w.astype(np.float64)) < 1e-5
+    assert rl2(dx.cpu().numpy(), want_dx) < 1e-5
+    if engine == "tc":        # the input-gradient GEMM on the tensor cores: W packed transposed, no materialised W^T
+        from pointnet12_b200.train import _gemm
+
+        old = ops.set_mlp_mode("bf16x3")
+        try:
+            dx_tc = _gemm(T(dy, dev), T(w, dev), None, transposed=True)
+            y_tc = _gemm(xb[:, :cin], T(w, dev), None)
+        finally:
+            ops.set_mlp_mode(old)
+        assert rl2(dx_tc.cpu().numpy(), want_dx) < 2e-5, rl2(dx_tc.cpu().numpy(), want_dx)
+        assert rl2(y_tc.cpu().numpy(), x.astype(np.float64) @ w.astype(np.float64).T) < 2e-5
 
 
 def test_group_and_interpolate_backward(dev):
@@ -238,6 +251,20 @@ def test_seg_metrics_bit_exact(dev):
 
 
 # ------------------------------------------------------------------------------------------------ blocks
+def _close_but_for_flips(got, want, strict):
+    """Input gradients of a max-pooled block.  The gradient of a (group, channel) goes to the arg-max row; when the two
+    largest activations of a group differ by less than the GEMM engines' rounding difference (~1e-5 relative between the
+    split-bf16 tensor-core products and fp32 FMAs), the engines route it to DIFFERENT points -- an O(1) change of a few
+    entries that the reference's own float32-vs-float64 runs show as well.  So: exact-fp32 engine = strict L2 bound;
+    tensor-core engine = the same bound on all but 0.1 % of the entries, and a loose L2 bound on everything."""
+    if strict:
+        assert rl2(got, want) < 1e-4
+        return
+    err = np.abs(got.astype(np.float64) - want).reshape(-1)
+    assert np.quantile(err, 0.999) < 1e-4 * np.abs(want).max(), np.quantile(err, 0.999)
+    assert rl2(got, want) < 2e-2
+
+
 def _grads(module):
     return {n: p.grad.detach().cpu().numpy() for n, p in module.named_parameters()}
 
@@ -253,7 +280,7 @@ def test_sa_block_train_vs_reference(dev, golden, gemm_mode):
     assert out.shape == (2, 128, 256) and out.requires_grad
     out.backward(T(g_sa, dev))
     assert rl2(out.detach().cpu().numpy(), g["sa.out"]) < 2e-5
-    assert rl2(pts.grad.cpu().numpy(), g["sa.dpoints"]) < 1e-4
+    _close_but_for_flips(pts.grad.cpu().numpy(), g["sa.dpoints"], strict=gemm_mode == "fp32")
     for n, gr in _grads(sa).items():
         ref = g["sa.grad." + n]
         if "convs" in n and n.endswith("bias"):
