@@ -82,7 +82,7 @@ __device__ __forceinline__ void store_split8(unsigned char* hi_img, unsigned cha
 __global__ void __launch_bounds__(THREADS)
 grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx, int64_t rows,
                       int64_t rows_per_split, int cout, int cin, float* __restrict__ dw, int64_t lddw,
-                      float* __restrict__ db) {
+                      float* __restrict__ db, int vec_red) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + NS * STAGE);   // full[NS], empty[NS], done
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 1);
@@ -124,29 +124,43 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
     const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
                                      ((unsigned long long)((((unsigned)KC / 8) * 128u >> 4) & 0x3FFF) << 32) | (1ull << 46);
 
-    for (int c = 0; c < chunks; ++c) {
-        const int s = c % NS;
-        const unsigned use = (unsigned)(c / NS);
-        if (c >= NS) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);      // the MMAs that read this stage have completed
-        unsigned char* st = smem + s * STAGE;
+    // register double buffer: the loads of chunk c+1 are in flight while chunk c is converted, stored and multiplied
+    float va[2][8], vb[2][8];
+    auto load_chunk = [&](int c) {
         const int64_t k0 = r0 + (int64_t)c * KC;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int kb = half + 2 * q;
-            float va[8], vb[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int64_t r = k0 + kb * 8 + j;
                 const bool in = r < r1;
-                va[j] = (in && a_ok) ? ap[r * lddy] : 0.0f;
-                vb[j] = (in && b_ok) ? bp[r * ldx] : 0.0f;
+                va[q][j] = (in && a_ok) ? __ldg(ap + r * lddy) : 0.0f;
+                vb[q][j] = (in && b_ok) ? __ldg(bp + r * ldx) : 0.0f;
             }
+        }
+    };
+    if (chunks > 0) load_chunk(0);
+    for (int c = 0; c < chunks; ++c) {
+        const int s = c % NS;
+        const unsigned use = (unsigned)(c / NS);
+        float ca[2][8], cb[2][8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ca[q][j] = va[q][j]; cb[q][j] = vb[q][j]; }
+        if (c + 1 < chunks) load_chunk(c + 1);
+        if (c >= NS) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);      // the MMAs that read this stage have completed
+        unsigned char* st = smem + s * STAGE;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int kb = half + 2 * q;
             if (do_bias) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bsum += va[j];
+                for (int j = 0; j < 8; ++j) bsum += ca[q][j];
             }
-            store_split8(st, st + IMG, row_off + (unsigned)kb * 128u, va);
-            store_split8(st + 2 * IMG, st + 3 * IMG, row_off + (unsigned)kb * 128u, vb);
+            store_split8(st, st + IMG, row_off + (unsigned)kb * 128u, ca[q]);
+            store_split8(st + 2 * IMG, st + 3 * IMG, row_off + (unsigned)kb * 128u, cb[q]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
         mbar_arrive(bar_full + 8 * s);
@@ -187,10 +201,18 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
             unsigned r[32];
             ld32(tbase + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)col0, r);
             if (co < cout) {
+                float* dst = dw + (int64_t)co * lddw + ci0 + col0;
+                if (vec_red && ci0 + col0 + 32 <= cin) {
+                    // 16-byte vector reductions: a quarter of the atomic operations the row slabs send to the same tile
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int ci = ci0 + col0 + j;
-                    if (ci < cin) atomicAdd(&dw[(int64_t)co * lddw + ci], __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                                     "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (ci0 + col0 + j < cin) atomicAdd(dst + j, __uint_as_float(r[j]));
                 }
             }
         }
@@ -220,12 +242,15 @@ PN_EXPORT int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* 
         if (sms <= 0) sms = 148;
     }
     const int64_t tiles = ceil_div(cout, TM) * ceil_div(cin, TN);
-    int64_t splits = ceil_div((int64_t)sms * 2, tiles);
+    // one CTA per SM: every extra row slab adds a whole tile of atomics on the same 128 x 128 addresses
+    int64_t splits = ceil_div((int64_t)sms, tiles);
     int64_t rps = ceil_div(ceil_div(rows, splits), KC) * KC;
     if (rps < 4 * KC) rps = 4 * KC;
     splits = ceil_div(rows, rps);
     PN_REQUIRE(splits <= 65535, PN_ERR_UNSUPPORTED, "pn_grad_weight_bf16x3: too many row splits");
     dim3 grid((unsigned)ceil_div(cout, TM), (unsigned)ceil_div(cin, TN), (unsigned)splits);
-    grad_weight_tc_kernel<<<grid, THREADS, SMEM, (cudaStream_t)stream>>>(dy, lddy, x, ldx, rows, rps, cout, cin, dw, lddw, db);
+    const int vec_red = ((uintptr_t)dw % 16 == 0) && (lddw % 4 == 0);
+    grad_weight_tc_kernel<<<grid, THREADS, SMEM, (cudaStream_t)stream>>>(dy, lddy, x, ldx, rows, rps, cout, cin, dw, lddw, db,
+                                                                        vec_red);
     return finish_launch("pn_grad_weight_bf16x3");
 }

@@ -981,12 +981,13 @@ def test_partseg_msg_smoke_shape(dev):
     assert torch.allclose(out.exp().sum(-1), torch.ones(8, 2048, device=dev), atol=1e-4)
 
 
-def test_train_mode_raises(dev):
-    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+def test_train_mode_raises_where_not_built(dev):
+    """PointNet2SemSeg trains (tests/test_gpu_train.py); the MSG blocks are inference-only and must say so, not fall back."""
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsMsg
 
-    net = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    net = PointNet2ClsMsg().to(dev).train()
     with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 4, 2048, device=dev))
+        net(torch.zeros(2, 3, 1024, device=dev))
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties (C2)

