@@ -370,6 +370,33 @@ int pn_seg_metrics_f32(const float* logp, int64_t ldx, const int64_t* target, in
 int pn_seg_metrics_accumulate(const int64_t* counts, int C, int64_t points, float* ious, uint32_t* count,
                               double* acc_sum, int64_t* batches, pn_stream_t stream);
 
+/* ================================================================================================================
+ * Raw SemanticKITTI scans -> network input: Semantic_KITTI_Utils.get
+ * (data_utils/kitti_utils.py:183-227) + SemKITTI_Loader.__getitem__ (data_utils/SemKITTI_Loader.py:91-115).
+ * points: B scans concatenated, float32 x 4 per point (x, y, z, reflectance: the .bin wire format), 16-byte aligned;
+ * raw_label: uint32 per point (.label: semantic id in the low 16 bits); offsets: int64 [B+1] (device) = first point of
+ * every scan; lut: uint8 [lut_size] = the learning_map of config/semantic-kitti.yaml as a table (ids beyond it -> 0).
+ * ================================================================================================================ */
+size_t pn_scan_workspace_bytes(int B, int64_t max_points);
+/* Keep flag per point -- learning_map[label] != 0 (kitti_utils.py:213-218) and, with inview != 0, the field-of-view
+ * test of points_basic_filter (:262-280): h_lo < atan2(y, x) < h_hi, v_lo < atan2(z, sqrt(x^2+y^2+z^2)) < v_hi in fp32
+ * (the caller passes the bounds as the fp32 values of -/+40 deg and -/+20 deg in radians) and |x|,|y|,|z|,d < 10000 --
+ * then an ORDER-PRESERVING compaction: kept[offsets[b] + i] = index inside scan b of its i-th kept point,
+ * kept_count[b] = how many.  max_points (host) = the longest scan, for the grid size. */
+int pn_scan_filter_f32(const float* points, const uint32_t* raw_label, const int64_t* offsets, int B, int64_t max_points,
+                       const uint8_t* lut, int lut_size, int inview, float h_lo, float h_hi, float v_lo, float v_hi,
+                       int32_t* kept, int32_t* kept_count, void* workspace, size_t workspace_bytes, pn_stream_t stream);
+/* out [B, 4, npoints] (channel-major, what PointNet2SemSeg.forward takes after pcdseg.py:167's transpose) and labels
+ * int64 [B, npoints] (learning_map[label] - 1): point j of scan b is kept point choice[b*npoints + j] of that scan
+ * (np.random.choice(length, npoints, replace=True), SemKITTI_Loader.py:110-113), normalised and clipped
+ * (pcd_normalize, :23-30) plus noise[(offsets[b] + i)*4 .. +3] (pcd_jitter, :17-21: one fp32 4-vector per KEPT point,
+ * already scaled and clipped by the caller; NULL = none).  choice == NULL: indices, and with sigma > 0 the jitter
+ * clip(sigma*N(0,1), -clip, clip), are drawn from the Philox4x32-10 stream seed_offset = {seed, offset} (device memory). */
+int pn_scan_sample_f32(const float* points, const uint32_t* raw_label, const int64_t* offsets, int B, const uint8_t* lut,
+                       int lut_size, const int32_t* kept, const int32_t* kept_count, int npoints, const int64_t* choice,
+                       const float* noise, float sigma, float clip, const uint64_t* seed_offset, float* out,
+                       int64_t* labels, pn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,8 @@ _SIGNATURES = {
     "pn_adam_f32": [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp],
     "pn_adam_dev_f32": [vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, f32, vp],
     "pn_seg_metrics_f32": [vp, i64, vp, i64, i32, vp, vp, vp],
+    "pn_scan_filter_f32": [vp, vp, vp, i32, i64, vp, i32, i32, f32, f32, f32, f32, vp, vp, vp, C.c_size_t, vp],
+    "pn_scan_sample_f32": [vp, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, vp, vp],
     "pn_seg_metrics_accumulate": [vp, i32, i64, vp, vp, vp, vp, vp],
 }
 
@@ -120,6 +122,8 @@ def lib():
         handle.pn_ball_grid_bytes.restype = C.c_size_t
         handle.pn_three_nn_blocks_bytes.argtypes = [i32, i32]
         handle.pn_three_nn_blocks_bytes.restype = C.c_size_t
+        handle.pn_scan_workspace_bytes.argtypes = [i32, i64]
+        handle.pn_scan_workspace_bytes.restype = C.c_size_t
         _lib = handle
     return _lib
 

@@ -125,3 +125,34 @@ def random_state_dict(shapes: dict, seed: int) -> dict:
         else:                                               # biases (conv, linear, BatchNorm beta)
             out[name] = rng.normal(0.0, 0.1, shape).astype(np.float32)
     return out
+
+
+# SemanticKITTI raw label id -> training class 0..19 (0 = ignored): the `learning_map` table of the dataset's public
+# semantic-kitti.yaml, which the reference reads at data_utils/kitti_utils.py:152-155.
+SEMANTIC_KITTI_LEARNING_MAP = {
+    0: 0, 1: 0, 10: 1, 11: 2, 13: 5, 15: 3, 16: 5, 18: 4, 20: 5, 30: 6, 31: 7, 32: 8, 40: 9, 44: 10, 48: 11, 49: 12, 50: 13,
+    51: 14, 52: 0, 60: 9, 70: 15, 71: 16, 72: 17, 80: 18, 81: 19, 99: 0, 252: 1, 253: 7, 254: 6, 255: 8, 256: 5, 257: 5,
+    258: 4, 259: 5}
+
+
+def raw_scan(n_points: int, seed: int):
+    """A synthetic RAW SemanticKITTI scan in the dataset's wire format: points [M, 4] float32 (x, y, z in metres over the
+    full 360 degrees, reflectance in [0, 1]) and labels [M] uint32 (semantic id in the low 16 bits, instance id above).
+    Points whose azimuth / elevation lies within 1e-5 rad of a field-of-view bound of the in-view filter (+-40, +-20 degrees)
+    get label 0 (dropped by every implementation), so the filter decision never hinges on the last ulp of atan2."""
+    rng = np.random.default_rng(seed)
+    az = np.deg2rad(rng.uniform(-180.0, 180.0, n_points))
+    el = np.deg2rad(rng.uniform(-24.8, 24.0, n_points))
+    r = rng.uniform(1.5, 80.0, n_points)
+    pts = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el),
+                    rng.uniform(0.0, 1.0, n_points)], axis=1).astype(np.float32)
+    ids = np.array(sorted(SEMANTIC_KITTI_LEARNING_MAP), dtype=np.uint32)
+    sem = ids[rng.integers(0, len(ids), n_points)]
+    x, y, z = (pts[:, i].astype(np.float64) for i in range(3))
+    h, v = np.arctan2(y, x), np.arctan2(z, np.sqrt(x * x + y * y + z * z))
+    edge = np.zeros(n_points, dtype=bool)
+    for ang, bound in ((h, 40.0), (h, -40.0), (v, 20.0), (v, -20.0)):
+        edge |= np.abs(ang - np.deg2rad(bound)) < 1e-5
+    sem[edge] = 0
+    inst = rng.integers(0, 200, n_points).astype(np.uint32)
+    return pts, (sem | (inst << 16)).astype(np.uint32)

@@ -1,0 +1,152 @@
+"""Scan pre-processing: the oracle against the reference's own data path (CPU), the CUDA path against both (GPU).
+
+tests/golden/preprocess_scans.npz comes from the reference's Semantic_KITTI_Utils.get / pcd_normalize / pcd_jitter /
+np.random.choice run on synthetic .bin / .label files (oracle/gen_golden_preprocess.py).  Everything here is bit-exact:
+the filter is a set of fp32 comparisons, the normalisation is correctly rounded fp32 arithmetic, and the random draws are
+passed in.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess_oracle as por
+from pointnet12_b200 import synthetic as syn
+
+LMAP = syn.SEMANTIC_KITTI_LEARNING_MAP
+M, NPOINTS = 20000, 3000
+
+
+def _scans():
+    return [syn.raw_scan(M, 7000 + i) for i in range(2)]
+
+
+def test_oracle_vs_reference_data_path(golden):
+    g = golden("preprocess_scans")
+    for i, (p, l) in enumerate(_scans()):
+        assert syn.checksum(p) == str(g[f"checksum{i}"])
+        kept, _ = por.scan_filter(p, l, LMAP, inview=True)
+        assert np.array_equal(kept, g[f"kept{i}"])
+        choice = g[f"choice{i}"].astype(np.int64)
+        pcd, lab = por.scan_sample(p, l, LMAP, NPOINTS, choice, noise=g[f"noise{i}"])
+        assert np.array_equal(pcd, g[f"train_pcd{i}"]) and np.array_equal(lab, g[f"label{i}"])
+        pcd, lab = por.scan_sample(p, l, LMAP, NPOINTS, choice, noise=None)
+        assert np.array_equal(pcd, g[f"eval_pcd{i}"]) and np.array_equal(lab, g[f"label{i}"])
+
+
+def test_raw_scan_has_no_boundary_points():
+    p, l = syn.raw_scan(50000, 1)
+    kept, _ = por.scan_filter(p, l, LMAP)
+    x, y, z = (p[kept, i].astype(np.float64) for i in range(3))
+    h, v = np.arctan2(y, x), np.arctan2(z, np.sqrt(x * x + y * y + z * z))
+    assert np.abs(np.abs(h) - np.deg2rad(40)).min() > 1e-5 and np.abs(np.abs(v) - np.deg2rad(20)).min() > 1e-5
+    assert 0.02 < len(kept) / 50000 < 0.25
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.gpu
+def test_cuda_vs_reference_and_oracle(dev, golden):
+    from pointnet12_b200.preprocess import ScanPreprocessor
+
+    g = golden("preprocess_scans")
+    scans = _scans()
+    pre = ScanPreprocessor(LMAP, "inview", dev)
+    batch = pre.upload([p for p, _ in scans], [l for _, l in scans])
+    kept, count = pre.filter(batch)
+    kept, count = kept.cpu().numpy(), count.cpu().numpy()
+    noise = np.zeros((2 * M, 4), dtype=np.float32)
+    for i in range(2):
+        assert count[i] == len(g[f"kept{i}"])
+        assert np.array_equal(kept[i * M:i * M + count[i]], g[f"kept{i}"])
+        noise[i * M:i * M + count[i]] = g[f"noise{i}"]
+    choice = torch.from_numpy(np.stack([g["choice0"], g["choice1"]]).astype(np.int64)).to(dev)
+    out, lab = pre(batch, NPOINTS, train=True, choice=choice, noise=torch.from_numpy(noise).to(dev))
+    assert out.shape == (2, 4, NPOINTS) and lab.shape == (2, NPOINTS) and lab.dtype == torch.int64
+    for i in range(2):
+        assert np.array_equal(out[i].cpu().numpy().T, g[f"train_pcd{i}"])              # bit-exact with the reference
+        assert np.array_equal(lab[i].cpu().numpy(), g[f"label{i}"])
+    out, lab = pre(batch, NPOINTS, train=False, choice=choice)
+    for i in range(2):
+        assert np.array_equal(out[i].cpu().numpy().T, g[f"eval_pcd{i}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("subset", ["inview", "all"])
+def test_cuda_ragged_batch_vs_oracle(dev, subset):
+    """Ragged scans (one empty after filtering, one spanning many tiles), both subsets, against the oracle."""
+    from pointnet12_b200.preprocess import ScanPreprocessor
+
+    sizes = [5000, 131072 + 77, 1, 2049, 40000]
+    scans = [syn.raw_scan(n, 7100 + i) for i, n in enumerate(sizes)]
+    scans[2] = (scans[2][0], np.zeros(1, dtype=np.uint32))                                # nothing survives: label 0
+    pre = ScanPreprocessor(LMAP, subset, dev)
+    batch = pre.upload([p for p, _ in scans], [l for _, l in scans])
+    kept, count = pre.filter(batch)
+    kept, count, off = kept.cpu().numpy(), count.cpu().numpy(), batch.offsets.cpu().numpy()
+    rng = np.random.default_rng(3)
+    npts = 4096
+    choice = np.zeros((len(sizes), npts), dtype=np.int64)
+    wants = []
+    for i, (p, l) in enumerate(scans):
+        want_kept, _ = por.scan_filter(p, l, LMAP, inview=subset == "inview")
+        assert count[i] == len(want_kept) and np.array_equal(kept[off[i]:off[i] + count[i]], want_kept)
+        if len(want_kept):
+            choice[i] = rng.integers(0, len(want_kept), npts)
+            wants.append(por.scan_sample(p, l, LMAP, npts, choice[i], inview=subset == "inview"))
+        else:
+            wants.append(None)
+    out, lab = pre(batch, npts, train=False, choice=torch.from_numpy(choice).to(dev), filtered=None)
+    for i, w in enumerate(wants):
+        if w is None:
+            assert not out[i].any() and (lab[i] == 0).all()       # an empty scan yields zeros (the reference would raise)
+        else:
+            assert np.array_equal(out[i].cpu().numpy().T, w[0]) and np.array_equal(lab[i].cpu().numpy(), w[1])
+
+
+@pytest.mark.gpu
+def test_cuda_device_draws(dev):
+    """Production mode: choice and jitter drawn on the device.  Every output point must be a kept point of its scan,
+    normalised, within the jitter clip; the draws are uniform, repeatable under torch.manual_seed and fresh per call."""
+    from pointnet12_b200.preprocess import ScanPreprocessor
+
+    scans = [syn.raw_scan(30000, 7200 + i) for i in range(3)]
+    pre = ScanPreprocessor(LMAP, "inview", dev)
+    batch = pre.upload([p for p, _ in scans], [l for _, l in scans])
+    torch.manual_seed(5)
+    ev, lab_ev = pre(batch, 20000, train=False)
+    tr, lab_tr = pre(batch, 20000, train=True)
+    for i, (p, l) in enumerate(scans):
+        kept, labels = por.scan_filter(p, l, LMAP)
+        base = por.pcd_normalize(p[kept])
+        got = ev[i].cpu().numpy().T
+        # every row is one of the kept points, bit for bit
+        table = {row.tobytes(): lab for row, lab in zip(base, labels)}
+        assert all(r.tobytes() in table for r in got[:2000])
+        assert all(table[r.tobytes()] == int(x) for r, x in zip(got[:2000], lab_ev[i, :2000].cpu().numpy()))
+        # uniform over the kept points: mean index fraction ~ 0.5, most points drawn at least once
+        index = {row.tobytes(): j for j, row in enumerate(base)}
+        drawn = np.array([index[r.tobytes()] for r in got])
+        assert abs(drawn.mean() / len(kept) - 0.5) < 0.02 and len(np.unique(drawn)) > 0.9 * len(kept) * (1 - np.exp(-20000 / len(kept)))
+        # jitter: |train - some kept point| <= clip per channel is implied by range; check the noise statistics instead
+    d = (tr - ev)                                                   # different draws: compare distributions only
+    assert torch.isfinite(tr).all() and tr.abs().max() <= 1.05 + 1e-6
+    torch.manual_seed(5)
+    pre2 = ScanPreprocessor(LMAP, "inview", dev)
+    ev2, _ = pre2(batch, 20000, train=False)
+    assert torch.equal(ev, ev2)                                     # same seed, same call number -> same draws
+    ev3, _ = pre2(batch, 20000, train=False)
+    assert not torch.equal(ev2, ev3)
+    # jitter statistics through a fixed choice: noise = train - eval, sigma 0.01 clipped at 0.05
+    choice = torch.zeros((3, 20000), dtype=torch.int64, device=dev)
+    choice[:] = torch.arange(20000, device=dev) % 1000
+    a, _ = pre(batch, 20000, train=False, choice=choice)
+    b, _ = pre(batch, 20000, train=True, choice=choice)
+    nz = (b - a)[:, :, :1000].double()
+    assert abs(nz.mean().item()) < 1e-3 and abs(nz.std().item() - 0.01) < 1e-3 and nz.abs().max().item() <= 0.05 + 1e-6
+    assert torch.equal((b - a)[:, :, :1000], (b - a)[:, :, 1000:2000])    # the same kept point gets the same jitter
