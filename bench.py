@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch of the critical-path kernels")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
                     help="bf16x3 (default, fp32 parity), bf16 (single-pass, stated tolerance) or fp32 (CUDA cores)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "train"],
+                    help="c2 (default): the headline eval forward; train: config C5, one training iteration per step "
+                         "(tools/bench_train.py; same JSON contract)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: one CUDA-graph replay per step (default); eager: ~40 launches per step")
     return ap.parse_args()
@@ -372,6 +375,13 @@ def run_ours(args):
 
 def main():
     args = parse()
+    if args.workload == "train" and args.impl == "ours":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_train
+
+        bench_train.main(["--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--eager"] if args.mode == "eager" else [])
+                         + (["--no-cpu-baseline"] if args.no_cpu_baseline else []))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -710,7 +710,7 @@ def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: boo
     return (dy, dgamma, dbeta) if fresh else dy
 
 
-GRAD_TC_MIN_TILE = 4096     # cout * cin from which the 128 x 128 tensor-core tile is worth its padding
+GRAD_TC_MIN_TILE = int(os.environ.get("PN12_GRAD_TC_MIN", "1024"))     # cout * cin from which the 128 x 128 tensor-core tile is worth its padding
 
 
 def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor],

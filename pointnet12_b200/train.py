@@ -220,25 +220,41 @@ class SegHeadFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------------------------------------
 # train-mode forwards called by the modules (model/pointnet_util.py, model/pointnet2.py)
-def set_abstraction_train(mod, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx=None):
+def set_abstraction_train(mod, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx=None, geometry=None):
+    """geometry: (new_xyz [B,S,3], group_idx [B,S,K]) when the caller has computed them already (side stream)."""
     if mod.group_all:
         raise NotImplementedError("training path: group_all levels are not built yet (PointNet2SemSeg has none)")
     xyz_pm = xyz.detach().permute(0, 2, 1)
     pts_pm = points.permute(0, 2, 1) if points is not None else None
-    with torch.no_grad():
-        new_xyz, idx = mod.geometry(xyz_pm, start_idx)
+    if geometry is None:
+        with torch.no_grad():
+            geometry = mod.geometry(xyz_pm, start_idx)
+    new_xyz, idx = geometry
     layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
     pooled = SetAbstractionFn.apply(mod, xyz_pm, pts_pm, new_xyz, idx, *_layer_params(layers))
     return new_xyz.permute(0, 2, 1), pooled.permute(0, 2, 1)
 
 
-def feature_propagation_train(mod, xyz1, xyz2, points1, points2):
-    with torch.no_grad():
-        idx, w = mod.geometry(xyz1.detach().permute(0, 2, 1), xyz2.detach().permute(0, 2, 1))
+def feature_propagation_train(mod, xyz1, xyz2, points1, points2, geometry=None):
+    """geometry: (idx [B,N,3], weight [B,N,3]) of the 3-NN search when the caller has computed them already."""
+    if geometry is None:
+        with torch.no_grad():
+            geometry = mod.geometry(xyz1.detach().permute(0, 2, 1), xyz2.detach().permute(0, 2, 1))
+    idx, w = geometry
     p1 = points1.permute(0, 2, 1) if points1 is not None else None
     layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
     out = FeaturePropagationFn.apply(mod, p1, points2.permute(0, 2, 1), idx, w, *_layer_params(layers))
     return out.permute(0, 2, 1)
+
+
+_GEO_STREAMS = {}
+
+
+def _geometry_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _GEO_STREAMS:
+        _GEO_STREAMS[key] = torch.cuda.Stream(device)
+    return _GEO_STREAMS[key]
 
 
 _SEED = {"next": 0}
@@ -259,15 +275,46 @@ def semseg_forward_train(net, points: torch.Tensor, fps_starts=None, dropout_mas
     xyz = points[:, :3, :]
     feats = points[:, 3:, :] if points.shape[1] > 3 else None
     sa = [net.sa1, net.sa2, net.sa3, net.sa4]
+    fp = [net.fp1, net.fp2, net.fp3, net.fp4]                     # fp[i] upsamples level i+1 -> level i
+    B, _, N = points.shape
+    if fps_starts is None:
+        from .model.pointnet_util import draw_fps_starts
+
+        fps_starts = draw_fps_starts(B, [N] + [m.npoint for m in sa[:-1]], points.device)
+    # Everything that depends on the coordinates only -- sampling and ball query of the four levels, the four 3-NN
+    # searches -- carries no gradient and runs back to back on a side stream; the feature path on the caller's stream
+    # waits level by level, so after the level-1 sampling (the long serial kernel) the MLPs overlap the rest of it.
+    user = torch.cuda.current_stream(points.device)
+    geo = _geometry_stream(points.device)
+    capturing = torch.cuda.is_current_stream_capturing()
+    sa_geo, fp_geo, sa_ready, fp_ready = [], [None] * 4, [], [None] * 4
+    geo.wait_stream(user)
+    with torch.no_grad(), torch.cuda.stream(geo):
+        xs_pm = [xyz.detach().permute(0, 2, 1)]
+        for i, m in enumerate(sa):
+            new_xyz, idx = m.geometry(xs_pm[i], fps_starts[i])
+            xs_pm.append(new_xyz)
+            sa_geo.append((new_xyz, idx))
+            ev = torch.cuda.Event()
+            ev.record(geo)
+            sa_ready.append(ev)
+        for i in (3, 2, 1, 0):                                   # fp4 is needed first
+            fp_geo[i] = fp[i].geometry(xs_pm[i], xs_pm[i + 1])
+            fp_ready[i] = torch.cuda.Event()
+            fp_ready[i].record(geo)
+        if not capturing:
+            for t in [t for pair in sa_geo + fp_geo for t in pair]:
+                t.record_stream(user)
     xs, fs = [xyz], [feats]
     for i, m in enumerate(sa):
-        nx, nf = set_abstraction_train(m, xs[-1], fs[-1], None if fps_starts is None else fps_starts[i])
+        user.wait_event(sa_ready[i])
+        nx, nf = set_abstraction_train(m, xs[-1], fs[-1], geometry=sa_geo[i])
         xs.append(nx)
         fs.append(nf)
-    up = feature_propagation_train(net.fp4, xs[3], xs[4], fs[3], fs[4])
-    up = feature_propagation_train(net.fp3, xs[2], xs[3], fs[2], up)
-    up = feature_propagation_train(net.fp2, xs[1], xs[2], fs[1], up)
-    up = feature_propagation_train(net.fp1, xs[0], xs[1], None, up)
+    up = fs[4]
+    for i in (3, 2, 1, 0):
+        user.wait_event(fp_ready[i])
+        up = feature_propagation_train(fp[i], xs[i], xs[i + 1], fs[i] if i > 0 else None, up, geometry=fp_geo[i])
     if dropout_mask is None and seed_offset is None and net.drop1.p > 0:
         seed_offset = dropout_seed(points.device)
     params = [net.conv1.weight, net.conv1.bias, net.bn1.weight, net.bn1.bias, net.conv2.weight, net.conv2.bias]

@@ -283,12 +283,15 @@ def test_sa_block_train_vs_reference(dev, golden, gemm_mode):
     out.backward(T(g_sa, dev))
     assert rl2(out.detach().cpu().numpy(), g["sa.out"]) < 2e-5
     _close_but_for_flips(pts.grad.cpu().numpy(), g["sa.dpoints"], strict=gemm_mode == "fp32")
+    # parameter gradients: sums over 16 k rows of random-sign terms, so the ~40 arg-max flips the tensor-core engine's
+    # 1e-5 rounding difference causes among 65 k (group, channel) pairs show up at the 1e-3 level (see _close_but_for_flips)
+    tol = 1e-4 if gemm_mode == "fp32" else 1e-2
     for n, gr in _grads(sa).items():
         ref = g["sa.grad." + n]
         if "convs" in n and n.endswith("bias"):
             assert np.abs(gr).max() < 1e-3, n                             # true gradient 0 (BatchNorm follows)
         else:
-            assert rl2(gr, ref) < 1e-4, (n, rl2(gr, ref))
+            assert rl2(gr, ref) < tol, (n, rl2(gr, ref))
     for n, b in sa.named_buffers():
         ref = g["sa.buffer." + n]
         assert np.abs(b.cpu().numpy().astype(np.float64) - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), n

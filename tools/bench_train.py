@@ -20,17 +20,44 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def cpu_train_oracle(B=2, N=2048):
+    """The float64 numpy oracle of one training iteration (oracle/train_oracle.py) on a bounded sample: points/s."""
+    import time
+
+    from oracle import oracle as orc
+    from oracle import train_oracle as tor
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+
+    torch.manual_seed(1234)
+    sd = orc.numpy_state_dict(PointNet2SemSeg(19, feature_dims=1).state_dict())
+    pts = syn.kitti_batch(B, N, config=5)
+    rng = np.random.default_rng(0)
+    target = rng.integers(0, 19, (B, N))
+    starts = [rng.integers(0, n, B) for n in (N, 1024, 256, 64)]
+    keep = rng.integers(0, 2, (B * N, 128))
+    t0 = time.perf_counter()
+    tor.semseg_train_step(sd, pts, target, starts, keep)
+    dt = time.perf_counter() - t0
+    return {"value": B * N / dt, "unit": "points/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"one training iteration (forward, loss, backward) of {B} clouds x {N} points, numpy float64 oracle "
+                      f"(BLAS threads) + C/OpenMP geometry, {dt:.2f} s"}
+
+
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--points", type=int, default=8000)
     ap.add_argument("--eager", action="store_true", help="launch kernel by kernel through autograd instead of one CUDA-graph replay")
-    args = ap.parse_args()
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args(argv)
     import torch.distributed as dist
 
-    from pointnet12_b200 import _native as nv, synthetic as syn
+    from bench import ClockSampler
+
+    from pointnet12_b200 import _native as nv, ops, synthetic as syn
     from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
     from pointnet12_b200.train import FlatAdam, GraphedTrainStep, cross_entropy
 
@@ -83,15 +110,33 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n0 = nv.launch_count
     evs = []
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            loss = step()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+    launches = nv.launch_count - n0
+    # end to end: the batch starts in pinned host memory every step and the loss is read back
+    host_pts, host_tgt = pts.cpu().pin_memory(), target.cpu().pin_memory()
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    e2e = []
     for _ in range(args.steps):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        loss = step()
+        pts.copy_(host_pts, non_blocking=True)
+        target.copy_(host_tgt, non_blocking=True)
+        host_loss.copy_(step(), non_blocking=True)
         b.record()
-        evs.append((a, b))
+        e2e.append((a, b))
     torch.cuda.synchronize()
-    launches = nv.launch_count - n0
+    e2e_total = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     times = np.array([a.elapsed_time(b) for a, b in evs])
     total = torch.tensor([times.sum()], device=dev, dtype=torch.float64)
     if world > 1:
@@ -105,11 +150,16 @@ def main():
         print(json.dumps({
             "metric": "pointnet2_semseg_train_points_per_sec", "value": world * B * N / (ms * 1e-3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "dtype": "f32 (CUDA-core GEMMs)", "data": "synthetic",
+            "scaling": "weak", "dtype": "f32 (GEMMs as 3-pass split bf16 on tensor cores)" if ops.mlp_mode() == "bf16x3" else "f32 (CUDA-core GEMMs)", "data": "synthetic",
             "config": {"workload": f"C5: PointNet2SemSeg(19, feature_dims=1) training step (forward, CrossEntropyLoss, backward, "
                                    f"gradient all-reduce, Adam), {B} clouds x {N} points per GPU, seeded random init",
                        "l2": "256 MiB written between timed steps", "launch": "eager" if args.eager else "forward + loss + backward as one CUDA-graph replay, then all-reduce and Adam"},
             "step_ms": {"min": float(times.min()), "median": float(np.median(times)), "max": float(times.max())},
+            "vs_baseline": None, "clocks": clocks.summary(),
+            "e2e": {"value": world * B * N / (float(e2e_total.item()) / args.steps * 1e-3), "unit": "points/s",
+                    "ms_per_step": float(e2e_total.item()) / args.steps,
+                    "h2d_bytes_per_step": int(host_pts.numel() * 4 + host_tgt.numel() * 8), "d2h_bytes_per_step": 4},
+            "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else cpu_train_oracle(),
             "phases_ms_eager": phases, "gpu_launches": int(launches), "final_loss": float(loss.item())}))
     if world > 1:
         dist.destroy_process_group()
