@@ -326,6 +326,22 @@ int pn_grad_weight_f32(const float* dy, int64_t lddy, const float* x, int64_t ld
  * bf16 hi + lo on the fly straight into the UMMA K-major layout, and adds its tile to dw with fp32 atomics. */
 int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin,
                           float* dw, int64_t lddw, float* db, pn_stream_t stream);
+/* The same with f(x) = act(x*x_scale[ci] + x_shift[ci]) applied to the x operand while it is loaded: the normalise + ReLU
+ * of the layer that produced x, for a forward that kept only that layer's pre-normalisation output (pn_train_gemm_bf16x3). */
+int pn_grad_weight_bn_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* x_scale,
+                             const float* x_shift, int x_relu, int64_t rows, int cout, int cin, float* dw, int64_t lddw,
+                             float* db, pn_stream_t stream);
+/* One layer of the training forward (or the input-gradient GEMM of its backward) on the tensor cores with BatchNorm fused
+ * on both sides: y[r,n] = sum_k f(x[r,k]) * W[n,k] + bias[n], f(v) = act(v*in_scale[k] + in_shift[k]) (in_scale NULL:
+ * identity) = the normalise + ReLU of the PREVIOUS layer applied on load; col_sum / col_sumsq (fp64, may be NULL, ADDED to)
+ * = the column sums of y and y*y for THIS layer's batch statistics (then pn_bn_finalize_f32).  w is [cout, cin] row-major,
+ * or with w_transposed != 0 the transpose of a row-major [cin, cout] matrix (dx = dy W reads W that way).  3-pass split
+ * bf16 with fp32 accumulation (fp32 parity).  Weights stay resident in shared memory: pn_train_gemm_supported(cin, cout)
+ * tells whether the layer fits (cout <= 256, padded cin*cout*4 <= 128 KB); wider layers use pn_mlp_rows_bf16x3. */
+int pn_train_gemm_supported(int cin, int cout);
+int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale, const float* in_shift,
+                         int in_relu, const float* w, int w_transposed, const float* bias, int cout, float* y, int64_t ldy,
+                         double* col_sum, double* col_sumsq, pn_stream_t stream);
 /* out [cols, rows] = in [rows, cols]^T (the weight of the input-gradient GEMM dx = dy W = pn_linear_f32(dy, W^T)). */
 int pn_transpose_f32(const float* in, int rows, int cols, float* out, pn_stream_t stream);
 /* Backward of the gather of sample_and_group (model/pointnet_util.py:128-131): dfeat[b, idx[b,s,k], :] +=

@@ -1,0 +1,369 @@
+// gemm_tc.cu -- the training step's layer GEMM on the tensor cores with BatchNorm fused on both sides
+// (reference: F.relu(bn(conv(x))) of model/pointnet_util.py:195-197, :310-312 and
+// pointnet2.py:172 in train() mode, and the input-gradient half of their autograd backward).
+//
+//     y[r, n] = sum_k f(x[r, k]) * W[n, k] + bias[n]          f(v) = relu(v * in_scale[k] + in_shift[k])   (optional)
+//     col_sum[n] += sum_r y[r, n],  col_sumsq[n] += sum_r y[r, n]^2                                         (optional, fp64)
+//
+// In train() mode BatchNorm needs the statistics of a layer's WHOLE output before the next layer can start, so the
+// forward cannot be one chain; unfused it costs three passes per layer (GEMM writes y, a reduction re-reads y, the
+// normalise+ReLU pass re-reads y and writes z: 20 bytes per element).  Here the statistics are accumulated in the GEMM's
+// epilogue and the normalise+ReLU of the PREVIOUS layer is applied while this GEMM loads its operand, so a layer costs one
+// read and one write (8 bytes per element) and the activated tensor z never exists; the backward recomputes what it needs
+// from y (pn_grad_weight_bf16x3 applies the same f to its x operand).
+//
+// Structure: persistent CTAs (up to two per SM).  The weights (<= 128 KB as bf16 hi + lo) are converted once per CTA into
+// shared memory in the UMMA K-major layout and stay resident; the x operand streams through a 2-stage ring of 128-row x
+// 32-column chunks that all 8 warps fill (fp32 -> f() -> bf16 hi/lo, 16-byte stores straight into the K-major layout,
+// register double buffer across chunks and tiles); an elected lane of warp 0 issues hi*hi + hi*lo + lo*hi per 16 columns
+// (tcgen05.mma kind::f16, both operands from shared memory, fp32 accumulator of 128 x cout in TMEM); the epilogue reads the
+// accumulator back (thread = row), adds the bias, stores y and reduces the column sums with a shuffle butterfly in fp64.
+// W can be given transposed (w[k, n]): the input-gradient GEMM dx = dy W of the backward pass reads W that way.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace pn {
+namespace gemm {
+
+constexpr int TM = 128, KC = 32, NS = 2, THREADS = 256;   // 2 stages + the register buffer: 128 x 128 layers fit two CTAs per SM
+constexpr int A_IMG = TM * KC * 2;            // one bf16 image of a 128 x 32 chunk: 8 KB
+constexpr int A_STAGE = 2 * A_IMG;            // hi + lo
+constexpr int W_MAX_BYTES = 128 * 1024;       // resident weights (hi + lo)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ bool elect() {
+    unsigned p;
+    asm volatile("{ .reg .pred q; elect.sync _|q, 0xffffffff; selp.u32 %0, 1, 0, q; }" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ld32(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 8 consecutive k of one row -> 8 bf16 hi + 8 bf16 lo, one 16-byte store each (a core-matrix row)
+__device__ __forceinline__ void store_split8(unsigned char* hi_img, unsigned char* lo_img, unsigned off, const float (&v)[8]) {
+    unsigned h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hb2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);       // .x (low half) = even k
+        const unsigned hb = *reinterpret_cast<const unsigned*>(&hb2);
+        const float r0 = v[2 * j] - __uint_as_float(hb << 16);
+        const float r1 = v[2 * j + 1] - __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 lb2 = __floats2bfloat162_rn(r0, r1);
+        h[j] = hb;
+        l[j] = *reinterpret_cast<const unsigned*>(&lb2);
+    }
+    *reinterpret_cast<uint4*>(hi_img + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_img + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Sum over the 32 lanes of a warp for 32 columns held one row per lane: a butterfly in which every step halves the
+// columns a lane is responsible for (31 shuffles).  Afterwards lane j holds the sum of column j.
+template <int W>
+__device__ __forceinline__ void colsum_step(double (&v)[32], int lane) {
+    if constexpr (W >= 1) {
+        const bool up = (lane & W) != 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const double send = up ? v[i] : v[i + W];
+            const double keep = up ? v[i + W] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+        }
+        colsum_step<W / 2>(v, lane);
+    }
+}
+
+struct Args {
+    const float* x; int64_t ldx; int64_t rows; int cin;
+    const float* in_scale; const float* in_shift; int in_relu;
+    const float* w; int w_transposed; const float* bias; int cout;
+    float* y; int64_t ldy;
+    double* col_sum; double* col_sumsq;
+    int k_pad, n_pad, x_vec;
+};
+
+__global__ void __launch_bounds__(THREADS)
+train_gemm_kernel(const Args a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int kch = a.k_pad / KC;                               // K chunks
+    const unsigned w_chunk_bytes = (unsigned)a.n_pad * KC * 4;  // hi + lo images of one K chunk of the weights
+    unsigned char* w_smem = smem;                               // [kch][hi: n_pad x 32 | lo: n_pad x 32]
+    unsigned char* a_smem = smem + (size_t)kch * w_chunk_bytes; // ring of NS stages
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(a_smem + NS * A_STAGE);   // full[NS], empty[NS], done
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 1);
+    double* part = reinterpret_cast<double*>(bars + 2 * NS + 2);                               // [2][4][n_pad] partial sums
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_done = smem_u32(bars + 2 * NS);
+
+    unsigned tmem_cols = 32;
+    while ((int)tmem_cols < a.n_pad) tmem_cols <<= 1;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar_full + 8 * s, THREADS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // ---- weights: fp32 -> bf16 hi/lo, K-major core matrices, once per CTA
+    {
+        const int kblocks = a.k_pad / 8;
+        for (int e = tid; e < a.n_pad * kblocks; e += THREADS) {
+            const int n = e % a.n_pad, kb = e / a.n_pad;        // consecutive threads = consecutive n
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kb * 8 + j;
+                float t = 0.0f;
+                if (n < a.cout && k < a.cin) t = a.w_transposed ? __ldg(a.w + (int64_t)k * a.cout + n) : __ldg(a.w + (int64_t)n * a.cin + k);
+                v[j] = t;
+            }
+            const int c = kb / (KC / 8), kbi = kb % (KC / 8);
+            unsigned char* img = w_smem + (size_t)c * w_chunk_bytes;
+            const unsigned off = (unsigned)(n >> 3) * (KC / 8) * 128u + (unsigned)kbi * 128u + (unsigned)(n & 7) * 16u;
+            store_split8(img, img + (size_t)a.n_pad * KC * 2, off, v);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tbase = *tmem_slot;
+
+    const int64_t tiles = (a.rows + TM - 1) / TM;
+    const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_chunks = my_tiles * kch;
+
+    // producer role: row m of the tile, k-blocks {half, half + 2} of every 32-column chunk
+    const int m = tid & 127, half = tid >> 7;
+    const unsigned row_off = (unsigned)(m >> 3) * (KC / 8) * 128u + (unsigned)(m & 7) * 16u;
+    const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(a.n_pad >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
+    const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
+                                     ((unsigned long long)((((unsigned)KC / 8) * 128u >> 4) & 0x3FFF) << 32) | (1ull << 46);
+
+    float va[2][8];
+    auto load_chunk = [&](int64_t gc) {
+        const int64_t it = gc / kch;
+        const int c = (int)(gc - it * kch);
+        const int64_t row = (blockIdx.x + it * gridDim.x) * TM + m;
+        const bool row_ok = row < a.rows;
+        const float* __restrict__ xr = a.x + row * a.ldx;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k0 = c * KC + (half + 2 * q) * 8;
+            if (row_ok && a.x_vec && k0 + 8 <= a.cin) {
+                const float4 lo4 = __ldg(reinterpret_cast<const float4*>(xr + k0));
+                const float4 hi4 = __ldg(reinterpret_cast<const float4*>(xr + k0 + 4));
+                va[q][0] = lo4.x; va[q][1] = lo4.y; va[q][2] = lo4.z; va[q][3] = lo4.w;
+                va[q][4] = hi4.x; va[q][5] = hi4.y; va[q][6] = hi4.z; va[q][7] = hi4.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) va[q][j] = (row_ok && k0 + j < a.cin) ? __ldg(xr + k0 + j) : 0.0f;
+            }
+        }
+    };
+    if (total_chunks > 0) load_chunk(0);
+    for (int64_t gc = 0; gc < total_chunks; ++gc) {
+        const int64_t it = gc / kch;
+        const int c = (int)(gc - it * kch);
+        const int s = (int)(gc % NS);
+        const unsigned use = (unsigned)(gc / NS);
+        float cur[2][8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[q][j] = va[q][j];
+        if (gc + 1 < total_chunks) load_chunk(gc + 1);
+        // f(): normalise + ReLU of the previous layer, applied to the operand on its way into shared memory
+        if (a.in_scale) {
+            const int64_t row = (blockIdx.x + it * gridDim.x) * TM + m;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int k0 = c * KC + (half + 2 * q) * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = k0 + j;
+                    float t = 0.0f;
+                    if (k < a.cin && row < a.rows) {
+                        t = fmaf(cur[q][j], __ldg(a.in_scale + k), __ldg(a.in_shift + k));
+                        if (a.in_relu) t = fmaxf(t, 0.0f);
+                    }
+                    cur[q][j] = t;
+                }
+            }
+        }
+        if (gc >= NS) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+        unsigned char* st = a_smem + s * A_STAGE;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) store_split8(st, st + A_IMG, row_off + (unsigned)(half + 2 * q) * 128u, cur[q]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_full + 8 * s);
+        if (warp == 0) {
+            mbar_wait(bar_full + 8 * s, use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect()) {
+                const unsigned a_hi = smem_u32(st), a_lo = a_hi + A_IMG;
+                const unsigned b_hi = smem_u32(w_smem) + (unsigned)c * w_chunk_bytes, b_lo = b_hi + (unsigned)a.n_pad * KC * 2;
+#pragma unroll
+                for (int t = 0; t < KC / 16; ++t) {
+                    const unsigned long long dah = dbase | (unsigned long long)(((a_hi + t * 256) >> 4) & 0x3FFF);
+                    const unsigned long long dal = dbase | (unsigned long long)(((a_lo + t * 256) >> 4) & 0x3FFF);
+                    const unsigned long long dbh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
+                    const unsigned long long dbl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
+                    const unsigned acc0 = (c > 0 || t > 0) ? 1u : 0u;
+                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(tbase),
+                                 "l"(dah), "l"(dbh), "r"(idesc), "r"(acc0) : "memory");
+                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(tbase),
+                                 "l"(dah), "l"(dbl), "r"(idesc), "r"(1u) : "memory");
+                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(tbase),
+                                 "l"(dal), "l"(dbh), "r"(idesc), "r"(1u) : "memory");
+                }
+                commit(bar_empty + 8 * s);
+                if (c + 1 == kch) commit(bar_done);
+            }
+            __syncwarp();
+        }
+        if (c + 1 < kch) continue;
+        // ---- epilogue of this row tile: accumulator (lane = row, column = output channel) -> + bias -> y, column sums
+        mbar_wait(bar_done, (unsigned)it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t row = (blockIdx.x + it * gridDim.x) * TM + (warp & 3) * 32 + lane;
+        const bool row_ok = row < a.rows;
+        const int nch = a.n_pad / 32, h = warp >> 2;
+        const int ch0 = h == 0 ? 0 : (nch + 1) / 2, ch1 = h == 0 ? (nch + 1) / 2 : nch;
+        for (int ch = ch0; ch < ch1; ++ch) {
+            const int col0 = ch * 32;
+            unsigned r[32];
+            ld32(tbase + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)col0, r);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = col0 + j;
+                v[j] = __uint_as_float(r[j]) + ((a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.0f);
+            }
+            if (row_ok) {
+                float* dst = a.y + row * a.ldy + col0;
+                if (col0 + 32 <= a.cout && ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < a.cout) dst[j] = v[j];
+                }
+            }
+            if (a.col_sum) {
+                double d1[32], d2[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double d = row_ok ? (double)v[j] : 0.0;
+                    d1[j] = d;
+                    d2[j] = d * d;
+                }
+                colsum_step<16>(d1, lane);
+                colsum_step<16>(d2, lane);
+                part[(0 * 4 + (warp & 3)) * a.n_pad + col0 + lane] = d1[0];
+                part[(1 * 4 + (warp & 3)) * a.n_pad + col0 + lane] = d2[0];
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                      // every warp has read the accumulator: the next tile may overwrite it
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (a.col_sum) {
+            for (int n = tid; n < a.cout; n += THREADS) {
+                atomicAdd(a.col_sum + n, part[(0 * 4 + 0) * a.n_pad + n] + part[(0 * 4 + 1) * a.n_pad + n] +
+                                             part[(0 * 4 + 2) * a.n_pad + n] + part[(0 * 4 + 3) * a.n_pad + n]);
+                atomicAdd(a.col_sumsq + n, part[(1 * 4 + 0) * a.n_pad + n] + part[(1 * 4 + 1) * a.n_pad + n] +
+                                               part[(1 * 4 + 2) * a.n_pad + n] + part[(1 * 4 + 3) * a.n_pad + n]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(tmem_cols));
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace gemm
+}  // namespace pn
+
+PN_EXPORT int pn_train_gemm_supported(int cin, int cout) {
+    using namespace pn::gemm;
+    if (cin < 1 || cout < 1) return 0;
+    const int k_pad = round_up(cin, KC), n_pad = round_up(cout, 32);
+    return n_pad <= 256 && (size_t)k_pad * n_pad * 4 <= (size_t)W_MAX_BYTES;
+}
+
+PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale,
+                                   const float* in_shift, int in_relu, const float* w, int w_transposed, const float* bias,
+                                   int cout, float* y, int64_t ldy, double* col_sum, double* col_sumsq, pn_stream_t stream) {
+    using namespace pn;
+    using namespace pn::gemm;
+    PN_REQUIRE(x && w && y, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: null pointer");
+    PN_REQUIRE(rows > 0 && cin > 0 && cout > 0 && ldx >= cin && ldy >= cout, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: bad shape");
+    PN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr) && (col_sum == nullptr) == (col_sumsq == nullptr), PN_ERR_BAD_ARG,
+               "pn_train_gemm_bf16x3: in_scale/in_shift and col_sum/col_sumsq come in pairs");
+    PN_REQUIRE(pn_train_gemm_supported(cin, cout), PN_ERR_UNSUPPORTED,
+               "pn_train_gemm_bf16x3: layer %d -> %d does not fit the resident-weight kernel (cout <= 256, padded cin*cout*4 <= 128 KB)", cin, cout);
+    Args a;
+    a.x = x; a.ldx = ldx; a.rows = rows; a.cin = cin;
+    a.in_scale = in_scale; a.in_shift = in_shift; a.in_relu = in_relu;
+    a.w = w; a.w_transposed = w_transposed; a.bias = bias; a.cout = cout;
+    a.y = y; a.ldy = ldy; a.col_sum = col_sum; a.col_sumsq = col_sumsq;
+    a.k_pad = round_up(cin, KC);
+    a.n_pad = round_up(cout, 32);
+    a.x_vec = ((uintptr_t)x % 16 == 0) && (ldx % 4 == 0);
+    const size_t smem = (size_t)a.k_pad * a.n_pad * 4 + NS * A_STAGE + 8 * (2 * NS + 2) + (size_t)2 * 4 * a.n_pad * sizeof(double) + 64;
+    static int sms = 0;
+    static size_t smem_set = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(train_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pn_train_gemm_bf16x3: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return (int)e;
+        }
+        smem_set = smem;
+    }
+    const int64_t tiles = ceil_div(rows, TM);
+    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+    const int64_t grid = tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm;
+    train_gemm_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(a);
+    return finish_launch("pn_train_gemm_bf16x3");
+}

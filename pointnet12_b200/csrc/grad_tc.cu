@@ -82,7 +82,8 @@ __device__ __forceinline__ void store_split8(unsigned char* hi_img, unsigned cha
 __global__ void __launch_bounds__(THREADS)
 grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x, int64_t ldx, int64_t rows,
                       int64_t rows_per_split, int cout, int cin, float* __restrict__ dw, int64_t lddw,
-                      float* __restrict__ db, int vec_red) {
+                      float* __restrict__ db, int vec_red, const float* __restrict__ x_scale, const float* __restrict__ x_shift,
+                      int x_relu) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + NS * STAGE);   // full[NS], empty[NS], done
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 1);
@@ -117,6 +118,10 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
     const float* __restrict__ bp = x + ci0 + m;
     const unsigned row_off = (unsigned)(m >> 3) * (KC / 8) * 128u + (unsigned)(m & 7) * 16u;
     const bool do_bias = db != nullptr && blockIdx.y == 0 && a_ok;
+    // optional f(x) = relu(x * scale[ci] + shift[ci]) on the x operand: the normalise + ReLU of the layer that produced x,
+    // when the forward kept only its pre-normalisation output (pn_train_gemm_bf16x3)
+    const bool x_tf = x_scale != nullptr;
+    const float xs = (x_tf && b_ok) ? x_scale[ci0 + m] : 1.0f, xh = (x_tf && b_ok) ? x_shift[ci0 + m] : 0.0f;
     float bsum = 0.0f;
     // instruction descriptor: D fp32, A / B bf16, both K-major, N = 128, M = 128
     const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TN >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
@@ -136,7 +141,15 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
                 const int64_t r = k0 + kb * 8 + j;
                 const bool in = r < r1;
                 va[q][j] = (in && a_ok) ? __ldg(ap + r * lddy) : 0.0f;
-                vb[q][j] = (in && b_ok) ? __ldg(bp + r * ldx) : 0.0f;
+                float t = 0.0f;
+                if (in && b_ok) {
+                    t = __ldg(bp + r * ldx);
+                    if (x_tf) {
+                        t = fmaf(t, xs, xh);
+                        if (x_relu) t = fmaxf(t, 0.0f);
+                    }
+                }
+                vb[q][j] = t;
             }
         }
     };
@@ -226,8 +239,23 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
 }  // namespace gtc
 }  // namespace pn
 
+static int grad_weight_tc(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin, float* dw,
+                          int64_t lddw, float* db, const float* x_scale, const float* x_shift, int x_relu, pn_stream_t stream);
+
 PN_EXPORT int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout,
                                     int cin, float* dw, int64_t lddw, float* db, pn_stream_t stream) {
+    return grad_weight_tc(dy, lddy, x, ldx, rows, cout, cin, dw, lddw, db, nullptr, nullptr, 0, stream);
+}
+
+PN_EXPORT int pn_grad_weight_bn_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* x_scale,
+                                       const float* x_shift, int x_relu, int64_t rows, int cout, int cin, float* dw,
+                                       int64_t lddw, float* db, pn_stream_t stream) {
+    PN_REQUIRE(x_scale && x_shift, PN_ERR_BAD_ARG, "pn_grad_weight_bn_bf16x3: null scale / shift");
+    return grad_weight_tc(dy, lddy, x, ldx, rows, cout, cin, dw, lddw, db, x_scale, x_shift, x_relu, stream);
+}
+
+static int grad_weight_tc(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin, float* dw,
+                          int64_t lddw, float* db, const float* x_scale, const float* x_shift, int x_relu, pn_stream_t stream) {
     using namespace pn;
     using namespace pn::gtc;
     PN_REQUIRE(dy && x && dw, PN_ERR_BAD_ARG, "pn_grad_weight_bf16x3: null pointer");
@@ -251,6 +279,6 @@ PN_EXPORT int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* 
     dim3 grid((unsigned)ceil_div(cout, TM), (unsigned)ceil_div(cin, TN), (unsigned)splits);
     const int vec_red = ((uintptr_t)dw % 16 == 0) && (lddw % 4 == 0);
     grad_weight_tc_kernel<<<grid, THREADS, SMEM, (cudaStream_t)stream>>>(dy, lddy, x, ldx, rows, rps, cout, cin, dw, lddw, db,
-                                                                        vec_red);
+                                                                        vec_red, x_scale, x_shift, x_relu);
     return finish_launch("pn_grad_weight_bf16x3");
 }

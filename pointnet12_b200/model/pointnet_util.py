@@ -290,7 +290,15 @@ class PointNetSetAbstraction(nn.Module):
         if self.group_all:
             new_xyz, grouped = sample_and_group_all(xyz_pm, pts_pm)
             B, S, K, C = grouped.shape
-            rows = _mlp_rows(grouped.view(B * S * K, C), self._folded.get(self.mlp_convs, self.mlp_bns))
+            per_layer = self._folded.layer_chains(self.mlp_convs, self.mlp_bns)
+            if per_layer is not None:
+                # the group-all MLP (e.g. 643 -> 256 -> 512 -> 1024) is wider than a fused chain takes (hidden layers <= 256),
+                # but every layer alone fits: one tensor-core launch per layer instead of the CUDA-core SGEMM
+                rows = grouped.view(B * S * K, C)
+                for c in per_layer:
+                    rows = ops.mlp_rows_tc(c, rows)
+            else:
+                rows = _mlp_rows(grouped.view(B * S * K, C), self._folded.get(self.mlp_convs, self.mlp_bns))
             pooled = ops.group_max(rows, K).view(B, S, -1)
         else:
             new_xyz, idx = self.geometry(xyz_pm, start_idx)

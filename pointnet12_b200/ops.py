@@ -664,6 +664,50 @@ def bn_batch_stats(y: torch.Tensor, bn, momentum_update: bool = True) -> BatchSt
     return st
 
 
+def bn_finalize(acc: torch.Tensor, rows: int, bn) -> BatchStats:
+    """pn_bn_finalize_f32 on column sums acc float64 [2, C] (sum, sum of squares) accumulated over `rows` rows -- by
+    pn_bn_stats_f32 or by the epilogue of pn_train_gemm_bf16x3; updates bn.running_* like nn.BatchNorm in train mode."""
+    Cc = acc.shape[1]
+    st = BatchStats()
+    buf = torch.empty((4, Cc), dtype=torch.float32, device=acc.device)
+    st.scale, st.shift, st.mean, st.invstd = buf[0], buf[1], buf[2], buf[3]
+    st.rows = rows
+    track = bn.track_running_stats and bn.running_mean is not None
+    with _on_device(acc):
+        nv.call("pn_bn_finalize_f32", acc[0].data_ptr(), acc[1].data_ptr(), rows, Cc, _p(bn.weight), _p(bn.bias),
+                float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1),
+                bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                bn.num_batches_tracked.data_ptr() if track and bn.num_batches_tracked is not None else None,
+                st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), _stream())
+    if track:
+        torch.autograd.graph.increment_version([b for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked) if b is not None])
+    return st
+
+
+def train_gemm_supported(cin: int, cout: int) -> bool:
+    return bool(nv.lib().pn_train_gemm_supported(int(cin), int(cout)))
+
+
+def train_gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], in_stats: Optional[BatchStats] = None,
+               in_relu: bool = True, stats_acc: Optional[torch.Tensor] = None, transposed: bool = False) -> torch.Tensor:
+    """pn_train_gemm_bf16x3: y = f(x) @ W^T + bias with f = the normalise(+ReLU) of the layer that produced x (in_stats:
+    its BatchStats; None = identity), column sums of y / y*y added to stats_acc (float64 [2, cout], zeroed by the caller).
+    W = w [cout, cin], or w^T for w [cin, cout] when transposed."""
+    x = _rowmat(x, "x")
+    rows, cin = x.shape
+    w = _f32(w, "w").contiguous()
+    cout = w.shape[1] if transposed else w.shape[0]
+    if (w.shape[0] if transposed else w.shape[1]) != cin:
+        raise ValueError(f"weight shape {tuple(w.shape)} does not match {cin} input channels")
+    y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
+    with _on_device(x):
+        nv.call("pn_train_gemm_bf16x3", x.data_ptr(), _ld(x), rows, cin, _p(in_stats.scale) if in_stats is not None else None,
+                _p(in_stats.shift) if in_stats is not None else None, int(in_relu), w.data_ptr(), int(transposed), _p(bias), cout,
+                y.data_ptr(), cout, _p(stats_acc[0]) if stats_acc is not None else None,
+                _p(stats_acc[1]) if stats_acc is not None else None, _stream())
+    return y
+
+
 def bn_act(y: torch.Tensor, st: BatchStats, relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     y = _rowmat(y, "y")
     rows, Cc = y.shape
@@ -714,7 +758,7 @@ GRAD_TC_MIN_TILE = int(os.environ.get("PN12_GRAD_TC_MIN", "1024"))     # cout * 
 
 
 def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor],
-                engine: str = "auto") -> None:
+                engine: str = "auto", x_stats: Optional[BatchStats] = None, x_relu: bool = True) -> None:
     """dw [cout, cin] += dy^T x, db [cout] += column sums of dy (in place; the buffers hold zeros or a gradient).
     engine: "tc" (pn_grad_weight_bf16x3, tensor cores, 3-pass split bf16), "fp32" (pn_grad_weight_f32, CUDA cores) or
     "auto" (tensor cores unless the MLP mode is 'fp32' or the layer is tiny)."""
@@ -725,6 +769,12 @@ def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optiona
         raise ValueError("grad_weight: shape mismatch")
     if engine == "auto":
         engine = "tc" if (_MLP_MODE == "bf16x3" and cout * cin >= GRAD_TC_MIN_TILE) else "fp32"
+    if x_stats is not None:
+        # x is the PRE-normalisation output of the previous layer: its normalise + ReLU is applied on load (tensor cores only)
+        with _on_device(dy):
+            nv.call("pn_grad_weight_bn_bf16x3", dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), x_stats.scale.data_ptr(),
+                    x_stats.shift.data_ptr(), int(x_relu), rows, cout, cin, dw.data_ptr(), cin, _p(db), _stream())
+        return
     name = {"tc": "pn_grad_weight_bf16x3", "fp32": "pn_grad_weight_f32"}[engine]
     with _on_device(dy):
         nv.call(name, dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), rows, cout, cin, dw.data_ptr(), cin, _p(db), _stream())

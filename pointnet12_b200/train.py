@@ -22,6 +22,7 @@ atomics; `ops.set_mlp_mode("fp32")` puts every GEMM on the CUDA cores.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -40,6 +41,8 @@ def _gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], transp
     gradient GEMM dx = dy W of a conv with weight w).  Tensor cores (single-layer tcgen05 chain, 3-pass split bf16 = fp32
     parity; the weight is re-packed on every call because it changes every iteration) unless the MLP mode is 'fp32'."""
     cout, cin = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+    if ops.mlp_mode() == "bf16x3" and FUSED_BN and ops.train_gemm_supported(cin, cout):
+        return ops.train_gemm(x, w, bias, transposed=transposed)      # weights converted in-kernel: no pack launch
     if ops.mlp_mode() == "bf16x3" and ops.PackedChain.supported([(cin, cout)]):
         return ops.mlp_rows_tc(ops.PackedChain([(w, bias, False)], transposed=transposed), x)
     return ops.linear(x, ops.transpose(w) if transposed else w, bias, relu=False)
@@ -54,34 +57,65 @@ def _grad_sink(p: torch.Tensor, shape) -> Tuple[torch.Tensor, bool]:
     return torch.zeros(shape, dtype=torch.float32, device=p.device), False
 
 
+FUSED_BN = os.environ.get("PN12_TRAIN_FUSED", "1") != "0"     # BatchNorm fused into the training GEMMs (pn_train_gemm_bf16x3)
+
+
 def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] = None):
     """x [rows, cin] -> (output, saved).  layers = [(conv, bn or None, relu)]; pool_K: the last layer's activation is
-    max-pooled over runs of K rows (set abstraction)."""
+    max-pooled over runs of K rows (set abstraction).
+
+    Fused path (tensor-core mode, layers that fit pn_train_gemm_bf16x3): a layer is ONE kernel -- the GEMM applies the
+    previous layer's normalise + ReLU while loading its operand and accumulates this layer's batch statistics in its
+    epilogue -- plus the tiny finalize; only the pre-normalisation outputs y exist in memory.  `pending` is the BatchStats
+    still to be applied to the current x.  saved[l] = (x, pending-at-input, y, stats, relu, argmax)."""
     saved = []
+    pending = None
+    rows = x.shape[0]
     for li, (conv, bn, relu) in enumerate(layers):
-        y = _gemm(x, _w2d(conv), conv.bias.detach() if conv.bias is not None else None)
+        w = _w2d(conv)
+        bias = conv.bias.detach() if conv.bias is not None else None
+        fused = (FUSED_BN and bn is not None and ops.mlp_mode() == "bf16x3" and (pending is None or relu)
+                 and ops.train_gemm_supported(w.shape[1], w.shape[0]))
         st, am = None, None
+        if bn is not None and not relu:
+            raise NotImplementedError("training path: BatchNorm layers are followed by ReLU in every supported block")
+        if fused:
+            acc = torch.zeros((2, w.shape[0]), dtype=torch.float64, device=x.device)
+            y = ops.train_gemm(x, w, bias, in_stats=pending, stats_acc=acc)
+            st = ops.bn_finalize(acc, rows, bn)
+            saved.append((x, pending, y, st, relu, None))
+            x, pending = y, st
+            continue
+        if pending is not None:                      # a layer the fused kernel does not take: materialise its input first
+            x, pending = ops.bn_act(x, pending, True), None
+        y = _gemm(x, w, bias)
         if bn is not None:
             st = ops.bn_batch_stats(y, bn)
-            if pool_K and li == len(layers) - 1:
-                z, am = ops.bn_act_max(y, st, pool_K, relu)
-            else:
-                z = ops.bn_act(y, st, relu)
+            saved.append((x, None, y, st, relu, None))
+            x, pending = y, st
         else:
-            if relu or (pool_K and li == len(layers) - 1):
+            if relu:
                 raise NotImplementedError("training path: a layer without BatchNorm must be a plain linear layer")
-            z = y
-        saved.append((x, y, st, relu, am))
-        x = z
+            saved.append((x, None, y, None, relu, None))
+            x = y
+    if pending is not None:                          # the block's output leaves in activated (and pooled) form
+        xin, pin, y, st, relu, _ = saved[-1]
+        if pool_K:
+            x, am = ops.bn_act_max(y, st, pool_K, relu)
+            saved[-1] = (xin, pin, y, st, relu, am)
+        else:
+            x = ops.bn_act(y, st, relu)
+    elif pool_K:
+        raise NotImplementedError("training path: the pooled layer must have BatchNorm")
     return x, saved
 
 
 def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optional[int], need_dx: bool):
-    """-> (dx or None, [per layer: (dW [Co,Ci], db, dgamma, dbeta)])."""
+    """-> (dx or None, [per layer: (dW [Co,Ci], db, dgamma, dbeta)]; None where the gradient went straight into p.grad)."""
     grads = [None] * len(layers)
     for li in range(len(layers) - 1, -1, -1):
         conv, bn, relu = layers[li]
-        x, y, st, _, am = saved[li]
+        x, x_stats, y, st, _, am = saved[li]
         dgamma = dbeta = None
         g_direct = False
         if st is not None:
@@ -93,7 +127,7 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
         w = _w2d(conv)
         dw, w_direct = _grad_sink(conv.weight, w.shape)
         db, b_direct = _grad_sink(conv.bias, (w.shape[0],)) if conv.bias is not None else (None, False)
-        ops.grad_weight(dy, x, dw, db)
+        ops.grad_weight(dy, x, dw, db, x_stats=x_stats)      # x_stats: x is the previous layer's y, activated on load
         grads[li] = (None if w_direct else dw, None if b_direct else db, None if g_direct else dgamma, None if g_direct else dbeta)
         dz = _gemm(dy, w, None, transposed=True) if (li > 0 or need_dx) else None
     return dz, grads

@@ -130,6 +130,49 @@ def test_grad_weight_and_input_gradient(dev, rows, cout, cin, ldx, engine):
         assert rl2(y_tc.cpu().numpy(), x.astype(np.float64) @ w.astype(np.float64).T) < 2e-5
 
 
+@pytest.mark.parametrize("rows,cin,cout,ldx,transposed", [
+    (1000, 67, 64, 68, False), (70001, 128, 128, 128, False), (4096, 4, 32, 4, False), (333, 131, 128, 132, False),
+    (5000, 128, 256, 128, False), (2048, 128, 19, 128, False), (9000, 64, 67, 64, True), (130, 256, 128, 256, True),
+    (127, 32, 32, 32, False)])
+def test_fused_train_gemm(dev, rows, cin, cout, ldx, transposed):
+    """pn_train_gemm_bf16x3: y = relu(x*scale+shift) @ W^T + b with the batch statistics of y from the epilogue, against
+    float64 numpy; then the weight-gradient kernel applying the same transform to its x operand."""
+    from pointnet12_b200 import ops
+
+    assert ops.train_gemm_supported(cin, cout)
+    rng = np.random.default_rng(rows + cin)
+    x = (rng.standard_normal((rows, cin)) * 2 + 0.5).astype(np.float32)
+    w = rng.standard_normal((cout, cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    xb = torch.zeros((rows, ldx), device=dev)
+    xb[:, :cin] = T(x, dev)
+    wt = T(w.T.copy() if transposed else w, dev)
+    # plain
+    y = ops.train_gemm(xb[:, :cin], wt, T(b, dev), transposed=transposed)
+    want = x.astype(np.float64) @ w.astype(np.float64).T + b
+    assert rl2(y.cpu().numpy(), want) < 2e-5
+    # fused: input transform + output statistics
+    st = ops.BatchStats()
+    st.scale, st.shift = T(rng.uniform(0.5, 1.5, cin).astype(np.float32), dev), T(rng.standard_normal(cin).astype(np.float32), dev)
+    st.mean = st.invstd = st.scale
+    acc = torch.zeros((2, cout), dtype=torch.float64, device=dev)
+    y = ops.train_gemm(xb[:, :cin], wt, T(b, dev), in_stats=st, stats_acc=acc, transposed=transposed)
+    z = np.maximum(x.astype(np.float64) * st.scale.cpu().numpy().astype(np.float64) + st.shift.cpu().numpy().astype(np.float64), 0)
+    want = z @ w.astype(np.float64).T + b
+    assert rl2(y.cpu().numpy(), want) < 2e-5
+    got = acc.cpu().numpy()
+    y64 = y.cpu().numpy().astype(np.float64)
+    assert np.abs(got[0] - y64.sum(0)).max() <= 1e-9 * np.abs(y64).sum(0).max() + 1e-6
+    assert np.abs(got[1] - (y64 ** 2).sum(0)).max() <= 1e-9 * (y64 ** 2).sum(0).max() + 1e-6
+    # weight gradient with the same transform applied to its x operand
+    dy = rng.standard_normal((rows, 48)).astype(np.float32)
+    dw = torch.zeros((48, cin), device=dev)
+    db = torch.zeros((48,), device=dev)
+    ops.grad_weight(T(dy, dev), xb[:, :cin], dw, db, x_stats=st)
+    assert rl2(dw.cpu().numpy(), dy.astype(np.float64).T @ z) < 2e-5
+    assert rl2(db.cpu().numpy(), dy.astype(np.float64).sum(0)) < 1e-5
+
+
 def test_group_and_interpolate_backward(dev):
     from pointnet12_b200 import ops
 

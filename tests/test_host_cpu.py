@@ -125,6 +125,21 @@ def _gloo_worker(rank, world, port, out):
         assert torch.equal(allv, (glob[:, 0, :] * 1000).long())
         ms = pdist.max_over_ranks([1.0 + rank, 5.0 - rank])
         assert ms == [float(world), 5.0]
+        # training step, data-parallel exchange: every rank's flat gradient is summed by ONE all-reduce and the 1/world
+        # factor is returned for the Adam kernel (train.FlatAdam; the update itself is a CUDA kernel, not run here)
+        from pointnet12_b200.train import FlatAdam
+
+        torch.manual_seed(0)
+        lin = torch.nn.Sequential(torch.nn.Conv1d(4, 8, 1), torch.nn.BatchNorm1d(8))
+        opt = FlatAdam(lin.parameters(), lr=1e-3, weight_decay=1e-4)
+        assert opt.flat.numel() == sum(p.numel() for p in lin.parameters())
+        assert all(p.data_ptr() >= opt.flat.data_ptr() for p in lin.parameters())        # parameters live in the flat buffer
+        opt.zero_grad()
+        lin(torch.randn(2, 4, 5)).sum().backward()                                        # autograd accumulates in place
+        assert opt.grad.abs().sum() > 0 and all(p.grad.data_ptr() >= opt.grad.data_ptr() for p in lin.parameters())
+        opt.grad.fill_(1.0 + rank)
+        scale = opt.all_reduce()
+        assert scale == 1.0 / world and torch.equal(opt.grad, torch.full_like(opt.grad, sum(1.0 + r for r in range(world))))
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
