@@ -14,10 +14,11 @@
 //
 // Structure: persistent CTAs (up to two per SM).  The weights (<= 128 KB as bf16 hi + lo) are converted once per CTA into
 // shared memory in the UMMA K-major layout and stay resident; the x operand streams through a 2-stage ring of 128-row x
-// 32-column chunks that all 8 warps fill (fp32 -> f() -> bf16 hi/lo, 16-byte stores straight into the K-major layout,
-// register double buffer across chunks and tiles); an elected lane of warp 0 issues hi*hi + hi*lo + lo*hi per 16 columns
-// (tcgen05.mma kind::f16, both operands from shared memory, fp32 accumulator of 128 x cout in TMEM); the epilogue reads the
-// accumulator back (thread = row), adds the bias, stores y and reduces the column sums with a shuffle butterfly in fp64.
+// 32-column chunks that the four PRODUCER warps fill (thread = row: fp32 -> f() -> bf16 hi/lo, 16-byte stores straight into
+// the K-major layout, register double buffer across chunks and tiles); an elected lane of warp 0 issues hi*hi + hi*lo +
+// lo*hi per 16 columns (tcgen05.mma kind::f16, both operands from shared memory) into one of TWO fp32 accumulators of
+// 128 x cout in TMEM; the four EPILOGUE warps read a finished accumulator back (thread = row), add the bias, store y and
+// reduce the column sums with a shuffle butterfly in fp64 -- while the producers and the tensor core work on the next tile.
 // W can be given transposed (w[k, n]): the input-gradient GEMM dx = dy W of the backward pass reads W that way.
 #include <cuda_bf16.h>
 
@@ -85,6 +86,19 @@ __device__ __forceinline__ void store_split8(unsigned char* hi_img, unsigned cha
 // Sum over the 32 lanes of a warp for 32 columns held one row per lane: a butterfly in which every step halves the
 // columns a lane is responsible for (31 shuffles).  Afterwards lane j holds the sum of column j.
 template <int W>
+__device__ __forceinline__ void colsum_step_f(float (&v)[32], int lane) {
+    if constexpr (W >= 4) {
+        const bool up = (lane & W) != 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const float send = up ? v[i] : v[i + W];
+            const float keep = up ? v[i + W] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+        }
+        colsum_step_f<W / 2>(v, lane);
+    }
+}
+template <int W>
 __device__ __forceinline__ void colsum_step(double (&v)[32], int lane) {
     if constexpr (W >= 1) {
         const bool up = (lane & W) != 0;
@@ -114,20 +128,26 @@ train_gemm_kernel(const Args a) {
     const unsigned w_chunk_bytes = (unsigned)a.n_pad * KC * 4;  // hi + lo images of one K chunk of the weights
     unsigned char* w_smem = smem;                               // [kch][hi: n_pad x 32 | lo: n_pad x 32]
     unsigned char* a_smem = smem + (size_t)kch * w_chunk_bytes; // ring of NS stages
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(a_smem + NS * A_STAGE);   // full[NS], empty[NS], done
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 1);
-    double* part = reinterpret_cast<double*>(bars + 2 * NS + 2);                               // [2][4][n_pad] partial sums
+    // barriers: full[NS] (128 producer arrivals), empty[NS] (MMA commit), acc_full[2] (MMA commit), acc_empty[2] (128 epilogue arrivals)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(a_smem + NS * A_STAGE);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 4);
+    float* tf = reinterpret_cast<float*>(bars + 16);                                           // [2][k_pad]: in_scale | in_shift (16-byte aligned)
+    double* part = reinterpret_cast<double*>(tf + 2 * a.k_pad);                                // [2 tiles][2][4][n_pad] partial sums
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_done = smem_u32(bars + 2 * NS);
+    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_accf = smem_u32(bars + 2 * NS),
+                   bar_acce = smem_u32(bars + 2 * NS + 2);
 
     unsigned tmem_cols = 32;
-    while ((int)tmem_cols < a.n_pad) tmem_cols <<= 1;
+    while ((int)tmem_cols < 2 * a.n_pad) tmem_cols <<= 1;       // two accumulators: the MMAs of tile i+1 overlap the epilogue of tile i
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_full + 8 * s, THREADS);
+            mbar_init(bar_full + 8 * s, THREADS / 2);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_done, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_accf + 8 * b, 1);
+            mbar_init(bar_acce + 8 * b, THREADS / 2);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -153,6 +173,13 @@ train_gemm_kernel(const Args a) {
             store_split8(img, img + (size_t)a.n_pad * KC * 2, off, v);
         }
     }
+    if (a.in_scale) {
+        // the operand transform's per-channel constants: read through shared memory (a warp's lanes all want the same k)
+        for (int k = tid; k < a.k_pad; k += THREADS) {
+            tf[k] = k < a.cin ? __ldg(a.in_scale + k) : 0.0f;
+            tf[a.k_pad + k] = k < a.cin ? __ldg(a.in_shift + k) : 0.0f;
+        }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -161,149 +188,164 @@ train_gemm_kernel(const Args a) {
 
     const int64_t tiles = (a.rows + TM - 1) / TM;
     const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_chunks = my_tiles * kch;
 
-    // producer role: row m of the tile, k-blocks {half, half + 2} of every 32-column chunk
-    const int m = tid & 127, half = tid >> 7;
-    const unsigned row_off = (unsigned)(m >> 3) * (KC / 8) * 128u + (unsigned)(m & 7) * 16u;
-    const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(a.n_pad >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
-    const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
-                                     ((unsigned long long)((((unsigned)KC / 8) * 128u >> 4) & 0x3FFF) << 32) | (1ull << 46);
-
-    float va[2][8];
-    auto load_chunk = [&](int64_t gc) {
-        const int64_t it = gc / kch;
-        const int c = (int)(gc - it * kch);
-        const int64_t row = (blockIdx.x + it * gridDim.x) * TM + m;
-        const bool row_ok = row < a.rows;
-        const float* __restrict__ xr = a.x + row * a.ldx;
+    if (warp < 4) {
+        // ================= producers (warps 0-3): thread = row of the tile; warp 0 also issues the MMAs =================
+        const int64_t total_chunks = my_tiles * kch;
+        const int m = tid;
+        const unsigned row_off = (unsigned)(m >> 3) * (KC / 8) * 128u + (unsigned)(m & 7) * 16u;
+        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(a.n_pad >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
+        const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
+                                         ((unsigned long long)((((unsigned)KC / 8) * 128u >> 4) & 0x3FFF) << 32) | (1ull << 46);
+        float va[KC];
+        auto load_chunk = [&](int64_t gc) {
+            const int64_t it = gc / kch;
+            const int c = (int)(gc - it * kch);
+            const int64_t row = (blockIdx.x + it * gridDim.x) * TM + m;
+            const bool row_ok = row < a.rows;
+            const float* __restrict__ xr = a.x + row * a.ldx + c * KC;
+            if (a.x_vec && (c + 1) * KC <= a.cin) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int k0 = c * KC + (half + 2 * q) * 8;
-            if (row_ok && a.x_vec && k0 + 8 <= a.cin) {
-                const float4 lo4 = __ldg(reinterpret_cast<const float4*>(xr + k0));
-                const float4 hi4 = __ldg(reinterpret_cast<const float4*>(xr + k0 + 4));
-                va[q][0] = lo4.x; va[q][1] = lo4.y; va[q][2] = lo4.z; va[q][3] = lo4.w;
-                va[q][4] = hi4.x; va[q][5] = hi4.y; va[q][6] = hi4.z; va[q][7] = hi4.w;
+                for (int i = 0; i < KC / 4; ++i) {
+                    const float4 t = row_ok ? __ldg(reinterpret_cast<const float4*>(xr) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    va[4 * i] = t.x; va[4 * i + 1] = t.y; va[4 * i + 2] = t.z; va[4 * i + 3] = t.w;
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) va[q][j] = (row_ok && k0 + j < a.cin) ? __ldg(xr + k0 + j) : 0.0f;
+                for (int j = 0; j < KC; ++j) va[j] = (row_ok && c * KC + j < a.cin) ? __ldg(xr + j) : 0.0f;
             }
-        }
-    };
-    if (total_chunks > 0) load_chunk(0);
-    for (int64_t gc = 0; gc < total_chunks; ++gc) {
-        const int64_t it = gc / kch;
-        const int c = (int)(gc - it * kch);
-        const int s = (int)(gc % NS);
-        const unsigned use = (unsigned)(gc / NS);
-        float cur[2][8];
+        };
+        if (total_chunks > 0) load_chunk(0);
+        for (int64_t gc = 0; gc < total_chunks; ++gc) {
+            const int64_t it = gc / kch;
+            const int c = (int)(gc - it * kch);
+            const int s = (int)(gc % NS);
+            const unsigned use = (unsigned)(gc / NS);
+            float cur[KC];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+            for (int j = 0; j < KC; ++j) cur[j] = va[j];
+            if (gc + 1 < total_chunks) load_chunk(gc + 1);
+            // f(): normalise + ReLU of the previous layer, applied to the operand on its way into shared memory
+            if (a.in_scale) {
+                const bool row_ok = (blockIdx.x + it * gridDim.x) * TM + m < a.rows;
+                const float4* sc4 = reinterpret_cast<const float4*>(tf + c * KC);
+                const float4* sh4 = reinterpret_cast<const float4*>(tf + a.k_pad + c * KC);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cur[q][j] = va[q][j];
-        if (gc + 1 < total_chunks) load_chunk(gc + 1);
-        // f(): normalise + ReLU of the previous layer, applied to the operand on its way into shared memory
-        if (a.in_scale) {
-            const int64_t row = (blockIdx.x + it * gridDim.x) * TM + m;
+                for (int i = 0; i < KC / 4; ++i) {
+                    const float4 sc = sc4[i], sh = sh4[i];       // padded channels: scale = shift = 0 -> 0
+                    float t0 = fmaf(cur[4 * i], sc.x, sh.x), t1 = fmaf(cur[4 * i + 1], sc.y, sh.y);
+                    float t2 = fmaf(cur[4 * i + 2], sc.z, sh.z), t3 = fmaf(cur[4 * i + 3], sc.w, sh.w);
+                    if (a.in_relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); t2 = fmaxf(t2, 0.0f); t3 = fmaxf(t3, 0.0f); }
+                    cur[4 * i] = row_ok ? t0 : 0.0f; cur[4 * i + 1] = row_ok ? t1 : 0.0f;
+                    cur[4 * i + 2] = row_ok ? t2 : 0.0f; cur[4 * i + 3] = row_ok ? t3 : 0.0f;
+                }
+            }
+            if (gc >= NS) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+            unsigned char* st = a_smem + s * A_STAGE;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int k0 = c * KC + (half + 2 * q) * 8;
+            for (int kb = 0; kb < KC / 8; ++kb) {
+                float v8[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = k0 + j;
-                    float t = 0.0f;
-                    if (k < a.cin && row < a.rows) {
-                        t = fmaf(cur[q][j], __ldg(a.in_scale + k), __ldg(a.in_shift + k));
-                        if (a.in_relu) t = fmaxf(t, 0.0f);
+                for (int j = 0; j < 8; ++j) v8[j] = cur[kb * 8 + j];
+                store_split8(st, st + A_IMG, row_off + (unsigned)kb * 128u, v8);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_full + 8 * s);
+            if (warp == 0) {
+                const int b = (int)(it & 1);
+                mbar_wait(bar_full + 8 * s, use & 1);
+                if (c == 0 && it >= 2) mbar_wait(bar_acce + 8 * b, (unsigned)((it >> 1) - 1) & 1);   // epilogue of tile it-2 has read it
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect()) {
+                    const unsigned acc = tbase + (unsigned)(b * a.n_pad);
+                    const unsigned a_hi = smem_u32(st), a_lo = a_hi + A_IMG;
+                    const unsigned b_hi = smem_u32(w_smem) + (unsigned)c * w_chunk_bytes, b_lo = b_hi + (unsigned)a.n_pad * KC * 2;
+#pragma unroll
+                    for (int t = 0; t < KC / 16; ++t) {
+                        const unsigned long long dah = dbase | (unsigned long long)(((a_hi + t * 256) >> 4) & 0x3FFF);
+                        const unsigned long long dal = dbase | (unsigned long long)(((a_lo + t * 256) >> 4) & 0x3FFF);
+                        const unsigned long long dbh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
+                        const unsigned long long dbl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
+                        const unsigned acc0 = (c > 0 || t > 0) ? 1u : 0u;
+                        asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(acc),
+                                     "l"(dah), "l"(dbh), "r"(idesc), "r"(acc0) : "memory");
+                        asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(acc),
+                                     "l"(dah), "l"(dbl), "r"(idesc), "r"(1u) : "memory");
+                        asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(acc),
+                                     "l"(dal), "l"(dbh), "r"(idesc), "r"(1u) : "memory");
                     }
-                    cur[q][j] = t;
+                    commit(bar_empty + 8 * s);
+                    if (c + 1 == kch) commit(bar_accf + 8 * b);
                 }
+                __syncwarp();
             }
         }
-        if (gc >= NS) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
-        unsigned char* st = a_smem + s * A_STAGE;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) store_split8(st, st + A_IMG, row_off + (unsigned)(half + 2 * q) * 128u, cur[q]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(bar_full + 8 * s);
-        if (warp == 0) {
-            mbar_wait(bar_full + 8 * s, use & 1);
+    } else {
+        // ================= epilogue (warps 4-7): thread = row (TMEM lane), all output channels =================
+        const int q = warp - 4;                                  // a warp reads the TMEM lanes of its quarter
+        const int et = tid - THREADS / 2;                        // 0..127
+        const int nch = a.n_pad / 32;
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int b = (int)(it & 1);
+            mbar_wait(bar_accf + 8 * b, (unsigned)(it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect()) {
-                const unsigned a_hi = smem_u32(st), a_lo = a_hi + A_IMG;
-                const unsigned b_hi = smem_u32(w_smem) + (unsigned)c * w_chunk_bytes, b_lo = b_hi + (unsigned)a.n_pad * KC * 2;
-#pragma unroll
-                for (int t = 0; t < KC / 16; ++t) {
-                    const unsigned long long dah = dbase | (unsigned long long)(((a_hi + t * 256) >> 4) & 0x3FFF);
-                    const unsigned long long dal = dbase | (unsigned long long)(((a_lo + t * 256) >> 4) & 0x3FFF);
-                    const unsigned long long dbh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
-                    const unsigned long long dbl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
-                    const unsigned acc0 = (c > 0 || t > 0) ? 1u : 0u;
-                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(tbase),
-                                 "l"(dah), "l"(dbh), "r"(idesc), "r"(acc0) : "memory");
-                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(tbase),
-                                 "l"(dah), "l"(dbl), "r"(idesc), "r"(1u) : "memory");
-                    asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q; }" ::"r"(tbase),
-                                 "l"(dal), "l"(dbh), "r"(idesc), "r"(1u) : "memory");
+            const int64_t row = (blockIdx.x + it * gridDim.x) * TM + q * 32 + lane;
+            const bool row_ok = row < a.rows;
+            double* pt = part + (size_t)b * 8 * a.n_pad;
+            for (int ch = 0; ch < nch; ++ch) {
+                const int col0 = ch * 32;
+                unsigned r[32];
+                ld32(tbase + ((unsigned)(q * 32) << 16) + (unsigned)(b * a.n_pad + col0), r);
+                if (ch + 1 == nch) {                             // the accumulator has been read: the MMAs of tile it+2 may overwrite it
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(bar_acce + 8 * b);
                 }
-                commit(bar_empty + 8 * s);
-                if (c + 1 == kch) commit(bar_done);
-            }
-            __syncwarp();
-        }
-        if (c + 1 < kch) continue;
-        // ---- epilogue of this row tile: accumulator (lane = row, column = output channel) -> + bias -> y, column sums
-        mbar_wait(bar_done, (unsigned)it & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t row = (blockIdx.x + it * gridDim.x) * TM + (warp & 3) * 32 + lane;
-        const bool row_ok = row < a.rows;
-        const int nch = a.n_pad / 32, h = warp >> 2;
-        const int ch0 = h == 0 ? 0 : (nch + 1) / 2, ch1 = h == 0 ? (nch + 1) / 2 : nch;
-        for (int ch = ch0; ch < ch1; ++ch) {
-            const int col0 = ch * 32;
-            unsigned r[32];
-            ld32(tbase + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)col0, r);
-            float v[32];
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = col0 + j;
-                v[j] = __uint_as_float(r[j]) + ((a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.0f);
-            }
-            if (row_ok) {
-                float* dst = a.y + row * a.ldy + col0;
-                if (col0 + 32 <= a.cout && ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
+                for (int j = 0; j < 32; ++j) {
+                    const int n = col0 + j;
+                    v[j] = __uint_as_float(r[j]) + ((a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.0f);
+                }
+                if (row_ok) {
+                    float* dst = a.y + row * a.ldy + col0;
+                    if (col0 + 32 <= a.cout && ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < a.cout) dst[j] = v[j];
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < a.cout) dst[j] = v[j];
+                    }
+                }
+                if (a.col_sum) {
+                    // column sums over the warp's 32 rows: the butterfly's first three steps (16 + 8 + 4 columns exchanged:
+                    // afterwards a lane holds 4 columns summed over 8 rows) in fp32, the last two and everything beyond in fp64
+                    float f1[32], f2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d = row_ok ? v[j] : 0.0f;
+                        f1[j] = d;
+                        f2[j] = d * d;
+                    }
+                    colsum_step_f<16>(f1, lane);
+                    colsum_step_f<16>(f2, lane);
+                    double d1[32], d2[32];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { d1[j] = (double)f1[j]; d2[j] = (double)f2[j]; }
+                    colsum_step<2>(d1, lane);
+                    colsum_step<2>(d2, lane);
+                    pt[(0 * 4 + q) * a.n_pad + col0 + lane] = d1[0];
+                    pt[(1 * 4 + q) * a.n_pad + col0 + lane] = d2[0];
                 }
             }
             if (a.col_sum) {
-                double d1[32], d2[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const double d = row_ok ? (double)v[j] : 0.0;
-                    d1[j] = d;
-                    d2[j] = d * d;
+                asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps: partial sums of this tile are in place
+                for (int n = et; n < a.cout; n += THREADS / 2) {
+                    atomicAdd(a.col_sum + n, pt[(0 * 4 + 0) * a.n_pad + n] + pt[(0 * 4 + 1) * a.n_pad + n] +
+                                                 pt[(0 * 4 + 2) * a.n_pad + n] + pt[(0 * 4 + 3) * a.n_pad + n]);
+                    atomicAdd(a.col_sumsq + n, pt[(1 * 4 + 0) * a.n_pad + n] + pt[(1 * 4 + 1) * a.n_pad + n] +
+                                                   pt[(1 * 4 + 2) * a.n_pad + n] + pt[(1 * 4 + 3) * a.n_pad + n]);
                 }
-                colsum_step<16>(d1, lane);
-                colsum_step<16>(d2, lane);
-                part[(0 * 4 + (warp & 3)) * a.n_pad + col0 + lane] = d1[0];
-                part[(1 * 4 + (warp & 3)) * a.n_pad + col0 + lane] = d2[0];
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                      // every warp has read the accumulator: the next tile may overwrite it
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (a.col_sum) {
-            for (int n = tid; n < a.cout; n += THREADS) {
-                atomicAdd(a.col_sum + n, part[(0 * 4 + 0) * a.n_pad + n] + part[(0 * 4 + 1) * a.n_pad + n] +
-                                             part[(0 * 4 + 2) * a.n_pad + n] + part[(0 * 4 + 3) * a.n_pad + n]);
-                atomicAdd(a.col_sumsq + n, part[(1 * 4 + 0) * a.n_pad + n] + part[(1 * 4 + 1) * a.n_pad + n] +
-                                               part[(1 * 4 + 2) * a.n_pad + n] + part[(1 * 4 + 3) * a.n_pad + n]);
             }
         }
     }
@@ -343,7 +385,7 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
     a.k_pad = round_up(cin, KC);
     a.n_pad = round_up(cout, 32);
     a.x_vec = ((uintptr_t)x % 16 == 0) && (ldx % 4 == 0);
-    const size_t smem = (size_t)a.k_pad * a.n_pad * 4 + NS * A_STAGE + 8 * (2 * NS + 2) + (size_t)2 * 4 * a.n_pad * sizeof(double) + 64;
+    const size_t smem = (size_t)a.k_pad * a.n_pad * 4 + NS * A_STAGE + 128 + (size_t)2 * 2 * 4 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) + 64;
     static int sms = 0;
     static size_t smem_set = 0;
     if (!sms) {
@@ -362,7 +404,7 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
         smem_set = smem;
     }
     const int64_t tiles = ceil_div(rows, TM);
-    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+    const int per_sm = (smem <= 112 * 1024 && a.n_pad <= 128) ? 2 : 1;      // two CTAs share the SM's 512 TMEM columns (2 x 2 x n_pad)
     const int64_t grid = tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm;
     train_gemm_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(a);
     return finish_launch("pn_train_gemm_bf16x3");

@@ -141,15 +141,7 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
                 const int64_t r = k0 + kb * 8 + j;
                 const bool in = r < r1;
                 va[q][j] = (in && a_ok) ? __ldg(ap + r * lddy) : 0.0f;
-                float t = 0.0f;
-                if (in && b_ok) {
-                    t = __ldg(bp + r * ldx);
-                    if (x_tf) {
-                        t = fmaf(t, xs, xh);
-                        if (x_relu) t = fmaxf(t, 0.0f);
-                    }
-                }
-                vb[q][j] = t;
+                vb[q][j] = (in && b_ok) ? __ldg(bp + r * ldx) : 0.0f;      // (kept branch-free: 32 loads in flight per thread)
             }
         }
     };
@@ -163,6 +155,17 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
 #pragma unroll
             for (int j = 0; j < 8; ++j) { ca[q][j] = va[q][j]; cb[q][j] = vb[q][j]; }
         if (c + 1 < chunks) load_chunk(c + 1);
+        if (x_tf) {      // f(x) on the copy, after the next chunk's loads have been issued
+            const int64_t k0 = r0 + (int64_t)c * KC;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t = fmaf(cb[q][j], xs, xh);
+                    if (x_relu) t = fmaxf(t, 0.0f);
+                    cb[q][j] = (b_ok && k0 + (half + 2 * q) * 8 + j < r1) ? t : 0.0f;
+                }
+        }
         if (c >= NS) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);      // the MMAs that read this stage have completed
         unsigned char* st = smem + s * STAGE;
 #pragma unroll

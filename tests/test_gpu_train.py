@@ -162,8 +162,9 @@ def test_fused_train_gemm(dev, rows, cin, cout, ldx, transposed):
     assert rl2(y.cpu().numpy(), want) < 2e-5
     got = acc.cpu().numpy()
     y64 = y.cpu().numpy().astype(np.float64)
-    assert np.abs(got[0] - y64.sum(0)).max() <= 1e-9 * np.abs(y64).sum(0).max() + 1e-6
-    assert np.abs(got[1] - (y64 ** 2).sum(0)).max() <= 1e-9 * (y64 ** 2).sum(0).max() + 1e-6
+    # sums over 8 rows are formed in fp32 (the first three butterfly steps), everything beyond in fp64
+    assert np.abs(got[0] - y64.sum(0)).max() <= 2e-7 * np.abs(y64).sum(0).max() + 1e-6
+    assert np.abs(got[1] - (y64 ** 2).sum(0)).max() <= 2e-7 * (y64 ** 2).sum(0).max() + 1e-6
     # weight gradient with the same transform applied to its x operand
     dy = rng.standard_normal((rows, 48)).astype(np.float32)
     dw = torch.zeros((48, cin), device=dev)

@@ -11,7 +11,12 @@ if len(sys.argv) > 2:
 agg = collections.OrderedDict()
 for x in recs:
     name = re.sub(r"\(.*", "", x["Kernel Name"])[:64]
-    t = float(x["Metric Value"])
+    try:
+        t = float(x["Metric Value"].replace(",", ""))
+    except ValueError:
+        continue
+    if t != t:
+        continue
     agg.setdefault(name, [0, 0.0])
     agg[name][0] += 1
     agg[name][1] += t
