@@ -734,13 +734,14 @@ def bn_act_max(y: torch.Tensor, st: BatchStats, K: int, relu: bool = True) -> Tu
 
 def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: bool = True,
                     argmax: Optional[torch.Tensor] = None, K: int = 1, dgamma: Optional[torch.Tensor] = None,
-                    dbeta: Optional[torch.Tensor] = None):
+                    dbeta: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None):
     """Backward of act(bn(y)) with batch statistics.  dgamma / dbeta given ([C] float32 buffers): the affine gradients
     are ADDED to them and dy [rows, C] is returned; otherwise -> (dy, dgamma, dbeta) with fresh buffers.
     argmax/K: dz is the pooled gradient [rows/K, C] of bn_act_max."""
     y, dz = _rowmat(y, "y"), _rowmat(dz, "dz")
     rows, Cc = y.shape
-    acc = torch.zeros((2, Cc), dtype=torch.float64, device=y.device)
+    if acc is None:          # float64 [2, C] scratch for the two reductions, ZEROED (a caller may pass a slice of a larger buffer)
+        acc = torch.zeros((2, Cc), dtype=torch.float64, device=y.device)
     dy = torch.empty((rows, Cc), dtype=torch.float32, device=y.device)
     fresh = dgamma is None
     if fresh:

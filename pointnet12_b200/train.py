@@ -71,6 +71,8 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] 
     saved = []
     pending = None
     rows = x.shape[0]
+    widest = max(c.weight.shape[0] for c, _, _ in layers)
+    accs = torch.zeros((len(layers), 2, widest), dtype=torch.float64, device=x.device)     # one fill for the block's statistics
     for li, (conv, bn, relu) in enumerate(layers):
         w = _w2d(conv)
         bias = conv.bias.detach() if conv.bias is not None else None
@@ -80,7 +82,7 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] 
         if bn is not None and not relu:
             raise NotImplementedError("training path: BatchNorm layers are followed by ReLU in every supported block")
         if fused:
-            acc = torch.zeros((2, w.shape[0]), dtype=torch.float64, device=x.device)
+            acc = accs[li, :, :w.shape[0]]
             y = ops.train_gemm(x, w, bias, in_stats=pending, stats_acc=acc)
             st = ops.bn_finalize(acc, rows, bn)
             saved.append((x, pending, y, st, relu, None))
@@ -113,6 +115,8 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] 
 def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optional[int], need_dx: bool):
     """-> (dx or None, [per layer: (dW [Co,Ci], db, dgamma, dbeta)]; None where the gradient went straight into p.grad)."""
     grads = [None] * len(layers)
+    widest = max(c.weight.shape[0] for c, _, _ in layers)
+    accs = torch.zeros((len(layers), 2, widest), dtype=torch.float64, device=dz.device)    # one fill for the block's reductions
     for li in range(len(layers) - 1, -1, -1):
         conv, bn, relu = layers[li]
         x, x_stats, y, st, _, am = saved[li]
@@ -121,7 +125,8 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
         if st is not None:
             dgamma, g_direct = _grad_sink(bn.weight, bn.weight.shape)
             dbeta, _ = _grad_sink(bn.bias, bn.bias.shape)
-            dy = ops.bn_act_backward(y, st, dz, relu, argmax=am, K=pool_K if am is not None else 1, dgamma=dgamma, dbeta=dbeta)
+            dy = ops.bn_act_backward(y, st, dz, relu, argmax=am, K=pool_K if am is not None else 1, dgamma=dgamma, dbeta=dbeta,
+                                     acc=accs[li, :, :y.shape[1]])
         else:
             dy = dz
         w = _w2d(conv)

@@ -141,10 +141,12 @@ def main(argv=None):
     total = torch.tensor([times.sum()], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
-    marks = []
-    step(marks)
-    torch.cuda.synchronize()
-    phases = {n1: round(e0.elapsed_time(e1), 4) for (n0_, e0), (n1, e1) in zip(marks[:-1], marks[1:])}
+    phases = None
+    if args.eager:                       # per-phase split of one more (instrumented) eager iteration
+        marks = []
+        step(marks)
+        torch.cuda.synchronize()
+        phases = {n1: round(e0.elapsed_time(e1), 4) for (n0_, e0), (n1, e1) in zip(marks[:-1], marks[1:])}
     if rank == 0:
         ms = float(total.item()) / args.steps
         print(json.dumps({
