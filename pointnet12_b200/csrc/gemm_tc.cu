@@ -154,9 +154,32 @@ train_gemm_kernel(const Args a) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    const int64_t tiles = (a.rows + TM - 1) / TM;
+    const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // the producers' first chunk is requested BEFORE the weight conversion, which then hides its latency
+    float va[KC];
+    auto load_chunk = [&](int64_t gc) {
+        const int64_t it = gc / kch;
+        const int c = (int)(gc - it * kch);
+        const int64_t row = (blockIdx.x + it * gridDim.x) * TM + (tid & 127);
+        const bool row_ok = row < a.rows;
+        const float* __restrict__ xr = a.x + row * a.ldx + c * KC;
+        if (a.x_vec && (c + 1) * KC <= a.cin) {
+#pragma unroll
+            for (int i = 0; i < KC / 4; ++i) {
+                const float4 t = row_ok ? __ldg(reinterpret_cast<const float4*>(xr) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                va[4 * i] = t.x; va[4 * i + 1] = t.y; va[4 * i + 2] = t.z; va[4 * i + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KC; ++j) va[j] = (row_ok && c * KC + j < a.cin) ? __ldg(xr + j) : 0.0f;
+        }
+    };
+    if (warp < 4 && my_tiles > 0) load_chunk(0);
     // ---- weights: fp32 -> bf16 hi/lo, K-major core matrices, once per CTA
     {
         const int kblocks = a.k_pad / 8;
+#pragma unroll 2
         for (int e = tid; e < a.n_pad * kblocks; e += THREADS) {
             const int n = e % a.n_pad, kb = e / a.n_pad;        // consecutive threads = consecutive n
             float v[8];
@@ -186,9 +209,6 @@ train_gemm_kernel(const Args a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tbase = *tmem_slot;
 
-    const int64_t tiles = (a.rows + TM - 1) / TM;
-    const int64_t my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
     if (warp < 4) {
         // ================= producers (warps 0-3): thread = row of the tile; warp 0 also issues the MMAs =================
         const int64_t total_chunks = my_tiles * kch;
@@ -197,25 +217,6 @@ train_gemm_kernel(const Args a) {
         const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(a.n_pad >> 3) << 17) | ((unsigned)(TM >> 4) << 24);
         const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
                                          ((unsigned long long)((((unsigned)KC / 8) * 128u >> 4) & 0x3FFF) << 32) | (1ull << 46);
-        float va[KC];
-        auto load_chunk = [&](int64_t gc) {
-            const int64_t it = gc / kch;
-            const int c = (int)(gc - it * kch);
-            const int64_t row = (blockIdx.x + it * gridDim.x) * TM + m;
-            const bool row_ok = row < a.rows;
-            const float* __restrict__ xr = a.x + row * a.ldx + c * KC;
-            if (a.x_vec && (c + 1) * KC <= a.cin) {
-#pragma unroll
-                for (int i = 0; i < KC / 4; ++i) {
-                    const float4 t = row_ok ? __ldg(reinterpret_cast<const float4*>(xr) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    va[4 * i] = t.x; va[4 * i + 1] = t.y; va[4 * i + 2] = t.z; va[4 * i + 3] = t.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < KC; ++j) va[j] = (row_ok && c * KC + j < a.cin) ? __ldg(xr + j) : 0.0f;
-            }
-        };
-        if (total_chunks > 0) load_chunk(0);
         for (int64_t gc = 0; gc < total_chunks; ++gc) {
             const int64_t it = gc / kch;
             const int c = (int)(gc - it * kch);
