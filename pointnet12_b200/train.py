@@ -306,8 +306,26 @@ def dropout_seed(device) -> torch.Tensor:
     return torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, _SEED["next"]], dtype=torch.int64).to(device, non_blocking=True)
 
 
+def semseg_geometry(net, points: torch.Tensor, fps_starts):
+    """Everything of a PointNet2SemSeg forward that depends on the coordinates only (no gradient): sampling + ball query of
+    the four set-abstraction levels and the four 3-NN searches, on the current stream.
+    -> ([(new_xyz [B,S,3], group_idx [B,S,K])] * 4, [(nn_idx [B,N,3], weight [B,N,3])] * 4 indexed like fp1..fp4)."""
+    sa = [net.sa1, net.sa2, net.sa3, net.sa4]
+    fp = [net.fp1, net.fp2, net.fp3, net.fp4]
+    with torch.no_grad():
+        xs_pm = [points[:, :3, :].detach().permute(0, 2, 1)]
+        sa_geo, fp_geo = [], [None] * 4
+        for i, m in enumerate(sa):
+            new_xyz, idx = m.geometry(xs_pm[i], fps_starts[i])
+            xs_pm.append(new_xyz)
+            sa_geo.append((new_xyz, idx))
+        for i in (3, 2, 1, 0):
+            fp_geo[i] = fp[i].geometry(xs_pm[i], xs_pm[i + 1])
+    return sa_geo, fp_geo
+
+
 def semseg_forward_train(net, points: torch.Tensor, fps_starts=None, dropout_mask: Optional[torch.Tensor] = None,
-                         seed_offset: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         seed_offset: Optional[torch.Tensor] = None, geometry=None) -> torch.Tensor:
     """PointNet2SemSeg.forward (pointnet2.py:159-176) in train() mode -> log-probabilities [B, N, classes] with grad_fn.
     dropout_mask (extension): uint8 [B*N, 128] keep-mask to use instead of drawing one (parity tests)."""
     ops._need_cuda(points, "points")
@@ -316,6 +334,22 @@ def semseg_forward_train(net, points: torch.Tensor, fps_starts=None, dropout_mas
     sa = [net.sa1, net.sa2, net.sa3, net.sa4]
     fp = [net.fp1, net.fp2, net.fp3, net.fp4]                     # fp[i] upsamples level i+1 -> level i
     B, _, N = points.shape
+    if geometry is not None:
+        # (extension) the caller computed semseg_geometry() for this batch already -- e.g. GraphedTrainStep prefetches it
+        # during the previous iteration -- so the feature path starts at once
+        sa_geo, fp_geo = geometry
+        xs, fs = [xyz], [feats]
+        for i, m in enumerate(sa):
+            nx, nf = set_abstraction_train(m, xs[-1], fs[-1], geometry=sa_geo[i])
+            xs.append(nx)
+            fs.append(nf)
+        up = fs[4]
+        for i in (3, 2, 1, 0):
+            up = feature_propagation_train(fp[i], xs[i], xs[i + 1], fs[i] if i > 0 else None, up, geometry=fp_geo[i])
+        if dropout_mask is None and seed_offset is None and net.drop1.p > 0:
+            seed_offset = dropout_seed(points.device)
+        params = [net.conv1.weight, net.conv1.bias, net.bn1.weight, net.bn1.bias, net.conv2.weight, net.conv2.bias]
+        return SegHeadFn.apply(net, up.permute(0, 2, 1), dropout_mask, seed_offset, *params)
     if fps_starts is None:
         from .model.pointnet_util import draw_fps_starts
 
@@ -493,15 +527,22 @@ class GraphedTrainStep:
     """One training iteration of PointNet2SemSeg as ONE CUDA-graph replay + the gradient exchange + the Adam launch.
 
     An eager iteration is ~240 kernel launches plus the autograd engine and is bound by the host (7.7 ms at config C5 for
-    ~3 ms of GPU work); captured once per input shape, forward + loss + backward replay as a single graph launch.
+    ~3.5 ms of GPU work); captured once per input shape, forward + loss + backward replay as a single graph launch.
 
         step = GraphedTrainStep(net, FlatAdam(net.parameters(), lr=1e-3, weight_decay=1e-4))
-        loss = step(points, target)         # points [B, 4, N], target [B, N]; returns the (device) loss of this iteration
+        loss = step(points, target)                            # points [B, 4, N], target [B, N] -> the (device) loss
+        loss = step(points, target, next_points=upcoming)      # ... and prefetch the NEXT batch's geometry meanwhile
 
     Per call the FPS start indices are drawn on the CPU generator exactly like the reference draws them
     (pointnet_util.py:75) and reach the graph, together with the dropout stream's {seed, offset}, through one small
     pinned staging buffer; the gradient all-reduce (when torch.distributed is initialised) and Adam run right behind
-    the replay on the same stream.  Warm-up iterations needed for the capture are rolled back."""
+    the replay on the same stream.  Warm-up iterations needed for the capture are rolled back.
+
+    next_points: sampling / ball query / 3-NN depend on the coordinates only, and level-1 sampling is 0.4 ms of serial
+    latency at the head of every iteration.  Given the upcoming batch, the replay computes ITS geometry on a side stream
+    while the current batch's feature path runs (two static geometry sets, two graphs that alternate); the next call, if
+    it gets exactly that batch, starts its feature path at once.  A call whose batch was not prefetched computes the
+    geometry first (eagerly); results are the same either way."""
 
     RING = 8
 
@@ -513,52 +554,69 @@ class GraphedTrainStep:
         self._bn_buffers = [b for m in self.net.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)
                             for b in (m.running_mean, m.running_var, m.num_batches_tracked) if b is not None]
 
-    def _forward_backward(self, st):
-        logp = semseg_forward_train(self.net, st["x"], fps_starts=list(st["ctl"][:-2].view(4, -1).unbind(0)),
-                                    seed_offset=st["ctl"][-2:])
+    @staticmethod
+    def _starts(st, p):
+        return list(st["ctl"][p][:-2].view(4, -1).unbind(0))
+
+    def _forward_backward(self, st, p):
+        logp = semseg_forward_train(self.net, st["x"][p], seed_offset=st["ctl"][p][-2:], geometry=st["geo"][p])
         loss = cross_entropy(logp, st["target"])
         self.opt.zero_grad()
         loss.backward()
         return loss
 
+    def _geometry_into(self, st, p):
+        """semseg_geometry of the batch in slot p -> the static geometry set p (on the current stream)."""
+        sa_geo, fp_geo = semseg_geometry(self.net, st["x"][p], self._starts(st, p))
+        if st["geo"][p] is None:
+            st["geo"][p] = ([tuple(t.clone() for t in pair) for pair in sa_geo], [tuple(t.clone() for t in pair) for pair in fp_geo])
+            return
+        for dst, src in zip(st["geo"][p][0] + st["geo"][p][1], sa_geo + fp_geo):
+            for d, t in zip(dst, src):
+                d.copy_(t)
+
     def _build(self, points, target):
+        from . import _native as nv
+
         dev = points.device
         B, C, N = points.shape
         net = self.net
         sizes = [N] + [m.npoint for m in (net.sa1, net.sa2, net.sa3)]
-        st = {"x": points.clone(), "target": target.clone().long().view(B, N), "sizes": sizes,
-              "ctl": torch.zeros((4 * B + 2,), dtype=torch.int64, device=dev),
-              "pinned": [torch.zeros((4 * B + 2,), dtype=torch.int64).pin_memory() for _ in range(self.RING)],
-              "events": [None] * self.RING, "slot": 0}
+        st = {"x": [points.clone(), points.clone()], "target": target.clone().long().view(B, N), "sizes": sizes,
+              "ctl": [torch.zeros((4 * B + 2,), dtype=torch.int64, device=dev) for _ in range(2)],
+              "geo": [None, None], "pinned": [torch.zeros((4 * B + 2,), dtype=torch.int64).pin_memory() for _ in range(self.RING)],
+              "events": [None] * self.RING, "slot": 0, "cur": 0, "prefetched": None, "graphs": [None, None], "loss": [None, None]}
         keep = [t.clone() for t in (self.opt.flat, *self._bn_buffers)]           # warm-up must not train
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            self._geometry_into(st, 0)
+            self._geometry_into(st, 1)
             for _ in range(self.warmup):
-                self._forward_backward(st)
+                self._forward_backward(st, 0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         with torch.no_grad():
             for t, k in zip((self.opt.flat, *self._bn_buffers), keep):
                 t.copy_(k)
-        from . import _native as nv
-
-        graph = torch.cuda.CUDAGraph()
-        n0 = nv.launch_count
-        with torch.cuda.graph(graph):
-            st["loss"] = self._forward_backward(st)
-        st["launches"] = nv.launch_count - n0          # entry-point calls captured in the graph (bench accounting)
-        st["graph"] = graph
+        geo_stream = _geometry_stream(dev)
+        for p in (0, 1):
+            graph = torch.cuda.CUDAGraph()
+            n0 = nv.launch_count
+            with torch.cuda.graph(graph):
+                cap = torch.cuda.current_stream(dev)
+                geo_stream.wait_stream(cap)
+                with torch.cuda.stream(geo_stream):              # the other slot's geometry, beside this slot's feature path
+                    self._geometry_into(st, 1 - p)
+                st["loss"][p] = self._forward_backward(st, p)
+                cap.wait_stream(geo_stream)
+            st["launches"] = nv.launch_count - n0                 # entry-point calls captured in a graph (bench accounting)
+            st["graphs"][p] = graph
         return st
 
-    def __call__(self, points: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        if not self.net.training:
-            raise RuntimeError("GraphedTrainStep: call net.train() first")
-        key = (tuple(points.shape), points.device)
-        st = self._graphs.get(key)
-        if st is None:
-            st = self._graphs[key] = self._build(points, target)
-        B = points.shape[0]
+    def _stage(self, st, p, B):
+        """Draws the FPS starts of the batch in slot p like the reference draws them and sends them, with the dropout
+        stream's {seed, offset}, to the slot's control buffer."""
         slot = st["slot"] = (st["slot"] + 1) % self.RING
         if st["events"][slot] is not None:
             st["events"][slot].synchronize()
@@ -568,18 +626,39 @@ class GraphedTrainStep:
         self._calls += 1
         pinned[-2] = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
         pinned[-1] = self._calls
-        st["ctl"].copy_(pinned, non_blocking=True)
+        st["ctl"][p].copy_(pinned, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         st["events"][slot] = ev
-        if points.data_ptr() != st["x"].data_ptr():
-            st["x"].copy_(points, non_blocking=True)
-        if target.data_ptr() != st["target"].data_ptr():
-            st["target"].copy_(target.view(st["target"].shape), non_blocking=True)
-        st["graph"].replay()
+
+    def __call__(self, points: torch.Tensor, target: torch.Tensor, next_points: Optional[torch.Tensor] = None) -> torch.Tensor:
         from . import _native as nv
 
+        if not self.net.training:
+            raise RuntimeError("GraphedTrainStep: call net.train() first")
+        key = (tuple(points.shape), points.device)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = self._build(points, target)
+        B = points.shape[0]
+        tag = (points.data_ptr(), points._version)
+        if st["prefetched"] == tag:
+            p = st["cur"] = 1 - st["cur"]                       # this batch's geometry was computed during the last replay
+        else:
+            p = st["cur"]
+            st["x"][p].copy_(points, non_blocking=True)
+            self._stage(st, p, B)
+            self._geometry_into(st, p)
+        if next_points is not None:
+            st["x"][1 - p].copy_(next_points, non_blocking=True)
+            self._stage(st, 1 - p, B)
+            st["prefetched"] = (next_points.data_ptr(), next_points._version)
+        else:
+            st["prefetched"] = None       # (the replay then recomputes the other slot's old geometry: harmless, no draws consumed)
+        if target.data_ptr() != st["target"].data_ptr():
+            st["target"].copy_(target.view(st["target"].shape), non_blocking=True)
+        st["graphs"][p].replay()
         nv.launch_count += st["launches"]
         torch.autograd.graph.increment_version(self._bn_buffers)
         self.opt.step(self.opt.all_reduce(self.group))
-        return st["loss"]
+        return st["loss"][p]

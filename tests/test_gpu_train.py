@@ -469,6 +469,28 @@ def test_graphed_train_step_matches_eager(dev):
     torch.manual_seed(10)
     for _ in range(4):
         lb.append(runner(pts, target).item())
+    # the same again with the next batch's geometry prefetched during every replay (two batches alternating)
+    c = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    c.load_state_dict(a.state_dict())
+    a2 = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    a2.load_state_dict(a.state_dict())
+    a2.drop1.p = c.drop1.p = 0.0
+    opt_a2, opt_c = FlatAdam(a2.parameters(), lr=1e-3, weight_decay=1e-4), FlatAdam(c.parameters(), lr=1e-3, weight_decay=1e-4)
+    pts2 = T(syn.kitti_batch(2, 4096, config=5, first=2), dev)
+    batches = [pts, pts2, pts, pts2, pts]
+    le, lp = [], []
+    torch.manual_seed(11)
+    for i in range(4):
+        loss = cross_entropy(a2(batches[i]), target)
+        opt_a2.zero_grad()
+        loss.backward()
+        opt_a2.step()
+        le.append(loss.item())
+    torch.manual_seed(11)
+    pre = GraphedTrainStep(c, opt_c)
+    for i in range(4):
+        lp.append(pre(batches[i], target, next_points=batches[i + 1]).item())
+    assert abs(le[0] - lp[0]) < 1e-5 and max(abs(x - y) / x for x, y in zip(le, lp)) < 2e-2, (le, lp)
     assert abs(la[0] - lb[0]) < 1e-5, (la, lb)                # identical weights, identical draws
     assert max(abs(x - y) / x for x, y in zip(la, lb)) < 2e-2, (la, lb)     # later: fp32 atomics order through Adam
     assert opt_a.steps == opt_b.steps == 4
