@@ -326,6 +326,9 @@ int pn_grad_weight_f32(const float* dy, int64_t lddy, const float* x, int64_t ld
  * bf16 hi + lo on the fly straight into the UMMA K-major layout, and adds its tile to dw with fp32 atomics. */
 int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin,
                           float* dw, int64_t lddw, float* db, pn_stream_t stream);
+/* Tuning hook: row slabs (CTAs) per SM of the tensor-core weight gradient, 1 (default: every extra slab adds a tile of
+ * atomics on the same addresses) or 2 (more loads in flight).  Process-wide. */
+int pn_grad_weight_set_ctas_per_sm(int ctas);
 /* The same with f(x) = act(x*x_scale[ci] + x_shift[ci]) applied to the x operand while it is loaded: the normalise + ReLU
  * of the layer that produced x, for a forward that kept only that layer's pre-normalisation output (pn_train_gemm_bf16x3). */
 int pn_grad_weight_bn_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* x_scale,
@@ -339,9 +342,12 @@ int pn_grad_weight_bn_bf16x3(const float* dy, int64_t lddy, const float* x, int6
  * bf16 with fp32 accumulation (fp32 parity).  Weights stay resident in shared memory: pn_train_gemm_supported(cin, cout)
  * tells whether the layer fits (cout <= 256, padded cin*cout*4 <= 128 KB); wider layers use pn_mlp_rows_bf16x3. */
 int pn_train_gemm_supported(int cin, int cout);
+/* w_scratch: caller-owned device buffer of pn_train_gemm_scratch_bytes(cin, cout) bytes, 128-byte aligned: the call first
+ * converts the weights into it (bf16 hi + lo in the kernel's shared-memory layout), then every CTA fetches that image. */
+size_t pn_train_gemm_scratch_bytes(int cin, int cout);
 int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale, const float* in_shift,
                          int in_relu, const float* w, int w_transposed, const float* bias, int cout, float* y, int64_t ldy,
-                         double* col_sum, double* col_sumsq, pn_stream_t stream);
+                         double* col_sum, double* col_sumsq, void* w_scratch, pn_stream_t stream);
 /* out [cols, rows] = in [rows, cols]^T (the weight of the input-gradient GEMM dx = dy W = pn_linear_f32(dy, W^T)). */
 int pn_transpose_f32(const float* in, int rows, int cols, float* out, pn_stream_t stream);
 /* Backward of the gather of sample_and_group (model/pointnet_util.py:128-131): dfeat[b, idx[b,s,k], :] +=

@@ -78,9 +78,10 @@ _SIGNATURES = {
     "pn_bn_bwd_apply_f32": [vp, i64, i64, i32, vp, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, vp],
     "pn_grad_weight_f32": [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp, vp],
     "pn_grad_weight_bf16x3": [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp, vp],
+    "pn_grad_weight_set_ctas_per_sm": [i32],
     "pn_grad_weight_bn_bf16x3": [vp, i64, vp, i64, vp, vp, i32, i64, i32, i32, vp, i64, vp, vp],
     "pn_train_gemm_supported": [i32, i32],
-    "pn_train_gemm_bf16x3": [vp, i64, i64, i32, vp, vp, i32, vp, i32, vp, i32, vp, i64, vp, vp, vp],
+    "pn_train_gemm_bf16x3": [vp, i64, i64, i32, vp, vp, i32, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp],
     "pn_transpose_f32": [vp, i32, i32, vp, vp],
     "pn_group_bwd_f32": [vp, i64, i32, i32, vp, i32, i32, i32, i32, vp, vp],
     "pn_three_interpolate_bwd_f32": [vp, i64, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp],
@@ -125,6 +126,8 @@ def lib():
         handle.pn_ball_grid_bytes.restype = C.c_size_t
         handle.pn_three_nn_blocks_bytes.argtypes = [i32, i32]
         handle.pn_three_nn_blocks_bytes.restype = C.c_size_t
+        handle.pn_train_gemm_scratch_bytes.argtypes = [i32, i32]
+        handle.pn_train_gemm_scratch_bytes.restype = C.c_size_t
         handle.pn_scan_workspace_bytes.argtypes = [i32, i64]
         handle.pn_scan_workspace_bytes.restype = C.c_size_t
         _lib = handle

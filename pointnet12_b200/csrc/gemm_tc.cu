@@ -12,8 +12,9 @@
 // read and one write (8 bytes per element) and the activated tensor z never exists; the backward recomputes what it needs
 // from y (pn_grad_weight_bf16x3 applies the same f to its x operand).
 //
-// Structure: persistent CTAs (up to two per SM).  The weights (<= 128 KB as bf16 hi + lo) are converted once per CTA into
-// shared memory in the UMMA K-major layout and stay resident; the x operand streams through a 2-stage ring of 128-row x
+// Structure: persistent CTAs (up to two per SM).  The weights (<= 128 KB as bf16 hi + lo) are converted once per call by a
+// small pre-pass into the UMMA K-major layout, fetched by every CTA with bulk copies (cp.async.bulk + mbarrier) and stay
+// resident in shared memory; the x operand streams through a 2-stage ring of 128-row x
 // 32-column chunks that the four PRODUCER warps fill (thread = row: fp32 -> f() -> bf16 hi/lo, 16-byte stores straight into
 // the K-major layout, register double buffer across chunks and tiles); an elected lane of warp 0 issues hi*hi + hi*lo +
 // lo*hi per 16 columns (tcgen05.mma kind::f16, both operands from shared memory) into one of TWO fp32 accumulators of
@@ -21,6 +22,7 @@
 // reduce the column sums with a shuffle butterfly in fp64 -- while the producers and the tensor core work on the next tile.
 // W can be given transposed (w[k, n]): the input-gradient GEMM dx = dy W of the backward pass reads W that way.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -31,6 +33,7 @@ constexpr int TM = 128, KC = 32, NS = 2, THREADS = 256;   // 2 stages + the regi
 constexpr int A_IMG = TM * KC * 2;            // one bf16 image of a 128 x 32 chunk: 8 KB
 constexpr int A_STAGE = 2 * A_IMG;            // hi + lo
 constexpr int W_MAX_BYTES = 128 * 1024;       // resident weights (hi + lo)
+constexpr int PF = 6;                         // L2 prefetch distance of the operand stream, in 32-column chunks
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -118,8 +121,35 @@ struct Args {
     const float* w; int w_transposed; const float* bias; int cout;
     float* y; int64_t ldy;
     double* col_sum; double* col_sumsq;
-    int k_pad, n_pad, x_vec;
+    int k_pad, n_pad, x_vec, debug;
+    const unsigned char* w_packed;   // bf16 hi/lo image of the weights in the kernel's shared-memory layout (train_pack_kernel)
 };
+
+// Weights fp32 -> bf16 hi/lo in the layout the GEMM keeps in shared memory: per 32-wide K chunk the hi image
+// [n_pad x 32] then the lo image, K-major core matrices.  Done ONCE per GEMM into a scratch buffer; every CTA of the GEMM
+// then fetches the image with bulk copies.  (Converting inside the GEMM cost ~18 us per CTA for a 128 x 128 layer: 296 CTAs
+// gathering the same 64 KB with scattered 4-byte loads.)
+__global__ void train_pack_kernel(const float* __restrict__ w, int w_transposed, int cin, int cout, int k_pad, int n_pad,
+                                  unsigned char* __restrict__ out) {
+    const int kblocks = k_pad / 8;
+    const unsigned w_chunk_bytes = (unsigned)n_pad * KC * 4;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_pad * kblocks; e += gridDim.x * blockDim.x) {
+        // consecutive threads read consecutive memory: along k for a row-major [cout, cin] weight, along n for its transpose
+        const int n = w_transposed ? e % n_pad : e / kblocks, kb = w_transposed ? e / n_pad : e % kblocks;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kb * 8 + j;
+            float t = 0.0f;
+            if (n < cout && k < cin) t = w_transposed ? __ldg(w + (int64_t)k * cout + n) : __ldg(w + (int64_t)n * cin + k);
+            v[j] = t;
+        }
+        const int c = kb / (KC / 8), kbi = kb % (KC / 8);
+        unsigned char* img = out + (size_t)c * w_chunk_bytes;
+        const unsigned off = (unsigned)(n >> 3) * (KC / 8) * 128u + (unsigned)kbi * 128u + (unsigned)(n & 7) * 16u;
+        store_split8(img, img + (size_t)n_pad * KC * 2, off, v);
+    }
+}
 
 __global__ void __launch_bounds__(THREADS)
 train_gemm_kernel(const Args a) {
@@ -130,12 +160,12 @@ train_gemm_kernel(const Args a) {
     unsigned char* a_smem = smem + (size_t)kch * w_chunk_bytes; // ring of NS stages
     // barriers: full[NS] (128 producer arrivals), empty[NS] (MMA commit), acc_full[2] (MMA commit), acc_empty[2] (128 epilogue arrivals)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(a_smem + NS * A_STAGE);
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 4);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 5);
     float* tf = reinterpret_cast<float*>(bars + 16);                                           // [2][k_pad]: in_scale | in_shift (16-byte aligned)
-    double* part = reinterpret_cast<double*>(tf + 2 * a.k_pad);                                // [2 tiles][2][4][n_pad] partial sums
+    double* cta_sum = reinterpret_cast<double*>(tf + 2 * a.k_pad);                             // [2][n_pad]: this CTA's column sums over all its tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_accf = smem_u32(bars + 2 * NS),
-                   bar_acce = smem_u32(bars + 2 * NS + 2);
+                   bar_acce = smem_u32(bars + 2 * NS + 2), bar_w = smem_u32(bars + 2 * NS + 4);
 
     unsigned tmem_cols = 32;
     while ((int)tmem_cols < 2 * a.n_pad) tmem_cols <<= 1;       // two accumulators: the MMAs of tile i+1 overlap the epilogue of tile i
@@ -148,7 +178,18 @@ train_gemm_kernel(const Args a) {
             mbar_init(bar_accf + 8 * b, 1);
             mbar_init(bar_acce + 8 * b, THREADS / 2);
         }
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the packed weights: bulk copies straight into their resident place, completion counted in bytes on bar_w
+        const unsigned wbytes = (unsigned)kch * w_chunk_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(wbytes) : "memory");
+        for (unsigned off = 0; off < wbytes; off += 32768u) {
+            const unsigned n = wbytes - off < 32768u ? wbytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(w_smem) + off),
+                         "l"(a.w_packed + off), "r"(n), "r"(bar_w)
+                         : "memory");
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
@@ -175,27 +216,17 @@ train_gemm_kernel(const Args a) {
             for (int j = 0; j < KC; ++j) va[j] = (row_ok && c * KC + j < a.cin) ? __ldg(xr + j) : 0.0f;
         }
     };
-    if (warp < 4 && my_tiles > 0) load_chunk(0);
-    // ---- weights: fp32 -> bf16 hi/lo, K-major core matrices, once per CTA
-    {
-        const int kblocks = a.k_pad / 8;
-#pragma unroll 2
-        for (int e = tid; e < a.n_pad * kblocks; e += THREADS) {
-            const int n = e % a.n_pad, kb = e / a.n_pad;        // consecutive threads = consecutive n
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = kb * 8 + j;
-                float t = 0.0f;
-                if (n < a.cout && k < a.cin) t = a.w_transposed ? __ldg(a.w + (int64_t)k * a.cout + n) : __ldg(a.w + (int64_t)n * a.cin + k);
-                v[j] = t;
-            }
-            const int c = kb / (KC / 8), kbi = kb % (KC / 8);
-            unsigned char* img = w_smem + (size_t)c * w_chunk_bytes;
-            const unsigned off = (unsigned)(n >> 3) * (KC / 8) * 128u + (unsigned)kbi * 128u + (unsigned)(n & 7) * 16u;
-            store_split8(img, img + (size_t)a.n_pad * KC * 2, off, v);
+    if (warp < 4 && my_tiles > 0) {
+        load_chunk(0);
+        for (int g2 = 1; g2 < PF && g2 < my_tiles * kch; ++g2) {
+            const int64_t it2 = g2 / kch;
+            const int c2 = (int)(g2 - it2 * kch);
+            const int64_t row2 = (blockIdx.x + it2 * gridDim.x) * TM + (tid & 127);
+            if (row2 < a.rows && c2 * KC < a.cin) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + row2 * a.ldx + c2 * KC));
         }
     }
+    if (a.col_sum)
+        for (int n = tid; n < 2 * a.n_pad; n += THREADS) cta_sum[n] = 0.0;
     if (a.in_scale) {
         // the operand transform's per-channel constants: read through shared memory (a warp's lanes all want the same k)
         for (int k = tid; k < a.k_pad; k += THREADS) {
@@ -226,6 +257,16 @@ train_gemm_kernel(const Args a) {
 #pragma unroll
             for (int j = 0; j < KC; ++j) cur[j] = va[j];
             if (gc + 1 < total_chunks) load_chunk(gc + 1);
+            // The register buffer keeps only ONE chunk (16 KB per CTA) in flight, far too little to cover the HBM latency:
+            // the line this thread will load PF chunks from now (its row's 128 bytes of that chunk) is requested into L2
+            // ahead of time -- a prefetch holds no register.
+            if (gc + PF < total_chunks) {
+                const int64_t g2 = gc + PF, it2 = g2 / kch;
+                const int c2 = (int)(g2 - it2 * kch);
+                const int64_t row2 = (blockIdx.x + it2 * gridDim.x) * TM + m;
+                if (row2 < a.rows && c2 * KC < a.cin)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + row2 * a.ldx + c2 * KC));
+            }
             // f(): normalise + ReLU of the previous layer, applied to the operand on its way into shared memory
             if (a.in_scale) {
                 const bool row_ok = (blockIdx.x + it * gridDim.x) * TM + m < a.rows;
@@ -244,7 +285,7 @@ train_gemm_kernel(const Args a) {
             if (gc >= NS) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
             unsigned char* st = a_smem + s * A_STAGE;
 #pragma unroll
-            for (int kb = 0; kb < KC / 8; ++kb) {
+            for (int kb = 0; kb < ((a.debug & 4) ? 0 : KC / 8); ++kb) {
                 float v8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v8[j] = cur[kb * 8 + j];
@@ -255,6 +296,7 @@ train_gemm_kernel(const Args a) {
             if (warp == 0) {
                 const int b = (int)(it & 1);
                 mbar_wait(bar_full + 8 * s, use & 1);
+                if (gc == 0) mbar_wait(bar_w, 0);                      // the weight image has landed
                 if (c == 0 && it >= 2) mbar_wait(bar_acce + 8 * b, (unsigned)((it >> 1) - 1) & 1);   // epilogue of tile it-2 has read it
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect()) {
@@ -262,7 +304,7 @@ train_gemm_kernel(const Args a) {
                     const unsigned a_hi = smem_u32(st), a_lo = a_hi + A_IMG;
                     const unsigned b_hi = smem_u32(w_smem) + (unsigned)c * w_chunk_bytes, b_lo = b_hi + (unsigned)a.n_pad * KC * 2;
 #pragma unroll
-                    for (int t = 0; t < KC / 16; ++t) {
+                    for (int t = 0; t < ((a.debug & 1) ? 0 : KC / 16); ++t) {
                         const unsigned long long dah = dbase | (unsigned long long)(((a_hi + t * 256) >> 4) & 0x3FFF);
                         const unsigned long long dal = dbase | (unsigned long long)(((a_lo + t * 256) >> 4) & 0x3FFF);
                         const unsigned long long dbh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
@@ -292,11 +334,10 @@ train_gemm_kernel(const Args a) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = (blockIdx.x + it * gridDim.x) * TM + q * 32 + lane;
             const bool row_ok = row < a.rows;
-            double* pt = part + (size_t)b * 8 * a.n_pad;
             for (int ch = 0; ch < nch; ++ch) {
                 const int col0 = ch * 32;
                 unsigned r[32];
-                ld32(tbase + ((unsigned)(q * 32) << 16) + (unsigned)(b * a.n_pad + col0), r);
+                if (!(a.debug & 16)) ld32(tbase + ((unsigned)(q * 32) << 16) + (unsigned)(b * a.n_pad + col0), r);
                 if (ch + 1 == nch) {                             // the accumulator has been read: the MMAs of tile it+2 may overwrite it
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(bar_acce + 8 * b);
@@ -307,6 +348,7 @@ train_gemm_kernel(const Args a) {
                     const int n = col0 + j;
                     v[j] = __uint_as_float(r[j]) + ((a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.0f);
                 }
+                if ((a.debug & 2) && v[0] != 12345.678f) continue;
                 if (row_ok) {
                     float* dst = a.y + row * a.ldy + col0;
                     if (col0 + 32 <= a.cout && ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
@@ -335,23 +377,22 @@ train_gemm_kernel(const Args a) {
                     for (int j = 0; j < 4; ++j) { d1[j] = (double)f1[j]; d2[j] = (double)f2[j]; }
                     colsum_step<2>(d1, lane);
                     colsum_step<2>(d2, lane);
-                    pt[(0 * 4 + q) * a.n_pad + col0 + lane] = d1[0];
-                    pt[(1 * 4 + q) * a.n_pad + col0 + lane] = d2[0];
-                }
-            }
-            if (a.col_sum) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps: partial sums of this tile are in place
-                for (int n = et; n < a.cout; n += THREADS / 2) {
-                    atomicAdd(a.col_sum + n, pt[(0 * 4 + 0) * a.n_pad + n] + pt[(0 * 4 + 1) * a.n_pad + n] +
-                                                 pt[(0 * 4 + 2) * a.n_pad + n] + pt[(0 * 4 + 3) * a.n_pad + n]);
-                    atomicAdd(a.col_sumsq + n, pt[(1 * 4 + 0) * a.n_pad + n] + pt[(1 * 4 + 1) * a.n_pad + n] +
-                                                   pt[(1 * 4 + 2) * a.n_pad + n] + pt[(1 * 4 + 3) * a.n_pad + n]);
+                    // per-CTA accumulation in shared memory (four warps meet per column); one global atomic per column
+                    // and CTA at the very end instead of one per tile
+                    atomicAdd(&cta_sum[col0 + lane], d1[0]);
+                    atomicAdd(&cta_sum[a.n_pad + col0 + lane], d2[0]);
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (a.col_sum) {
+        for (int n = tid; n < a.cout; n += THREADS) {
+            atomicAdd(a.col_sum + n, cta_sum[n]);
+            atomicAdd(a.col_sumsq + n, cta_sum[a.n_pad + n]);
+        }
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(tmem_cols));
 }
 
@@ -367,12 +408,20 @@ PN_EXPORT int pn_train_gemm_supported(int cin, int cout) {
     return n_pad <= 256 && (size_t)k_pad * n_pad * 4 <= (size_t)W_MAX_BYTES;
 }
 
+PN_EXPORT size_t pn_train_gemm_scratch_bytes(int cin, int cout) {
+    using namespace pn::gemm;
+    if (!pn_train_gemm_supported(cin, cout)) return 0;
+    return (size_t)round_up(cin, KC) * round_up(cout, 32) * 4;
+}
+
 PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale,
                                    const float* in_shift, int in_relu, const float* w, int w_transposed, const float* bias,
-                                   int cout, float* y, int64_t ldy, double* col_sum, double* col_sumsq, pn_stream_t stream) {
+                                   int cout, float* y, int64_t ldy, double* col_sum, double* col_sumsq, void* w_scratch,
+                                   pn_stream_t stream) {
     using namespace pn;
     using namespace pn::gemm;
-    PN_REQUIRE(x && w && y, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: null pointer");
+    PN_REQUIRE(x && w && y && w_scratch, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: null pointer");
+    PN_REQUIRE(((uintptr_t)w_scratch & 127) == 0, PN_ERR_ALIGNMENT, "pn_train_gemm_bf16x3: w_scratch must be 128-byte aligned");
     PN_REQUIRE(rows > 0 && cin > 0 && cout > 0 && ldx >= cin && ldy >= cout, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: bad shape");
     PN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr) && (col_sum == nullptr) == (col_sumsq == nullptr), PN_ERR_BAD_ARG,
                "pn_train_gemm_bf16x3: in_scale/in_shift and col_sum/col_sumsq come in pairs");
@@ -386,7 +435,15 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
     a.k_pad = round_up(cin, KC);
     a.n_pad = round_up(cout, 32);
     a.x_vec = ((uintptr_t)x % 16 == 0) && (ldx % 4 == 0);
-    const size_t smem = (size_t)a.k_pad * a.n_pad * 4 + NS * A_STAGE + 128 + (size_t)2 * 2 * 4 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) + 64;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("PN12_GEMM_DEBUG");     // profiling only: 1 = no MMAs, 2 = no epilogue work, 4 = no operand stores
+            dbg = e ? atoi(e) : 0;
+        }
+        a.debug = dbg;
+    }
+    const size_t smem = (size_t)a.k_pad * a.n_pad * 4 + NS * A_STAGE + 128 + (size_t)2 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) + 64;
     static int sms = 0;
     static size_t smem_set = 0;
     if (!sms) {
@@ -403,6 +460,12 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
             return (int)e;
         }
         smem_set = smem;
+    }
+    a.w_packed = static_cast<const unsigned char*>(w_scratch);
+    {
+        const int items = a.n_pad * (a.k_pad / 8);
+        train_pack_kernel<<<(items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, w_transposed, cin, cout, a.k_pad, a.n_pad,
+                                                                                static_cast<unsigned char*>(w_scratch));
     }
     const int64_t tiles = ceil_div(rows, TM);
     const int per_sm = (smem <= 112 * 1024 && a.n_pad <= 128) ? 2 : 1;      // two CTAs share the SM's 512 TMEM columns (2 x 2 x n_pad)

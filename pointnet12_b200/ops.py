@@ -700,11 +700,12 @@ def train_gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], i
     if (w.shape[0] if transposed else w.shape[1]) != cin:
         raise ValueError(f"weight shape {tuple(w.shape)} does not match {cin} input channels")
     y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
+    scratch = torch.empty((int(nv.lib().pn_train_gemm_scratch_bytes(cin, cout)),), dtype=torch.uint8, device=x.device)
     with _on_device(x):
         nv.call("pn_train_gemm_bf16x3", x.data_ptr(), _ld(x), rows, cin, _p(in_stats.scale) if in_stats is not None else None,
                 _p(in_stats.shift) if in_stats is not None else None, int(in_relu), w.data_ptr(), int(transposed), _p(bias), cout,
                 y.data_ptr(), cout, _p(stats_acc[0]) if stats_acc is not None else None,
-                _p(stats_acc[1]) if stats_acc is not None else None, _stream())
+                _p(stats_acc[1]) if stats_acc is not None else None, scratch.data_ptr(), _stream(), tag=(rows, cin, cout))
     return y
 
 
@@ -756,6 +757,15 @@ def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: boo
 
 
 GRAD_TC_MIN_TILE = int(os.environ.get("PN12_GRAD_TC_MIN", "1024"))     # cout * cin from which the 128 x 128 tensor-core tile is worth its padding
+
+
+def set_grad_weight_ctas_per_sm(ctas: int = 1) -> None:
+    """Tuning hook (pn_grad_weight_set_ctas_per_sm)."""
+    nv.call("pn_grad_weight_set_ctas_per_sm", int(ctas))
+
+
+if os.environ.get("PN12_GRADW_CTAS"):
+    set_grad_weight_ctas_per_sm(int(os.environ["PN12_GRADW_CTAS"]))
 
 
 def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor],

@@ -148,6 +148,32 @@ def main(argv=None):
     total = torch.tensor([times.sum()], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    # roofline of the dominant kernel (the fused layer GEMM, HBM-bound): CUDA events around every call of one eager
+    # iteration; algorithmic bytes = rows * (cin + cout) * 4 per call (operand read once, output written once)
+    roofline = None
+    if ops.mlp_mode() == "bf16x3":
+        nv.time_entry_points(["pn_train_gemm_bf16x3"])
+        for _ in range(3):
+            flush.fill_(1)
+            eager_step()
+        torch.cuda.synchronize()
+        recs = nv.time_entry_points(None)["pn_train_gemm_bf16x3"]
+        if recs:
+            n_calls = len(recs) // 3
+            recs = recs[-n_calls:]                            # the last of the three iterations
+            t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+            nbytes = sum(r * (ci + co) * 4 for _, _, (r, ci, co) in recs)
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                peak, src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            except Exception:
+                peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+            ach = nbytes / (t_ms * 1e-3) / 1e9
+            roofline = {"kernel": "gemm::train_gemm_kernel (pn_train_gemm_bf16x3: forward layer GEMMs with fused BatchNorm, input-gradient GEMMs)",
+                        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": src, "algorithmic_bytes_per_step": int(nbytes), "launches_per_step": n_calls,
+                        "kernel_ms_per_step": t_ms, "share_of_step": t_ms / (float(total.item()) / args.steps),
+                        "timing": "CUDA events around each call in an eager iteration after the timed region (includes ~2 us of launch gap per call)"}
     phases = None
     if args.eager:                       # per-phase split of one more (instrumented) eager iteration
         marks = []
@@ -164,7 +190,7 @@ def main(argv=None):
                                    f"gradient all-reduce, Adam), {B} clouds x {N} points per GPU, seeded random init",
                        "l2": "256 MiB written between timed steps", "launch": "eager" if args.eager else "forward + loss + backward (+ the next batch's sampling / grouping on a side stream) as one CUDA-graph replay, then all-reduce and Adam"},
             "step_ms": {"min": float(times.min()), "median": float(np.median(times)), "max": float(times.max())},
-            "vs_baseline": None, "clocks": clocks.summary(),
+            "vs_baseline": None, "clocks": clocks.summary(), "roofline": roofline,
             "e2e": {"value": world * B * N / (float(e2e_total.item()) / args.steps * 1e-3), "unit": "points/s",
                     "ms_per_step": float(e2e_total.item()) / args.steps,
                     "h2d_bytes_per_step": int(host_pts.numel() * 4 + host_tgt.numel() * 8), "d2h_bytes_per_step": 4},
