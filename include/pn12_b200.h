@@ -419,6 +419,16 @@ int pn_scan_sample_f32(const float* points, const uint32_t* raw_label, const int
                        const float* noise, float sigma, float clip, const uint64_t* seed_offset, float* out,
                        int64_t* labels, pn_stream_t stream);
 
+/* ---- row f-4 helpers ------------------------------------------------------------------------------------------- */
+/* chamfer_batch / chamfer_non_batch (model/chamfer.py:7-53): per_point [B,N] (may be NULL) = min_m ||p1[b,n] - p2[b,m]||_2,
+ * *total (fp64, device, overwritten) = their sum; the reference divides by B.  Clouds via strides, D <= 8 coordinates. */
+int pn_chamfer_f32(const float* p1, int64_t aB, int64_t aN, int64_t aC, const float* p2, int64_t bB, int64_t bN, int64_t bC,
+                   int B, int N, int M, int D, float* per_point, double* total, pn_stream_t stream);
+/* SemKITTI_2_Common.__call__ (data_utils/kitti_utils.py:97-110): y[r, j] = max(x[r, src0[j]], x[r, src1[j]]) for j < n_out
+ * (src1[j] == src0[j] for classes that are not merged); src0 / src1 are device int32 [n_out], indices < n_in. */
+int pn_class_merge_f32(const float* x, int64_t ldx, int64_t rows, int n_in, int n_out, const int* src0, const int* src1,
+                       float* y, pn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

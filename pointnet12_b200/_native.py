@@ -93,6 +93,8 @@ _SIGNATURES = {
     "pn_seg_metrics_f32": [vp, i64, vp, i64, i32, vp, vp, vp],
     "pn_scan_filter_f32": [vp, vp, vp, i32, i64, vp, i32, i32, f32, f32, f32, f32, vp, vp, vp, C.c_size_t, vp],
     "pn_scan_sample_f32": [vp, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, f32, f32, vp, vp, vp, vp],
+    "pn_chamfer_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp],
+    "pn_class_merge_f32": [vp, i64, i64, i32, i32, vp, vp, vp, vp],
     "pn_seg_metrics_accumulate": [vp, i32, i64, vp, vp, vp, vp, vp],
 }
 

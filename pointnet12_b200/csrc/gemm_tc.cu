@@ -29,7 +29,8 @@
 namespace pn {
 namespace gemm {
 
-constexpr int TM = 128, KC = 32, NS = 2, THREADS = 256;   // 2 stages + the register buffer: 128 x 128 layers fit two CTAs per SM
+constexpr int TM = 128, KC = 32, THREADS = 256;
+constexpr int NS_MAX = 4, NA_MAX = 4;          // operand ring stages / TMEM accumulators: chosen per layer by the host (Args::ns, ::na)
 constexpr int A_IMG = TM * KC * 2;            // one bf16 image of a 128 x 32 chunk: 8 KB
 constexpr int A_STAGE = 2 * A_IMG;            // hi + lo
 constexpr int W_MAX_BYTES = 128 * 1024;       // resident weights (hi + lo)
@@ -121,7 +122,7 @@ struct Args {
     const float* w; int w_transposed; const float* bias; int cout;
     float* y; int64_t ldy;
     double* col_sum; double* col_sumsq;
-    int k_pad, n_pad, x_vec, debug;
+    int k_pad, n_pad, x_vec, debug, ns, na;
     const unsigned char* w_packed;   // bf16 hi/lo image of the weights in the kernel's shared-memory layout (train_pack_kernel)
 };
 
@@ -151,30 +152,31 @@ __global__ void train_pack_kernel(const float* __restrict__ w, int w_transposed,
     }
 }
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 train_gemm_kernel(const Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int kch = a.k_pad / KC;                               // K chunks
+    const int NS = a.ns, NA = a.na;
     const unsigned w_chunk_bytes = (unsigned)a.n_pad * KC * 4;  // hi + lo images of one K chunk of the weights
     unsigned char* w_smem = smem;                               // [kch][hi: n_pad x 32 | lo: n_pad x 32]
     unsigned char* a_smem = smem + (size_t)kch * w_chunk_bytes; // ring of NS stages
-    // barriers: full[NS] (128 producer arrivals), empty[NS] (MMA commit), acc_full[2] (MMA commit), acc_empty[2] (128 epilogue arrivals)
+    // barriers: full[4] (128 producer arrivals), empty[4] (MMA commit), acc_full[4] (MMA commit), acc_empty[4] (128 epilogue arrivals), weights
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(a_smem + NS * A_STAGE);
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * NS + 5);
-    float* tf = reinterpret_cast<float*>(bars + 16);                                           // [2][k_pad]: in_scale | in_shift (16-byte aligned)
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4 * NS_MAX + 1);
+    float* tf = reinterpret_cast<float*>(bars + 32);                                           // [2][k_pad]: in_scale | in_shift (16-byte aligned)
     double* cta_sum = reinterpret_cast<double*>(tf + 2 * a.k_pad);                             // [2][n_pad]: this CTA's column sums over all its tiles
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_accf = smem_u32(bars + 2 * NS),
-                   bar_acce = smem_u32(bars + 2 * NS + 2), bar_w = smem_u32(bars + 2 * NS + 4);
+    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS_MAX), bar_accf = smem_u32(bars + 2 * NS_MAX),
+                   bar_acce = smem_u32(bars + 3 * NS_MAX), bar_w = smem_u32(bars + 4 * NS_MAX);
 
     unsigned tmem_cols = 32;
-    while ((int)tmem_cols < 2 * a.n_pad) tmem_cols <<= 1;       // two accumulators: the MMAs of tile i+1 overlap the epilogue of tile i
+    while ((int)tmem_cols < NA * a.n_pad) tmem_cols <<= 1;      // NA accumulators: the MMAs of the next tiles overlap the epilogue of tile i
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar_full + 8 * s, THREADS / 2);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NA; ++b) {
             mbar_init(bar_accf + 8 * b, 1);
             mbar_init(bar_acce + 8 * b, THREADS / 2);
         }
@@ -294,10 +296,10 @@ train_gemm_kernel(const Args a) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_full + 8 * s);
             if (warp == 0) {
-                const int b = (int)(it & 1);
+                const int b = (int)(it % NA);
                 mbar_wait(bar_full + 8 * s, use & 1);
                 if (gc == 0) mbar_wait(bar_w, 0);                      // the weight image has landed
-                if (c == 0 && it >= 2) mbar_wait(bar_acce + 8 * b, (unsigned)((it >> 1) - 1) & 1);   // epilogue of tile it-2 has read it
+                if (c == 0 && it >= NA) mbar_wait(bar_acce + 8 * b, (unsigned)(it / NA - 1) & 1);   // epilogue of tile it-NA has read it
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect()) {
                     const unsigned acc = tbase + (unsigned)(b * a.n_pad);
@@ -329,8 +331,8 @@ train_gemm_kernel(const Args a) {
         const int et = tid - THREADS / 2;                        // 0..127
         const int nch = a.n_pad / 32;
         for (int64_t it = 0; it < my_tiles; ++it) {
-            const int b = (int)(it & 1);
-            mbar_wait(bar_accf + 8 * b, (unsigned)(it >> 1) & 1);
+            const int b = (int)(it % NA);
+            mbar_wait(bar_accf + 8 * b, (unsigned)(it / NA) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = (blockIdx.x + it * gridDim.x) * TM + q * 32 + lane;
             const bool row_ok = row < a.rows;
@@ -443,7 +445,16 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
         }
         a.debug = dbg;
     }
-    const size_t smem = (size_t)a.k_pad * a.n_pad * 4 + NS * A_STAGE + 128 + (size_t)2 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) + 64;
+    // Ring depth and accumulator count: a row tile is handed producer -> tensor core -> epilogue through mbarriers, ~3 us per
+    // tile of latency, so narrow layers (one or two K chunks per tile) need several tiles in flight.  Layers whose weights
+    // leave room get 4 stages; two CTAs share the SM's 512 TMEM columns, so each may hold 256 / n_pad accumulators.
+    const size_t w_bytes = (size_t)a.k_pad * a.n_pad * 4;
+    const size_t fixed = 256 /* barriers + TMEM slot */ + (size_t)2 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) + 64;
+    a.ns = (w_bytes + 4 * A_STAGE + fixed <= 112 * 1024) ? 4 : 2;
+    const size_t smem = w_bytes + (size_t)a.ns * A_STAGE + fixed;
+    const int per_sm = (smem <= 112 * 1024 && a.n_pad <= 128) ? 2 : 1;      // two CTAs share the SM's 512 TMEM columns
+    a.na = (per_sm == 2 ? 256 : 512) / a.n_pad;
+    if (a.na > NA_MAX) a.na = NA_MAX;
     static int sms = 0;
     static size_t smem_set = 0;
     if (!sms) {
@@ -468,7 +479,6 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
                                                                                 static_cast<unsigned char*>(w_scratch));
     }
     const int64_t tiles = ceil_div(rows, TM);
-    const int per_sm = (smem <= 112 * 1024 && a.n_pad <= 128) ? 2 : 1;      // two CTAs share the SM's 512 TMEM columns (2 x 2 x n_pad)
     const int64_t grid = tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm;
     train_gemm_kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(a);
     return finish_launch("pn_train_gemm_bf16x3");

@@ -783,3 +783,87 @@ PN_EXPORT int pn_seg_metrics_accumulate(const int64_t* counts, int C, int64_t po
                                                                                      count, acc_sum, batches);
     return finish_launch("pn_seg_metrics_accumulate");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Row f-4 helpers.
+// chamfer_batch / chamfer_non_batch (model/chamfer.py:7-53): sum over b, n of min_m ||p1[b,n] - p2[b,m]||_2, divided by B.
+// One thread per p1 point, p2 staged through shared memory in tiles; the minimum is taken over squared distances
+// (sqrt is monotonic) and the root drawn once per point; block sums in fp64.
+namespace pn {
+constexpr int CH_TILE = 256, CH_MAXD = 8;
+__global__ void __launch_bounds__(CH_TILE)
+chamfer_kernel(const float* __restrict__ p1, int64_t aB, int64_t aN, int64_t aC, const float* __restrict__ p2, int64_t bB,
+               int64_t bN, int64_t bC, int N, int M, int D, float* __restrict__ per_point, double* __restrict__ total) {
+    __shared__ float tile[CH_TILE][CH_MAXD];
+    __shared__ double red[CH_TILE / 32];
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * CH_TILE + threadIdx.x;
+    float q[CH_MAXD];
+#pragma unroll
+    for (int c = 0; c < CH_MAXD; ++c) q[c] = (n < N && c < D) ? p1[b * aB + (int64_t)n * aN + c * aC] : 0.0f;
+    float best = CUDART_INF_F;
+    for (int m0 = 0; m0 < M; m0 += CH_TILE) {
+        const int m = m0 + threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < CH_MAXD; ++c) tile[threadIdx.x][c] = (m < M && c < D) ? p2[b * bB + (int64_t)m * bN + c * bC] : 0.0f;
+        __syncthreads();
+        const int lim = min(CH_TILE, M - m0);
+        for (int j = 0; j < lim; ++j) {
+            float d = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CH_MAXD; ++c) {
+                const float t = q[c] - tile[j][c];
+                d = fmaf(t, t, d);
+            }
+            best = fminf(best, d);
+        }
+        __syncthreads();
+    }
+    const float dist = n < N ? sqrtf(best) : 0.0f;
+    if (n < N && per_point) per_point[(int64_t)b * N + n] = dist;
+    double s = (double)dist;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < CH_TILE / 32; ++i) t += red[i];
+        atomicAdd(total, t);
+    }
+}
+
+// SemKITTI_2_Common.__call__ (data_utils/kitti_utils.py:97-110): common[..., j] = max(logits[..., src0[j]], logits[..., src1[j]])
+__global__ void class_merge_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int n_out, const int* __restrict__ src0,
+                                   const int* __restrict__ src1, float* __restrict__ y) {
+    const int64_t total = rows * n_out;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % n_out);
+        const int64_t r = e / n_out;
+        y[e] = fmaxf(x[r * ldx + src0[j]], x[r * ldx + src1[j]]);
+    }
+}
+}  // namespace pn
+
+PN_EXPORT int pn_chamfer_f32(const float* p1, int64_t aB, int64_t aN, int64_t aC, const float* p2, int64_t bB, int64_t bN,
+                             int64_t bC, int B, int N, int M, int D, float* per_point, double* total, pn_stream_t stream) {
+    PN_REQUIRE(p1 && p2 && total, PN_ERR_BAD_ARG, "pn_chamfer_f32: null pointer");
+    PN_REQUIRE(B > 0 && B <= 65535 && N > 0 && M > 0 && D > 0 && D <= CH_MAXD, PN_ERR_BAD_ARG, "pn_chamfer_f32: bad sizes (D <= 8)");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(total, 0, sizeof(double), st);
+    if (e != cudaSuccess) {
+        set_error("pn_chamfer_f32: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    dim3 grid((unsigned)ceil_div(N, CH_TILE), (unsigned)B);
+    chamfer_kernel<<<grid, CH_TILE, 0, st>>>(p1, aB, aN, aC, p2, bB, bN, bC, N, M, D, per_point, total);
+    return finish_launch("pn_chamfer_f32");
+}
+
+PN_EXPORT int pn_class_merge_f32(const float* x, int64_t ldx, int64_t rows, int n_in, int n_out, const int* src0,
+                                 const int* src1, float* y, pn_stream_t stream) {
+    PN_REQUIRE(x && src0 && src1 && y, PN_ERR_BAD_ARG, "pn_class_merge_f32: null pointer");
+    PN_REQUIRE(rows > 0 && n_in > 0 && n_out > 0 && ldx >= n_in, PN_ERR_BAD_ARG, "pn_class_merge_f32: bad shape");
+    class_merge_kernel<<<ew_blocks(rows * n_out, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, n_out, src0, src1, y);
+    return finish_launch("pn_class_merge_f32");
+}

@@ -109,3 +109,51 @@ class ScanPreprocessor:
                     self.lut.data_ptr(), self.lut.numel(), kept.data_ptr(), count.data_ptr(), int(npoints), ops._p(choice),
                     ops._p(noise), float(sigma), float(self.CLIP), ops._p(seed), out.data_ptr(), labels.data_ptr(), ops._stream())
         return out, labels
+
+
+class SemKITTI_2_Common:
+    """Drop-in for data_utils/kitti_utils.py:61-117: wraps a model and merges its 19 SemanticKITTI log-probability channels into
+    the 16 'common' classes (max over the merged pair) with one kernel instead of 16 indexed copies.  Same constructor,
+    attributes (`semkitti_names`, `semkitti_2_common`, `colors`, `semkitti_colors`, `common`) and call as the reference."""
+
+    semkitti_names = ['car', 'bicycle', 'motorcycle', 'truck', 'other-vehicle', 'person', 'bicyclist', 'motorcyclist', 'road',
+                      'parking', 'sidewalk', 'other-ground', 'building', 'fence', 'vegetation', 'trunk', 'terrain', 'pole',
+                      'traffic-sign']
+    semkitti_2_common = ['road', 'parking+sidewalk', 'building', 'fence', 'trunk+pole', 'traffic-sign', 'vegetation', 'terrain',
+                         'person', 'bicyclist+motorcyclist', 'car', 'truck', 'other-vehicle', 'motorcycle', 'bicycle', 'other-ground']
+    _colors = [[245, 150, 100], [245, 230, 100], [150, 60, 30], [180, 30, 80], [255, 0, 0], [30, 30, 255], [200, 40, 255],
+               [90, 30, 150], [255, 0, 255], [255, 150, 255], [75, 0, 75], [75, 0, 175], [0, 200, 255], [50, 120, 255],
+               [0, 175, 0], [0, 60, 135], [80, 240, 150], [150, 240, 255], [0, 0, 255]]
+
+    def __init__(self, model, model_name):
+        self.model_name, self.model, self.common = model_name, model, None
+        pairs = [[self.semkitti_names.index(n) for n in c.split('+')] for c in self.semkitti_2_common]
+        if any(len(p) > 2 for p in pairs):
+            raise NotImplementedError("not implemented!")
+        self._src = [[p[0] for p in pairs], [p[-1] for p in pairs]]
+        self.semkitti_colors = np.array(self._colors)
+        self.colors = np.array([self._colors[p[0]] for p in pairs])
+        self._dev_src = {}
+
+    def merge(self, logits: torch.Tensor) -> torch.Tensor:
+        """[B, N, 19] -> [B, N, 16]."""
+        ops._need_cuda(logits, "logits")
+        x = logits.float().contiguous()
+        k = x.shape[-1]
+        if x.device not in self._dev_src:
+            self._dev_src[x.device] = torch.tensor(self._src, dtype=torch.int32, device=x.device)
+        src = self._dev_src[x.device]
+        out = torch.empty(tuple(x.shape[:-1]) + (len(self.semkitti_2_common),), dtype=torch.float32, device=x.device)
+        rows = x.numel() // k
+        with ops._on_device(x):
+            nv.call("pn_class_merge_f32", x.data_ptr(), k, rows, k, out.shape[-1], src[0].data_ptr(), src[1].data_ptr(),
+                    out.data_ptr(), ops._stream())
+        return out
+
+    def __call__(self, x):
+        if self.model_name == 'pointnet':
+            logits, feature_transform = self.model(x)
+        else:
+            logits = self.model(x)
+        self.common = self.merge(logits)
+        return (self.common, feature_transform) if self.model_name == 'pointnet' else self.common

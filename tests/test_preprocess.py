@@ -150,3 +150,39 @@ def test_cuda_device_draws(dev):
     nz = (b - a)[:, :, :1000].double()
     assert abs(nz.mean().item()) < 1e-3 and abs(nz.std().item() - 0.01) < 1e-3 and nz.abs().max().item() <= 0.05 + 1e-6
     assert torch.equal((b - a)[:, :, :1000], (b - a)[:, :, 1000:2000])    # the same kept point gets the same jitter
+
+
+# ------------------------------------------------------------------------------------------------ row f-4 helpers
+@pytest.mark.gpu
+def test_chamfer_known_answer_and_random(dev):
+    """model/chamfer.py:55-67, the reference's only known-answer check: both spellings print 11.6073."""
+    from model.chamfer import chamfer_batch, chamfer_non_batch
+
+    p1 = torch.tensor([[[1., 2, 3], [4, 5, 6], [3, 5, 6], [5, 6, 7]], [[2., 2, 3], [3, 5, 6], [4, 5, 6], [8, 6, 7]]], device=dev)
+    p2 = torch.tensor([[[3., 7, 8], [1, 4, 5]], [[3., 8, 8], [2, 4, 5]]], device=dev)
+    a = chamfer_batch(p1, p2).item()
+    b = ((chamfer_batch(p1[:1], p2[:1]) + chamfer_batch(p1[1:], p2[1:])) / 2).item()
+    c = ((chamfer_non_batch(p1[:1], p2[:1]) + chamfer_non_batch(p1[1:], p2[1:])) / 2).item()
+    assert abs(a - 11.6073) < 1e-4 and abs(b - 11.6073) < 1e-4 and abs(c - 11.6073) < 1e-4
+    rng = np.random.default_rng(2)
+    x, y = rng.standard_normal((3, 1000, 3)).astype(np.float32), rng.standard_normal((3, 777, 3)).astype(np.float32)
+    d = np.sqrt(((x[:, :, None, :].astype(np.float64) - y[:, None, :, :]) ** 2).sum(-1)).min(2).sum() / 3
+    got = chamfer_batch(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev).permute(0, 2, 1).contiguous().permute(0, 2, 1)).item()
+    assert abs(got - d) < 1e-4 * d
+
+
+@pytest.mark.gpu
+def test_semkitti_2_common_merge(dev):
+    """data_utils/kitti_utils.py:97-110 restated with numpy indexing."""
+    from pointnet12_b200.preprocess import SemKITTI_2_Common
+
+    rng = np.random.default_rng(4)
+    logits = rng.standard_normal((2, 500, 19)).astype(np.float32)
+    m = SemKITTI_2_Common(lambda x: x, "pointnet2")
+    got = m(torch.from_numpy(logits).to(dev)).cpu().numpy()
+    want = np.zeros((2, 500, 16), dtype=np.float32)
+    for j, c in enumerate(m.semkitti_2_common):
+        idx = [m.semkitti_names.index(n) for n in c.split('+')]
+        want[:, :, j] = logits[:, :, idx].max(2)
+    assert got.shape == (2, 500, 16) and np.array_equal(got, want)
+    assert m.colors.shape == (16, 3) and m.semkitti_colors.shape == (19, 3)
