@@ -348,6 +348,15 @@ size_t pn_train_gemm_scratch_bytes(int cin, int cout);
 int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale, const float* in_shift,
                          int in_relu, const float* w, int w_transposed, const float* bias, int cout, float* y, int64_t ldy,
                          double* col_sum, double* col_sumsq, void* w_scratch, pn_stream_t stream);
+/* The input-gradient GEMM of the backward pass with the NEXT reduction fused into its epilogue: dz = dy W (w / w_transposed
+ * as above; dz is the gradient w.r.t. the activated output of the layer below) and, from that layer's pre-normalisation
+ * output prev_y [rows, cout] and batch constants, s1 += sum_r g, s2 += sum_r g*xhat with g = dz * [prev_y*scale+shift > 0],
+ * xhat = (prev_y - mean)*invstd -- exactly what pn_bn_bwd_stats_f32 would compute in a pass of its own over dz and prev_y
+ * (s1, s2: fp64 [cout], zeroed by the caller; then pn_bn_bwd_apply_f32). */
+int pn_train_gemm_bnbwd_bf16x3(const float* dy, int64_t lddy, int64_t rows, int cin, const float* w, int w_transposed, int cout,
+                               float* dz, int64_t lddz, const float* prev_y, int64_t ld_prev, const float* prev_scale,
+                               const float* prev_shift, const float* prev_mean, const float* prev_invstd, double* s1, double* s2,
+                               void* w_scratch, pn_stream_t stream);
 /* out [cols, rows] = in [rows, cols]^T (the weight of the input-gradient GEMM dx = dy W = pn_linear_f32(dy, W^T)). */
 int pn_transpose_f32(const float* in, int rows, int cols, float* out, pn_stream_t stream);
 /* Backward of the gather of sample_and_group (model/pointnet_util.py:128-131): dfeat[b, idx[b,s,k], :] +=

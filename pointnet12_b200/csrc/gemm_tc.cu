@@ -123,6 +123,8 @@ struct Args {
     float* y; int64_t ldy;
     double* col_sum; double* col_sumsq;
     int k_pad, n_pad, x_vec, debug, ns, na;
+    // backward statistics in the epilogue (all NULL for the forward): the layer BELOW's pre-normalisation output and constants
+    const float* py; int64_t ldpy; const float* p_scale; const float* p_shift; const float* p_mean; const float* p_invstd;
     const unsigned char* w_packed;   // bf16 hi/lo image of the weights in the kernel's shared-memory layout (train_pack_kernel)
 };
 
@@ -165,6 +167,8 @@ train_gemm_kernel(const Args a) {
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 4 * NS_MAX + 1);
     float* tf = reinterpret_cast<float*>(bars + 32);                                           // [2][k_pad]: in_scale | in_shift (16-byte aligned)
     double* cta_sum = reinterpret_cast<double*>(tf + 2 * a.k_pad);                             // [2][n_pad]: this CTA's column sums over all its tiles
+    float* bias_s = reinterpret_cast<float*>(cta_sum + 2 * a.n_pad);                           // [n_pad], zero beyond cout
+    float* pc = bias_s + a.n_pad;                                                               // [4][n_pad]: scale, shift, mean, invstd of the layer below
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS_MAX), bar_accf = smem_u32(bars + 2 * NS_MAX),
                    bar_acce = smem_u32(bars + 3 * NS_MAX), bar_w = smem_u32(bars + 4 * NS_MAX);
@@ -229,6 +233,15 @@ train_gemm_kernel(const Args a) {
     }
     if (a.col_sum)
         for (int n = tid; n < 2 * a.n_pad; n += THREADS) cta_sum[n] = 0.0;
+    for (int n = tid; n < a.n_pad; n += THREADS) bias_s[n] = (a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.0f;
+    if (a.py)
+        for (int n = tid; n < a.n_pad; n += THREADS) {
+            const bool ok = n < a.cout;
+            pc[n] = ok ? __ldg(a.p_scale + n) : 0.0f;
+            pc[a.n_pad + n] = ok ? __ldg(a.p_shift + n) : 0.0f;
+            pc[2 * a.n_pad + n] = ok ? __ldg(a.p_mean + n) : 0.0f;
+            pc[3 * a.n_pad + n] = ok ? __ldg(a.p_invstd + n) : 0.0f;
+        }
     if (a.in_scale) {
         // the operand transform's per-channel constants: read through shared memory (a warp's lanes all want the same k)
         for (int k = tid; k < a.k_pad; k += THREADS) {
@@ -345,10 +358,14 @@ train_gemm_kernel(const Args a) {
                     mbar_arrive(bar_acce + 8 * b);
                 }
                 float v[32];
+                const float4* b4 = reinterpret_cast<const float4*>(bias_s + col0);       // (a warp's lanes all want the same n)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = col0 + j;
-                    v[j] = __uint_as_float(r[j]) + ((a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.0f);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bb = b4[j >> 2];
+                    v[j] = __uint_as_float(r[j]) + bb.x;
+                    v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+                    v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
+                    v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
                 }
                 if ((a.debug & 2) && v[0] != 12345.678f) continue;
                 if (row_ok) {
@@ -366,11 +383,45 @@ train_gemm_kernel(const Args a) {
                     // column sums over the warp's 32 rows: the butterfly's first three steps (16 + 8 + 4 columns exchanged:
                     // afterwards a lane holds 4 columns summed over 8 rows) in fp32, the last two and everything beyond in fp64
                     float f1[32], f2[32];
+                    if (a.py) {
+                        // BACKWARD statistics: this GEMM's output is dz of the layer below (gradient w.r.t. its activated
+                        // output); with that layer's pre-normalisation output yp: g = dz * [yp*scale+shift > 0],
+                        // xhat = (yp - mean) * invstd, and the two sums its BatchNorm backward needs are sum g, sum g*xhat
+                        const float* __restrict__ ypr = a.py + row * a.ldpy + col0;
+                        const bool vec = col0 + 32 <= a.cout && ((a.ldpy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.py) & 15) == 0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float d = row_ok ? v[j] : 0.0f;
-                        f1[j] = d;
-                        f2[j] = d * d;
+                        for (int j = 0; j < 32; j += 4) {
+                            float yp[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (row_ok) {
+                                if (vec) {
+                                    const float4 t = __ldg(reinterpret_cast<const float4*>(ypr + j));
+                                    yp[0] = t.x; yp[1] = t.y; yp[2] = t.z; yp[3] = t.w;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i)
+                                        if (col0 + j + i < a.cout) yp[i] = __ldg(ypr + j + i);
+                                }
+                            }
+                            const float4 sc = *reinterpret_cast<const float4*>(pc + col0 + j);
+                            const float4 sh = *reinterpret_cast<const float4*>(pc + a.n_pad + col0 + j);
+                            const float4 mu = *reinterpret_cast<const float4*>(pc + 2 * a.n_pad + col0 + j);
+                            const float4 is = *reinterpret_cast<const float4*>(pc + 3 * a.n_pad + col0 + j);
+                            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                            const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float g = (row_ok && fmaf(yp[i], scv[i], shv[i]) > 0.0f) ? v[j + i] : 0.0f;
+                                f1[j + i] = g;
+                                f2[j + i] = g * ((yp[i] - muv[i]) * isv[i]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = row_ok ? v[j] : 0.0f;
+                            f1[j] = d;
+                            f2[j] = d * d;
+                        }
                     }
                     colsum_step_f<16>(f1, lane);
                     colsum_step_f<16>(f2, lane);
@@ -416,10 +467,34 @@ PN_EXPORT size_t pn_train_gemm_scratch_bytes(int cin, int cout) {
     return (size_t)round_up(cin, KC) * round_up(cout, 32) * 4;
 }
 
+static int train_gemm_launch(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale, const float* in_shift,
+                             int in_relu, const float* w, int w_transposed, const float* bias, int cout, float* y, int64_t ldy,
+                             double* col_sum, double* col_sumsq, const float* py, int64_t ldpy, const float* p_scale,
+                             const float* p_shift, const float* p_mean, const float* p_invstd, void* w_scratch, pn_stream_t stream);
+
 PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale,
                                    const float* in_shift, int in_relu, const float* w, int w_transposed, const float* bias,
                                    int cout, float* y, int64_t ldy, double* col_sum, double* col_sumsq, void* w_scratch,
                                    pn_stream_t stream) {
+    return train_gemm_launch(x, ldx, rows, cin, in_scale, in_shift, in_relu, w, w_transposed, bias, cout, y, ldy, col_sum, col_sumsq,
+                             nullptr, 0, nullptr, nullptr, nullptr, nullptr, w_scratch, stream);
+}
+
+PN_EXPORT int pn_train_gemm_bnbwd_bf16x3(const float* dy, int64_t lddy, int64_t rows, int cin, const float* w, int w_transposed,
+                                         int cout, float* dz, int64_t lddz, const float* prev_y, int64_t ld_prev,
+                                         const float* prev_scale, const float* prev_shift, const float* prev_mean,
+                                         const float* prev_invstd, double* s1, double* s2, void* w_scratch, pn_stream_t stream) {
+    PN_REQUIRE(prev_y && prev_scale && prev_shift && prev_mean && prev_invstd && s1 && s2, PN_ERR_BAD_ARG,
+               "pn_train_gemm_bnbwd_bf16x3: null pointer");
+    PN_REQUIRE(ld_prev >= cout, PN_ERR_BAD_ARG, "pn_train_gemm_bnbwd_bf16x3: ld_prev smaller than cout");
+    return train_gemm_launch(dy, lddy, rows, cin, nullptr, nullptr, 0, w, w_transposed, nullptr, cout, dz, lddz, s1, s2, prev_y, ld_prev,
+                             prev_scale, prev_shift, prev_mean, prev_invstd, w_scratch, stream);
+}
+
+static int train_gemm_launch(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale, const float* in_shift,
+                             int in_relu, const float* w, int w_transposed, const float* bias, int cout, float* y, int64_t ldy,
+                             double* col_sum, double* col_sumsq, const float* py, int64_t ldpy, const float* p_scale,
+                             const float* p_shift, const float* p_mean, const float* p_invstd, void* w_scratch, pn_stream_t stream) {
     using namespace pn;
     using namespace pn::gemm;
     PN_REQUIRE(x && w && y && w_scratch, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: null pointer");
@@ -434,6 +509,7 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
     a.in_scale = in_scale; a.in_shift = in_shift; a.in_relu = in_relu;
     a.w = w; a.w_transposed = w_transposed; a.bias = bias; a.cout = cout;
     a.y = y; a.ldy = ldy; a.col_sum = col_sum; a.col_sumsq = col_sumsq;
+    a.py = py; a.ldpy = ldpy; a.p_scale = p_scale; a.p_shift = p_shift; a.p_mean = p_mean; a.p_invstd = p_invstd;
     a.k_pad = round_up(cin, KC);
     a.n_pad = round_up(cout, 32);
     a.x_vec = ((uintptr_t)x % 16 == 0) && (ldx % 4 == 0);
@@ -449,7 +525,8 @@ PN_EXPORT int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, in
     // tile of latency, so narrow layers (one or two K chunks per tile) need several tiles in flight.  Layers whose weights
     // leave room get 4 stages; two CTAs share the SM's 512 TMEM columns, so each may hold 256 / n_pad accumulators.
     const size_t w_bytes = (size_t)a.k_pad * a.n_pad * 4;
-    const size_t fixed = 256 /* barriers + TMEM slot */ + (size_t)2 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) + 64;
+    const size_t fixed = 256 /* barriers + TMEM slot */ + (size_t)2 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) +
+                         (size_t)5 * a.n_pad * sizeof(float) + 64;
     a.ns = (w_bytes + 4 * A_STAGE + fixed <= 112 * 1024) ? 4 : 2;
     const size_t smem = w_bytes + (size_t)a.ns * A_STAGE + fixed;
     const int per_sm = (smem <= 112 * 1024 && a.n_pad <= 128) ? 2 : 1;      // two CTAs share the SM's 512 TMEM columns

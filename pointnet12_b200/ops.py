@@ -709,6 +709,27 @@ def train_gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], i
     return y
 
 
+def train_gemm_bnbwd(dy: torch.Tensor, w: torch.Tensor, prev_y: torch.Tensor, prev_st: BatchStats, acc: torch.Tensor,
+                     transposed: bool = True) -> torch.Tensor:
+    """pn_train_gemm_bnbwd_bf16x3: dz = dy @ W (w [cout_layer, cin_layer] given as stored, transposed=True) plus, in the
+    epilogue, the two reductions of the BatchNorm backward of the layer BELOW (pre-normalisation output prev_y, statistics
+    prev_st) into acc (float64 [2, C], zeroed): bn_act_backward(..., acc=acc, acc_ready=True) then skips its own pass."""
+    dy = _rowmat(dy, "dy")
+    rows, cin = dy.shape
+    w = _f32(w, "w").contiguous()
+    cout = w.shape[1] if transposed else w.shape[0]
+    prev_y = _rowmat(prev_y, "prev_y")
+    if prev_y.shape != (rows, cout):
+        raise ValueError("prev_y must be [rows, cout]")
+    dz = torch.empty((rows, cout), dtype=torch.float32, device=dy.device)
+    scratch = torch.empty((int(nv.lib().pn_train_gemm_scratch_bytes(cin, cout)),), dtype=torch.uint8, device=dy.device)
+    with _on_device(dy):
+        nv.call("pn_train_gemm_bnbwd_bf16x3", dy.data_ptr(), _ld(dy), rows, cin, w.data_ptr(), int(transposed), cout, dz.data_ptr(),
+                cout, prev_y.data_ptr(), _ld(prev_y), prev_st.scale.data_ptr(), prev_st.shift.data_ptr(), prev_st.mean.data_ptr(),
+                prev_st.invstd.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(), scratch.data_ptr(), _stream())
+    return dz
+
+
 def bn_act(y: torch.Tensor, st: BatchStats, relu: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     y = _rowmat(y, "y")
     rows, Cc = y.shape
@@ -735,7 +756,7 @@ def bn_act_max(y: torch.Tensor, st: BatchStats, K: int, relu: bool = True) -> Tu
 
 def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: bool = True,
                     argmax: Optional[torch.Tensor] = None, K: int = 1, dgamma: Optional[torch.Tensor] = None,
-                    dbeta: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None):
+                    dbeta: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None, acc_ready: bool = False):
     """Backward of act(bn(y)) with batch statistics.  dgamma / dbeta given ([C] float32 buffers): the affine gradients
     are ADDED to them and dy [rows, C] is returned; otherwise -> (dy, dgamma, dbeta) with fresh buffers.
     argmax/K: dz is the pooled gradient [rows/K, C] of bn_act_max."""
@@ -751,7 +772,8 @@ def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: boo
     common = (y.data_ptr(), _ld(y), rows, Cc, dz.data_ptr(), _ld(dz), _p(argmax), int(K), st.scale.data_ptr(),
               st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), int(relu), acc[0].data_ptr(), acc[1].data_ptr())
     with _on_device(y):
-        nv.call("pn_bn_bwd_stats_f32", *common, _stream())
+        if not acc_ready:        # (acc_ready: the reductions were accumulated by the epilogue of train_gemm_bnbwd)
+            nv.call("pn_bn_bwd_stats_f32", *common, _stream())
         nv.call("pn_bn_bwd_apply_f32", *common, dy.data_ptr(), Cc, dgamma.data_ptr(), dbeta.data_ptr(), _stream())
     return (dy, dgamma, dbeta) if fresh else dy
 

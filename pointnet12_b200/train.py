@@ -58,6 +58,7 @@ def _grad_sink(p: torch.Tensor, shape) -> Tuple[torch.Tensor, bool]:
 
 
 FUSED_BN = os.environ.get("PN12_TRAIN_FUSED", "1") != "0"     # BatchNorm fused into the training GEMMs (pn_train_gemm_bf16x3)
+FUSED_BN_BWD = os.environ.get("PN12_TRAIN_FUSED_BWD", "0") != "0"   # BatchNorm-backward reductions in the input-gradient GEMM's epilogue
 
 
 def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] = None):
@@ -117,6 +118,7 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
     grads = [None] * len(layers)
     widest = max(c.weight.shape[0] for c, _, _ in layers)
     accs = torch.zeros((len(layers), 2, widest), dtype=torch.float64, device=dz.device)    # one fill for the block's reductions
+    stats_done = False           # the reductions of this layer's BatchNorm backward were fused into the GEMM that produced dz
     for li in range(len(layers) - 1, -1, -1):
         conv, bn, relu = layers[li]
         x, x_stats, y, st, _, am = saved[li]
@@ -126,15 +128,23 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
             dgamma, g_direct = _grad_sink(bn.weight, bn.weight.shape)
             dbeta, _ = _grad_sink(bn.bias, bn.bias.shape)
             dy = ops.bn_act_backward(y, st, dz, relu, argmax=am, K=pool_K if am is not None else 1, dgamma=dgamma, dbeta=dbeta,
-                                     acc=accs[li, :, :y.shape[1]])
+                                     acc=accs[li, :, :y.shape[1]], acc_ready=stats_done)
         else:
             dy = dz
+        stats_done = False
         w = _w2d(conv)
         dw, w_direct = _grad_sink(conv.weight, w.shape)
         db, b_direct = _grad_sink(conv.bias, (w.shape[0],)) if conv.bias is not None else (None, False)
         ops.grad_weight(dy, x, dw, db, x_stats=x_stats)      # x_stats: x is the previous layer's y, activated on load
         grads[li] = (None if w_direct else dw, None if b_direct else db, None if g_direct else dgamma, None if g_direct else dbeta)
-        dz = _gemm(dy, w, None, transposed=True) if (li > 0 or need_dx) else None
+        if (li > 0 and x_stats is not None and FUSED_BN and FUSED_BN_BWD and ops.mlp_mode() == "bf16x3"
+                and ops.train_gemm_supported(w.shape[0], w.shape[1])):
+            # the layer below kept only its pre-normalisation output (x here): the input-gradient GEMM also accumulates the
+            # two reductions of THAT layer's BatchNorm backward in its epilogue, saving a pass over dz and x
+            dz = ops.train_gemm_bnbwd(dy, w, x, x_stats, accs[li - 1, :, :w.shape[1]])
+            stats_done = True
+        else:
+            dz = _gemm(dy, w, None, transposed=True) if (li > 0 or need_dx) else None
     return dz, grads
 
 

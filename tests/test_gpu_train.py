@@ -174,6 +174,33 @@ def test_fused_train_gemm(dev, rows, cin, cout, ldx, transposed):
     assert rl2(db.cpu().numpy(), dy.astype(np.float64).sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("rows,co,ci", [(4096, 64, 64), (70001, 128, 128), (1000, 128, 67), (333, 32, 4)])
+def test_input_gradient_gemm_with_fused_bn_backward_statistics(dev, rows, co, ci):
+    """pn_train_gemm_bnbwd_bf16x3: dz = dy W and, in the epilogue, sum g / sum g*xhat of the layer below."""
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(rows + ci)
+    dy = rng.standard_normal((rows, co)).astype(np.float32)
+    w = rng.standard_normal((co, ci)).astype(np.float32)
+    yp = rng.standard_normal((rows, ci)).astype(np.float32)
+    st = ops.BatchStats()
+    st.scale, st.shift = T(rng.uniform(0.5, 1.5, ci).astype(np.float32), dev), T(rng.standard_normal(ci).astype(np.float32) * 0.3, dev)
+    st.mean, st.invstd = T(rng.standard_normal(ci).astype(np.float32) * 0.1, dev), T(rng.uniform(0.5, 2, ci).astype(np.float32), dev)
+    acc = torch.zeros((2, ci), dtype=torch.float64, device=dev)
+    dz = ops.train_gemm_bnbwd(T(dy, dev), T(w, dev), T(yp, dev), st, acc)
+    want = dy.astype(np.float64) @ w.astype(np.float64)
+    assert rl2(dz.cpu().numpy(), want) < 2e-5
+    sc, sh, mu, inv = (t.cpu().numpy().astype(np.float64) for t in (st.scale, st.shift, st.mean, st.invstd))
+    dzg = dz.cpu().numpy().astype(np.float64)
+    mask = (yp.astype(np.float32) * st.scale.cpu().numpy() + st.shift.cpu().numpy()) > 0          # fp32 like the kernel (fma vs mul+add: see below)
+    g = dzg * mask
+    xh = (yp.astype(np.float64) - mu) * inv
+    got = acc.cpu().numpy()
+    # a few elements sit within one rounding of the ReLU threshold (the kernel uses a fused multiply-add): allow their weight
+    slack = 1e-5 * np.abs(dzg).sum(0).max()
+    assert np.abs(got[0] - g.sum(0)).max() < slack and np.abs(got[1] - (g * xh).sum(0)).max() < 3 * slack
+
+
 def test_group_and_interpolate_backward(dev):
     from pointnet12_b200 import ops
 
