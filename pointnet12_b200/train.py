@@ -651,8 +651,10 @@ class GraphedTrainStep:
         if st is None:
             st = self._graphs[key] = self._build(points, target)
         B = points.shape[0]
-        tag = (points.data_ptr(), points._version)
-        if st["prefetched"] == tag:
+        # the prefetched batch is recognised by storage and version; the runner keeps a reference to it until then, so the
+        # storage cannot have been freed and handed to another tensor in between
+        ref = st["prefetched"]
+        if ref is not None and points.data_ptr() == ref[0].data_ptr() and points._version == ref[1] and points.shape == ref[0].shape:
             p = st["cur"] = 1 - st["cur"]                       # this batch's geometry was computed during the last replay
         else:
             p = st["cur"]
@@ -662,7 +664,7 @@ class GraphedTrainStep:
         if next_points is not None:
             st["x"][1 - p].copy_(next_points, non_blocking=True)
             self._stage(st, 1 - p, B)
-            st["prefetched"] = (next_points.data_ptr(), next_points._version)
+            st["prefetched"] = (next_points, next_points._version)
         else:
             st["prefetched"] = None       # (the replay then recomputes the other slot's old geometry: harmless, no draws consumed)
         if target.data_ptr() != st["target"].data_ptr():
