@@ -528,3 +528,61 @@ def test_graphed_train_step_matches_eager(dev):
     runner2 = GraphedTrainStep(b, opt_b)
     l1, l2 = runner2(pts, target).item(), runner2(pts, target).item()
     assert np.isfinite(l1) and np.isfinite(l2) and l1 != l2
+
+
+@pytest.mark.parametrize("B,N", [(3, 1500), (1, 1027)])
+def test_train_step_ragged_shapes_vs_oracle(dev, gemm_mode, B, N):
+    """Shapes that are not multiples of the 128-row tiles (and a batch of one), seeded random weights, both GEMM engines,
+    against the float64 oracle: loss, log-probabilities, head gradients, BatchNorm buffers, and the Adam update."""
+    from oracle import oracle as orc
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+    from pointnet12_b200.train import FlatAdam, cross_entropy, semseg_forward_train
+
+    torch.manual_seed(77)
+    net = PointNet2SemSeg(19, feature_dims=1)
+    sd0 = orc.numpy_state_dict(net.state_dict())
+    net = net.to(dev).train()
+    opt = FlatAdam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    rng = np.random.default_rng(B * 1000 + N)
+    pts = syn.kitti_batch(B, N, config=5)
+    target = rng.integers(0, 19, (B, N))
+    starts = [rng.integers(0, n, B) for n in (N, 1024, 256, 64)]
+    keep = rng.integers(0, 2, (B * N, 128)).astype(np.uint8)
+    logp = semseg_forward_train(net, T(pts, dev), fps_starts=[T(s, dev) for s in starts], dropout_mask=T(keep, dev))
+    loss = cross_entropy(logp, T(target, dev))
+    opt.zero_grad()
+    loss.backward()
+    want = tor.semseg_train_step(sd0, pts, target, starts, keep)
+    assert abs(loss.item() - want["loss"]) < 2e-4
+    assert rl2(logp.detach().cpu().numpy(), want["logp"]) < 3e-4
+    grads = _grads(net)
+    for name in ("conv2.weight", "conv2.bias"):
+        assert rl2(grads[name], want["grads"][name]) < 2e-3, (name, rl2(grads[name], want["grads"][name]))
+    # sums of random-sign terms over the rows, gated by a ReLU mask: ONE mask flip (an activation within the engines' 1e-5
+    # rounding difference of zero) moves such a sum by 1/sqrt(rows) ~ 2e-2 of its size
+    flip_tol = 2e-3 if gemm_mode == "fp32" else 5e-2
+    for name in ("bn1.weight", "bn1.bias"):
+        assert rl2(grads[name], want["grads"][name]) < flip_tol, (name, rl2(grads[name], want["grads"][name]))
+    # deeper gradients: every arg-max / ReLU flip on the way down moves whole gradient rows (few rows at sa4: 16 centroids per
+    # cloud).  Exact-fp32 engine: within 5e-2 in L2; tensor-core engine (more flips): direction within 0.98 cosine.
+    for name in ("conv1.weight", "fp1.mlp_convs.2.weight", "sa4.mlp_convs.0.weight", "sa1.mlp_convs.0.weight"):
+        a_, b_ = grads[name].astype(np.float64).reshape(-1), np.asarray(want["grads"][name], np.float64).reshape(-1)
+        if gemm_mode == "fp32":
+            assert rl2(a_, b_) < 5e-2, (name, rl2(a_, b_))
+        else:
+            cos = float(a_ @ b_ / (np.linalg.norm(a_) * np.linalg.norm(b_)))
+            assert cos > 0.98 and abs(np.linalg.norm(a_) / np.linalg.norm(b_) - 1) < 0.1, (name, cos)
+    for name, buf in net.named_buffers():
+        if name.endswith("num_batches_tracked"):
+            assert int(buf) == 1
+        else:
+            ref = want["buffers"][name]
+            assert np.abs(buf.cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), name
+    # the optimizer step on the flat buffer == torch.optim.Adam's formula applied to our gradients
+    before = {n: p.detach().cpu().numpy().astype(np.float64) for n, p in net.named_parameters()}
+    opt.step()
+    for name in ("conv2.weight", "sa3.mlp_bns.1.bias", "fp2.mlp_convs.0.weight"):
+        p_new, _, _ = tor.adam_step(before[name], grads[name], 0.0, 0.0, 1)
+        got = dict(net.named_parameters())[name].detach().cpu().numpy()
+        assert np.abs(got - p_new).max() < 2e-6, name
