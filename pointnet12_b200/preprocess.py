@@ -51,6 +51,8 @@ class ScanPreprocessor:
         self.bounds = (float(np.float32(-self.H_FOV[1] * np.pi / 180)), float(np.float32(-self.H_FOV[0] * np.pi / 180)),
                        float(np.float32(self.V_FOV[0] * np.pi / 180)), float(np.float32(self.V_FOV[1] * np.pi / 180)))
         self._calls = 0
+        self._stage = {}                 # grow-only pinned staging buffers (pinning memory costs milliseconds per call otherwise)
+        self._seed_ring, self._seed_slot = None, 0
 
     def upload(self, points: Sequence[np.ndarray], raw_labels: Sequence[np.ndarray]) -> ScanBatch:
         if len(points) != len(raw_labels) or not points:
@@ -60,8 +62,15 @@ class ScanPreprocessor:
             if p.ndim != 2 or p.shape[1] != 4 or l.shape[0] != p.shape[0]:
                 raise ValueError("Scan and Label don't contain same number of points")     # kitti_utils.py:210
         total = sum(lengths)
-        hp = torch.empty((total, 4), dtype=torch.float32).pin_memory()
-        hl = torch.empty((total,), dtype=torch.int32).pin_memory()
+        # pinned staging, reused across calls once the copy that last read it has completed
+        st = self._stage
+        if st.get("cap", 0) < total:
+            cap = int(total * 1.25) + 1024
+            st.update(cap=cap, points=torch.empty((cap, 4), dtype=torch.float32).pin_memory(),
+                      labels=torch.empty((cap,), dtype=torch.int32).pin_memory(), event=None)
+        if st["event"] is not None:
+            st["event"].synchronize()
+        hp, hl = st["points"][:total], st["labels"][:total]
         o = 0
         for p, l, n in zip(points, raw_labels, lengths):
             hp[o:o + n] = torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32))
@@ -71,8 +80,28 @@ class ScanPreprocessor:
         b.points = hp.to(self.device, non_blocking=True)
         b.raw_label = hl.to(self.device, non_blocking=True)
         b.offsets = torch.tensor([0] + list(np.cumsum(lengths)), dtype=torch.int64).to(self.device)
+        st["event"] = torch.cuda.Event()
+        st["event"].record(torch.cuda.current_stream(self.device))
         b.lengths, b.B, b.max_points = lengths, len(lengths), max(lengths)
         return b
+
+    def _seed(self) -> torch.Tensor:
+        """{seed, offset} of this call's Philox stream on the device, sent through a small ring of pinned buffers (no
+        synchronous pageable copy on the way)."""
+        if self._seed_ring is None:
+            self._seed_ring = [(torch.zeros((2,), dtype=torch.int64).pin_memory(), torch.zeros((2,), dtype=torch.int64, device=self.device),
+                                [None]) for _ in range(8)]
+        self._seed_slot = (self._seed_slot + 1) % len(self._seed_ring)
+        host, dev, ev = self._seed_ring[self._seed_slot]
+        if ev[0] is not None:
+            ev[0].synchronize()
+        self._calls += 1
+        host[0] = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        host[1] = self._calls
+        dev.copy_(host, non_blocking=True)
+        ev[0] = torch.cuda.Event()
+        ev[0].record(torch.cuda.current_stream(self.device))
+        return dev
 
     def filter(self, batch: ScanBatch) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (kept int32 [total]: per scan the indices of its kept points in file order, kept_count int32 [B])."""
@@ -97,8 +126,7 @@ class ScanPreprocessor:
         labels = torch.empty((batch.B, int(npoints)), dtype=torch.int64, device=self.device)
         seed = None
         if choice is None or (train and noise is None):
-            self._calls += 1
-            seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, self._calls], dtype=torch.int64).to(self.device)
+            seed = self._seed()
         if choice is not None:
             choice = ops._i64(choice, "choice")
         if noise is not None:

@@ -33,10 +33,13 @@ def main():
     dev = torch.device("cuda", 0)
     scans = [syn.raw_scan(args.raw, 7300 + i) for i in range(args.scans)]
     pre = ScanPreprocessor(syn.SEMANTIC_KITTI_LEARNING_MAP, "inview", dev)
-    t0 = time.perf_counter()
-    batch = pre.upload([p for p, _ in scans], [l for _, l in scans])
-    torch.cuda.synchronize()
-    upload_ms = (time.perf_counter() - t0) * 1e3
+    ups = []
+    for _ in range(4):                                   # the first call allocates the pinned staging buffers
+        t0 = time.perf_counter()
+        batch = pre.upload([p for p, _ in scans], [l for _, l in scans])
+        torch.cuda.synchronize()
+        ups.append((time.perf_counter() - t0) * 1e3)
+    upload_ms = float(np.median(ups[1:]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     times = []
     for it in range(55):
@@ -67,7 +70,7 @@ def main():
                       "ms_per_batch": ms, "config": {"workload": f"{args.scans} raw scans x {args.raw} points -> [{args.scans}, 4, {args.npoints}] "
                                                      "+ labels (train: jitter on), inputs resident", "kept_points": kept},
                       "algorithmic_bytes": algo, "achieved_GBps": algo / (ms * 1e-3) / 1e9, "measured_peaks": peak,
-                      "upload_ms_pageable_to_device": upload_ms,
+                      "upload_ms_numpy_to_device": upload_ms, "upload_ms_first_call": ups[0],
                       "cpu_oracle_ms_per_scan": cpu_ms, "cpu_oracle_ms_per_batch_estimate": cpu_ms * args.scans}))
 
 
