@@ -53,9 +53,9 @@ def parse():
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch of the critical-path kernels")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
                     help="bf16x3 (default, fp32 parity), bf16 (single-pass, stated tolerance) or fp32 (CUDA cores)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "train"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "train", "preprocess"],
                     help="c2 (default): the headline eval forward; train: config C5, one training iteration per step "
-                         "(tools/bench_train.py; same JSON contract)")
+                         "(tools/bench_train.py; same JSON contract); preprocess: raw scans -> network input (tools/bench_preprocess.py)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: one CUDA-graph replay per step (default); eager: ~40 launches per step")
     return ap.parse_args()
@@ -373,14 +373,63 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def cpu_train_oracle(B=2, N=2048):
+    """The float64 numpy oracle of one training iteration (oracle/train_oracle.py) on a bounded sample: points/s."""
+    import numpy as np
+    import torch
+
+    from oracle import oracle as orc
+    from oracle import train_oracle as tor
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+
+    torch.manual_seed(1234)
+    sd = orc.numpy_state_dict(PointNet2SemSeg(19, feature_dims=1).state_dict())
+    pts = syn.kitti_batch(B, N, config=5)
+    rng = np.random.default_rng(0)
+    target = rng.integers(0, 19, (B, N))
+    starts = [rng.integers(0, n, B) for n in (N, 1024, 256, 64)]
+    keep = rng.integers(0, 2, (B * N, 128))
+    t0 = time.perf_counter()
+    tor.semseg_train_step(sd, pts, target, starts, keep)
+    dt = time.perf_counter() - t0
+    return {"value": B * N / dt, "unit": "points/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"one training iteration (forward, loss, backward) of {B} clouds x {N} points, numpy float64 oracle "
+                      f"(BLAS threads) + C/OpenMP geometry, {dt:.2f} s"}
+
+
+def cpu_preprocess_oracle(scan, npoints, scans):
+    """CPU leg of --workload preprocess: the numpy restatement of the reference's loader path on ONE raw scan."""
+    import numpy as np
+
+    from oracle import preprocess_oracle as por
+    from pointnet12_b200 import synthetic as syn
+
+    t0 = time.perf_counter()
+    k, _ = por.scan_filter(*scan, syn.SEMANTIC_KITTI_LEARNING_MAP)
+    rng = np.random.default_rng(0)
+    por.scan_sample(*scan, syn.SEMANTIC_KITTI_LEARNING_MAP, npoints, rng.integers(0, len(k), npoints),
+                    noise=np.zeros((len(k), 4), np.float32))
+    ms = (time.perf_counter() - t0) * 1e3
+    return {"value": scan[0].shape[0] / (ms * 1e-3), "unit": "points/s", "cores": 1, "kind": "port",
+            "sample": f"one raw scan of {scan[0].shape[0]} points through oracle/preprocess_oracle.py (numpy), {ms:.1f} ms; "
+                      f"a batch of {scans} scans = {ms * scans:.0f} ms"}
+
+
 def main():
     args = parse()
-    if args.workload == "train" and args.impl == "ours":
+    if args.workload in ("train", "preprocess") and args.impl == "ours":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
+        if args.workload == "preprocess":
+            import bench_preprocess
+
+            bench_preprocess.main([], cpu_baseline=None if args.no_cpu_baseline else cpu_preprocess_oracle)
+            return
         import bench_train
 
         bench_train.main(["--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--eager"] if args.mode == "eager" else [])
-                         + (["--no-cpu-baseline"] if args.no_cpu_baseline else []))
+                         + (["--no-cpu-baseline"] if args.no_cpu_baseline else []),
+                         cpu_baseline=None if args.no_cpu_baseline else cpu_train_oracle)
         return
     if args.impl == "reference":
         run_reference(args)

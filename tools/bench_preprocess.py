@@ -5,7 +5,7 @@
 Prints one JSON line: raw points/s through filter + sample (CUDA events, median of 50, 256 MiB written between
 iterations), the algorithmic HBM traffic (every raw point and label read twice -- count pass and scatter pass -- plus the
 kept-index list and the outputs) against the measured copy peak, the host-to-device staging time of the raw scans, and
-the CPU oracle (numpy restatement of the reference's loader) on one scan for comparison.
+(when launched through `python bench.py --workload preprocess`, whose CPU leg may execute oracle/) the numpy oracle on one scan.
 """
 import argparse
 import json
@@ -20,13 +20,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(argv=None, cpu_baseline=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--scans", type=int, default=8)
     ap.add_argument("--raw", type=int, default=120000)
     ap.add_argument("--npoints", type=int, default=24000)
-    args = ap.parse_args()
-    from oracle import preprocess_oracle as por
+    args = ap.parse_args(argv)
     from pointnet12_b200 import synthetic as syn
     from pointnet12_b200.preprocess import ScanPreprocessor
 
@@ -60,18 +59,13 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    t0 = time.perf_counter()
-    k, _ = por.scan_filter(*scans[0], syn.SEMANTIC_KITTI_LEARNING_MAP)
-    rng = np.random.default_rng(0)
-    por.scan_sample(*scans[0], syn.SEMANTIC_KITTI_LEARNING_MAP, args.npoints, rng.integers(0, len(k), args.npoints),
-                    noise=np.zeros((len(k), 4), np.float32))
-    cpu_ms = (time.perf_counter() - t0) * 1e3
+    cpu = cpu_baseline(scans[0], args.npoints, args.scans) if cpu_baseline is not None else None
     print(json.dumps({"metric": "scan_preprocess_raw_points_per_sec", "value": raw_total / (ms * 1e-3), "unit": "points/s",
                       "ms_per_batch": ms, "config": {"workload": f"{args.scans} raw scans x {args.raw} points -> [{args.scans}, 4, {args.npoints}] "
                                                      "+ labels (train: jitter on), inputs resident", "kept_points": kept},
                       "algorithmic_bytes": algo, "achieved_GBps": algo / (ms * 1e-3) / 1e9, "measured_peaks": peak,
                       "upload_ms_numpy_to_device": upload_ms, "upload_ms_first_call": ups[0],
-                      "cpu_oracle_ms_per_scan": cpu_ms, "cpu_oracle_ms_per_batch_estimate": cpu_ms * args.scans}))
+                      "cpu_baseline": cpu}))
 
 
 if __name__ == "__main__":

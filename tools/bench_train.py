@@ -6,7 +6,9 @@
 A step = forward in train() mode (batch-statistics BatchNorm, dropout) + the reference's loss + backward + gradient
 all-reduce (NCCL, one flat 3.9 MB buffer; skipped at N=1) + Adam, all through the package's public training API
 (pointnet12_b200.train).  Inputs resident; CUDA events around every step; MAX over ranks.  Prints one JSON line
-(rank 0) with points/s, ms/step and the per-phase split of an extra instrumented step.
+(rank 0) with points/s, ms/step, e2e, clocks and the live roofline of the dominant kernel.  The CPU leg (`cpu_baseline`: the
+float64 oracle of the iteration) is supplied by bench.py -- `python bench.py --workload train` -- because only bench.py's CPU legs
+may execute oracle/; run directly, this tool reports "cpu_baseline": null.
 """
 import argparse
 import json
@@ -20,31 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def cpu_train_oracle(B=2, N=2048):
-    """The float64 numpy oracle of one training iteration (oracle/train_oracle.py) on a bounded sample: points/s."""
-    import time
-
-    from oracle import oracle as orc
-    from oracle import train_oracle as tor
-    from pointnet12_b200 import synthetic as syn
-    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
-
-    torch.manual_seed(1234)
-    sd = orc.numpy_state_dict(PointNet2SemSeg(19, feature_dims=1).state_dict())
-    pts = syn.kitti_batch(B, N, config=5)
-    rng = np.random.default_rng(0)
-    target = rng.integers(0, 19, (B, N))
-    starts = [rng.integers(0, n, B) for n in (N, 1024, 256, 64)]
-    keep = rng.integers(0, 2, (B * N, 128))
-    t0 = time.perf_counter()
-    tor.semseg_train_step(sd, pts, target, starts, keep)
-    dt = time.perf_counter() - t0
-    return {"value": B * N / dt, "unit": "points/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": f"one training iteration (forward, loss, backward) of {B} clouds x {N} points, numpy float64 oracle "
-                      f"(BLAS threads) + C/OpenMP geometry, {dt:.2f} s"}
-
-
-def main(argv=None):
+def main(argv=None, cpu_baseline=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
@@ -194,7 +172,7 @@ def main(argv=None):
             "e2e": {"value": world * B * N / (float(e2e_total.item()) / args.steps * 1e-3), "unit": "points/s",
                     "ms_per_step": float(e2e_total.item()) / args.steps,
                     "h2d_bytes_per_step": int(host_pts.numel() * 4 + host_tgt.numel() * 8), "d2h_bytes_per_step": 4},
-            "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else cpu_train_oracle(),
+            "cpu_baseline": None if (args.no_cpu_baseline or world > 1 or cpu_baseline is None) else cpu_baseline(),
             "phases_ms_eager": phases, "gpu_launches": int(launches), "final_loss": float(loss.item())}))
     if world > 1:
         dist.destroy_process_group()
