@@ -43,11 +43,21 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// PN12_GEMM_SPIN (compile-time experiment): busy-poll with test_wait instead of the potentially suspending try_wait.
+// Measured on B200: no difference (33.2 vs 33.0 us per 128 x 128 layer), so the suspending wait stays.
+#ifndef PN12_GEMM_SPIN
+#define PN12_GEMM_SPIN 0
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned done = 0;
     while (!done) {
+#if PN12_GEMM_SPIN
+        asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#else
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
     }
 }
 __device__ __forceinline__ bool elect() {
