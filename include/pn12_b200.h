@@ -343,7 +343,15 @@ int pn_grad_weight_bn_bf16x3(const float* dy, int64_t lddy, const float* x, int6
  * tells whether the layer fits (cout <= 256, padded cin*cout*4 <= 128 KB); wider layers use pn_mlp_rows_bf16x3. */
 int pn_train_gemm_supported(int cin, int cout);
 /* w_scratch: caller-owned device buffer of pn_train_gemm_scratch_bytes(cin, cout) bytes, 128-byte aligned: the call first
- * converts the weights into it (bf16 hi + lo in the kernel's shared-memory layout), then every CTA fetches that image. */
+ * converts the weights into it (bf16 hi + lo in the kernel's shared-memory layout), then every CTA fetches that image.
+ * w == NULL: w_scratch already holds the image -- pn_train_pack_many converts the weights of MANY layers (a table of
+ * pn_train_pack_item in DEVICE memory; `transposed` as w_transposed) in one launch, e.g. once per training iteration. */
+typedef struct pn_train_pack_item {
+    const float* w; /* [cout, cin] row-major, or its transpose [cin, cout] when transposed != 0 */
+    void* out;      /* pn_train_gemm_scratch_bytes(cin, cout) bytes, 128-byte aligned */
+    int cin, cout, transposed, reserved;
+} pn_train_pack_item;
+int pn_train_pack_many(const pn_train_pack_item* items, int n_items, int max_cin, int max_cout, pn_stream_t stream);
 size_t pn_train_gemm_scratch_bytes(int cin, int cout);
 int pn_train_gemm_bf16x3(const float* x, int64_t ldx, int64_t rows, int cin, const float* in_scale, const float* in_shift,
                          int in_relu, const float* w, int w_transposed, const float* bias, int cout, float* y, int64_t ldy,

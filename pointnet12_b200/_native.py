@@ -81,6 +81,7 @@ _SIGNATURES = {
     "pn_grad_weight_set_ctas_per_sm": [i32],
     "pn_grad_weight_bn_bf16x3": [vp, i64, vp, i64, vp, vp, i32, i64, i32, i32, vp, i64, vp, vp],
     "pn_train_gemm_supported": [i32, i32],
+    "pn_train_pack_many": [vp, i32, i32, i32, vp],
     "pn_train_gemm_bf16x3": [vp, i64, i64, i32, vp, vp, i32, vp, i32, vp, i32, vp, i64, vp, vp, vp, vp],
     "pn_train_gemm_bnbwd_bf16x3": [vp, i64, i64, i32, vp, i32, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "pn_transpose_f32": [vp, i32, i32, vp, vp],

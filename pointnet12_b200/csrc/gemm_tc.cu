@@ -164,6 +164,31 @@ __global__ void train_pack_kernel(const float* __restrict__ w, int w_transposed,
     }
 }
 
+// The same for MANY layers in one launch (blockIdx.y = item): all weights of a network, both orientations, packed once per
+// training iteration instead of once per GEMM call.
+__global__ void train_pack_many_kernel(const pn_train_pack_item* __restrict__ items) {
+    const pn_train_pack_item it = items[blockIdx.y];
+    const int k_pad = (it.cin + KC - 1) / KC * KC, n_pad = (it.cout + 31) / 32 * 32;
+    const int kblocks = k_pad / 8;
+    const unsigned w_chunk_bytes = (unsigned)n_pad * KC * 4;
+    unsigned char* out = static_cast<unsigned char*>(it.out);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_pad * kblocks; e += gridDim.x * blockDim.x) {
+        const int n = it.transposed ? e % n_pad : e / kblocks, kb = it.transposed ? e / n_pad : e % kblocks;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kb * 8 + j;
+            float t = 0.0f;
+            if (n < it.cout && k < it.cin) t = it.transposed ? __ldg(it.w + (int64_t)k * it.cout + n) : __ldg(it.w + (int64_t)n * it.cin + k);
+            v[j] = t;
+        }
+        const int c = kb / (KC / 8), kbi = kb % (KC / 8);
+        unsigned char* img = out + (size_t)c * w_chunk_bytes;
+        const unsigned off = (unsigned)(n >> 3) * (KC / 8) * 128u + (unsigned)kbi * 128u + (unsigned)(n & 7) * 16u;
+        store_split8(img, img + (size_t)n_pad * KC * 2, off, v);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 train_gemm_kernel(const Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -471,6 +496,17 @@ PN_EXPORT int pn_train_gemm_supported(int cin, int cout) {
     return n_pad <= 256 && (size_t)k_pad * n_pad * 4 <= (size_t)W_MAX_BYTES;
 }
 
+PN_EXPORT int pn_train_pack_many(const pn_train_pack_item* items, int n_items, int max_cin, int max_cout, pn_stream_t stream) {
+    using namespace pn;
+    using namespace pn::gemm;
+    PN_REQUIRE(items && n_items > 0 && n_items <= 65535 && max_cin > 0 && max_cout > 0, PN_ERR_BAD_ARG, "pn_train_pack_many: bad arguments");
+    const int entries = round_up(max_cout, 32) * (round_up(max_cin, KC) / 8);
+    int bx = (entries + 255) / 256;
+    if (bx > 16) bx = 16;
+    train_pack_many_kernel<<<dim3((unsigned)bx, (unsigned)n_items), 256, 0, (cudaStream_t)stream>>>(items);
+    return finish_launch("pn_train_pack_many");
+}
+
 PN_EXPORT size_t pn_train_gemm_scratch_bytes(int cin, int cout) {
     using namespace pn::gemm;
     if (!pn_train_gemm_supported(cin, cout)) return 0;
@@ -507,7 +543,7 @@ static int train_gemm_launch(const float* x, int64_t ldx, int64_t rows, int cin,
                              const float* p_shift, const float* p_mean, const float* p_invstd, void* w_scratch, pn_stream_t stream) {
     using namespace pn;
     using namespace pn::gemm;
-    PN_REQUIRE(x && w && y && w_scratch, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: null pointer");
+    PN_REQUIRE(x && y && w_scratch, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: null pointer");
     PN_REQUIRE(((uintptr_t)w_scratch & 127) == 0, PN_ERR_ALIGNMENT, "pn_train_gemm_bf16x3: w_scratch must be 128-byte aligned");
     PN_REQUIRE(rows > 0 && cin > 0 && cout > 0 && ldx >= cin && ldy >= cout, PN_ERR_BAD_ARG, "pn_train_gemm_bf16x3: bad shape");
     PN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr) && (col_sum == nullptr) == (col_sumsq == nullptr), PN_ERR_BAD_ARG,
@@ -560,7 +596,7 @@ static int train_gemm_launch(const float* x, int64_t ldx, int64_t rows, int cin,
         smem_set = smem;
     }
     a.w_packed = static_cast<const unsigned char*>(w_scratch);
-    {
+    if (w) {      // w == NULL: w_scratch already holds the image (pn_train_pack_many at the start of the iteration)
         const int items = a.n_pad * (a.k_pad / 8);
         train_pack_kernel<<<(items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, w_transposed, cin, cout, a.k_pad, a.n_pad,
                                                                                 static_cast<unsigned char*>(w_scratch));

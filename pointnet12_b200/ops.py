@@ -689,7 +689,8 @@ def train_gemm_supported(cin: int, cout: int) -> bool:
 
 
 def train_gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], in_stats: Optional[BatchStats] = None,
-               in_relu: bool = True, stats_acc: Optional[torch.Tensor] = None, transposed: bool = False) -> torch.Tensor:
+               in_relu: bool = True, stats_acc: Optional[torch.Tensor] = None, transposed: bool = False,
+               packed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """pn_train_gemm_bf16x3: y = f(x) @ W^T + bias with f = the normalise(+ReLU) of the layer that produced x (in_stats:
     its BatchStats; None = identity), column sums of y / y*y added to stats_acc (float64 [2, cout], zeroed by the caller).
     W = w [cout, cin], or w^T for w [cin, cout] when transposed."""
@@ -700,17 +701,20 @@ def train_gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], i
     if (w.shape[0] if transposed else w.shape[1]) != cin:
         raise ValueError(f"weight shape {tuple(w.shape)} does not match {cin} input channels")
     y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
-    scratch = torch.empty((int(nv.lib().pn_train_gemm_scratch_bytes(cin, cout)),), dtype=torch.uint8, device=x.device)
+    # packed: the weight image already converted by pn_train_pack_many (train.PackedWeights); else converted by this call
+    scratch = packed if packed is not None else torch.empty((int(nv.lib().pn_train_gemm_scratch_bytes(cin, cout)),),
+                                                            dtype=torch.uint8, device=x.device)
     with _on_device(x):
         nv.call("pn_train_gemm_bf16x3", x.data_ptr(), _ld(x), rows, cin, _p(in_stats.scale) if in_stats is not None else None,
-                _p(in_stats.shift) if in_stats is not None else None, int(in_relu), w.data_ptr(), int(transposed), _p(bias), cout,
+                _p(in_stats.shift) if in_stats is not None else None, int(in_relu), None if packed is not None else w.data_ptr(),
+                int(transposed), _p(bias), cout,
                 y.data_ptr(), cout, _p(stats_acc[0]) if stats_acc is not None else None,
                 _p(stats_acc[1]) if stats_acc is not None else None, scratch.data_ptr(), _stream(), tag=(rows, cin, cout))
     return y
 
 
 def train_gemm_bnbwd(dy: torch.Tensor, w: torch.Tensor, prev_y: torch.Tensor, prev_st: BatchStats, acc: torch.Tensor,
-                     transposed: bool = True) -> torch.Tensor:
+                     transposed: bool = True, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """pn_train_gemm_bnbwd_bf16x3: dz = dy @ W (w [cout_layer, cin_layer] given as stored, transposed=True) plus, in the
     epilogue, the two reductions of the BatchNorm backward of the layer BELOW (pre-normalisation output prev_y, statistics
     prev_st) into acc (float64 [2, C], zeroed): bn_act_backward(..., acc=acc, acc_ready=True) then skips its own pass."""
@@ -722,9 +726,11 @@ def train_gemm_bnbwd(dy: torch.Tensor, w: torch.Tensor, prev_y: torch.Tensor, pr
     if prev_y.shape != (rows, cout):
         raise ValueError("prev_y must be [rows, cout]")
     dz = torch.empty((rows, cout), dtype=torch.float32, device=dy.device)
-    scratch = torch.empty((int(nv.lib().pn_train_gemm_scratch_bytes(cin, cout)),), dtype=torch.uint8, device=dy.device)
+    scratch = packed if packed is not None else torch.empty((int(nv.lib().pn_train_gemm_scratch_bytes(cin, cout)),),
+                                                            dtype=torch.uint8, device=dy.device)
     with _on_device(dy):
-        nv.call("pn_train_gemm_bnbwd_bf16x3", dy.data_ptr(), _ld(dy), rows, cin, w.data_ptr(), int(transposed), cout, dz.data_ptr(),
+        nv.call("pn_train_gemm_bnbwd_bf16x3", dy.data_ptr(), _ld(dy), rows, cin, None if packed is not None else w.data_ptr(),
+                int(transposed), cout, dz.data_ptr(),
                 cout, prev_y.data_ptr(), _ld(prev_y), prev_st.scale.data_ptr(), prev_st.shift.data_ptr(), prev_st.mean.data_ptr(),
                 prev_st.invstd.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(), scratch.data_ptr(), _stream())
     return dz

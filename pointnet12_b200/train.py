@@ -36,13 +36,67 @@ def _w2d(conv) -> torch.Tensor:
     return conv.weight.detach().reshape(conv.weight.shape[0], -1)
 
 
-def _gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], transposed: bool = False) -> torch.Tensor:
+class PackedWeights:
+    """The conv weights of a network in the fused GEMM's shared-memory layout (bf16 hi + lo), both orientations (W for the
+    forward, W^T for the input gradient), converted by ONE launch per training iteration (pn_train_pack_many) instead of one
+    small launch in front of every GEMM.  lookup() returns the image of a weight, or None when it is not in the arena or the
+    parameter's storage has moved since (the GEMM then converts the weight itself)."""
+
+    def __init__(self, convs):
+        import numpy as np
+
+        from . import _native as nv
+
+        items, self.slots, total = [], {}, 0
+        for conv in convs:
+            co, ci = int(conv.weight.shape[0]), int(conv.weight[0].numel())
+            for tr in (False, True):
+                cin, cout = (co, ci) if tr else (ci, co)
+                if not ops.train_gemm_supported(cin, cout):
+                    continue
+                nbytes = int(nv.lib().pn_train_gemm_scratch_bytes(cin, cout))
+                items.append((conv.weight, total, nbytes, cin, cout, tr))
+                total += (nbytes + 127) // 128 * 128
+        self.n = len(items)
+        if not self.n:
+            return
+        dev = items[0][0].device
+        self.arena = torch.empty((total,), dtype=torch.uint8, device=dev)
+        table = np.zeros(self.n, dtype=[("w", "<u8"), ("out", "<u8"), ("cin", "<i4"), ("cout", "<i4"), ("tr", "<i4"), ("res", "<i4")])
+        for i, (w, off, nbytes, cin, cout, tr) in enumerate(items):
+            table[i] = (w.data_ptr(), self.arena.data_ptr() + off, cin, cout, int(tr), 0)
+            self.slots[(w.data_ptr(), tr)] = self.arena[off:off + nbytes]
+        self.table = torch.from_numpy(table.view(np.uint8).copy()).to(dev)
+        self.max_cin, self.max_cout = max(i[3] for i in items), max(i[4] for i in items)
+        self._ptrs = [(w, w.data_ptr()) for w, *_ in items]
+
+    def valid(self) -> bool:
+        return self.n > 0 and all(w.data_ptr() == p for w, p in self._ptrs)
+
+    def pack(self) -> None:
+        from . import _native as nv
+
+        with ops._on_device(self.arena):
+            nv.call("pn_train_pack_many", self.table.data_ptr(), self.n, self.max_cin, self.max_cout, ops._stream())
+
+    def lookup(self, w: torch.Tensor, transposed: bool):
+        return self.slots.get((w.data_ptr(), bool(transposed)))
+
+
+def _net_convs(net):
+    convs = []
+    for m in (net.sa1, net.sa2, net.sa3, net.sa4, net.fp4, net.fp3, net.fp2, net.fp1):
+        convs += list(m.mlp_convs)
+    return convs + [net.conv1, net.conv2]
+
+
+def _gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], transposed: bool = False, arena=None) -> torch.Tensor:
     """x [rows, cin] @ W^T + bias with W = w [cout, cin] (or, transposed=True, W = w^T for w [cin, cout]: the input-
     gradient GEMM dx = dy W of a conv with weight w).  Tensor cores (single-layer tcgen05 chain, 3-pass split bf16 = fp32
     parity; the weight is re-packed on every call because it changes every iteration) unless the MLP mode is 'fp32'."""
     cout, cin = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
     if ops.mlp_mode() == "bf16x3" and FUSED_BN and ops.train_gemm_supported(cin, cout):
-        return ops.train_gemm(x, w, bias, transposed=transposed)      # weights converted in-kernel: no pack launch
+        return ops.train_gemm(x, w, bias, transposed=transposed, packed=arena.lookup(w, transposed) if arena is not None else None)
     if ops.mlp_mode() == "bf16x3" and ops.PackedChain.supported([(cin, cout)]):
         return ops.mlp_rows_tc(ops.PackedChain([(w, bias, False)], transposed=transposed), x)
     return ops.linear(x, ops.transpose(w) if transposed else w, bias, relu=False)
@@ -58,10 +112,11 @@ def _grad_sink(p: torch.Tensor, shape) -> Tuple[torch.Tensor, bool]:
 
 
 FUSED_BN = os.environ.get("PN12_TRAIN_FUSED", "1") != "0"     # BatchNorm fused into the training GEMMs (pn_train_gemm_bf16x3)
+PACK_ONCE = os.environ.get("PN12_TRAIN_PACK_ONCE", "1") != "0"      # all weight images converted by one launch per iteration
 FUSED_BN_BWD = os.environ.get("PN12_TRAIN_FUSED_BWD", "0") != "0"   # BatchNorm-backward reductions in the input-gradient GEMM's epilogue
 
 
-def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] = None):
+def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] = None, arena=None):
     """x [rows, cin] -> (output, saved).  layers = [(conv, bn or None, relu)]; pool_K: the last layer's activation is
     max-pooled over runs of K rows (set abstraction).
 
@@ -84,14 +139,15 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] 
             raise NotImplementedError("training path: BatchNorm layers are followed by ReLU in every supported block")
         if fused:
             acc = accs[li, :, :w.shape[0]]
-            y = ops.train_gemm(x, w, bias, in_stats=pending, stats_acc=acc)
+            y = ops.train_gemm(x, w, bias, in_stats=pending, stats_acc=acc,
+                               packed=arena.lookup(conv.weight, False) if arena is not None else None)
             st = ops.bn_finalize(acc, rows, bn)
             saved.append((x, pending, y, st, relu, None))
             x, pending = y, st
             continue
         if pending is not None:                      # a layer the fused kernel does not take: materialise its input first
             x, pending = ops.bn_act(x, pending, True), None
-        y = _gemm(x, w, bias)
+        y = _gemm(x, w, bias, arena=arena)
         if bn is not None:
             st = ops.bn_batch_stats(y, bn)
             saved.append((x, None, y, st, relu, None))
@@ -113,7 +169,7 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] 
     return x, saved
 
 
-def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optional[int], need_dx: bool):
+def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optional[int], need_dx: bool, arena=None):
     """-> (dx or None, [per layer: (dW [Co,Ci], db, dgamma, dbeta)]; None where the gradient went straight into p.grad)."""
     grads = [None] * len(layers)
     widest = max(c.weight.shape[0] for c, _, _ in layers)
@@ -141,10 +197,11 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
                 and ops.train_gemm_supported(w.shape[0], w.shape[1])):
             # the layer below kept only its pre-normalisation output (x here): the input-gradient GEMM also accumulates the
             # two reductions of THAT layer's BatchNorm backward in its epilogue, saving a pass over dz and x
-            dz = ops.train_gemm_bnbwd(dy, w, x, x_stats, accs[li - 1, :, :w.shape[1]])
+            dz = ops.train_gemm_bnbwd(dy, w, x, x_stats, accs[li - 1, :, :w.shape[1]],
+                                      packed=arena.lookup(conv.weight, True) if arena is not None else None)
             stats_done = True
         else:
-            dz = _gemm(dy, w, None, transposed=True) if (li > 0 or need_dx) else None
+            dz = _gemm(dy, conv.weight.detach().reshape(w.shape), None, transposed=True, arena=arena) if (li > 0 or need_dx) else None
     return dz, grads
 
 
@@ -187,7 +244,8 @@ class SetAbstractionFn(torch.autograd.Function):
         layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
         grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=False, pad4=True)          # [B,S,K,ld]
         x0 = grouped.view(B * S * K, -1)[:, :3 + D]
-        pooled, saved = mlp_forward(x0, layers, pool_K=K)
+        ctx.arena = getattr(mod, "_pn_arena", None)
+        pooled, saved = mlp_forward(x0, layers, pool_K=K, arena=ctx.arena)
         ctx.mod, ctx.saved, ctx.idx, ctx.geom = mod, saved, idx, (B, xyz_pm.shape[1], S, K, D)
         return pooled.view(B, S, -1)
 
@@ -197,7 +255,7 @@ class SetAbstractionFn(torch.autograd.Function):
         B, N, S, K, D = ctx.geom
         layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
         need_dx = D > 0 and ctx.needs_input_grad[2]
-        dx0, grads = mlp_backward(ctx.saved, layers, _rows_of(dpooled, dpooled.shape[-1]), K, need_dx)
+        dx0, grads = mlp_backward(ctx.saved, layers, _rows_of(dpooled, dpooled.shape[-1]), K, need_dx, arena=ctx.arena)
         dpts = ops.group_backward(dx0, 3, D, ctx.idx, N) if need_dx else None
         ctx.saved = None
         return (None, None, dpts, None, None, *_layer_grads(layers, grads))
@@ -212,7 +270,8 @@ class FeaturePropagationFn(torch.autograd.Function):
         B, N, _ = idx.shape
         layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
         x0 = ops.three_interpolate(p1, p2, idx, w).view(B * N, -1)
-        out, saved = mlp_forward(x0, layers)
+        ctx.arena = getattr(mod, "_pn_arena", None)
+        out, saved = mlp_forward(x0, layers, arena=ctx.arena)
         ctx.mod, ctx.saved, ctx.nn = mod, saved, (idx, w)
         ctx.geom = (B, N, p2.shape[1], p1.shape[2] if p1 is not None else 0, p2.shape[2])
         return out.view(B, N, -1)
@@ -222,7 +281,7 @@ class FeaturePropagationFn(torch.autograd.Function):
         mod = ctx.mod
         B, N, S, D1, D2 = ctx.geom
         layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
-        dx0, grads = mlp_backward(ctx.saved, layers, _rows_of(dout, dout.shape[-1]), None, True)
+        dx0, grads = mlp_backward(ctx.saved, layers, _rows_of(dout, dout.shape[-1]), None, True, arena=ctx.arena)
         dp1, dp2 = ops.three_interpolate_backward(dx0, D1, D2, ctx.nn[0], ctx.nn[1], S)
         ctx.saved = None
         return (None, dp1 if ctx.needs_input_grad[1] else None, dp2 if ctx.needs_input_grad[2] else None, None, None,
@@ -236,13 +295,14 @@ class SegHeadFn(torch.autograd.Function):
     def forward(ctx, net, feat, mask, seed_offset, *params):
         B, N, C = feat.shape
         layers = [(net.conv1, net.bn1, True)]
-        z1, saved = mlp_forward(feat.contiguous().view(B * N, C), layers)
+        ctx.arena = arena = getattr(net, "_pn_arena", None)
+        z1, saved = mlp_forward(feat.contiguous().view(B * N, C), layers, arena=arena)
         p = float(net.drop1.p)
         if p > 0.0 or mask is not None:
             zd, mask = ops.dropout(z1, p, seed_offset=seed_offset, mask=mask)
         else:
             zd, mask = z1, None
-        logits = _gemm(zd, _w2d(net.conv2), net.conv2.bias.detach())
+        logits = _gemm(zd, _w2d(net.conv2), net.conv2.bias.detach(), arena=arena)
         logp = ops.log_softmax(logits)
         ctx.net, ctx.saved, ctx.tail = net, saved, (zd, mask, logp, p)
         return logp.view(B, N, -1)
@@ -257,10 +317,10 @@ class SegHeadFn(torch.autograd.Function):
         dw2, w_direct = _grad_sink(net.conv2.weight, w2.shape)
         db2, b_direct = _grad_sink(net.conv2.bias, (k,))
         ops.grad_weight(dlogits, zd, dw2, db2)
-        dzd = _gemm(dlogits, w2, None, transposed=True)
+        dzd = _gemm(dlogits, w2, None, transposed=True, arena=ctx.arena)
         dz1 = ops.dropout(dzd, p, mask=mask)[0] if mask is not None else dzd
         layers = [(net.conv1, net.bn1, True)]
-        dfeat, grads = mlp_backward(ctx.saved, layers, dz1, None, True)
+        dfeat, grads = mlp_backward(ctx.saved, layers, dz1, None, True, arena=ctx.arena)
         B, N = dlogp.shape[0], dlogp.shape[1]
         ctx.saved = ctx.tail = None
         return (None, dfeat.view(B, N, -1), None, None, *_layer_grads(layers, grads),
@@ -336,6 +396,29 @@ def semseg_geometry(net, points: torch.Tensor, fps_starts):
 
 def semseg_forward_train(net, points: torch.Tensor, fps_starts=None, dropout_mask: Optional[torch.Tensor] = None,
                          seed_offset: Optional[torch.Tensor] = None, geometry=None) -> torch.Tensor:
+    """PointNet2SemSeg.forward in train() mode (see _semseg_forward_train).  With the fused tensor-core GEMMs every conv weight
+    is converted to the kernels' layout ONCE here, for the forward and the backward of this iteration (PackedWeights)."""
+    arena = None
+    if FUSED_BN and PACK_ONCE and ops.mlp_mode() == "bf16x3" and points.is_cuda:
+        arena = net.__dict__.get("_pn_packed")
+        if arena is None or not arena.valid():
+            arena = net.__dict__["_pn_packed"] = PackedWeights(_net_convs(net))
+        if arena.n:
+            arena.pack()
+        else:
+            arena = None
+    holders = [net, net.sa1, net.sa2, net.sa3, net.sa4, net.fp4, net.fp3, net.fp2, net.fp1]
+    for m in holders:
+        m.__dict__["_pn_arena"] = arena          # read by the autograd blocks (kept in their ctx for the backward)
+    try:
+        return _semseg_forward_train(net, points, fps_starts, dropout_mask, seed_offset, geometry)
+    finally:
+        for m in holders:
+            m.__dict__["_pn_arena"] = None
+
+
+def _semseg_forward_train(net, points: torch.Tensor, fps_starts=None, dropout_mask: Optional[torch.Tensor] = None,
+                          seed_offset: Optional[torch.Tensor] = None, geometry=None) -> torch.Tensor:
     """PointNet2SemSeg.forward (pointnet2.py:159-176) in train() mode -> log-probabilities [B, N, classes] with grad_fn.
     dropout_mask (extension): uint8 [B*N, 128] keep-mask to use instead of drawing one (parity tests)."""
     ops._need_cuda(points, "points")
