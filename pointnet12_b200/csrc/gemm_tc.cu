@@ -204,6 +204,7 @@ train_gemm_kernel(const Args a) {
     double* cta_sum = reinterpret_cast<double*>(tf + 2 * a.k_pad);                             // [2][n_pad]: this CTA's column sums over all its tiles
     float* bias_s = reinterpret_cast<float*>(cta_sum + 2 * a.n_pad);                           // [n_pad], zero beyond cout
     float* pc = bias_s + a.n_pad;                                                               // [4][n_pad]: scale, shift, mean, invstd of the layer below
+    float* stg_all = pc + 4 * a.n_pad;                                                          // [4 epilogue warps][32 rows][20]: output staging
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS_MAX), bar_accf = smem_u32(bars + 2 * NS_MAX),
                    bar_acce = smem_u32(bars + 3 * NS_MAX), bar_w = smem_u32(bars + 4 * NS_MAX);
@@ -403,18 +404,38 @@ train_gemm_kernel(const Args a) {
                     v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
                 }
                 if ((a.debug & 2) && v[0] != 12345.678f) continue;
-                if (row_ok) {
-                    float* dst = a.y + row * a.ldy + col0;
+                if (!(a.debug & 64)) {
                     if (col0 + 32 <= a.cout && ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
+                        // A thread owns a ROW of the accumulator, so storing straight from registers makes every store
+                        // instruction touch 32 different lines with 16 bytes each (measured: 11 of 38 us for a 128 x 128
+                        // layer).  The 32 x 32 block goes through a per-warp shared-memory tile in two halves of 16
+                        // columns instead: 4 lanes then write the 64 contiguous bytes of a row, 8 rows per instruction.
+                        float* stg = stg_all + q * (32 * 20);
+                        const int64_t row0 = (blockIdx.x + it * gridDim.x) * TM + q * 32;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
+                        for (int hcol = 0; hcol < 2; ++hcol) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(stg + lane * 20 + j) =
+                                    make_float4(v[hcol * 16 + j], v[hcol * 16 + j + 1], v[hcol * 16 + j + 2], v[hcol * 16 + j + 3]);
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = (lane >> 2) + 8 * i;
+                                const float4 t = *reinterpret_cast<const float4*>(stg + r * 20 + (lane & 3) * 4);
+                                if (row0 + r < a.rows)
+                                    *reinterpret_cast<float4*>(a.y + (row0 + r) * a.ldy + col0 + hcol * 16 + (lane & 3) * 4) = t;
+                            }
+                            __syncwarp();
+                        }
+                    } else if (row_ok) {
+                        float* dst = a.y + row * a.ldy + col0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (col0 + j < a.cout) dst[j] = v[j];
                     }
                 }
-                if (a.col_sum) {
+                if (a.col_sum && !(a.debug & 32)) {
                     // column sums over the warp's 32 rows: the butterfly's first three steps (16 + 8 + 4 columns exchanged:
                     // afterwards a lane holds 4 columns summed over 8 rows) in fp32, the last two and everything beyond in fp64
                     float f1[32], f2[32];
@@ -562,7 +583,7 @@ static int train_gemm_launch(const float* x, int64_t ldx, int64_t rows, int cin,
     {
         static int dbg = -1;
         if (dbg < 0) {
-            const char* e = getenv("PN12_GEMM_DEBUG");     // profiling only: 1 = no MMAs, 2 = no epilogue work, 4 = no operand stores
+            const char* e = getenv("PN12_GEMM_DEBUG");     // profiling only: 1 = no MMAs, 2 = no epilogue work, 4 = no operand stores, 8 = (unused), 16 = no TMEM loads, 32 = no statistics, 64 = no y stores
             dbg = e ? atoi(e) : 0;
         }
         a.debug = dbg;
@@ -572,7 +593,7 @@ static int train_gemm_launch(const float* x, int64_t ldx, int64_t rows, int cin,
     // leave room get 4 stages; two CTAs share the SM's 512 TMEM columns, so each may hold 256 / n_pad accumulators.
     const size_t w_bytes = (size_t)a.k_pad * a.n_pad * 4;
     const size_t fixed = 256 /* barriers + TMEM slot */ + (size_t)2 * a.n_pad * sizeof(double) + (size_t)2 * a.k_pad * sizeof(float) +
-                         (size_t)5 * a.n_pad * sizeof(float) + 64;
+                         (size_t)5 * a.n_pad * sizeof(float) + (size_t)4 * 32 * 20 * sizeof(float) + 64;
     a.ns = (w_bytes + 4 * A_STAGE + fixed <= 112 * 1024) ? 4 : 2;
     const size_t smem = w_bytes + (size_t)a.ns * A_STAGE + fixed;
     const int per_sm = (smem <= 112 * 1024 && a.n_pad <= 128) ? 2 : 1;      // two CTAs share the SM's 512 TMEM columns

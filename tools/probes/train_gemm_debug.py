@@ -9,10 +9,11 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for rows, cin, cout in [(64000, 128, 128), (262144, 32, 64)]:
     x = torch.randn(rows, cin, device=dev); w = torch.randn(cout, cin, device=dev); b = torch.randn(cout, device=dev)
     g = torch.cuda.CUDAGraph()
-    ops.train_gemm(x, w, b); torch.cuda.synchronize()
+    acc = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+    ops.train_gemm(x, w, b, stats_acc=acc); torch.cuda.synchronize()
     with torch.cuda.graph(g):
         for _ in range(10):
-            ops.train_gemm(x, w, b)
+            ops.train_gemm(x, w, b, stats_acc=acc)
     ts = []
     for _ in range(5):
         flush.fill_(1)
