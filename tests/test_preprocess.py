@@ -186,3 +186,48 @@ def test_semkitti_2_common_merge(dev):
         want[:, :, j] = logits[:, :, idx].max(2)
     assert got.shape == (2, 500, 16) and np.array_equal(got, want)
     assert m.colors.shape == (16, 3) and m.semkitti_colors.shape == (19, 3)
+
+
+# ------------------------------------------------------------------------------------------------ the widened path end to end
+@pytest.mark.gpu
+def test_eval_iteration_raw_scans_to_metrics(dev, ckpt_path, ckpt_state):
+    """One iteration of the reference's evaluation loop with every stage on the device -- raw scans (rows f-3) ->
+    PointNet2SemSeg forward with the shipped checkpoint (rows a) -> test_kitti_semseg's metrics (row f-2) -- against the same
+    chain built from the three oracles."""
+    from oracle import oracle as orc
+    from oracle import train_oracle as tor
+    from pointnet12_b200.model.utils import load_pointnet
+    from pointnet12_b200.preprocess import ScanPreprocessor
+    from pointnet12_b200.train import SegMetrics
+
+    npts, B = 4096, 2
+    scans = [syn.raw_scan(30000, 7400 + i) for i in range(B)]
+    rng = np.random.default_rng(8)
+    kept = [por.scan_filter(p, l, LMAP)[0] for p, l in scans]
+    choice = np.stack([rng.integers(0, len(k), npts) for k in kept])
+    starts = [rng.integers(0, n, B) for n in (npts, 1024, 256, 64)]
+    # device chain
+    pre = ScanPreprocessor(LMAP, "inview", dev)
+    batch = pre.upload([p for p, _ in scans], [l for _, l in scans])
+    points, target = pre(batch, npts, train=False, choice=torch.from_numpy(choice).to(dev))
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    with torch.no_grad():
+        logp = net.module(points, fps_starts=[torch.from_numpy(s).to(dev) for s in starts])
+    metrics = SegMetrics(19, dev)
+    metrics.update(logp, target)
+    acc, miou, cat = metrics.result()
+    # oracle chain
+    pcs, labs = zip(*[por.scan_sample(p, l, LMAP, npts, choice[i]) for i, (p, l) in enumerate(scans)])
+    pts_o = np.stack([pc.T for pc in pcs]).astype(np.float32)                    # [B, 4, N]
+    assert np.array_equal(points.cpu().numpy(), pts_o) and np.array_equal(target.cpu().numpy(), np.stack(labs))
+    logp_o = orc.pointnet2_semseg(ckpt_state, pts_o, starts)
+    got = logp.cpu().numpy()
+    assert float(np.abs(got - logp_o).max() / max(1.0, np.abs(logp_o).max())) < 1e-3
+    acc_o, miou_o, cat_o = tor.test_kitti_semseg([(logp_o, np.stack(labs))], 19)
+    # labels may differ only where the oracle's own top-2 margin is below the log-prob tolerance
+    top2 = np.sort(logp_o, -1)[..., -2:]
+    stable = (top2[..., 1] - top2[..., 0]) > 2e-3
+    assert np.array_equal(got.argmax(-1)[stable], logp_o.argmax(-1)[stable])
+    if stable.all():
+        assert np.array_equal(cat, cat_o) and miou == miou_o
+    assert abs(acc - acc_o) <= (~stable).sum() / stable.size + 1e-12
