@@ -93,10 +93,59 @@ def blocks(ref):
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def cls_nets(ref):
+    """PointNet2ClsSsg / PointNet2ClsMsg (pointnet2.py:7-73) in train mode: forward, F.nll_loss, backward on 4 ModelNet40-shaped
+    clouds; seeded default init (the test rebuilds OUR net under the same seed; asserted identical here).  The two dropout
+    masks are captured with forward hooks (1 where the dropout input is 0)."""
+    from pointnet12_b200.model import pointnet2 as ours
+
+    arrays = {}
+    xyz = syn.modelnet_batch(4, 1024, seed=4100)
+    target = np.random.default_rng(4100).integers(0, 40, size=(4,)).astype(np.int64)
+    arrays["target"] = target
+    for tag, cls_name, nstarts in (("ssg", "PointNet2ClsSsg", (1024, 512)), ("msg", "PointNet2ClsMsg", (1024, 512))):
+        torch.manual_seed(4242)
+        net = getattr(ref["pointnet2"], cls_name)().train()
+        torch.manual_seed(4242)
+        mine = getattr(ours, cls_name)()
+        assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), mine.state_dict().values())), cls_name
+        seen = {}
+        net.drop1.register_forward_hook(lambda m, i, o: seen.update(x1=i[0].detach().clone(), y1=o.detach().clone()))
+        net.drop2.register_forward_hook(lambda m, i, o: seen.update(x2=i[0].detach().clone(), y2=o.detach().clone()))
+        torch.manual_seed(9)
+        starts = [torch.randint(0, n, (4,), dtype=torch.long).numpy() for n in nstarts]
+        torch.manual_seed(9)
+        out = net(torch.from_numpy(xyz))
+        logp = out[0] if isinstance(out, tuple) else out
+        loss = torch.nn.functional.nll_loss(logp, torch.from_numpy(target))
+        net.zero_grad()
+        loss.backward()
+        arrays[f"{tag}.starts"] = np.stack(starts).astype(np.int32)
+        arrays[f"{tag}.logp"] = logp.detach().numpy()
+        arrays[f"{tag}.loss"] = np.float64(loss.item())
+        for k in (1, 2):
+            x, y = seen[f"x{k}"], seen[f"y{k}"]
+            arrays[f"{tag}.keep{k}"] = torch.where(x != 0, y != 0, torch.ones_like(x, dtype=torch.bool)).numpy().astype(np.uint8)
+        for name, p in net.named_parameters():
+            g = p.grad.detach().numpy().reshape(-1)
+            arrays[f"{tag}.grad.{name}"] = (g if g.size <= FULL_MAX else g[::STRIDE]).astype(np.float32)
+        for name, b in net.named_buffers():
+            if not name.endswith("num_batches_tracked"):
+                arrays[f"{tag}.buffer.{name}"] = b.detach().numpy()
+        print(f"{cls_name}: loss {loss.item():.5f}")
+    path = os.path.join(OUT, "train_cls_seeded.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def main():
     torch.set_num_threads(8)
     ref = import_reference()
+    if "--cls-only" in sys.argv:
+        cls_nets(ref)
+        return
     blocks(ref)
+    cls_nets(ref)
     net = ref["pointnet2"].PointNet2SemSeg(CLASSES, feature_dims=1)
     sd = torch.load(os.path.join(REF, "checkpoints", CKPT), map_location="cpu")
     net.load_state_dict({k[len("module."):]: v for k, v in sd.items()})

@@ -102,9 +102,12 @@ class PointNet2ClsMsg(_Net):
             sa3=_all(640 + 3, [256, 512, 1024]))
         self._cls_fc(0.4, 40)
 
-    def forward(self, xyz):
-        _eval_only(self)
+    def forward(self, xyz, dropout_masks=None):
         _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+        if self.training:          # batch-statistics BatchNorm, dropout, autograd (pointnet12_b200/train.py)
+            from ..train import cls_head_train
+
+            return cls_head_train(self, fs[3].reshape(xyz.shape[0], 1024), dropout_masks), fs[3]
         return self._cls_head(fs[3].reshape(xyz.shape[0], 1024)), fs[3]
 
 
@@ -118,9 +121,12 @@ class PointNet2ClsSsg(_Net):
                      sa3=_all(256 + 3, [256, 512, 1024]))
         self._cls_fc(0.4, 40)
 
-    def forward(self, xyz):
-        _eval_only(self)
+    def forward(self, xyz, dropout_masks=None):
         _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+        if self.training:
+            from ..train import cls_head_train
+
+            return cls_head_train(self, fs[3].reshape(xyz.shape[0], 1024), dropout_masks)
         return self._cls_head(fs[3].reshape(xyz.shape[0], 1024))
 
 

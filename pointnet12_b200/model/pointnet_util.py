@@ -26,7 +26,7 @@ views of that storage, so chaining modules costs no transposes.
 
 eval(): BatchNorm is folded into the conv weights from the running statistics and the fused tensor-core chains run.
 train(): PointNetSetAbstraction and PointNetFeaturePropagation normalise with batch statistics and return tensors with a
-grad_fn (pointnet12_b200/train.py: forward and backward on our kernels); the MSG block still raises in train() mode.
+grad_fn (pointnet12_b200/train.py: forward and backward on our kernels), and so does PointNetSetAbstractionMsg.
 CPU tensors raise: there is no CPU fallback.
 """
 from __future__ import annotations
@@ -327,7 +327,10 @@ class PointNetSetAbstractionMsg(nn.Module):
         self._folded = [FoldedLayers() for _ in mlp_list]
 
     def forward(self, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx: Optional[torch.Tensor] = None):
-        _eval_only(self)
+        if self.training:
+            from ..train import set_abstraction_msg_train
+
+            return set_abstraction_msg_train(self, xyz, points, start_idx)
         xyz_pm = xyz.permute(0, 2, 1)
         pts_pm = points.permute(0, 2, 1) if points is not None else None
         B = xyz_pm.shape[0]

@@ -235,30 +235,38 @@ def _rows_of(grad: torch.Tensor, C: int) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 class SetAbstractionFn(torch.autograd.Function):
     """Grouping + shared MLP (batch-stat BN) + max over nsample of PointNetSetAbstraction.forward
-    (model/pointnet_util.py:187-199).  Sampling / ball query carry no gradient and are done by the caller."""
+    (model/pointnet_util.py:187-199) or of one scale of PointNetSetAbstractionMsg.forward (:239-257; `branch` selects the
+    scale, channel order [features, xyz_rel]).  Sampling / ball query carry no gradient and are done by the caller."""
 
     @staticmethod
-    def forward(ctx, mod, xyz_pm, pts_pm, new_xyz, idx, *params):
+    def _layers(mod, branch):
+        if branch is None:
+            return [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
+        return [(c, b, True) for c, b in zip(mod.conv_blocks[branch], mod.bn_blocks[branch])]
+
+    @staticmethod
+    def forward(ctx, mod, branch, xyz_pm, pts_pm, new_xyz, idx, *params):
         B, S, K = idx.shape
         D = pts_pm.shape[2] if pts_pm is not None else 0
-        layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
-        grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=False, pad4=True)          # [B,S,K,ld]
+        layers = SetAbstractionFn._layers(mod, branch)
+        msg = branch is not None
+        grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=msg, pad4=True)            # [B,S,K,ld]
         x0 = grouped.view(B * S * K, -1)[:, :3 + D]
         ctx.arena = getattr(mod, "_pn_arena", None)
         pooled, saved = mlp_forward(x0, layers, pool_K=K, arena=ctx.arena)
-        ctx.mod, ctx.saved, ctx.idx, ctx.geom = mod, saved, idx, (B, xyz_pm.shape[1], S, K, D)
+        ctx.mod, ctx.branch, ctx.saved, ctx.idx, ctx.geom = mod, branch, saved, idx, (B, xyz_pm.shape[1], S, K, D)
         return pooled.view(B, S, -1)
 
     @staticmethod
     def backward(ctx, dpooled):
-        mod = ctx.mod
         B, N, S, K, D = ctx.geom
-        layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
-        need_dx = D > 0 and ctx.needs_input_grad[2]
+        layers = SetAbstractionFn._layers(ctx.mod, ctx.branch)
+        need_dx = D > 0 and ctx.needs_input_grad[3]
         dx0, grads = mlp_backward(ctx.saved, layers, _rows_of(dpooled, dpooled.shape[-1]), K, need_dx, arena=ctx.arena)
-        dpts = ops.group_backward(dx0, 3, D, ctx.idx, N) if need_dx else None
+        # the feature channels sit behind the three xyz columns (SSG order) or in front of them (MSG order)
+        dpts = ops.group_backward(dx0, 3 if ctx.branch is None else 0, D, ctx.idx, N) if need_dx else None
         ctx.saved = None
-        return (None, None, dpts, None, None, *_layer_grads(layers, grads))
+        return (None, None, None, dpts, None, None, *_layer_grads(layers, grads))
 
 
 class FeaturePropagationFn(torch.autograd.Function):
@@ -327,21 +335,95 @@ class SegHeadFn(torch.autograd.Function):
                 None if w_direct else dw2.view_as(net.conv2.weight), None if b_direct else db2)
 
 
+class ClsHeadFn(torch.autograd.Function):
+    """fc1-bn1-relu-drop1-fc2-bn2-relu-drop2-fc3-log_softmax of the classification nets (pointnet2.py:41-45, :68-72) in
+    training mode, on rows = clouds.  masks: optional uint8 keep-masks of the two dropouts (parity tests)."""
+
+    @staticmethod
+    def forward(ctx, net, x, masks, seed_offset, *params):
+        stages, cur = [], x.contiguous()
+        for i, (fc, bn, drop) in enumerate(((net.fc1, net.bn1, net.drop1), (net.fc2, net.bn2, net.drop2))):
+            z, saved = mlp_forward(cur, [(fc, bn, True)])
+            p = float(drop.p)
+            mask = masks[i] if masks is not None else None
+            if p > 0.0 or mask is not None:
+                so = None if mask is not None else seed_offset + torch.tensor([0, 7919 * (i + 1)], dtype=torch.int64, device=x.device)
+                cur, mask = ops.dropout(z, p, seed_offset=so, mask=mask)
+            else:
+                cur = z
+            stages.append((saved, mask, p))
+        logits = _gemm(cur, _w2d(net.fc3), net.fc3.bias.detach())
+        logp = ops.log_softmax(logits)
+        ctx.net, ctx.stages, ctx.tail = net, stages, (cur, logp)
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        net = ctx.net
+        last_in, logp = ctx.tail
+        dlogits = ops.log_softmax_backward(dlogp.contiguous(), logp)
+        w3 = _w2d(net.fc3)
+        dw3, w_direct = _grad_sink(net.fc3.weight, w3.shape)
+        db3, b_direct = _grad_sink(net.fc3.bias, (w3.shape[0],))
+        ops.grad_weight(dlogits, last_in, dw3, db3)
+        dz = _gemm(dlogits, w3, None, transposed=True)
+        out = []
+        for (saved, mask, p), (fc, bn) in zip(reversed(ctx.stages), ((net.fc2, net.bn2), (net.fc1, net.bn1))):
+            if mask is not None:
+                dz = ops.dropout(dz, p, mask=mask)[0]
+            dz, grads = mlp_backward(saved, [(fc, bn, True)], dz, None, True)
+            out = _layer_grads([(fc, bn, True)], grads) + out
+        ctx.stages = ctx.tail = None
+        return (None, dz, None, None, *out, None if w_direct else dw3, None if b_direct else db3)
+
+
+def cls_head_train(net, global_feat: torch.Tensor, dropout_masks=None, seed_offset=None) -> torch.Tensor:
+    """global_feat [B, 1024] -> log-probabilities [B, classes] with grad_fn."""
+    if dropout_masks is None and seed_offset is None:
+        seed_offset = dropout_seed(global_feat.device)
+    params = [net.fc1.weight, net.fc1.bias, net.bn1.weight, net.bn1.bias, net.fc2.weight, net.fc2.bias, net.bn2.weight,
+              net.bn2.bias, net.fc3.weight, net.fc3.bias]
+    return ClsHeadFn.apply(net, global_feat, dropout_masks, seed_offset, *params)
+
+
 # ------------------------------------------------------------------------------------------------
 # train-mode forwards called by the modules (model/pointnet_util.py, model/pointnet2.py)
 def set_abstraction_train(mod, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx=None, geometry=None):
     """geometry: (new_xyz [B,S,3], group_idx [B,S,K]) when the caller has computed them already (side stream)."""
-    if mod.group_all:
-        raise NotImplementedError("training path: group_all levels are not built yet (PointNet2SemSeg has none)")
     xyz_pm = xyz.detach().permute(0, 2, 1)
     pts_pm = points.permute(0, 2, 1) if points is not None else None
-    if geometry is None:
-        with torch.no_grad():
-            geometry = mod.geometry(xyz_pm, start_idx)
-    new_xyz, idx = geometry
-    layers = [(c, b, True) for c, b in zip(mod.mlp_convs, mod.mlp_bns)]
-    pooled = SetAbstractionFn.apply(mod, xyz_pm, pts_pm, new_xyz, idx, *_layer_params(layers))
+    if mod.group_all:
+        # sample_and_group_all (pointnet_util.py:140-157): one group holding every point, centroid = origin, no recentring
+        # (x - 0 == x exactly, so the same gather kernel serves); the max then runs over all N rows of a cloud
+        B, N, _ = xyz_pm.shape
+        new_xyz = torch.zeros((B, 1, 3), dtype=torch.float32, device=xyz.device)
+        idx = torch.arange(N, dtype=torch.int64, device=xyz.device).expand(B, 1, N).contiguous()
+    else:
+        if geometry is None:
+            with torch.no_grad():
+                geometry = mod.geometry(xyz_pm, start_idx)
+        new_xyz, idx = geometry
+    layers = SetAbstractionFn._layers(mod, None)
+    pooled = SetAbstractionFn.apply(mod, None, xyz_pm, pts_pm, new_xyz, idx, *_layer_params(layers))
     return new_xyz.permute(0, 2, 1), pooled.permute(0, 2, 1)
+
+
+def set_abstraction_msg_train(mod, xyz: torch.Tensor, points: Optional[torch.Tensor], start_idx=None):
+    """PointNetSetAbstractionMsg.forward (pointnet_util.py:224-261) in train() mode: one FPS, then per radius ball query ->
+    grouping ([features, xyz_rel]) -> shared MLP with batch statistics -> max; the scales are concatenated on the channels."""
+    from .model.pointnet_util import farthest_point_sample
+
+    xyz_pm = xyz.detach().permute(0, 2, 1)
+    pts_pm = points.permute(0, 2, 1) if points is not None else None
+    with torch.no_grad():
+        new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, mod.npoint, start_idx))
+    outs = []
+    for i, radius in enumerate(mod.radius_list):
+        with torch.no_grad():
+            idx = ops.ball_query(radius, mod.nsample_list[i], xyz_pm, new_xyz)
+        layers = SetAbstractionFn._layers(mod, i)
+        outs.append(SetAbstractionFn.apply(mod, i, xyz_pm, pts_pm, new_xyz, idx, *_layer_params(layers)))
+    return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=2).permute(0, 2, 1)
 
 
 def feature_propagation_train(mod, xyz1, xyz2, points1, points2, geometry=None):

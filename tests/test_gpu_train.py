@@ -586,3 +586,47 @@ def test_train_step_ragged_shapes_vs_oracle(dev, gemm_mode, B, N):
         p_new, _, _ = tor.adam_step(before[name], grads[name], 0.0, 0.0, 1)
         got = dict(net.named_parameters())[name].detach().cpu().numpy()
         assert np.abs(got - p_new).max() < 2e-6, name
+
+
+@pytest.mark.parametrize("tag,cls_name", [("ssg", "PointNet2ClsSsg"), ("msg", "PointNet2ClsMsg")])
+def test_cls_nets_train_step_vs_reference(dev, golden, gemm_mode, tag, cls_name):
+    """PointNet2ClsSsg / PointNet2ClsMsg in train() mode (group-all level, MSG blocks, fc head with two dropouts) against the
+    reference's own autograd (tests/golden/train_cls_seeded.npz: forward, F.nll_loss, backward on 4 clouds x 1024 points)."""
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model import pointnet2 as ours
+    from pointnet12_b200.model.pointnet_util import draw_fps_starts  # noqa: F401  (the draws are replayed through the seed)
+
+    g = golden("train_cls_seeded")
+    torch.manual_seed(4242)
+    net = getattr(ours, cls_name)().to(dev).train()
+    xyz = T(syn.modelnet_batch(4, 1024, seed=4100), dev)
+    masks = [T(g[f"{tag}.keep1"], dev), T(g[f"{tag}.keep2"], dev)]
+    torch.manual_seed(9)                                   # the reference's two FPS start draws, same generator, same order
+    out = net(xyz, dropout_masks=masks)
+    logp = out[0] if isinstance(out, tuple) else out
+    loss = torch.nn.functional.nll_loss(logp, T(g["target"], dev))
+    net.zero_grad()
+    loss.backward()
+    assert abs(loss.item() - float(g[f"{tag}.loss"])) < 2e-4
+    assert rl2(logp.detach().cpu().numpy(), g[f"{tag}.logp"]) < 2e-4
+    grads = _grads(net)
+    tight = 2e-3 if gemm_mode == "fp32" else 5e-2          # ReLU / arg-max flips (see the SA block test); 4 rows in the head
+    for name, gr in grads.items():
+        ref = g[f"{tag}.grad.{name}"]
+        mine = gr.reshape(-1)
+        if mine.size > 20000:
+            mine = mine[::9]
+        is_bias_before_bn = name.endswith(".bias") and ("convs" in name or "conv_blocks" in name or name in ("fc1.bias", "fc2.bias"))
+        if is_bias_before_bn:
+            assert np.abs(mine).max() < 1e-3, name          # analytically zero: BatchNorm follows
+            continue
+        a_, b_ = mine.astype(np.float64), ref.astype(np.float64)
+        if name.startswith("fc3"):
+            assert rl2(a_, b_) < tight, (name, rl2(a_, b_))
+        else:
+            cos = float(a_ @ b_ / max(np.linalg.norm(a_) * np.linalg.norm(b_), 1e-30))
+            assert cos > (0.999 if gemm_mode == "fp32" else 0.98), (name, cos)
+    for name, buf in net.named_buffers():
+        if not name.endswith("num_batches_tracked"):
+            ref = g[f"{tag}.buffer.{name}"]
+            assert np.abs(buf.cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), name
