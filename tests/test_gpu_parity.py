@@ -982,12 +982,15 @@ def test_partseg_msg_smoke_shape(dev):
 
 
 def test_train_mode_raises_where_not_built(dev):
-    """PointNet2SemSeg trains (tests/test_gpu_train.py); the MSG blocks are inference-only and must say so, not fall back."""
-    from pointnet12_b200.model.pointnet2 import PointNet2ClsMsg
+    """PointNet2SemSeg, PointNet2ClsSsg and PointNet2ClsMsg train (tests/test_gpu_train.py); the part-segmentation nets and the
+    PointNet family are inference-only and must say so, not fall back."""
+    from pointnet12_b200.model.pointnet import PointNetSeg
+    from pointnet12_b200.model.pointnet2 import PointNet2PartSegSsg
 
-    net = PointNet2ClsMsg().to(dev).train()
     with pytest.raises(NotImplementedError):
-        net(torch.zeros(2, 3, 1024, device=dev))
+        PointNet2PartSegSsg(50).to(dev).train()(torch.zeros(2, 3, 1024, device=dev))
+    with pytest.raises(NotImplementedError):
+        PointNetSeg(19, 4, True).to(dev).train()(torch.zeros(1, 4, 2048, device=dev))
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties (C2)

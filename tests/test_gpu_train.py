@@ -611,6 +611,7 @@ def test_cls_nets_train_step_vs_reference(dev, golden, gemm_mode, tag, cls_name)
     assert rl2(logp.detach().cpu().numpy(), g[f"{tag}.logp"]) < 2e-4
     grads = _grads(net)
     tight = 2e-3 if gemm_mode == "fp32" else 5e-2          # ReLU / arg-max flips (see the SA block test); 4 rows in the head
+    bad = []
     for name, gr in grads.items():
         ref = g[f"{tag}.grad.{name}"]
         mine = gr.reshape(-1)
@@ -621,11 +622,16 @@ def test_cls_nets_train_step_vs_reference(dev, golden, gemm_mode, tag, cls_name)
             assert np.abs(mine).max() < 1e-3, name          # analytically zero: BatchNorm follows
             continue
         a_, b_ = mine.astype(np.float64), ref.astype(np.float64)
+        if np.linalg.norm(a_) < 1e-4 and np.linalg.norm(b_) < 1e-4:
+            continue      # analytically zero as well: the beta of a level's last BatchNorm only shifts what the NEXT BatchNorm removes
         if name.startswith("fc3"):
-            assert rl2(a_, b_) < tight, (name, rl2(a_, b_))
+            if not rl2(a_, b_) < tight:
+                bad.append((name, "rl2", rl2(a_, b_)))
         else:
             cos = float(a_ @ b_ / max(np.linalg.norm(a_) * np.linalg.norm(b_), 1e-30))
-            assert cos > (0.999 if gemm_mode == "fp32" else 0.98), (name, cos)
+            if not cos > (0.999 if gemm_mode == "fp32" else 0.98):
+                bad.append((name, "cos", round(cos, 4), float(np.linalg.norm(a_)), float(np.linalg.norm(b_))))
+    assert not bad, bad
     for name, buf in net.named_buffers():
         if not name.endswith("num_batches_tracked"):
             ref = g[f"{tag}.buffer.{name}"]
