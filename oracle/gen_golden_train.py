@@ -133,6 +133,31 @@ def cls_nets(ref):
             if not name.endswith("num_batches_tracked"):
                 arrays[f"{tag}.buffer.{name}"] = b.detach().numpy()
         print(f"{cls_name}: loss {loss.item():.5f}")
+    # PointNet2PartSegSsg (pointnet2.py:75-104): two outputs (log-probs, features before dropout), both in the loss
+    torch.manual_seed(4343)
+    net = ref["pointnet2"].PointNet2PartSegSsg(50).train()
+    torch.manual_seed(4343)
+    mine = ours.PointNet2PartSegSsg(50)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), mine.state_dict().values()))
+    xyz2 = syn.modelnet_batch(2, 1024, seed=4200)
+    tgt2 = np.random.default_rng(4200).integers(0, 50, size=(2, 1024)).astype(np.int64)
+    seen = {}
+    net.drop1.register_forward_hook(lambda m, i, o: seen.update(x=i[0].detach().clone(), y=o.detach().clone()))
+    torch.manual_seed(9)
+    starts = [torch.randint(0, n, (2,), dtype=torch.long).numpy() for n in (1024, 512)]
+    torch.manual_seed(9)
+    logp, feat = net(torch.from_numpy(xyz2))
+    loss = torch.nn.functional.nll_loss(logp.reshape(-1, 50), torch.from_numpy(tgt2).reshape(-1)) + 1e-3 * feat.pow(2).mean()
+    net.zero_grad()
+    loss.backward()
+    keep = torch.where(seen["x"] != 0, seen["y"] != 0, torch.ones_like(seen["x"], dtype=torch.bool))      # [B,128,N]
+    arrays.update({"part.target": tgt2.astype(np.int8), "part.logp": logp.detach().numpy().astype(np.float32),
+                   "part.feat_sub": feat.detach().numpy()[:, :, ::8], "part.loss": np.float64(loss.item()),
+                   "part.keep_bits": np.packbits(keep.permute(0, 2, 1).reshape(2 * 1024, 128).numpy(), axis=1)})
+    for name, p in net.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1)
+        arrays[f"part.grad.{name}"] = (g if g.size <= FULL_MAX else g[::STRIDE]).astype(np.float32)
+    print(f"PointNet2PartSegSsg: loss {loss.item():.5f}")
     path = os.path.join(OUT, "train_cls_seeded.npz")
     np.savez_compressed(path, **arrays)
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")

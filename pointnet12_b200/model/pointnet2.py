@@ -141,11 +141,14 @@ class PointNet2PartSegSsg(_Net):
                      fp3=_fp(1280, [256, 256]), fp2=_fp(384, [256, 128]), fp1=_fp(128, [128, 128, 128]))
         self._seg_convs(num_classes)
 
-    def forward(self, xyz):
-        _eval_only(self)
+    def forward(self, xyz, dropout_mask=None):
         xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
         f2 = self.fp3(xs[2], xs[3], fs[2], fs[3])
         f1 = self.fp2(xs[1], xs[2], fs[1], f2)
+        if self.training:
+            from ..train import seg_head_train
+
+            return seg_head_train(self, self.fp1(xyz, xs[1], None, f1), dropout_mask)
         return self._seg_head(self.fp1(xyz, xs[1], None, f1))
 
 
@@ -161,13 +164,16 @@ class PointNet2PartSegMsg_one_hot(_Net):
             fp3=_fp(1536, [256, 256]), fp2=_fp(576, [256, 128]), fp1=_fp(150, [128, 128]))
         self._seg_convs(num_classes)
 
-    def forward(self, xyz, norm_plt, cls_label):
-        _eval_only(self)
+    def forward(self, xyz, norm_plt, cls_label, dropout_mask=None):
         B, _, N = xyz.shape
         xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, norm_plt)
         f2 = self.fp3(xs[2], xs[3], fs[2], fs[3])
         f1 = self.fp2(xs[1], xs[2], fs[1], f2)
         skip = torch.cat([cls_label.view(B, 16, 1).expand(B, 16, N), xyz, norm_plt], 1)   # host-side glue [B,22,N]
+        if self.training:
+            from ..train import seg_head_train
+
+            return seg_head_train(self, self.fp1(xyz, xs[1], skip, f1), dropout_mask)[0]
         return self._seg_head(self.fp1(xyz, xs[1], skip, f1))[0]
 
 

@@ -303,6 +303,7 @@ class SegHeadFn(torch.autograd.Function):
     def forward(ctx, net, feat, mask, seed_offset, *params):
         B, N, C = feat.shape
         layers = [(net.conv1, net.bn1, True)]
+        ctx.set_materialize_grads(False)          # the second output is usually unused: no 33 MB of zeros for its gradient
         ctx.arena = arena = getattr(net, "_pn_arena", None)
         z1, saved = mlp_forward(feat.contiguous().view(B * N, C), layers, arena=arena)
         p = float(net.drop1.p)
@@ -313,13 +314,17 @@ class SegHeadFn(torch.autograd.Function):
         logits = _gemm(zd, _w2d(net.conv2), net.conv2.bias.detach(), arena=arena)
         logp = ops.log_softmax(logits)
         ctx.net, ctx.saved, ctx.tail = net, saved, (zd, mask, logp, p)
-        return logp.view(B, N, -1)
+        # second output: the activated conv1-bn1 features BEFORE dropout, which the part-segmentation nets return as well
+        # (pointnet2.py:99-104); it carries a gradient of its own
+        return logp.view(B, N, -1), z1.view(B, N, -1)
 
     @staticmethod
-    def backward(ctx, dlogp):
+    def backward(ctx, dlogp, dfeat_out=None):
         net = ctx.net
         zd, mask, logp, p = ctx.tail
         k = logp.shape[1]
+        if dlogp is None:
+            raise NotImplementedError("segmentation head: the log-probabilities must take part in the loss")
         dlogits = ops.log_softmax_backward(_rows_of(dlogp, k), logp)
         w2 = _w2d(net.conv2)
         dw2, w_direct = _grad_sink(net.conv2.weight, w2.shape)
@@ -327,6 +332,8 @@ class SegHeadFn(torch.autograd.Function):
         ops.grad_weight(dlogits, zd, dw2, db2)
         dzd = _gemm(dlogits, w2, None, transposed=True, arena=ctx.arena)
         dz1 = ops.dropout(dzd, p, mask=mask)[0] if mask is not None else dzd
+        if dfeat_out is not None:
+            dz1 = dz1 + _rows_of(dfeat_out, dz1.shape[1])
         layers = [(net.conv1, net.bn1, True)]
         dfeat, grads = mlp_backward(ctx.saved, layers, dz1, None, True, arena=ctx.arena)
         B, N = dlogp.shape[0], dlogp.shape[1]
@@ -524,7 +531,7 @@ def _semseg_forward_train(net, points: torch.Tensor, fps_starts=None, dropout_ma
         if dropout_mask is None and seed_offset is None and net.drop1.p > 0:
             seed_offset = dropout_seed(points.device)
         params = [net.conv1.weight, net.conv1.bias, net.bn1.weight, net.bn1.bias, net.conv2.weight, net.conv2.bias]
-        return SegHeadFn.apply(net, up.permute(0, 2, 1), dropout_mask, seed_offset, *params)
+        return SegHeadFn.apply(net, up.permute(0, 2, 1), dropout_mask, seed_offset, *params)[0]
     if fps_starts is None:
         from .model.pointnet_util import draw_fps_starts
 
@@ -566,7 +573,17 @@ def _semseg_forward_train(net, points: torch.Tensor, fps_starts=None, dropout_ma
     if dropout_mask is None and seed_offset is None and net.drop1.p > 0:
         seed_offset = dropout_seed(points.device)
     params = [net.conv1.weight, net.conv1.bias, net.bn1.weight, net.bn1.bias, net.conv2.weight, net.conv2.bias]
-    return SegHeadFn.apply(net, up.permute(0, 2, 1), dropout_mask, seed_offset, *params)
+    return SegHeadFn.apply(net, up.permute(0, 2, 1), dropout_mask, seed_offset, *params)[0]
+
+
+def seg_head_train(net, l0_points: torch.Tensor, dropout_mask=None, seed_offset=None):
+    """conv1-bn1-relu-drop1-conv2-log_softmax of the part-segmentation nets in train() mode (pointnet2.py:99-104):
+    l0_points [B,128,N] -> (log_probs [B,N,k], feat [B,128,N]), both with grad_fn."""
+    if dropout_mask is None and seed_offset is None and net.drop1.p > 0:
+        seed_offset = dropout_seed(l0_points.device)
+    params = [net.conv1.weight, net.conv1.bias, net.bn1.weight, net.bn1.bias, net.conv2.weight, net.conv2.bias]
+    logp, feat = SegHeadFn.apply(net, l0_points.permute(0, 2, 1), dropout_mask, seed_offset, *params)
+    return logp, feat.permute(0, 2, 1)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -636,3 +636,38 @@ def test_cls_nets_train_step_vs_reference(dev, golden, gemm_mode, tag, cls_name)
         if not name.endswith("num_batches_tracked"):
             ref = g[f"{tag}.buffer.{name}"]
             assert np.abs(buf.cpu().numpy() - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), name
+
+
+def test_partseg_net_train_step_vs_reference(dev, golden, gemm_mode):
+    """PointNet2PartSegSsg in train() mode: group-all level, feature propagation from a single coarse point, and a head with TWO
+    outputs in the loss (log-probabilities and the pre-dropout features), against the reference's own autograd."""
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet2 import PointNet2PartSegSsg
+
+    g = golden("train_cls_seeded")
+    torch.manual_seed(4343)
+    net = PointNet2PartSegSsg(50).to(dev).train()
+    xyz = T(syn.modelnet_batch(2, 1024, seed=4200), dev)
+    keep = T(np.unpackbits(g["part.keep_bits"], axis=1)[:, :128].astype(np.uint8), dev)
+    torch.manual_seed(9)
+    logp, feat = net(xyz, dropout_mask=keep)
+    assert logp.shape == (2, 1024, 50) and feat.shape == (2, 128, 1024)
+    target = T(g["part.target"].astype(np.int64), dev)
+    loss = torch.nn.functional.nll_loss(logp.reshape(-1, 50), target.reshape(-1)) + 1e-3 * feat.pow(2).mean()
+    net.zero_grad()
+    loss.backward()
+    assert abs(loss.item() - float(g["part.loss"])) < 2e-4
+    assert rl2(logp.detach().cpu().numpy(), g["part.logp"]) < 2e-4
+    assert rl2(feat.detach().cpu().numpy()[:, :, ::8], g["part.feat_sub"]) < 2e-4
+    bad = []
+    for name, gr in _grads(net).items():
+        ref = g[f"part.grad.{name}"].astype(np.float64)
+        mine = gr.reshape(-1).astype(np.float64)
+        if mine.size > 20000:
+            mine = mine[::9]
+        if np.linalg.norm(mine) < 1e-4 and np.linalg.norm(ref) < 1e-4:
+            continue                                       # analytically zero (a bias / beta ahead of a BatchNorm)
+        cos = float(mine @ ref / max(np.linalg.norm(mine) * np.linalg.norm(ref), 1e-30))
+        if not (cos > (0.999 if gemm_mode == "fp32" else 0.98) and abs(np.linalg.norm(mine) / np.linalg.norm(ref) - 1) < 0.05):
+            bad.append((name, round(cos, 4), float(np.linalg.norm(mine)), float(np.linalg.norm(ref))))
+    assert not bad, bad
