@@ -982,13 +982,9 @@ def test_partseg_msg_smoke_shape(dev):
 
 
 def test_train_mode_raises_where_not_built(dev):
-    """PointNet2SemSeg, PointNet2ClsSsg and PointNet2ClsMsg train (tests/test_gpu_train.py); the part-segmentation nets and the
-    PointNet family are inference-only and must say so, not fall back."""
+    """The PointNet++ nets train (tests/test_gpu_train.py); the PointNet family is inference-only and must say so, not fall back."""
     from pointnet12_b200.model.pointnet import PointNetSeg
-    from pointnet12_b200.model.pointnet2 import PointNet2PartSegSsg
 
-    with pytest.raises(NotImplementedError):
-        PointNet2PartSegSsg(50).to(dev).train()(torch.zeros(2, 3, 1024, device=dev))
     with pytest.raises(NotImplementedError):
         PointNetSeg(19, 4, True).to(dev).train()(torch.zeros(1, 4, 2048, device=dev))
 

@@ -658,15 +658,18 @@ def test_partseg_net_train_step_vs_reference(dev, golden, gemm_mode):
     loss.backward()
     assert abs(loss.item() - float(g["part.loss"])) < 2e-4
     assert rl2(logp.detach().cpu().numpy(), g["part.logp"]) < 2e-4
-    assert rl2(feat.detach().cpu().numpy()[:, :, ::8], g["part.feat_sub"]) < 2e-4
+    assert rl2(feat.detach().cpu().numpy()[:, :, ::8], g["part.feat_sub"]) < (2e-4 if gemm_mode == "fp32" else 1e-3)
     bad = []
     for name, gr in _grads(net).items():
         ref = g[f"part.grad.{name}"].astype(np.float64)
         mine = gr.reshape(-1).astype(np.float64)
         if mine.size > 20000:
             mine = mine[::9]
+        if name.endswith(".bias") and ("mlp_convs" in name or name == "conv1.bias"):
+            assert np.abs(mine).max() < 1e-3, name         # analytically zero: BatchNorm follows (the reference holds round-off)
+            continue
         if np.linalg.norm(mine) < 1e-4 and np.linalg.norm(ref) < 1e-4:
-            continue                                       # analytically zero (a bias / beta ahead of a BatchNorm)
+            continue                                       # analytically zero as well (the beta ahead of the next BatchNorm)
         cos = float(mine @ ref / max(np.linalg.norm(mine) * np.linalg.norm(ref), 1e-30))
         if not (cos > (0.999 if gemm_mode == "fp32" else 0.98) and abs(np.linalg.norm(mine) / np.linalg.norm(ref) - 1) < 0.05):
             bad.append((name, round(cos, 4), float(np.linalg.norm(mine)), float(np.linalg.norm(ref))))
