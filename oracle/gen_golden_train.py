@@ -163,14 +163,50 @@ def cls_nets(ref):
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def pointnet_seg(ref):
+    """PointNetSeg(19, input_dims=4, feature_transform=True) -- the default model of the reference's training driver
+    (pcdseg.py:49-52, :128) -- one iteration as pcdseg.py:166-186 runs it: CrossEntropyLoss on the transposed log-probs plus
+    0.001 * feature_transform_reguliarzer(trans_feat).  Gradients: every 31st element of the large tensors."""
+    from pointnet12_b200.model import pointnet as ours
+
+    rp = ref["pointnet"]
+    torch.manual_seed(4444)
+    net = rp.PointNetSeg(19, input_dims=4, feature_transform=True).train()
+    torch.manual_seed(4444)
+    mine = ours.PointNetSeg(19, input_dims=4, feature_transform=True)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), mine.state_dict().values()))
+    pts = syn.kitti_batch(2, 1024, config=7)
+    target = np.random.default_rng(7000).integers(0, 19, size=(2, 1024)).astype(np.int64)
+    logits, trans_feat = net(torch.from_numpy(pts))
+    loss = torch.nn.CrossEntropyLoss()(logits.transpose(2, 1), torch.from_numpy(target))
+    loss = loss + rp.feature_transform_reguliarzer(trans_feat) * 0.001
+    net.zero_grad()
+    loss.backward()
+    arrays = {"target": target.astype(np.int8), "logp": logits.detach().numpy(), "trans_feat": trans_feat.detach().numpy(),
+              "loss": np.float64(loss.item())}
+    for name, p in net.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1)
+        arrays["grad." + name] = (g if g.size <= 4096 else g[::31]).astype(np.float32)
+    for name, b in net.named_buffers():
+        if not name.endswith("num_batches_tracked"):
+            arrays["buffer." + name] = b.detach().numpy()
+    path = os.path.join(OUT, "train_pointnet_seg_seeded.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"PointNetSeg: loss {loss.item():.5f}; wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def main():
     torch.set_num_threads(8)
     ref = import_reference()
     if "--cls-only" in sys.argv:
         cls_nets(ref)
         return
+    if "--pointnet-only" in sys.argv:
+        pointnet_seg(ref)
+        return
     blocks(ref)
     cls_nets(ref)
+    pointnet_seg(ref)
     net = ref["pointnet2"].PointNet2SemSeg(CLASSES, feature_dims=1)
     sd = torch.load(os.path.join(REF, "checkpoints", CKPT), map_location="cpu")
     net.load_state_dict({k[len("module."):]: v for k, v in sd.items()})

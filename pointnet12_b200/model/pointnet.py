@@ -199,7 +199,10 @@ class PointNetSeg(nn.Module):
         self._folded_tail = FoldedLayers()
 
     def forward(self, x):
-        _eval_only(self)
+        if self.training:          # batch-statistics BatchNorm + autograd (pointnet12_b200/train.py), pcdseg.py:166-186
+            from ..train import pointnet_seg_train
+
+            return pointnet_seg_train(self, x)
         B, _, N = x.shape
         g, pointfeat, _, trans_feat = self.feat.encode_rows(_point_rows(x))
         (w1, b1), (w2, b2), (w3, b3), (w4, b4) = self._folded.get(

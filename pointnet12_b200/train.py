@@ -132,11 +132,12 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[Tuple], pool_K: Optional[int] 
     for li, (conv, bn, relu) in enumerate(layers):
         w = _w2d(conv)
         bias = conv.bias.detach() if conv.bias is not None else None
-        fused = (FUSED_BN and bn is not None and ops.mlp_mode() == "bf16x3" and (pending is None or relu)
+        fused = (FUSED_BN and bn is not None and ops.mlp_mode() == "bf16x3"
                  and ops.train_gemm_supported(w.shape[1], w.shape[0]))
         st, am = None, None
-        if bn is not None and not relu:
-            raise NotImplementedError("training path: BatchNorm layers are followed by ReLU in every supported block")
+        if bn is not None and not relu and li != len(layers) - 1:
+            # (a BatchNorm without ReLU is supported as the LAST layer of a chain only: PointNetEncoder's bn3 ahead of the max)
+            raise NotImplementedError("training path: an inner BatchNorm layer must be followed by ReLU")
         if fused:
             acc = accs[li, :, :w.shape[0]]
             y = ops.train_gemm(x, w, bias, in_stats=pending, stats_acc=acc,
@@ -391,6 +392,96 @@ def cls_head_train(net, global_feat: torch.Tensor, dropout_masks=None, seed_offs
     params = [net.fc1.weight, net.fc1.bias, net.bn1.weight, net.bn1.bias, net.fc2.weight, net.fc2.bias, net.bn2.weight,
               net.bn2.bias, net.fc3.weight, net.fc3.bias]
     return ClsHeadFn.apply(net, global_feat, dropout_masks, seed_offset, *params)
+
+
+class MlpRowsFn(torch.autograd.Function):
+    """A conv1x1 / Linear + BatchNorm(batch statistics) + ReLU chain over rows [rows, cin], optionally max-pooled over runs of
+    K rows (the per-point stacks, global max and fully connected layers of model/pointnet.py in train() mode)."""
+
+    @staticmethod
+    def forward(ctx, layers, pool_K, x, *params):
+        out, saved = mlp_forward(x, layers, pool_K=pool_K)
+        ctx.layers, ctx.pool_K, ctx.saved = layers, pool_K, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx, grads = mlp_backward(ctx.saved, ctx.layers, dout.contiguous(), ctx.pool_K, ctx.needs_input_grad[2])
+        ctx.saved = None
+        return (None, None, dx, *_layer_grads(ctx.layers, grads))
+
+
+def mlp_rows_train(layers, x: torch.Tensor, pool_K: Optional[int] = None) -> torch.Tensor:
+    return MlpRowsFn.apply(layers, pool_K, x.contiguous(), *_layer_params(layers))
+
+
+class BmmPointsFn(torch.autograd.Function):
+    """torch.bmm(x [B,N,k], trans [B,k,k2]) of pointnet.py:105-107, :113-115 with both gradients."""
+
+    @staticmethod
+    def forward(ctx, x, trans):
+        ctx.save_for_backward(x, trans)
+        return ops.bmm_points(x, trans)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, trans = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.bmm_points(dy, trans.transpose(1, 2)) if ctx.needs_input_grad[0] else None
+        dtrans = None
+        if ctx.needs_input_grad[1]:
+            B, N, k = x.shape
+            dtrans = torch.zeros_like(trans)
+            for b in range(B):                    # dtrans[b] = x[b]^T dy[b]: the weight-gradient kernel with the roles swapped
+                ops.grad_weight(x[b].contiguous(), dy[b], dtrans[b], None)
+        return dx, dtrans
+
+
+class LogSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = ops.log_softmax(x.contiguous())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.log_softmax_backward(dy.contiguous(), ctx.saved_tensors[0])
+
+
+def stn_train(stn, x_pm: torch.Tensor) -> torch.Tensor:
+    """STN3d / STNkd.forward (pointnet.py:27-45, :66-84) in train() mode: x_pm [B,N,k] -> [B,k,k]."""
+    B, N, k = x_pm.shape
+    g = mlp_rows_train([(stn.conv1, stn.bn1, True), (stn.conv2, stn.bn2, True), (stn.conv3, stn.bn3, True)],
+                       x_pm.reshape(B * N, k), pool_K=N)                                  # [B, 1024]
+    h = mlp_rows_train([(stn.fc1, stn.bn4, True), (stn.fc2, stn.bn5, True), (stn.fc3, None, False)], g)
+    return (h + torch.eye(stn.k, device=h.device, dtype=h.dtype).flatten()).view(B, stn.k, stn.k)
+
+
+def pointnet_encoder_train(enc, x_pm: torch.Tensor):
+    """PointNetEncoder.forward (pointnet.py:100-131) in train() mode on point-major rows:
+    -> (global [B,1024], pointfeat [B,N,64], trans, trans_feat)."""
+    B, N, _ = x_pm.shape
+    trans = stn_train(enc.stn, x_pm)
+    x = BmmPointsFn.apply(x_pm.contiguous(), trans)
+    x = mlp_rows_train([(enc.conv1, enc.bn1, True)], x.reshape(B * N, -1)).view(B, N, 64)
+    trans_feat = None
+    if enc.feature_transform:
+        trans_feat = stn_train(enc.fstn, x)
+        x = BmmPointsFn.apply(x, trans_feat)
+    g = mlp_rows_train([(enc.conv2, enc.bn2, True), (enc.conv3, enc.bn3, False)], x.reshape(B * N, 64), pool_K=N)
+    return g, x, trans, trans_feat
+
+
+def pointnet_seg_train(net, x: torch.Tensor):
+    """PointNetSeg.forward (pointnet.py:243-254) in train() mode: x [B,D,N] -> (log_probs [B,N,k], trans_feat)."""
+    ops._need_cuda(x, "x")
+    B, _, N = x.shape
+    g, pointfeat, _, trans_feat = pointnet_encoder_train(net.feat, x.permute(0, 2, 1))
+    rows = torch.cat([g[:, None, :].expand(B, N, g.shape[1]), pointfeat], dim=2).reshape(B * N, -1)       # [global | pointfeat], :128-131
+    logits = mlp_rows_train([(net.conv1, net.bn1, True), (net.conv2, net.bn2, True), (net.conv3, net.bn3, True),
+                             (net.conv4, None, False)], rows)
+    return LogSoftmaxFn.apply(logits).view(B, N, -1), trans_feat
 
 
 # ------------------------------------------------------------------------------------------------

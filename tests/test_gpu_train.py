@@ -674,3 +674,43 @@ def test_partseg_net_train_step_vs_reference(dev, golden, gemm_mode):
         if not (cos > (0.999 if gemm_mode == "fp32" else 0.98) and abs(np.linalg.norm(mine) / np.linalg.norm(ref) - 1) < 0.05):
             bad.append((name, round(cos, 4), float(np.linalg.norm(mine)), float(np.linalg.norm(ref))))
     assert not bad, bad
+
+
+def test_pointnet_seg_train_step_vs_reference(dev, golden, gemm_mode):
+    """PointNetSeg(19, 4, feature_transform=True), the default model of the reference's training driver, one iteration as
+    pcdseg.py:166-186 runs it (CrossEntropyLoss + 0.001 * feature_transform_reguliarzer) against the reference's autograd:
+    input / feature transforms (STN, bmm with both gradients), BatchNorm without ReLU ahead of the global max, 1088-wide head."""
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet import PointNetSeg, feature_transform_reguliarzer
+
+    g = golden("train_pointnet_seg_seeded")
+    torch.manual_seed(4444)
+    net = PointNetSeg(19, input_dims=4, feature_transform=True).to(dev).train()
+    pts = T(syn.kitti_batch(2, 1024, config=7), dev)
+    logits, trans_feat = net(pts)
+    assert logits.shape == (2, 1024, 19) and trans_feat.shape == (2, 64, 64)
+    loss = torch.nn.CrossEntropyLoss()(logits.transpose(2, 1), T(g["target"].astype(np.int64), dev))
+    loss = loss + feature_transform_reguliarzer(trans_feat) * 0.001
+    net.zero_grad()
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 3e-4
+    assert rl2(logits.detach().cpu().numpy(), g["logp"]) < (3e-4 if gemm_mode == "fp32" else 1e-3)
+    assert rl2(trans_feat.detach().cpu().numpy(), g["trans_feat"]) < (3e-4 if gemm_mode == "fp32" else 2e-3)
+    bad = []
+    for name, gr in _grads(net).items():
+        ref = g["grad." + name].astype(np.float64)
+        mine = gr.reshape(-1).astype(np.float64)
+        if mine.size > 4096:
+            mine = mine[::31]
+        if np.linalg.norm(mine) < 1e-4 and np.linalg.norm(ref) < 1e-4:
+            continue                                       # analytically zero (bias / beta ahead of a BatchNorm) or tiny
+        if name.endswith(".bias") and np.abs(ref).max() < 1e-3 and np.abs(mine).max() < 1e-3:
+            continue
+        cos = float(mine @ ref / max(np.linalg.norm(mine) * np.linalg.norm(ref), 1e-30))
+        if not (cos > (0.995 if gemm_mode == "fp32" else 0.97) and abs(np.linalg.norm(mine) / np.linalg.norm(ref) - 1) < 0.1):
+            bad.append((name, round(cos, 4), float(np.linalg.norm(mine)), float(np.linalg.norm(ref))))
+    assert not bad, bad
+    for name, buf in net.named_buffers():
+        if not name.endswith("num_batches_tracked"):
+            ref = g["buffer." + name]
+            assert np.abs(buf.cpu().numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), name
