@@ -982,11 +982,12 @@ def test_partseg_msg_smoke_shape(dev):
 
 
 def test_train_mode_raises_where_not_built(dev):
-    """The PointNet++ nets train (tests/test_gpu_train.py); the PointNet family is inference-only and must say so, not fall back."""
-    from pointnet12_b200.model.pointnet import PointNetSeg
+    """The PointNet++ nets and PointNetSeg train (tests/test_gpu_train.py); PointNetCls / PointNetDenseCls are inference-only and
+    must say so, not fall back."""
+    from pointnet12_b200.model.pointnet import PointNetCls
 
     with pytest.raises(NotImplementedError):
-        PointNetSeg(19, 4, True).to(dev).train()(torch.zeros(1, 4, 2048, device=dev))
+        PointNetCls(40, False).to(dev).train()(torch.zeros(2, 3, 1024, device=dev))
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties (C2)

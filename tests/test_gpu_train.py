@@ -686,17 +686,20 @@ def test_pointnet_seg_train_step_vs_reference(dev, golden, gemm_mode):
     g = golden("train_pointnet_seg_seeded")
     torch.manual_seed(4444)
     net = PointNetSeg(19, input_dims=4, feature_transform=True).to(dev).train()
-    pts = T(syn.kitti_batch(2, 1024, config=7), dev)
+    pts = T(syn.kitti_batch(8, 512, config=7), dev)       # 8 clouds: batch statistics of the STN's fc layers need more than 2 rows
     logits, trans_feat = net(pts)
-    assert logits.shape == (2, 1024, 19) and trans_feat.shape == (2, 64, 64)
+    assert logits.shape == (8, 512, 19) and trans_feat.shape == (8, 64, 64)
     loss = torch.nn.CrossEntropyLoss()(logits.transpose(2, 1), T(g["target"].astype(np.int64), dev))
     loss = loss + feature_transform_reguliarzer(trans_feat) * 0.001
     net.zero_grad()
     loss.backward()
-    assert abs(loss.item() - float(g["loss"])) < 3e-4
-    assert rl2(logits.detach().cpu().numpy(), g["logp"]) < (3e-4 if gemm_mode == "fp32" else 1e-3)
-    assert rl2(trans_feat.detach().cpu().numpy(), g["trans_feat"]) < (3e-4 if gemm_mode == "fp32" else 2e-3)
     bad = []
+    if not abs(loss.item() - float(g["loss"])) < 3e-4:
+        bad.append(("loss", loss.item(), float(g["loss"])))
+    if not rl2(logits.detach().cpu().numpy(), g["logp"]) < (3e-4 if gemm_mode == "fp32" else 1e-3):
+        bad.append(("logp", rl2(logits.detach().cpu().numpy(), g["logp"])))
+    if not rl2(trans_feat.detach().cpu().numpy(), g["trans_feat"]) < (3e-4 if gemm_mode == "fp32" else 2e-3):
+        bad.append(("trans_feat", rl2(trans_feat.detach().cpu().numpy(), g["trans_feat"])))
     for name, gr in _grads(net).items():
         ref = g["grad." + name].astype(np.float64)
         mine = gr.reshape(-1).astype(np.float64)
