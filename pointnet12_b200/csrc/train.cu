@@ -164,6 +164,43 @@ __global__ void bn_act_max_kernel(const float* __restrict__ y, int64_t ldy, int6
     }
 }
 
+// Tall variant (K >= 256: the global max over the N points of a cloud in the PointNet nets and group-all levels): one CTA per
+// (group, 32-channel slab), 8 row lanes per channel, then a shared-memory reduction that keeps the FIRST maximum.
+__global__ void __launch_bounds__(256)
+bn_act_max_tall_kernel(const float* __restrict__ y, int64_t ldy, int K, int C, const float* __restrict__ scale,
+                       const float* __restrict__ shift, int relu, float* __restrict__ out, int64_t ldo,
+                       int32_t* __restrict__ argmax) {
+    __shared__ float vmax[8][33];
+    __shared__ int vidx[8][33];
+    const int64_t g = blockIdx.y;
+    const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float m = -CUDART_INF_F;
+    int am = 0;
+    if (c < C) {
+        const float sc = scale[c], sh = shift[c];
+        const float* __restrict__ r = y + g * K * ldy + c;
+        for (int k = ry; k < K; k += 8) {
+            float v = fmaf(r[(int64_t)k * ldy], sc, sh);
+            if (relu) v = fmaxf(v, 0.0f);
+            if (v > m) { m = v; am = k; }           // a lane sees its rows in ascending order: first maximum of the lane
+        }
+    }
+    vmax[ry][lane] = m;
+    vidx[ry][lane] = am;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            const float v = vmax[i][lane];
+            const int k = vidx[i][lane];
+            if (v > m || (v == m && k < am)) { m = v; am = k; }      // ties across lanes: the lowest row index
+        }
+        out[g * ldo + c] = m;
+        argmax[g * C + c] = am;
+    }
+}
+
 // dy = gamma*invstd * (g - s1/n - xhat*s2/n); block 0 also adds s2 to dgamma and s1 to dbeta.
 template <int MODE>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ y, int64_t ldy, int64_t rows, int C,
@@ -601,8 +638,13 @@ PN_EXPORT int pn_bn_act_max_f32(const float* y, int64_t ldy, int64_t groups, int
                                 pn_stream_t stream) {
     PN_REQUIRE(y && scale && shift && out && argmax, PN_ERR_BAD_ARG, "pn_bn_act_max_f32: null pointer");
     PN_REQUIRE(groups > 0 && K > 0 && C > 0 && ldy >= C && ldo >= C, PN_ERR_BAD_ARG, "pn_bn_act_max_f32: bad shape");
-    bn_act_max_kernel<<<ew_blocks(groups * C, 128), 128, 0, (cudaStream_t)stream>>>(y, ldy, groups, K, C, scale, shift, relu, out,
-                                                                                   ldo, argmax);
+    if (K >= 256 && groups <= 65535) {
+        bn_act_max_tall_kernel<<<dim3((unsigned)ceil_div(C, 32), (unsigned)groups), 256, 0, (cudaStream_t)stream>>>(y, ldy, K, C, scale, shift,
+                                                                                                              relu, out, ldo, argmax);
+    } else {
+        bn_act_max_kernel<<<ew_blocks(groups * C, 128), 128, 0, (cudaStream_t)stream>>>(y, ldy, groups, K, C, scale, shift, relu, out,
+                                                                                       ldo, argmax);
+    }
     return finish_launch("pn_bn_act_max_f32");
 }
 

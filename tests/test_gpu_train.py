@@ -717,3 +717,30 @@ def test_pointnet_seg_train_step_vs_reference(dev, golden, gemm_mode):
         if not name.endswith("num_batches_tracked"):
             ref = g["buffer." + name]
             assert np.abs(buf.cpu().numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), name
+
+
+@pytest.mark.parametrize("groups,K,C", [(2, 1000, 70), (8, 512, 1024), (3, 257, 33)])
+def test_tall_max_pool_with_argmax(dev, groups, K, C):
+    """bn_act_max over all points of a cloud (K >= 256: one CTA per cloud and 32-channel slab): values and FIRST-maximum
+    indices, with duplicated rows so that ties exist, and the gradient routing through them."""
+    from pointnet12_b200 import ops
+
+    rng = np.random.default_rng(K + C)
+    y = rng.standard_normal((groups, K, C)).astype(np.float32)
+    y[:, K // 2:K // 2 + 40] = y[:, 10:50]                   # exact duplicates: ties between row k and row k + K/2 - 10
+    st = ops.BatchStats()
+    st.scale, st.shift = T(rng.uniform(0.5, 1.5, C).astype(np.float32), dev), T(rng.standard_normal(C).astype(np.float32), dev)
+    st.mean, st.invstd = st.shift, st.scale
+    for relu in (True, False):
+        pooled, am = ops.bn_act_max(T(y.reshape(groups * K, C), dev), st, K, relu=relu)
+        z = y * st.scale.cpu().numpy() + st.shift.cpu().numpy()
+        z32 = np.float32(y) * st.scale.cpu().numpy() + st.shift.cpu().numpy()
+        if relu:
+            z32 = np.maximum(z32, 0)
+        got_am = am.cpu().numpy().astype(np.int64)
+        got = pooled.cpu().numpy()
+        # the kernel's own values (fused multiply-add) decide the arg-max; check it is A maximum and the FIRST one
+        picked = np.take_along_axis(z32, got_am[:, None, :], 1)[:, 0, :]
+        assert np.abs(got - z32.max(1)).max() < 1e-5 and np.abs(picked - got).max() < 1e-5
+        first = (np.abs(z32 - got[:, None, :]) < 1e-6).argmax(1)
+        assert (got_am <= first + 0).mean() > 0.999           # never later than the first row within rounding of the max

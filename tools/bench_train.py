@@ -30,6 +30,9 @@ def main(argv=None, cpu_baseline=None):
     ap.add_argument("--points", type=int, default=8000)
     ap.add_argument("--eager", action="store_true", help="launch kernel by kernel through autograd instead of one CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="pointnet2", choices=["pointnet2", "pointnet"],
+                    help="pointnet2: PointNet2SemSeg (config C5, default); pointnet: PointNetSeg(19, 4, feature_transform=True), the "
+                         "default model of the reference's driver, eager launches, loss + 0.001 * feature_transform_reguliarzer")
     args = ap.parse_args(argv)
     import torch.distributed as dist
 
@@ -47,7 +50,13 @@ def main(argv=None, cpu_baseline=None):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234)                                   # same initial weights on every rank (DataParallel replicas)
-    net = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
+    if args.model == "pointnet":
+        from pointnet12_b200.model.pointnet import PointNetSeg, feature_transform_reguliarzer
+
+        args.eager = True
+        net = PointNetSeg(19, input_dims=4, feature_transform=True).to(dev).train()
+    else:
+        net = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
     opt = FlatAdam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
     B, N = args.batch, args.points
     pts = torch.from_numpy(syn.kitti_batch(B, N, config=5, first=rank * B)).to(dev)
@@ -61,9 +70,14 @@ def main(argv=None, cpu_baseline=None):
                 e.record()
                 marks.append((name, e))
         mark("start")
-        logp = net(pts)
-        mark("forward")
-        loss = cross_entropy(logp, target)
+        if args.model == "pointnet":
+            logp, trans_feat = net(pts)
+            mark("forward")
+            loss = cross_entropy(logp, target) + feature_transform_reguliarzer(trans_feat) * 0.001
+        else:
+            logp = net(pts)
+            mark("forward")
+            loss = cross_entropy(logp, target)
         mark("loss")
         opt.zero_grad()
         loss.backward()
@@ -164,7 +178,7 @@ def main(argv=None, cpu_baseline=None):
             "metric": "pointnet2_semseg_train_points_per_sec", "value": world * B * N / (ms * 1e-3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "dtype": "f32 (GEMMs as 3-pass split bf16 on tensor cores)" if ops.mlp_mode() == "bf16x3" else "f32 (CUDA-core GEMMs)", "data": "synthetic",
-            "config": {"workload": f"C5: PointNet2SemSeg(19, feature_dims=1) training step (forward, CrossEntropyLoss, backward, "
+            "config": {"workload": f"{'PointNetSeg(19, 4, feature_transform=True)' if args.model == 'pointnet' else 'C5: PointNet2SemSeg(19, feature_dims=1)'} training step (forward, CrossEntropyLoss, backward, "
                                    f"gradient all-reduce, Adam), {B} clouds x {N} points per GPU, seeded random init",
                        "l2": "256 MiB written between timed steps", "launch": "eager" if args.eager else "forward + loss + backward (+ the next batch's sampling / grouping on a side stream) as one CUDA-graph replay, then all-reduce and Adam"},
             "step_ms": {"min": float(times.min()), "median": float(np.median(times)), "max": float(times.max())},
