@@ -99,6 +99,15 @@ def _gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], transp
         return ops.train_gemm(x, w, bias, transposed=transposed, packed=arena.lookup(w, transposed) if arena is not None else None)
     if ops.mlp_mode() == "bf16x3" and ops.PackedChain.supported([(cin, cout)]):
         return ops.mlp_rows_tc(ops.PackedChain([(w, bias, False)], transposed=transposed), x)
+    if ops.mlp_mode() == "bf16x3" and cout > 1024 and ops.PackedChain.supported([(cin, 1024)]):
+        # wider than one chain takes (PointNetSeg's 1088-channel input gradient): column slabs of <= 1024 outputs
+        out = torch.empty((x.shape[0], cout), dtype=torch.float32, device=x.device)
+        for c0 in range(0, cout, 1024):
+            c1 = min(cout, c0 + 1024)
+            wk = (w[:, c0:c1] if transposed else w[c0:c1]).contiguous()
+            bk = bias[c0:c1].contiguous() if bias is not None else None
+            ops.mlp_rows_tc(ops.PackedChain([(wk, bk, False)], transposed=transposed), x, out=out[:, c0:c1])
+        return out
     return ops.linear(x, ops.transpose(w) if transposed else w, bias, relu=False)
 
 

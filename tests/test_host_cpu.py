@@ -174,3 +174,17 @@ def test_reference_import_path_aliases():
                  "sample_and_group_all", "PointNetSetAbstraction", "PointNetSetAbstractionMsg",
                  "PointNetFeaturePropagation"):
         assert hasattr(mu, name)
+
+
+def test_train_mode_refuses_cpu_tensors():
+    """train() mode has no CPU fallback either: every trainable net refuses CPU tensors before any work is done."""
+    from pointnet12_b200.model.pointnet import PointNetSeg
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsSsg, PointNet2PartSegSsg, PointNet2SemSeg
+    from pointnet12_b200.train import cross_entropy
+
+    for net, x in ((PointNet2SemSeg(19, feature_dims=1), torch.zeros(1, 4, 2048)), (PointNet2ClsSsg(), torch.zeros(2, 3, 1024)),
+                   (PointNet2PartSegSsg(50), torch.zeros(2, 3, 1024)), (PointNetSeg(19, 4, True), torch.zeros(2, 4, 512))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            net.train()(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cross_entropy(torch.zeros(1, 8, 19), torch.zeros(1, 8, dtype=torch.long))
