@@ -956,3 +956,69 @@ class GraphedTrainStep:
         torch.autograd.graph.increment_version(self._bn_buffers)
         self.opt.step(self.opt.all_reduce(self.group))
         return st["loss"][p]
+
+
+class GraphedStep:
+    """Generic CUDA-graph training iteration for nets whose train-mode forward draws nothing on the host (PointNetSeg: no
+    sampling, no dropout): forward + loss + backward are captured once per input shape and replayed; the gradient exchange and
+    Adam follow on the same stream.  loss_fn(net, points, target) -> scalar loss tensor with grad_fn.
+
+        step = GraphedStep(net, FlatAdam(net.parameters(), ...),
+                           lambda net, x, t: cross_entropy((out := net(x))[0], t) + feature_transform_reguliarzer(out[1]) * 0.001)
+        loss = step(points, target)
+    """
+
+    def __init__(self, net, optimizer: "FlatAdam", loss_fn, group=None, warmup: int = 2):
+        self.net = net.module if hasattr(net, "module") else net
+        self.opt, self.loss_fn, self.group, self.warmup = optimizer, loss_fn, group, warmup
+        self._graphs = {}
+        self._bn_buffers = [b for m in self.net.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)
+                            for b in (m.running_mean, m.running_var, m.num_batches_tracked) if b is not None]
+
+    def _fb(self, st):
+        loss = self.loss_fn(self.net, st["x"], st["target"])
+        self.opt.zero_grad()
+        loss.backward()
+        return loss
+
+    def _build(self, points, target):
+        from . import _native as nv
+
+        dev = points.device
+        st = {"x": points.clone(), "target": target.clone()}
+        keep = [t.clone() for t in (self.opt.flat, *self._bn_buffers)]           # warm-up must not train
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self._fb(st)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for t, k in zip((self.opt.flat, *self._bn_buffers), keep):
+                t.copy_(k)
+        graph = torch.cuda.CUDAGraph()
+        n0 = nv.launch_count
+        with torch.cuda.graph(graph):
+            st["loss"] = self._fb(st)
+        st["launches"], st["graph"] = nv.launch_count - n0, graph
+        return st
+
+    def __call__(self, points: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        from . import _native as nv
+
+        if not self.net.training:
+            raise RuntimeError("GraphedStep: call net.train() first")
+        key = (tuple(points.shape), tuple(target.shape), points.device)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = self._build(points, target)
+        if points.data_ptr() != st["x"].data_ptr():
+            st["x"].copy_(points, non_blocking=True)
+        if target.data_ptr() != st["target"].data_ptr():
+            st["target"].copy_(target, non_blocking=True)
+        st["graph"].replay()
+        nv.launch_count += st["launches"]
+        torch.autograd.graph.increment_version(self._bn_buffers)
+        self.opt.step(self.opt.all_reduce(self.group))
+        return st["loss"]

@@ -744,3 +744,34 @@ def test_tall_max_pool_with_argmax(dev, groups, K, C):
         assert np.abs(got - z32.max(1)).max() < 1e-5 and np.abs(picked - got).max() < 1e-5
         first = (np.abs(z32 - got[:, None, :]) < 1e-6).argmax(1)
         assert (got_am <= first + 0).mean() > 0.999           # never later than the first row within rounding of the max
+
+
+def test_graphed_step_pointnet_matches_eager(dev):
+    """GraphedStep (generic CUDA-graph iteration) on PointNetSeg == the eager iteration with the same loss."""
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet import PointNetSeg, feature_transform_reguliarzer
+    from pointnet12_b200.train import FlatAdam, GraphedStep, cross_entropy
+
+    pts = T(syn.kitti_batch(4, 1024, config=7), dev)
+    target = T(np.random.default_rng(2).integers(0, 19, (4, 1024)), dev)
+    torch.manual_seed(5)
+    a = PointNetSeg(19, 4, True).to(dev).train()
+    b = PointNetSeg(19, 4, True).to(dev).train()
+    b.load_state_dict(a.state_dict())
+
+    def loss_fn(n, x, t):
+        out, tf = n(x)
+        return cross_entropy(out, t) + feature_transform_reguliarzer(tf) * 0.001
+
+    opt_a, opt_b = FlatAdam(a.parameters(), lr=1e-3, weight_decay=1e-4), FlatAdam(b.parameters(), lr=1e-3, weight_decay=1e-4)
+    runner = GraphedStep(b, opt_b, loss_fn)
+    la, lb = [], []
+    for _ in range(3):
+        loss = loss_fn(a, pts, target)
+        opt_a.zero_grad()
+        loss.backward()
+        opt_a.step()
+        la.append(loss.item())
+        lb.append(runner(pts, target).item())
+    assert abs(la[0] - lb[0]) < 1e-5 and max(abs(x - y) / x for x, y in zip(la, lb)) < 2e-2, (la, lb)
+    assert la[-1] < la[0] and int(b.bn1.num_batches_tracked) == 3

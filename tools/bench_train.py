@@ -53,7 +53,6 @@ def main(argv=None, cpu_baseline=None):
     if args.model == "pointnet":
         from pointnet12_b200.model.pointnet import PointNetSeg, feature_transform_reguliarzer
 
-        args.eager = True
         net = PointNetSeg(19, input_dims=4, feature_transform=True).to(dev).train()
     else:
         net = PointNet2SemSeg(19, feature_dims=1).to(dev).train()
@@ -88,8 +87,20 @@ def main(argv=None, cpu_baseline=None):
         mark("adam")
         return loss
 
-    graphed = None if args.eager else GraphedTrainStep(net, opt)
     eager_step = step
+    if args.eager:
+        graphed = None
+    elif args.model == "pointnet":
+        from pointnet12_b200.train import GraphedStep
+
+        def pn_loss(n, x, t):
+            out, trans_feat = n(x)
+            return cross_entropy(out, t) + feature_transform_reguliarzer(trans_feat) * 0.001
+
+        gstep = GraphedStep(net, opt, pn_loss)
+        graphed = lambda x, t, next_points=None: gstep(x, t)   # noqa: E731  (nothing to prefetch: no sampling stage)
+    else:
+        graphed = GraphedTrainStep(net, opt)
     if graphed is not None:
         def step(marks=None):                                  # noqa: F811
             # the upcoming batch is known (a loader runs ahead): its geometry is prefetched during this iteration
