@@ -19,7 +19,7 @@ The dropout mask is an INPUT here (the reference draws it from torch's generator
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 

@@ -211,7 +211,7 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
                                       packed=arena.lookup(conv.weight, True) if arena is not None else None)
             stats_done = True
         else:
-            dz = _gemm(dy, conv.weight.detach().reshape(w.shape), None, transposed=True, arena=arena) if (li > 0 or need_dx) else None
+            dz = _gemm(dy, w, None, transposed=True, arena=arena) if (li > 0 or need_dx) else None
     return dz, grads
 
 

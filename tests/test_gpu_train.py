@@ -594,7 +594,6 @@ def test_cls_nets_train_step_vs_reference(dev, golden, gemm_mode, tag, cls_name)
     reference's own autograd (tests/golden/train_cls_seeded.npz: forward, F.nll_loss, backward on 4 clouds x 1024 points)."""
     from pointnet12_b200 import synthetic as syn
     from pointnet12_b200.model import pointnet2 as ours
-    from pointnet12_b200.model.pointnet_util import draw_fps_starts  # noqa: F401  (the draws are replayed through the seed)
 
     g = golden("train_cls_seeded")
     torch.manual_seed(4242)

@@ -12,7 +12,6 @@ L2 norm, and by 3e-4 .. 5e-4 between 1 and 8 threads.  The oracle sits inside th
 float64 reference); the limits below are that band with a margin.
 """
 import numpy as np
-import pytest
 import torch
 
 from oracle import oracle as orc
