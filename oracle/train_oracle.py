@@ -11,9 +11,12 @@ what the reference does in one iteration of its training loop, pcdseg.py:157-186
     loss.backward(); optimizer.step()                     torch.optim.Adam(lr, (0.9, 0.999), 1e-8, weight_decay=1e-4)
 
 and of test_kitti_semseg (pcdseg.py:58-97).  Parity status: PINNED -- tests/golden/train_step_ckpt.npz holds the loss,
-log-probabilities, every parameter gradient, the updated BatchNorm buffers and the Adam-updated parameters produced by the
-reference itself (oracle/gen_golden_train.py imports /root/reference/model and runs its autograd on the CPU);
-tests/test_oracle_golden.py checks this file against them.
+log-probabilities, every parameter gradient and the updated BatchNorm buffers produced by the reference itself, and
+train_blocks_seeded.npz one set-abstraction and one feature-propagation block (oracle/gen_golden_train.py imports
+/root/reference/model and runs its autograd on the CPU); tests/test_train_oracle.py checks this file against them, and
+adam_step against torch.optim.Adam.  (The classification / part-segmentation nets and PointNetSeg have no restatement here:
+their CUDA training path is checked directly against the reference's autograd fixtures, train_cls_seeded.npz and
+train_pointnet_seg_seeded.npz.)
 
 The dropout mask is an INPUT here (the reference draws it from torch's generator; the golden generator records it).
 """
