@@ -192,6 +192,27 @@ def pointnet_seg(ref):
     for name, b in net.named_buffers():
         if not name.endswith("num_batches_tracked"):
             arrays["buffer." + name] = b.detach().numpy()
+    # PointNetCls(40, feature_transform=True) (pointnet.py:133-151): dropout sits between fc2 and bn2
+    torch.manual_seed(4545)
+    cnet = rp.PointNetCls(40, feature_transform=True).train()
+    torch.manual_seed(4545)
+    cmine = ours.PointNetCls(40, feature_transform=True)
+    assert all(torch.equal(a, b) for a, b in zip(cnet.state_dict().values(), cmine.state_dict().values()))
+    cx = syn.modelnet_batch(8, 512, seed=4300)
+    ctgt = np.random.default_rng(4300).integers(0, 40, size=(8,)).astype(np.int64)
+    seen = {}
+    cnet.dropout.register_forward_hook(lambda m, i, o: seen.update(x=i[0].detach().clone(), y=o.detach().clone()))
+    torch.manual_seed(3)
+    clogp, ctf = cnet(torch.from_numpy(cx))
+    closs = torch.nn.functional.nll_loss(clogp, torch.from_numpy(ctgt)) + rp.feature_transform_reguliarzer(ctf) * 0.001
+    cnet.zero_grad()
+    closs.backward()
+    arrays.update({"cls.target": ctgt, "cls.logp": clogp.detach().numpy(), "cls.loss": np.float64(closs.item()),
+                   "cls.keep": torch.where(seen["x"] != 0, seen["y"] != 0, torch.ones_like(seen["x"], dtype=torch.bool)).numpy().astype(np.uint8)})
+    for name, p in cnet.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1)
+        arrays["cls.grad." + name] = (g if g.size <= 4096 else g[::31]).astype(np.float32)
+    print(f"PointNetCls: loss {closs.item():.5f}")
     path = os.path.join(OUT, "train_pointnet_seg_seeded.npz")
     np.savez_compressed(path, **arrays)
     print(f"PointNetSeg: loss {loss.item():.5f}; wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")

@@ -171,8 +171,11 @@ class PointNetCls(nn.Module):
         self.relu = nn.ReLU()
         self._folded = FoldedLayers()
 
-    def forward(self, x):
-        _eval_only(self)
+    def forward(self, x, dropout_mask=None):
+        if self.training:
+            from ..train import pointnet_cls_train
+
+            return pointnet_cls_train(self, x, dropout_mask)
         g, _, _, trans_feat = self.feat.encode_rows(_point_rows(x))
         (w1, b1), (w2, b2), (w3, b3) = self._folded.get([self.fc1, self.fc2, self.fc3], [self.bn1, self.bn2, None])
         h = ops.linear(g, w1, b1, relu=True)

@@ -458,6 +458,50 @@ class LogSoftmaxFn(torch.autograd.Function):
         return ops.log_softmax_backward(dy.contiguous(), ctx.saved_tensors[0])
 
 
+class BatchNormActFn(torch.autograd.Function):
+    """A BatchNorm (batch statistics) + optional ReLU on rows that does not directly follow its linear layer (PointNetCls:
+    relu(bn2(dropout(fc2(x)))), pointnet.py:148)."""
+
+    @staticmethod
+    def forward(ctx, bn, relu, x, gamma, beta):
+        x = x.contiguous()
+        st = ops.bn_batch_stats(x, bn)
+        ctx.bn, ctx.relu, ctx.st = bn, relu, st
+        ctx.save_for_backward(x)
+        return ops.bn_act(x, st, relu)
+
+    @staticmethod
+    def backward(ctx, dz):
+        (x,) = ctx.saved_tensors
+        dy, dgamma, dbeta = ops.bn_act_backward(x, ctx.st, dz.contiguous(), ctx.relu)
+        return None, None, dy, dgamma, dbeta
+
+
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed_offset, mask):
+        y, mask = ops.dropout(x.contiguous(), p, seed_offset=seed_offset, mask=mask)
+        ctx.p, ctx.mask = p, mask
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(dy.contiguous(), ctx.p, mask=ctx.mask)[0], None, None, None
+
+
+def pointnet_cls_train(net, x: torch.Tensor, dropout_mask=None):
+    """PointNetCls.forward (pointnet.py:146-151) in train() mode: x [B,3,N] -> (log_probs [B,k], trans_feat)."""
+    ops._need_cuda(x, "x")
+    g, _, _, trans_feat = pointnet_encoder_train(net.feat, x.permute(0, 2, 1))
+    h = mlp_rows_train([(net.fc1, net.bn1, True), (net.fc2, None, False)], g)
+    p = float(net.dropout.p)
+    if p > 0.0 or dropout_mask is not None:
+        h = DropoutFn.apply(h, p, None if dropout_mask is not None else dropout_seed(x.device), dropout_mask)
+    h = BatchNormActFn.apply(net.bn2, True, h, net.bn2.weight, net.bn2.bias)
+    logits = mlp_rows_train([(net.fc3, None, False)], h)
+    return LogSoftmaxFn.apply(logits), trans_feat
+
+
 def stn_train(stn, x_pm: torch.Tensor) -> torch.Tensor:
     """STN3d / STNkd.forward (pointnet.py:27-45, :66-84) in train() mode: x_pm [B,N,k] -> [B,k,k]."""
     B, N, k = x_pm.shape

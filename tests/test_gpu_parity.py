@@ -982,12 +982,12 @@ def test_partseg_msg_smoke_shape(dev):
 
 
 def test_train_mode_raises_where_not_built(dev):
-    """The PointNet++ nets and PointNetSeg train (tests/test_gpu_train.py); PointNetCls / PointNetDenseCls are inference-only and
+    """The PointNet++ nets, PointNetSeg and PointNetCls train (tests/test_gpu_train.py); PointNetDenseCls is inference-only and
     must say so, not fall back."""
-    from pointnet12_b200.model.pointnet import PointNetCls
+    from pointnet12_b200.model.pointnet import PointNetDenseCls
 
     with pytest.raises(NotImplementedError):
-        PointNetCls(40, False).to(dev).train()(torch.zeros(2, 3, 1024, device=dev))
+        PointNetDenseCls(16, 50).to(dev).train()(torch.zeros(2, 3, 1024, device=dev), torch.zeros(2, 16, device=dev))
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties (C2)

@@ -774,3 +774,36 @@ def test_graphed_step_pointnet_matches_eager(dev):
         lb.append(runner(pts, target).item())
     assert abs(la[0] - lb[0]) < 1e-5 and max(abs(x - y) / x for x, y in zip(la, lb)) < 2e-2, (la, lb)
     assert la[-1] < la[0] and int(b.bn1.num_batches_tracked) == 3
+
+
+def test_pointnet_cls_train_step_vs_reference(dev, golden, gemm_mode):
+    """PointNetCls(40, feature_transform=True): BatchNorm that follows a dropout instead of its linear layer
+    (relu(bn2(dropout(fc2(x)))), pointnet.py:148), against the reference's autograd."""
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet import PointNetCls, feature_transform_reguliarzer
+
+    g = golden("train_pointnet_seg_seeded")
+    torch.manual_seed(4545)
+    net = PointNetCls(40, feature_transform=True).to(dev).train()
+    logp, tf = net(T(syn.modelnet_batch(8, 512, seed=4300), dev), dropout_mask=T(g["cls.keep"], dev))
+    loss = torch.nn.functional.nll_loss(logp, T(g["cls.target"], dev)) + feature_transform_reguliarzer(tf) * 0.001
+    net.zero_grad()
+    loss.backward()
+    bad = []
+    if not abs(loss.item() - float(g["cls.loss"])) < 5e-4:
+        bad.append(("loss", loss.item(), float(g["cls.loss"])))
+    if not rl2(logp.detach().cpu().numpy(), g["cls.logp"]) < (5e-4 if gemm_mode == "fp32" else 2e-3):
+        bad.append(("logp", rl2(logp.detach().cpu().numpy(), g["cls.logp"])))
+    for name, gr in _grads(net).items():
+        ref = g["cls.grad." + name].astype(np.float64)
+        mine = gr.reshape(-1).astype(np.float64)
+        if mine.size > 4096:
+            mine = mine[::31]
+        if np.linalg.norm(mine) < 1e-4 and np.linalg.norm(ref) < 1e-4:
+            continue
+        if name.endswith(".bias") and np.abs(ref).max() < 1e-3 and np.abs(mine).max() < 1e-3:
+            continue
+        cos = float(mine @ ref / max(np.linalg.norm(mine) * np.linalg.norm(ref), 1e-30))
+        if not (cos > (0.995 if gemm_mode == "fp32" else 0.97) and abs(np.linalg.norm(mine) / np.linalg.norm(ref) - 1) < 0.1):
+            bad.append((name, round(cos, 4), float(np.linalg.norm(mine)), float(np.linalg.norm(ref))))
+    assert not bad, bad
