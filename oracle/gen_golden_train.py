@@ -213,6 +213,33 @@ def pointnet_seg(ref):
         g = p.grad.detach().numpy().reshape(-1)
         arrays["cls.grad." + name] = (g if g.size <= 4096 else g[::31]).astype(np.float32)
     print(f"PointNetCls: loss {closs.item():.5f}")
+    # PointNetDenseCls(16, 50) (pointnet.py:153-228): two heads sharing the encoder, 4944-channel concat
+    torch.manual_seed(4646)
+    dnet = rp.PointNetDenseCls(16, 50).train()
+    torch.manual_seed(4646)
+    dmine = ours.PointNetDenseCls(16, 50)
+    assert all(torch.equal(a, b) for a, b in zip(dnet.state_dict().values(), dmine.state_dict().values()))
+    dx = syn.modelnet_batch(8, 256, seed=4400)
+    rng = np.random.default_rng(4400)
+    dlabel = np.eye(16, dtype=np.float32)[rng.integers(0, 16, 8)]
+    dcls, dseg = rng.integers(0, 16, size=(8,)).astype(np.int64), rng.integers(0, 50, size=(8, 256)).astype(np.int64)
+    seen = {}
+    dnet.dropout.register_forward_hook(lambda m, i, o: seen.update(x=i[0].detach().clone(), y=o.detach().clone()))
+    torch.manual_seed(3)
+    net1, net2, dtf = dnet(torch.from_numpy(dx), torch.from_numpy(dlabel))
+    dloss = (torch.nn.functional.cross_entropy(net1, torch.from_numpy(dcls))
+             + torch.nn.functional.nll_loss(net2.reshape(-1, 50), torch.from_numpy(dseg).reshape(-1))
+             + rp.feature_transform_reguliarzer(dtf) * 0.001)
+    dnet.zero_grad()
+    dloss.backward()
+    arrays.update({"dense.label": dlabel, "dense.cls_target": dcls, "dense.seg_target": dseg.astype(np.int8),
+                   "dense.cls_logits": net1.detach().numpy(), "dense.seg_logp": net2.detach().numpy(),
+                   "dense.loss": np.float64(dloss.item()),
+                   "dense.keep": torch.where(seen["x"] != 0, seen["y"] != 0, torch.ones_like(seen["x"], dtype=torch.bool)).numpy().astype(np.uint8)})
+    for name, p in dnet.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1)
+        arrays["dense.grad." + name] = (g if g.size <= 4096 else g[::63]).astype(np.float32)
+    print(f"PointNetDenseCls: loss {dloss.item():.5f}")
     path = os.path.join(OUT, "train_pointnet_seg_seeded.npz")
     np.savez_compressed(path, **arrays)
     print(f"PointNetSeg: loss {loss.item():.5f}; wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB")

@@ -260,8 +260,11 @@ class PointNetDenseCls(nn.Module):
         self.bns3 = nn.BatchNorm1d(128)
         self._folded = FoldedLayers()
 
-    def forward(self, point_cloud, label):
-        _eval_only(self)
+    def forward(self, point_cloud, label, dropout_mask=None):
+        if self.training:
+            from ..train import pointnet_densecls_train
+
+            return pointnet_densecls_train(self, point_cloud, label, dropout_mask)
         B, _, N = point_cloud.shape
         L = self._folded.get(
             [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5, self.fc1, self.fc2, self.fc3,

@@ -502,6 +502,40 @@ def pointnet_cls_train(net, x: torch.Tensor, dropout_mask=None):
     return LogSoftmaxFn.apply(logits), trans_feat
 
 
+def pointnet_densecls_train(net, point_cloud: torch.Tensor, label: torch.Tensor, dropout_mask=None):
+    """PointNetDenseCls.forward (pointnet.py:186-228) in train() mode: (point_cloud [B,3,N], label [B,16]) ->
+    (cls logits [B,cat_num], seg log_probs [B,N,part_num], trans_feat).  The per-point stacks, transforms and heads run on the
+    autograd blocks above; the global max of out5 (which is also a per-point input of the segmentation head) and the concats are
+    torch glue."""
+    ops._need_cuda(point_cloud, "point_cloud")
+    B, _, N = point_cloud.shape
+    x_pm = point_cloud.permute(0, 2, 1).contiguous()
+    trans = stn_train(net.stn, x_pm)
+    pct = BmmPointsFn.apply(x_pm, trans)
+    out1 = mlp_rows_train([(net.conv1, net.bn1, True)], pct.reshape(B * N, 3))
+    out2 = mlp_rows_train([(net.conv2, net.bn2, True)], out1)
+    out3 = mlp_rows_train([(net.conv3, net.bn3, True)], out2)
+    trans_feat = stn_train(net.fstn, out3.view(B, N, 128))
+    nt = BmmPointsFn.apply(out3.view(B, N, 128), trans_feat)
+    out4 = mlp_rows_train([(net.conv4, net.bn4, True)], nt.reshape(B * N, 128))
+    out5 = mlp_rows_train([(net.conv5, net.bn5, False)], out4)                              # BatchNorm without ReLU, :209
+    out_max = out5.view(B, N, 2048).max(dim=1)[0]                                           # [B, 2048]
+    # classification head: fc1-bnc1-relu, fc2-dropout-bnc2-relu, fc3 (raw logits, :213-215)
+    h = mlp_rows_train([(net.fc1, net.bnc1, True), (net.fc2, None, False)], out_max)
+    p = float(net.dropout.p)
+    if p > 0.0 or dropout_mask is not None:
+        h = DropoutFn.apply(h, p, None if dropout_mask is not None else dropout_seed(h.device), dropout_mask)
+    h = BatchNormActFn.apply(net.bnc2, True, h, net.bnc2.weight, net.bnc2.bias)
+    cls_logits = mlp_rows_train([(net.fc3, None, False)], h)
+    # segmentation head on cat([expand(out_max | label), out1 .. out5]) = 4944 channels per point (:218-227)
+    expand = torch.cat([out_max, label.float()], 1)[:, None, :].expand(B, N, 2048 + label.shape[1])
+    concat = torch.cat([expand, out1.view(B, N, -1), out2.view(B, N, -1), out3.view(B, N, -1), out4.view(B, N, -1),
+                        out5.view(B, N, -1)], dim=2).reshape(B * N, -1)
+    seg = mlp_rows_train([(net.convs1, net.bns1, True), (net.convs2, net.bns2, True), (net.convs3, net.bns3, True),
+                          (net.convs4, None, False)], concat)
+    return cls_logits, LogSoftmaxFn.apply(seg).view(B, N, -1), trans_feat
+
+
 def stn_train(stn, x_pm: torch.Tensor) -> torch.Tensor:
     """STN3d / STNkd.forward (pointnet.py:27-45, :66-84) in train() mode: x_pm [B,N,k] -> [B,k,k]."""
     B, N, k = x_pm.shape

@@ -981,13 +981,13 @@ def test_partseg_msg_smoke_shape(dev):
     assert torch.allclose(out.exp().sum(-1), torch.ones(8, 2048, device=dev), atol=1e-4)
 
 
-def test_train_mode_raises_where_not_built(dev):
-    """The PointNet++ nets, PointNetSeg and PointNetCls train (tests/test_gpu_train.py); PointNetDenseCls is inference-only and
-    must say so, not fall back."""
+def test_every_net_has_a_train_mode(dev):
+    """No net raises in train() mode any more (tests/test_gpu_train.py checks each against the reference's autograd); what
+    still raises is a CPU tensor (tests/test_host_cpu.py)."""
     from pointnet12_b200.model.pointnet import PointNetDenseCls
 
-    with pytest.raises(NotImplementedError):
-        PointNetDenseCls(16, 50).to(dev).train()(torch.zeros(2, 3, 1024, device=dev), torch.zeros(2, 16, device=dev))
+    out = PointNetDenseCls(16, 50).to(dev).train()(torch.randn(4, 3, 256, device=dev), torch.zeros(4, 16, device=dev))
+    assert out[1].grad_fn is not None and out[0].shape == (4, 16)
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties (C2)

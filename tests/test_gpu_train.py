@@ -807,3 +807,41 @@ def test_pointnet_cls_train_step_vs_reference(dev, golden, gemm_mode):
         if not (cos > (0.995 if gemm_mode == "fp32" else 0.97) and abs(np.linalg.norm(mine) / np.linalg.norm(ref) - 1) < 0.1):
             bad.append((name, round(cos, 4), float(np.linalg.norm(mine)), float(np.linalg.norm(ref))))
     assert not bad, bad
+
+
+def test_pointnet_densecls_train_step_vs_reference(dev, golden, gemm_mode):
+    """PointNetDenseCls(16, 50): shared encoder with two heads (raw classification logits and per-point log-probabilities over a
+    4944-channel concat), against the reference's autograd."""
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet import PointNetDenseCls, feature_transform_reguliarzer
+
+    g = golden("train_pointnet_seg_seeded")
+    torch.manual_seed(4646)
+    net = PointNetDenseCls(16, 50).to(dev).train()
+    cls_logits, seg_logp, tf = net(T(syn.modelnet_batch(8, 256, seed=4400), dev), T(g["dense.label"], dev),
+                                   dropout_mask=T(g["dense.keep"], dev))
+    assert cls_logits.shape == (8, 16) and seg_logp.shape == (8, 256, 50) and tf.shape == (8, 128, 128)
+    loss = (torch.nn.functional.cross_entropy(cls_logits, T(g["dense.cls_target"], dev))
+            + torch.nn.functional.nll_loss(seg_logp.reshape(-1, 50), T(g["dense.seg_target"].astype(np.int64), dev).reshape(-1))
+            + feature_transform_reguliarzer(tf) * 0.001)
+    net.zero_grad()
+    loss.backward()
+    bad = []
+    if not abs(loss.item() - float(g["dense.loss"])) < 1e-3:
+        bad.append(("loss", loss.item(), float(g["dense.loss"])))
+    for key, got in (("dense.cls_logits", cls_logits), ("dense.seg_logp", seg_logp)):
+        if not rl2(got.detach().cpu().numpy(), g[key]) < (1e-3 if gemm_mode == "fp32" else 5e-3):
+            bad.append((key, rl2(got.detach().cpu().numpy(), g[key])))
+    for name, gr in _grads(net).items():
+        ref = g["dense.grad." + name].astype(np.float64)
+        mine = gr.reshape(-1).astype(np.float64)
+        if mine.size > 4096:
+            mine = mine[::63]
+        if np.linalg.norm(mine) < 1e-4 and np.linalg.norm(ref) < 1e-4:
+            continue
+        if name.endswith(".bias") and np.abs(ref).max() < 1e-3 and np.abs(mine).max() < 1e-3:
+            continue
+        cos = float(mine @ ref / max(np.linalg.norm(mine) * np.linalg.norm(ref), 1e-30))
+        if not (cos > (0.99 if gemm_mode == "fp32" else 0.95) and abs(np.linalg.norm(mine) / np.linalg.norm(ref) - 1) < 0.15):
+            bad.append((name, round(cos, 4), float(np.linalg.norm(mine)), float(np.linalg.norm(ref))))
+    assert not bad, bad
