@@ -4,8 +4,8 @@ Reference: pcdseg.py:157-186 -- `model.train()`, `logits = model(points)`, `nn.C
 target)`, `loss.backward()`, `optimizer.step()` with torch.optim.Adam(lr, betas (0.9, 0.999), eps 1e-8, weight_decay 1e-4)
 under nn.DataParallel -- and pcdseg.py:58-97 (test_kitti_semseg).
 
-The drop-in contract is the reference's own: in train() mode the modules of model/pointnet_util.py, the five PointNet++ nets
-and PointNetSeg (both models pcdseg.py can train) return tensors that carry a grad_fn, so the reference's loop (torch loss, loss.backward(), any torch optimizer) runs
+The drop-in contract is the reference's own: in train() mode the modules of model/pointnet_util.py, and every net of
+model/pointnet2.py and model/pointnet.py (both models pcdseg.py can train among them) return tensors that carry a grad_fn, so the reference's loop (torch loss, loss.backward(), any torch optimizer) runs
 unchanged; every kernel underneath -- forward with batch-statistics BatchNorm, dropout, and the whole backward -- is ours
 (csrc/train.cu + linear.cu + the sampling / grouping kernels of the inference path).  One torch.autograd.Function per
 block (set abstraction, feature propagation, segmentation head): autograd only connects them.
