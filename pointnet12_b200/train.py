@@ -969,7 +969,8 @@ class GraphedTrainStep:
         with torch.no_grad():
             for t, k in zip((self.opt.flat, *self._bn_buffers), keep):
                 t.copy_(k)
-        geo_stream = _geometry_stream(dev)
+        geo_stream = torch.cuda.Stream(dev)      # the runner's own side stream: never shared with eager (uncaptured) work
+        st["geo_stream"] = geo_stream
         for p in (0, 1):
             graph = torch.cuda.CUDAGraph()
             n0 = nv.launch_count
