@@ -22,7 +22,7 @@ PN_EXPORT int pn_set_pdl(int enabled) {
     return PN_OK;
 }
 
-PN_EXPORT int pn_version(void) { return 200; /* 0.2.0 */ }
+PN_EXPORT int pn_version(void) { return 300; /* 0.3.0: training step, metrics, scan pre-processing, chamfer / class merge */ }
 
 PN_EXPORT const char* pn_last_error_string(void) { return pn::g_err; }
 

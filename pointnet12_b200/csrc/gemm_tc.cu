@@ -377,7 +377,6 @@ train_gemm_kernel(const Args a) {
     } else {
         // ================= epilogue (warps 4-7): thread = row (TMEM lane), all output channels =================
         const int q = warp - 4;                                  // a warp reads the TMEM lanes of its quarter
-        const int et = tid - THREADS / 2;                        // 0..127
         const int nch = a.n_pad / 32;
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int b = (int)(it % NA);
