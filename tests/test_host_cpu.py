@@ -188,3 +188,36 @@ def test_train_mode_refuses_cpu_tensors():
             net.train()(x)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cross_entropy(torch.zeros(1, 8, 19), torch.zeros(1, 8, dtype=torch.long))
+
+
+def test_training_abi_argument_validation_needs_no_gpu():
+    """The training / pre-processing entry points validate their arguments before any launch (no GPU needed)."""
+    lib = nv.lib()
+    assert lib.pn_version() >= 300
+    # planning helpers
+    assert lib.pn_train_gemm_supported(128, 128) == 1 and lib.pn_train_gemm_supported(4, 32) == 1
+    assert lib.pn_train_gemm_supported(259, 256) == 0            # 288 x 256 x 4 bytes of weights > 128 KB
+    assert lib.pn_train_gemm_supported(128, 512) == 0            # more than 256 output channels
+    assert lib.pn_train_gemm_scratch_bytes(67, 64) == 96 * 64 * 4 and lib.pn_train_gemm_scratch_bytes(259, 256) == 0
+    assert lib.pn_scan_workspace_bytes(8, 120000) == 8 * 59 * 4 and lib.pn_scan_workspace_bytes(0, 5) == 0
+    # null pointers / bad shapes are refused with a message, nothing is launched
+    assert lib.pn_bn_stats_f32(None, 128, 10, 128, None, None, None) == -1
+    assert b"null pointer" in lib.pn_last_error_string()
+    buf = (C.c_float * 4)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.pn_bn_stats_f32(p, 2, 10, 4, p, p, None) == -1    # leading dimension smaller than the row
+    assert lib.pn_bn_bwd_stats_f32(p, 4, 10, 4, p, 4, p, 3, p, p, p, p, 1, p, p, None) == -1 and b"multiple of K" in lib.pn_last_error_string()
+    assert lib.pn_grad_weight_f32(p, 4, p, 4, 0, 4, 4, p, 4, None, None) == -1
+    assert lib.pn_grad_weight_set_ctas_per_sm(3) == -1 and lib.pn_grad_weight_set_ctas_per_sm(1) == 0
+    assert lib.pn_dropout_f32(p, 4, 1, 4, C.c_float(1.5), p, None, None, p, 4, None) == -1       # p must be < 1
+    assert lib.pn_adam_f32(p, p, p, p, 4, C.c_float(1e-3), C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(0.0), 0,
+                           C.c_float(1.0), None) == -1 and b"step" in lib.pn_last_error_string()
+    assert lib.pn_seg_metrics_f32(p, 100, p, 1, 100, None, p, None) == -1                       # more than 64 classes
+    q = C.c_void_p(1 << 20)          # a 128-byte aligned address; validation fails before anything is dereferenced
+    assert lib.pn_train_gemm_bf16x3(p, 259, 10, 259, None, None, 0, p, 0, None, 256, p, 256, None, None, q, None) == -2
+    assert b"does not fit" in lib.pn_last_error_string()
+    assert lib.pn_train_gemm_bf16x3(p, 4, 10, 4, p, None, 0, p, 0, None, 4, p, 4, None, None, q, None) == -1   # scale without shift
+    assert lib.pn_train_gemm_bf16x3(p, 4, 10, 4, None, None, 0, p, 0, None, 4, p, 4, None, None, C.c_void_p((1 << 20) + 4), None) == -3
+    assert lib.pn_scan_sample_f32(p, p, p, 1, p, 4, p, p, 8, None, None, C.c_float(0.0), C.c_float(0.0), None, p, p, None) == -1
+    assert b"choice indices or a Philox seed" in lib.pn_last_error_string()
+    assert lib.pn_chamfer_f32(p, 3, 3, 1, p, 3, 3, 1, 1, 1, 1, 9, None, p, None) == -1            # D <= 8
