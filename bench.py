@@ -36,6 +36,7 @@ if ROOT not in sys.path:
 
 CKPT = os.path.join(ROOT, "tests", "golden", "pointnet2-inview-0.55884-0001.pth")
 BATCH, NPOINTS, CLASSES = 8, 24000, 19
+BASE_BATCHES, NB_INPUTS = 12, 48     # 96 synthetic clouds, combined into 48 different batches (147 MB > L2)
 LEVEL_N = (24000, 1024, 256, 64)
 METRIC = "pointnet2_semseg_forward_points_per_sec"
 FPS_DRAM_BYTES_PER_LAUNCH = 2337024   # ncu: 2.34 MB read + 0 written per level-1 launch (the cloud lives in registers)
@@ -49,8 +50,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (our arm only)")
-    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch of the critical-path kernels")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (our arm only)")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("PN12_DEPTH", "2")), help="batches in flight (GraphedSemSeg depth)")
+    ap.add_argument("--ref-clouds", type=int, default=0, help="reference arm: clouds per step (0 = the full batch of 8, reduced "
+                                                              "automatically if the run would exceed a few minutes)")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-C5 `train` / `dp_check` sub-records")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
                     help="bf16x3 (default, fp32 parity), bf16 (single-pass, stated tolerance) or fp32 (CUDA cores)")
     ap.add_argument("--workload", default="c2", choices=["c2", "train", "preprocess"],
@@ -160,7 +164,22 @@ def fps_starts(torch, batch):
     return [torch.randint(0, n, (batch,), dtype=torch.long) for n in LEVEL_N]
 
 
-# ------------------------------------------------------------------------------------------------ CPU oracle legs
+def shared_config(depth):
+    """`config` of BOTH arms (identical keys and values, so that the driver can compare them)."""
+    return {
+        "workload": WORKLOAD, "batch_per_gpu": BATCH, "points_per_cloud": NPOINTS,
+        "launch": (f"B200 arm: one CUDA-graph replay per batch (6 internal streams forked/joined inside the graph), {depth} batches "
+                   f"in flight on {depth} static buffer sets (GraphedSemSeg.submit / result: the level-1 sampling of batch k+1 runs "
+                   "beside the tensor-core chains of batch k; chain tiles handed out dynamically); reference arm: the unmodified "
+                   "model/utils.py load_pointnet + eval forward on the host CPU, all cores"),
+        "l2": (f"inputs larger than L2: the timed steps rotate over {NB_INPUTS} different input batches "
+               f"({NB_INPUTS * BATCH * 4 * NPOINTS * 4 / 1e6:.0f} MB resident in HBM / pinned host memory > 126 MB L2); "
+               "the `sequential` sub-record writes 512 MiB between steps instead"),
+        "fps_start": "torch.randint on the CPU generator per level and batch, as the reference draws it",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
 def oracle_forward_timer(batch):
     import torch
 
@@ -182,39 +201,129 @@ def oracle_forward_timer(batch):
     return step, orc.num_threads()
 
 
+def import_reference():
+    """The UNMODIFIED reference package from baseline/_ref (tools/install_reference.py copies /root/reference/model/*.py there,
+    byte for byte, with a sha256 manifest) as `_pn12_ref`; returns its model.utils module or None when it is absent / altered."""
+    import importlib.util
+    import types
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import install_reference as inst
+
+    if not inst.verify():
+        return None
+    base = os.path.join(inst.DST, "model")
+    pkg = types.ModuleType("_pn12_ref")
+    pkg.__path__ = [base]
+    sys.modules["_pn12_ref"] = pkg
+    mods = {}
+    for name in ("pointnet_util", "pointnet", "pointnet2", "utils"):
+        spec = importlib.util.spec_from_file_location(f"_pn12_ref.{name}", os.path.join(base, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["utils"], os.path.join(inst.DST, "checkpoints", os.path.basename(CKPT))
+
+
 def run_reference(args):
-    """Reference arm: the CPU port of the reference algorithm on the host cores, same config/metric/unit."""
+    """Reference arm: the reference's OWN PyTorch-CPU path (model/utils.py:15-34 load_pointnet -> DataParallel(PointNet2SemSeg)
+    .eval(), pointnet2.py:159-176) from baseline/_ref, on all host cores, same config / metric / unit.  CUDA is hidden from this
+    process, so load_pointnet takes its `cuda not available` branch.  Falls back to the C/OpenMP oracle port (kind "port") only
+    when baseline/_ref is missing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step, threads = oracle_forward_timer(BATCH)
-    for _ in range(max(1, min(args.warmup, 2))):
-        step()
-    times = [step() for _ in range(args.steps)]
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):          # torchrun pins every rank to one thread
+        os.environ.pop(k, None)
+    import contextlib
+    import io
+
+    import torch
+
+    from pointnet12_b200 import synthetic as syn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = import_reference()
+    clouds = BATCH if args.ref_clouds <= 0 else args.ref_clouds
+    if ref is not None:
+        utils, ckpt = ref
+        with contextlib.redirect_stdout(io.StringIO()):       # load_pointnet prints '=> cuda not available'
+            net = utils.load_pointnet("pointnet2", CLASSES, ckpt)
+        kind, what = "reference", "unmodified reference (baseline/_ref: model/utils.py load_pointnet, torch %s CPU)" % torch.__version__
+        pts = torch.from_numpy(syn.kitti_batch(BATCH, NPOINTS, config=2))
+
+        def step(n):
+            t = time.perf_counter()
+            torch.manual_seed(0)                              # fixes the four FPS start draws (pointnet_util.py:75)
+            with torch.no_grad():
+                net(pts[:n])
+            return time.perf_counter() - t
+    else:
+        stepper, cores = oracle_forward_timer(BATCH)
+        kind, what = "port", "C/OpenMP oracle port (oracle/pn_oracle.c): baseline/_ref is absent"
+        clouds = BATCH
+
+        def step(n):
+            return stepper()
+    first = step(clouds)                                      # warm-up; also sizes the sample
+    if args.ref_clouds <= 0 and kind == "reference" and first * (args.steps + 1) > 240.0:
+        clouds = max(1, min(BATCH, int(BATCH * 240.0 / (first * (args.steps + 1)))))     # keep the run within a few minutes
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
+        step(clouds)
+    times = [step(clouds) for _ in range(args.steps)]
     total = sum(times)
-    value = BATCH * NPOINTS * args.steps / total
+    value = clouds * NPOINTS * args.steps / total
+    sample = (f"{'full step' if clouds == BATCH else 'bounded sample'}: {clouds} clouds x {NPOINTS} points per step, {args.steps} steps after "
+              f"{max(1, min(args.warmup, 2))} warm-up, {what}, {cores} threads on {os.cpu_count()} host CPUs")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": BATCH, "points_per_cloud": NPOINTS},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"full step: {BATCH} clouds x {NPOINTS} points per step, {args.steps} steps, "
-                                   f"C/OpenMP oracle (oracle/pn_oracle.c) on {os.cpu_count()} host CPUs"},
+        "config": shared_config(args.depth),
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def reference_leg_subprocess(depth):
+    """The reference arm in a child process with CUDA hidden (1 warm-up + 1 timed full batch): the `cpu_baseline` of our line."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                              "--ref-clouds", str(BATCH), "--depth", str(depth)], env=env, capture_output=True, text=True, timeout=600)
+        line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        return line["cpu_baseline"]
+    except Exception as e:   # noqa: BLE001
+        return {"value": None, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"[:300]}
+
+
 # ------------------------------------------------------------------------------------------------ our arm
+def make_inputs(torch, rank):
+    """NB_INPUTS different batches: every batch is a different combination of 8 of 96 synthetic clouds (a pinned host tensor
+    [NB, 8, 4, N]); together they exceed the L2, so a timed step never finds its input cached."""
+    import numpy as np
+
+    from pointnet12_b200 import synthetic as syn
+
+    base = np.concatenate([syn.kitti_batch(BATCH, NPOINTS, config=2, first=(rank * BASE_BATCHES + i) * BATCH) for i in range(BASE_BATCHES)])
+    rng = np.random.default_rng(100 + rank)
+    need = NB_INPUTS * BATCH
+    order = np.concatenate([rng.permutation(len(base)) for _ in range((need + len(base) - 1) // len(base))])[:need]
+    return torch.from_numpy(base[order].reshape(NB_INPUTS, BATCH, 4, NPOINTS)).pin_memory()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from pointnet12_b200 import _native as nv
     from pointnet12_b200 import ops
-    from pointnet12_b200 import synthetic as syn
     from pointnet12_b200.model.utils import load_pointnet
     from pointnet12_b200.runtime import GraphedSemSeg
 
@@ -222,21 +331,27 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU port)")
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
+    # CPU legs first (rank 0 of a single-GPU run only): nothing else competes for the host cores yet
+    cpu_legs = {}
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_legs["cpu_baseline"] = reference_leg_subprocess(args.depth)
+        step, threads = oracle_forward_timer(BATCH)
+        step()
+        times = [step() for _ in range(5)]
+        cpu_legs["cpu_baseline_port"] = {"value": BATCH * NPOINTS * len(times) / sum(times), "unit": "points/s", "cores": threads,
+                                         "kind": "port", "sample": f"5 forwards of the same {BATCH} x {NPOINTS} batch after 1 warm-up, "
+                                                                   f"C/OpenMP oracle (oracle/pn_oracle.c) on {os.cpu_count()} host CPUs"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    if args.pdl:
-        ops.set_pdl(True)
     ops.set_mlp_mode(args.precision)
     net = load_pointnet("pointnet2", CLASSES, CKPT, device=dev)
-    # four different batches per rank, rotated, so consecutive steps never see the same clouds
-    host_batches = [torch.from_numpy(syn.kitti_batch(BATCH, NPOINTS, config=2, first=(rank * 4 + i) * BATCH)).pin_memory()
-                    for i in range(4)]
-    dev_batches = [h.to(dev) for h in host_batches]
-    host_out = torch.empty((BATCH, NPOINTS, CLASSES), dtype=torch.float32).pin_memory()
+    host_batches = make_inputs(torch, rank)
+    dev_batches = host_batches.to(dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -245,132 +360,136 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    runner = GraphedSemSeg(net) if args.mode == "graph" else None
+    depth = 1 if args.mode == "eager" else args.depth
+    runner = GraphedSemSeg(net, depth=depth) if args.mode == "graph" else None
+    seq_runner = GraphedSemSeg(net, depth=1) if args.mode == "graph" else None
 
-    def step_eager(i):
-        with torch.no_grad():
-            return net(dev_batches[i % 4])
-
-    def step_resident(i):
-        if runner is not None:
-            return runner(dev_batches[i % 4])
-        return step_eager(i)
-
-    def step_e2e(i):
-        if runner is not None:
-            runner(host_batches[i % 4], to_host=True)    # D2H copies are graph nodes; result in the runner's pinned buffer
-            return
-        with torch.no_grad():
-            x = host_batches[i % 4].to(dev, non_blocking=True)
-            net(x, host_out=host_out)
-
-    def timed(step_fn, steps):
-        """Sum of per-step CUDA-event durations; L2 is flushed (untimed) between steps."""
-        evs = []
+    def region(batches, steps, to_host):
+        """K steps with `depth` batches in flight, timed as ONE region on the device; returns (ms, per-step completion times)."""
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dones, pending = [], []
+        start.record()
         for i in range(steps):
+            if runner is None:
+                with torch.no_grad():
+                    x = batches[i % NB_INPUTS]
+                    if to_host:
+                        net(x.to(dev, non_blocking=True), host_out=eager_host_out)
+                    else:
+                        net(x)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                dones.append(ev)
+                continue
+            pending.append(runner.submit(batches[i % NB_INPUTS], to_host=to_host))
+            if len(pending) >= depth:
+                t = pending.pop(0)
+                runner.result(t)              # device output: orders this stream after batch k; host output: waits for it
+                dones.append(t.done)
+        for t in pending:
+            runner.result(t)
+            dones.append(t.done)
+        end.record()
+        torch.cuda.synchronize()
+        marks = [start.elapsed_time(d) for d in dones]
+        return start.elapsed_time(end), [b - a for a, b in zip([0.0] + marks[:-1], marks)]
+
+    eager_host_out = torch.empty((BATCH, NPOINTS, CLASSES), dtype=torch.float32).pin_memory() if runner is None else None
+    if runner is not None:
+        runner.timing = True
+    torch.manual_seed(1234 + rank)
+    W = max(args.warmup, 3)
+    region(dev_batches, W, False)
+    region(host_batches, W, True)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM, `depth` batches in flight
+    with ClockSampler(local) as clocks:
+        ms, per_step = region(dev_batches, args.steps, False)
+    barrier()
+    # ---- timed region 2: end to end from pinned host memory and back
+    ms_e2e, _ = region(host_batches, args.steps, True)
+    barrier()
+
+    # ---- one batch at a time (round-1 protocol: per-step CUDA events, 512 MiB written between steps) for comparison
+    seq = None
+    if seq_runner is not None:
+        evs = []
+        for i in range(W + args.steps):
             flush.fill_(i & 0xFF)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            step_fn(i)
+            seq_runner(dev_batches[i % NB_INPUTS])
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-        per_step = [a.elapsed_time(b) for a, b in evs]
-        timed.last = per_step
-        return sum(per_step)      # ms
-
-    torch.manual_seed(1234 + rank)
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
-        step_e2e(i)
+        seq_ms = [a.elapsed_time(b) for a, b in evs[W:]]
+        seq = sum(seq_ms) / len(seq_ms)
     barrier()
 
-    # ---- timed region 1: inputs resident in HBM
-    if runner is None:
-        nv.time_entry_points(FPS_ENTRY_POINTS)   # eager: the dominant kernel's launches carry their own events
-    launches0 = nv.launch_count
-    with ClockSampler(local) as clocks:
-        ms = timed(step_resident, args.steps)
-    barrier()
-    spread = sorted(timed.last)
-    launches = nv.launch_count - launches0
-    if runner is None:
-        fps_records = sum(nv.time_entry_points(None).values(), [])
-    else:
-        # a graph node cannot be bracketed by events: time the identical kernel in an eager pass of the same steps
-        nv.time_entry_points(FPS_ENTRY_POINTS)
-        l0 = nv.launch_count
-        timed(step_eager, args.steps)
-        launches = nv.launch_count - l0            # kernels per step x steps = nodes the graph replays
-        fps_records = sum(nv.time_entry_points(None).values(), [])
-        barrier()
+    # launches per forward (= kernel nodes a replay runs), counted on an eager forward
+    l0 = nv.launch_count
+    with torch.no_grad():
+        net(dev_batches[0])
+    per_forward = nv.launch_count - l0
+    torch.cuda.synchronize()
 
-    # ---- timed region 2: end to end from pinned host memory and back
-    barrier()
-    ms_e2e = timed(step_e2e, args.steps)
-    barrier()
-
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, seq if seq is not None else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, seq = float(t[0]), float(t[1]), float(t[2])
     points = world * BATCH * NPOINTS * args.steps
 
+    line = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        l1 = [a.elapsed_time(b) for a, b, tag in fps_records if tag == (BATCH, NPOINTS, 1024)]
-        fps_ms = sum(l1) / len(l1)
-        fps_bytes = BATCH * 1024 * NPOINTS * 16
-        achieved = fps_bytes / (fps_ms * 1e-3) / 1e9
-        all_fps_ms = sum(a.elapsed_time(b) for a, b, _ in fps_records) / args.steps
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import kernel_rooflines
+
+        torch.manual_seed(0)
+        st = [s.to(dev) for s in fps_starts(torch, BATCH)]
+        per_kernel = kernel_rooflines.measure(net, dev_batches[0], st)
+        fps1 = next(k for k in per_kernel["kernels"] if k["name"] == "fps level 1")
+        spread = sorted(per_step)
+        precision = ops.mlp_precision()
+        cfg = shared_config(depth)
+        cfg["precision"] = {"bf16x3": "bf16x3: tcgen05 tensor cores, 3-pass split bf16 with fp32 accumulation (fp32 parity, ~1e-5 relative)",
+                            "bf16": "bf16: tcgen05 tensor cores, single pass (max |delta log-prob| 0.38, 99.6 % equal labels at this config)",
+                            "fp32": "fp32 FMA on CUDA cores"}[precision] if args.precision != "bf16x3" else None
+        if cfg["precision"] is None:
+            del cfg["precision"]                 # (default mode: both arms then carry identical `config` objects)
         line = {
             "metric": METRIC, "value": points / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16x3": "f32 (MLP products as split bf16 hi/lo on tensor cores)", "bf16": "bf16 (fp32 accumulation)",
-                      "fp32": "f32"}[ops.mlp_precision()],
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "points_per_cloud": NPOINTS,
-                       "precision": {"bf16x3": "bf16x3: tcgen05 tensor cores, 3-pass split bf16 with fp32 accumulation (fp32 "
-                                               "parity, ~1e-5 relative)",
-                                     "bf16": "bf16: tcgen05 tensor cores, single pass (max |delta log-prob| 0.38, 99.6 % equal "
-                                             "labels at this config)",
-                                     "fp32": "fp32 FMA on CUDA cores"}[ops.mlp_precision()],
-                       "launch": ("one CUDA-graph replay per step (5 internal streams forked/joined inside the graph)"
-                                  if runner is not None else "eager launches on 5 internal streams"),
-                       "l2": "512 MiB written between timed steps",
-                       "fps_start": "torch.randint on the CPU generator per level, as the reference draws it"},
+                      "fp32": "f32"}[precision],
+            "data": "synthetic", "config": cfg,
             "e2e": {"value": points / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": BATCH * 4 * NPOINTS * 4 + 4 * BATCH * 8,
                     "d2h_bytes_per_step": BATCH * NPOINTS * CLASSES * 4},
-            "gpu_launches": launches,
-            "step_ms": {"min": spread[0], "median": spread[len(spread) // 2], "max": spread[-1]},
-            "roofline": {"kernel": "fps_async_kernel<4,24,true> (pn_fps_progress_f32, level 1: N=24000 -> 1024 centroids)",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": FPS_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                           "(profiles/r01_v11_ncu_full_summary.csv)",
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": fps_bytes,
-                         "launch_ms": fps_ms, "share_of_step": fps_ms / (ms / args.steps),
-                         "all_fps_levels_ms_per_step": all_fps_ms,
-                         "timing": ("CUDA events around the launch, eager pass over the same steps right after the timed "
-                                    "graph replays" if runner is not None else "CUDA events around the launch inside the timed steps"),
-                         "note": "coordinates and running distances are register-resident, so DRAM traffic is ~0; "
-                                 "the figure is effective bandwidth on SURVEY 8(d)'s algorithmic bytes"},
+            "gpu_launches": per_forward * args.steps,
+            "step_ms": {"min": spread[0], "median": spread[len(spread) // 2], "max": spread[-1],
+                        "what": "intervals between the completions of consecutive batches inside the timed region"},
+            "sequential": None if not seq else {"ms_per_step": seq, "value": world * BATCH * NPOINTS / (seq * 1e-3), "unit": "points/s",
+                                                "what": "one batch at a time (depth 1), per-step CUDA events, 512 MiB written between steps: "
+                                                        "the round-1 protocol"},
+            "roofline": {"kernel": "fps_async_kernel (pn_fps_f32 / pn_fps_progress_f32, level 1: N=24000 -> 1024 centroids)",
+                         "bound": "hbm", "achieved": fps1["achieved"], "peak": fps1["peak"], "unit": "GB/s", "frac": fps1["frac"],
+                         "traffic": fps1["traffic"] if fps1["traffic"] is not None else FPS_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)",
+                         "peak_source": per_kernel["peak_source"], "algorithmic_bytes_per_launch": fps1["algorithmic_bytes"],
+                         "launch_ms": fps1["launch_ms"], "share_of_step": fps1["launch_ms"] / (ms / args.steps),
+                         "timing": "CUDA events around the stand-alone launch (cold L2) right after the timed regions; inside the step "
+                                   "the kernel overlaps the previous batch's chains, so its share of the step can approach 1",
+                         "note": "coordinates and running distances are register-resident, so DRAM traffic is ~0; the figure is "
+                                 "effective bandwidth on SURVEY 8(d)'s algorithmic bytes"},
+            "roofline_all": per_kernel,
             "clocks": clocks.summary(),
         }
-        if not args.no_cpu_baseline:
-            step, threads = oracle_forward_timer(BATCH)
-            step()
-            times = [step() for _ in range(5)]
-            line["cpu_baseline"] = {"value": BATCH * NPOINTS * len(times) / sum(times), "unit": "points/s",
-                                    "cores": threads, "kind": "port",
-                                    "sample": f"5 forwards of the same {BATCH} x {NPOINTS} batch after 1 warm-up, C/OpenMP "
-                                              f"oracle on {os.cpu_count()} host CPUs"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        line.update(cpu_legs)
+        if "cpu_baseline" in cpu_legs:
+            line["cpu_baseline_torch"] = cpu_legs["cpu_baseline"]
+    return line, (world, rank, dev)
 
 
 def cpu_train_oracle(B=2, N=2048):
@@ -433,8 +552,32 @@ def main():
         return
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    line, (world, rank, dev) = run_ours(args)
+    if not args.no_train and args.mode == "graph":
+        # config C5 in front of the driver: the training iteration with its NCCL gradient all-reduce, and the data-parallel
+        # equivalence check, on the same ranks (tools/bench_train.py)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_train
+
+        train = bench_train.main(["--steps", str(max(10, args.steps)), "--warmup", str(max(3, args.warmup)), "--no-cpu-baseline"],
+                                 init_pg=False, emit=False)
+        check = bench_train.dp_check(world, rank, dev)
+        if line is not None:
+            line["train"] = None if train is None else {
+                k: train[k] for k in ("metric", "value", "unit", "ms_per_step", "step_ms", "e2e", "allreduce_us", "allreduce_bytes",
+                                      "gpu_launches", "final_loss")}
+            if train is not None:
+                line["train"]["config"] = train["config"]
+                line["train"]["roofline"] = train["roofline"]
+            line["dp_check"] = check
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -11,7 +11,8 @@
  *   - extern "C", plain pointers and sizes only.  All pointers are DEVICE pointers unless noted.
  *   - The caller owns every buffer; the library never allocates, frees or synchronises.
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and capturable in a
- *     CUDA graph.  Entry points are stateless and re-entrant.
+ *     CUDA graph.  Entry points are stateless and re-entrant: the library keeps no mutable process-wide settings;
+ *     everything that tunes a launch travels with the call in a pn_launch_opts (NULL = defaults).
  *   - Point clouds are addressed point-major through ELEMENT strides (sB, sN, sC): element (b, n, c)
  *     lives at base[b*sB + n*sN + c*sC].  This covers the permuted [B,3,N] views the reference passes
  *     around (model/pointnet_util.py:184) as well as contiguous [B,N,3].
@@ -44,11 +45,40 @@ enum pn_status {
 /* Library identification: version = major*10000 + minor*100 + patch. */
 int pn_version(void);
 const char* pn_last_error_string(void);
-/* Programmatic dependent launch of the critical-path kernels (chains, grid ball query, index_points): 1 = on,
- * 0 = plain stream-ordered launches (default: inside the CUDA graph the dependent launch brought no gain).  Process-wide. */
-int pn_set_pdl(int enabled);
 /* Queries the current device; fails with PN_ERR_DEVICE unless compute capability is 10.x. */
 int pn_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Per-call launch options of the sampling and fused-chain entry points (a HOST struct, read during the call; NULL or
+ * all zeros = defaults).  They replace the process-wide setters of ABI 0.3: two threads can run different precisions
+ * or launch shapes at the same time.
+ *   mlp_passes    0 or 3 = all three split-bf16 products, fp32 parity (~1e-5 relative); 1 = only a_hi * w_hi, i.e. plain
+ *                 bf16 inputs with fp32 accumulation -- a third of the tensor-core work (config C4).  Same packed blob.
+ *   mlp_engine    0 = automatic (chains whose packed weights fit in shared memory run on the resident-weight kernel,
+ *                 larger chains stream their weights through a ring), 1 = always stream, 2 = resident or fail;
+ *                 +4 = row-per-thread producers only (no coalesced quad producer), +8 = no N-slicing of single-layer
+ *                 chains, +16 = 8-warp streaming CTAs only.  For benchmarks and tests.
+ *   reserved_sms  SMs the resident-weight launches (one persistent CTA per SM) leave to kernels of other streams.
+ *   tile_counter  (device pointer or NULL) ONE zeroed uint32 owned by the caller and not shared with a launch that may
+ *                 run at the same time: the resident-weight kernel then hands out its 128-row tiles through this
+ *                 counter instead of a static round-robin, so CTAs that get their SM late (another stream's kernels
+ *                 hold it) only take what is left; the kernel resets the counter to zero before it ends.
+ *   mlp_debug     profiling hook: device buffer of 4 * 64 * 32 int64 (or NULL); CTA 0 of a resident-weight launch records
+ *                 clock64() per phase: [group][tile round % 64][tile start, producer done, then per layer: MMA issue
+ *                 start, MMAs issued, accumulator ready, epilogue done; last: tile done].
+ *   fps_cluster / fps_threads / fps_exchange
+ *                 force the cluster size (1,2,4,8,16), threads per CTA (64..1024) and the intra-cluster exchange of
+ *                 pn_fps_f32 (1 = DSMEM store + barrier.cluster, 2 = st.async + mbarrier, 3 = the same without the per-CTA
+ *                 z table, i.e. two st.async per winner instead of one); 0 = automatic. */
+typedef struct pn_launch_opts {
+    int mlp_passes;
+    int mlp_engine;
+    int reserved_sms;
+    int fps_cluster;
+    int fps_threads;
+    int fps_exchange;
+    uint32_t* tile_counter;
+    void* mlp_debug;
+} pn_launch_opts;
 
 /* farthest_point_sample (model/pointnet_util.py:63-84).
  * xyz [B,N,3] via strides; start_idx [B] = the torch.randint draw of :75 (made by the caller on the
@@ -59,13 +89,7 @@ int pn_device_check(int* sm_count, int* cc_major, int* cc_minor);
  * per-iteration arg-max is exchanged between the CTAs with st.async + mbarrier (no barrier in the loop).
  * Limits: N <= 131072. */
 int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
-               const int64_t* start_idx, int64_t* out_idx, pn_stream_t stream);
-
-/* Tuning hook for pn_fps_f32: force the cluster size (1,2,4,8,16), threads per CTA (64..1024) and the
- * intra-cluster exchange (1 = DSMEM store + barrier.cluster, 2 = st.async + mbarrier, 3 = the same without the
- * per-CTA z table, i.e. two st.async per winner instead of one); 0 = automatic.
- * Process-wide; meant for benchmarks and tests. */
-int pn_fps_set_config(int cluster_size, int threads, int exchange);
+               const int64_t* start_idx, int64_t* out_idx, const pn_launch_opts* opts, pn_stream_t stream);
 
 /* square_distance (model/pointnet_util.py:19-40): out[b,i,j] = ((-2*dot) + |src_i|^2) + |dst_j|^2
  * with dot = fma(z,z', fma(y,y', x*x')), i.e. the fp32 rounding sequence of the reference's CPU path.
@@ -115,9 +139,10 @@ int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC,
  * not done -- normally nothing -- so the result never depends on the two kernels having run side by side.
  * Limits: N <= 32768. */
 int pn_fps_progress_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
-                        const int64_t* start_idx, int64_t* out_idx, uint64_t* progress, pn_stream_t stream);
-/* Launch shape pn_fps_f32 would use for (B, N, npoint): CTAs in the grid and dynamic shared memory per CTA. */
-int pn_fps_launch_info(int B, int N, int npoint, int* ctas, size_t* smem_bytes);
+                        const int64_t* start_idx, int64_t* out_idx, uint64_t* progress, const pn_launch_opts* opts,
+                        pn_stream_t stream);
+/* Launch shape pn_fps_f32 would use for (B, N, npoint, opts): CTAs in the grid and dynamic shared memory per CTA. */
+int pn_fps_launch_info(int B, int N, int npoint, const pn_launch_opts* opts, int* ctas, size_t* smem_bytes);
 int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const uint64_t* progress, int B, int N,
                              int S, int s_end, float radius2, int nsample, const void* grid, size_t grid_bytes, int ctas,
                              size_t min_smem_bytes, int32_t* done, int64_t* out_idx, pn_stream_t stream);
@@ -220,7 +245,7 @@ enum pn_mlp_out { PN_MLP_OUT_ROWS = 0, PN_MLP_OUT_MAX32 = 1, PN_MLP_OUT_LOG_SOFT
  * MAX32: y [rows/32, cout] = max over each run of 32 rows; LOG_SOFTMAX: y [rows, cout] log-probabilities.
  * (The per-point conv chains of model/pointnet.py.) */
 int pn_mlp_rows_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* x, int64_t ldx, int64_t rows,
-                       int out_mode, float* y, int64_t ldy, pn_stream_t stream);
+                       int out_mode, float* y, int64_t ldy, const pn_launch_opts* opts, pn_stream_t stream);
 
 /* One whole set-abstraction level after sampling (model/pointnet_util.py:127-131 + :194-199, or the MSG
  * branch :243-256 with msg_order = 1): gather + recentre + concat straight into the tensor-core operand,
@@ -230,14 +255,16 @@ int pn_mlp_rows_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* x
 int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
                          int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
                          const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
-                         int S, int K, int msg_order, float* out, int64_t ldo, pn_stream_t stream);
+                         int S, int K, int msg_order, float* out, int64_t ldo, const pn_launch_opts* opts,
+                         pn_stream_t stream);
 /* The same with the output mode chosen by the caller: PN_MLP_OUT_MAX32 as above, or PN_MLP_OUT_ROWS to keep the
  * [B*S*K, cout_last] rows (used when a level with few row tiles runs layer by layer: single-layer chains are
  * N-sliced over gridDim.y so that they fill the GPU). */
 int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
                      int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
                      const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
-                     int S, int K, int msg_order, int out_mode, float* out, int64_t ldo, pn_stream_t stream);
+                     int S, int K, int msg_order, int out_mode, float* out, int64_t ldo, const pn_launch_opts* opts,
+                     pn_stream_t stream);
 
 /* One feature-propagation level after the 3-NN search (model/pointnet_util.py:301-312): weighted gather of
  * the three coarse rows + skip concat straight into the tensor-core operand, then the conv+BN+ReLU chain.
@@ -259,26 +286,7 @@ int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* poi
                      int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2, int S,
                      const int64_t* idx, const float* weight, int relu_in, const int32_t* order, int64_t order_es,
                      int64_t order_bs, const float* residual, int64_t ldr, int B, int N, int out_mode, float* out,
-                     int64_t ldo, pn_stream_t stream);
-
-/* Tuning hook for the fused chains: 0 = automatic (chains whose packed weights fit in shared memory run on the
- * resident-weight kernel: weights loaded once per CTA, 2 or 4 warp groups per CTA each with its own row tile
- * and TMEM slice; larger chains stream their weights through a ring), 1 = always stream, 2 = resident or fail;
- * +4 = keep the row-per-thread producers (disables the coalesced quad producer of the FP levels);
- * +8 = no N-slicing of single-layer chains; +16 = 8-warp streaming CTAs only (no 16-warp CTAs on small grids).
- * Process-wide; meant for benchmarks and tests. */
-int pn_mlp_set_engine(int engine);
-/* Precision of the fused chains: 3 (default) = all three split-bf16 products, fp32 parity (~1e-5 relative); 1 = only
- * a_hi * w_hi, i.e. plain bf16 inputs with fp32 accumulation -- a third of the tensor-core work, for callers that accept
- * bf16 accuracy (config C4).  The packed blob is the same.  Process-wide. */
-int pn_mlp_set_precision(int passes);
-/* SMs the resident-weight launches (one persistent CTA per SM) leave to kernels running on other streams at the same
- * time (e.g. the next level's sampling, one CTA per cloud).  Read at launch; 0 by default.  Process-wide. */
-int pn_mlp_set_reserved_sms(int sms);
-/* Profiling hook: a device buffer of 4 * 64 * 32 int64 (or NULL to disable).  While set, CTA 0 of every resident-
- * weight chain launch records clock64() per phase: [group][tile round % 64][tile start, producer done, then per
- * layer: MMA issue start, MMAs issued, accumulator ready, epilogue done; last: tile done]. */
-int pn_mlp_set_debug(void* timeline);
+                     int64_t ldo, const pn_launch_opts* opts, pn_stream_t stream);
 
 /* ================================================================================================================
  * Training step of PointNet2SemSeg (reference pcdseg.py:157-186) and evaluation
@@ -326,9 +334,6 @@ int pn_grad_weight_f32(const float* dy, int64_t lddy, const float* x, int64_t ld
  * bf16 hi + lo on the fly straight into the UMMA K-major layout, and adds its tile to dw with fp32 atomics. */
 int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin,
                           float* dw, int64_t lddw, float* db, pn_stream_t stream);
-/* Tuning hook: row slabs (CTAs) per SM of the tensor-core weight gradient, 1 (default: every extra slab adds a tile of
- * atomics on the same addresses) or 2 (more loads in flight).  Process-wide. */
-int pn_grad_weight_set_ctas_per_sm(int ctas);
 /* The same with f(x) = act(x*x_scale[ci] + x_shift[ci]) applied to the x operand while it is loaded: the normalise + ReLU
  * of the layer that produced x, for a forward that kept only that layer's pre-normalisation output (pn_train_gemm_bf16x3). */
 int pn_grad_weight_bn_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* x_scale,

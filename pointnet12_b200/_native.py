@@ -29,20 +29,27 @@ class MlpDesc(C.Structure):
 
 _descp = C.POINTER(MlpDesc)
 
+
+class LaunchOpts(C.Structure):
+    """pn_launch_opts of include/pn12_b200.h: per-call launch options (all zeros = defaults)."""
+    _fields_ = [("mlp_passes", C.c_int), ("mlp_engine", C.c_int), ("reserved_sms", C.c_int), ("fps_cluster", C.c_int),
+                ("fps_threads", C.c_int), ("fps_exchange", C.c_int), ("tile_counter", C.c_void_p), ("mlp_debug", C.c_void_p)]
+
+
+_optsp = C.POINTER(LaunchOpts)
+
 # name -> argtypes, mirroring include/pn12_b200.h
 _SIGNATURES = {
     "pn_version": [],
-    "pn_set_pdl": [i32],
     "pn_device_check": [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
-    "pn_fps_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp],
-    "pn_fps_set_config": [i32, i32, i32],
+    "pn_fps_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, _optsp, vp],
     "pn_square_distance_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, vp, vp],
     "pn_ball_query_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, vp],
     "pn_ball_grid_build_f32": [vp, i64, i64, i64, i32, i32, f32, vp, C.c_size_t, vp],
     "pn_ball_query_grid_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, vp, vp,
                                vp],
-    "pn_fps_progress_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp, vp],
-    "pn_fps_launch_info": [i32, i32, i32, C.POINTER(i32), C.POINTER(C.c_size_t)],
+    "pn_fps_progress_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp, _optsp, vp],
+    "pn_fps_launch_info": [i32, i32, i32, _optsp, C.POINTER(i32), C.POINTER(C.c_size_t)],
     "pn_ball_query_stream_f32": [vp, i64, i64, i64, vp, i32, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, C.c_size_t, vp, vp,
                                  vp],
     "pn_index_points_f32": [vp, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp],
@@ -58,18 +65,14 @@ _SIGNATURES = {
     "pn_log_softmax_f32": [vp, i64, i64, i32, vp, i64, vp],
     "pn_mlp_pack_bf16x3": [_descp, C.POINTER(vp), C.POINTER(vp), vp, vp],
     "pn_mlp_pack_t_bf16x3": [_descp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp, vp],
-    "pn_mlp_rows_bf16x3": [_descp, vp, vp, i64, i64, i32, vp, i64, vp],
+    "pn_mlp_rows_bf16x3": [_descp, vp, vp, i64, i64, i32, vp, i64, _optsp, vp],
     "pn_sa_mlp_max_bf16x3": [_descp, vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32,
-                             i32, i32, vp, i64, vp],
+                             i32, i32, vp, i64, _optsp, vp],
     "pn_sa_mlp_bf16x3": [_descp, vp, vp, i64, i64, i64, vp, i64, i64, i64, i32, vp, i64, i64, i64, vp, i32, i32, i32,
-                         i32, i32, i32, vp, i64, vp],
+                         i32, i32, i32, vp, i64, _optsp, vp],
     "pn_fp_mlp_bf16x3": [_descp, vp, vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, vp, i64, i64, vp,
-                         i64, i32, i32, i32, vp, i64, vp],
+                         i64, i32, i32, i32, vp, i64, _optsp, vp],
     "pn_ball_grid_order": [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)],
-    "pn_mlp_set_engine": [i32],
-    "pn_mlp_set_debug": [vp],
-    "pn_mlp_set_reserved_sms": [i32],
-    "pn_mlp_set_precision": [i32],
     "pn_bn_stats_f32": [vp, i64, i64, i32, vp, vp, vp],
     "pn_bn_finalize_f32": [vp, vp, i64, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp],
     "pn_bn_act_f32": [vp, i64, i64, i32, vp, vp, i32, vp, i64, vp],
@@ -78,7 +81,6 @@ _SIGNATURES = {
     "pn_bn_bwd_apply_f32": [vp, i64, i64, i32, vp, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, vp],
     "pn_grad_weight_f32": [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp, vp],
     "pn_grad_weight_bf16x3": [vp, i64, vp, i64, i64, i32, i32, vp, i64, vp, vp],
-    "pn_grad_weight_set_ctas_per_sm": [i32],
     "pn_grad_weight_bn_bf16x3": [vp, i64, vp, i64, vp, vp, i32, i64, i32, i32, vp, i64, vp, vp],
     "pn_train_gemm_supported": [i32, i32],
     "pn_train_pack_many": [vp, i32, i32, i32, vp],

@@ -6,7 +6,6 @@
 namespace pn {
 
 static thread_local char g_err[512] = "no error";
-int g_pdl = 0;   // measured on B200 at C2 size: no gain inside the CUDA graph (1.071 vs 1.053 ms per step), so off by default
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -17,12 +16,7 @@ void set_error(const char* fmt, ...) {
 
 }  // namespace pn
 
-PN_EXPORT int pn_set_pdl(int enabled) {
-    pn::g_pdl = enabled ? 1 : 0;
-    return PN_OK;
-}
-
-PN_EXPORT int pn_version(void) { return 300; /* 0.3.0: training step, metrics, scan pre-processing, chamfer / class merge */ }
+PN_EXPORT int pn_version(void) { return 400; /* 0.4.0: per-call pn_launch_opts replace the process-wide setters; dynamic tile scheduling */ }
 
 PN_EXPORT const char* pn_last_error_string(void) { return pn::g_err; }
 

@@ -330,8 +330,6 @@ ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, in
                        float radius2, int K, const unsigned char* __restrict__ ws_all, size_t ws_stride, int threshold,
                        int bm_words, const int* __restrict__ done, int64_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char gq_smem[];
-    pdl_trigger();
-    pdl_wait();   // the centroids come from the kernel before
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int s = blockIdx.x * WARPS + warp;
@@ -475,7 +473,7 @@ PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, i
             return (int)e;
         }
         dim3 grid((unsigned)ceil_div(S, warps), (unsigned)B);
-        e = launch_pdl(kern, grid, dim3(warps * 32), smem, st, xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
+        e = launch_kernel(kern, grid, dim3(warps * 32), smem, st, xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
                        static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N), threshold, bm_words, done, out_idx);
         if (e != cudaSuccess) {
             cudaGetLastError();

@@ -33,26 +33,14 @@ inline int finish_launch(const char* what) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// ---- programmatic dependent launch: the kernels of the forward's critical path are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are placed and run their prologue
-// (barrier init, TMEM allocation, weight loads) while the previous kernel drains; pdl_wait() is the point after which
-// the previous kernel's results may be read.  Both instructions are no-ops for a normally launched kernel.
-extern int g_pdl;   // pn_set_pdl: 1 = on, 0 = off (default)
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
+// Launch with the extended API (dynamic shared memory above 48 KB was enabled by the caller via cudaFuncSetAttribute).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

@@ -368,20 +368,23 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
     cluster.sync();  // nobody leaves while a peer may still be storing into its shared memory
 }
 
-static thread_local int g_last_ctas = 0;        // launch shape of the last dispatch on this thread (pn_fps_launch_info)
-static thread_local size_t g_last_smem = 0;
-static thread_local bool g_query_only = false;
-static int g_force_cluster = 0;
-static int g_force_threads = 0;
-static int g_force_exchange = 0;  // 0 auto (st.async where possible), 1 barrier.cluster, 2 st.async
+// Per-call launch configuration (from pn_launch_opts) and, for pn_fps_launch_info, where to report the launch shape.
+struct FpsCfg {
+    int cluster = 0, threads = 0;
+    int exchange = 0;       // 0 auto (st.async where possible), 1 barrier.cluster, 2 st.async
+    bool no_ztable = false; // exchange 3: st.async without the per-CTA z table
+    bool query_only = false;
+    int* ctas = nullptr;
+    size_t* smem = nullptr;
+};
 
 template <typename Kern>
-static int launch_cluster_kernel(Kern kern, const char* what, int CL, int threads, size_t smem, const float* xyz, int64_t sB,
-                                 int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start, int64_t* out,
+static int launch_cluster_kernel(Kern kern, const char* what, int CL, int threads, size_t smem, const FpsCfg& cfg_, const float* xyz,
+                                 int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start, int64_t* out,
                                  unsigned long long* seq, int chunk, cudaStream_t stream) {
-    g_last_ctas = B * CL;
-    g_last_smem = smem;
-    if (g_query_only) return PN_OK;
+    if (cfg_.ctas) *cfg_.ctas = B * CL;
+    if (cfg_.smem) *cfg_.smem = smem;
+    if (cfg_.query_only) return PN_OK;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) {
@@ -413,10 +416,10 @@ static int launch_cluster_kernel(Kern kern, const char* what, int CL, int thread
     return PN_OK;
 }
 
-#define PN_FPS_ARGS xyz, sB, sN, sC, B, N, npoint, start, out, seq, chunk, stream
+#define PN_FPS_ARGS fc, xyz, sB, sN, sC, B, N, npoint, start, out, seq, chunk, stream
 
 template <int THREADS>
-static int dispatch_barrier(int pts, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+static int dispatch_barrier(int pts, int CL, const FpsCfg& fc, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
                             const int64_t* start, int64_t* out, unsigned long long* seq, int chunk, cudaStream_t stream) {
     const size_t smem = (size_t)kFpsSmemHeader + (size_t)chunk * 3 * sizeof(float);
 #define PN_FPS_CASE(P)                                                                                              \
@@ -435,13 +438,11 @@ static int dispatch_barrier(int pts, int CL, const float* xyz, int64_t sB, int64
     return PN_ERR_UNSUPPORTED;
 }
 
-static int g_force_ztable = 0;   // 0 auto (z table when it fits), 1 never
-
 template <int NW>
-static int dispatch_async(int pts, int CL, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+static int dispatch_async(int pts, int CL, const FpsCfg& fc, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
                           const int64_t* start, int64_t* out, unsigned long long* seq, int chunk, cudaStream_t stream) {
     const size_t smem0 = (size_t)kAsyncSmemHeader + (size_t)chunk * 3 * sizeof(float);
-    const bool zt = g_force_ztable == 0 && smem0 + (size_t)N * sizeof(float) <= 200 * 1024;
+    const bool zt = !fc.no_ztable && smem0 + (size_t)N * sizeof(float) <= 200 * 1024;
     const size_t smem = smem0 + (zt ? (size_t)N * sizeof(float) : 0);
 #define PN_FPS_CASE(P)                                                                                                       \
     if (pts <= P)                                                                                                            \
@@ -460,53 +461,62 @@ static int dispatch_async(int pts, int CL, const float* xyz, int64_t sB, int64_t
 
 }  // namespace pn
 
-PN_EXPORT int pn_fps_set_config(int cluster_size, int threads, int exchange) {
+static int fps_cfg_from_opts(const pn_launch_opts* o, pn::FpsCfg* fc) {
+    if (!o) return PN_OK;
+    const int cluster_size = o->fps_cluster, threads = o->fps_threads, exchange = o->fps_exchange;
     const bool cl_ok = cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 ||
                        cluster_size == 8 || cluster_size == 16;
     const bool th_ok = threads == 0 || threads == 64 || threads == 128 || threads == 256 || threads == 512 ||
                        threads == 1024;
     PN_REQUIRE(cl_ok && th_ok && exchange >= 0 && exchange <= 3, PN_ERR_BAD_ARG,
-               "pn_fps_set_config: cluster_size in {0,1,2,4,8,16}, threads in {0,64..1024}, exchange in {0,1,2,3}");
-    pn::g_force_cluster = cluster_size;
-    pn::g_force_threads = threads;
-    pn::g_force_exchange = exchange == 3 ? 2 : exchange;
-    pn::g_force_ztable = exchange == 3 ? 1 : 0;
+               "pn_launch_opts: fps_cluster in {0,1,2,4,8,16}, fps_threads in {0,64..1024}, fps_exchange in {0,1,2,3}");
+    fc->cluster = cluster_size;
+    fc->threads = threads;
+    fc->exchange = exchange == 3 ? 2 : exchange;
+    fc->no_ztable = exchange == 3;
     return PN_OK;
 }
 
-static int fps_dispatch(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start,
-                        int64_t* out, unsigned long long* seq, pn_stream_t stream_);
+static int fps_dispatch(const pn::FpsCfg& fc, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+                        const int64_t* start, int64_t* out, unsigned long long* seq, pn_stream_t stream_);
 
 PN_EXPORT int pn_fps_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
-                         const int64_t* start, int64_t* out, pn_stream_t stream_) {
+                         const int64_t* start, int64_t* out, const pn_launch_opts* opts, pn_stream_t stream_) {
     PN_REQUIRE(xyz && start && out, PN_ERR_BAD_ARG, "pn_fps_f32: null pointer");
-    return fps_dispatch(xyz, sB, sN, sC, B, N, npoint, start, out, nullptr, stream_);
+    pn::FpsCfg fc;
+    if (int rc = fps_cfg_from_opts(opts, &fc)) return rc;
+    return fps_dispatch(fc, xyz, sB, sN, sC, B, N, npoint, start, out, nullptr, stream_);
 }
 
 PN_EXPORT int pn_fps_progress_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
-                                  const int64_t* start, int64_t* out, uint64_t* progress, pn_stream_t stream_) {
+                                  const int64_t* start, int64_t* out, uint64_t* progress, const pn_launch_opts* opts,
+                                  pn_stream_t stream_) {
     PN_REQUIRE(xyz && start && out && progress, PN_ERR_BAD_ARG, "pn_fps_progress_f32: null pointer");
-    return fps_dispatch(xyz, sB, sN, sC, B, N, npoint, start, out, reinterpret_cast<unsigned long long*>(progress), stream_);
+    pn::FpsCfg fc;
+    if (int rc = fps_cfg_from_opts(opts, &fc)) return rc;
+    return fps_dispatch(fc, xyz, sB, sN, sC, B, N, npoint, start, out, reinterpret_cast<unsigned long long*>(progress), stream_);
 }
 
-PN_EXPORT int pn_fps_launch_info(int B, int N, int npoint, int* ctas, size_t* smem_bytes) {
+PN_EXPORT int pn_fps_launch_info(int B, int N, int npoint, const pn_launch_opts* opts, int* ctas, size_t* smem_bytes) {
     PN_REQUIRE(ctas && smem_bytes, PN_ERR_BAD_ARG, "pn_fps_launch_info: null pointer");
-    pn::g_query_only = true;
-    const int rc = fps_dispatch(reinterpret_cast<const float*>(16), 3 * (int64_t)N, 1, N, B, N, npoint,
-                                reinterpret_cast<const int64_t*>(16), reinterpret_cast<int64_t*>(16), nullptr, nullptr);
-    pn::g_query_only = false;
-    *ctas = pn::g_last_ctas;
-    *smem_bytes = pn::g_last_smem;
-    return rc;
+    pn::FpsCfg fc;
+    if (int rc = fps_cfg_from_opts(opts, &fc)) return rc;
+    fc.query_only = true;
+    fc.ctas = ctas;
+    fc.smem = smem_bytes;
+    *ctas = 0;
+    *smem_bytes = 0;
+    return fps_dispatch(fc, reinterpret_cast<const float*>(16), 3 * (int64_t)N, 1, N, B, N, npoint,
+                        reinterpret_cast<const int64_t*>(16), reinterpret_cast<int64_t*>(16), nullptr, nullptr);
 }
 
-static int fps_dispatch(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint, const int64_t* start,
-                        int64_t* out, unsigned long long* seq, pn_stream_t stream_) {
+static int fps_dispatch(const pn::FpsCfg& fc, const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
+                        const int64_t* start, int64_t* out, unsigned long long* seq, pn_stream_t stream_) {
     using namespace pn;
     PN_REQUIRE(B > 0 && N > 0 && npoint > 0, PN_ERR_BAD_ARG, "pn_fps_f32: B, N, npoint must be positive (got %d, %d, %d)", B,
                N, npoint);
     cudaStream_t stream = (cudaStream_t)stream_;
-    int CL = g_force_cluster;
+    int CL = fc.cluster;
     if (CL == 0) {
         if (N <= 3072) CL = 1;
         else if (N <= 6144) CL = 2;
@@ -516,17 +526,17 @@ static int fps_dispatch(const float* xyz, int64_t sB, int64_t sN, int64_t sC, in
     }
     const int chunk = (int)ceil_div(N, CL);
     // st.async exchange: clusters only, at most 64 slots (cluster size x warps) and 32 points per thread
-    bool use_async = CL > 1 && g_force_exchange != 1;
-    int threads = g_force_threads;
+    bool use_async = CL > 1 && fc.exchange != 1;
+    int threads = fc.threads;
     if (use_async) {
         if (threads == 0) threads = (chunk <= 4096 && CL * 4 <= kMaxSlots) ? 128 : 256;
         const int nw = threads / 32;
         if (threads > 256 || CL * nw > kMaxSlots || ceil_div(chunk, threads) > 32) {
-            PN_REQUIRE(g_force_exchange != 2, PN_ERR_UNSUPPORTED,
+            PN_REQUIRE(fc.exchange != 2, PN_ERR_UNSUPPORTED,
                        "pn_fps_f32: st.async exchange needs cluster*warps <= 64, threads <= 256 and <= 32 points per thread "
                        "(N=%d cluster=%d threads=%d)", N, CL, threads);
             use_async = false;
-            threads = g_force_threads;
+            threads = fc.threads;
         }
     }
     if (use_async) {

@@ -244,14 +244,6 @@ grad_weight_tc_kernel(const float* __restrict__ dy, int64_t lddy, const float* _
 
 static int grad_weight_tc(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout, int cin, float* dw,
                           int64_t lddw, float* db, const float* x_scale, const float* x_shift, int x_relu, pn_stream_t stream);
-static int g_ctas_per_sm = 1;
-
-PN_EXPORT int pn_grad_weight_set_ctas_per_sm(int ctas) {
-    PN_REQUIRE(ctas >= 1 && ctas <= 2, PN_ERR_BAD_ARG, "pn_grad_weight_set_ctas_per_sm: 1 or 2");
-    g_ctas_per_sm = ctas;
-    return PN_OK;
-}
-
 PN_EXPORT int pn_grad_weight_bf16x3(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t rows, int cout,
                                     int cin, float* dw, int64_t lddw, float* db, pn_stream_t stream) {
     return grad_weight_tc(dy, lddy, x, ldx, rows, cout, cin, dw, lddw, db, nullptr, nullptr, 0, stream);
@@ -281,7 +273,7 @@ static int grad_weight_tc(const float* dy, int64_t lddy, const float* x, int64_t
     }
     const int64_t tiles = ceil_div(cout, TM) * ceil_div(cin, TN);
     // one CTA per SM: every extra row slab adds a whole tile of atomics on the same 128 x 128 addresses
-    int64_t splits = ceil_div((int64_t)sms * g_ctas_per_sm, tiles);
+    int64_t splits = ceil_div((int64_t)sms, tiles);
     int64_t rps = ceil_div(ceil_div(rows, splits), KC) * KC;
     if (rps < 4 * KC) rps = 4 * KC;
     splits = ceil_div(rows, rps);

@@ -15,8 +15,6 @@ namespace pn {
 // ------------------------------------------------------------------------------------------------
 __global__ void index_points_kernel(const float* __restrict__ points, int64_t pB, int64_t pN, int64_t pC, int N, int C,
                                     const int64_t* __restrict__ idx, int64_t M, int64_t total, float* __restrict__ out) {
-    pdl_trigger();
-    pdl_wait();
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(e % C);
         const int64_t row = e / C;
@@ -222,7 +220,7 @@ PN_EXPORT int pn_index_points_f32(const float* points, int64_t pB, int64_t pN, i
     PN_REQUIRE(points && idx && out, PN_ERR_BAD_ARG, "pn_index_points_f32: null pointer");
     PN_REQUIRE(B > 0 && N > 0 && C > 0 && M > 0, PN_ERR_BAD_ARG, "pn_index_points_f32: sizes must be positive");
     const int64_t total = (int64_t)B * M * C;
-    cudaError_t e = launch_pdl(index_points_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, points, pB, pN,
+    cudaError_t e = launch_kernel(index_points_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, points, pB, pN,
                                pC, N, C, idx, M, total, out);
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -259,7 +259,8 @@ struct TcIo {
     int out_mode; float* y; int64_t ldy; int group;
     const float* res; int64_t ldr;   // optional per-row term added to layer 0's pre-activation: res[row * ldr + channel]
     int quad_fp;      // TC_IN_FP: all channel runs are float4-addressable -> coalesced quad producer (fp_quad_producer)
-    long long* dbg;   // optional timeline (pn_mlp_set_debug): CTA 0 records clock64() per phase
+    long long* dbg;   // optional timeline (pn_launch_opts.mlp_debug): CTA 0 records clock64() per phase
+    unsigned* tile_ctr;   // resident kernel: zeroed counter the 128-row tiles are handed out through (NULL: static round-robin)
 };
 
 template <int IN>
@@ -602,16 +603,13 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
     // the same static schedule of (tile, layer, pass, chunk, slice), so slice number i always sits in stage i % NS
     unsigned fill = 0, use = 0, fill_st = 0, use_st = 0, done_phase = 0;
     int nlog = 0;
-    auto stamp = [&](int tag) {   // pn_mlp_set_debug: flat (tag, clock) log of CTA 0, thread 0
+    auto stamp = [&](int tag) {   // pn_launch_opts.mlp_debug: flat (tag, clock) log of CTA 0, thread 0
         if (io.dbg != nullptr && blockIdx.x == 0 && tid == 0 && nlog < 500) {
             io.dbg[1 + 2 * nlog] = tag;
             io.dbg[2 + 2 * nlog] = clock64();
             io.dbg[0] = ++nlog;
         }
     };
-
-    pdl_trigger();
-    pdl_wait();   // everything above touched only this kernel's own resources and the weight blob
 
     const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
     const int64_t ntiles = io.nseg * tiles_per_seg;
@@ -891,10 +889,11 @@ __global__ void __launch_bounds__(kResThreads, 1)
 mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restrict__ blob, const __grid_constant__ TcIo io) {
     constexpr int GROUPS = 16 / WPG, GTHREADS = WPG * 32, HALVES = WPG / 4, GCOLS = 512 / GROUPS, CSTEP = 32 * HALVES;
     extern __shared__ __align__(128) unsigned char smem[];
-    // layout: [blob: weight images | bias table][barriers: weights, done[GROUPS]][tmem ptr]
+    // layout: [blob: weight images | bias table][barriers: weights, done[GROUPS]][tmem ptr][next tile of every group]
     const float* sbias = reinterpret_cast<const float*>(smem + ch.bias_off);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + ((ch.blob_bytes + 15u) & ~15u));
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 1 + GROUPS);
+    volatile unsigned* tile_slot = reinterpret_cast<volatile unsigned*>(bars + 6);   // [GROUPS <= 4]
     const unsigned bar_w = tc_smem_u32(&bars[0]);
     const unsigned smem_w = tc_smem_u32(smem);
 
@@ -902,6 +901,14 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: MMA operands stay in uniform registers
     const int g = warp / WPG, gw = warp % WPG;
     const unsigned bar_done = tc_smem_u32(&bars[1 + g]);
+    const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
+    const int64_t ntiles = io.nseg * tiles_per_seg;
+    // Dynamic tile scheduling (io.tile_ctr): every group draws its tiles from one global counter, so a CTA whose SM was
+    // held by another stream's kernel when the launch began only takes what is left when it finally starts.  Every group
+    // draws until its first out-of-range ticket: ntiles + gridDim.x * GROUPS draws in total, and whoever receives the
+    // last ticket resets the counter for the next launch that is handed the same word.
+    const bool dyn = io.tile_ctr != nullptr;
+    const unsigned last_ticket = (unsigned)ntiles + gridDim.x * GROUPS - 1u;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -910,13 +917,25 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
         tc_mbar_init(bar_w, 1);
         for (int i = 0; i < GROUPS; ++i) tc_mbar_init(tc_smem_u32(&bars[1 + i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // the whole blob, in pieces of at most 32 KB, all completing on one barrier
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(ch.blob_bytes) : "memory");
-        for (unsigned off = 0; off < ch.blob_bytes; off += 32768u) {
-            const unsigned n = ch.blob_bytes - off < 32768u ? ch.blob_bytes - off : 32768u;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_w + off),
-                         "l"(blob + off), "r"(n), "r"(bar_w)
-                         : "memory");
+        bool any = true;
+        if (dyn) {
+            any = false;
+            for (int i = 0; i < GROUPS; ++i) {
+                const unsigned t = atomicAdd(io.tile_ctr, 1u);
+                if (t == last_ticket) atomicExch(io.tile_ctr, 0u);
+                tile_slot[i] = t;
+                any = any || (int64_t)t < ntiles;
+            }
+        }
+        if (any) {   // (a CTA that arrives after the last tile was taken must not leave with a copy in flight)
+            // the whole blob, in pieces of at most 32 KB, all completing on one barrier
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(ch.blob_bytes) : "memory");
+            for (unsigned off = 0; off < ch.blob_bytes; off += 32768u) {
+                const unsigned n = ch.blob_bytes - off < 32768u ? ch.blob_bytes - off : 32768u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_w + off),
+                             "l"(blob + off), "r"(n), "r"(bar_w)
+                             : "memory");
+            }
         }
     }
     tc_fence_before();
@@ -931,19 +950,19 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
     unsigned done_phase = 0;
     bool w_ready = false;
 
-    pdl_trigger();
-    pdl_wait();   // everything above (TMEM, barriers, the weight blob on its way) is independent of the kernel before
-
-    const int64_t tiles_per_seg = (io.seg_rows + 127) / 128;
-    const int64_t ntiles = io.nseg * tiles_per_seg;
-    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + g; tile < ntiles; tile += (int64_t)gridDim.x * GROUPS) {
+    const bool leader = gw == 0 && lane == 0;   // draws the group's tickets (and issues its MMAs)
+    int round = 0;
+    for (int64_t tile = dyn ? (int64_t)tile_slot[g] : (int64_t)blockIdx.x * GROUPS + g; tile < ntiles; ++round) {
+        // the NEXT tile's ticket is drawn now and only looked at when this tile is finished: the atomic's latency hides
+        unsigned next_ticket = 0u;
+        if (dyn && leader) next_ticket = atomicAdd(io.tile_ctr, 1u);
         const int64_t seg = tile / tiles_per_seg;
         const int64_t r_in_seg = (tile % tiles_per_seg) * 128 + wl * 32 + lane;
         RowCtx<IN> rc;
         rc.valid = r_in_seg < io.seg_rows;
         rc.row = seg * io.seg_rows + r_in_seg;
         const bool rec = io.dbg != nullptr && blockIdx.x == 0 && gw == 0 && lane == 0;
-        long long* drow = io.dbg + (g * 64 + (tile / ((int64_t)gridDim.x * GROUPS)) % 64) * 32;
+        long long* drow = io.dbg + (g * 64 + round % 64) * 32;
         int dcol = 0;
         if (rec) drow[dcol++] = clock64();
         row_setup<IN>(io, rc);
@@ -1136,10 +1155,15 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 }
             }
             if (rec) drow[dcol++] = clock64();
+            if (last && dyn && leader) {   // published before the group's closing barrier, read by everyone after it
+                if (next_ticket == last_ticket) atomicExch(io.tile_ctr, 0u);
+                tile_slot[g] = next_ticket;
+            }
             tc_fence_before();
             tc_group_bar(1 + g, GTHREADS);
         }
         if (rec) drow[dcol++] = clock64();
+        tile = dyn ? (int64_t)tile_slot[g] : tile + (int64_t)gridDim.x * GROUPS;
     }
     tc_fence_before();
     __syncthreads();
@@ -1148,14 +1172,38 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
 
 static size_t tc_res_smem_bytes(const TcChain& c) { return (size_t)((c.blob_bytes + 15u) & ~15u) + 8 * 8 + 16; }
 
-// 0 = automatic (resident when the chain fits), 1 = always stream (mlp_tc_kernel), 2 = resident or fail
-static int g_tc_engine = 0;
-static long long* g_tc_dbg = nullptr;   // pn_mlp_set_debug
-static int g_tc_quad = 1;               // pn_mlp_set_engine(engine | 4) disables the coalesced quad producer
-static int g_tc_nslice = 1;             // pn_mlp_set_engine(engine | 8) disables N-slicing of single-layer chains
-static int g_tc_wide = 1;               // pn_mlp_set_engine(engine | 16) disables the 16-warp streaming CTAs
-static int g_tc_reserved = 0;           // pn_mlp_set_reserved_sms
-static int g_tc_split = 1;              // pn_mlp_set_precision: 1 = bf16x3 (fp32 parity), 0 = single-pass bf16
+// Per-call launch options (pn_launch_opts), decoded.
+struct TcOpts {
+    int engine = 0;             // 0 = automatic (resident when the chain fits), 1 = always stream (mlp_tc_kernel), 2 = resident or fail
+    int quad = 1;               // mlp_engine | 4 disables the coalesced quad producer
+    int nslice = 1;             // mlp_engine | 8 disables N-slicing of single-layer chains
+    int wide = 1;               // mlp_engine | 16 disables the 16-warp streaming CTAs
+    int reserved = 0;           // reserved_sms
+    int split = 1;              // mlp_passes: 1 = bf16x3 (fp32 parity), 0 = single-pass bf16
+    long long* dbg = nullptr;   // mlp_debug
+    unsigned* tile_ctr = nullptr;
+};
+
+static int tc_opts_from(const pn_launch_opts* o, TcOpts* t, const char* what) {
+    if (!o) return PN_OK;
+    PN_REQUIRE(o->mlp_passes == 0 || o->mlp_passes == 1 || o->mlp_passes == 3, PN_ERR_BAD_ARG,
+               "%s: pn_launch_opts.mlp_passes must be 3 (or 0: split bf16, fp32 parity) or 1 (plain bf16)", what);
+    const int engine = o->mlp_engine;
+    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 32, PN_ERR_BAD_ARG,
+               "%s: pn_launch_opts.mlp_engine: 0 = automatic, 1 = streaming, 2 = resident; +4 = row-per-thread producers only; "
+               "+8 = no N-slicing; +16 = 8-warp streaming CTAs only", what);
+    PN_REQUIRE(o->reserved_sms >= 0 && o->reserved_sms < 148, PN_ERR_BAD_ARG, "%s: pn_launch_opts.reserved_sms must be in [0, 148)", what);
+    PN_REQUIRE(((uintptr_t)o->tile_counter & 3) == 0, PN_ERR_ALIGNMENT, "%s: pn_launch_opts.tile_counter must be 4-byte aligned", what);
+    t->split = o->mlp_passes == 1 ? 0 : 1;
+    t->engine = engine & 3;
+    t->quad = (engine & 4) ? 0 : 1;
+    t->nslice = (engine & 8) ? 0 : 1;
+    t->wide = (engine & 16) ? 0 : 1;
+    t->reserved = o->reserved_sms;
+    t->dbg = static_cast<long long*>(o->mlp_debug);
+    t->tile_ctr = o->tile_counter;
+    return PN_OK;
+}
 
 // Resident kernel usable?  Returns warps per group (8 or 4), or 0.
 static int tc_resident_wpg(const TcChain& c) {
@@ -1173,16 +1221,16 @@ static size_t tc_smem_bytes(const TcChain& c, int nstages) {
 }
 
 template <int IN>
-static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaStream_t stream, const char* what) {
+static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, const TcOpts& to, cudaStream_t stream, const char* what) {
     const int64_t ntiles_all = io.nseg * ((io.seg_rows + 127) / 128);
     // single-layer chains on few row tiles: slice the output channels over gridDim.y so that the launch fills the GPU
     int pass_w = kTcNPass;
-    if (ch.nlayers == 1 && g_tc_nslice && io.out_mode != TC_OUT_LOGSOFTMAX && ntiles_all * ((ch.L[0].n_pad + kTcNPass - 1) / kTcNPass) < 148) {
+    if (ch.nlayers == 1 && to.nslice && io.out_mode != TC_OUT_LOGSOFTMAX && ntiles_all * ((ch.L[0].n_pad + kTcNPass - 1) / kTcNPass) < 148) {
         pass_w = 128;
         while (pass_w > 32 && ntiles_all * ((ch.L[0].n_pad + pass_w - 1) / pass_w) < 148) pass_w /= 2;
     }
-    const int wpg = (g_tc_engine == 1 || (pass_w != kTcNPass && g_tc_engine != 2)) ? 0 : tc_resident_wpg(ch);
-    PN_REQUIRE(g_tc_engine != 2 || wpg != 0, PN_ERR_UNSUPPORTED, "%s: chain does not fit the resident kernel", what);
+    const int wpg = (to.engine == 1 || (pass_w != kTcNPass && to.engine != 2)) ? 0 : tc_resident_wpg(ch);
+    PN_REQUIRE(to.engine != 2 || wpg != 0, PN_ERR_UNSUPPORTED, "%s: chain does not fit the resident kernel", what);
     if (wpg != 0) {
         const size_t rsmem = tc_res_smem_bytes(ch);
         auto launch_res = [&](auto rkern, int groups) -> int {
@@ -1195,13 +1243,14 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
             // one persistent CTA per SM; SMs held by kernels of other streams are left out (a CTA that had to wait for
             // its SM would start its full static share of tiles late and stretch the whole launch)
             const int64_t want = (ntiles_all + groups - 1) / groups;
-            const int64_t sms = 148 - g_tc_reserved > 1 ? 148 - g_tc_reserved : 1;
+            const int64_t sms = 148 - to.reserved > 1 ? 148 - to.reserved : 1;
             const unsigned grid = (unsigned)(want < sms ? want : sms);
             TcIo io2 = io;
-            io2.dbg = g_tc_dbg;
+            io2.dbg = to.dbg;
+            io2.tile_ctr = to.tile_ctr;
             TcChain chr = ch;
-            chr.split = g_tc_split;
-            e = launch_pdl(rkern, dim3(grid), dim3(kResThreads), rsmem, stream, chr, static_cast<const unsigned char*>(blob), io2);
+            chr.split = to.split;
+            e = launch_kernel(rkern, dim3(grid), dim3(kResThreads), rsmem, stream, chr, static_cast<const unsigned char*>(blob), io2);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -1214,7 +1263,7 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     // ring depth: what fits in ~110 KB (two CTAs can share an SM), at least 2, at most kTcMaxStages
     TcChain chs = ch;
     chs.pass_w = pass_w;
-    chs.split = g_tc_split;
+    chs.split = to.split;
     if (pass_w != kTcNPass) {   // re-plan the per-CTA resources for the narrower pass
         const TcLayer& L0 = ch.L[0];
         const int xw = L0.n_pad < pass_w ? L0.n_pad : pass_w;
@@ -1239,7 +1288,7 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     PN_REQUIRE(smem <= 227 * 1024, PN_ERR_UNSUPPORTED, "%s: chain needs %zu bytes of shared memory", what, smem);
     // (only the FP producer / epilogues gained from 16 warps; the SA levels did not, and their 8-warp CTAs fit beside the
     // background 3-NN search that runs at the same time)
-    const bool wide = g_tc_wide && IN == TC_IN_FP && (int64_t)ntiles_all * (pass_w != kTcNPass ? (ch.L[0].n_pad + pass_w - 1) / pass_w : 1) <= 148;
+    const bool wide = to.wide && IN == TC_IN_FP && (int64_t)ntiles_all * (pass_w != kTcNPass ? (ch.L[0].n_pad + pass_w - 1) / pass_w : 1) <= 148;
     auto kern = wide ? mlp_tc_kernel<IN, 512> : mlp_tc_kernel<IN, 256>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -1257,8 +1306,8 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
     const unsigned ny = (unsigned)((ch.L[ch.nlayers - 1].n_pad + pass_w - 1) / pass_w);
     const dim3 grid((unsigned)(ntiles < cap ? ntiles : cap), pass_w != kTcNPass ? ny : 1u);
     TcIo io2 = io;
-    io2.dbg = g_tc_dbg;
-    e = launch_pdl(kern, grid, dim3(wide ? 512 : 256), smem, stream, chs, static_cast<const unsigned char*>(blob), io2);
+    io2.dbg = to.dbg;
+    e = launch_kernel(kern, grid, dim3(wide ? 512 : 256), smem, stream, chs, static_cast<const unsigned char*>(blob), io2);
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -1270,34 +1319,6 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, cudaSt
 }  // namespace pn
 
 // ------------------------------------------------------------------------------------------------ C ABI
-PN_EXPORT int pn_mlp_set_precision(int passes) {
-    PN_REQUIRE(passes == 1 || passes == 3, PN_ERR_BAD_ARG, "pn_mlp_set_precision: 3 = split bf16 (fp32 parity), 1 = plain bf16");
-    pn::g_tc_split = passes == 3 ? 1 : 0;
-    return PN_OK;
-}
-
-PN_EXPORT int pn_mlp_set_reserved_sms(int sms) {
-    PN_REQUIRE(sms >= 0 && sms < 148, PN_ERR_BAD_ARG, "pn_mlp_set_reserved_sms: 0 <= sms < 148");
-    pn::g_tc_reserved = sms;
-    return PN_OK;
-}
-
-PN_EXPORT int pn_mlp_set_debug(void* timeline) {
-    pn::g_tc_dbg = static_cast<long long*>(timeline);
-    return PN_OK;
-}
-
-PN_EXPORT int pn_mlp_set_engine(int engine) {
-    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 32, PN_ERR_BAD_ARG,
-               "pn_mlp_set_engine: 0 = automatic, 1 = streaming, 2 = resident; +4 = row-per-thread producers only; "
-               "+8 = no N-slicing; +16 = 8-warp streaming CTAs only");
-    pn::g_tc_engine = engine & 3;
-    pn::g_tc_quad = (engine & 4) ? 0 : 1;
-    pn::g_tc_nslice = (engine & 8) ? 0 : 1;
-    pn::g_tc_wide = (engine & 16) ? 0 : 1;
-    return PN_OK;
-}
-
 PN_EXPORT size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc) {
     pn::TcChain ch;
     const char* why;
@@ -1355,11 +1376,13 @@ static int tc_common_checks(const pn_mlp_desc* desc, const void* blob, pn::TcCha
 }
 
 PN_EXPORT int pn_mlp_rows_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* x, int64_t ldx, int64_t rows,
-                                 int out_mode, float* y, int64_t ldy, pn_stream_t stream) {
+                                 int out_mode, float* y, int64_t ldy, const pn_launch_opts* opts, pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
     int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_mlp_rows_bf16x3");
     if (rc) return rc;
+    TcOpts to;
+    if ((rc = tc_opts_from(opts, &to, "pn_mlp_rows_bf16x3"))) return rc;
     PN_REQUIRE(x && y && rows > 0 && ldx >= desc->cin[0], PN_ERR_BAD_ARG, "pn_mlp_rows_bf16x3: bad arguments");
     PN_REQUIRE(out_mode != TC_OUT_MAX || rows % 32 == 0, PN_ERR_UNSUPPORTED, "pn_mlp_rows_bf16x3: max-pool needs rows %% 32 == 0");
     TcIo io = {};
@@ -1371,25 +1394,29 @@ PN_EXPORT int pn_mlp_rows_bf16x3(const pn_mlp_desc* desc, const void* blob, cons
     io.y = y;
     io.ldy = ldy;
     io.group = 32;
-    return tc_launch<TC_IN_ROWS>(ch, blob, io, (cudaStream_t)stream, "pn_mlp_rows_bf16x3");
+    return tc_launch<TC_IN_ROWS>(ch, blob, io, to, (cudaStream_t)stream, "pn_mlp_rows_bf16x3");
 }
 
 PN_EXPORT int pn_sa_mlp_max_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
                                    int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
                                    const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
-                                   int S, int K, int msg_order, float* out, int64_t ldo, pn_stream_t stream) {
+                                   int S, int K, int msg_order, float* out, int64_t ldo, const pn_launch_opts* opts,
+                                   pn_stream_t stream) {
     return pn_sa_mlp_bf16x3(desc, blob, xyz, xB, xN, xC, feat, fB, fN, fC, D, new_xyz, qB, qN, qC, idx, B, N, S, K, msg_order,
-                            PN_MLP_OUT_MAX32, out, ldo, stream);
+                            PN_MLP_OUT_MAX32, out, ldo, opts, stream);
 }
 
 PN_EXPORT int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* xyz, int64_t xB, int64_t xN,
                                int64_t xC, const float* feat, int64_t fB, int64_t fN, int64_t fC, int D,
                                const float* new_xyz, int64_t qB, int64_t qN, int64_t qC, const int64_t* idx, int B, int N,
-                               int S, int K, int msg_order, int out_mode, float* out, int64_t ldo, pn_stream_t stream) {
+                               int S, int K, int msg_order, int out_mode, float* out, int64_t ldo, const pn_launch_opts* opts,
+                               pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
     int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_sa_mlp_max_bf16x3");
     if (rc) return rc;
+    TcOpts to;
+    if ((rc = tc_opts_from(opts, &to, "pn_sa_mlp_bf16x3"))) return rc;
     PN_REQUIRE(out_mode == TC_OUT_MAX || out_mode == TC_OUT_ROWS, PN_ERR_BAD_ARG,
                "pn_sa_mlp_bf16x3: out_mode must be 0 (rows) or 1 (max over nsample)");
     PN_REQUIRE(xyz && new_xyz && idx && out, PN_ERR_BAD_ARG, "pn_sa_mlp_max_bf16x3: null pointer");
@@ -1409,18 +1436,20 @@ PN_EXPORT int pn_sa_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
     io.y = out;
     io.ldy = ldo;
     io.group = K == 16 ? 16 : 32;   // pooled output: one row per 16 / 32 grouped rows (K > 32: the caller reduces the K/32 partial rows)
-    return tc_launch<TC_IN_SA>(ch, blob, io, (cudaStream_t)stream, "pn_sa_mlp_max_bf16x3");
+    return tc_launch<TC_IN_SA>(ch, blob, io, to, (cudaStream_t)stream, "pn_sa_mlp_max_bf16x3");
 }
 
 PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const float* points1, int64_t p1B, int64_t p1N,
                                int64_t p1C, int D1, const float* points2, int64_t p2B, int64_t p2N, int64_t p2C, int D2,
                                int S, const int64_t* idx, const float* weight, int relu_in, const int32_t* order,
                                int64_t order_es, int64_t order_bs, const float* residual, int64_t ldr, int B, int N,
-                               int out_mode, float* out, int64_t ldo, pn_stream_t stream) {
+                               int out_mode, float* out, int64_t ldo, const pn_launch_opts* opts, pn_stream_t stream) {
     using namespace pn;
     TcChain ch;
     int rc = tc_common_checks(desc, blob, &ch, out_mode, "pn_fp_mlp_bf16x3");
     if (rc) return rc;
+    TcOpts to;
+    if ((rc = tc_opts_from(opts, &to, "pn_fp_mlp_bf16x3"))) return rc;
     PN_REQUIRE(points2 && idx && weight && out, PN_ERR_BAD_ARG, "pn_fp_mlp_bf16x3: null pointer");
     PN_REQUIRE((points1 != nullptr) == (D1 > 0) && desc->cin[0] == D1 + D2, PN_ERR_BAD_ARG,
                "pn_fp_mlp_bf16x3: first layer expects %d channels, inputs provide %d + %d", desc->cin[0], D1, D2);
@@ -1444,11 +1473,11 @@ PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
         auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
         bool ok = p2C == 1 && (p2N % 4) == 0 && (p2B % 4) == 0 && (D2 % 4) == 0 && al16(points2);
         if (D1 > 0) ok = ok && p1C == 1 && (p1N % 4) == 0 && (p1B % 4) == 0 && (D1 % 4) == 0 && al16(points1);
-        io.quad_fp = (ok && g_tc_quad) ? 1 : 0;
+        io.quad_fp = (ok && to.quad) ? 1 : 0;
     }
     io.out_mode = out_mode;
     io.y = out;
     io.ldy = ldo;
     io.group = 32;
-    return tc_launch<TC_IN_FP>(ch, blob, io, (cudaStream_t)stream, "pn_fp_mlp_bf16x3");
+    return tc_launch<TC_IN_FP>(ch, blob, io, to, (cudaStream_t)stream, "pn_fp_mlp_bf16x3");
 }

@@ -466,8 +466,15 @@ cross_entropy_kernel(const float* __restrict__ x, int64_t ldx, const int64_t* __
         float s = 0.0f;
         for (int c = 0; c < C; ++c) s += expf(xr[c] - m);
         const float lse = m + logf(s);
-        int64_t t = target[r];
-        t = t < 0 ? 0 : (t >= C ? C - 1 : t);
+        const int64_t t = target[r];
+        if (t < 0 || t >= C) {
+            // nn.CrossEntropyLoss raises on a label outside [0, C); an asynchronous kernel cannot, so the loss and this
+            // row's gradient are poisoned with NaN instead of being computed against a clamped label
+            local += (double)CUDART_NAN_F;
+            if (dx)
+                for (int c = 0; c < C; ++c) dx[r * lddx + c] = CUDART_NAN_F;
+            continue;
+        }
         local += (double)(lse - xr[t]);
         if (dx) {
             const float k = grad_scale / (float)rows;

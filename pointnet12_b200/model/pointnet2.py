@@ -231,12 +231,13 @@ class PointNet2SemSeg(_Net):
         # (ops.ball_query_stream); the regular query afterwards only fills in what the streamed one did not finish.
         grid1, streamed = None, None
         S1, K1 = sa[0].npoint, sa[0].nsample
+        fps1_cfg = ops.fps1_config()
         if N >= ops.GRID_MIN_POINTS:
-            if ops.STREAM_BALL_QUERY and N <= 32768:
-                fps_ctas, fps_smem = ops.fps_launch_info(B, N, S1)
+            if ops.stream_ball_query() and N <= 32768:
+                fps_ctas, fps_smem = ops.fps_launch_info(B, N, S1, fps1_cfg)
                 sms = torch.cuda.get_device_properties(points.device).multi_processor_count
-                ctas = (sms - fps_ctas) // B * B
-                if ctas >= max(B, ops.STREAM_BALL_MIN_FREE_SMS):
+                ctas = ops.stream_ball_ctas(sms - fps_ctas, B)
+                if ctas >= max(B, ops.STREAM_BALL_MIN_FREE_SMS if not ops.stream_ball_share() else B):
                     streamed = {"progress": torch.zeros((B, S1), dtype=torch.int64, device=points.device),
                                 "done": torch.zeros((B, S1), dtype=torch.int32, device=points.device),
                                 "out": torch.empty((B, S1, K1), dtype=torch.int64, device=points.device)}
@@ -245,7 +246,8 @@ class PointNet2SemSeg(_Net):
         with torch.cuda.stream(main):
             # level-1 sampling (the long serial kernel), issued FIRST: its clusters need whole groups of free SMs, so the
             # kernels that run beside it must find it already in place
-            fps1 = ops.fps(x0, S1, ops._i64(fps_starts[0], "start_idx"), progress=streamed["progress"] if streamed else None)
+            fps1 = ops.fps(x0, S1, ops._i64(fps_starts[0], "start_idx"), progress=streamed["progress"] if streamed else None,
+                           config=fps1_cfg)
         if N >= ops.GRID_MIN_POINTS:
             with torch.cuda.stream(geo):
                 geo.wait_event(begin)
@@ -256,7 +258,7 @@ class PointNet2SemSeg(_Net):
                 with torch.cuda.stream(feed):                # its own stream: `geo` must be free for level 2 when sampling ends
                     feed.wait_event(grid_ready)
                     ops.ball_query_stream(sa[0].radius, K1, x0, grid1, streamed["progress"], streamed["done"], streamed["out"],
-                                          ctas, 227 * 1024 - fps_smem + 1024)
+                                          ctas, 0 if ops.stream_ball_share() else 227 * 1024 - fps_smem + 1024)
                     streamed["finished"] = torch.cuda.Event()
                     streamed["finished"].record(feed)
 
@@ -292,7 +294,9 @@ class PointNet2SemSeg(_Net):
             # first layer acts on the 1024 coarse points (interpolation commutes with it): it is appended to fp2's chain,
             # whose output rows are exactly those points, so fp2 hands over z = W1 * l1_features + b1 directly.
             head = (self._head, [self.conv1, self.conv2], [self.bn1, None], [True, False], ops.OUT_LOG_SOFTMAX)
-            first = fp[0].first_layer_spec(head) if ops.mlp_mode() == "bf16x3" else None
+            # (only when fp1 really upsamples: `features` folds its first layer under the same N > S condition; with
+            # N <= sa1.npoint the fine level runs the complete chain and must be handed the plain fp2 features)
+            first = fp[0].first_layer_spec(head) if (ops.mlp_mode() == "bf16x3" and N > S1) else None
             fp2z = None
             if first is not None:
                 fp2z = (self.__dict__.setdefault("_fp2z", FoldedLayers()), [first[0]], [first[1]], [False], ops.OUT_ROWS)

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -76,43 +77,120 @@ def device_check() -> Tuple[int, int, int]:
     return sm.value, ma.value, mi.value
 
 
-def set_pdl(enabled: bool = True) -> None:
-    """Programmatic dependent launch of the critical-path kernels (pn_set_pdl)."""
-    nv.call("pn_set_pdl", int(bool(enabled)))
+# ------------------------------------------------------------------------------------------------
+# Launch options.  The C ABI keeps no process-wide settings: everything that tunes a launch travels with the call in a
+# pn_launch_opts.  Here the settings live in a process-wide default plus a per-THREAD override (`options(...)`), so two
+# Python threads can run, say, the fp32-parity and the single-pass bf16 precision at the same time.
+_tls = threading.local()
+_DEFAULTS = {
+    "precision": "bf16x3",      # 'bf16x3' | 'bf16' | 'fp32'  (set_mlp_mode)
+    "mlp_engine": 0,            # pn_launch_opts.mlp_engine flags (set_mlp_engine)
+    "reserved_sms": 0,          # SMs the resident-weight chain launches leave to other streams
+    "fps_config": (0, 0, 0),    # (cluster size, threads per CTA, exchange) of pn_fps_f32; 0 = automatic
+    "mlp_debug": None,          # device pointer of the chain timeline buffer
+    "tile_counters": None,      # TileCounters: resident chains draw their tiles dynamically (see TileCounters)
+}
+
+
+def _opt(name: str):
+    return getattr(_tls, name, _DEFAULTS[name])
+
+
+class options:
+    """with ops.options(precision="bf16", fps_config=(4, 256, 2)): ...  -- overrides for the calling thread only."""
+
+    def __init__(self, **kw):
+        for k in kw:
+            if k not in _DEFAULTS:
+                raise TypeError(f"unknown option {k!r}; known: {sorted(_DEFAULTS)}")
+        if "precision" in kw and kw["precision"] not in ("bf16x3", "bf16", "fp32"):
+            raise ValueError("precision must be 'bf16x3', 'bf16' or 'fp32'")
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        missing = object()
+        for k, v in self.kw.items():
+            self.old[k] = getattr(_tls, k, missing)
+            setattr(_tls, k, v)
+        self.missing = missing
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            if v is self.missing:
+                delattr(_tls, k)
+            else:
+                setattr(_tls, k, v)
+
+
+class TileCounters:
+    """A pool of zeroed uint32 words for pn_launch_opts.tile_counter.  Inside `with ops.options(tile_counters=pool)`
+    every resident-weight chain launch takes the next word and hands out its row tiles through it (dynamic scheduling):
+    CTAs whose SM is held by another stream's kernel when the launch begins only take what is left.  The kernel resets
+    its word before it ends, so a captured CUDA graph can be replayed; launches that may run at the same time must not
+    share a word, hence one pool per graph."""
+
+    def __init__(self, device, n: int = 64):
+        self.buf = torch.zeros((n,), dtype=torch.int32, device=device)
+        self.used = 0
+
+    def take(self) -> int:
+        if self.used >= self.buf.numel():
+            raise RuntimeError("TileCounters: pool exhausted")
+        self.used += 1
+        return self.buf.data_ptr() + 4 * (self.used - 1)
+
+
+def _launch_opts(dynamic_tiles: bool = False, fps_config=None) -> "nv.LaunchOpts":
+    o = nv.LaunchOpts()
+    o.mlp_passes = 1 if _opt("precision") == "bf16" else 3
+    o.mlp_engine = _opt("mlp_engine")
+    o.reserved_sms = _opt("reserved_sms")
+    o.fps_cluster, o.fps_threads, o.fps_exchange = fps_config if fps_config is not None else _opt("fps_config")
+    o.mlp_debug = _opt("mlp_debug")
+    pool = _opt("tile_counters")
+    o.tile_counter = pool.take() if (dynamic_tiles and pool is not None) else None
+    return o
 
 
 def fps_set_config(cluster_size: int = 0, threads: int = 0, exchange: int = 0) -> None:
-    """Tuning hook: cluster size, threads per CTA, exchange (1 = barrier.cluster, 2 = st.async); 0 = automatic."""
-    nv.call("pn_fps_set_config", cluster_size, threads, exchange)
+    """Tuning hook (process default): cluster size, threads per CTA, exchange (1 = barrier.cluster, 2 = st.async, 3 = st.async
+    without the z table); 0 = automatic.  Per thread / per call: options(fps_config=...) / fps(..., config=...)."""
+    _DEFAULTS["fps_config"] = (int(cluster_size), int(threads), int(exchange))
 
 
 # ------------------------------------------------------------------------------------------------
-def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor, progress: Optional[torch.Tensor] = None) -> torch.Tensor:
+def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor, progress: Optional[torch.Tensor] = None,
+        config: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """farthest_point_sample (pointnet_util.py:63-84); start_idx [B] int64 on the device.
     progress: a ZEROED int64 [B, npoint] tensor -> the kernel also publishes every centroid as it is chosen
-    (index << 32 | 1), for consumers running beside it (ball_query_stream)."""
+    (index << 32 | 1), for consumers running beside it (ball_query_stream).
+    config: (cluster size, threads per CTA, exchange) for this call (default: options / fps_set_config; 0 = automatic)."""
     xyz = _cloud(xyz, "xyz", 3)
     B, N, _ = xyz.shape
     start_idx = _i64(start_idx, "start_idx")
     if start_idx.shape != (B,):
         raise ValueError(f"start_idx must have shape ({B},), got {tuple(start_idx.shape)}")
     out = torch.empty((B, int(npoint)), dtype=torch.int64, device=xyz.device)
+    lo = _launch_opts(fps_config=config)
     with _on_device(xyz):
         if progress is None:
             nv.call("pn_fps_f32", xyz.data_ptr(), *xyz.stride(), B, N, int(npoint), start_idx.data_ptr(), out.data_ptr(),
-                    _stream(), tag=(B, N, int(npoint)))
+                    C.byref(lo), _stream(), tag=(B, N, int(npoint)))
         else:
             if progress.shape != (B, int(npoint)) or progress.dtype != torch.int64 or not progress.is_contiguous():
                 raise ValueError("progress must be a contiguous int64 [B, npoint] tensor")
             nv.call("pn_fps_progress_f32", xyz.data_ptr(), *xyz.stride(), B, N, int(npoint), start_idx.data_ptr(),
-                    out.data_ptr(), progress.data_ptr(), _stream(), tag=(B, N, int(npoint)))
+                    out.data_ptr(), progress.data_ptr(), C.byref(lo), _stream(), tag=(B, N, int(npoint)))
     return out
 
 
-def fps_launch_info(B: int, N: int, npoint: int) -> Tuple[int, int]:
+def fps_launch_info(B: int, N: int, npoint: int, config: Optional[Tuple[int, int, int]] = None) -> Tuple[int, int]:
     """(CTAs, dynamic shared memory per CTA) of the sampling launch for this shape."""
     ctas, smem = C.c_int(), C.c_size_t()
-    nv.check(nv.lib().pn_fps_launch_info(int(B), int(N), int(npoint), C.byref(ctas), C.byref(smem)), "pn_fps_launch_info")
+    lo = _launch_opts(fps_config=config)
+    nv.check(nv.lib().pn_fps_launch_info(int(B), int(N), int(npoint), C.byref(lo), C.byref(ctas), C.byref(smem)),
+             "pn_fps_launch_info")
     return ctas.value, smem.value
 
 
@@ -122,8 +200,27 @@ def fps_launch_info(B: int, N: int, npoint: int) -> Tuple[int, int]:
 FP_SKIP_AHEAD = os.environ.get("PN12_FP_SKIP_AHEAD", "0") != "0"
 FP1_BUCKET_ORDER = os.environ.get("PN12_FP1_ORDER", "0") != "0"   # fp1 walks the fine points in bucket order (helped the row-per-thread gather: 195 -> 183 us; with the quad producer it costs 0.6 %: scattered index / output rows)
 HOST_OUT_SLICES = int(os.environ.get("PN12_HOST_OUT_SLICES", "8"))   # batch slices of the last level when the output goes to the host
-STREAM_BALL_QUERY = os.environ.get("PN12_STREAM_BALL", "1") != "0"
+def stream_ball_query() -> bool:      # PN12_STREAM_BALL=0: the level-1 ball query runs after sampling instead of beside it
+    return os.environ.get("PN12_STREAM_BALL", "1") != "0"
+
+
 STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for the streamed ball query to be worth it
+# Tuning knobs of the level-1 stage (read per forward, so a benchmark can sweep them inside one process):
+#   PN12_FPS1="cluster,threads,exchange"  launch shape of the level-1 sampling (default: automatic = 8 CTAs x 4 warps per cloud)
+#   PN12_STREAM_BALL_CTAS=n               persistent CTAs of the streamed ball query (default: every SM sampling leaves idle)
+#   PN12_STREAM_BALL_SHARE=1              let those CTAs share an SM with a sampling CTA (default: shared memory sized to forbid it)
+def fps1_config() -> Optional[Tuple[int, int, int]]:
+    v = os.environ.get("PN12_FPS1", "")
+    return tuple(int(t) for t in v.split(",")) if v else None
+
+
+def stream_ball_ctas(free_sms: int, B: int) -> int:
+    v = int(os.environ.get("PN12_STREAM_BALL_CTAS", "0"))
+    return (v if v > 0 else free_sms) // B * B
+
+
+def stream_ball_share() -> bool:
+    return os.environ.get("PN12_STREAM_BALL_SHARE", "0") != "0"
 
 
 STREAM_BALL_TAIL = int(os.environ.get("PN12_STREAM_BALL_TAIL", "0"))    # last centroids per cloud left to the follow-up query (measured at C2: 0 is best, 0.891 vs 0.905-0.918 ms with 16..128)
@@ -405,52 +502,48 @@ def log_softmax(x: torch.Tensor) -> torch.Tensor:
 # Fused shared-MLP chains on the tensor cores (tcgen05 + TMEM): pn_*_bf16x3 entry points.
 # "bf16x3" computes every product as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation: fp32 parity
 # (relative error ~1e-5) at tensor-core speed.  "fp32" keeps the exact-fp32 CUDA-core path (pn_linear_f32).
-_MLP_MODE = os.environ.get("PN12_MLP", "bf16x3")
-if _MLP_MODE == "bf16":       # PN12_MLP=bf16: resolved to the single-pass precision at the first set_mlp_mode / import below
-    _MLP_MODE = "bf16x3"
-    _ENV_BF16 = True
-else:
-    _ENV_BF16 = False
 OUT_ROWS, OUT_MAX32, OUT_LOG_SOFTMAX = 0, 1, 2
-
-
-_MLP_BF16 = False
+if os.environ.get("PN12_MLP", "bf16x3") in ("bf16x3", "bf16", "fp32"):
+    _DEFAULTS["precision"] = os.environ.get("PN12_MLP", "bf16x3")
 
 
 def set_mlp_mode(mode: str) -> str:
     """'bf16x3' (tensor cores, 3-pass split bf16 = fp32 parity, default), 'bf16' (the same kernels issuing only the
     hi x hi product: plain bf16 inputs, fp32 accumulation, a third of the tensor-core work) or 'fp32' (CUDA cores, exact
-    fp32 accumulation).  Returns the old mode."""
-    global _MLP_MODE, _MLP_BF16
+    fp32 accumulation).  Sets the process default (and drops the calling thread's override); returns the old mode.
+    For one thread or one block of code use `with ops.options(precision=...)`."""
     if mode not in ("bf16x3", "bf16", "fp32"):
         raise ValueError("mode must be 'bf16x3', 'bf16' or 'fp32'")
-    old = "bf16" if (_MLP_BF16 and _MLP_MODE == "bf16x3") else _MLP_MODE
-    _MLP_MODE = "fp32" if mode == "fp32" else "bf16x3"       # which engine the modules pick
-    _MLP_BF16 = mode == "bf16"
-    nv.call("pn_mlp_set_precision", 1 if _MLP_BF16 else 3)
+    old = _opt("precision")
+    _DEFAULTS["precision"] = mode
+    if hasattr(_tls, "precision"):
+        del _tls.precision
     return old
 
 
 def mlp_mode() -> str:
     """The engine the modules use: 'bf16x3' (tensor-core chains, in either precision) or 'fp32'."""
-    return _MLP_MODE
+    return "fp32" if _opt("precision") == "fp32" else "bf16x3"
 
 
 def mlp_precision() -> str:
-    return "fp32" if _MLP_MODE == "fp32" else ("bf16" if _MLP_BF16 else "bf16x3")
+    return _opt("precision")
+
+
+_ENGINES = {"auto": 0, "stream": 1, "resident": 2, "auto-rowwise": 4, "resident-rowwise": 6, "auto-noslice": 8,
+            "stream-noslice": 9, "auto-narrow": 16, "stream-narrow": 17}
 
 
 def set_mlp_engine(engine: str = "auto") -> None:
-    """Tuning hook (pn_mlp_set_engine): 'auto' (resident-weight kernel when the packed chain fits in shared memory,
-    streaming ring otherwise), 'stream' or 'resident'; '*-rowwise' keeps the row-per-thread producers (no coalesced
-    quad producer) for A/B comparisons."""
-    nv.call("pn_mlp_set_engine", {"auto": 0, "stream": 1, "resident": 2, "auto-rowwise": 4, "resident-rowwise": 6,
-                                  "auto-noslice": 8, "stream-noslice": 9, "auto-narrow": 16, "stream-narrow": 17}[engine])
+    """Tuning hook (process default of pn_launch_opts.mlp_engine): 'auto' (resident-weight kernel when the packed chain fits
+    in shared memory, streaming ring otherwise), 'stream' or 'resident'; '*-rowwise' keeps the row-per-thread producers (no
+    coalesced quad producer) for A/B comparisons."""
+    _DEFAULTS["mlp_engine"] = _ENGINES[engine]
 
 
 def set_reserved_sms(sms: int = 0) -> None:
-    """SMs the resident-weight chain launches leave to kernels of other streams (pn_mlp_set_reserved_sms)."""
-    nv.call("pn_mlp_set_reserved_sms", int(sms))
+    """SMs the resident-weight chain launches of the CALLING THREAD leave to kernels of other streams."""
+    _tls.reserved_sms = int(sms)
 
 
 FOLD_FIRST_FP_LAYER = os.environ.get("PN12_FP_FOLD", "1") != "0"
@@ -519,7 +612,7 @@ def mlp_rows_tc(chain: PackedChain, x: torch.Tensor, out_mode: int = OUT_ROWS,
     ldy = out.stride(0) if out_rows > 1 else max(out.stride(0), chain.cout)
     with _on_device(x):
         nv.call("pn_mlp_rows_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), x.data_ptr(), ldx, rows, out_mode,
-                out.data_ptr(), ldy, _stream())
+                out.data_ptr(), ldy, C.byref(_launch_opts(True)), _stream())
     return out
 
 
@@ -545,7 +638,7 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
         with _on_device(xyz):
             nv.call("pn_sa_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), xyz.data_ptr(), *xyz.stride(), _p(feat),
                     *fs, D, new_xyz.data_ptr(), *new_xyz.stride(), idx.data_ptr(), B, N, S, K, int(msg_order), int(out_mode),
-                    part.data_ptr(), chain.cout, _stream())
+                    part.data_ptr(), chain.cout, C.byref(_launch_opts(True)), _stream())
         pooled = group_max(part, K // 32, out=out)
         return pooled.view(B, S, chain.cout) if out is None else out
     if out_mode == OUT_ROWS:
@@ -563,7 +656,7 @@ def sa_mlp_max_tc(chain: PackedChain, xyz: torch.Tensor, feat: Optional[torch.Te
     with _on_device(xyz):
         nv.call("pn_sa_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), xyz.data_ptr(), *xyz.stride(), _p(feat),
                 *fs, D, new_xyz.data_ptr(), *new_xyz.stride(), idx.data_ptr(), B, N, S, K, int(msg_order), int(out_mode),
-                out.data_ptr(), ldo, _stream())
+                out.data_ptr(), ldo, C.byref(_launch_opts(True)), _stream())
     return out
 
 
@@ -617,7 +710,7 @@ def fp_mlp_tc(chain: PackedChain, points1: Optional[torch.Tensor], points2: torc
     with _on_device(points2):
         nv.call("pn_fp_mlp_bf16x3", C.byref(chain.desc), chain.blob.data_ptr(), _p(points1), *s1, D1, points2.data_ptr(),
                 *points2.stride(), D2, S, idx.data_ptr(), weight.data_ptr(), int(bool(relu_in)), optr, oes, obs, rptr, ldr,
-                B, N, out_mode, out.data_ptr(), chain.cout, _stream())
+                B, N, out_mode, out.data_ptr(), chain.cout, C.byref(_launch_opts(True)), _stream())
     return full_out
 
 
@@ -787,15 +880,6 @@ def bn_act_backward(y: torch.Tensor, st: BatchStats, dz: torch.Tensor, relu: boo
 GRAD_TC_MIN_TILE = int(os.environ.get("PN12_GRAD_TC_MIN", "1024"))     # cout * cin from which the 128 x 128 tensor-core tile is worth its padding
 
 
-def set_grad_weight_ctas_per_sm(ctas: int = 1) -> None:
-    """Tuning hook (pn_grad_weight_set_ctas_per_sm)."""
-    nv.call("pn_grad_weight_set_ctas_per_sm", int(ctas))
-
-
-if os.environ.get("PN12_GRADW_CTAS"):
-    set_grad_weight_ctas_per_sm(int(os.environ["PN12_GRADW_CTAS"]))
-
-
 def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor],
                 engine: str = "auto", x_stats: Optional[BatchStats] = None, x_relu: bool = True) -> None:
     """dw [cout, cin] += dy^T x, db [cout] += column sums of dy (in place; the buffers hold zeros or a gradient).
@@ -807,7 +891,7 @@ def grad_weight(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, db: Optiona
     if x.shape[0] != rows or dw.shape != (cout, cin) or not dw.is_contiguous() or dw.dtype != torch.float32:
         raise ValueError("grad_weight: shape mismatch")
     if engine == "auto":
-        engine = "tc" if (_MLP_MODE == "bf16x3" and cout * cin >= GRAD_TC_MIN_TILE) else "fp32"
+        engine = "tc" if (mlp_mode() == "bf16x3" and cout * cin >= GRAD_TC_MIN_TILE) else "fp32"
     if x_stats is not None:
         # x is the PRE-normalisation output of the previous layer: its normalise + ReLU is applied on load (tensor cores only)
         with _on_device(dy):
@@ -938,6 +1022,3 @@ def seg_metrics(logp: torch.Tensor, target: torch.Tensor, want_pred: bool = Fals
         nv.call("pn_seg_metrics_f32", x.data_ptr(), _ld(x), target.data_ptr(), rows, Cc, _p(pred), counts.data_ptr(), _stream())
     return (counts, pred.view(logp.shape[:-1])) if want_pred else counts
 
-
-if _ENV_BF16:
-    set_mlp_mode("bf16")

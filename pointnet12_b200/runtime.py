@@ -1,33 +1,72 @@
-"""CUDA-graph replay of a network forward (launch-bound inner loop -> one graph launch per batch).
+"""CUDA-graph replay of a network forward, with several batches in flight.
 
-A PointNet2SemSeg forward is ~40 kernel launches spread over three streams; captured once per input shape it
-replays as a single graph launch, with the fork/join between the streams preserved as graph dependencies.
-Only device memory, streams and graphs come from PyTorch; every node of the graph is one of our kernels.
+A PointNet2SemSeg forward is ~40 kernel launches spread over six streams; captured once per input shape it replays as
+a single graph launch, with the fork/join between the streams preserved as graph dependencies.  Only device memory,
+streams and graphs come from PyTorch; every node of the graph is one of our kernels.
 
     runner = GraphedSemSeg(net)            # net: PointNet2SemSeg or the load_pointnet wrapper, in eval mode
     logp = runner(points)                  # points [B, 4, N] on the device or in (pinned) host memory
 
-The FPS start indices are still drawn on the CPU generator for every call, exactly like the reference
-(pointnet_util.py:75), and reach the graph's static buffer through a small ring of pinned staging buffers.
+Batches in flight (`depth` > 1).  One forward is a long serial phase on a third of the SMs (level-1 farthest-point sampling:
+1024 dependent iterations per cloud) followed by tensor-core chains that want the whole GPU; consecutive batches are
+independent (the reference's loop `for points, target in loader: pred = model(points)`, pcdseg.py:58-97), so the runner keeps
+`depth` static buffer sets with one captured graph each and replays them on their own streams: the sampling of batch k+1 runs
+beside the chains of batch k.  The resident-weight chain kernels then hand out their row tiles dynamically (ops.TileCounters),
+because a persistent CTA may get its SM only when a sampling cluster of the other batch has left it.
+
+    t1 = runner.submit(batch1)             # asynchronous: copies the input, replays set (k % depth)
+    t2 = runner.submit(batch2)
+    logp1 = runner.result(t1)              # orders the current stream (device output) or the host (to_host) after batch 1
+    ...                                    # a result stays valid until `depth` further submits
+
+The FPS start indices are drawn on the CPU generator for every batch, exactly like the reference (pointnet_util.py:75),
+and reach the graph's static buffer through a small ring of pinned staging buffers.
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
+from . import ops
+
+
+class Ticket:
+    """Handle of a submitted batch (GraphedSemSeg.submit)."""
+
+    __slots__ = ("set", "seq", "done", "to_host")
+
+    def __init__(self, st, seq, done, to_host):
+        self.set, self.seq, self.done, self.to_host = st, seq, done, to_host
+
 
 class GraphedSemSeg:
-    """Shape-keyed CUDA-graph cache around PointNet2SemSeg.forward."""
+    """Shape-keyed CUDA-graph cache around PointNet2SemSeg.forward with `depth` batches in flight."""
 
-    RING = 8
+    RING = 4
 
-    def __init__(self, net, warmup: int = 2):
+    def __init__(self, net, warmup: int = 2, depth: int = 1):
         self.net = net.module if hasattr(net, "module") else net
         self.warmup = warmup
+        self.depth = max(1, int(depth))
         self._graphs: Dict[Tuple, dict] = {}
+        self._tensors = list(self.net.parameters()) + list(self.net.buffers())
+        self._sig = None
 
-    def _build(self, points: torch.Tensor, to_host: bool = False) -> dict:
+    # ---- the captured graphs bake in the device pointers of the folded / packed weights: any change of a parameter or
+    # BatchNorm buffer (optimizer step, load_state_dict, .to()) must rebuild them (and must not replay freed blobs)
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in self._tensors)
+
+    def _check_weights(self, dev):
+        sig = self._signature()
+        if sig != self._sig:
+            if self._graphs:
+                torch.cuda.synchronize(dev)       # replays in flight still read the old blobs
+                self._graphs.clear()
+            self._sig = sig
+
+    def _build_set(self, points: torch.Tensor, to_host: bool) -> dict:
         net, dev = self.net, points.device
         B, C, N = points.shape
         sizes = [N] + [m.npoint for m in (net.sa1, net.sa2, net.sa3)]
@@ -38,35 +77,47 @@ class GraphedSemSeg:
             "pinned": [torch.zeros((len(sizes), B), dtype=torch.int64).pin_memory() for _ in range(self.RING)],
             "events": [None] * self.RING,
             "slot": 0,
+            "stream": torch.cuda.Stream(dev),
+            "counters": ops.TileCounters(dev, 128) if self.depth > 1 else None,
+            "seq": -1,
         }
         st["x"].copy_(points)
         classes = net.conv2.out_channels
         st["host_out"] = torch.empty((B, N, classes), dtype=torch.float32).pin_memory() if to_host else None
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():
+        stream = st["stream"]
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream), torch.no_grad():
             for _ in range(self.warmup):             # folds BatchNorm, packs weights, sizes the allocator pools
                 net(st["x"], fps_starts=list(st["starts"].unbind(0)), host_out=st["host_out"])
-        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.current_stream(dev).wait_stream(stream)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph), torch.no_grad():
-            st["out"] = net(st["x"], fps_starts=list(st["starts"].unbind(0)), host_out=st["host_out"])
+        with ops.options(tile_counters=st["counters"]):
+            with torch.cuda.graph(graph, stream=stream), torch.no_grad():
+                st["out"] = net(st["x"], fps_starts=list(st["starts"].unbind(0)), host_out=st["host_out"])
         st["graph"] = graph
         return st
 
-    @torch.no_grad()
-    def __call__(self, points: torch.Tensor, out: torch.Tensor = None, to_host: bool = False) -> torch.Tensor:
-        """Replays the captured forward.  Returns the graph's static output buffer (valid until the next call)
-        or, when `out` is given (device or pinned host), copies the log-probabilities there asynchronously.
-        to_host=True: the device-to-host copies are nodes of the graph (the last level runs in two batch halves
-        and the first half travels while the second is computed); returns the runner's static PINNED HOST buffer,
-        complete once the current stream has been synchronised and valid until the next call."""
-        dev = points.device if points.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    def _sets(self, points: torch.Tensor, dev, to_host: bool) -> dict:
+        self._check_weights(dev)
         key = (tuple(points.shape), dev, bool(to_host))
-        st = self._graphs.get(key)
-        if st is None:
-            st = self._graphs[key] = self._build(points.to(dev), to_host=bool(to_host))
+        entry = self._graphs.get(key)
+        if entry is None:
+            on_dev = points.to(dev)
+            entry = self._graphs[key] = {"sets": [self._build_set(on_dev, bool(to_host)) for _ in range(self.depth)], "n": 0}
+            self._sig = self._signature()         # (the warm-up folded the weights; versions are unchanged, pointers too)
+        return entry
+
+    @torch.no_grad()
+    def submit(self, points: torch.Tensor, to_host: bool = False) -> Ticket:
+        """Starts the forward of one batch on the next buffer set and returns at once.  `points`: device tensor (ordered
+        after the work already queued on the current stream) or pinned host tensor (copied by the set's own stream)."""
+        dev = points.device if points.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        entry = self._sets(points, dev, to_host)
+        seq = entry["n"]
+        entry["n"] = seq + 1
+        st = entry["sets"][seq % self.depth]
+        st["seq"] = seq
         B = points.shape[0]
         slot = st["slot"] = (st["slot"] + 1) % self.RING
         if st["events"][slot] is not None:
@@ -74,15 +125,113 @@ class GraphedSemSeg:
         pinned = st["pinned"][slot]
         for i, n in enumerate(st["sizes"]):           # the reference's draws, same generator, same order
             pinned[i] = torch.randint(0, n, (B,), dtype=torch.long)
-        st["starts"].copy_(pinned, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        st["events"][slot] = ev
-        st["x"].copy_(points, non_blocking=True)
-        st["graph"].replay()
+        stream = st["stream"]
+        # ordered after the caller's stream: a device input exists from here on, and whatever the caller queued to consume
+        # the result this set held before (`depth` submits ago) has been issued ahead of this point
+        ready = torch.cuda.Event()
+        ready.record()
+        stream.wait_event(ready)
+        if points.is_cuda:
+            points.record_stream(stream)
+        with torch.cuda.stream(stream):
+            st["starts"].copy_(pinned, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            st["events"][slot] = ev
+            st["x"].copy_(points, non_blocking=True)
+            st["graph"].replay()
+            done = torch.cuda.Event()
+            done.record()
+        return Ticket(st, seq, done, bool(to_host))
+
+    def result(self, ticket: Ticket) -> torch.Tensor:
+        """The log-probabilities [B, N, classes] of a submitted batch.  Device output: the set's static buffer, ordered before
+        whatever the caller queues next on the current stream.  to_host: the set's static PINNED HOST buffer, complete on
+        return (the host waits for that batch only).  Valid until `depth` further submits reuse the set."""
+        if ticket.set["seq"] != ticket.seq:
+            raise RuntimeError(f"the result of batch {ticket.seq} was overwritten: at most depth={self.depth} batches are in flight")
+        if ticket.to_host:
+            ticket.done.synchronize()
+            return ticket.set["host_out"]
+        torch.cuda.current_stream(ticket.set["out"].device).wait_event(ticket.done)
+        return ticket.set["out"]
+
+    @torch.no_grad()
+    def __call__(self, points: torch.Tensor, out: torch.Tensor = None, to_host: bool = False) -> torch.Tensor:
+        """One batch, start to finish: submit + result.  Returns the static output buffer (valid until `depth` further
+        calls) or, when `out` is given (device or pinned host), copies the log-probabilities there asynchronously.
+        to_host=True: the device-to-host copies are nodes of the graph (the last level runs in batch slices and the first
+        clouds travel while the last are computed); returns the runner's static PINNED HOST buffer."""
+        res = self.result(self.submit(points, to_host=to_host))
         if to_host:
-            return st["host_out"]
+            return res
         if out is not None:
-            out.copy_(st["out"], non_blocking=True)
+            out.copy_(res, non_blocking=True)
             return out
+        return res
+
+    def run_pipelined(self, batches, to_host: bool = False, consume=None) -> Optional[List[torch.Tensor]]:
+        """The reference's evaluation loop (pcdseg.py:58-97) with `depth` batches in flight: submits batch k + depth - 1
+        before it hands batch k's result to `consume(k, logp)` (default: collect clones)."""
+        pending, results = [], []
+        for k, pts in enumerate(batches):
+            pending.append((k, self.submit(pts, to_host=to_host)))
+            if len(pending) >= self.depth:
+                j, t = pending.pop(0)
+                r = self.result(t)
+                results.append(consume(j, r) if consume is not None else r.clone())
+        for j, t in pending:
+            r = self.result(t)
+            results.append(consume(j, r) if consume is not None else r.clone())
+        return results
+
+
+class GraphedModule:
+    """CUDA-graph replay of any eval-mode network of this package whose forward draws nothing on the host -- PointNetSeg /
+    PointNetCls / PointNetDenseCls (model/pointnet.py: no sampling, hence no FPS start draw).  Config C1 (PointNetSeg, one
+    cloud of 24000 points) is ~25 launches of a few microseconds each plus per-call host glue; captured once per input shape
+    it is one graph launch.  Returns the graph's static output tensors (valid until the next call); rebuilt when a parameter
+    or BatchNorm buffer changes, like GraphedSemSeg."""
+
+    def __init__(self, net, warmup: int = 2):
+        self.net = net.module if hasattr(net, "module") else net
+        self.warmup = warmup
+        self._graphs: Dict[Tuple, dict] = {}
+        self._tensors = list(self.net.parameters()) + list(self.net.buffers())
+        self._sig = None
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in self._tensors)
+
+    @torch.no_grad()
+    def __call__(self, *inputs: torch.Tensor):
+        dev = next((t.device for t in inputs if t.is_cuda), torch.device("cuda", torch.cuda.current_device()))
+        sig = self._signature()
+        if sig != self._sig:
+            if self._graphs:
+                torch.cuda.synchronize(dev)
+                self._graphs.clear()
+            self._sig = sig
+        key = tuple((tuple(t.shape), t.dtype) for t in inputs) + (dev,)
+        st = self._graphs.get(key)
+        if st is None:
+            st = {"in": [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in inputs]}
+            for s, t in zip(st["in"], inputs):
+                s.copy_(t)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self.net(*st["in"])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["out"] = self.net(*st["in"])
+            st["graph"] = graph
+            self._graphs[key] = st
+            self._sig = self._signature()
+        for s, t in zip(st["in"], inputs):
+            s.copy_(t, non_blocking=True)
+        st["graph"].replay()
         return st["out"]

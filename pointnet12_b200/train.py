@@ -189,10 +189,10 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
         conv, bn, relu = layers[li]
         x, x_stats, y, st, _, am = saved[li]
         dgamma = dbeta = None
-        g_direct = False
+        g_direct = beta_direct = False
         if st is not None:
             dgamma, g_direct = _grad_sink(bn.weight, bn.weight.shape)
-            dbeta, _ = _grad_sink(bn.bias, bn.bias.shape)
+            dbeta, beta_direct = _grad_sink(bn.bias, bn.bias.shape)
             dy = ops.bn_act_backward(y, st, dz, relu, argmax=am, K=pool_K if am is not None else 1, dgamma=dgamma, dbeta=dbeta,
                                      acc=accs[li, :, :y.shape[1]], acc_ready=stats_done)
         else:
@@ -202,7 +202,7 @@ def mlp_backward(saved, layers: Sequence[Tuple], dz: torch.Tensor, pool_K: Optio
         dw, w_direct = _grad_sink(conv.weight, w.shape)
         db, b_direct = _grad_sink(conv.bias, (w.shape[0],)) if conv.bias is not None else (None, False)
         ops.grad_weight(dy, x, dw, db, x_stats=x_stats)      # x_stats: x is the previous layer's y, activated on load
-        grads[li] = (None if w_direct else dw, None if b_direct else db, None if g_direct else dgamma, None if g_direct else dbeta)
+        grads[li] = (None if w_direct else dw, None if b_direct else db, None if g_direct else dgamma, None if beta_direct else dbeta)
         if (li > 0 and x_stats is not None and FUSED_BN and FUSED_BN_BWD and ops.mlp_mode() == "bf16x3"
                 and ops.train_gemm_supported(w.shape[0], w.shape[1])):
             # the layer below kept only its pre-normalisation output (x here): the input-gradient GEMM also accumulates the
@@ -829,17 +829,35 @@ class FlatAdam:
                 p.grad = self.grad[o:o + k].view(p.shape)
             o += k
 
+    def _adopt_stray_grads(self):
+        """`net.zero_grad()` (set_to_none) or an assignment to p.grad detaches a parameter from the flat gradient: autograd
+        then accumulates into a fresh tensor the update would never see.  Fold such gradients back into the flat buffer and
+        re-point .grad (a parameter without a gradient contributes zeros, like torch.optim.Adam skipping it would not --
+        so that case raises instead of silently applying stale values)."""
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            if p.grad is None:
+                raise RuntimeError("FlatAdam: a parameter has no .grad (was net.zero_grad(set_to_none=True) called after the "
+                                   "backward pass?); use FlatAdam.zero_grad()")
+            if p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                self.grad[o:o + k].copy_(p.grad.detach().reshape(-1))
+                p.grad = self.grad[o:o + k].view(p.shape)
+            o += k
+
     def all_reduce(self, group=None):
         """Sum the flat gradient over the data-parallel ranks (one NCCL all-reduce of numel*4 bytes); the division by
         the world size is folded into the update (grad_scale)."""
         import torch.distributed as dist
 
+        self._adopt_stray_grads()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
             return 1.0 / dist.get_world_size(group)
         return 1.0
 
     def step(self, grad_scale: float = 1.0):
+        self._adopt_stray_grads()
         g = self.param_groups[0]
         if float(g["lr"]) != self._lr_host:          # the reference's per-epoch decay (pcdseg.py:160-164)
             self._lr_host = float(g["lr"])

@@ -26,10 +26,20 @@ def test_library_exports_every_declared_symbol():
 
 def test_argument_validation_needs_no_gpu():
     lib = nv.lib()
-    assert lib.pn_fps_f32(None, 0, 0, 0, 1, 16, 4, None, None, None) == -1
+    assert lib.pn_fps_f32(None, 0, 0, 0, 1, 16, 4, None, None, None, None) == -1
     assert b"null pointer" in lib.pn_last_error_string()
-    assert lib.pn_fps_set_config(3, 0, 0) == -1
-    assert lib.pn_fps_set_config(0, 0, 0) == 0
+    # launch options travel with the call (pn_launch_opts); a bad cluster size is refused before anything is launched
+    ctas, smem = C.c_int(), C.c_size_t()
+    bad = nv.LaunchOpts()
+    bad.fps_cluster = 3
+    assert lib.pn_fps_launch_info(8, 24000, 1024, C.byref(bad), C.byref(ctas), C.byref(smem)) == -1
+    assert b"fps_cluster" in lib.pn_last_error_string()
+    assert lib.pn_fps_launch_info(8, 24000, 1024, None, C.byref(ctas), C.byref(smem)) == 0 and ctas.value == 64
+    four = nv.LaunchOpts()
+    four.fps_cluster, four.fps_threads, four.fps_exchange = 4, 256, 2
+    assert lib.pn_fps_launch_info(8, 24000, 1024, C.byref(four), C.byref(ctas), C.byref(smem)) == 0 and ctas.value == 32
+    # no process-wide setters are left in the ABI
+    assert not [s for s in nv.declared_symbols() if "_set_" in s]
     d = nv.MlpDesc()
     d.nlayers = 2
     d.cin[0], d.cout[0], d.relu[0] = 128, 128, 1
@@ -208,7 +218,6 @@ def test_training_abi_argument_validation_needs_no_gpu():
     assert lib.pn_bn_stats_f32(p, 2, 10, 4, p, p, None) == -1    # leading dimension smaller than the row
     assert lib.pn_bn_bwd_stats_f32(p, 4, 10, 4, p, 4, p, 3, p, p, p, p, 1, p, p, None) == -1 and b"multiple of K" in lib.pn_last_error_string()
     assert lib.pn_grad_weight_f32(p, 4, p, 4, 0, 4, 4, p, 4, None, None) == -1
-    assert lib.pn_grad_weight_set_ctas_per_sm(3) == -1 and lib.pn_grad_weight_set_ctas_per_sm(1) == 0
     assert lib.pn_dropout_f32(p, 4, 1, 4, C.c_float(1.5), p, None, None, p, 4, None) == -1       # p must be < 1
     assert lib.pn_adam_f32(p, p, p, p, 4, C.c_float(1e-3), C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(0.0), 0,
                            C.c_float(1.0), None) == -1 and b"step" in lib.pn_last_error_string()

@@ -200,3 +200,52 @@ def test_other_heads_seeded(golden):
     logp, tf = orc.pointnet_cls(sd, x, feature_transform=True)
     assert rel_err(tf, g["pointnet_cls_tf"]) < 1e-4
     assert rel_err(logp, g["pointnet_cls_logp"]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ round-2 fixtures
+@pytest.mark.parametrize("n", [32768, 65536, 120000])
+def test_fps_large_n(golden, n):
+    """farthest_point_sample at the C3 sizes (oracle/gen_golden_r2.py): the oracle reproduces the reference bit for bit."""
+    g = golden("fps_large_n")
+    pts = syn.kitti_batch(2, n, config=3)
+    assert syn.checksum(pts) == str(g[f"n{n}_input_sum"])
+    got = orc.farthest_point_sample(pts.transpose(0, 2, 1)[:, :, :3], 1024, g[f"n{n}_start"])
+    assert np.array_equal(got, g[f"n{n}_fps"].astype(np.int64))
+
+
+@pytest.mark.parametrize("n", [1024, 512])
+def test_pointnet2_semseg_small_n(golden, ckpt_state, n):
+    """N <= sa1.npoint: level 1 'samples' as many (or more) centroids than there are points (pointnet2.py:159-176)."""
+    import torch
+
+    g = golden("semseg_small_n")
+    torch.manual_seed(n)
+    st = [torch.randint(0, m, (2,), dtype=torch.long).numpy() for m in (n, 1024, 256, 64)]
+    got = orc.pointnet2_semseg(ckpt_state, syn.kitti_batch(2, n, config=21), st)
+    assert rel_err(got, g[f"n{n}_logp"]) < 1e-4
+
+
+def test_pointnet2_cls_msg_b32(golden):
+    """The C4 batch: 32 ModelNet40-shaped clouds of 1024 points."""
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsMsg
+
+    g = golden("cls_msg_b32")
+    sd = _seeded_sd(_shapes(PointNet2ClsMsg), 1234)
+    logp, l3 = orc.pointnet2_cls_msg(sd, syn.modelnet_batch(32, 1024), _starts([1024, 512], 32))
+    assert rel_err(l3, g["l3_points"]) < 1e-4
+    assert rel_err(logp, g["logp"]) < 1e-4
+
+
+def test_pointnet_seg_c1(golden):
+    """PointNetSeg at the C1 shape (B = 1, N = 24000)."""
+    from pointnet12_b200.model.pointnet import PointNetSeg
+
+    g = golden("pointnet_seg_c1")
+    pts = syn.kitti_batch(1, 24000, config=1)
+    assert syn.checksum(pts) == str(g["input_sum"])
+    sd = _seeded_sd(_shapes(lambda: PointNetSeg(19, input_dims=4, feature_transform=True)), 1234)
+    logp, tf = orc.pointnet_seg(sd, pts, feature_transform=True)
+    assert rel_err(tf, g["trans_feat"]) < 1e-4
+    assert rel_err(logp[:, ::8], g["logp_sub"]) < 1e-4
+    sure = g["margin"].astype(np.float32) > 2e-3
+    assert np.array_equal(logp.argmax(-1)[sure], g["label"].astype(np.int64)[sure])

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(argv=None, cpu_baseline=None):
+def main(argv=None, cpu_baseline=None, init_pg=True, emit=True):
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
@@ -47,7 +47,7 @@ def main(argv=None, cpu_baseline=None):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
+    if world > 1 and init_pg:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234)                                   # same initial weights on every rank (DataParallel replicas)
     if args.model == "pointnet":
@@ -177,15 +177,32 @@ def main(argv=None, cpu_baseline=None):
                         "peak_source": src, "algorithmic_bytes_per_step": int(nbytes), "launches_per_step": n_calls,
                         "kernel_ms_per_step": t_ms, "share_of_step": t_ms / (float(total.item()) / args.steps),
                         "timing": "CUDA events around each call in an eager iteration after the timed region (includes ~2 us of launch gap per call)"}
+    # the gradient exchange alone: one NCCL all-reduce of the flat 3.9 MB gradient (device-timed, mean of 20, max over ranks)
+    allreduce_us = None
+    if world > 1:
+        for _ in range(3):
+            opt.all_reduce()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            opt.all_reduce()
+        b.record()
+        torch.cuda.synchronize()
+        t_ar = torch.tensor([a.elapsed_time(b) / 20 * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_ar, op=dist.ReduceOp.MAX)
+        allreduce_us = float(t_ar.item())
     phases = None
     if args.eager:                       # per-phase split of one more (instrumented) eager iteration
         marks = []
         step(marks)
         torch.cuda.synchronize()
         phases = {n1: round(e0.elapsed_time(e1), 4) for (n0_, e0), (n1, e1) in zip(marks[:-1], marks[1:])}
+    record = None
     if rank == 0:
         ms = float(total.item()) / args.steps
-        print(json.dumps({
+        record = {
             "metric": "pointnet2_semseg_train_points_per_sec", "value": world * B * N / (ms * 1e-3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "dtype": "f32 (GEMMs as 3-pass split bf16 on tensor cores)" if ops.mlp_mode() == "bf16x3" else "f32 (CUDA-core GEMMs)", "data": "synthetic",
@@ -198,9 +215,85 @@ def main(argv=None, cpu_baseline=None):
                     "ms_per_step": float(e2e_total.item()) / args.steps,
                     "h2d_bytes_per_step": int(host_pts.numel() * 4 + host_tgt.numel() * 8), "d2h_bytes_per_step": 4},
             "cpu_baseline": None if (args.no_cpu_baseline or world > 1 or cpu_baseline is None) else cpu_baseline(),
-            "phases_ms_eager": phases, "gpu_launches": int(launches), "final_loss": float(loss.item())}))
-    if world > 1:
+            "allreduce_us": allreduce_us, "allreduce_bytes": int(opt.grad.numel() * 4),
+            "phases_ms_eager": phases, "gpu_launches": int(launches), "final_loss": float(loss.item())}
+        if emit:
+            print(json.dumps(record))
+    if world > 1 and init_pg:
         dist.destroy_process_group()
+    return record
+
+
+def dp_check(world: int, rank: int, dev, points: int = 8000, clouds: int = 8):
+    """Data-parallel equivalence on hardware (the reference's DataParallel, pcdseg.py:141):
+    a fixed global batch of 8 * world clouds is processed (a) sharded, 8 clouds per rank, and (b) by rank 0 alone, shard after
+    shard.  Eval forward: the per-cloud log-probabilities must be torch.equal (clouds are independent).  Training iteration
+    (seeded weights, BatchNorm statistics per replica as DataParallel computes them, same dropout streams): the all-reduced
+    mean gradient against the mean of rank 0's per-shard gradients, relative L2 (atomics reorder sums: <= 1e-5)."""
+    import torch.distributed as dist
+
+    from pointnet12_b200 import synthetic as syn
+    from pointnet12_b200.model.pointnet2 import PointNet2SemSeg
+    from pointnet12_b200.train import cross_entropy, semseg_forward_train
+
+    def shard(s):
+        x = torch.from_numpy(syn.kitti_batch(clouds, points, config=2, first=5000 + clouds * s)).to(dev)
+        g = torch.Generator().manual_seed(777 + s)
+        st = [torch.randint(0, n, (clouds,), generator=g, dtype=torch.long).to(dev) for n in (points, 1024, 256, 64)]
+        tgt = torch.randint(0, 19, (clouds, points), generator=g, dtype=torch.long).to(dev)
+        so = torch.tensor([4242 + s, 1], dtype=torch.int64, device=dev)          # dropout stream {seed, offset} of this shard
+        return x, st, tgt, so
+
+    torch.manual_seed(1234)                                   # identical replicas
+    net = PointNet2SemSeg(19, feature_dims=1).to(dev)
+    params = [p for p in net.parameters() if p.requires_grad]
+
+    def eval_logp(s):
+        x, st, _, _ = shard(s)
+        net.eval()
+        with torch.no_grad():
+            return net(x, fps_starts=st)
+
+    def train_grad(s):
+        x, st, tgt, so = shard(s)
+        net.train()
+        for p in params:
+            p.grad = None
+        loss = cross_entropy(semseg_forward_train(net, x, st, seed_offset=so), tgt)
+        loss.backward()
+        return torch.cat([p.grad.reshape(-1) for p in params]).clone()
+
+    state = {k: v.clone() for k, v in net.state_dict().items()}   # train() forwards move the BatchNorm running statistics
+
+    def reset():
+        net.load_state_dict(state)
+
+    mine = eval_logp(rank)
+    g_mine = train_grad(rank)
+    reset()
+    if world > 1:
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+        g_mean = g_mine.clone()
+        dist.all_reduce(g_mean, op=dist.ReduceOp.SUM)
+        g_mean /= world
+    else:
+        gathered, g_mean = [mine], g_mine
+    if rank != 0:
+        return None
+    equal = True
+    g_alone = torch.zeros_like(g_mean)
+    for s in range(world):
+        equal = equal and bool(torch.equal(eval_logp(s), gathered[s]))
+        g_alone += train_grad(s)
+        reset()
+    g_alone /= world
+    rel = float((g_mean - g_alone).norm() / g_alone.norm())
+    return {"global_batch_clouds": clouds * world, "points_per_cloud": points, "world": world,
+            "logp_equal_across_world_sizes": equal, "mean_gradient_rel_l2": rel, "gradient_ok": rel <= 1e-5,
+            "what": "the same global batch sharded over the ranks vs processed by rank 0 alone, shard by shard (BatchNorm statistics "
+                    "per replica, as DataParallel computes them); eval log-probs compared with torch.equal, the all-reduced mean "
+                    "gradient of one training iteration by relative L2"}
 
 
 if __name__ == "__main__":

@@ -46,10 +46,9 @@ else:
 dbg = torch.zeros(4 * 64 * 32, dtype=torch.int64, device=dev)
 for _ in range(2):
     run()
-nv.call("pn_mlp_set_debug", dbg.data_ptr())
-run()
-torch.cuda.synchronize()
-nv.call("pn_mlp_set_debug", None)
+with ops.options(mlp_debug=dbg.data_ptr()):   # pn_launch_opts.mlp_debug of every chain launch in this block
+    run()
+    torch.cuda.synchronize()
 t = dbg.cpu().numpy().reshape(4, 64, 32)
 t0 = t[t > 0].min()
 names = ["start", "prod"] + sum([[f"L{l}.issue0", f"L{l}.issued", f"L{l}.ready", f"L{l}.epi"] for l in range(nl)], []) + ["done"]

@@ -20,10 +20,9 @@ with torch.no_grad():
     for _ in range(3):
         net(x)
     flush.fill_(1)
-    nv.call("pn_mlp_set_debug", dbg.data_ptr())
-    net(x)
-    torch.cuda.synchronize()
-    nv.call("pn_mlp_set_debug", None)
+    with ops.options(mlp_debug=dbg.data_ptr()):
+        net(x)
+        torch.cuda.synchronize()
 t = dbg.cpu().numpy().reshape(4, 64, 32)
 t0 = t[t > 0].min()
 names = ["start", "prod"] + sum([[f"L{l}.issue0", f"L{l}.issued", f"L{l}.ready", f"L{l}.epi"] for l in range(4)], []) + ["done"]

@@ -46,10 +46,9 @@ else:
 dbg = torch.zeros(1 + 2 * 512, dtype=torch.int64, device=dev)
 for _ in range(2):
     run()
-nv.call("pn_mlp_set_debug", dbg.data_ptr())
-run()
-torch.cuda.synchronize()
-nv.call("pn_mlp_set_debug", None)
+with ops.options(mlp_debug=dbg.data_ptr()):   # pn_launch_opts.mlp_debug of every chain launch in this block
+    run()
+    torch.cuda.synchronize()
 t = dbg.cpu().numpy()
 n = int(t[0])
 names = {1: "tile", 2: "prod", 3: "issued", 4: "ready", 5: "epi", 6: "w", 7: "m"}
