@@ -89,6 +89,8 @@ _DEFAULTS = {
     "fps_config": (0, 0, 0),    # (cluster size, threads per CTA, exchange) of pn_fps_f32; 0 = automatic
     "mlp_debug": None,          # device pointer of the chain timeline buffer
     "tile_counters": None,      # TileCounters: resident chains draw their tiles dynamically (see TileCounters)
+    "fps1_config": None,        # launch shape of the LEVEL-1 sampling of PointNet2SemSeg (None = automatic); PN12_FPS1 overrides
+    "stream_ball": True,        # level-1 ball query answered beside the sampling (False: after it); PN12_STREAM_BALL overrides
 }
 
 
@@ -201,7 +203,8 @@ FP_SKIP_AHEAD = os.environ.get("PN12_FP_SKIP_AHEAD", "0") != "0"
 FP1_BUCKET_ORDER = os.environ.get("PN12_FP1_ORDER", "0") != "0"   # fp1 walks the fine points in bucket order (helped the row-per-thread gather: 195 -> 183 us; with the quad producer it costs 0.6 %: scattered index / output rows)
 HOST_OUT_SLICES = int(os.environ.get("PN12_HOST_OUT_SLICES", "8"))   # batch slices of the last level when the output goes to the host
 def stream_ball_query() -> bool:      # PN12_STREAM_BALL=0: the level-1 ball query runs after sampling instead of beside it
-    return os.environ.get("PN12_STREAM_BALL", "1") != "0"
+    v = os.environ.get("PN12_STREAM_BALL", "")
+    return (v != "0") if v else bool(_opt("stream_ball"))
 
 
 STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for the streamed ball query to be worth it
@@ -211,7 +214,7 @@ STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for t
 #   PN12_STREAM_BALL_SHARE=1              let those CTAs share an SM with a sampling CTA (default: shared memory sized to forbid it)
 def fps1_config() -> Optional[Tuple[int, int, int]]:
     v = os.environ.get("PN12_FPS1", "")
-    return tuple(int(t) for t in v.split(",")) if v else None
+    return tuple(int(t) for t in v.split(",")) if v else _opt("fps1_config")
 
 
 def stream_ball_ctas(free_sms: int, B: int) -> int:

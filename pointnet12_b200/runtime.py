@@ -44,11 +44,13 @@ class GraphedSemSeg:
     """Shape-keyed CUDA-graph cache around PointNet2SemSeg.forward with `depth` batches in flight."""
 
     RING = 4
+    FPS1_PIPELINED = (4, 256, 2)
 
     def __init__(self, net, warmup: int = 2, depth: int = 1):
         self.net = net.module if hasattr(net, "module") else net
         self.warmup = warmup
         self.depth = max(1, int(depth))
+        self.timing = False                       # True: tickets carry timing-enabled completion events (benchmarks)
         self._graphs: Dict[Tuple, dict] = {}
         self._tensors = list(self.net.parameters()) + list(self.net.buffers())
         self._sig = None
@@ -65,6 +67,15 @@ class GraphedSemSeg:
                 torch.cuda.synchronize(dev)       # replays in flight still read the old blobs
                 self._graphs.clear()
             self._sig = sig
+
+    def _capture_options(self, st) -> dict:
+        """Launch options of a captured forward.  With several batches in flight what counts is the SM time a batch occupies,
+        not the latency of one forward: level-1 sampling runs as 4 CTAs x 8 warps per cloud (half the SMs of the latency-optimal
+        8 x 4, ~35 % longer) and the level-1 ball query runs after it on the whole GPU instead of polling beside it on SMs the
+        other batches' chains can use (measured at C2, B200: profiles/r02_pipeline_sweep.md)."""
+        if self.depth == 1:
+            return {"tile_counters": None}
+        return {"tile_counters": st["counters"], "fps1_config": self.FPS1_PIPELINED, "stream_ball": False}
 
     def _build_set(self, points: torch.Tensor, to_host: bool) -> dict:
         net, dev = self.net, points.device
@@ -88,11 +99,12 @@ class GraphedSemSeg:
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream), torch.no_grad():
             for _ in range(self.warmup):             # folds BatchNorm, packs weights, sizes the allocator pools
-                net(st["x"], fps_starts=list(st["starts"].unbind(0)), host_out=st["host_out"])
+                with ops.options(**{k: v for k, v in self._capture_options(st).items() if k != "tile_counters"}):
+                    net(st["x"], fps_starts=list(st["starts"].unbind(0)), host_out=st["host_out"])
         torch.cuda.current_stream(dev).wait_stream(stream)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with ops.options(tile_counters=st["counters"]):
+        with ops.options(**self._capture_options(st)):
             with torch.cuda.graph(graph, stream=stream), torch.no_grad():
                 st["out"] = net(st["x"], fps_starts=list(st["starts"].unbind(0)), host_out=st["host_out"])
         st["graph"] = graph
@@ -140,7 +152,7 @@ class GraphedSemSeg:
             st["events"][slot] = ev
             st["x"].copy_(points, non_blocking=True)
             st["graph"].replay()
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=self.timing)
             done.record()
         return Ticket(st, seq, done, bool(to_host))
 

@@ -289,11 +289,19 @@ def dp_check(world: int, rank: int, dev, points: int = 8000, clouds: int = 8):
         reset()
     g_alone /= world
     rel = float((g_mean - g_alone).norm() / g_alone.norm())
+    # noise floor: the SAME shard twice on the same GPU (the backward kernels accumulate with fp32 atomics, whose order varies)
+    g_a = train_grad(0)
+    reset()
+    g_b = train_grad(0)
+    reset()
+    floor = float((g_a - g_b).norm() / g_a.norm())
     return {"global_batch_clouds": clouds * world, "points_per_cloud": points, "world": world,
-            "logp_equal_across_world_sizes": equal, "mean_gradient_rel_l2": rel, "gradient_ok": rel <= 1e-5,
+            "logp_equal_across_world_sizes": equal, "mean_gradient_rel_l2": rel, "rerun_noise_floor_rel_l2": floor,
+            "gradient_ok": rel <= max(1e-5, 3.0 * floor),
             "what": "the same global batch sharded over the ranks vs processed by rank 0 alone, shard by shard (BatchNorm statistics "
                     "per replica, as DataParallel computes them); eval log-probs compared with torch.equal, the all-reduced mean "
-                    "gradient of one training iteration by relative L2"}
+                    "gradient of one training iteration by relative L2 (bar: 1e-5, or 3x the run-to-run floor of one GPU repeating "
+                    "one shard -- fp32 atomics in the backward kernels reorder sums)"}
 
 
 if __name__ == "__main__":
