@@ -43,6 +43,7 @@ struct TcChain {
     int nlayers, stage_bytes, tmem_cols, x_cols, a_lo_off, bias_floats;
     int nstages;        // ring depth of the streaming kernel (set at launch)
     int pass_w;         // output channels per accumulation pass of the streaming kernel: kTcNPass, or the N-slice width
+    int probe;          // timing probes of the resident kernel (results invalid): 1 = producer only, 2 = one group only, 4 = no producer
     int split;          // 1 = all three products a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (fp32 parity); 0 = a_hi*w_hi only (plain bf16)
     unsigned bias_off;  // byte offset of the bias table in the blob
     unsigned blob_bytes;
@@ -56,6 +57,7 @@ static bool plan_chain(const pn_mlp_desc* d, TcChain* c, const char** why) {
     *why = "";
     if (!d || d->nlayers < 1 || d->nlayers > kTcMaxLayers) { *why = "nlayers must be in [1, 6]"; return false; }
     c->nlayers = d->nlayers;
+    c->probe = 0;
     unsigned off = 0;
     int bias_floats = 0, stage = 0, x_cols = 0, a_k = 0;
     for (int l = 0; l < d->nlayers; ++l) {
@@ -554,6 +556,64 @@ __device__ __forceinline__ void fp_quad_producer(const TcIo& io, int64_t seg, in
     }
 }
 
+// Fast path of the quad producer for levels WITHOUT skip input whose channel count fills whole 16-channel groups (fp1 of the
+// segmentation nets: 24000 rows per cloud, the hot case).  The generic path above decides per row and per channel group
+// (valid? skip or interpolated? padding?), and every such branch ends a basic block: ptxas then issues a row's loads, waits
+// for them and only then turns to the next row -- ~26 dependent L2 round trips per tile (measured: 11.3 k cycles per 128-row
+// tile, the same for one warp group as for two: pure latency).  Here nothing branches: invalid rows are clamped to the last
+// valid row and given zero weights, so the 24 index / weight loads of a thread's four rows are issued back to back, and so are
+// the twelve 16-byte row loads of every channel group.
+__device__ __forceinline__ void fp_quad_producer_fast(const TcIo& io, int64_t seg, int64_t row0, int lane, int kchunk, int cg0,
+                                                      int cgstep, unsigned t_ahi, unsigned t_alo, long long* stamps = nullptr) {
+    const int qd = lane & 3, rq = lane >> 2;
+    const float* src[4][3];
+    float wgt[4][3];
+    const int64_t hi = io.S2 - 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r_in_seg = row0 + rq + 8 * i;
+        const bool valid = r_in_seg < io.seg_rows;
+        const int64_t row = seg * io.seg_rows + (valid ? r_in_seg : io.seg_rows - 1);
+        const int64_t* ip = io.idx3 + row * 3;
+        const float* wp = io.w3 + row * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            int64_t j = ip[k];
+            j = j < 0 ? 0 : (j > hi ? hi : j);
+            src[i][k] = io.p2 + seg * io.p2B + j * io.p2N + qd * 4;
+            const float w = wp[k];
+            wgt[i][k] = valid ? w : 0.0f;
+        }
+    }
+    const float floor_v = io.relu_in ? 0.0f : -CUDART_INF_F;   // relu(v) = max(v, 0); identity = max(v, -inf)
+    if (stamps) { if (wgt[0][0] + wgt[1][1] + wgt[2][2] + wgt[3][0] > -1.0f && src[0][0] != nullptr && src[3][2] != nullptr) *stamps++ = clock64(); }
+    for (int cg = cg0; cg * 16 < kchunk; cg += cgstep) {
+        float4 a[4][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a[i][k] = *reinterpret_cast<const float4*>(src[i][k] + cg * 16);
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // same fp32 operation order as row_value / fp_quad_value
+            v[i].x = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(a[i][0].x, wgt[i][0]), __fmul_rn(a[i][1].x, wgt[i][1])), __fmul_rn(a[i][2].x, wgt[i][2])), floor_v);
+            v[i].y = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(a[i][0].y, wgt[i][0]), __fmul_rn(a[i][1].y, wgt[i][1])), __fmul_rn(a[i][2].y, wgt[i][2])), floor_v);
+            v[i].z = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(a[i][0].z, wgt[i][0]), __fmul_rn(a[i][1].z, wgt[i][1])), __fmul_rn(a[i][2].z, wgt[i][2])), floor_v);
+            v[i].w = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(a[i][0].w, wgt[i][0]), __fmul_rn(a[i][1].w, wgt[i][1])), __fmul_rn(a[i][2].w, wgt[i][2])), floor_v);
+        }
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+            unsigned ha0, ha1, la0, la1, hb0, hb1, lb0, lb1;
+            tc_split4(v[2 * blk], ha0, ha1, la0, la1);
+            tc_split4(v[2 * blk + 1], hb0, hb1, lb0, lb1);
+            const unsigned off = ((unsigned)(blk * 16) << 16) + (unsigned)cg * 8;
+            tc_st_16x256(t_ahi + off, ha0, ha1, hb0, hb1);
+            tc_st_16x256(t_alo + off, la0, la1, lb0, lb1);
+        }
+        if (stamps) *stamps++ = clock64();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 // THREADS = 256 (8 warps, two CTAs per SM) or 512 (16 warps, one CTA per SM: used when the grid has at most one CTA per
 // SM anyway -- twice the warps halve the latency-bound producer and epilogue phases of the small levels).
@@ -894,6 +954,7 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + ((ch.blob_bytes + 15u) & ~15u));
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 1 + GROUPS);
     volatile unsigned* tile_slot = reinterpret_cast<volatile unsigned*>(bars + 6);   // [GROUPS <= 4]
+    unsigned* mma_lock = reinterpret_cast<unsigned*>(bars + 8);
     const unsigned bar_w = tc_smem_u32(&bars[0]);
     const unsigned smem_w = tc_smem_u32(smem);
 
@@ -914,6 +975,7 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
+        *mma_lock = 0u;
         tc_mbar_init(bar_w, 1);
         for (int i = 0; i < GROUPS; ++i) tc_mbar_init(tc_smem_u32(&bars[1 + i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -953,6 +1015,7 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
     const bool leader = gw == 0 && lane == 0;   // draws the group's tickets (and issues its MMAs)
     int round = 0;
     for (int64_t tile = dyn ? (int64_t)tile_slot[g] : (int64_t)blockIdx.x * GROUPS + g; tile < ntiles; ++round) {
+        if ((ch.probe & 2) && g > 0) break;
         // the NEXT tile's ticket is drawn now and only looked at when this tile is finished: the atomic's latency hides
         unsigned next_ticket = 0u;
         if (dyn && leader) next_ticket = atomicAdd(io.tile_ctr, 1u);
@@ -970,11 +1033,14 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
         for (int l = 0; l < ch.nlayers; ++l) {
             const TcLayer& L = ch.L[l];
             const bool last = l + 1 == ch.nlayers;
-            if (l == 0) {
+            if (l == 0 && !(ch.probe & 4)) {
                 // ---- producer: rows -> TMEM A region
                 bool quad = false;
                 if constexpr (IN == TC_IN_FP) quad = io.quad_fp != 0;
-                if (quad) {
+                if (quad && io.quad_fp == 2) {
+                    fp_quad_producer_fast(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, L.k_pad, half, HALVES, t_ahi, t_alo,
+                                          rec ? drow + 22 : nullptr);
+                } else if (quad) {
                     fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, 0, L.k_pad, L.k_real, half, HALVES,
                                      t_ahi, t_alo);
                 } else {
@@ -989,45 +1055,61 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 tc_fence_before();
                 tc_group_bar(1 + g, GTHREADS);
             }
+            if (ch.probe & 1) break;
             if (rec) drow[dcol++] = clock64();
             if (gw == 0) {
-                if (lane == 0) {
-                    if (!w_ready) tc_mbar_wait(bar_w, 0);
-                    tc_fence_after();
-                    const unsigned wl_base = smem_w + L.w_off;
-                    const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(L.n_pad >> 3) << 17) | (8u << 24);
-                    const int ns = (L.k_pad + kTcKSub - 1) / kTcKSub;
-                    for (int s = 0; s < ns; ++s) {
-                        const int kw = min(kTcKSub, L.k_pad - s * kTcKSub);
-                        const unsigned b_hi = wl_base + (unsigned)L.n_pad * (s * kTcKSub) * 4, b_lo = b_hi + (unsigned)L.n_pad * kw * 2;
-                        const unsigned long long dbase = ((unsigned long long)((128u >> 4) & 0x3FFF) << 16) |
-                                                         ((unsigned long long)((((unsigned)kw / 8) * 128u >> 4) & 0x3FFF) << 32) |
-                                                         (1ull << 46);
-                        for (int t = 0; t < kw / 16; ++t) {
-                            const unsigned kcol = (unsigned)(s * kTcKSub + t * 16) / 2;   // A columns of this K step
-                            const unsigned long long dh = dbase | (unsigned long long)(((b_hi + t * 256) >> 4) & 0x3FFF);
-                            const unsigned long long dl = dbase | (unsigned long long)(((b_lo + t * 256) >> 4) & 0x3FFF);
-                            const unsigned acc0 = (s > 0 || t > 0) ? 1u : 0u;
+                // ---- MMA issue.  The whole warp walks the (warp-uniform) loop and one elected lane issues: every operand of
+                // tcgen05.mma then lives in a uniform register.  (Issued from inside an `if (lane == 0)` branch the same loop
+                // costs an ELECT + 3 x R2UR.BROADCAST waterfall per MMA, ~90 cycles against the 64 the tensor pipe needs.)
+                if (!w_ready) tc_mbar_wait(bar_w, 0);
+                // One group issues a whole layer at a time.  Without the lock the groups interleave their MMAs in the tensor
+                // queue, both layers complete together and the groups stay in lock-step: MMA phases with idle CUDA cores, then
+                // epilogue phases with an idle tensor pipe.  With it the first group's accumulator is ready after one layer's
+                // worth of MMAs and its epilogue runs under the second group's: the groups settle half a phase apart.
+                if (ch.probe != 8) {
+                    if (lane == 0) while (atomicCAS(mma_lock, 0u, 1u) != 0u) {}
+                    __syncwarp();
+                }
+                tc_fence_after();
+                const unsigned wl_base = smem_w + L.w_off;
+                const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(L.n_pad >> 3) << 17) | (8u << 24);
+                const int ns = L.k_pad / kTcKSub;                    // k_pad is a multiple of 32: every slice is 32 wide
+                // shared-memory descriptor: LBO = 128 B (next 8 K values), SBO = 512 B (next 8 rows), version bit 46; the
+                // start-address field (bits 0-13, 16-byte units) advances by 16 per 16-wide K step, n_pad * 8 per slice,
+                // and the lo image of a slice sits n_pad * 4 units after its hi image
+                const unsigned d_hi32 = (unsigned)((((32u / 8) * 128u >> 4) & 0x3FFF) | (1u << 14));
+                unsigned d_lo32 = (((128u >> 4) & 0x3FFF) << 16) | ((wl_base >> 4) & 0x3FFF);
+                const unsigned lo_img = (unsigned)L.n_pad * 4u, slice = (unsigned)L.n_pad * 8u;
+                const bool issuer = tc_elect();
+                unsigned kcol = 0;
+                for (int s = 0; s < ns; ++s) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const unsigned long long dh = ((unsigned long long)d_hi32 << 32) | (unsigned long long)(d_lo32 + 16u * t);
+                        const unsigned long long dl = dh + lo_img;
+                        const unsigned acc0 = (s > 0 || t > 0) ? 1u : 0u;
+                        if (issuer) {
                             asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
                                              tbase),
                                          "r"(a_hi_col + kcol), "l"(dh), "r"(idesc), "r"(acc0)
                                          : "memory");
                             if (ch.split) {
-                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                                 tbase),
-                                             "r"(a_hi_col + kcol), "l"(dl), "r"(idesc), "r"(1u)
+                                asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;" ::"r"(tbase), "r"(a_hi_col + kcol),
+                                             "l"(dl), "r"(idesc)
                                              : "memory");
-                                asm volatile("{ .reg .pred q; setp.ne.b32 q, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q; }" ::"r"(
-                                                 tbase),
-                                             "r"(a_lo_col + kcol), "l"(dh), "r"(idesc), "r"(1u)
+                                asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;" ::"r"(tbase), "r"(a_lo_col + kcol),
+                                             "l"(dh), "r"(idesc)
                                              : "memory");
                             }
                         }
+                        kcol += 8;
                     }
-                    tc_commit(bar_done);
-                    if (rec) drow[dcol++] = clock64();
+                    d_lo32 += slice;
                 }
-                __syncwarp();   // lanes 1-31 park here while lane 0 feeds the tensor core
+                if (issuer) tc_commit(bar_done);
+                __syncwarp();
+                if (ch.probe != 8 && lane == 0) atomicExch(mma_lock, 0u);
+                if (rec) drow[dcol++] = clock64();
             }
             tc_mbar_wait(bar_done, done_phase);
             done_phase ^= 1;
@@ -1165,12 +1247,13 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
         if (rec) drow[dcol++] = clock64();
         tile = dyn ? (int64_t)tile_slot[g] : tile + (int64_t)gridDim.x * GROUPS;
     }
+    if (ch.probe && tid == 0) tc_mbar_wait(bar_w, 0);   // (probe modes may skip every reader of the weights)
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(512));
 }
 
-static size_t tc_res_smem_bytes(const TcChain& c) { return (size_t)((c.blob_bytes + 15u) & ~15u) + 8 * 8 + 16; }
+static size_t tc_res_smem_bytes(const TcChain& c) { return (size_t)((c.blob_bytes + 15u) & ~15u) + 9 * 8 + 16; }
 
 // Per-call launch options (pn_launch_opts), decoded.
 struct TcOpts {
@@ -1180,6 +1263,8 @@ struct TcOpts {
     int wide = 1;               // mlp_engine | 16 disables the 16-warp streaming CTAs
     int reserved = 0;           // reserved_sms
     int split = 1;              // mlp_passes: 1 = bf16x3 (fp32 parity), 0 = single-pass bf16
+    int probe = 0;              // (mlp_engine >> 5) & 7: timing probes (results invalid)
+    int engine_bits = 0;        // the raw mlp_engine flags (+256: generic quad producer even where the fast path applies; +512: no MMA issue lock)
     long long* dbg = nullptr;   // mlp_debug
     unsigned* tile_ctr = nullptr;
 };
@@ -1189,7 +1274,7 @@ static int tc_opts_from(const pn_launch_opts* o, TcOpts* t, const char* what) {
     PN_REQUIRE(o->mlp_passes == 0 || o->mlp_passes == 1 || o->mlp_passes == 3, PN_ERR_BAD_ARG,
                "%s: pn_launch_opts.mlp_passes must be 3 (or 0: split bf16, fp32 parity) or 1 (plain bf16)", what);
     const int engine = o->mlp_engine;
-    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 32, PN_ERR_BAD_ARG,
+    PN_REQUIRE(engine >= 0 && (engine & 3) <= 2 && engine < 1024, PN_ERR_BAD_ARG,
                "%s: pn_launch_opts.mlp_engine: 0 = automatic, 1 = streaming, 2 = resident; +4 = row-per-thread producers only; "
                "+8 = no N-slicing; +16 = 8-warp streaming CTAs only", what);
     PN_REQUIRE(o->reserved_sms >= 0 && o->reserved_sms < 148, PN_ERR_BAD_ARG, "%s: pn_launch_opts.reserved_sms must be in [0, 148)", what);
@@ -1199,6 +1284,8 @@ static int tc_opts_from(const pn_launch_opts* o, TcOpts* t, const char* what) {
     t->quad = (engine & 4) ? 0 : 1;
     t->nslice = (engine & 8) ? 0 : 1;
     t->wide = (engine & 16) ? 0 : 1;
+    t->probe = (engine >> 5) & 7;
+    t->engine_bits = engine;
     t->reserved = o->reserved_sms;
     t->dbg = static_cast<long long*>(o->mlp_debug);
     t->tile_ctr = o->tile_counter;
@@ -1250,6 +1337,7 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, const 
             io2.tile_ctr = to.tile_ctr;
             TcChain chr = ch;
             chr.split = to.split;
+            chr.probe = (to.engine_bits & 512) ? 8 : to.probe;
             e = launch_kernel(rkern, dim3(grid), dim3(kResThreads), rsmem, stream, chr, static_cast<const unsigned char*>(blob), io2);
             if (e != cudaSuccess) {
                 cudaGetLastError();
@@ -1474,6 +1562,8 @@ PN_EXPORT int pn_fp_mlp_bf16x3(const pn_mlp_desc* desc, const void* blob, const 
         bool ok = p2C == 1 && (p2N % 4) == 0 && (p2B % 4) == 0 && (D2 % 4) == 0 && al16(points2);
         if (D1 > 0) ok = ok && p1C == 1 && (p1N % 4) == 0 && (p1B % 4) == 0 && (D1 % 4) == 0 && al16(points1);
         io.quad_fp = (ok && to.quad) ? 1 : 0;
+        // 2 = the branch-free fast path: no skip input, no processing order, every 16-channel group is full
+        if (io.quad_fp && D1 == 0 && order == nullptr && (D2 % 16) == 0 && desc->cin[0] == D2 && !(to.engine_bits & 256)) io.quad_fp = 2;
     }
     io.out_mode = out_mode;
     io.y = out;

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+python tools/probes/res_timeline.py sa1 2>&1 | grep -v Warn | head -12
+python tools/probes/res_timeline.py sa2 2>&1 | grep -v Warn | head -8

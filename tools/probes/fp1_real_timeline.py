@@ -8,7 +8,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from pointnet12_b200 import _native as nv, synthetic as syn  # noqa: E402
+from pointnet12_b200 import ops, synthetic as syn  # noqa: E402
 from pointnet12_b200.model.utils import load_pointnet  # noqa: E402
 
 dev = torch.device("cuda", 0)
@@ -33,4 +33,4 @@ for g in range(2):
             continue
         d = np.diff(row[:len(names)])
         print(f"group {g} round {r}: start={int(row[0] - t0)} total={int(row[len(names) - 1] - row[0])}  " +
-              " ".join(f"{n}:{int(v)}" for n, v in zip(names[1:], d)))
+              " ".join(f"{n}:{int(v)}" for n, v in zip(names[1:], d)) + "  | producer: " + " ".join(str(int(v - row[0])) for v in row[22:28] if v > 0))

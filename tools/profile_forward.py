@@ -14,7 +14,11 @@ dev = torch.device("cuda", 0)
 net = load_pointnet("pointnet2", 19, os.path.join(ROOT, "tests", "golden", "pointnet2-inview-0.55884-0001.pth"), device=dev)
 x = torch.from_numpy(syn.kitti_batch(8, 24000, config=2)).to(dev)
 with torch.no_grad():
-    for _ in range(warm + 1):
+    for i in range(warm + 1):
         torch.manual_seed(0)
+        if i == warm:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()          # ncu --profile-from-start off: only the last forward is profiled
         net(x)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
