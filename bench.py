@@ -391,7 +391,7 @@ def run_ours(args):
             dones.append(t.done)
         end.record()
         torch.cuda.synchronize()
-        marks = [start.elapsed_time(d) for d in dones]
+        marks = sorted(start.elapsed_time(d) for d in dones)     # (batches run on their own streams and may finish out of order)
         return start.elapsed_time(end), [b - a for a, b in zip([0.0] + marks[:-1], marks)]
 
     eager_host_out = torch.empty((BATCH, NPOINTS, CLASSES), dtype=torch.float32).pin_memory() if runner is None else None

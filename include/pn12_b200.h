@@ -141,6 +141,18 @@ int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC,
 int pn_fps_progress_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, int B, int N, int npoint,
                         const int64_t* start_idx, int64_t* out_idx, uint64_t* progress, const pn_launch_opts* opts,
                         pn_stream_t stream);
+/* farthest_point_sample over a cloud whose bucket workspace exists already (pn_ball_grid_build_f32 with any radius): the same
+ * result as pn_fps_f32, bit for bit, computed with bucket pruning -- the cloud is read in cell order, so a warp's points are
+ * spatially compact, and a warp skips its whole distance update whenever the lower bound of the new centroid's distance to the
+ * warp's bounding box (evaluated with the distance's own fp32 rounding sequence, which is monotone) is not below the largest
+ * running distance of the warp.  Points live in shared memory (16 B each, 12288 per CTA): 2 CTAs per cloud of 24000 points
+ * instead of 4-8, for callers that keep several batches in flight and care about SM time rather than latency.
+ * xyz / strides: the cloud the grid was built from (only the start points are read from it).  progress: as in
+ * pn_fps_progress_f32, or NULL.  opts (tuning hooks): fps_threads = 512 -> 16 warps x 24 points per lane instead of 32 x 12,
+ * fps_exchange = 1 -> no pruning.  Limits: N <= 49152. */
+int pn_fps_sorted_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, const void* grid, size_t grid_bytes, int B, int N,
+                      int npoint, const int64_t* start_idx, int64_t* out_idx, uint64_t* progress, const pn_launch_opts* opts,
+                      pn_stream_t stream);
 /* Launch shape pn_fps_f32 would use for (B, N, npoint, opts): CTAs in the grid and dynamic shared memory per CTA. */
 int pn_fps_launch_info(int B, int N, int npoint, const pn_launch_opts* opts, int* ctas, size_t* smem_bytes);
 int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const uint64_t* progress, int B, int N,

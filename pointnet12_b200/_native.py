@@ -49,6 +49,7 @@ _SIGNATURES = {
     "pn_ball_query_grid_f32": [vp, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, vp, vp,
                                vp],
     "pn_fps_progress_f32": [vp, i64, i64, i64, i32, i32, i32, vp, vp, vp, _optsp, vp],
+    "pn_fps_sorted_f32": [vp, i64, i64, i64, vp, C.c_size_t, i32, i32, i32, vp, vp, vp, _optsp, vp],
     "pn_fps_launch_info": [i32, i32, i32, _optsp, C.POINTER(i32), C.POINTER(C.c_size_t)],
     "pn_ball_query_stream_f32": [vp, i64, i64, i64, vp, i32, i32, i32, i32, f32, i32, vp, C.c_size_t, i32, C.c_size_t, vp, vp,
                                  vp],

@@ -45,6 +45,9 @@ __device__ __forceinline__ const float4* grid_sorted(const unsigned char* ws) {
     return reinterpret_cast<const float4*>(ws + kGridHdrWords * 4 + (((size_t)kGridMaxCells + 1 + 3) / 4) * 16);
 }
 
+size_t ball_grid_cloud_bytes(int N) { return grid_cloud_bytes(N); }
+size_t ball_grid_sorted_offset() { return (size_t)kGridHdrWords * 4 + (((size_t)kGridMaxCells + 1 + 3) / 4) * 16; }
+
 // cell coordinate along one axis; monotone in v, NOT clamped above/below the grid except to keep the int sane
 __device__ __forceinline__ int grid_coord(float v, float lo, float inv) {
     const float t = __fmul_rn(__fsub_rn(v, lo), inv);
@@ -332,16 +335,19 @@ ball_query_grid_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, in
     extern __shared__ __align__(16) unsigned char gq_smem[];
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    const int s = blockIdx.x * WARPS + warp;
-    // `done` (may be NULL): rows already produced by ball_query_stream_kernel; a CTA whose rows are all done leaves
-    bool valid = s < S;
-    if (done) {
-        if (valid && done[(int64_t)b * S + s]) valid = false;
-        if (!__syncthreads_or(valid)) return;
+    // (the grid may be capped: a CTA then walks several groups of WARPS centroids)
+    for (int sg = blockIdx.x; sg * WARPS < S; sg += gridDim.x) {
+        const int s = sg * WARPS + warp;
+        // `done` (may be NULL): rows already produced by ball_query_stream_kernel; a group whose rows are all done is skipped
+        bool valid = s < S;
+        if (done) {
+            if (valid && done[(int64_t)b * S + s]) valid = false;
+            if (!__syncthreads_or(valid)) continue;
+        }
+        const float* a = qxyz + (int64_t)b * qB + (int64_t)(s < S ? s : 0) * qN;
+        gq_block<WARPS>(xyz, xB, xN, xC, N, radius2, K, ws_all + (size_t)b * ws_stride, threshold, bm_words, gq_smem, b, valid, a[0],
+                        a[qC], a[2 * qC], out + ((int64_t)b * S + (s < S ? s : 0)) * K);
     }
-    const float* a = qxyz + (int64_t)b * qB + (int64_t)(s < S ? s : 0) * qN;
-    gq_block<WARPS>(xyz, xB, xN, xC, N, radius2, K, ws_all + (size_t)b * ws_stride, threshold, bm_words, gq_smem, b, valid, a[0],
-                    a[qC], a[2 * qC], out + ((int64_t)b * S + (s < S ? s : 0)) * K);
 }
 
 // The same search fed by a RUNNING farthest-point-sampling kernel: a persistent grid on the SMs that sampling leaves idle
@@ -472,7 +478,8 @@ PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, i
             set_error("pn_ball_query_grid_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        dim3 grid((unsigned)ceil_div(S, warps), (unsigned)B);
+        int64_t gx = ceil_div(S, warps);
+        dim3 grid((unsigned)gx, (unsigned)B);
         e = launch_kernel(kern, grid, dim3(warps * 32), smem, st, xyz, xB, xN, xC, new_xyz, qB, qN, qC, N, S, radius2, nsample,
                        static_cast<const unsigned char*>(grid_ws), grid_cloud_bytes(N), threshold, bm_words, done, out_idx);
         if (e != cudaSuccess) {

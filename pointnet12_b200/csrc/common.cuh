@@ -33,6 +33,11 @@ inline int finish_launch(const char* what) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Layout of the per-cloud bucket workspace of pn_ball_grid_build_f32 (ball_grid.cu): bytes per cloud and the offset of the
+// cell-sorted float4 (x, y, z, original index) records, for kernels of other files that walk the cloud in bucket order.
+size_t ball_grid_cloud_bytes(int N);
+size_t ball_grid_sorted_offset();
+
 // Launch with the extended API (dynamic shared memory above 48 KB was enabled by the caller via cudaFuncSetAttribute).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {

@@ -368,6 +368,195 @@ fps_async_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t 
     cluster.sync();  // nobody leaves while a peer may still be storing into its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bucket-pruned sampling (exact).  With several batches in flight (runtime.GraphedSemSeg depth > 1) what counts is the SM
+// time a sampling launch occupies, not its latency: fps_async_kernel keeps the cloud in registers, which caps a CTA at
+// ~6000 points (4 CTAs = 4 SMs per cloud of 24000) and has every thread update every point in every iteration.  This kernel
+// reads the cloud in BUCKET order (the cell-sorted float4 (x, y, z, original index) records pn_ball_grid_build_f32 makes
+// anyway for the ball query), so a warp's PTS * 32 consecutive points are spatially compact, keeps them in SHARED memory
+// (16 B per point: 12288 points per CTA, two CTAs per cloud) and only the running distances in registers, and skips a warp's
+// whole update when the new centroid cannot change any of its distances:
+//     lb = ((ddx*ddx + ddy*ddy) + ddz*ddz),  ddx = max(lo.x - c.x, c.x - hi.x, 0), ...   (the warp's bounding box)
+// is evaluated with the same rounding sequence as the distance itself; IEEE rounding is monotone, so lb <= d(p, c) for every
+// point p of the box in fp32, and lb >= max_p mindist(p) implies min(mindist(p), d(p, c)) == mindist(p) for all of them:
+// the update is the identity and the warp's cached (max, arg-max) stays valid.  After the first ~50 centroids a new centroid
+// touches 10-20 % of the warps, so four warps share a scheduler at the cost of one.  The result is bit-identical to the
+// reference: ties are resolved to the lowest ORIGINAL index (carried in the record, compared explicitly, because storage
+// order is no longer index order).  Exchange between the CTAs: st.async + mbarrier as in fps_async_kernel (no z table).
+template <int NW, int PTS>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+fps_pruned_kernel(const float* __restrict__ xyz, int64_t sB, int64_t sN, int64_t sC, const unsigned char* __restrict__ grid_ws,
+                  size_t ws_stride, size_t sorted_off, int N, int npoint, const int64_t* __restrict__ start,
+                  int64_t* __restrict__ out, unsigned long long* seq, int no_prune) {
+    static_assert(PTS % 2 == 0, "points are processed in packed pairs");
+    constexpr int CAP = NW * PTS * 32, NQ = PTS / 2;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw);          // [2]
+    FpsSlot* slots = reinterpret_cast<FpsSlot*>(smem_raw + 64);                            // [2][kMaxSlots]
+    // the CTA's points, two per pair of 16-byte records so that the packed fp32x2 operands need no shuffling:
+    //   rec[((warp * NQ + q) * 2 + 0) * 32 + lane] = (x_a, x_b, y_a, y_b)      a = point 2q, b = point 2q + 1 of the lane
+    //   rec[((warp * NQ + q) * 2 + 1) * 32 + lane] = (z_a, z_b, index_a, index_b)
+    float4* rec = reinterpret_cast<float4*>(smem_raw + kAsyncSmemHeader);                  // [CAP]
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CL = cluster.num_blocks();
+    const unsigned rank = cluster.block_rank();
+    const int nslot = (int)CL * NW;
+    const int b = blockIdx.x / CL;
+    const float* __restrict__ p = xyz + (int64_t)b * sB;
+    const float4* __restrict__ sorted = reinterpret_cast<const float4*>(grid_ws + (size_t)b * ws_stride + sorted_off);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float4* wrec = rec + (size_t)warp * NQ * 2 * 32 + lane;        // this lane's records: wrec[(q * 2 + h) * 32]
+    const int g0 = (int)rank * CAP + warp * PTS * 32;              // the warp's run inside the cloud's bucket order
+
+    float d[PTS];
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        float4 v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = g0 + (2 * q + u) * 32 + lane;
+            const bool ok = j < N;
+            v[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));           // empty slot: index 0xFFFFFFFF
+            if (ok) v[u] = sorted[j];
+            d[2 * q + u] = ok ? 1e10f : -2.0f;                               // -2: never selected, never updated
+            if (ok) {
+                lo[0] = fminf(lo[0], v[u].x); hi[0] = fmaxf(hi[0], v[u].x);
+                lo[1] = fminf(lo[1], v[u].y); hi[1] = fmaxf(hi[1], v[u].y);
+                lo[2] = fminf(lo[2], v[u].z); hi[2] = fmaxf(hi[2], v[u].z);
+            }
+        }
+        wrec[(q * 2 + 0) * 32] = make_float4(v[0].x, v[1].x, v[0].y, v[1].y);
+        wrec[(q * 2 + 1) * 32] = make_float4(v[0].z, v[1].z, v[0].w, v[1].w);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    const bool warp_empty = g0 >= N;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int far = (int)start[b];
+    far = min(max(far, 0), N - 1);
+    float cx = p[(int64_t)far * sN], cy = p[(int64_t)far * sN + sC], cz = p[(int64_t)far * sN + 2 * sC];
+    __syncthreads();
+    cluster.sync();  // barriers initialised and peers resident before any st.async
+
+    const unsigned my_slot = rank * NW + warp;
+    const unsigned dst_cta = lane < (int)CL ? lane : 0;
+    const unsigned r_slot0 = map_to_cta(smem_u32(&slots[my_slot]), dst_cta);
+    const unsigned r_bar0 = map_to_cta(smem_u32(&mbar[0]), dst_cta);
+    const unsigned l_bar0 = smem_u32(&mbar[0]);
+    constexpr unsigned kParSlotOff = kMaxSlots * sizeof(FpsSlot), kParBarOff = sizeof(unsigned long long);
+
+    // the warp's cached winner: (distance bits, original index, coordinates); valid while no distance of the warp changes
+    float wmax = warp_empty ? -1.0f : 1e10f;     // max of the warp's running distances (as a float, for the box test)
+    unsigned wm = 0u, wi = kNoIndex;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+
+    int64_t* __restrict__ o = out + (int64_t)b * npoint;
+    for (int i = 0; i < npoint; ++i) {
+        const int par = i & 1;
+        if (rank == 0 && tid == 0) {
+            o[i] = far;
+            if (seq) *reinterpret_cast<volatile unsigned long long*>(seq + (int64_t)b * npoint + i) = ((unsigned long long)(unsigned)far << 32) | 1ull;
+        }
+        if (i == npoint - 1) break;  // the last arg-max would never be used
+        if (tid == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(l_bar0 + par * kParBarOff),
+                         "r"((unsigned)(nslot * kSlotBytes))
+                         : "memory");
+        // lower bound of the distance from the new centroid to any point of the warp's box, in the distance's own rounding
+        const float ddx = fmaxf(fmaxf(__fsub_rn(lo[0], cx), __fsub_rn(cx, hi[0])), 0.0f);
+        const float ddy = fmaxf(fmaxf(__fsub_rn(lo[1], cy), __fsub_rn(cy, hi[1])), 0.0f);
+        const float ddz = fmaxf(fmaxf(__fsub_rn(lo[2], cz), __fsub_rn(cz, hi[2])), 0.0f);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+        if (lb < wmax || (no_prune && !warp_empty)) {   // warp-uniform
+            const unsigned long long ncx = pack2(-cx, -cx), ncy = pack2(-cy, -cy), ncz = pack2(-cz, -cz);
+            float bv = -2.0f;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 xy = wrec[(q * 2 + 0) * 32];
+                const float4 zi = wrec[(q * 2 + 1) * 32];
+                float d0, d1;
+                sqdist_diff2(pack2(xy.x, xy.y), pack2(xy.z, xy.w), pack2(zi.x, zi.y), ncx, ncy, ncz, d0, d1);
+                d[2 * q] = fminf(d[2 * q], d0);
+                d[2 * q + 1] = fminf(d[2 * q + 1], d1);
+                bv = fmaxf(bv, fmaxf(d[2 * q], d[2 * q + 1]));
+            }
+            const unsigned vb = __float_as_uint(fmaxf(bv, 0.0f));
+            wm = __reduce_max_sync(0xffffffffu, vb);
+            // the lowest ORIGINAL index among the points that attain the warp's maximum (ties are resolved by index, as
+            // torch.max does in index order; storage order is bucket order): only the few lanes that hold the maximum look
+            unsigned cand = kNoIndex;
+            int kb = 0;
+            if (bv >= 0.0f && vb == wm) {
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) {
+                    if (d[k] == bv) {
+                        const float4 zi = wrec[((k >> 1) * 2 + 1) * 32];
+                        const unsigned ov = __float_as_uint((k & 1) ? zi.w : zi.z);
+                        if (ov < cand) {
+                            cand = ov;
+                            kb = k;
+                        }
+                    }
+                }
+            }
+            wi = __reduce_min_sync(0xffffffffu, cand);
+            const unsigned who = __ballot_sync(0xffffffffu, cand == wi && cand != kNoIndex);
+            const int src = who ? __ffs(who) - 1 : 0;
+            const float4 xy = wrec[((kb >> 1) * 2 + 0) * 32];
+            const float4 zi = wrec[((kb >> 1) * 2 + 1) * 32];
+            wx = __shfl_sync(0xffffffffu, (kb & 1) ? xy.y : xy.x, src);
+            wy = __shfl_sync(0xffffffffu, (kb & 1) ? xy.w : xy.z, src);
+            wz = __shfl_sync(0xffffffffu, (kb & 1) ? zi.y : zi.x, src);
+            wmax = __uint_as_float(wm);
+        }
+        if (lane < (int)CL) {
+            const unsigned r_slot = r_slot0 + par * kParSlotOff, r_bar = r_bar0 + par * kParBarOff;
+            asm volatile(
+                "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                    r_slot),
+                "r"(wm), "r"(wi), "r"(__float_as_uint(wx)), "r"(__float_as_uint(wy)), "r"(r_bar)
+                : "memory");
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(r_slot + 16),
+                         "r"(__float_as_uint(wz)), "r"(r_bar)
+                         : "memory");
+        }
+        mbar_wait(l_bar0 + par * kParBarOff, (unsigned)((i >> 1) & 1));
+        // reduce the CL*NW slots: one or two per lane
+        unsigned sv = 0u, si = kNoIndex;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (lane < nslot) {
+            const FpsSlot& s0 = slots[par * kMaxSlots + lane];
+            sv = s0.val; si = s0.idx; px = s0.x; py = s0.y; pz = s0.z;
+        }
+        if (lane + 32 < nslot) {
+            const FpsSlot& s1 = slots[par * kMaxSlots + lane + 32];
+            if (s1.val > sv || (s1.val == sv && s1.idx < si)) {
+                sv = s1.val; si = s1.idx; px = s1.x; py = s1.y; pz = s1.z;
+            }
+        }
+        const unsigned bm = __reduce_max_sync(0xffffffffu, sv);
+        const unsigned bi = __reduce_min_sync(0xffffffffu, sv == bm ? si : kNoIndex);
+        const unsigned who = __ballot_sync(0xffffffffu, sv == bm && si == bi);
+        const int src = __ffs(who) - 1;
+        far = (int)bi;
+        cx = __shfl_sync(0xffffffffu, px, src);
+        cy = __shfl_sync(0xffffffffu, py, src);
+        cz = __shfl_sync(0xffffffffu, pz, src);
+    }
+    cluster.sync();  // nobody leaves while a peer may still be storing into its shared memory
+}
+
 // Per-call launch configuration (from pn_launch_opts) and, for pn_fps_launch_info, where to report the launch shape.
 struct FpsCfg {
     int cluster = 0, threads = 0;
@@ -495,6 +684,56 @@ PN_EXPORT int pn_fps_progress_f32(const float* xyz, int64_t sB, int64_t sN, int6
     pn::FpsCfg fc;
     if (int rc = fps_cfg_from_opts(opts, &fc)) return rc;
     return fps_dispatch(fc, xyz, sB, sN, sC, B, N, npoint, start, out, reinterpret_cast<unsigned long long*>(progress), stream_);
+}
+
+PN_EXPORT int pn_fps_sorted_f32(const float* xyz, int64_t sB, int64_t sN, int64_t sC, const void* grid, size_t grid_bytes, int B,
+                                int N, int npoint, const int64_t* start, int64_t* out, uint64_t* progress, const pn_launch_opts* opts,
+                                pn_stream_t stream_) {
+    using namespace pn;
+    PN_REQUIRE(xyz && grid && start && out, PN_ERR_BAD_ARG, "pn_fps_sorted_f32: null pointer");
+    PN_REQUIRE(B > 0 && N > 0 && npoint > 0, PN_ERR_BAD_ARG, "pn_fps_sorted_f32: B, N, npoint must be positive (got %d, %d, %d)", B, N,
+               npoint);
+    PN_REQUIRE(grid_bytes >= pn_ball_grid_bytes(B, N), PN_ERR_BAD_ARG, "pn_fps_sorted_f32: grid buffer too small");
+    // 32 warps x 12 points per lane (default), or (tuning hook, fps_threads = 512) 16 warps x 24 points per lane
+    // (both hold 12288 points per CTA; beyond two CTAs per cloud only the 16-warp shape keeps cluster x warps <= 64 slots)
+    int NW = ((opts && opts->fps_threads == 512) || N > 2 * 12288) ? 16 : 32;
+    if (opts && opts->fps_threads == 256 && N <= 8 * 6144) NW = 8;       // 8 warps x 24 points: 6144 per CTA, two CTAs fit one SM
+    const int PTS = NW == 32 ? 12 : 24;
+    const int CAP = NW * PTS * 32;
+    const int CL = (int)ceil_div(N, CAP);
+    PN_REQUIRE(CL <= 64 / NW, PN_ERR_UNSUPPORTED, "pn_fps_sorted_f32: N=%d exceeds %d (%d CTAs of %d points)", N, 64 / NW * CAP, 64 / NW, CAP);
+    const int no_prune = (opts && opts->fps_exchange == 1) ? 1 : 0;      // tuning hook: every warp updates every iteration
+    auto launch = [&](auto kern) -> int {
+        const size_t smem = (size_t)kAsyncSmemHeader + (size_t)CAP * sizeof(float4);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pn_fps_sorted_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * CL));
+        cfg.blockDim = dim3((unsigned)(NW * 32));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream_;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, xyz, sB, sN, sC, static_cast<const unsigned char*>(grid), ball_grid_cloud_bytes(N),
+                               ball_grid_sorted_offset(), N, npoint, start, out, reinterpret_cast<unsigned long long*>(progress),
+                               no_prune);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("pn_fps_sorted_f32: launch failed (cluster=%d smem=%zu): %s", CL, smem, cudaGetErrorString(e));
+            return (int)e;
+        }
+        return PN_OK;
+    };
+    return NW == 32 ? launch(fps_pruned_kernel<32, 12>) : (NW == 16 ? launch(fps_pruned_kernel<16, 24>) : launch(fps_pruned_kernel<8, 24>));
 }
 
 PN_EXPORT int pn_fps_launch_info(int B, int N, int npoint, const pn_launch_opts* opts, int* ctas, size_t* smem_bytes) {

@@ -243,11 +243,15 @@ class PointNet2SemSeg(_Net):
                                 "out": torch.empty((B, S1, K1), dtype=torch.int64, device=points.device)}
                     begin.record(user)                       # (again: the zero fills come first)
                     main.wait_event(begin)
-        with torch.cuda.stream(main):
-            # level-1 sampling (the long serial kernel), issued FIRST: its clusters need whole groups of free SMs, so the
-            # kernels that run beside it must find it already in place
-            fps1 = ops.fps(x0, S1, ops._i64(fps_starts[0], "start_idx"), progress=streamed["progress"] if streamed else None,
-                           config=fps1_cfg)
+        sorted_cfg = None
+        if ops.GRID_MIN_POINTS <= N <= ops.FPS_SORTED_MAX_POINTS and streamed is None:
+            sorted_cfg = ops.fps1_sorted()
+        if sorted_cfg is None:
+            with torch.cuda.stream(main):
+                # level-1 sampling (the long serial kernel), issued FIRST: its clusters need whole groups of free SMs, so the
+                # kernels that run beside it must find it already in place
+                fps1 = self._whatif("fps1", lambda: ops.fps(x0, S1, ops._i64(fps_starts[0], "start_idx"),
+                                                            progress=streamed["progress"] if streamed else None, config=fps1_cfg))
         if N >= ops.GRID_MIN_POINTS:
             with torch.cuda.stream(geo):
                 geo.wait_event(begin)
@@ -261,6 +265,13 @@ class PointNet2SemSeg(_Net):
                                           ctas, 0 if ops.stream_ball_share() else 227 * 1024 - fps_smem + 1024)
                     streamed["finished"] = torch.cuda.Event()
                     streamed["finished"].record(feed)
+        if sorted_cfg is not None:
+            with torch.cuda.stream(main):
+                # throughput mode (several batches in flight): the bucket-pruned sampling kernel reads the cloud in the cell
+                # order of the ball-query buckets, so it starts after the bucket build (~35 us) and occupies fewer SMs
+                main.wait_event(grid_ready)
+                fps1 = self._whatif("fps1", lambda: ops.fps_sorted(x0, grid1, S1, ops._i64(fps_starts[0], "start_idx"),
+                                                                   config=sorted_cfg))
 
         with torch.cuda.stream(main):
             x1 = ops.index_points(x0, fps1)
@@ -289,7 +300,7 @@ class PointNet2SemSeg(_Net):
                 main.wait_event(streamed["finished"])
                 balls[0] = ops.ball_query(sa[0].radius, K1, x0, x1, grid=grid1, done=streamed["done"], out=streamed["out"])
             else:
-                balls[0] = ops.ball_query(sa[0].radius, K1, x0, x1, grid=grid1)
+                balls[0] = self._whatif("bq1", lambda: ops.ball_query(sa[0].radius, K1, x0, x1, grid=grid1))
             # fp1 and the segmentation head (conv1-bn1-relu, conv2, log_softmax) run as ONE chain: 70 % of the FLOPs.  Its
             # first layer acts on the 1024 coarse points (interpolation commutes with it): it is appended to fp2's chain,
             # whose output rows are exactly those points, so fp2 hands over z = W1 * l1_features + b1 directly.
@@ -316,9 +327,9 @@ class PointNet2SemSeg(_Net):
             # sa1 / sa2 run one persistent CTA per SM while level 2-4 sampling holds a few SMs: leave those out
             ops.set_reserved_sms(ops.fps_launch_info(B, S1, sa[1].npoint)[0])
             try:
-                fs = [f0, sa[0].features(x0, f0, x1, balls[0])]
+                fs = [f0, self._whatif("sa1", lambda: sa[0].features(x0, f0, x1, balls[0]))]
                 main.wait_event(ready[1])
-                fs.append(sa[1].features(xs[1], fs[1], xs[2], balls[1]))
+                fs.append(self._whatif("sa2", lambda: sa[1].features(xs[1], fs[1], xs[2], balls[1])))
             finally:
                 ops.set_reserved_sms(0)
             skip_ahead(1)
@@ -339,7 +350,7 @@ class PointNet2SemSeg(_Net):
                         nn_big.wait_event(wide_done)
                         if grid1 is not None:
                             nn_big.wait_event(grid_ready)
-                        nns[0] = fp[0].geometry(x0, x1, order=grid1, background=True)
+                        nns[0] = self._whatif("nn1", lambda: fp[0].geometry(x0, x1, order=grid1, background=True))
                         done_big = torch.cuda.Event()
                         done_big.record(nn_big)
             main.wait_event(done_small)
@@ -357,7 +368,8 @@ class PointNet2SemSeg(_Net):
                 up = fp[1].features(fs[1], up, *nns[1])
             main.wait_event(done_big)
             if host_out is None or ops.mlp_mode() != "bf16x3":
-                logp = fp[0].features(None, up, *nns[0], head=head, order=grid1 if ops.FP1_BUCKET_ORDER else None)
+                logp = self._whatif("fp1", lambda: fp[0].features(None, up, *nns[0], head=head,
+                                                                  order=grid1 if ops.FP1_BUCKET_ORDER else None))
                 if host_out is not None:
                     host_out.copy_(logp, non_blocking=True)
             else:
@@ -381,6 +393,20 @@ class PointNet2SemSeg(_Net):
         if not torch.cuda.is_current_stream_capturing():
             logp.record_stream(user)       # allocated on `main`, handed to the caller's stream
         return logp
+
+    def _whatif(self, name, fn):
+        """Analysis hook (tools/pipeline_sweep.py --whatif): with PN12_WHATIF=name[,name] the named kernel group is launched
+        once and its (stale) result reused afterwards -- the step time without that group bounds what optimising it can buy.
+        Results are wrong in that mode; unset (the default) this is just fn()."""
+        import os
+
+        skip = os.environ.get("PN12_WHATIF", "")
+        if not skip or name not in skip.split(","):
+            return fn()
+        cache = self.__dict__.setdefault("_whatif_cache", {})
+        if name not in cache:
+            cache[name] = fn()
+        return cache[name]
 
     def _copy_stream(self, device):
         key = ("copy", torch.device(device).index)

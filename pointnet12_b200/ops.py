@@ -91,6 +91,7 @@ _DEFAULTS = {
     "tile_counters": None,      # TileCounters: resident chains draw their tiles dynamically (see TileCounters)
     "fps1_config": None,        # launch shape of the LEVEL-1 sampling of PointNet2SemSeg (None = automatic); PN12_FPS1 overrides
     "stream_ball": True,        # level-1 ball query answered beside the sampling (False: after it); PN12_STREAM_BALL overrides
+    "fps1_sorted": None,        # level-1 sampling through the bucket-pruned kernel (fps_sorted) with this config; PN12_FPS1_SORTED overrides
 }
 
 
@@ -187,6 +188,29 @@ def fps(xyz: torch.Tensor, npoint: int, start_idx: torch.Tensor, progress: Optio
     return out
 
 
+def fps_sorted(xyz: torch.Tensor, grid: "BallGrid", npoint: int, start_idx: torch.Tensor,
+               progress: Optional[torch.Tensor] = None, config: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+    """farthest_point_sample with bucket pruning (pn_fps_sorted_f32): identical indices to fps(), computed from the cell-sorted
+    copy of the cloud inside `grid` (any radius); 2 CTAs per cloud of up to 24576 points.  For throughput (several batches in
+    flight), not latency."""
+    xyz = _cloud(xyz, "xyz", 3)
+    B, N, _ = xyz.shape
+    if (grid.B, grid.N) != (B, N):
+        raise ValueError("grid was built for another cloud shape")
+    start_idx = _i64(start_idx, "start_idx")
+    if start_idx.shape != (B,):
+        raise ValueError(f"start_idx must have shape ({B},), got {tuple(start_idx.shape)}")
+    out = torch.empty((B, int(npoint)), dtype=torch.int64, device=xyz.device)
+    with _on_device(xyz):
+        nv.call("pn_fps_sorted_f32", xyz.data_ptr(), *xyz.stride(), grid.buf.data_ptr(), grid.nbytes, B, N, int(npoint),
+                start_idx.data_ptr(), out.data_ptr(), _p(progress), C.byref(_launch_opts(fps_config=config)), _stream(),
+                tag=(B, N, int(npoint)))
+    return out
+
+
+FPS_SORTED_MAX_POINTS = 4 * 16 * 24 * 32
+
+
 def fps_launch_info(B: int, N: int, npoint: int, config: Optional[Tuple[int, int, int]] = None) -> Tuple[int, int]:
     """(CTAs, dynamic shared memory per CTA) of the sampling launch for this shape."""
     ctas, smem = C.c_int(), C.c_size_t()
@@ -215,6 +239,13 @@ STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for t
 def fps1_config() -> Optional[Tuple[int, int, int]]:
     v = os.environ.get("PN12_FPS1", "")
     return tuple(int(t) for t in v.split(",")) if v else _opt("fps1_config")
+
+
+def fps1_sorted() -> Optional[Tuple[int, int, int]]:
+    v = os.environ.get("PN12_FPS1_SORTED", "")
+    if v == "0":
+        return None
+    return tuple(int(t) for t in v.split(",")) if v else _opt("fps1_sorted")
 
 
 def stream_ball_ctas(free_sms: int, B: int) -> int:

@@ -34,6 +34,24 @@ def test_fps_large_n_golden_and_oracle(dev, golden, N):
         assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("B,N,npoint,config", [(8, 24000, 1024, None), (3, 5000, 300, None), (2, 33000, 256, None), (1, 49152, 128, None),
+                                                (5, 777, 100, None), (2, 24000, 256, (0, 512, 0)), (2, 24000, 256, (0, 256, 0)),
+                                                (2, 12289, 200, (0, 0, 1))])
+def test_fps_bucket_pruned_equals_reference_order(dev, B, N, npoint, config):
+    """pn_fps_sorted_f32: farthest-point sampling with exact bucket pruning over the cell-sorted copy of the cloud (32 x 12,
+    16 x 24 and 8 x 24 warps x points per lane; 1-4 CTAs per cloud; pruning off): the same indices as the oracle, bit for
+    bit -- ties between duplicated points are resolved by ORIGINAL index although storage order is bucket order."""
+    from pointnet12_b200 import ops
+
+    pts = syn.kitti_batch(B, N, config=8)
+    st = starts([N], B, seed=N)[0]
+    want = orc.farthest_point_sample(pts.transpose(0, 2, 1)[:, :, :3], npoint, st.numpy())
+    x0 = views(cuda(pts, dev))[0]
+    grid = ops.ball_grid(x0, 0.1)
+    got = ops.fps_sorted(x0, grid, npoint, st.to(dev), config=config)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
 # ------------------------------------------------------------------------------------------------ N <= sa1.npoint
 @pytest.mark.parametrize("N", [1024, 512])
 @pytest.mark.parametrize("mode", ["bf16x3", "fp32"])

@@ -33,9 +33,10 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
 
 def run(depth, env, steps):
-    for k in ("PN12_FPS1", "PN12_STREAM_BALL", "PN12_STREAM_BALL_CTAS", "PN12_STREAM_BALL_SHARE"):
+    for k in ("PN12_FPS1", "PN12_STREAM_BALL", "PN12_STREAM_BALL_CTAS", "PN12_STREAM_BALL_SHARE", "PN12_WHATIF"):
         os.environ.pop(k, None)
     os.environ.update(env)
+    net.module.__dict__.pop("_whatif_cache", None)
     runner = GraphedSemSeg(net, depth=depth)
     torch.manual_seed(7)
     outs = runner.run_pipelined(xs)                       # builds the graphs; results for the equality check
