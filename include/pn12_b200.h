@@ -223,6 +223,10 @@ int pn_three_interpolate_f32(const float* points1, int64_t p1B, int64_t p1N, int
 /* F.log_softmax over the channels of each row (pointnet2.py:174; pointnet.py:251). */
 int pn_log_softmax_f32(const float* x, int64_t ldx, int64_t rows, int C, float* y, int64_t ldy,
                        pn_stream_t stream);
+/* pred.argmax(-1) of the reference's evaluation loop (pcdseg.py:75) over rows of C <= 256 scores: one uint8 label per row,
+ * the first maximum wins (torch.argmax).  What an evaluation loop needs of the [B, N, classes] log-probabilities: moving the
+ * labels to the host instead costs 1 byte per point instead of 4 * classes. */
+int pn_argmax_labels_u8(const float* x, int64_t ldx, int64_t rows, int C, uint8_t* labels, pn_stream_t stream);
 
 /* ---- fused shared-MLP chains on the tensor cores (tcgen05 + TMEM), fp32 parity by 3-pass split bf16 ----
  * A chain is up to PN_MLP_MAX_LAYERS layers  y = act(x * w^T + bias)  with BatchNorm already folded into

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "pn_three_interpolate_f32": [vp, i64, i64, i64, i32, vp, i64, i64, i64, i32, i32, vp, vp, i32, i32, vp, i64, i64,
                                  vp],
     "pn_log_softmax_f32": [vp, i64, i64, i32, vp, i64, vp],
+    "pn_argmax_labels_u8": [vp, i64, i64, i32, vp, vp],
     "pn_mlp_pack_bf16x3": [_descp, C.POINTER(vp), C.POINTER(vp), vp, vp],
     "pn_mlp_pack_t_bf16x3": [_descp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), vp, vp],
     "pn_mlp_rows_bf16x3": [_descp, vp, vp, i64, i64, i32, vp, i64, _optsp, vp],

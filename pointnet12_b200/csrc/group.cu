@@ -206,6 +206,25 @@ log_softmax_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C
     }
 }
 
+// pred.argmax(-1) of the evaluation loop (pcdseg.py:75): the label of every point as one byte; the first maximum wins, as
+// torch.argmax does.  One thread per row (rows of <= 64 classes are a handful of 16-byte loads).
+__global__ void __launch_bounds__(256)
+argmax_labels_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, unsigned char* __restrict__ y) {
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+        const float* __restrict__ r = x + row * ldx;
+        float m = r[0];
+        int best = 0;
+        for (int c = 1; c < C; ++c) {
+            const float v = r[c];
+            if (v > m) {
+                m = v;
+                best = c;
+            }
+        }
+        y[row] = (unsigned char)best;
+    }
+}
+
 static inline unsigned grid_for(int64_t total, int threads, int per_sm = 8) {
     const int64_t want = ceil_div(total, threads);
     const int64_t cap = 148LL * per_sm;
@@ -293,4 +312,12 @@ PN_EXPORT int pn_log_softmax_f32(const float* x, int64_t ldx, int64_t rows, int 
     PN_REQUIRE(rows > 0 && C > 0 && ldx >= C && ldy >= C, PN_ERR_BAD_ARG, "pn_log_softmax_f32: bad sizes");
     log_softmax_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, y, ldy);
     return finish_launch("pn_log_softmax_f32");
+}
+
+PN_EXPORT int pn_argmax_labels_u8(const float* x, int64_t ldx, int64_t rows, int C, uint8_t* labels, pn_stream_t stream) {
+    using namespace pn;
+    PN_REQUIRE(x && labels, PN_ERR_BAD_ARG, "pn_argmax_labels_u8: null pointer");
+    PN_REQUIRE(rows > 0 && C > 0 && C <= 256 && ldx >= C, PN_ERR_BAD_ARG, "pn_argmax_labels_u8: bad sizes (1 <= C <= 256)");
+    argmax_labels_kernel<<<grid_for(rows, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, C, labels);
+    return finish_launch("pn_argmax_labels_u8");
 }

@@ -21,6 +21,48 @@ def env_world() -> Tuple[int, int, int]:
             int(os.environ.get("LOCAL_RANK", "0")))
 
 
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(index: int) -> int:
+    """NUMA node of a GPU's PCIe slot from sysfs, or -1 (one node, a virtualised topology, no sysfs)."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            return int(f.read().strip())
+    except Exception:   # noqa: BLE001
+        return -1
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin the calling process to the CPUs of its GPU's NUMA node, BEFORE it allocates pinned host buffers: the staging
+    memory of the end-to-end path (3 MB in, 14.6 MB out per batch and GPU) then sits next to the PCIe root the copies cross
+    instead of on whichever node the launcher started the process on (round 1: eight ranks on node 0, 73 % of linear end
+    to end at 8 GPUs).  Returns what was done, for the benchmark record; a no-op where the topology does not say."""
+    info = {"gpu": local_rank, "numa_node": gpu_numa_node(local_rank), "cpus": None, "bound": False}
+    node = info["numa_node"]
+    if node < 0 or not hasattr(os, "sched_setaffinity"):
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"], info["bound"] = len(allowed), True
+    except Exception:   # noqa: BLE001
+        pass
+    return info
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [lo, hi) slice of n_items for this rank; the first n_items % world ranks get one extra."""
     if not 0 <= rank < world:

@@ -532,6 +532,19 @@ def log_softmax(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def argmax_labels(logp: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logp [..., C] -> uint8 labels [...] = logp.argmax(-1) (pcdseg.py:75), the first maximum winning (pn_argmax_labels_u8)."""
+    Cc = logp.shape[-1]
+    x, rows, _, ldx = _rows(logp.reshape(-1, Cc), "logp")
+    if out is None:
+        out = torch.empty(logp.shape[:-1], dtype=torch.uint8, device=x.device)
+    elif out.dtype != torch.uint8 or out.numel() != rows or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError("out must be a contiguous uint8 CUDA tensor with one element per row")
+    with _on_device(x):
+        nv.call("pn_argmax_labels_u8", x.data_ptr(), ldx, rows, Cc, out.data_ptr(), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # Fused shared-MLP chains on the tensor cores (tcgen05 + TMEM): pn_*_bf16x3 entry points.
 # "bf16x3" computes every product as a_hi*w_hi + a_hi*w_lo + a_lo*w_hi with fp32 accumulation: fp32 parity

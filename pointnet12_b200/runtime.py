@@ -94,7 +94,9 @@ class GraphedSemSeg:
         }
         st["x"].copy_(points)
         classes = net.conv2.out_channels
-        st["host_out"] = torch.empty((B, N, classes), dtype=torch.float32).pin_memory() if to_host else None
+        labels = to_host == "labels"
+        st["host_out"] = torch.empty((B, N, classes), dtype=torch.float32).pin_memory() if (to_host and not labels) else None
+        st["host_labels"] = torch.empty((B, N), dtype=torch.uint8).pin_memory() if labels else None
         stream = st["stream"]
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream), torch.no_grad():
@@ -107,23 +109,30 @@ class GraphedSemSeg:
         with ops.options(**self._capture_options(st)):
             with torch.cuda.graph(graph, stream=stream), torch.no_grad():
                 st["out"] = net(st["x"], fps_starts=list(st["starts"].unbind(0)), host_out=st["host_out"])
+                if labels:      # what the reference's evaluation loop keeps of the output: pred.argmax(-1) (pcdseg.py:75)
+                    st["labels"] = ops.argmax_labels(st["out"])
+                    st["host_labels"].copy_(st["labels"], non_blocking=True)
         st["graph"] = graph
         return st
 
-    def _sets(self, points: torch.Tensor, dev, to_host: bool) -> dict:
+    def _sets(self, points: torch.Tensor, dev, to_host) -> dict:
         self._check_weights(dev)
-        key = (tuple(points.shape), dev, bool(to_host))
+        mode = "labels" if to_host == "labels" else bool(to_host)
+        key = (tuple(points.shape), dev, mode)
         entry = self._graphs.get(key)
         if entry is None:
             on_dev = points.to(dev)
-            entry = self._graphs[key] = {"sets": [self._build_set(on_dev, bool(to_host)) for _ in range(self.depth)], "n": 0}
+            entry = self._graphs[key] = {"sets": [self._build_set(on_dev, mode) for _ in range(self.depth)], "n": 0}
             self._sig = self._signature()         # (the warm-up folded the weights; versions are unchanged, pointers too)
         return entry
 
     @torch.no_grad()
-    def submit(self, points: torch.Tensor, to_host: bool = False) -> Ticket:
+    def submit(self, points: torch.Tensor, to_host=False) -> Ticket:
         """Starts the forward of one batch on the next buffer set and returns at once.  `points`: device tensor (ordered
-        after the work already queued on the current stream) or pinned host tensor (copied by the set's own stream)."""
+        after the work already queued on the current stream) or pinned host tensor (copied by the set's own stream).
+        to_host: False (device log-probabilities), True (log-probabilities [B, N, classes] into the set's pinned host buffer)
+        or "labels" (only pred.argmax(-1) as uint8 [B, N] travels to the host: what the reference's evaluation loop uses,
+        pcdseg.py:75 -- 1 byte per point instead of 76)."""
         dev = points.device if points.is_cuda else torch.device("cuda", torch.cuda.current_device())
         entry = self._sets(points, dev, to_host)
         seq = entry["n"]
@@ -154,7 +163,7 @@ class GraphedSemSeg:
             st["graph"].replay()
             done = torch.cuda.Event(enable_timing=self.timing)
             done.record()
-        return Ticket(st, seq, done, bool(to_host))
+        return Ticket(st, seq, done, "labels" if to_host == "labels" else bool(to_host))
 
     def result(self, ticket: Ticket) -> torch.Tensor:
         """The log-probabilities [B, N, classes] of a submitted batch.  Device output: the set's static buffer, ordered before
@@ -164,7 +173,7 @@ class GraphedSemSeg:
             raise RuntimeError(f"the result of batch {ticket.seq} was overwritten: at most depth={self.depth} batches are in flight")
         if ticket.to_host:
             ticket.done.synchronize()
-            return ticket.set["host_out"]
+            return ticket.set["host_labels"] if ticket.to_host == "labels" else ticket.set["host_out"]
         torch.cuda.current_stream(ticket.set["out"].device).wait_event(ticket.done)
         return ticket.set["out"]
 
@@ -182,7 +191,7 @@ class GraphedSemSeg:
             return out
         return res
 
-    def run_pipelined(self, batches, to_host: bool = False, consume=None) -> Optional[List[torch.Tensor]]:
+    def run_pipelined(self, batches, to_host=False, consume=None) -> Optional[List[torch.Tensor]]:
         """The reference's evaluation loop (pcdseg.py:58-97) with `depth` batches in flight: submits batch k + depth - 1
         before it hands batch k's result to `consume(k, logp)` (default: collect clones)."""
         pending, results = [], []

@@ -298,3 +298,24 @@ def test_cross_entropy_poisons_out_of_range_labels(dev):
     t[7] = 19
     loss, dx = ops.cross_entropy(x, t)
     assert bool(torch.isnan(loss)) and bool(torch.isnan(dx[7]).all()) and bool(torch.isfinite(dx[8]).all())
+
+
+def test_labels_output_mode(dev, ckpt_path):
+    """to_host="labels": only pred.argmax(-1) (pcdseg.py:75) travels to the host, as uint8; equal to the arg-max of the
+    log-probabilities (first maximum wins, like torch.argmax), sequential and with batches in flight."""
+    from pointnet12_b200 import ops
+    from pointnet12_b200.model.utils import load_pointnet
+    from pointnet12_b200.runtime import GraphedSemSeg
+
+    x = torch.randn(1000, 19, device=dev)
+    x[5, 3] = x[5, 7] = 9.0                                   # a tie: the first maximum wins
+    assert torch.equal(ops.argmax_labels(x).long(), x.argmax(-1)) and int(ops.argmax_labels(x)[5]) == 3
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    xs = [cuda(syn.kitti_batch(4, 8000, config=2, first=4 * i), dev) for i in range(4)]
+    for depth in (1, 3):
+        runner = GraphedSemSeg(net, depth=depth)
+        torch.manual_seed(9)
+        want = [r.argmax(-1).to(torch.uint8).cpu() for r in runner.run_pipelined(xs)]
+        torch.manual_seed(9)
+        got = runner.run_pipelined([x.cpu().pin_memory() for x in xs], to_host="labels")
+        assert all(g.dtype == torch.uint8 and not g.is_cuda and torch.equal(g, w) for g, w in zip(got, want))
