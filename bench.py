@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (our arm only)")
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("PN12_DEPTH", "4")), help="batches in flight (GraphedSemSeg depth)")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("PN12_DEPTH", "6")), help="batches in flight (GraphedSemSeg depth)")
     ap.add_argument("--ref-clouds", type=int, default=0, help="reference arm: clouds per step (0 = the full batch of 8, reduced "
                                                               "automatically if the run would exceed a few minutes)")
     ap.add_argument("--no-train", action="store_true", help="skip the config-C5 `train` / `dp_check` sub-records")

@@ -377,7 +377,7 @@ class PointNet2SemSeg(_Net):
                 copier = self._copy_stream(points.device)
                 # batch slices: the device-to-host copy (the slower side: 14.6 MB at ~55 GB/s vs 134 us of compute at C2)
                 # should start as early as possible, so the slices are small -- one or two clouds
-                nslice = min(B, ops.HOST_OUT_SLICES)
+                nslice = min(B, ops.host_out_slices())
                 cuts = [round(i * B / nslice) for i in range(nslice + 1)]
                 for b0, b1 in zip(cuts[:-1], cuts[1:]):
                     if b0 == b1:

@@ -91,6 +91,7 @@ _DEFAULTS = {
     "tile_counters": None,      # TileCounters: resident chains draw their tiles dynamically (see TileCounters)
     "fps1_config": None,        # launch shape of the LEVEL-1 sampling of PointNet2SemSeg (None = automatic); PN12_FPS1 overrides
     "stream_ball": True,        # level-1 ball query answered beside the sampling (False: after it); PN12_STREAM_BALL overrides
+    "host_out_slices": None,    # batch slices of the last level when the output goes to the host (None: HOST_OUT_SLICES)
     "fps1_sorted": None,        # level-1 sampling through the bucket-pruned kernel (fps_sorted) with this config; PN12_FPS1_SORTED overrides
 }
 
@@ -239,6 +240,11 @@ STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for t
 def fps1_config() -> Optional[Tuple[int, int, int]]:
     v = os.environ.get("PN12_FPS1", "")
     return tuple(int(t) for t in v.split(",")) if v else _opt("fps1_config")
+
+
+def host_out_slices() -> int:
+    v = _opt("host_out_slices")
+    return HOST_OUT_SLICES if v is None else int(v)
 
 
 def fps1_sorted() -> Optional[Tuple[int, int, int]]:

@@ -24,6 +24,7 @@ and reach the graph's static buffer through a small ring of pinned staging buffe
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -75,7 +76,10 @@ class GraphedSemSeg:
         other batches' chains can use (measured at C2, B200: profiles/r02_pipeline_sweep.md)."""
         if self.depth == 1:
             return {"tile_counters": None}
-        return {"tile_counters": st["counters"], "fps1_config": self.FPS1_PIPELINED, "stream_ball": False}
+        # (the last level is NOT cut into batch slices for the host output: the copy of batch k overlaps batch k+1 anyway, and
+        # eight one-cloud launches of fp1 + head quantise badly: 188 tiles on 148 SMs each)
+        return {"tile_counters": st["counters"], "fps1_config": self.FPS1_PIPELINED, "stream_ball": False,
+                "host_out_slices": int(os.environ.get("PN12_PIPE_HOST_SLICES", "1"))}
 
     def _build_set(self, points: torch.Tensor, to_host: bool) -> dict:
         net, dev = self.net, points.device
