@@ -1,6 +1,6 @@
 """bench.py -- PointNet++ SSG semantic-segmentation forward, points/sec (BASELINE.json metric, config C2).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--depth D]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -9,15 +9,18 @@ batch of 8 synthetic KITTI-shaped clouds of 24 000 points (xyz + reflectance) pe
 independent, so ranks shard the work with no data-path collective (weak scaling: 8 clouds per GPU).
 
 Our arm prints one JSON line with
-  value         whole-job points/sec, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e           the same through the public nn.Module call with pinned HOST input and HOST output
-                (H2D of the batch and D2H of the [B,N,19] log-probs inside the timed region)
-  roofline      the dominant kernel (level-1 farthest-point sampling, pn_fps_f32 at N=24000): algorithmic
-                bytes B*npoint*N*16 per launch / mean launch duration measured with CUDA events inside the
-                timed steps, against the measured HBM copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (a C/OpenMP port of the reference algorithm, oracle/) on the same batch
-`--impl reference` times that CPU oracle port as the reference arm (the reference itself is pure Python and
-cannot travel to the GPU box; the port is ~10x faster than the reference's own PyTorch-CPU path).
+  value          whole-job points/sec, inputs resident in HBM, `depth` batches in flight (runtime.GraphedSemSeg), the K steps
+                 timed as one region with CUDA events, max over ranks; inputs rotate over 48 different batches (> L2)
+  sequential     the same one batch at a time with per-step events and an L2 flush between steps (round-1 protocol)
+  e2e            the same loop from pinned HOST batches to pinned HOST [B,N,19] log-probabilities (H2D and D2H in the region)
+  e2e_labels     ... moving only pred.argmax(-1) (uint8) to the host: what the reference's evaluation loop consumes
+  roofline       the dominant kernel (level-1 farthest-point sampling at N=24000): algorithmic bytes B*npoint*N*16 per
+                 launch / launch duration (CUDA events, stand-alone, cold L2) against the measured HBM copy bandwidth
+  roofline_all   every kernel group of the forward timed alone, against its roofline (tools/kernel_rooflines.py)
+  cpu_baseline   the UNMODIFIED reference (baseline/_ref: model/utils.py load_pointnet + eval forward) on the host CPUs,
+                 CUDA hidden, in a child process; cpu_baseline_port = the C/OpenMP oracle port (oracle/)
+  train, dp_check  config C5 (training iteration with the NCCL gradient all-reduce) and the data-parallel equivalence check
+`--impl reference` runs that unmodified reference as the reference arm (rank 0 only under torchrun), same metric and `config`.
 """
 from __future__ import annotations
 
