@@ -484,9 +484,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": BATCH * 4 * NPOINTS * 4 + 4 * BATCH * 8,
                     "d2h_bytes_per_step": BATCH * NPOINTS * CLASSES * 4,
                     "host_link_gbs_all_gpus": world * (BATCH * 4 * NPOINTS * 4 + BATCH * NPOINTS * CLASSES * 4) / (ms_e2e / args.steps * 1e-3) / 1e9,
-                    "note": "the [B, N, 19] fp32 log-probabilities are 14.6 MB per batch and GPU; on this pool's virtualised hosts the "
-                            "PCIe path sustains ~23 GB/s for one GPU and ~85-100 GB/s for all eight together, which bounds this figure "
-                            "at N = 8 whatever the GPUs do (see e2e_labels for the evaluation loop's real consumer)"},
+                    "note": "the [B, N, 19] fp32 log-probabilities are 14.6 MB per batch and GPU; a plain pinned copy of that size runs at "
+                            "~54 GB/s on one GPU of this pool's (virtualised) hosts, but all eight GPUs together saturate the host link at "
+                            "~100 GB/s, which bounds this figure at N = 8 whatever the GPUs do (see e2e_labels for the evaluation loop's "
+                            "real consumer); with K = 20 steps the fill and drain of the 6-deep pipeline are inside the timed region"},
             "e2e_labels": None if not ms_lab else {
                 "value": points / (ms_lab * 1e-3), "unit": "points/s", "ms_per_step": ms_lab / args.steps,
                 "h2d_bytes_per_step": BATCH * 4 * NPOINTS * 4 + 4 * BATCH * 8, "d2h_bytes_per_step": BATCH * NPOINTS,

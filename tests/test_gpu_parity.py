@@ -421,7 +421,7 @@ def test_cpu_tensor_raises(dev):
 def test_bad_arguments_report_errors(dev):
     from pointnet12_b200 import _native as nv
 
-    rc = nv.lib().pn_fps_f32(None, 0, 0, 0, 1, 16, 4, None, None, None)
+    rc = nv.lib().pn_fps_f32(None, 0, 0, 0, 1, 16, 4, None, None, None, None)
     assert rc == -1 and b"null pointer" in nv.lib().pn_last_error_string()
     x = torch.zeros(1, 200000, 3, device=dev)
     with pytest.raises(RuntimeError, match="pn_fps_f32"):
