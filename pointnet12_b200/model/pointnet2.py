@@ -325,7 +325,7 @@ class PointNet2SemSeg(_Net):
                         skipped[i].record(ahead)
 
             # sa1 / sa2 run one persistent CTA per SM while level 2-4 sampling holds a few SMs: leave those out
-            ops.set_reserved_sms(ops.fps_launch_info(B, S1, sa[1].npoint)[0])
+            ops.set_reserved_sms(ops.fps_launch_info(B, S1, sa[1].npoint)[0] if ops.reserve_level2_sms() else 0)
             try:
                 fs = [f0, self._whatif("sa1", lambda: sa[0].features(x0, f0, x1, balls[0]))]
                 main.wait_event(ready[1])
@@ -350,7 +350,7 @@ class PointNet2SemSeg(_Net):
                         nn_big.wait_event(wide_done)
                         if grid1 is not None:
                             nn_big.wait_event(grid_ready)
-                        nns[0] = self._whatif("nn1", lambda: fp[0].geometry(x0, x1, order=grid1, background=True))
+                        nns[0] = self._whatif("nn1", lambda: fp[0].geometry(x0, x1, order=grid1, background=ops.nn1_background()))
                         done_big = torch.cuda.Event()
                         done_big.record(nn_big)
             main.wait_event(done_small)

@@ -91,6 +91,8 @@ _DEFAULTS = {
     "tile_counters": None,      # TileCounters: resident chains draw their tiles dynamically (see TileCounters)
     "fps1_config": None,        # launch shape of the LEVEL-1 sampling of PointNet2SemSeg (None = automatic); PN12_FPS1 overrides
     "stream_ball": True,        # level-1 ball query answered beside the sampling (False: after it); PN12_STREAM_BALL overrides
+    "nn1_background": True,     # fp1's 3-NN search on a capped grid (see nn1_background)
+    "reserve_level2": True,     # sa1 / sa2 leave the level-2 sampling's SMs out of their grids
     "host_out_slices": None,    # batch slices of the last level when the output goes to the host (None: HOST_OUT_SLICES)
     "fps1_sorted": None,        # level-1 sampling through the bucket-pruned kernel (fps_sorted) with this config; PN12_FPS1_SORTED overrides
 }
@@ -240,6 +242,19 @@ STREAM_BALL_MIN_FREE_SMS = 32    # SMs the sampling launch must leave idle for t
 def fps1_config() -> Optional[Tuple[int, int, int]]:
     v = os.environ.get("PN12_FPS1", "")
     return tuple(int(t) for t in v.split(",")) if v else _opt("fps1_config")
+
+
+def nn1_background() -> bool:
+    """fp1's 3-NN block search on a capped grid (~3 small CTAs per SM) so that the chains of the critical path find room beside
+    it (one batch at a time), or on its full grid (option / PN12_NN1_BACKGROUND=0)."""
+    v = os.environ.get("PN12_NN1_BACKGROUND", "")
+    return (v != "0") if v else bool(_opt("nn1_background"))
+
+
+def reserve_level2_sms() -> bool:
+    """sa1 / sa2 leave the SMs of the concurrent level-2 sampling out of their persistent grids (PN12_RESERVE_L2=0: do not)."""
+    v = os.environ.get("PN12_RESERVE_L2", "")
+    return (v != "0") if v else bool(_opt("reserve_level2"))
 
 
 def host_out_slices() -> int:
