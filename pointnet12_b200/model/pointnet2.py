@@ -54,6 +54,13 @@ class _Net(nn.Module):
 
     # -- heads (eval: dropout is the identity) ---------------------------------------------------
     def _cls_head(self, global_feat: torch.Tensor) -> torch.Tensor:
+        # three single-layer tensor-core chains (a [B, 1024] matrix is one row tile: each launch is sliced over the output
+        # channels, so the 1024 x 512 weights are read by 16 CTAs instead of one SIMT tile marching through them: 200 -> 45 us at B=32)
+        per_layer = self._head.layer_chains([self.fc1, self.fc2, self.fc3], [self.bn1, self.bn2, None], [True, True, False])
+        if per_layer is not None:
+            x = ops.mlp_rows_tc(per_layer[0], global_feat)
+            x = ops.mlp_rows_tc(per_layer[1], x)
+            return ops.mlp_rows_tc(per_layer[2], x, ops.OUT_LOG_SOFTMAX)
         (w1, b1), (w2, b2), (w3, b3) = self._head.get([self.fc1, self.fc2, self.fc3], [self.bn1, self.bn2, None])
         x = ops.linear(global_feat, w1, b1, relu=True)
         x = ops.linear(x, w2, b2, relu=True)
@@ -68,10 +75,24 @@ class _Net(nn.Module):
         logp = ops.log_softmax(ops.linear(feat, w2, b2, relu=False))
         return logp.view(B, N, -1), feat.view(B, N, -1).permute(0, 2, 1)
 
-    def _encode(self, names, xyz, points):
+    ENCODER = ("sa1", "sa2", "sa3")     # the set-abstraction levels `_encode` runs (PointNet2SemSeg has its own forward)
+
+    def fps_level_sizes(self, n_points: int):
+        """Cloud sizes the sampling levels of this net draw their FPS start index from, in call order (pointnet_util.py:75):
+        what a CUDA-graph runner must draw on the host for every batch (runtime.GraphedModule)."""
+        sizes, n = [], int(n_points)
+        for name in self.ENCODER:
+            lvl = getattr(self, name)
+            if not getattr(lvl, "group_all", False):
+                sizes.append(n)
+                n = lvl.npoint
+        return sizes
+
+    def _encode(self, names, xyz, points, fps_starts=None):
         """Run set-abstraction levels in order; returns the per-level (xyz, features) lists.
         The FPS start indices of all sampling levels are drawn up front (same generator, same order as the
-        reference's per-level draws) so that they reach the device in one asynchronous copy."""
+        reference's per-level draws) so that they reach the device in one asynchronous copy; `fps_starts` (extension):
+        the caller has drawn them already ([B] int64 device tensors, one per sampling level)."""
         ops._need_cuda(xyz, "xyz")
         levels = [getattr(self, name) for name in names]
         sizes, n = [], xyz.shape[2]
@@ -79,7 +100,7 @@ class _Net(nn.Module):
             if not getattr(lvl, "group_all", False):
                 sizes.append(n)
                 n = lvl.npoint
-        starts = iter(draw_fps_starts(xyz.shape[0], sizes, xyz.device))
+        starts = iter(fps_starts if fps_starts is not None else draw_fps_starts(xyz.shape[0], sizes, xyz.device))
         xs, fs = [xyz], [points]
         for lvl in levels:
             if getattr(lvl, "group_all", False):
@@ -102,8 +123,8 @@ class PointNet2ClsMsg(_Net):
             sa3=_all(640 + 3, [256, 512, 1024]))
         self._cls_fc(0.4, 40)
 
-    def forward(self, xyz, dropout_masks=None):
-        _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+    def forward(self, xyz, dropout_masks=None, fps_starts=None):
+        _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None, fps_starts)
         if self.training:          # batch-statistics BatchNorm, dropout, autograd (pointnet12_b200/train.py)
             from ..train import cls_head_train
 
@@ -121,8 +142,8 @@ class PointNet2ClsSsg(_Net):
                      sa3=_all(256 + 3, [256, 512, 1024]))
         self._cls_fc(0.4, 40)
 
-    def forward(self, xyz, dropout_masks=None):
-        _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+    def forward(self, xyz, dropout_masks=None, fps_starts=None):
+        _, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None, fps_starts)
         if self.training:
             from ..train import cls_head_train
 
@@ -141,8 +162,8 @@ class PointNet2PartSegSsg(_Net):
                      fp3=_fp(1280, [256, 256]), fp2=_fp(384, [256, 128]), fp1=_fp(128, [128, 128, 128]))
         self._seg_convs(num_classes)
 
-    def forward(self, xyz, dropout_mask=None):
-        xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None)
+    def forward(self, xyz, dropout_mask=None, fps_starts=None):
+        xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, None, fps_starts)
         f2 = self.fp3(xs[2], xs[3], fs[2], fs[3])
         f1 = self.fp2(xs[1], xs[2], fs[1], f2)
         if self.training:
@@ -164,9 +185,9 @@ class PointNet2PartSegMsg_one_hot(_Net):
             fp3=_fp(1536, [256, 256]), fp2=_fp(576, [256, 128]), fp1=_fp(150, [128, 128]))
         self._seg_convs(num_classes)
 
-    def forward(self, xyz, norm_plt, cls_label, dropout_mask=None):
+    def forward(self, xyz, norm_plt, cls_label, dropout_mask=None, fps_starts=None):
         B, _, N = xyz.shape
-        xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, norm_plt)
+        xs, fs = self._encode(("sa1", "sa2", "sa3"), xyz, norm_plt, fps_starts)
         f2 = self.fp3(xs[2], xs[3], fs[2], fs[3])
         f1 = self.fp2(xs[1], xs[2], fs[1], f2)
         skip = torch.cat([cls_label.view(B, 16, 1).expand(B, 16, N), xyz, norm_plt], 1)   # host-side glue [B,22,N]

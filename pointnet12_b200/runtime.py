@@ -212,11 +212,15 @@ class GraphedSemSeg:
 
 
 class GraphedModule:
-    """CUDA-graph replay of any eval-mode network of this package whose forward draws nothing on the host -- PointNetSeg /
-    PointNetCls / PointNetDenseCls (model/pointnet.py: no sampling, hence no FPS start draw).  Config C1 (PointNetSeg, one
-    cloud of 24000 points) is ~25 launches of a few microseconds each plus per-call host glue; captured once per input shape
-    it is one graph launch.  Returns the graph's static output tensors (valid until the next call); rebuilt when a parameter
-    or BatchNorm buffer changes, like GraphedSemSeg."""
+    """CUDA-graph replay of any eval-mode network of this package, one batch at a time.  PointNetSeg / PointNetCls /
+    PointNetDenseCls (model/pointnet.py) draw nothing on the host; the PointNet++ classification / part-segmentation nets
+    (model/pointnet2.py) draw one FPS start index per sampling level and cloud: the runner draws them for every call on the CPU
+    generator, in the reference's order (pointnet_util.py:75), and feeds the graph's static buffer (`fps_level_sizes`).
+    Config C1 (PointNetSeg, one cloud of 24000 points) is ~25 launches of a few microseconds each plus per-call host glue, config
+    C4 (PointNet2ClsMsg, 32 clouds of 1024 points) ~70; captured once per input shape each is one graph launch.  Returns the
+    graph's static output tensors (valid until the next call); rebuilt when a parameter or BatchNorm buffer changes."""
+
+    RING = 4
 
     def __init__(self, net, warmup: int = 2):
         self.net = net.module if hasattr(net, "module") else net
@@ -227,6 +231,11 @@ class GraphedModule:
 
     def _signature(self):
         return tuple((t.data_ptr(), t._version) for t in self._tensors)
+
+    def _forward(self, st):
+        if st["starts"] is not None:
+            return self.net(*st["in"], fps_starts=list(st["starts"].unbind(0)))
+        return self.net(*st["in"])
 
     @torch.no_grad()
     def __call__(self, *inputs: torch.Tensor):
@@ -239,23 +248,41 @@ class GraphedModule:
             self._sig = sig
         key = tuple((tuple(t.shape), t.dtype) for t in inputs) + (dev,)
         st = self._graphs.get(key)
+        B = inputs[0].shape[0]
         if st is None:
-            st = {"in": [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in inputs]}
+            st = {"in": [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in inputs], "starts": None, "slot": 0}
+            sizes = self.net.fps_level_sizes(inputs[0].shape[2]) if hasattr(self.net, "fps_level_sizes") else []
+            if sizes:
+                st["sizes"] = sizes
+                st["starts"] = torch.zeros((len(sizes), B), dtype=torch.int64, device=dev)
+                st["pinned"] = [torch.zeros((len(sizes), B), dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+                st["events"] = [None] * self.RING
             for s, t in zip(st["in"], inputs):
                 s.copy_(t)
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(self.warmup):
-                    self.net(*st["in"])
+                    self._forward(st)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                st["out"] = self.net(*st["in"])
+                st["out"] = self._forward(st)
             st["graph"] = graph
             self._graphs[key] = st
             self._sig = self._signature()
+        if st["starts"] is not None:
+            slot = st["slot"] = (st["slot"] + 1) % self.RING
+            if st["events"][slot] is not None:
+                st["events"][slot].synchronize()
+            pinned = st["pinned"][slot]
+            for i, n in enumerate(st["sizes"]):           # the reference's draws, same generator, same order
+                pinned[i] = torch.randint(0, n, (B,), dtype=torch.long)
+            st["starts"].copy_(pinned, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            st["events"][slot] = ev
         for s, t in zip(st["in"], inputs):
             s.copy_(t, non_blocking=True)
         st["graph"].replay()

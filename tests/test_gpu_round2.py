@@ -319,3 +319,25 @@ def test_labels_output_mode(dev, ckpt_path):
         torch.manual_seed(9)
         got = runner.run_pipelined([x.cpu().pin_memory() for x in xs], to_host="labels")
         assert all(g.dtype == torch.uint8 and not g.is_cuda and torch.equal(g, w) for g, w in zip(got, want))
+
+
+def test_graphed_module_cls_msg(dev, golden):
+    """runtime.GraphedModule on a net that samples (PointNet2ClsMsg): the FPS start indices are drawn per call like the
+    reference draws them, so a replay equals the eager forward under the same seed -- for different seeds too."""
+    from pointnet12_b200.model.pointnet2 import PointNet2ClsMsg
+    from pointnet12_b200.runtime import GraphedModule
+
+    net = _seeded(PointNet2ClsMsg(), 1234, dev)
+    x = cuda(syn.modelnet_batch(32, 1024), dev)
+    runner = GraphedModule(net)
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            want_logp, want_l3 = net(x)
+            want_logp, want_l3 = want_logp.clone(), want_l3.clone()
+        torch.manual_seed(seed)
+        logp, l3 = runner(x)
+        assert torch.equal(logp, want_logp) and torch.equal(l3, want_l3)
+    g = golden("cls_msg_b32")
+    torch.manual_seed(0)
+    assert rel_err(runner(x)[0], g["logp"]) < LOGP_TOL

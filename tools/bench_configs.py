@@ -63,6 +63,11 @@ with torch.no_grad():
         ms = median_ms(lambda: net(x))
         print(json.dumps({"config": "C4 PointNet2ClsMsg B=32 N=1024", "precision": mode, "ms": round(ms, 4),
                           "clouds_per_s": round(32 / ms * 1e3), "tflops_useful": round(250.6 / ms, 1)}), flush=True)
+        if mode != "fp32":
+            runner = GraphedModule(net)
+            ms = median_ms(lambda: runner(x))
+            print(json.dumps({"config": "C4 PointNet2ClsMsg B=32 N=1024, one CUDA-graph replay", "precision": mode, "ms": round(ms, 4),
+                              "clouds_per_s": round(32 / ms * 1e3), "tflops_useful": round(250.6 / ms, 1)}), flush=True)
 ops.set_mlp_mode("bf16x3")
 
 # host link: pinned device-to-host / host-to-device copies of one C2 output / input
