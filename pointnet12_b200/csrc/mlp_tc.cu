@@ -382,6 +382,17 @@ __device__ __forceinline__ void row_load32(const TcIo& io, const RowCtx<IN>& c, 
         }
     }
     if constexpr (IN == TC_IN_SA) {
+        if (io.msg_order && k0 == io.D) {   // the chunk that starts at the recentred coordinates: [dx, dy, dz, padding], no branches
+            const float px = c.valid ? c.xyz_j[0] : 0.0f, py = c.valid ? c.xyz_j[io.xC] : 0.0f, pz = c.valid ? c.xyz_j[2 * io.xC] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            if (c.valid) {
+                v[0] = __fsub_rn(px, c.cx);
+                v[1] = __fsub_rn(py, c.cy);
+                v[2] = __fsub_rn(pz, c.cz);
+            }
+            return;
+        }
         const int f0 = io.msg_order ? k0 : k0 - 3;   // first feature channel covered if the block is all features
         const bool all_feat = io.msg_order ? (k0 + 32 <= io.D) : (k0 >= 3 && k0 + 32 <= k_real);
         if (c.valid && all_feat && io.fC == 1 && ((reinterpret_cast<uintptr_t>(c.feat_j + f0) & 15) == 0)) {
@@ -395,6 +406,38 @@ __device__ __forceinline__ void row_load32(const TcIo& io, const RowCtx<IN>& c, 
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = row_value<IN>(io, c, k0 + j, k_real);
+}
+
+// Fast path of the set-abstraction producer for levels whose whole input row fits one 32-channel chunk with at most four
+// feature channels (sa1 of every net: xyz alone or xyz + reflectance / normals).  The generic path (row_setup + row_value per
+// channel) branches per element, and every branch ends a basic block: index -> centroid -> coordinates -> features became a
+// chain of dependent round trips (the producer was half of sa1's tile time).  Here the index is the only dependency: the
+// point's coordinates, its features and the centroid are loaded unconditionally (a row beyond the end is clamped to row 0
+// and zeroed afterwards) right after it, in one round trip.  Channel order: [features (D), xyz - centroid (3)], i.e.
+// msg_order = 1, which is how every SA chain is packed (FoldedLayers.chain(xyz_last=True)).
+__device__ __forceinline__ void sa_small_row(const TcIo& io, bool valid, int64_t row, float (&v)[32]) {
+    const int64_t r = valid ? row : 0;
+    const int64_t bs = r / io.K;
+    const int64_t b = bs / io.S, s = bs % io.S;
+    int64_t j = io.idx[r];
+    j = j < 0 ? 0 : (j >= io.N ? io.N - 1 : j);
+    const float* pj = io.xyz + b * io.xB + j * io.xN;
+    const float* q = io.qxyz + b * io.qB + s * io.qN;
+    const float* fj = io.feat ? io.feat + b * io.fB + j * io.fN : pj;
+    const int64_t fc = io.feat ? io.fC : 0;
+    const float f0 = fj[0], f1 = fj[io.D > 1 ? fc : 0], f2 = fj[io.D > 2 ? 2 * fc : 0], f3 = fj[io.D > 3 ? 3 * fc : 0];
+    const float dx = __fsub_rn(pj[0], q[0]), dy = __fsub_rn(pj[io.xC], q[io.qC]), dz = __fsub_rn(pj[2 * io.xC], q[2 * io.qC]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+    if (valid) {
+        switch (io.D) {     // warp-uniform; no loads inside
+            case 0: v[0] = dx; v[1] = dy; v[2] = dz; break;
+            case 1: v[0] = f0; v[1] = dx; v[2] = dy; v[3] = dz; break;
+            case 2: v[0] = f0; v[1] = f1; v[2] = dx; v[3] = dy; v[4] = dz; break;
+            case 3: v[0] = f0; v[1] = f1; v[2] = f2; v[3] = dx; v[4] = dy; v[5] = dz; break;
+            default: v[0] = f0; v[1] = f1; v[2] = f2; v[3] = f3; v[4] = dx; v[5] = dy; v[6] = dz; break;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ quad producer
@@ -1028,7 +1071,9 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
         long long* drow = io.dbg + (g * 64 + round % 64) * 32;
         int dcol = 0;
         if (rec) drow[dcol++] = clock64();
-        row_setup<IN>(io, rc);
+        bool sa_small = false;
+        if constexpr (IN == TC_IN_SA) sa_small = ch.L[0].k_pad == 32 && io.D <= 4 && io.msg_order != 0 && !(ch.probe & 16);
+        if (!sa_small) row_setup<IN>(io, rc);
 
         for (int l = 0; l < ch.nlayers; ++l) {
             const TcLayer& L = ch.L[l];
@@ -1043,6 +1088,12 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 } else if (quad) {
                     fp_quad_producer(io, seg, (tile % tiles_per_seg) * 128 + wl * 32, lane, 0, L.k_pad, L.k_real, half, HALVES,
                                      t_ahi, t_alo);
+                } else if (sa_small) {
+                    if (half == 0) {
+                        float v[32];
+                        sa_small_row(io, rc.valid, rc.row, v);
+                        tc_store_split32(t_ahi, t_alo, v);
+                    }
                 } else {
                     for (int k0 = half * 32; k0 < L.k_pad; k0 += CSTEP) {   // this thread's row
                         float v[32];
@@ -1066,7 +1117,10 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 // queue, both layers complete together and the groups stay in lock-step: MMA phases with idle CUDA cores, then
                 // epilogue phases with an idle tensor pipe.  With it the first group's accumulator is ready after one layer's
                 // worth of MMAs and its epilogue runs under the second group's: the groups settle half a phase apart.
-                if (ch.probe != 8) {
+                // (Two groups only: with four groups of small layers -- sa1 -- the MMAs are too short to be worth serialising and
+                // three spinning lanes cost more than they save: 44.0 vs 41.9 us.)
+                const bool use_lock = GROUPS == 2 && ch.probe != 8;
+                if (use_lock) {
                     if (lane == 0) while (atomicCAS(mma_lock, 0u, 1u) != 0u) {}
                     __syncwarp();
                 }
@@ -1108,7 +1162,7 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                 }
                 if (issuer) tc_commit(bar_done);
                 __syncwarp();
-                if (ch.probe != 8 && lane == 0) atomicExch(mma_lock, 0u);
+                if (use_lock && lane == 0) atomicExch(mma_lock, 0u);
                 if (rec) drow[dcol++] = clock64();
             }
             tc_mbar_wait(bar_done, done_phase);
@@ -1284,7 +1338,7 @@ static int tc_opts_from(const pn_launch_opts* o, TcOpts* t, const char* what) {
     t->quad = (engine & 4) ? 0 : 1;
     t->nslice = (engine & 8) ? 0 : 1;
     t->wide = (engine & 16) ? 0 : 1;
-    t->probe = (engine >> 5) & 7;
+    t->probe = ((engine >> 5) & 7) | ((engine & 256) ? 16 : 0);   // +256 also selects the generic SA producer
     t->engine_bits = engine;
     t->reserved = o->reserved_sms;
     t->dbg = static_cast<long long*>(o->mlp_debug);

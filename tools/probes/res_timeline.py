@@ -12,6 +12,8 @@ from pointnet12_b200 import ops, synthetic as syn  # noqa: E402
 from pointnet12_b200.model.utils import load_pointnet  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "sa1"
+if len(sys.argv) > 2:
+    ops._DEFAULTS["mlp_engine"] = int(sys.argv[2])       # e.g. 512 = no MMA issue lock, 256 = generic producers
 dev = torch.device("cuda", 0)
 net = load_pointnet("pointnet2", 19, os.path.join(ROOT, "tests", "golden", "pointnet2-inview-0.55884-0001.pth"), device=dev)
 n = net.module
@@ -46,7 +48,7 @@ with torch.no_grad():
         torch.cuda.synchronize()
 print(f"{which}: {a.elapsed_time(b) * 1e3:.1f} us")
 t = dbg.cpu().numpy().reshape(4, 64, 32)
-names = ["start", "prod", "bar"] + sum([[f"L{l}.issued", f"L{l}.ready", f"L{l}.epi"] for l in range(nl)], []) + ["done"]
+names = ["start", "prod"] + sum([[f"L{l}.issue0", f"L{l}.issued", f"L{l}.ready", f"L{l}.epi"] for l in range(nl)], []) + ["done"]
 t0 = t[t > 0].min()
 for g in range(groups):
     for r in (0, 1, 2, 3, 4):
