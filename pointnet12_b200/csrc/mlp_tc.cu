@@ -226,13 +226,10 @@ __device__ __forceinline__ void tc_store_max16(const unsigned (&r)[32], const fl
     for (int h = 0; h < 2; ++h) {
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float f = __uint_as_float(r[h * 16 + j]) + bias[c0 + h * 16 + j];
-            if (relu) f = fmaxf(f, 0.0f);
-            v[j] = valid ? f : -CUDART_INF_F;
-        }
-        const float m = tc_colmax16(v, lane);
+        for (int j = 0; j < 16; ++j) v[j] = valid ? __uint_as_float(r[h * 16 + j]) : -CUDART_INF_F;
         const int n = c0 + h * 16 + (lane & 15);
+        float m = tc_colmax16(v, lane) + bias[n];      // (max first: bias + ReLU are monotone, the result is bit-identical)
+        if (relu) m = fmaxf(m, 0.0f);
         if (any_valid && n < n_real) y[g * ldy + n] = m;
     }
 }
@@ -918,14 +915,12 @@ mlp_tc_kernel(const __grid_constant__ TcChain ch, const unsigned char* __restric
                             tc_store_max16(r, bias, L.relu, rc.valid, rc.row, lane, c0, L.n_real - n0, io.y + n0, io.ldy);
                             continue;
                         }
+                        // max first, bias + ReLU on the one survivor: x -> relu(fl(x + b)) is monotone, so the result is bit-identical
                         float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float f = __uint_as_float(r[j]) + bias[c0 + j];
-                            if (L.relu) f = fmaxf(f, 0.0f);
-                            v[j] = rc.valid ? f : -CUDART_INF_F;
-                        }
-                        const float mine = tc_colmax32(v, lane);
+                        for (int j = 0; j < 32; ++j) v[j] = rc.valid ? __uint_as_float(r[j]) : -CUDART_INF_F;
+                        float mine = tc_colmax32(v, lane) + bias[c0 + lane];
+                        if (L.relu) mine = fmaxf(mine, 0.0f);
                         const int n = n0 + c0 + lane;
                         if (any_valid && n < L.n_real) io.y[g * io.ldy + n] = mine;
                     }
@@ -1239,14 +1234,12 @@ mlp_tc_res_kernel(const __grid_constant__ TcChain ch, const unsigned char* __res
                         tc_store_max16(r, bias, L.relu, rc.valid, rc.row, lane, c0, L.n_real, io.y, io.ldy);
                         continue;
                     }
+                    // max first, bias + ReLU on the one survivor: x -> relu(fl(x + b)) is monotone, so the result is bit-identical
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float f = __uint_as_float(r[j]) + bias[c0 + j];
-                        if (L.relu) f = fmaxf(f, 0.0f);
-                        v[j] = rc.valid ? f : -CUDART_INF_F;
-                    }
-                    const float mine = tc_colmax32(v, lane);
+                    for (int j = 0; j < 32; ++j) v[j] = rc.valid ? __uint_as_float(r[j]) : -CUDART_INF_F;
+                    float mine = tc_colmax32(v, lane) + bias[c0 + lane];
+                    if (L.relu) mine = fmaxf(mine, 0.0f);
                     const int n = c0 + lane;
                     if (any_valid && n < L.n_real) io.y[gi * io.ldy + n] = mine;
                 }
