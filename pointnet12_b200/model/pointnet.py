@@ -79,11 +79,51 @@ class _STN(nn.Module):
             for w, b in layers[:3]:
                 h = ops.linear(h, w, b, relu=True)
             g = ops.group_max(h, N)                                               # [B,1024]
+        # fc1-bn4-relu, fc2-bn5-relu, fc3 on the [B, 1024] rows: one row tile, so each layer is a single-layer tensor-core chain
+        # sliced over its output channels (16 CTAs read the 1024 x 512 weights instead of one SIMT tile marching through them:
+        # 100 -> ~12 us per layer at B = 1); "+ iden" is added afterwards, in the reference's own order (pointnet.py:40-43)
+        slabs = self._fc_chains(layers[3:])
+        if slabs is not None:
+            for parts in slabs:
+                if len(parts) == 1:
+                    g = ops.mlp_rows_tc(parts[0][0], g)
+                else:        # fc3 of the 64 x 64 transform has 4096 outputs: column slabs of <= 1024, written side by side
+                    out = torch.empty((B, sum(c.cout for c, _ in parts)), dtype=torch.float32, device=g.device)
+                    for c, col in parts:
+                        ops.mlp_rows_tc(c, g, out=out[:, col:col + c.cout])
+                    g = out
+            return g.view(B, self.k, self.k) + torch.eye(self.k, device=g.device, dtype=g.dtype)
         g = ops.linear(g, *layers[3], relu=True)
         g = ops.linear(g, *layers[4], relu=True)
         w3, b3 = layers[5]
         b3 = b3 + torch.eye(self.k, device=b3.device, dtype=b3.dtype).flatten()   # "+ iden" as a bias
         return ops.linear(g, w3, b3, relu=False).view(B, self.k, self.k)
+
+    def _fc_chains(self, fc_layers):
+        """fc1 / fc2 / fc3 (BatchNorm folded) as single-layer tensor-core chains: per layer a list of (chain, first output
+        column); layers with more than 1024 outputs are cut into column slabs.  None in fp32 mode / when a layer does not fit.
+        Cached until the folded weights change."""
+        if ops.mlp_mode() != "bf16x3":
+            return None
+        cached = self.__dict__.get("_fc_chain_cache")
+        if cached is not None and cached[0] is fc_layers[0][0]:
+            return cached[1]
+        relus = [True, True, False]
+        out = []
+        for (w, b), relu in zip(fc_layers, relus):
+            cout, cin = w.shape
+            parts = []
+            for col in range(0, cout, 1024):
+                n = min(1024, cout - col)
+                if not ops.PackedChain.supported([(cin, n)]):
+                    out = None
+                    break
+                parts.append((ops.PackedChain([(w[col:col + n].contiguous(), b[col:col + n].contiguous(), relu)]), col))
+            if out is None:
+                break
+            out.append(parts)
+        self.__dict__["_fc_chain_cache"] = (fc_layers[0][0], out)
+        return out
 
     def forward(self, x):
         _eval_only(self)
@@ -211,8 +251,30 @@ class PointNetSeg(nn.Module):
         (w1, b1), (w2, b2), (w3, b3), (w4, b4) = self._folded.get(
             [self.conv1, self.conv2, self.conv3, self.conv4], [self.bn1, self.bn2, self.bn3, None])
         # conv1 on cat([global(1024) repeated, pointfeat(64)]): the global half is a per-cloud bias
-        cloud_bias = ops.linear(g, w1[:, :1024].contiguous(), b1, relu=False)     # [B,512]
-        h = ops.linear_cloud_bias(pointfeat, w1[:, 1024:].contiguous(), cloud_bias, relu=True).view(B * N, 512)
+        cb = self.__dict__.get("_cloud_bias_chain")
+        if cb is None or cb[0] is not w1:      # (re)packed when the folded weights change
+            chain = None
+            if ops.mlp_mode() == "bf16x3" and ops.PackedChain.supported([(1024, w1.shape[0])]):
+                chain = ops.PackedChain([(w1[:, :1024].contiguous(), b1, False)])
+            cb = self.__dict__["_cloud_bias_chain"] = (w1, chain, w1[:, 1024:].contiguous())
+        if cb[1] is not None and ops.mlp_mode() == "bf16x3":
+            cloud_bias = ops.mlp_rows_tc(cb[1], g)                                # [B,512]: one N-sliced tensor-core launch
+        else:
+            cloud_bias = ops.linear(g, w1[:, :1024].contiguous(), b1, relu=False)     # [B,512]
+        if cb[1] is not None and ops.mlp_mode() == "bf16x3" and B <= 4:
+            # per-point half of conv1 (64 -> 512) on the tensor cores; the per-cloud bias is written into the packed chain's bias
+            # table right before each cloud's launch (stream-ordered, so a graph replays it) instead of re-packing the weights
+            pc = self.__dict__.get("_point_chain")
+            if pc is None or pc[0] is not w1:
+                chain = ops.PackedChain([(cb[2], torch.zeros_like(b1), True)])
+                pc = self.__dict__["_point_chain"] = (w1, chain, chain.bias_view(0))
+            h = torch.empty((B, N, w1.shape[0]), dtype=torch.float32, device=pointfeat.device)
+            for b in range(B):
+                pc[2].copy_(cloud_bias[b])
+                ops.mlp_rows_tc(pc[1], pointfeat[b], out=h[b])
+            h = h.view(B * N, w1.shape[0])
+        else:
+            h = ops.linear_cloud_bias(pointfeat, cb[2], cloud_bias, relu=True).view(B * N, 512)
         # conv2 (512 -> 256) as a single-layer tensor-core chain, conv3 -> conv4 -> log_softmax as one more
         c2 = self._folded_c2.chain([self.conv2], [self.bn2], [True])
         tail = self._folded_tail.chain([self.conv3, self.conv4], [self.bn3, None], [True, False])

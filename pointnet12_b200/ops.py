@@ -653,6 +653,20 @@ class PackedChain:
                 nv.call("pn_mlp_pack_bf16x3", C.byref(self.desc), wp, bp, self.blob.data_ptr(), _stream())
         self._keep = (ws, bs)     # the pack kernels read them asynchronously
 
+    def bias_view(self, layer: int = 0) -> torch.Tensor:
+        """The fp32 bias of one layer inside the packed blob ([cout] view): a caller whose bias depends on the input (the
+        per-cloud bias of PointNetSeg's first head layer) writes it there before the launch instead of re-packing the chain."""
+        off, boff = 0, 0
+        n = int(self.desc.nlayers)
+        pad = lambda v: (v + 31) // 32 * 32      # noqa: E731
+        for l in range(n):
+            k_pad = pad(int(self.desc.cin[l])) if l == 0 else pad(int(self.desc.cout[l - 1]))
+            off += pad(int(self.desc.cout[l])) * k_pad * 4
+        for l in range(layer):
+            boff += pad(int(self.desc.cout[l]))
+        start = off + 4 * boff
+        return self.blob[start:start + 4 * int(self.desc.cout[layer])].view(torch.float32)
+
     @staticmethod
     def supported(dims: Sequence[Tuple[int, int]]) -> bool:
         """dims = [(cin, cout), ...]"""
