@@ -91,10 +91,12 @@ def test_fps_vs_oracle(dev, N, npoint, B):
 @pytest.mark.parametrize("cluster,threads,exchange", [(1, 1024, 0), (2, 512, 1), (4, 256, 1), (8, 128, 1), (8, 512, 1),
                                                       (16, 128, 1), (16, 256, 1), (2, 128, 2), (2, 256, 2), (4, 64, 2),
                                                       (4, 128, 2), (8, 64, 2), (8, 128, 2), (8, 256, 2), (16, 64, 2),
-                                                      (16, 128, 2), (8, 128, 3), (4, 128, 3), (16, 64, 3)])
+                                                      (16, 128, 2), (8, 128, 3), (4, 128, 3), (16, 64, 3),
+                                                      (16, 512, 0), (8, 512, 0), (2, 1024, 0), (4, 512, 0)])
 def test_fps_every_cluster_shape(dev, cluster, threads, exchange):
     """Every cluster size / CTA width / exchange mechanism (barrier.cluster, st.async + mbarrier with the per-CTA z
-    table = one 16-byte message per winner, or without it = two messages) gives the same (bit-exact) answer."""
+    table = one 16-byte message per winner, or without it = two messages; CTAs wider than 8 warps: block-level winner
+    sent with st.async unless exchange = 1) gives the same (bit-exact) answer."""
     from pointnet12_b200 import ops
 
     N, npoint, B = 8000, 128, 3
