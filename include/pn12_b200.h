@@ -244,6 +244,11 @@ typedef struct pn_mlp_desc {
 
 /* Size of the packed blob; 0 (and an error string) if the chain is not supported. */
 size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc);
+/* Warp groups (2 or 4) of the resident-weight kernel if the chain's packed weights fit in shared memory (and its layers in
+ * the tile shapes of that kernel), else 0: the chain then streams its weights through a ring for every row tile.  A caller
+ * with many row tiles can split such a chain into parts that do fit (the intermediate rows cost far less HBM traffic than
+ * re-reading the weights per tile). */
+int pn_mlp_resident_groups(const pn_mlp_desc* desc);
 /* w[l]: device pointer to [cout[l], cin[l]] row-major fp32; bias[l]: device pointer or NULL.  The arrays w and
  * bias themselves live in HOST memory.  blob: 128-byte aligned device buffer. */
 int pn_mlp_pack_bf16x3(const pn_mlp_desc* desc, const float* const* w, const float* const* bias, void* blob,

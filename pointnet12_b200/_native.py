@@ -130,6 +130,8 @@ def lib():
             fn.restype = i32
         handle.pn_mlp_blob_bytes.argtypes = [_descp]
         handle.pn_mlp_blob_bytes.restype = C.c_size_t
+        handle.pn_mlp_resident_groups.argtypes = [_descp]
+        handle.pn_mlp_resident_groups.restype = C.c_int
         handle.pn_ball_grid_bytes.argtypes = [i32, i32]
         handle.pn_ball_grid_bytes.restype = C.c_size_t
         handle.pn_three_nn_blocks_bytes.argtypes = [i32, i32]

@@ -1454,6 +1454,14 @@ static int tc_launch(const TcChain& ch, const void* blob, const TcIo& io, const 
 }  // namespace pn
 
 // ------------------------------------------------------------------------------------------------ C ABI
+PN_EXPORT int pn_mlp_resident_groups(const pn_mlp_desc* desc) {
+    pn::TcChain ch;
+    const char* why;
+    if (!pn::plan_chain(desc, &ch, &why)) return 0;
+    const int wpg = pn::tc_resident_wpg(ch);
+    return wpg ? 16 / wpg : 0;
+}
+
 PN_EXPORT size_t pn_mlp_blob_bytes(const pn_mlp_desc* desc) {
     pn::TcChain ch;
     const char* why;

@@ -181,6 +181,31 @@ class FoldedLayers:
             self._per_layer_key = self._layers
         return self._per_layer or None
 
+    def chain_resident_split(self, convs, bns, relus=None, xyz_last: bool = False):
+        """(first, rest): the chain cut after its first layer, when the whole chain is too large to keep its weights in shared
+        memory but both parts are not.  A level with many row tiles then runs as two resident-weight launches with the first
+        layer's output rows in between (HBM traffic of rows * C1 * 8 bytes) instead of re-streaming every layer's weights for
+        every 128-row tile.  None when the chain fits as a whole, a part does not fit, or the mode is 'fp32'."""
+        if ops.mlp_mode() != "bf16x3" or len(convs) < 2:
+            return None
+        layers = self.get(convs, bns)
+        if getattr(self, "_res_split", None) is None or self._res_split_key is not self._layers:
+            whole = self.chain(convs, bns, relus, xyz_last=xyz_last)
+            self._res_split = False
+            if whole is not None and not whole.resident:
+                relus_l = [True] * len(layers) if relus is None else list(relus)
+                packed = [(w, b, r) for (w, b), r in zip(layers, relus_l)]
+                if xyz_last:
+                    w0, b0, r0 = packed[0]
+                    packed[0] = (torch.cat([w0[:, 3:], w0[:, :3]], 1).contiguous(), b0, r0)
+                dims = [(w.shape[1], w.shape[0]) for w, _, _ in packed]
+                if ops.PackedChain.supported(dims[:1]) and ops.PackedChain.supported(dims[1:]):
+                    first, rest = ops.PackedChain(packed[:1]), ops.PackedChain(packed[1:])
+                    if first.resident and rest.resident:
+                        self._res_split = (first, rest)
+            self._res_split_key = self._layers
+        return self._res_split or None
+
     def chain_skip_split(self, convs, bns, relus, d1: int):
         """(skip, rest) for a feature-propagation level with skip input: the first layer's weight is cut at column d1 --
         `skip` = W[:, :d1] alone (no bias, no activation: applied to the skip features ahead of time), `rest` = the chain
@@ -219,6 +244,9 @@ class FoldedLayers:
                                ops.PackedChain([(w, b, r) for (w, b), r in zip(rest, relus[1:])]))
             self._split_key = self._layers
         return self._split or None
+
+
+RESIDENT_SPLIT_MIN_TILES = 1024     # row tiles from which re-streaming a chain's weights per tile costs more than the split
 
 
 def _eval_only(module: nn.Module) -> None:
@@ -338,21 +366,41 @@ class PointNetSetAbstractionMsg(nn.Module):
         new_xyz = ops.index_points(xyz_pm, farthest_point_sample(xyz_pm, S, start_idx))
         widths = [blk[-1].out_channels for blk in self.conv_blocks]
         out = torch.empty((B, S, sum(widths)), dtype=torch.float32, device=xyz.device)
+        # (the scales are independent, but running them on three streams was measured SLOWER -- 2.25 vs 1.90 ms at C4: their
+        # persistent chain kernels fight for the same SMs -- so they run back to back)
         col = 0
         for i, radius in enumerate(self.radius_list):
-            K = self.nsample_list[i]
-            idx = ops.ball_query(radius, K, xyz_pm, new_xyz)
-            chain = self._folded[i].chain(self.conv_blocks[i], self.bn_blocks[i]) if (K == 16 or K % 32 == 0) else None
-            if chain is not None:
-                ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=True,
-                                  out=out.view(B * S, -1)[:, col:col + widths[i]])
-                col += widths[i]
-                continue
-            grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=True)
-            rows = _mlp_rows(grouped.view(B * S * K, -1), self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]))
-            ops.group_max(rows, K, out=out.view(B * S, -1)[:, col:col + widths[i]])   # written in place: no concat
+            self._scale(i, radius, xyz_pm, pts_pm, new_xyz, out.view(B * S, -1)[:, col:col + widths[i]], B, S)
             col += widths[i]
         return new_xyz.permute(0, 2, 1), out.permute(0, 2, 1)
+
+
+def _msg_scale(self, i, radius, xyz_pm, pts_pm, new_xyz, out_cols, B, S):
+    """One scale of PointNetSetAbstractionMsg on the current stream: ball query -> chain -> max, written into its output
+    columns.  Returns the temporaries (kept alive / recorded on the caller's stream by forward)."""
+    K = self.nsample_list[i]
+    idx = ops.ball_query(radius, K, xyz_pm, new_xyz)
+    chain = self._folded[i].chain(self.conv_blocks[i], self.bn_blocks[i]) if (K == 16 or K % 32 == 0) else None
+    split = None
+    if chain is not None and K % 32 == 0 and B * S * K // 128 >= RESIDENT_SPLIT_MIN_TILES:
+        split = self._folded[i].chain_resident_split(self.conv_blocks[i], self.bn_blocks[i])
+    if split is not None:
+        # many row tiles and a chain too large for shared memory but whose halves fit: two resident-weight launches instead of
+        # streaming all weights once per tile
+        rows = ops.sa_mlp_max_tc(split[0], xyz_pm, pts_pm, new_xyz, idx, msg_order=True, out_mode=ops.OUT_ROWS)
+        part = ops.mlp_rows_tc(split[1], rows, ops.OUT_MAX32)
+        ops.group_max(part, K // 32, out=out_cols)
+        return (idx, rows, part)
+    if chain is not None:
+        ops.sa_mlp_max_tc(chain, xyz_pm, pts_pm, new_xyz, idx, msg_order=True, out=out_cols)
+        return (idx,)
+    grouped = ops.group(xyz_pm, pts_pm, new_xyz, idx, msg_order=True)
+    rows = _mlp_rows(grouped.view(B * S * K, -1), self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]))
+    ops.group_max(rows, K, out=out_cols)   # written in place: no concat
+    return (idx, grouped, rows)
+
+
+PointNetSetAbstractionMsg._scale = _msg_scale
 
 
 class PointNetFeaturePropagation(nn.Module):

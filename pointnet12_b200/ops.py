@@ -653,6 +653,12 @@ class PackedChain:
                 nv.call("pn_mlp_pack_bf16x3", C.byref(self.desc), wp, bp, self.blob.data_ptr(), _stream())
         self._keep = (ws, bs)     # the pack kernels read them asynchronously
 
+    @property
+    def resident(self) -> bool:
+        """True when the chain's weights stay resident in shared memory (pn_mlp_resident_groups): one weight load per CTA
+        instead of one per row tile."""
+        return nv.lib().pn_mlp_resident_groups(C.byref(self.desc)) > 0
+
     def bias_view(self, layer: int = 0) -> torch.Tensor:
         """The fp32 bias of one layer inside the packed blob ([cout] view): a caller whose bias depends on the input (the
         per-cloud bias of PointNetSeg's first head layer) writes it there before the launch instead of re-packing the chain."""
