@@ -25,6 +25,8 @@ and reach the graph's static buffer through a small ring of pinned staging buffe
 from __future__ import annotations
 
 import os
+import time
+from collections import deque
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -55,6 +57,12 @@ class GraphedSemSeg:
         self._graphs: Dict[Tuple, dict] = {}
         self._tensors = list(self.net.parameters()) + list(self.net.buffers())
         self._sig = None
+        # Host-output modes: the host waits for batch k before it submits batch k + depth.  Left alone, the batches in flight
+        # fall into step (they finish in bursts, the host resubmits in bursts, all of them sample at once and then all of them
+        # run their chains) and the overlap of sampling with the chains is lost: 0.46 instead of 0.42 ms per batch at C2.
+        # Submits are therefore spaced at least `pace` x the running time per batch apart, from the first batch of a run on
+        # (state per shape and mode: _sets()["pace"]; profiles/r02_summary.md section 5).
+        self.pace = float(os.environ.get("PN12_PIPE_PACE", "0.92")) if self.depth > 1 else 0.0
 
     # ---- the captured graphs bake in the device pointers of the folded / packed weights: any change of a parameter or
     # BatchNorm buffer (optimizer step, load_state_dict, .to()) must rebuild them (and must not replay freed blobs)
@@ -126,7 +134,11 @@ class GraphedSemSeg:
         entry = self._graphs.get(key)
         if entry is None:
             on_dev = points.to(dev)
-            entry = self._graphs[key] = {"sets": [self._build_set(on_dev, mode) for _ in range(self.depth)], "n": 0}
+            entry = self._graphs[key] = {"sets": [self._build_set(on_dev, mode) for _ in range(self.depth)], "n": 0,
+                                           "pace": {"done_at": deque(maxlen=8), "blocked": 0, "per_batch": None, "in_flight": 0,
+                                                    "last_submit": 0.0}}
+            for st in entry["sets"]:
+                st["pace"] = entry["pace"]
             self._sig = self._signature()         # (the warm-up folded the weights; versions are unchanged, pointers too)
         return entry
 
@@ -139,6 +151,17 @@ class GraphedSemSeg:
         pcdseg.py:75 -- 1 byte per point instead of 76)."""
         dev = points.device if points.is_cuda else torch.device("cuda", torch.cuda.current_device())
         entry = self._sets(points, dev, to_host)
+        if to_host and self.pace > 0.0:
+            pc = entry["pace"]
+            if pc["in_flight"] <= 0:
+                pc["done_at"].clear()             # the pipeline ran empty: completion times before the pause say nothing
+                pc["blocked"] = 0
+            if pc["per_batch"] is not None:
+                until = pc["last_submit"] + self.pace * pc["per_batch"]
+                while time.perf_counter() < until:
+                    pass
+            pc["last_submit"] = time.perf_counter()
+            pc["in_flight"] += 1
         seq = entry["n"]
         entry["n"] = seq + 1
         st = entry["sets"][seq % self.depth]
@@ -176,7 +199,26 @@ class GraphedSemSeg:
         if ticket.set["seq"] != ticket.seq:
             raise RuntimeError(f"the result of batch {ticket.seq} was overwritten: at most depth={self.depth} batches are in flight")
         if ticket.to_host:
+            t0 = time.perf_counter()
             ticket.done.synchronize()
+            if self.pace > 0.0:
+                # running time per batch, per window of 8 completions: if the host had to wait for any of them the GPU set the
+                # rate (followed upwards by 5 % per window at most: a hiccup must not throttle what comes after it); if it
+                # never waited, the spacing itself set the rate: shorten it
+                pc, now = ticket.set["pace"], time.perf_counter()
+                pc["in_flight"] = max(0, pc["in_flight"] - 1)
+                pc["blocked"] += now - t0 > 20e-6
+                pc["done_at"].append(now)
+                if len(pc["done_at"]) == pc["done_at"].maxlen:
+                    seen = (pc["done_at"][-1] - pc["done_at"][0]) / (len(pc["done_at"]) - 1)
+                    if pc["per_batch"] is None:
+                        pc["per_batch"] = seen
+                    elif pc["blocked"]:
+                        pc["per_batch"] = min(max(seen, 0.93 * pc["per_batch"]), 1.05 * pc["per_batch"])
+                    else:
+                        pc["per_batch"] *= 0.93
+                    pc["done_at"].clear()
+                    pc["blocked"] = 0
             return ticket.set["host_labels"] if ticket.to_host == "labels" else ticket.set["host_out"]
         torch.cuda.current_stream(ticket.set["out"].device).wait_event(ticket.done)
         return ticket.set["out"]

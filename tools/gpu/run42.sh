@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT
+timeout 600 python tools/probes/e2e_pacing.py 2>&1 | grep -v Warn

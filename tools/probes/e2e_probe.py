@@ -16,8 +16,10 @@ dev = torch.device("cuda", 0)
 net = load_pointnet("pointnet2", 19, os.path.join(ROOT, "tests", "golden", "pointnet2-inview-0.55884-0001.pth"), device=dev)
 hs = [torch.from_numpy(syn.kitti_batch(8, 24000, config=2, first=8 * i)).pin_memory() for i in range(6)]
 ds = [h.to(dev) for h in hs]
-for depth in (4, 6):
-    for slices in ("1", "2", "8"):
+DEPTHS = [int(d) for d in os.environ.get("E2E_DEPTHS", "4,6").split(",")]
+SLICES = os.environ.get("E2E_SLICES", "1,2,8").split(",")
+for depth in DEPTHS:
+    for slices in SLICES:
         os.environ["PN12_PIPE_HOST_SLICES"] = slices
         runner = GraphedSemSeg(net, depth=depth)
         for mode, batches in ((False, ds), (True, hs), ("labels", hs)):
