@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (our arm only)")
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("PN12_DEPTH", "6")), help="batches in flight (GraphedSemSeg depth)")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("PN12_DEPTH", "10")), help="batches in flight (GraphedSemSeg depth)")
     ap.add_argument("--ref-clouds", type=int, default=0, help="reference arm: clouds per step (0 = the full batch of 8, reduced "
                                                               "automatically if the run would exceed a few minutes)")
     ap.add_argument("--no-train", action="store_true", help="skip the config-C5 `train` / `dp_check` sub-records")
@@ -490,7 +490,7 @@ def run_ours(args):
                     "note": "the [B, N, 19] fp32 log-probabilities are 14.6 MB per batch and GPU; a plain pinned copy of that size runs at "
                             "~54 GB/s on one GPU of this pool's (virtualised) hosts, but all eight GPUs together saturate the host link at "
                             "~100 GB/s, which bounds this figure at N = 8 whatever the GPUs do (see e2e_labels for the evaluation loop's "
-                            "real consumer); with K = 20 steps the fill and drain of the 6-deep pipeline are inside the timed region"},
+                            "real consumer); the fill and drain of the pipeline are inside the timed region (K steps, " + f"{depth} batches in flight)"},
             "e2e_labels": None if not ms_lab else {
                 "value": points / (ms_lab * 1e-3), "unit": "points/s", "ms_per_step": ms_lab / args.steps,
                 "h2d_bytes_per_step": BATCH * 4 * NPOINTS * 4 + 4 * BATCH * 8, "d2h_bytes_per_step": BATCH * NPOINTS,

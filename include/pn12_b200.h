@@ -66,7 +66,7 @@ int pn_device_check(int* sm_count, int* cc_major, int* cc_minor);
  *                 clock64() per phase: [group][tile round % 64][tile start, producer done, then per layer: MMA issue
  *                 start, MMAs issued, accumulator ready, epilogue done; last: tile done].
  *   fps_cluster / fps_threads / fps_exchange
- *                 force the cluster size (1,2,4,8,16), threads per CTA (64..1024) and the intra-cluster exchange of
+ *                 force the cluster size (1,2,3,4,8,16), threads per CTA (64..1024) and the intra-cluster exchange of
  *                 pn_fps_f32 (1 = DSMEM store + barrier.cluster, 2 = st.async + mbarrier, 3 = the same without the per-CTA
  *                 z table, i.e. two st.async per winner instead of one); 0 = automatic. */
 typedef struct pn_launch_opts {

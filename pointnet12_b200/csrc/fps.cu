@@ -696,6 +696,9 @@ static int dispatch_async(int pts, int CL, const FpsCfg& fc, const float* xyz, i
     PN_FPS_CASE(16);
     PN_FPS_CASE(24);
     PN_FPS_CASE(32);
+    if constexpr (NW == 8) {   // 256 threads own the whole register file: 2 CTAs x 48 points hold a 24000-point cloud
+        PN_FPS_CASE(48);
+    }
 #undef PN_FPS_CASE
     set_error("pn_fps_f32: %d points per thread at %d warps exceeds the register-resident limit", pts, NW);
     return PN_ERR_UNSUPPORTED;
@@ -706,12 +709,12 @@ static int dispatch_async(int pts, int CL, const FpsCfg& fc, const float* xyz, i
 static int fps_cfg_from_opts(const pn_launch_opts* o, pn::FpsCfg* fc) {
     if (!o) return PN_OK;
     const int cluster_size = o->fps_cluster, threads = o->fps_threads, exchange = o->fps_exchange;
-    const bool cl_ok = cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 ||
+    const bool cl_ok = cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 3 || cluster_size == 4 ||
                        cluster_size == 8 || cluster_size == 16;
     const bool th_ok = threads == 0 || threads == 64 || threads == 128 || threads == 256 || threads == 512 ||
                        threads == 1024;
     PN_REQUIRE(cl_ok && th_ok && exchange >= 0 && exchange <= 3, PN_ERR_BAD_ARG,
-               "pn_launch_opts: fps_cluster in {0,1,2,4,8,16}, fps_threads in {0,64..1024}, fps_exchange in {0,1,2,3}");
+               "pn_launch_opts: fps_cluster in {0,1,2,3,4,8,16}, fps_threads in {0,64..1024}, fps_exchange in {0,1,2,3}");
     fc->cluster = cluster_size;
     fc->threads = threads;
     fc->exchange = exchange == 3 ? 2 : exchange;
@@ -824,9 +827,9 @@ static int fps_dispatch(const pn::FpsCfg& fc, const float* xyz, int64_t sB, int6
     if (use_async) {
         if (threads == 0) threads = (chunk <= 4096 && CL * 4 <= kMaxSlots) ? 128 : 256;
         const int nw = threads / 32;
-        if (threads > 256 || CL * nw > kMaxSlots || ceil_div(chunk, threads) > 32) {
+        if (threads > 256 || CL * nw > kMaxSlots || ceil_div(chunk, threads) > (threads == 256 ? 48 : 32)) {
             PN_REQUIRE(fc.exchange != 2, PN_ERR_UNSUPPORTED,
-                       "pn_fps_f32: st.async exchange needs cluster*warps <= 64, threads <= 256 and <= 32 points per thread "
+                       "pn_fps_f32: st.async exchange needs cluster*warps <= 64, threads <= 256 and <= 32 (48 at 256 threads) points per thread "
                        "(N=%d cluster=%d threads=%d)", N, CL, threads);
             use_async = false;
             threads = fc.threads;

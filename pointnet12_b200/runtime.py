@@ -47,7 +47,8 @@ class GraphedSemSeg:
     """Shape-keyed CUDA-graph cache around PointNet2SemSeg.forward with `depth` batches in flight."""
 
     RING = 4
-    FPS1_PIPELINED = (4, 256, 2)
+    FPS1_PIPELINED = (3, 256, 2)          # depth 2..7: 3 CTAs x 8 warps per cloud
+    FPS1_DEEP = (2, 256, 2)               # depth >= 8: 2 CTAs x 8 warps, 48 points per thread
 
     def __init__(self, net, warmup: int = 2, depth: int = 1):
         self.net = net.module if hasattr(net, "module") else net
@@ -79,14 +80,15 @@ class GraphedSemSeg:
 
     def _capture_options(self, st) -> dict:
         """Launch options of a captured forward.  With several batches in flight what counts is the SM time a batch occupies,
-        not the latency of one forward: level-1 sampling runs as 4 CTAs x 8 warps per cloud (half the SMs of the latency-optimal
-        8 x 4, ~35 % longer) and the level-1 ball query runs after it on the whole GPU instead of polling beside it on SMs the
-        other batches' chains can use (measured at C2, B200: profiles/r02_pipeline_sweep.md)."""
+        not the latency of one forward: level-1 sampling runs on 3 or (deep pipelines) 2 CTAs of 8 warps per cloud instead of
+        the latency-optimal 8 CTAs x 4 warps (0.73 / 1.00 ms instead of 0.48 ms, on 24 / 16 SMs instead of 64 at C2), and the
+        level-1 ball query runs after it on the whole GPU instead of polling beside it on SMs the other batches' chains can
+        use (measured at C2, B200: profiles/r02_summary.md sections 1 and 6)."""
         if self.depth == 1:
             return {"tile_counters": None}
         # (the last level is NOT cut into batch slices for the host output: the copy of batch k overlaps batch k+1 anyway, and
         # eight one-cloud launches of fp1 + head quantise badly: 188 tiles on 148 SMs each)
-        return {"tile_counters": st["counters"], "fps1_config": self.FPS1_PIPELINED, "stream_ball": False,
+        return {"tile_counters": st["counters"], "fps1_config": self.FPS1_DEEP if self.depth >= 8 else self.FPS1_PIPELINED, "stream_ball": False,
                 "host_out_slices": int(os.environ.get("PN12_PIPE_HOST_SLICES", "1"))}
 
     def _build_set(self, points: torch.Tensor, to_host: bool) -> dict:

@@ -147,9 +147,25 @@ def test_pointnet_seg_c1_golden(dev, golden):
 
 
 # ------------------------------------------------------------------------------------------------ batches in flight
-@pytest.mark.parametrize("depth", [2, 3])
+@pytest.mark.parametrize("config", [(2, 256, 2), (2, 256, 3), (3, 256, 2), (3, 256, 3)])
+def test_fps_few_wide_ctas(dev, config):
+    """The level-1 shapes of the deep pipelines: a 24000-point cloud on 2 CTAs x 8 warps (48 points per thread, the whole
+    register file) or 3 CTAs (cluster of three) -- bit-exact against the oracle like every other shape."""
+    from pointnet12_b200 import ops
+
+    B, N, npoint = 2, 24000, 256
+    pts = syn.kitti_batch(B, N, config=17)
+    st = starts([N], B, seed=23)[0]
+    want = orc.farthest_point_sample(pts.transpose(0, 2, 1)[:, :, :3], npoint, st.numpy())
+    got = ops.fps(views(cuda(pts, dev))[0], npoint, st.to(dev), config=config)
+    assert np.array_equal(got.cpu().numpy(), want)
+    ctas, _ = ops.fps_launch_info(B, N, npoint, config)
+    assert ctas == B * config[0]
+
+
+@pytest.mark.parametrize("depth", [2, 3, 8])
 def test_pipelined_runner_equals_sequential(dev, ckpt_path, depth):
-    """GraphedSemSeg(depth = 2, 3): the forwards of consecutive batches overlap on the GPU (sampling of batch k+1 beside
+    """GraphedSemSeg(depth = 2, 3, 8; from 8 on level-1 sampling runs on 2 CTAs per cloud): the forwards of consecutive batches overlap on the GPU (sampling of batch k+1 beside
     the chains of batch k, chain tiles handed out dynamically); over 6 different batches the log-probabilities are
     torch.equal to the sequential (depth 1) runner's and to the eager forward's, on the device and through the pinned
     host output."""
@@ -174,7 +190,7 @@ def test_pipelined_runner_equals_sequential(dev, ckpt_path, depth):
     got = runner.run_pipelined(hosts, to_host=True)
     assert all((not a.is_cuda) and torch.equal(a, b.cpu()) for a, b in zip(got, want)), "pinned host output"
     # a ticket whose buffer set has been reused is refused instead of returning another batch's result
-    tickets = [runner.submit(x) for x in xs[:depth + 1]]
+    tickets = [runner.submit(xs[i % len(xs)]) for i in range(depth + 1)]
     with pytest.raises(RuntimeError, match="overwritten"):
         runner.result(tickets[0])
     torch.cuda.synchronize()
