@@ -31,7 +31,7 @@ def test_argument_validation_needs_no_gpu():
     # launch options travel with the call (pn_launch_opts); a bad cluster size is refused before anything is launched
     ctas, smem = C.c_int(), C.c_size_t()
     bad = nv.LaunchOpts()
-    bad.fps_cluster = 3
+    bad.fps_cluster = 5
     assert lib.pn_fps_launch_info(8, 24000, 1024, C.byref(bad), C.byref(ctas), C.byref(smem)) == -1
     assert b"fps_cluster" in lib.pn_last_error_string()
     assert lib.pn_fps_launch_info(8, 24000, 1024, None, C.byref(ctas), C.byref(smem)) == 0 and ctas.value == 64
