@@ -197,8 +197,8 @@ int pn_three_nn_f32(const float* xyz1, int64_t aB, int64_t aN, int64_t aC, const
                     pn_stream_t stream);
 
 /* The same 3-NN search as pn_three_nn_f32 (identical idx / weight, ties included), as an exact branch-and-bound:
- * pn_three_nn_blocks_build_f32 Morton-sorts the S <= 8192 coarse points of every cloud into blocks of 32 with
- * bounding boxes (blocks: caller-owned, 16-byte aligned, pn_three_nn_blocks_bytes(B, S) bytes); in
+ * pn_three_nn_blocks_build_f32 Morton-sorts the S <= 8192 coarse points of every cloud into blocks of 16 or 32 with
+ * bounding boxes (blocks: caller-owned, opaque, 16-byte aligned, pn_three_nn_blocks_bytes(B, S) bytes); in
  * pn_three_nn_blocks_f32 one warp serves 32 fine points, visits the blocks nearest-first and stops when the nearest
  * unvisited block is farther than the warp's worst third-neighbour distance.  order (may be NULL): processing order
  * of the fine points as in pn_fp_mlp_bf16x3 -- pass the bucket order of the fine cloud (pn_ball_grid_order) so that
