@@ -466,7 +466,8 @@ def run_ours(args):
 
         torch.manual_seed(0)
         st = [s.to(dev) for s in fps_starts(torch, BATCH)]
-        per_kernel = kernel_rooflines.measure(net, dev_batches[0], st)
+        fps1_shape = (runner.FPS1_DEEP if depth >= 8 else runner.FPS1_PIPELINED) if (runner is not None and depth > 1) else None
+        per_kernel = kernel_rooflines.measure(net, dev_batches[0], st, fps1_config=fps1_shape)
         fps1 = next(k for k in per_kernel["kernels"] if k["name"] == "fps level 1")
         spread = sorted(per_step)
         precision = ops.mlp_precision()
@@ -509,10 +510,16 @@ def run_ours(args):
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)",
                          "peak_source": per_kernel["peak_source"], "algorithmic_bytes_per_launch": fps1["algorithmic_bytes"],
                          "launch_ms": fps1["launch_ms"], "share_of_step": fps1["launch_ms"] / (ms / args.steps),
-                         "timing": "CUDA events around the stand-alone launch (cold L2) right after the timed regions; inside the step "
-                                   "the kernel overlaps the previous batch's chains, so its share of the step can approach 1",
-                         "note": "coordinates and running distances are register-resident, so DRAM traffic is ~0; the figure is "
-                                 "effective bandwidth on SURVEY 8(d)'s algorithmic bytes"},
+                         "launch_shape": fps1.get("launch_shape"), "sms_occupied": fps1.get("sms_occupied"),
+                         "fp32_pipe_frac_on_its_sms": fps1.get("fp32_pipe_frac_on_its_sms"),
+                         "timing": "CUDA events around the stand-alone launch (cold L2) right after the timed regions, in the launch "
+                                   "shape the timed step uses; inside the step the kernel runs beside the other batches' kernels",
+                         "note": "coordinates and running distances are register-resident, so DRAM traffic is ~0 and the figure is an "
+                                 "effective bandwidth on SURVEY 8(d)'s algorithmic bytes.  With batches in flight the runner trades "
+                                 "latency for SM time: 2 CTAs per cloud (16 of 148 SMs, 1.0 ms) instead of the latency-optimal 8 (64 "
+                                 "SMs, 0.46 ms, frac 1.04: second fps row of roofline_all), so this fraction HALVES while the step gets "
+                                 "faster; what bounds the kernel is the FP32 pipe of the SMs it occupies (fp32_pipe_frac_on_its_sms: "
+                                 "12 lane operations per point and iteration, none fusable under the reference's rounding)"},
             "roofline_all": per_kernel,
             "clocks": clocks.summary(),
         }

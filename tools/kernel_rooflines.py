@@ -46,8 +46,10 @@ def _chain_flops(rows, convs):
     return 2.0 * rows * sum(c.weight.shape[0] * c.weight.shape[1] for c in convs)
 
 
-def measure(net, points, starts, reps=5):
-    """net: PointNet2SemSeg (eval) on the device, points [B,4,N] on the device, starts: the four FPS start vectors (device)."""
+def measure(net, points, starts, reps=5, fps1_config=None):
+    """net: PointNet2SemSeg (eval) on the device, points [B,4,N] on the device, starts: the four FPS start vectors (device).
+    fps1_config: launch shape (cluster, threads, exchange) of the level-1 sampling the measured step really uses (the runner
+    with batches in flight samples on 2-3 CTAs per cloud); the one-batch-at-a-time shape is reported next to it."""
     from pointnet12_b200 import ops
 
     n = net.module if hasattr(net, "module") else net
@@ -92,8 +94,22 @@ def measure(net, points, starts, reps=5):
         xs, fs, balls = [x0], [f0], []
         # ---- level 1: sampling, buckets, ball query, chain
         S, K, r = sa[0].npoint, sa[0].nsample, sa[0].radius
-        ms, fps1 = timed(lambda: ops.fps(x0, S, starts[0], config=ops.fps1_config()))
+        cfg1 = tuple(fps1_config) if fps1_config is not None else ops.fps1_config()
+        ms, fps1 = timed(lambda: ops.fps(x0, S, starts[0], config=cfg1))
         hbm_row("fps level 1", "fps_async_kernel (pn_fps_f32)", ms, B * S * N * 16, "fps1")
+        ctas, _ = ops.fps_launch_info(B, N, S, cfg1)
+        # the kernel keeps the cloud in registers: what bounds it is the FP32 pipe of the SMs it occupies -- 12 lane operations
+        # per point and iteration (3 sub, 3 mul, 2 add, min, compare, 2 selects), nothing fusable without changing the
+        # reference's rounding
+        out[-1].update({"launch_shape": {"cluster": cfg1[0], "threads": cfg1[1], "exchange": cfg1[2]}, "sms_occupied": ctas,
+                        "fp32_lane_ops": int(B) * S * N * 12,
+                        "fp32_pipe_frac_on_its_sms": B * S * N * 12 / (ms * 1e-3 * ctas * 128 * 1.965e9)})
+        if fps1_config is not None and tuple(fps1_config) != tuple(ops.fps1_config()):
+            ms_l, _ = timed(lambda: ops.fps(x0, S, starts[0], config=ops.fps1_config()))
+            hbm_row("fps level 1, one batch at a time (latency-optimal shape, GraphedSemSeg depth 1)", "fps_async_kernel (pn_fps_f32)",
+                    ms_l, B * S * N * 16, "fps1")
+            ctas_l, _ = ops.fps_launch_info(B, N, S, ops.fps1_config())
+            out[-1].update({"sms_occupied": ctas_l, "fp32_pipe_frac_on_its_sms": B * S * N * 12 / (ms_l * 1e-3 * ctas_l * 128 * 1.965e9)})
         x1 = ops.index_points(x0, fps1)
         ms, grid1 = timed(lambda: ops.ball_grid(x0, r))
         hbm_row("ball-query buckets level 1", "ball_grid_build_kernel (pn_ball_grid_build_f32)", ms, B * N * 16 * 2, "grid1")
