@@ -188,9 +188,9 @@ constexpr int kGqTile = 2048;   // points per staged tile in the dense phase (32
 //   phase 1 (per warp): count the candidates of the 27 neighbouring cells; at most `threshold` -> test them all,
 //                       128 per trip with the four 16-byte loads of a lane in flight together, hits -> bitmap ->
 //                       first K set bits.  More -> the centroid is left pending.
-//   phase 2 (per CTA) : the pending (dense) centroids scan the raw cloud in index order through tiles staged in
-//                       shared memory by the whole CTA (the bitmap space is reused); early exit per warp and per CTA.
-// The work of one CTA on WARPS centroids of cloud b (warp w: centroid (ax, ay, az), result row o; !valid warps only help).
+//   phase 2 (per warp): a pending (dense) centroid scans the raw cloud in index order, 128 points per trip, until its
+//                       K-th hit.
+// The work of one CTA on WARPS centroids of cloud b (warp w: centroid (ax, ay, az), result row o); the warps are independent.
 template <int WARPS>
 __device__ __forceinline__ void gq_block(const float* __restrict__ xyz, int64_t xB, int64_t xN, int64_t xC, int N, float radius2,
                                          int K, const unsigned char* __restrict__ ws, int threshold, int bm_words,
@@ -287,39 +287,34 @@ __device__ __forceinline__ void gq_block(const float* __restrict__ xyz, int64_t 
         }
     }
 
-    // ---- dense neighbourhoods: ordered scan over staged tiles, ends after a short prefix
-    if (__syncthreads_or(pending)) {
-        float4* __restrict__ tile = reinterpret_cast<float4*>(gq_smem);
+    // ---- dense neighbourhoods: the warp scans the raw cloud in index order by itself, 128 points per trip (the loads of a
+    // trip in flight together), and stops at the K-th hit -- a dense ball has it after a short prefix.  (Round 1 staged tiles
+    // of the cloud through shared memory for the whole CTA: ncu showed 51 % of all warp samples waiting at those CTA barriers,
+    // seven warps idling while one scanned.)
+    if (pending) {   // warp-uniform
         const float* __restrict__ p = xyz + (int64_t)b * xB;
-        for (int t0 = 0; t0 < N; t0 += kGqTile) {
-            const int tn = min(kGqTile, N - t0);
-            for (int i = threadIdx.x; i < tn; i += WARPS * 32) {
-                const float* r = p + (int64_t)(t0 + i) * xN;
-                const float x = r[0], y = r[xC], z = r[2 * xC];
-                tile[i] = make_float4(x, y, z, sqnorm3(x, y, z));
+        for (int c = 0; c < N && cnt < K; c += 128) {
+            float px[4], py[4], pz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(c + u * 32 + lane, N - 1);
+                const float* r = p + (int64_t)i * xN;
+                px[u] = r[0];
+                py[u] = r[xC];
+                pz[u] = r[2 * xC];
             }
-            __syncthreads();
-            if (pending) {   // warp-uniform
-                for (int c = 0; c < tn && cnt < K; c += 64) {
-                    const int i0 = c + lane, i1 = c + 32 + lane;
-                    const float4 v0 = i0 < tn ? tile[i0] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-                    const float4 v1 = i1 < tn ? tile[i1] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-                    const bool h0 = !(sqdist_expand(ax, ay, az, sa, v0.x, v0.y, v0.z, v0.w) > radius2);
-                    const bool h1 = !(sqdist_expand(ax, ay, az, sa, v1.x, v1.y, v1.z, v1.w) > radius2);
-                    const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-                    if (m0 | m1) {
-                        if (cnt == 0) first = t0 + c + (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1);
-                        const int p0 = cnt + __popc(m0 & lt_mask);
-                        if (h0 && p0 < K) o[p0] = t0 + i0;
-                        const int n0 = cnt + __popc(m0);
-                        const int p1 = n0 + __popc(m1 & lt_mask);
-                        if (h1 && p1 < K) o[p1] = t0 + i1;
-                        cnt = n0 + __popc(m1);
-                    }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = c + u * 32 + lane;
+                const bool h = i < N && !(sqdist_expand(ax, ay, az, sa, px[u], py[u], pz[u], sqnorm3(px[u], py[u], pz[u])) > radius2);
+                const unsigned m = __ballot_sync(0xffffffffu, h);
+                if (m) {
+                    if (cnt == 0) first = c + u * 32 + __ffs(m) - 1;
+                    const int pos = cnt + __popc(m & lt_mask);
+                    if (h && pos < K) o[pos] = i;
+                    cnt += __popc(m);
                 }
-                pending = cnt < K;
             }
-            if (!__syncthreads_or(pending)) break;
         }
     }
     if (valid)
@@ -413,6 +408,16 @@ ball_query_stream_kernel(const float* __restrict__ xyz, int64_t xB, int64_t xN, 
 
 }  // namespace pn
 
+// Break-even between testing C candidates of the 27 cells (hits ~ 0.155 C) and scanning ~ 33 N / (hits + 1) points of the raw
+// cloud from global memory until the K-th hit.  Measured at N = 24000, B = 8, radius 0.1 for thresholds 1280 / 2560 / 5120 / 8192 /
+// always cells: 151 / 80 / 60 / 70 / 215 us alone (a warp that scans most of the cloud by itself is a long tail), and 0.343 / 0.3415 /
+// 0.346 / 0.348 ms per batch with ten batches in flight (within 2 %): C^2 ~ 1024 N.
+static int gq_auto_threshold(int N) {
+    int t = 64;
+    while ((int64_t)t * t < (int64_t)1024 * N) t += 64;
+    return t;
+}
+
 PN_EXPORT size_t pn_ball_grid_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
     return (size_t)B * pn::grid_cloud_bytes(N);
@@ -460,13 +465,7 @@ PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, i
                "pn_ball_query_grid_f32: grid buffer holds %zu bytes, %zu needed", grid_bytes, pn_ball_grid_bytes(B, N));
     PN_REQUIRE(N <= 1048576, PN_ERR_UNSUPPORTED, "pn_ball_query_grid_f32: N=%d exceeds 1048576", N);
     PN_REQUIRE(B <= 65535, PN_ERR_UNSUPPORTED, "pn_ball_query_grid_f32: B=%d exceeds 65535", B);
-    if (threshold == 0) {
-        // break-even between testing C candidates (~7 cycles each, latency-bound) and scanning ~ 33 N / (hits + 1)
-        // staged points (~1.5 cycles each), hits ~ 0.155 C
-        int t = 64;
-        while ((int64_t)t * t < (int64_t)64 * N) t += 64;
-        threshold = t;
-    }
+    if (threshold == 0) threshold = gq_auto_threshold(N);
     const int bm_words = (int)ceil_div(ceil_div(N, 32), 32) * 32;
     cudaStream_t st = (cudaStream_t)stream;
     auto launch = [&](auto kern, int warps) -> int {
@@ -492,12 +491,6 @@ PN_EXPORT int pn_ball_query_grid_f32(const float* xyz, int64_t xB, int64_t xN, i
     if (N <= 32768) return launch(ball_query_grid_kernel<8>, 8);      // bitmaps: <= 4 KB per warp
     if (N <= 262144) return launch(ball_query_grid_kernel<4>, 4);     // <= 32 KB per warp
     return launch(ball_query_grid_kernel<1>, 1);                      // <= 128 KB
-}
-
-static int gq_auto_threshold(int N) {
-    int t = 64;
-    while ((int64_t)t * t < (int64_t)64 * N) t += 64;
-    return t;
 }
 
 PN_EXPORT int pn_ball_query_stream_f32(const float* xyz, int64_t xB, int64_t xN, int64_t xC, const uint64_t* progress, int B, int N,

@@ -369,7 +369,7 @@ def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Te
         elif (grid.B, grid.N) != (B, N) or grid.r2 != r2:
             raise ValueError("grid was built for another cloud shape or radius")
         if threshold is None:
-            threshold = {"grid": 0, "grid-cells": 2 ** 31 - 1, "grid-scan": -1}[method]
+            threshold = {"grid": int(os.environ.get("PN12_BQ_THRESHOLD", "0")), "grid-cells": 2 ** 31 - 1, "grid-scan": -1}[method]
         nv.call("pn_ball_query_grid_f32", xyz.data_ptr(), *xyz.stride(), new_xyz.data_ptr(), *new_xyz.stride(), B, N, S,
                 r2, int(nsample), grid.buf.data_ptr(), grid.nbytes, threshold, _p(done), out.data_ptr(), _stream())
     return out

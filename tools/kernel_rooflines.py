@@ -94,7 +94,8 @@ def measure(net, points, starts, reps=5, fps1_config=None):
         xs, fs, balls = [x0], [f0], []
         # ---- level 1: sampling, buckets, ball query, chain
         S, K, r = sa[0].npoint, sa[0].nsample, sa[0].radius
-        cfg1 = tuple(fps1_config) if fps1_config is not None else ops.fps1_config()
+        auto1 = tuple(ops.fps1_config() or (0, 0, 0))          # the one-batch-at-a-time shape (automatic unless PN12_FPS1 is set)
+        cfg1 = tuple(fps1_config) if fps1_config is not None else auto1
         ms, fps1 = timed(lambda: ops.fps(x0, S, starts[0], config=cfg1))
         hbm_row("fps level 1", "fps_async_kernel (pn_fps_f32)", ms, B * S * N * 16, "fps1")
         ctas, _ = ops.fps_launch_info(B, N, S, cfg1)
@@ -104,11 +105,11 @@ def measure(net, points, starts, reps=5, fps1_config=None):
         out[-1].update({"launch_shape": {"cluster": cfg1[0], "threads": cfg1[1], "exchange": cfg1[2]}, "sms_occupied": ctas,
                         "fp32_lane_ops": int(B) * S * N * 12,
                         "fp32_pipe_frac_on_its_sms": B * S * N * 12 / (ms * 1e-3 * ctas * 128 * 1.965e9)})
-        if fps1_config is not None and tuple(fps1_config) != tuple(ops.fps1_config()):
-            ms_l, _ = timed(lambda: ops.fps(x0, S, starts[0], config=ops.fps1_config()))
+        if cfg1 != auto1:
+            ms_l, _ = timed(lambda: ops.fps(x0, S, starts[0], config=auto1))
             hbm_row("fps level 1, one batch at a time (latency-optimal shape, GraphedSemSeg depth 1)", "fps_async_kernel (pn_fps_f32)",
                     ms_l, B * S * N * 16, "fps1")
-            ctas_l, _ = ops.fps_launch_info(B, N, S, ops.fps1_config())
+            ctas_l, _ = ops.fps_launch_info(B, N, S, auto1)
             out[-1].update({"sms_occupied": ctas_l, "fp32_pipe_frac_on_its_sms": B * S * N * 12 / (ms_l * 1e-3 * ctas_l * 128 * 1.965e9)})
         x1 = ops.index_points(x0, fps1)
         ms, grid1 = timed(lambda: ops.ball_grid(x0, r))

@@ -34,7 +34,7 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
 def run(depth, env, steps):
     for k in ("PN12_FPS1", "PN12_STREAM_BALL", "PN12_STREAM_BALL_CTAS", "PN12_STREAM_BALL_SHARE", "PN12_WHATIF", "PN12_NN1_BACKGROUND",
-              "PN12_RESERVE_L2", "PN12_FPS1_SORTED"):
+              "PN12_RESERVE_L2", "PN12_FPS1_SORTED", "PN12_BQ_THRESHOLD"):
         os.environ.pop(k, None)
     os.environ.update(env)
     net.module.__dict__.pop("_whatif_cache", None)
