@@ -3,6 +3,9 @@
 chamfer_batch(p1 [B,N,D], p2 [B,M,D]) = sum over b, n of min_m ||p1[b,n] - p2[b,m]||_2, divided by B (chamfer.py:32-53);
 chamfer_non_batch is the same for B == 1 without the division (:7-30).  One kernel (pn_chamfer_f32): no [B,N,M,D] cube.
 The reference's only known-answer check lives in this file (`__main__`, :55-67: 11.6073 twice); tests/ repeats it.
+
+Forward only: the result carries no grad_fn (the reference's torch expression is differentiable, but nothing in the reference
+calls this loss in training -- it is an evaluation helper); inputs that require grad are refused rather than silently detached.
 """
 import torch
 
@@ -11,6 +14,8 @@ from .. import ops
 
 
 def _chamfer_sum(p1: torch.Tensor, p2: torch.Tensor) -> torch.Tensor:
+    if torch.is_grad_enabled() and (p1.requires_grad or p2.requires_grad):
+        raise NotImplementedError("chamfer: forward only (no backward kernel); call it under torch.no_grad() or detach the clouds")
     p1, p2 = ops._cloud(p1, "p1"), ops._cloud(p2, "p2")
     assert p1.size(0) == p2.size(0) and p1.size(2) == p2.size(2)
     B, N, D = p1.shape

@@ -116,11 +116,18 @@ class ScanPreprocessor:
         return kept, count
 
     def __call__(self, batch: ScanBatch, npoints: int, train: bool, choice: Optional[torch.Tensor] = None,
-                 noise: Optional[torch.Tensor] = None, filtered=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                 noise: Optional[torch.Tensor] = None, filtered=None, check_empty: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (points [B, 4, npoints] float32, labels [B, npoints] int64).
         choice int64 [B, npoints] / noise float32 [total, 4] (row offsets[b] + i = jitter of the i-th kept point of scan
-        b): the reference's own draws, for parity; by default both are drawn on the device (jitter only when train)."""
+        b): the reference's own draws, for parity; by default both are drawn on the device (jitter only when train).
+        check_empty: a scan whose filter keeps no point raises ValueError, like the reference's np.random.choice(0, npoints)
+        (SemKITTI_Loader.py:100-106); the check reads the B kept counts back (one small synchronising copy) -- a throughput
+        loop that knows its scans may pass False, the sampling kernel then emits all-zero points with label 0 for such a scan."""
         kept, count = self.filter(batch) if filtered is None else filtered
+        if check_empty:
+            empty = (count == 0).nonzero().flatten().tolist()
+            if empty:
+                raise ValueError(f"scan(s) {empty} of the batch keep no point after the '{self.subset}' filter: nothing to sample from")
         out = torch.empty((batch.B, 4, int(npoints)), dtype=torch.float32, device=self.device)
         labels = torch.empty((batch.B, int(npoints)), dtype=torch.int64, device=self.device)
         seed = None

@@ -101,10 +101,13 @@ def test_cuda_ragged_batch_vs_oracle(dev, subset):
             wants.append(por.scan_sample(p, l, LMAP, npts, choice[i], inview=subset == "inview"))
         else:
             wants.append(None)
-    out, lab = pre(batch, npts, train=False, choice=torch.from_numpy(choice).to(dev), filtered=None)
+    if any(w is None for w in wants):
+        with pytest.raises(ValueError, match="keep no point"):   # like the reference's np.random.choice(0, npoints)
+            pre(batch, npts, train=False, choice=torch.from_numpy(choice).to(dev))
+    out, lab = pre(batch, npts, train=False, choice=torch.from_numpy(choice).to(dev), filtered=None, check_empty=False)
     for i, w in enumerate(wants):
         if w is None:
-            assert not out[i].any() and (lab[i] == 0).all()       # an empty scan yields zeros (the reference would raise)
+            assert not out[i].any() and (lab[i] == 0).all()       # unchecked: an empty scan yields zeros
         else:
             assert np.array_equal(out[i].cpu().numpy().T, w[0]) and np.array_equal(lab[i].cpu().numpy(), w[1])
 
@@ -153,6 +156,24 @@ def test_cuda_device_draws(dev):
 
 
 # ------------------------------------------------------------------------------------------------ row f-4 helpers
+@pytest.mark.gpu
+def test_cuda_empty_scan_raises(dev):
+    """A scan whose in-view filter keeps nothing (every point behind the sensor) raises like the reference's
+    np.random.choice(0, npoints) instead of being sampled as zeros (round-1 advisor finding)."""
+    from pointnet12_b200.preprocess import ScanPreprocessor
+
+    p, l = syn.raw_scan(4000, 7100)
+    behind = p.copy()
+    behind[:, 0] = -np.abs(behind[:, 0]) - 1.0
+    pre = ScanPreprocessor(LMAP, "inview", dev)
+    batch = pre.upload([p, behind], [l, l])
+    with pytest.raises(ValueError, match="keep no point"):
+        pre(batch, 512, train=False)
+    out, lab = pre(batch, 512, train=False, check_empty=False)
+    assert torch.count_nonzero(out[1]).item() == 0 and torch.count_nonzero(lab[1]).item() == 0
+    assert torch.count_nonzero(out[0]).item() > 0
+
+
 @pytest.mark.gpu
 def test_chamfer_known_answer_and_random(dev):
     """model/chamfer.py:55-67, the reference's only known-answer check: both spellings print 11.6073."""
