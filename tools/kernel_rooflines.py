@@ -171,4 +171,5 @@ if __name__ == "__main__":
     x = torch.from_numpy(syn.kitti_batch(8, 24000, config=2)).to(dev)
     torch.manual_seed(0)
     st = [torch.randint(0, m, (8,), dtype=torch.long).to(dev) for m in (24000, 1024, 256, 64)]
-    print(json.dumps(measure(net, x, st), indent=1))
+    shape = tuple(int(t) for t in sys.argv[sys.argv.index("--fps1") + 1].split(",")) if "--fps1" in sys.argv else None
+    print(json.dumps(measure(net, x, st, fps1_config=shape), indent=1))
