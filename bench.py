@@ -510,10 +510,13 @@ def run_ours(args):
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/)",
                          "peak_source": per_kernel["peak_source"], "algorithmic_bytes_per_launch": fps1["algorithmic_bytes"],
                          "launch_ms": fps1["launch_ms"], "share_of_step": fps1["launch_ms"] / (ms / args.steps),
+                         "sm_time_share_of_step": (fps1.get("sms_occupied") or 0) / 148.0 * fps1["launch_ms"] / (ms / args.steps),
                          "launch_shape": fps1.get("launch_shape"), "sms_occupied": fps1.get("sms_occupied"),
                          "fp32_pipe_frac_on_its_sms": fps1.get("fp32_pipe_frac_on_its_sms"),
                          "timing": "CUDA events around the stand-alone launch (cold L2) right after the timed regions, in the launch "
-                                   "shape the timed step uses; inside the step the kernel runs beside the other batches' kernels",
+                                   "shape the timed step uses; inside the step the kernel runs beside the other batches' kernels, so "
+                                   "share_of_step (latency / step) exceeds 1 and sm_time_share_of_step (x its share of the 148 SMs) is "
+                                   "the comparable figure; the serialised ncu list (profiles/r02_final_launches_summary.txt) shows 56 %",
                          "note": "coordinates and running distances are register-resident, so DRAM traffic is ~0 and the figure is an "
                                  "effective bandwidth on SURVEY 8(d)'s algorithmic bytes.  With batches in flight the runner trades "
                                  "latency for SM time: 2 CTAs per cloud (16 of 148 SMs, 1.0 ms) instead of the latency-optimal 8 (64 "
