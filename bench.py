@@ -511,6 +511,9 @@ def run_ours(args):
                          "peak_source": per_kernel["peak_source"], "algorithmic_bytes_per_launch": fps1["algorithmic_bytes"],
                          "launch_ms": fps1["launch_ms"], "share_of_step": fps1["launch_ms"] / (ms / args.steps),
                          "sm_time_share_of_step": (fps1.get("sms_occupied") or 0) / 148.0 * fps1["launch_ms"] / (ms / args.steps),
+                         # launches of consecutive batches overlap: one sampling launch completes per step
+                         "achieved_per_step": fps1["algorithmic_bytes"] / (ms / args.steps * 1e-3) / 1e9,
+                         "frac_per_step": fps1["algorithmic_bytes"] / (ms / args.steps * 1e-3) / 1e9 / fps1["peak"],
                          "launch_shape": fps1.get("launch_shape"), "sms_occupied": fps1.get("sms_occupied"),
                          "fp32_pipe_frac_on_its_sms": fps1.get("fp32_pipe_frac_on_its_sms"),
                          "timing": "CUDA events around the stand-alone launch (cold L2) right after the timed regions, in the launch "
