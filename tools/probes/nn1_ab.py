@@ -1,4 +1,5 @@
-"""fp1's 3-NN search alone (cold L2) on one real forward's tensors."""
+"""fp1's 3-NN search alone (cold L2) on one C2 batch: block search in bucket order vs the all-pairs scan (no order given).
+PN12_NN_BLOCK=8|16|32 forces the block size of the search."""
 import os, sys, statistics
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,4 +21,4 @@ for order in (grid, None):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); r = fp.geometry(x, x1, order=order); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    print("variant", os.environ.get("PN12_NN_VARIANT", "0"), "order" if order is not None else "no order", "us", round(statistics.median(ts) * 1e3, 1), "checksum", int(r[0].sum()))
+    print("block", os.environ.get("PN12_NN_BLOCK", "auto"), "block search" if order is not None else "all-pairs scan", "us", round(statistics.median(ts) * 1e3, 1), "checksum", int(r[0].sum()))
