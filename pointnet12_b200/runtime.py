@@ -101,6 +101,7 @@ class GraphedSemSeg:
             "sizes": sizes,
             "pinned": [torch.zeros((len(sizes), B), dtype=torch.int64).pin_memory() for _ in range(self.RING)],
             "events": [None] * self.RING,
+            "ready": torch.cuda.Event(),
             "slot": 0,
             "stream": torch.cuda.Stream(dev),
             "counters": ops.TileCounters(dev, 128) if self.depth > 1 else None,
@@ -170,24 +171,25 @@ class GraphedSemSeg:
         st["seq"] = seq
         B = points.shape[0]
         slot = st["slot"] = (st["slot"] + 1) % self.RING
-        if st["events"][slot] is not None:
-            st["events"][slot].synchronize()          # the copy that last used this staging buffer has run
+        ev = st["events"][slot]
+        if ev is not None:
+            ev.synchronize()                          # the copy that last used this staging buffer has run
+        else:
+            ev = st["events"][slot] = torch.cuda.Event()
         pinned = st["pinned"][slot]
-        for i, n in enumerate(st["sizes"]):           # the reference's draws, same generator, same order
-            pinned[i] = torch.randint(0, n, (B,), dtype=torch.long)
+        for i, n in enumerate(st["sizes"]):           # the reference's draws, same generator, same order, straight into pinned memory
+            torch.randint(0, n, (B,), dtype=torch.long, out=pinned[i])
         stream = st["stream"]
         # ordered after the caller's stream: a device input exists from here on, and whatever the caller queued to consume
         # the result this set held before (`depth` submits ago) has been issued ahead of this point
-        ready = torch.cuda.Event()
-        ready.record()
+        ready = st["ready"]                           # (events are reused: the host side of a submit is ~100 us, all of it on the
+        ready.record()                                #  critical path of a short run's pipeline fill)
         stream.wait_event(ready)
         if points.is_cuda:
             points.record_stream(stream)
         with torch.cuda.stream(stream):
             st["starts"].copy_(pinned, non_blocking=True)
-            ev = torch.cuda.Event()
             ev.record()
-            st["events"][slot] = ev
             st["x"].copy_(points, non_blocking=True)
             st["graph"].replay()
             done = torch.cuda.Event(enable_timing=self.timing)
