@@ -43,6 +43,52 @@ class Ticket:
         self.set, self.seq, self.done, self.to_host = st, seq, done, to_host
 
 
+class Pacer:
+    """Spacing of the submits of a host-output loop (GraphedSemSeg.pace).
+
+    The host waits for batch k before it submits batch k + depth; left alone, the batches in flight fall into step: they finish
+    in a burst, the host resubmits in a burst, all of them sample at once and then all of them run their chains.  Submits are
+    therefore spaced at least `factor` x the running time per batch apart.  That time is estimated over windows of `window`
+    completions: if the host had to wait for any of them the GPU set the rate (followed upwards by 5 % per window at most, so that a
+    hiccup does not throttle what comes after it); if it never waited, the spacing itself set the rate and is shortened by 7 %.
+    Pure host logic (clock and sleep are injectable: tests/test_host_cpu.py)."""
+
+    def __init__(self, factor: float, window: int = 8, clock=time.perf_counter):
+        self.factor, self.clock = float(factor), clock
+        self.done_at = deque(maxlen=window)
+        self.blocked = 0
+        self.per_batch = None          # running seconds per batch
+        self.in_flight = 0
+        self.last_submit = 0.0
+
+    def next_submit_time(self) -> float:
+        """Earliest time of the next submit (0.0: at once)."""
+        if self.in_flight <= 0:        # the pipeline ran empty: completion times before the pause say nothing
+            self.done_at.clear()
+            self.blocked = 0
+        return self.last_submit + self.factor * self.per_batch if self.per_batch is not None else 0.0
+
+    def submitted(self) -> None:
+        self.last_submit = self.clock()
+        self.in_flight += 1
+
+    def completed(self, waited: float) -> None:
+        """A result was handed out; `waited`: seconds the host spent blocked on it."""
+        self.in_flight = max(0, self.in_flight - 1)
+        self.blocked += waited > 20e-6
+        self.done_at.append(self.clock())
+        if len(self.done_at) == self.done_at.maxlen:
+            seen = (self.done_at[-1] - self.done_at[0]) / (len(self.done_at) - 1)
+            if self.per_batch is None:
+                self.per_batch = seen
+            elif self.blocked:
+                self.per_batch = min(max(seen, 0.93 * self.per_batch), 1.05 * self.per_batch)
+            else:
+                self.per_batch *= 0.93
+            self.done_at.clear()
+            self.blocked = 0
+
+
 class GraphedSemSeg:
     """Shape-keyed CUDA-graph cache around PointNet2SemSeg.forward with `depth` batches in flight."""
 
@@ -58,11 +104,7 @@ class GraphedSemSeg:
         self._graphs: Dict[Tuple, dict] = {}
         self._tensors = list(self.net.parameters()) + list(self.net.buffers())
         self._sig = None
-        # Host-output modes: the host waits for batch k before it submits batch k + depth.  Left alone, the batches in flight
-        # fall into step (they finish in bursts, the host resubmits in bursts, all of them sample at once and then all of them
-        # run their chains) and the overlap of sampling with the chains is lost: 0.46 instead of 0.42 ms per batch at C2.
-        # Submits are therefore spaced at least `pace` x the running time per batch apart, from the first batch of a run on
-        # (state per shape and mode: _sets()["pace"]; profiles/r02_summary.md section 5).
+        # host-output modes: submits are spaced >= pace x the running time per batch apart (class Pacer; state per shape and mode)
         self.pace = float(os.environ.get("PN12_PIPE_PACE", "0.92")) if self.depth > 1 else 0.0
 
     # ---- the captured graphs bake in the device pointers of the folded / packed weights: any change of a parameter or
@@ -138,8 +180,7 @@ class GraphedSemSeg:
         if entry is None:
             on_dev = points.to(dev)
             entry = self._graphs[key] = {"sets": [self._build_set(on_dev, mode) for _ in range(self.depth)], "n": 0,
-                                           "pace": {"done_at": deque(maxlen=8), "blocked": 0, "per_batch": None, "in_flight": 0,
-                                                    "last_submit": 0.0}}
+                                           "pace": Pacer(self.pace)}
             for st in entry["sets"]:
                 st["pace"] = entry["pace"]
             self._sig = self._signature()         # (the warm-up folded the weights; versions are unchanged, pointers too)
@@ -155,16 +196,10 @@ class GraphedSemSeg:
         dev = points.device if points.is_cuda else torch.device("cuda", torch.cuda.current_device())
         entry = self._sets(points, dev, to_host)
         if to_host and self.pace > 0.0:
-            pc = entry["pace"]
-            if pc["in_flight"] <= 0:
-                pc["done_at"].clear()             # the pipeline ran empty: completion times before the pause say nothing
-                pc["blocked"] = 0
-            if pc["per_batch"] is not None:
-                until = pc["last_submit"] + self.pace * pc["per_batch"]
-                while time.perf_counter() < until:
-                    pass
-            pc["last_submit"] = time.perf_counter()
-            pc["in_flight"] += 1
+            until = entry["pace"].next_submit_time()
+            while time.perf_counter() < until:
+                pass
+            entry["pace"].submitted()
         seq = entry["n"]
         entry["n"] = seq + 1
         st = entry["sets"][seq % self.depth]
@@ -206,23 +241,7 @@ class GraphedSemSeg:
             t0 = time.perf_counter()
             ticket.done.synchronize()
             if self.pace > 0.0:
-                # running time per batch, per window of 8 completions: if the host had to wait for any of them the GPU set the
-                # rate (followed upwards by 5 % per window at most: a hiccup must not throttle what comes after it); if it
-                # never waited, the spacing itself set the rate: shorten it
-                pc, now = ticket.set["pace"], time.perf_counter()
-                pc["in_flight"] = max(0, pc["in_flight"] - 1)
-                pc["blocked"] += now - t0 > 20e-6
-                pc["done_at"].append(now)
-                if len(pc["done_at"]) == pc["done_at"].maxlen:
-                    seen = (pc["done_at"][-1] - pc["done_at"][0]) / (len(pc["done_at"]) - 1)
-                    if pc["per_batch"] is None:
-                        pc["per_batch"] = seen
-                    elif pc["blocked"]:
-                        pc["per_batch"] = min(max(seen, 0.93 * pc["per_batch"]), 1.05 * pc["per_batch"])
-                    else:
-                        pc["per_batch"] *= 0.93
-                    pc["done_at"].clear()
-                    pc["blocked"] = 0
+                ticket.set["pace"].completed(time.perf_counter() - t0)
             return ticket.set["host_labels"] if ticket.to_host == "labels" else ticket.set["host_out"]
         torch.cuda.current_stream(ticket.set["out"].device).wait_event(ticket.done)
         return ticket.set["out"]

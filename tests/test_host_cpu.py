@@ -230,3 +230,54 @@ def test_training_abi_argument_validation_needs_no_gpu():
     assert lib.pn_scan_sample_f32(p, p, p, 1, p, 4, p, p, 8, None, None, C.c_float(0.0), C.c_float(0.0), None, p, p, None) == -1
     assert b"choice indices or a Philox seed" in lib.pn_last_error_string()
     assert lib.pn_chamfer_f32(p, 3, 3, 1, p, 3, 3, 1, 1, 1, 1, 9, None, p, None) == -1            # D <= 8
+
+
+def _simulate_pacer(gpu_ms, host_ms, depth, steps, factor=0.92, seed_est=None):
+    """Discrete-event model of the host-output loop: a GPU that finishes one batch every gpu_ms (FIFO, a batch cannot finish
+    before gpu_ms after its submit), a host that needs host_ms per submit and waits for batch k before submitting batch k + depth.
+    Returns (pacer, submit times)."""
+    from pointnet12_b200.runtime import Pacer
+
+    now = [0.0]
+    pacer = Pacer(factor, clock=lambda: now[0])
+    pacer.per_batch = seed_est
+    done_at, submits, pending = [], [], []
+    gpu_free = 0.0
+    for k in range(steps):
+        now[0] = max(now[0], pacer.next_submit_time())
+        pacer.submitted()                      # (as in GraphedSemSeg.submit: the spacing counts from the start of a submit's host work)
+        submits.append(now[0])
+        now[0] += host_ms * 1e-3
+        gpu_free = max(gpu_free, now[0]) + gpu_ms * 1e-3
+        done_at.append(gpu_free)
+        pending.append(k)
+        if len(pending) >= depth:
+            j = pending.pop(0)
+            t0 = now[0]
+            now[0] = max(now[0], done_at[j])
+            pacer.completed(now[0] - t0)
+    return pacer, submits
+
+
+def test_pacer_follows_the_gpu_rate_and_never_throttles():
+    """The submit pacing of the host-output loop (runtime.Pacer): with a GPU-bound loop the estimate settles on the GPU's time per
+    batch and the submits end up evenly spaced just below it; an estimate that is far too large (a hiccup, another workload
+    before) decays instead of throttling the loop; a host-bound loop is never slowed down."""
+    # GPU-bound: 0.40 ms per batch, host 0.10 ms per submit
+    pacer, submits = _simulate_pacer(gpu_ms=0.40, host_ms=0.10, depth=6, steps=400)
+    assert 0.33e-3 < pacer.per_batch < 0.42e-3                            # (it hovers just below the GPU's 0.40 ms)
+    gaps = [b - a for a, b in zip(submits[-50:-1], submits[-49:])]
+    assert min(gaps) > 0.30e-3 and max(gaps) < 0.50e-3                   # no bursts, no stalls
+    total = submits[-1] / len(submits)
+    assert total < 0.41e-3                                                # throughput = the GPU's
+    # a stale estimate five times too large decays geometrically: after 400 batches the loop runs at the GPU's rate again
+    pacer, submits = _simulate_pacer(gpu_ms=0.40, host_ms=0.10, depth=6, steps=400, seed_est=2.0e-3)
+    assert pacer.per_batch < 0.45e-3
+    tail = (submits[-1] - submits[-101]) / 100
+    assert tail < 0.41e-3
+    # host-bound (0.6 ms per submit against 0.4 ms of GPU time): pacing must not add to it
+    pacer, submits = _simulate_pacer(gpu_ms=0.40, host_ms=0.60, depth=6, steps=200)
+    assert (submits[-1] - submits[-101]) / 100 < 0.61e-3
+    # disabled estimate: first window of a fresh pacer never waits
+    from pointnet12_b200.runtime import Pacer
+    assert Pacer(0.92).next_submit_time() == 0.0
