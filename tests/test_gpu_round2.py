@@ -357,3 +357,30 @@ def test_graphed_module_cls_msg(dev, golden):
     g = golden("cls_msg_b32")
     torch.manual_seed(0)
     assert rel_err(runner(x)[0], g["logp"]) < LOGP_TOL
+
+
+@pytest.mark.parametrize("block", ["8", "32"])
+def test_three_nn_block_size_hook(dev, block):
+    """PN12_NN_BLOCK (read once per process) forces the block size of the 3-NN block search: 8 and 32 points per block give the
+    all-pairs scan's indices and weights like the default 16 (own process: the hook is latched at first use)."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, numpy as np\n"
+        "from pointnet12_b200 import ops, synthetic as syn\n"
+        "dev = torch.device('cuda', 0)\n"
+        "x = torch.from_numpy(syn.kitti_batch(2, 6000, config=6)).to(dev).permute(0, 2, 1)[:, :, :3]\n"
+        "for S in (1024, 100):\n"
+        "    st = torch.zeros((2,), dtype=torch.long, device=dev)\n"
+        "    c = ops.index_points(x, ops.fps(x, S, st)).contiguous()\n"
+        "    grid = ops.ball_grid(x, 0.1)\n"
+        "    bi, bw = ops.three_nn(x, c, order=grid, method='blocks')\n"
+        "    si, sw = ops.three_nn(x, c, method='scan')\n"
+        "    assert torch.equal(bi, si) and torch.equal(bw, sw), S\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PN12_NN_BLOCK=block, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
