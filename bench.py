@@ -466,7 +466,7 @@ def run_ours(args):
 
         torch.manual_seed(0)
         st = [s.to(dev) for s in fps_starts(torch, BATCH)]
-        fps1_shape = (runner.FPS1_DEEP if depth >= 8 else runner.FPS1_PIPELINED) if (runner is not None and depth > 1) else None
+        fps1_shape = runner.fps1_shape(NPOINTS) if runner is not None else None
         per_kernel = kernel_rooflines.measure(net, dev_batches[0], st, fps1_config=fps1_shape)
         fps1 = next(k for k in per_kernel["kernels"] if k["name"] == "fps level 1")
         spread = sorted(per_step)

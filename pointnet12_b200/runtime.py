@@ -130,8 +130,20 @@ class GraphedSemSeg:
             return {"tile_counters": None}
         # (the last level is NOT cut into batch slices for the host output: the copy of batch k overlaps batch k+1 anyway, and
         # eight one-cloud launches of fp1 + head quantise badly: 188 tiles on 148 SMs each)
-        return {"tile_counters": st["counters"], "fps1_config": self.FPS1_DEEP if self.depth >= 8 else self.FPS1_PIPELINED, "stream_ball": False,
+        return {"tile_counters": st["counters"], "fps1_config": self.fps1_shape(st["x"].shape[2]), "stream_ball": False,
                 "host_out_slices": int(os.environ.get("PN12_PIPE_HOST_SLICES", "1"))}
+
+    def fps1_shape(self, N: int) -> Optional[Tuple[int, int, int]]:
+        """Launch shape (cluster, threads, exchange) of the level-1 sampling with batches in flight: the fewest CTAs of 8 warps
+        whose threads can hold the cloud in registers (48 points each), from 2 (depth >= 8) or 3 upwards; None (the automatic,
+        latency-optimal shape) for one batch at a time and for clouds beyond 8 x 256 x 48 points."""
+        if self.depth == 1:
+            return None
+        first = self.FPS1_DEEP if self.depth >= 8 else self.FPS1_PIPELINED
+        for cluster in (2, 3, 4, 8):
+            if cluster >= first[0] and N <= cluster * 256 * 48:
+                return (cluster, 256, 2)
+        return None
 
     def _build_set(self, points: torch.Tensor, to_host: bool) -> dict:
         net, dev = self.net, points.device

@@ -384,3 +384,24 @@ def test_three_nn_block_size_hook(dev, block):
     env = dict(os.environ, PN12_NN_BLOCK=block, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_pipelined_runner_picks_a_sampling_shape_that_fits(dev, ckpt_path):
+    """With batches in flight level-1 sampling runs on as few CTAs as hold the cloud in registers (2 x 256 threads x 48 points
+    up to N = 24576); a larger cloud must move to 3, 4 or 8 CTAs (or the automatic shape) instead of failing, and the results
+    stay torch.equal to the one-batch-at-a-time runner's."""
+    from pointnet12_b200.model.utils import load_pointnet
+    from pointnet12_b200.runtime import GraphedSemSeg
+
+    net = load_pointnet("pointnet2", 19, ckpt_path, device=dev)
+    deep = GraphedSemSeg(net, depth=8)
+    assert deep.fps1_shape(24000) == (2, 256, 2) and deep.fps1_shape(30000) == (3, 256, 2) and deep.fps1_shape(40000) == (4, 256, 2)
+    assert deep.fps1_shape(98304) == (8, 256, 2) and deep.fps1_shape(120000) is None
+    assert GraphedSemSeg(net, depth=1).fps1_shape(24000) is None
+    xs = [cuda(syn.kitti_batch(2, 30000, config=2, first=2 * i), dev) for i in range(3)]
+    torch.manual_seed(5)
+    want = GraphedSemSeg(net, depth=1).run_pipelined(xs)
+    torch.manual_seed(5)
+    got = deep.run_pipelined(xs)
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    torch.cuda.synchronize()
