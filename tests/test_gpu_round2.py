@@ -398,10 +398,11 @@ def test_pipelined_runner_picks_a_sampling_shape_that_fits(dev, ckpt_path):
     assert deep.fps1_shape(24000) == (2, 256, 2) and deep.fps1_shape(30000) == (3, 256, 2) and deep.fps1_shape(40000) == (4, 256, 2)
     assert deep.fps1_shape(98304) == (8, 256, 2) and deep.fps1_shape(120000) is None
     assert GraphedSemSeg(net, depth=1).fps1_shape(24000) is None
-    xs = [cuda(syn.kitti_batch(2, 30000, config=2, first=2 * i), dev) for i in range(3)]
-    torch.manual_seed(5)
-    want = GraphedSemSeg(net, depth=1).run_pipelined(xs)
-    torch.manual_seed(5)
-    got = deep.run_pipelined(xs)
-    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    for N in (30000, 2048, 512):          # (small clouds: no bucket grid below 4096 points, fewer points than centroids at 512)
+        xs = [cuda(syn.kitti_batch(2, N, config=2, first=2 * i), dev) for i in range(3)]
+        torch.manual_seed(5)
+        want = GraphedSemSeg(net, depth=1).run_pipelined(xs)
+        torch.manual_seed(5)
+        got = deep.run_pipelined(xs)
+        assert all(torch.equal(a, b) for a, b in zip(got, want)), N
     torch.cuda.synchronize()
