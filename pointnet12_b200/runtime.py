@@ -209,8 +209,12 @@ class GraphedSemSeg:
         entry = self._sets(points, dev, to_host)
         if to_host and self.pace > 0.0:
             until = entry["pace"].next_submit_time()
-            while time.perf_counter() < until:
-                pass
+            while True:                               # sleep (the interpreter lock is free for other threads), spin the last 0.1 ms
+                rem = until - time.perf_counter()
+                if rem <= 0.0:
+                    break
+                if rem > 150e-6:
+                    time.sleep(rem - 100e-6)
             entry["pace"].submitted()
         seq = entry["n"]
         entry["n"] = seq + 1
