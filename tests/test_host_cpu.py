@@ -281,3 +281,22 @@ def test_pacer_follows_the_gpu_rate_and_never_throttles():
     # disabled estimate: first window of a fresh pacer never waits
     from pointnet12_b200.runtime import Pacer
     assert Pacer(0.92).next_submit_time() == 0.0
+
+
+def test_pipelined_sampling_shape_follows_cloud_size():
+    """Host logic of runtime.GraphedSemSeg.fps1_shape (no GPU needed): the fewest 8-warp CTAs whose threads hold the cloud in
+    registers at 48 points each, from 2 (deep pipelines) or 3 upwards; the automatic shape for one batch at a time and beyond
+    8 x 256 x 48 points."""
+    import torch
+
+    from pointnet12_b200.runtime import GraphedSemSeg
+
+    net = torch.nn.Linear(2, 2)
+    one, mid, deep = GraphedSemSeg(net, depth=1), GraphedSemSeg(net, depth=4), GraphedSemSeg(net, depth=10)
+    assert one.fps1_shape(24000) is None and one.pace == 0.0
+    assert [mid.fps1_shape(n) for n in (512, 24000, 36864, 36865, 49152, 49153, 98304, 98305)] == \
+        [(3, 256, 2), (3, 256, 2), (3, 256, 2), (4, 256, 2), (4, 256, 2), (8, 256, 2), (8, 256, 2), None]
+    assert [deep.fps1_shape(n) for n in (24000, 24576, 24577, 120000)] == [(2, 256, 2), (2, 256, 2), (3, 256, 2), None]
+    for n in (24000, 30000, 60000, 98304):            # every chosen shape respects the kernel's limits (fps.cu: <= 48 points per thread,
+        c, t, _ = deep.fps1_shape(n)                  # cluster x warps <= 64 slots)
+        assert -(-(-(-n // c)) // t) <= 48 and c * (t // 32) <= 64
