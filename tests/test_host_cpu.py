@@ -300,3 +300,42 @@ def test_pipelined_sampling_shape_follows_cloud_size():
     for n in (24000, 30000, 60000, 98304):            # every chosen shape respects the kernel's limits (fps.cu: <= 48 points per thread,
         c, t, _ = deep.fps1_shape(n)                  # cluster x warps <= 64 slots)
         assert -(-(-(-n // c)) // t) <= 48 and c * (t // 32) <= 64
+
+
+def test_runner_weight_change_detection_cheap_and_exact_for_inplace_updates(monkeypatch):
+    """runtime.GraphedSemSeg._check_weights (host logic, no GPU): in a tight pipelined loop only the version counters are summed,
+    and every in-place update (optimizer step, load_state_dict, copy_) is still caught at the next submit; a pointer change is
+    caught by the full check after a pause; one batch at a time the full signature is taken on every call."""
+    import time
+
+    import torch
+
+    from pointnet12_b200.runtime import GraphedSemSeg
+
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda dev=None: None)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4))
+    r = GraphedSemSeg(net, depth=4)
+    r._check_weights(None)
+    r._graphs = {"shape": "graphs"}
+    for _ in range(5):
+        r._check_weights(None)
+    assert r._graphs                                            # nothing changed: graphs kept
+    with torch.no_grad():
+        net[0].weight.mul_(2.0)                                 # in-place: version bump, same pointer
+    r._check_weights(None)
+    assert not r._graphs
+    r._graphs = {"shape": "graphs"}
+    net.load_state_dict({k: v.clone() + 1 for k, v in net.state_dict().items()})
+    r._check_weights(None)
+    assert not r._graphs
+    r._graphs = {"shape": "graphs"}
+    net[0].weight.data = net[0].weight.data.clone()             # pointer change without a version bump of the old storage
+    time.sleep(0.003)                                           # ... seen by the full check that follows any pause
+    r._check_weights(None)
+    assert not r._graphs
+    one = GraphedSemSeg(net, depth=1)
+    one._check_weights(None)
+    one._graphs = {"shape": "graphs"}
+    net[1].running_mean.data = net[1].running_mean.data.clone()
+    one._check_weights(None)                                    # depth 1: always the full signature
+    assert not one._graphs
